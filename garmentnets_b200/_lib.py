@@ -1,0 +1,90 @@
+"""ctypes binding of the C-ABI declared in ``include/garmentnets_b200.h``.
+
+The prototypes are parsed from the header itself, so the Python argtypes can never drift from the C
+declarations.  There is NO fallback: if the shared library is missing (not built) every call raises
+``GarmentNetsB200Error`` -- the product path never routes around the CUDA extension.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from typing import Dict, List, Tuple
+
+_ROOT = os.path.dirname(os.path.abspath(__file__))
+HEADER_PATH = os.path.join(os.path.dirname(_ROOT), "include", "garmentnets_b200.h")
+LIB_PATH = os.path.join(_ROOT, "lib", "libgarmentnets_b200.so")
+
+
+class GarmentNetsB200Error(RuntimeError):
+    """Raised for every non-zero status of the native library (and when it cannot be loaded)."""
+
+
+_CTYPES = {
+    "int32_t": ctypes.c_int32,
+    "int64_t": ctypes.c_int64,
+    "float": ctypes.c_float,
+    "double": ctypes.c_double,
+}
+
+
+def parse_header(path: str = HEADER_PATH) -> Dict[str, Tuple[object, List[object]]]:
+    """Return {name: (restype, [argtypes])} for every ``gnb_*`` prototype in the header."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos: Dict[str, Tuple[object, List[object]]] = {}
+    for m in re.finditer(r"(const\s+char\s*\*|int32_t|int64_t)\s+(gnb_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        restype = ctypes.c_char_p if "char" in ret else _CTYPES[ret]
+        argtypes: List[object] = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "*" in a:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    base = a.replace("const ", "").split(" ")[0]
+                    argtypes.append(_CTYPES[base])
+        protos[name] = (restype, argtypes)
+    return protos
+
+
+_lib = None
+_protos = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library once; fail loudly when it is absent."""
+    global _lib, _protos
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GarmentNetsB200Error(
+            f"native library not built: {LIB_PATH} (run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C garmentnets_b200/csrc`); there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    _protos = parse_header()
+    for name, (restype, argtypes) in _protos.items():
+        fn = getattr(lib, name)  # AttributeError if the header declares something the library lacks
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().gnb_last_error().decode("utf-8", "replace")
+
+
+def call(name: str, *args):
+    """Invoke ``name`` and raise on a negative status.  Pointers are passed as ints (``tensor.data_ptr()``)."""
+    lib = load()
+    fn = getattr(lib, name)
+    conv = [None if (a is None) else a for a in args]
+    status = fn(*conv)
+    if isinstance(status, int) and status < 0:
+        msg = last_error()
+        if status == -4:
+            raise ValueError(f"{name}: {msg}")  # mirrors skimage's ValueError (ref predict.py:188)
+        raise GarmentNetsB200Error(f"{name} failed with status {status}: {msg}")
+    return status

@@ -1,0 +1,86 @@
+"""Per-point MLP -- mirror of the reference's ``components/mlp.py`` (``MLP`` :9-20, ``PointBatchNorm1D`` :3-7).
+
+``MLP(channels, batch_norm)`` returns an ``nn.Sequential`` of ``Sequential(Linear, ReLU, PointBatchNorm1D)`` blocks
+with the reference's ``state_dict`` keys (``{l}.0.weight``, ``{l}.2.running_mean`` ...).  In eval mode every block is
+ONE launch of ``gnb_linear`` (GEMM + bias + ReLU + folded BatchNorm affine).  Training-mode forward is outside the
+inference hot path and is refused rather than silently served by another backend.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from .. import ops
+
+
+class FoldedBatchNorm:
+    """Mixin: eval-mode BatchNorm as a per-channel affine that the preceding GEMM's epilogue applies."""
+
+    def folded_affine(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Eval-mode BN as y = x*scale + shift (scale = gamma/sqrt(var+eps), shift = beta - mean*scale); cached
+        until a parameter or running statistic changes."""
+        key = (self.running_mean._version, self.running_var._version, self.weight._version, self.bias._version,
+               self.running_mean.data_ptr(), self.weight.data_ptr())
+        cached = getattr(self, "_gnb_fold", None)
+        if cached is None or cached[0] != key:
+            with torch.no_grad():
+                scale = self.weight * torch.rsqrt(self.running_var + self.eps)
+                shift = self.bias - self.running_mean * scale
+            cached = (key, scale.contiguous(), shift.contiguous())
+            self._gnb_fold = cached
+        return cached[1], cached[2]
+
+
+
+class PointBatchNorm1D(FoldedBatchNorm, nn.BatchNorm1d):
+    """BatchNorm1d over the last dim of an arbitrarily shaped [..., C] tensor (ref components/mlp.py:3-7)."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise NotImplementedError("garmentnets_b200 implements the inference hot path only (BatchNorm in eval mode)")
+        # Stand-alone BN never occurs on the hot path (it is fused into the Linear block); kept for API completeness
+        # as the same fused kernel with an identity weight.
+        scale, shift = self.folded_affine()
+        flat = x.reshape(-1, x.shape[-1])
+        eye = torch.eye(flat.shape[1], dtype=torch.float32, device=flat.device)
+        return ops.linear(flat, eye, None, False, scale, shift).view(x.shape)
+
+
+class _Block(nn.Sequential):
+    """Linear -> ReLU -> (PointBatchNorm1D): one fused kernel launch."""
+
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None,
+                rows_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.training:
+            raise NotImplementedError("garmentnets_b200 implements the inference hot path only (eval mode)")
+        lin = self[0]
+        scale = shift = None
+        if len(self) > 2:
+            scale, shift = self[2].folded_affine()
+        lead = x.shape[:-1]
+        flat = x.reshape(-1, x.shape[-1]) if x.dim() != 2 else x
+        y = ops.linear(flat, lin.weight, lin.bias, True, scale, shift, out=out, rows_dev=rows_dev)
+        return y if x.dim() == 2 else y.view(*lead, y.shape[-1])
+
+
+class FusedMLP(nn.Sequential):
+    def forward(self, x: torch.Tensor, rows_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+        for block in self:
+            x = block(x, rows_dev=rows_dev)
+        return x
+
+    @property
+    def channels(self):
+        return [self[0][0].in_features] + [b[0].out_features for b in self]
+
+
+def MLP(channels, batch_norm=True):
+    blocks = []
+    for cin, cout in zip(channels[:-1], channels[1:]):
+        parts = [nn.Linear(cin, cout), nn.ReLU()]
+        if batch_norm:
+            parts.append(PointBatchNorm1D(cout))
+        blocks.append(_Block(*parts))
+    return FusedMLP(*blocks)

@@ -1,0 +1,204 @@
+"""PointNet++ modules -- mirror of the reference's ``components/pointnet2.py`` (``SAModule`` :11-33,
+``GlobalSAModule`` :36-52, ``FPModule`` :61-76, module-level ``MLP`` :55-59) on the sm_100a kernels.
+
+Same constructor signatures, attribute paths (``.conv.local_nn`` etc., hence the same checkpoint keys) and
+``forward`` contracts.  The third-party ops the reference calls (torch_cluster ``fps`` / ``radius`` / ``knn``, PyG
+``PointConv`` / ``knn_interpolate`` / ``global_max_pool``) are replaced by ``gnb_*`` entry points; their functional
+forms are also exported here under the PyG names for the import shims.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import ops
+from .mlp import FoldedBatchNorm, FusedMLP, _Block
+
+
+# ------------------------------------------------------------------------------------------------ functional
+class CloudIndex:
+    """CSR description of a PyG-style flat batch: device ``ptr`` plus its host copy (sizes the launches)."""
+
+    def __init__(self, ptr: torch.Tensor, ptr_host: np.ndarray):
+        self.ptr = ptr
+        self.ptr_host = np.asarray(ptr_host, dtype=np.int64)
+
+    @property
+    def num_graphs(self) -> int:
+        return len(self.ptr_host) - 1
+
+    @property
+    def max_n(self) -> int:
+        return int(np.diff(self.ptr_host).max()) if self.num_graphs else 0
+
+    @property
+    def total(self) -> int:
+        return int(self.ptr_host[-1])
+
+    @staticmethod
+    def from_batch(batch: torch.Tensor) -> "CloudIndex":
+        # one device->host read, like the reference's `int(batch.max()) + 1` inside torch_cluster
+        ptr = ops.batch_to_ptr(batch)
+        return CloudIndex(ptr, ptr.cpu().numpy())
+
+    @staticmethod
+    def uniform(B: int, n: int, device) -> "CloudIndex":
+        host = np.arange(B + 1, dtype=np.int64) * n
+        return CloudIndex(torch.from_numpy(host).to(device), host)
+
+    def subsample(self, ratio: float) -> "CloudIndex":
+        counts = ops.fps_counts(self.ptr_host, ratio)
+        host = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        return CloudIndex(torch.from_numpy(host).to(self.ptr.device), host)
+
+    def batch_vector(self) -> torch.Tensor:
+        counts = torch.from_numpy(np.diff(self.ptr_host)).to(self.ptr.device)
+        return torch.repeat_interleave(torch.arange(self.num_graphs, device=self.ptr.device), counts)
+
+
+def fps(pos, batch=None, ratio=0.5, random_start=True, *, index: Optional[CloudIndex] = None,
+        start: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """torch_geometric.nn.fps (ref components/pointnet2.py:26).  ``start`` injects the per-cloud start index."""
+    if index is None:
+        index = CloudIndex.from_batch(batch if batch is not None else pos.new_zeros(pos.shape[0], dtype=torch.int64))
+    sub = index.subsample(ratio)
+    if start is None and random_start:
+        sizes = np.maximum(np.diff(index.ptr_host), 1)
+        start = torch.from_numpy((np.random.randint(0, 2 ** 31, size=len(sizes)) % sizes).astype(np.int64)).to(pos.device)
+    return ops.fps(pos, index.ptr, sub.ptr, index.max_n, sub.total, start)
+
+
+def radius(x, y, r, batch_x=None, batch_y=None, max_num_neighbors=32, *, index_x=None, index_y=None):
+    """torch_geometric.nn.radius (ref components/pointnet2.py:28-29): returns stacked [row(y idx), col(x idx)]."""
+    index_x = index_x or CloudIndex.from_batch(batch_x if batch_x is not None else x.new_zeros(len(x), dtype=torch.int64))
+    index_y = index_y or CloudIndex.from_batch(batch_y if batch_y is not None else y.new_zeros(len(y), dtype=torch.int64))
+    nbr, cnt = ops.ball_query(x, y, index_x.ptr, index_y.ptr, r, max_num_neighbors)
+    row, col = ops.radius_pairs(nbr, cnt)
+    return torch.stack([row, col], dim=0)
+
+
+def global_max_pool(x, batch, size=None, *, index: Optional[CloudIndex] = None):
+    """torch_geometric.nn.global_max_pool (ref components/pointnet2.py:49); ``batch`` is sorted."""
+    index = index or CloudIndex.from_batch(batch)
+    return ops.segment_max(x, index.ptr)
+
+
+def knn_interpolate(x, pos_x, pos_y, batch_x=None, batch_y=None, k=3, num_workers=1, *, index_x=None, index_y=None,
+                    out: Optional[torch.Tensor] = None):
+    """torch_geometric.nn.knn_interpolate (ref components/pointnet2.py:72)."""
+    index_x = index_x or CloudIndex.from_batch(batch_x if batch_x is not None else pos_x.new_zeros(len(pos_x), dtype=torch.int64))
+    index_y = index_y or CloudIndex.from_batch(batch_y if batch_y is not None else pos_y.new_zeros(len(pos_y), dtype=torch.int64))
+    idx, d2 = ops.knn(pos_x, pos_y, index_x.ptr, index_y.ptr, k)
+    if out is None:
+        out = torch.empty((pos_y.shape[0], x.shape[1]), dtype=torch.float32, device=x.device)
+    ops.knn_interpolate_into(x, idx, d2, out)
+    return out
+
+
+class PointConv(nn.Module):
+    """torch_geometric.nn.PointConv (1.7.2) restricted to what the reference uses: ``local_nn``, max aggregation,
+    ``add_self_loops=True``, no ``global_nn``."""
+
+    def __init__(self, local_nn=None, global_nn=None, add_self_loops=True, **kwargs):
+        super().__init__()
+        if global_nn is not None:
+            raise NotImplementedError("PointConv(global_nn=...) is not used on the GarmentNets hot path")
+        self.local_nn = local_nn
+        self.global_nn = None
+        self.add_self_loops = add_self_loops
+
+    def forward_grouped(self, x, pos_x, pos_y, nbr, cnt) -> torch.Tensor:
+        """Edge set = ball query U self loop (see include/garmentnets_b200.h, N4); message MLP; segment max."""
+        if not self.add_self_loops:
+            raise NotImplementedError("PointConv(add_self_loops=False) is not used on the GarmentNets hot path")
+        M, K = nbr.shape
+        eoffs = ops.pointconv_edges(nbr, cnt)
+        cin = 0 if x is None else x.shape[1]
+        rows = M * (K + 1)  # worst case; kernels stop at the device-side edge total eoffs[M]
+        edge = torch.empty((rows, cin + 3), dtype=torch.float32, device=pos_x.device)
+        ops.pointconv_gather(x, pos_x, pos_y, nbr, cnt, eoffs, edge)
+        total = eoffs[M:]
+        h = edge
+        for block in self.local_nn:
+            h = block(h, rows_dev=total)
+        return ops.segment_max(h, eoffs)
+
+    def forward(self, x, pos, edge_index):
+        raise NotImplementedError(
+            "PointConv.forward(edge_index) is served through SAModule (ball query and grouping are fused); "
+            "call SAModule.forward or PointConv.forward_grouped")
+
+
+# ------------------------------------------------------------------------------------------------ modules
+class SAModule(nn.Module):
+    """Local set abstraction: FPS -> ball query (<=64) -> PointConv (ref components/pointnet2.py:11-33)."""
+
+    def __init__(self, ratio, r, nn):
+        super().__init__()
+        self.ratio = ratio
+        self.r = r
+        self.conv = PointConv(nn)
+        self.random_start = True  # the reference's fps default; set False (or pass fps_start) for determinism
+
+    def forward(self, x, pos, batch, *, index: Optional[CloudIndex] = None, fps_start: Optional[torch.Tensor] = None,
+                return_index: bool = False):
+        index = index or CloudIndex.from_batch(batch)
+        sub = index.subsample(self.ratio)
+        idx = fps(pos, None, self.ratio, self.random_start, index=index, start=fps_start)
+        pos_y = pos[idx]
+        nbr, cnt = ops.ball_query(pos, pos_y, index.ptr, sub.ptr, self.r, 64)
+        out = self.conv.forward_grouped(x, pos, pos_y, nbr, cnt)
+        batch_y = batch[idx] if batch is not None else sub.batch_vector()
+        if return_index:
+            return out, pos_y, batch_y, sub, {"idx": idx, "nbr": nbr, "cnt": cnt}
+        return out, pos_y, batch_y
+
+
+class GlobalSAModule(nn.Module):
+    """Global set abstraction (ref components/pointnet2.py:36-52)."""
+
+    def __init__(self, nn):
+        super().__init__()
+        self.nn = nn
+
+    def forward(self, x, pos, batch, *, index: Optional[CloudIndex] = None):
+        index = index or CloudIndex.from_batch(batch)
+        h = self.nn(torch.cat([x, pos], dim=1))
+        out = ops.segment_max(h, index.ptr)
+        B = out.shape[0]
+        return out, pos.new_zeros((B, 3)), torch.arange(B, device=pos.device)
+
+
+def MLP(channels, batch_norm=True):
+    """The unused module-level helper of the reference (components/pointnet2.py:55-59): Linear, ReLU, BatchNorm1d."""
+    blocks = [_Block(nn.Linear(channels[i - 1], channels[i]), nn.ReLU(), _PlainBN(channels[i]))
+              for i in range(1, len(channels))]
+    return FusedMLP(*blocks)
+
+
+class _PlainBN(FoldedBatchNorm, nn.BatchNorm1d):
+    pass
+
+
+class FPModule(nn.Module):
+    """Feature propagation: kNN inverse-distance interpolation + skip concat + MLP (ref components/pointnet2.py:61-76)."""
+
+    def __init__(self, k, nn):
+        super().__init__()
+        self.k = k
+        self.nn = nn
+
+    def forward(self, x, pos, batch, x_skip, pos_skip, batch_skip, *, index: Optional[CloudIndex] = None,
+                index_skip: Optional[CloudIndex] = None):
+        index = index or CloudIndex.from_batch(batch)
+        index_skip = index_skip or CloudIndex.from_batch(batch_skip)
+        c = x.shape[1]
+        cs = 0 if x_skip is None else x_skip.shape[1]
+        buf = torch.empty((pos_skip.shape[0], c + cs), dtype=torch.float32, device=x.device)
+        knn_interpolate(x, pos, pos_skip, k=self.k, index_x=index, index_y=index_skip, out=buf)
+        if x_skip is not None:
+            buf[:, c:] = x_skip
+        return self.nn(buf), pos_skip, batch_skip

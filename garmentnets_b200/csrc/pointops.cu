@@ -1,0 +1,444 @@
+// Point-set kernels of the PointNet++ stage: farthest point sampling, ball query, kNN + inverse-distance
+// interpolation, PointConv grouping and segment max.  These are integer/index-heavy, latency- or L2-bound
+// kernels: coalesced loads, shared-memory staging of a cloud, warp-ballot compaction and warp-shuffle reductions.
+//
+// Reference semantics restated (file:line relative to the reference repository):
+//   components/pointnet2.py:26      fps(pos, batch, ratio)                       -> gnb_fps
+//   components/pointnet2.py:28-29   radius(pos, pos[idx], r, ..., 64)           -> gnb_ball_query
+//   components/pointnet2.py:72      knn_interpolate(x, pos, pos_skip, ..., k)   -> gnb_knn + gnb_knn_interpolate
+//   components/pointnet2.py:30-31   PointConv(nn)(x, (pos, pos[idx]), edges)    -> gnb_pointconv_* + gnb_segment_max
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace gnb {
+
+// ------------------------------------------------------------------------------------------------
+// Farthest point sampling: one CTA per cloud, strictly sequential rounds.  The cloud lives in shared
+// memory (centroid broadcast) and, on the fast path, each thread keeps its PPT points and their running
+// min-distances in registers.  One barrier per round: per-warp (dist,index) keys are double-buffered and
+// every warp redundantly reduces the 32 partials.
+// key = dist_bits << 32 | (0xFFFFFFFF - index): max key == max distance, ties -> lowest index.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+template <int T, int PPT>
+__global__ void __launch_bounds__(T, 1)
+fps_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, const int64_t* __restrict__ start,
+           const int64_t* __restrict__ out_ptr, int64_t* __restrict__ out, int stride) {
+    extern __shared__ float sm[];
+    __shared__ unsigned long long wbest[2][32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t p0 = ptr[b];
+    const int n = (int)(ptr[b + 1] - p0);
+    const int64_t o0 = out_ptr[b];
+    const int m = (int)(out_ptr[b + 1] - o0);
+    if (n <= 0 || m <= 0) return;
+    float* sx = sm;
+    float* sy = sm + stride;
+    float* sz = sm + 2 * stride;
+    float* sd = sm + 3 * stride;  // only used on the generic path (PPT == 0)
+    for (int i = tid; i < n; i += T) {
+        sx[i] = pos[(p0 + i) * 3 + 0];
+        sy[i] = pos[(p0 + i) * 3 + 1];
+        sz[i] = pos[(p0 + i) * 3 + 2];
+        if (PPT == 0) sd[i] = CUDART_INF_F;
+    }
+    int cur = 0;
+    if (start != nullptr) {
+        long long s = start[b];
+        cur = (int)(s < 0 ? 0 : (s >= n ? n - 1 : s));
+    }
+    if (tid == 0) out[o0] = p0 + cur;
+    __syncthreads();
+
+    float px[PPT > 0 ? PPT : 1], py[PPT > 0 ? PPT : 1], pz[PPT > 0 ? PPT : 1], pd[PPT > 0 ? PPT : 1];
+    if (PPT > 0) {
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            int i = tid + j * T;
+            bool ok = i < n;
+            px[j] = ok ? sx[i] : 0.f;
+            py[j] = ok ? sy[i] : 0.f;
+            pz[j] = ok ? sz[i] : 0.f;
+            pd[j] = ok ? CUDART_INF_F : -1.f;  // -1 never wins (real distances are >= 0)
+        }
+    }
+    constexpr int NW = T / 32;
+    for (int s = 1; s < m; ++s) {
+        const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
+        unsigned long long best = 0ull;
+        if (PPT > 0) {
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+                float d = sqdist_nofma(px[j], py[j], pz[j], cx, cy, cz);
+                float dm = fminf(pd[j], d);
+                pd[j] = dm;
+                if (dm >= 0.f) {
+                    unsigned long long key = ((unsigned long long)__float_as_uint(dm) << 32) |
+                                             (unsigned long long)(0xFFFFFFFFu - (unsigned)(tid + j * T));
+                    best = key > best ? key : best;
+                }
+            }
+        } else {
+            for (int i = tid; i < n; i += T) {
+                float d = sqdist_nofma(sx[i], sy[i], sz[i], cx, cy, cz);
+                float dm = fminf(sd[i], d);
+                sd[i] = dm;
+                unsigned long long key = ((unsigned long long)__float_as_uint(dm) << 32) |
+                                         (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+                best = key > best ? key : best;
+            }
+        }
+        best = warp_max_u64(best);
+        if (lane == 0) wbest[s & 1][warp] = best;
+        __syncthreads();
+        unsigned long long k2 = lane < NW ? wbest[s & 1][lane] : 0ull;
+        k2 = warp_max_u64(k2);
+        cur = (int)(0xFFFFFFFFu - (unsigned)(k2 & 0xFFFFFFFFull));
+        if (tid == 0) out[o0 + s] = p0 + cur;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ball query: one warp per query, the cloud is scanned in index order 32 points at a time; a ballot +
+// popc prefix gives each in-radius point its ordered slot, so the first K hits in index order are kept.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_segment(const int64_t* __restrict__ ptr, int B, int64_t i) {
+    int lo = 0, hi = B;  // ptr[lo] <= i < ptr[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (ptr[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+ball_query_kernel(const float* __restrict__ x, const float* __restrict__ y, const int64_t* __restrict__ ptr_x,
+                  const int64_t* __restrict__ ptr_y, int B, int64_t sumM, float r2, int K,
+                  int64_t* __restrict__ nbr, int32_t* __restrict__ cnt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= sumM) return;
+    const int b = find_segment(ptr_y, B, q);
+    const float qx = y[q * 3], qy = y[q * 3 + 1], qz = y[q * 3 + 2];
+    const int64_t s = ptr_x[b], e = ptr_x[b + 1];
+    int count = 0;
+    for (int64_t base = s; base < e && count < K; base += 32) {
+        const int64_t j = base + lane;
+        bool hit = false;
+        if (j < e) {
+            float d = sqdist_nofma(x[j * 3], x[j * 3 + 1], x[j * 3 + 2], qx, qy, qz);
+            hit = d < r2;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        const int rank = __popc(mask & ((1u << lane) - 1u));
+        if (hit && count + rank < K) nbr[q * K + count + rank] = j;
+        count += __popc(mask);
+    }
+    count = count < K ? count : K;
+    for (int t = count + lane; t < K; t += 32) nbr[q * K + t] = -1;
+    if (lane == 0) cnt[q] = count;
+}
+
+__global__ void radius_pairs_kernel(const int64_t* __restrict__ nbr, const int32_t* __restrict__ cnt,
+                                    const int64_t* __restrict__ offs, int64_t sumM, int K,
+                                    int64_t* __restrict__ row, int64_t* __restrict__ col) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= sumM) return;
+    const int c = cnt[q];
+    const int64_t o = offs[q];
+    for (int t = lane; t < c; t += 32) {
+        row[o + t] = q;
+        col[o + t] = nbr[q * K + t];
+    }
+}
+
+// single-CTA exclusive scan (inputs here are at most a few 10^4 per-centroid counts)
+__global__ void __launch_bounds__(1024)
+scan_kernel(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+    __shared__ long long wsum[32];
+    __shared__ long long chunk_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long carry = 0;  // identical in every thread
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + tid;
+        const long long v = i < n ? (long long)in[i] : 0ll;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const long long w = wsum[lane];
+            long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                long long t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            wsum[lane] = wi - w;  // exclusive offset of each warp
+            if (lane == 31) chunk_total = wi;
+        }
+        __syncthreads();
+        if (i < n) out[i] = carry + wsum[warp] + incl - v;
+        carry += chunk_total;
+        __syncthreads();  // wsum / chunk_total are rewritten by the next chunk
+    }
+    if (tid == 0) out[n] = carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kNN: one thread per query, sorted insertion over the cloud in index order (strict <, so equal
+// distances keep the lower index first).
+// ------------------------------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(128)
+knn_kernel(const float* __restrict__ x, const float* __restrict__ y, const int64_t* __restrict__ ptr_x,
+           const int64_t* __restrict__ ptr_y, int B, int64_t Ny, int k, int64_t* __restrict__ idx,
+           float* __restrict__ d2out) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Ny) return;
+    const int b = find_segment(ptr_y, B, q);
+    const float qx = y[q * 3], qy = y[q * 3 + 1], qz = y[q * 3 + 2];
+    float bd[KT];
+    int64_t bi[KT];
+#pragma unroll
+    for (int p = 0; p < KT; ++p) { bd[p] = CUDART_INF_F; bi[p] = -1; }
+    const int64_t s = ptr_x[b], e = ptr_x[b + 1];
+    for (int64_t j = s; j < e; ++j) {
+        float cd = sqdist_nofma(__ldg(x + j * 3), __ldg(x + j * 3 + 1), __ldg(x + j * 3 + 2), qx, qy, qz);
+        if (cd < bd[KT - 1] || KT > k) {
+            int64_t cj = j;
+            bool ins = false;
+#pragma unroll
+            for (int p = 0; p < KT; ++p) {
+                if (p < k) {
+                    bool sw = ins || (cd < bd[p]);
+                    if (sw) {
+                        float td = bd[p]; bd[p] = cd; cd = td;
+                        int64_t tj = bi[p]; bi[p] = cj; cj = tj;
+                        ins = true;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < KT; ++p) {
+        if (p < k) {
+            idx[q * k + p] = bi[p];
+            d2out[q * k + p] = bd[p];
+        }
+    }
+}
+
+// inverse-distance interpolation, one warp per output row, channels across lanes.
+__global__ void __launch_bounds__(256)
+knn_interp_kernel(const float* __restrict__ feat, int64_t ldf, const int64_t* __restrict__ idx,
+                  const float* __restrict__ d2, int64_t Ny, int k, int C, float* __restrict__ out, int64_t ldo) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= Ny) return;
+    for (int c = lane; c < C; c += 32) {
+        float num = 0.f, den = 0.f;
+        bool first = true;
+        for (int p = 0; p < k; ++p) {
+            const int64_t j = idx[q * k + p];
+            if (j < 0) continue;
+            const float w = __fdiv_rn(1.0f, fmaxf(d2[q * k + p], 1e-16f));
+            const float t = __fmul_rn(feat[j * ldf + c], w);
+            if (first) { num = t; den = w; first = false; }
+            else { num = __fadd_rn(num, t); den = __fadd_rn(den, w); }
+        }
+        out[q * ldo + c] = first ? 0.f : __fdiv_rn(num, den);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PointConv grouping
+// ------------------------------------------------------------------------------------------------
+__global__ void pointconv_edge_count_kernel(const int64_t* __restrict__ nbr, const int32_t* __restrict__ cnt,
+                                            int64_t sumM, int K, int32_t* __restrict__ ecnt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sumM) return;
+    const int c = cnt[i];
+    bool has_self = false;
+    for (int t = 0; t < c; ++t) has_self |= (nbr[i * K + t] == i);
+    ecnt[i] = c + (has_self ? 0 : 1);
+}
+
+__global__ void __launch_bounds__(256)
+pointconv_gather_kernel(const float* __restrict__ xf, int64_t ldx, int Cin, const float* __restrict__ pos_x,
+                        const float* __restrict__ pos_y, const int64_t* __restrict__ nbr,
+                        const int32_t* __restrict__ cnt, const int64_t* __restrict__ eoffs, int64_t sumM, int K,
+                        float* __restrict__ edge, int64_t lde) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= sumM) return;
+    const int c = cnt[i];
+    const int64_t e0 = eoffs[i];
+    const int ne = (int)(eoffs[i + 1] - e0);
+    const float cx = pos_y[i * 3], cy = pos_y[i * 3 + 1], cz = pos_y[i * 3 + 2];
+    int w = 0;  // write cursor (edges with j == i are skipped and appended once at the end)
+    for (int t = 0; t <= c; ++t) {
+        int64_t j;
+        if (t < c) {
+            j = nbr[i * K + t];
+            if (j == i) continue;
+        } else {
+            j = i;  // the self loop added by PointConv (flat point index i, see header)
+        }
+        if (w >= ne) break;
+        float* dst = edge + (e0 + w) * lde;
+        for (int ch = lane; ch < Cin; ch += 32) dst[ch] = xf[j * ldx + ch];
+        if (lane < 3) {
+            const float pc = lane == 0 ? cx : (lane == 1 ? cy : cz);
+            dst[Cin + lane] = __fsub_rn(pos_x[j * 3 + lane], pc);
+        }
+        ++w;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+segment_max_kernel(const float* __restrict__ rows, int64_t ldr, const int64_t* __restrict__ offs, int64_t nseg,
+                   int C, float* __restrict__ out, int64_t ldo) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= nseg) return;
+    const int64_t e0 = offs[i], e1 = offs[i + 1];
+    for (int c = lane; c < C; c += 32) {
+        float m = 0.f;
+        if (e1 > e0) {
+            m = rows[e0 * ldr + c];
+            for (int64_t e = e0 + 1; e < e1; ++e) m = fmaxf(m, rows[e * ldr + c]);
+        }
+        out[i * ldo + c] = m;
+    }
+}
+
+}  // namespace gnb
+
+using namespace gnb;
+
+extern "C" {
+
+int32_t gnb_fps(const float* pos, const int64_t* ptr, int32_t B, const int64_t* start, const int64_t* out_ptr,
+                int64_t* out, int32_t max_n_host, void* stream) {
+    GNB_REQUIRE(pos && ptr && out_ptr && out, "gnb_fps: null pointer");
+    GNB_REQUIRE(B >= 0 && max_n_host >= 0, "gnb_fps: negative size");
+    if (B == 0 || max_n_host == 0) return GNB_OK;
+    cudaStream_t st = as_stream(stream);
+    const int stride = (max_n_host + 31) & ~31;
+    if (max_n_host <= 512 * 8) {
+        const size_t smem = (size_t)3 * stride * sizeof(float);
+        GNB_CUDA(cudaFuncSetAttribute(fps_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fps_kernel<512, 8><<<B, 512, smem, st>>>(pos, ptr, start, out_ptr, out, stride);
+    } else if (max_n_host <= 1024 * 8) {
+        const size_t smem = (size_t)3 * stride * sizeof(float);
+        GNB_CUDA(cudaFuncSetAttribute(fps_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fps_kernel<1024, 8><<<B, 1024, smem, st>>>(pos, ptr, start, out_ptr, out, stride);
+    } else {
+        const size_t smem = (size_t)4 * stride * sizeof(float);
+        if (smem > 227 * 1024) {
+            set_error("gnb_fps: cloud of %d points exceeds the shared-memory envelope (14336)", max_n_host);
+            return GNB_ERR_UNSUPPORTED;
+        }
+        GNB_CUDA(cudaFuncSetAttribute(fps_kernel<1024, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fps_kernel<1024, 0><<<B, 1024, smem, st>>>(pos, ptr, start, out_ptr, out, stride);
+    }
+    return check_launch("gnb_fps");
+}
+
+int32_t gnb_ball_query(const float* x, const float* y, const int64_t* ptr_x, const int64_t* ptr_y, int32_t B,
+                       int64_t sumM, double r, int32_t K, int64_t* nbr, int32_t* cnt, void* stream) {
+    GNB_REQUIRE(x && y && ptr_x && ptr_y && nbr && cnt, "gnb_ball_query: null pointer");
+    GNB_REQUIRE(B > 0 && K > 0 && sumM >= 0, "gnb_ball_query: bad size");
+    if (sumM == 0) return GNB_OK;
+    const float r2 = (float)(r * r);  // torch_cluster passes r*r (double) into a float kernel argument
+    const int wpb = 8;
+    ball_query_kernel<<<(unsigned)ceil_div<int64_t>(sumM, wpb), wpb * 32, 0, as_stream(stream)>>>(
+        x, y, ptr_x, ptr_y, B, sumM, r2, K, nbr, cnt);
+    return check_launch("gnb_ball_query");
+}
+
+int32_t gnb_radius_pairs(const int64_t* nbr, const int32_t* cnt, const int64_t* offs, int64_t sumM, int32_t K,
+                         int64_t* row, int64_t* col, void* stream) {
+    GNB_REQUIRE(nbr && cnt && offs && row && col, "gnb_radius_pairs: null pointer");
+    if (sumM == 0) return GNB_OK;
+    radius_pairs_kernel<<<(unsigned)ceil_div<int64_t>(sumM, 8), 256, 0, as_stream(stream)>>>(nbr, cnt, offs, sumM, K,
+                                                                                          row, col);
+    return check_launch("gnb_radius_pairs");
+}
+
+int32_t gnb_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* out, void* stream) {
+    GNB_REQUIRE(in && out, "gnb_exclusive_scan_i32: null pointer");
+    GNB_REQUIRE(n >= 0 && n <= (1ll << 24), "gnb_exclusive_scan_i32: n out of range");
+    scan_kernel<<<1, 1024, 0, as_stream(stream)>>>(in, n, out);
+    return check_launch("gnb_exclusive_scan_i32");
+}
+
+int32_t gnb_knn(const float* x, const float* y, const int64_t* ptr_x, const int64_t* ptr_y, int32_t B, int64_t Ny,
+                int32_t k, int64_t* idx, float* d2, void* stream) {
+    GNB_REQUIRE(x && y && ptr_x && ptr_y && idx && d2, "gnb_knn: null pointer");
+    GNB_REQUIRE(k >= 1 && k <= 16, "gnb_knn: k=%d outside [1,16]", k);
+    if (Ny == 0) return GNB_OK;
+    const unsigned grid = (unsigned)ceil_div<int64_t>(Ny, 128);
+    cudaStream_t st = as_stream(stream);
+    if (k == 1) knn_kernel<1><<<grid, 128, 0, st>>>(x, y, ptr_x, ptr_y, B, Ny, k, idx, d2);
+    else if (k <= 3) knn_kernel<3><<<grid, 128, 0, st>>>(x, y, ptr_x, ptr_y, B, Ny, k, idx, d2);
+    else if (k <= 8) knn_kernel<8><<<grid, 128, 0, st>>>(x, y, ptr_x, ptr_y, B, Ny, k, idx, d2);
+    else knn_kernel<16><<<grid, 128, 0, st>>>(x, y, ptr_x, ptr_y, B, Ny, k, idx, d2);
+    return check_launch("gnb_knn");
+}
+
+int32_t gnb_knn_interpolate(const float* feat, int64_t ldf, const int64_t* idx, const float* d2, int64_t Ny,
+                            int32_t k, int32_t C, float* out, int64_t ldo, void* stream) {
+    GNB_REQUIRE(feat && idx && d2 && out, "gnb_knn_interpolate: null pointer");
+    if (Ny == 0 || C == 0) return GNB_OK;
+    knn_interp_kernel<<<(unsigned)ceil_div<int64_t>(Ny, 8), 256, 0, as_stream(stream)>>>(feat, ldf, idx, d2, Ny, k, C,
+                                                                                      out, ldo);
+    return check_launch("gnb_knn_interpolate");
+}
+
+int32_t gnb_pointconv_edge_count(const int64_t* nbr, const int32_t* cnt, int64_t sumM, int32_t K, int32_t* ecnt,
+                                 void* stream) {
+    GNB_REQUIRE(nbr && cnt && ecnt, "gnb_pointconv_edge_count: null pointer");
+    if (sumM == 0) return GNB_OK;
+    pointconv_edge_count_kernel<<<(unsigned)ceil_div<int64_t>(sumM, 256), 256, 0, as_stream(stream)>>>(nbr, cnt, sumM,
+                                                                                                    K, ecnt);
+    return check_launch("gnb_pointconv_edge_count");
+}
+
+int32_t gnb_pointconv_gather(const float* x_feat, int64_t ldx, int32_t Cin, const float* pos_x, const float* pos_y,
+                             const int64_t* nbr, const int32_t* cnt, const int64_t* eoffs, int64_t sumM, int32_t K,
+                             float* edge, int64_t lde, void* stream) {
+    GNB_REQUIRE(pos_x && pos_y && nbr && cnt && eoffs && edge, "gnb_pointconv_gather: null pointer");
+    GNB_REQUIRE(Cin == 0 || x_feat, "gnb_pointconv_gather: null features");
+    GNB_REQUIRE(lde >= Cin + 3, "gnb_pointconv_gather: lde too small");
+    if (sumM == 0) return GNB_OK;
+    pointconv_gather_kernel<<<(unsigned)ceil_div<int64_t>(sumM, 8), 256, 0, as_stream(stream)>>>(
+        x_feat, ldx, Cin, pos_x, pos_y, nbr, cnt, eoffs, sumM, K, edge, lde);
+    return check_launch("gnb_pointconv_gather");
+}
+
+int32_t gnb_segment_max(const float* rows, int64_t ldr, const int64_t* offs, int64_t nseg, int32_t C, float* out,
+                        int64_t ldo, void* stream) {
+    GNB_REQUIRE(rows && offs && out, "gnb_segment_max: null pointer");
+    if (nseg == 0 || C == 0) return GNB_OK;
+    segment_max_kernel<<<(unsigned)ceil_div<int64_t>(nseg, 8), 256, 0, as_stream(stream)>>>(rows, ldr, offs, nseg, C,
+                                                                                         out, ldo);
+    return check_launch("gnb_segment_max");
+}
+
+}  // extern "C"

@@ -1,0 +1,306 @@
+"""Tensor-level wrappers around the C-ABI (``include/garmentnets_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every computation below is a call into
+``libgarmentnets_b200.so``.  Inputs must live on a CUDA device -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+REDUCE = {"sum": 0, "add": 0, "mean": 1, "max": 2, "min": 3}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype: torch.dtype, name: str, contiguous: bool = True) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.GarmentNetsB200Error(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.GarmentNetsB200Error(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        t = t.contiguous()
+    return t
+
+
+def _rows(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+    """2-D fp32 tensor whose last dim is contiguous; returns (tensor, row stride)."""
+    t = _req(t, torch.float32, name, contiguous=False)
+    if t.dim() != 2:
+        raise _lib.GarmentNetsB200Error(f"{name}: expected a 2-D tensor")
+    if t.shape[1] > 1 and t.stride(1) != 1 or t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+    return t, int(ld)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------- point ops
+def batch_to_ptr(batch: torch.Tensor, num_graphs: Optional[int] = None) -> torch.Tensor:
+    """Sorted PyG batch vector -> CSR offsets i64[B+1] (plumbing; one bincount + cumsum)."""
+    if num_graphs is None:
+        num_graphs = int(batch.max().item()) + 1 if batch.numel() else 0
+    counts = torch.bincount(batch, minlength=num_graphs)
+    ptr = torch.zeros(num_graphs + 1, dtype=torch.int64, device=batch.device)
+    torch.cumsum(counts, 0, out=ptr[1:])
+    return ptr
+
+
+def fps_counts(ptr_host, ratio: float):
+    """m_b = ceil(fp32(n_b) * fp32(ratio)) (torch_cluster 1.5.9 `fps`: deg.float() * ratio, ceil)."""
+    import numpy as np
+    n = np.diff(np.asarray(ptr_host, dtype=np.int64)).astype(np.float32)
+    return np.ceil(n * np.float32(ratio)).astype(np.int64)
+
+
+def fps(pos: torch.Tensor, ptr: torch.Tensor, out_ptr: torch.Tensor, max_n: int, total_m: int,
+        start: Optional[torch.Tensor] = None) -> torch.Tensor:
+    pos = _req(pos, torch.float32, "pos")
+    ptr = _req(ptr, torch.int64, "ptr")
+    out_ptr = _req(out_ptr, torch.int64, "out_ptr")
+    if start is not None:
+        start = _req(start, torch.int64, "start")
+    out = torch.empty(total_m, dtype=torch.int64, device=pos.device)
+    _lib.call("gnb_fps", pos.data_ptr(), ptr.data_ptr(), ptr.numel() - 1, _ptr(start), out_ptr.data_ptr(),
+              out.data_ptr(), int(max_n), _stream())
+    return out
+
+
+def ball_query(x: torch.Tensor, y: torch.Tensor, ptr_x: torch.Tensor, ptr_y: torch.Tensor, r: float,
+               K: int = 64) -> Tuple[torch.Tensor, torch.Tensor]:
+    x = _req(x, torch.float32, "x")
+    y = _req(y, torch.float32, "y")
+    M = y.shape[0]
+    nbr = torch.empty((M, K), dtype=torch.int64, device=x.device)
+    cnt = torch.empty((M,), dtype=torch.int32, device=x.device)
+    _lib.call("gnb_ball_query", x.data_ptr(), y.data_ptr(), ptr_x.data_ptr(), ptr_y.data_ptr(), ptr_x.numel() - 1, M,
+              float(r), int(K), nbr.data_ptr(), cnt.data_ptr(), _stream())
+    return nbr, cnt
+
+
+def exclusive_scan(cnt: torch.Tensor) -> torch.Tensor:
+    cnt = _req(cnt, torch.int32, "cnt")
+    out = torch.empty(cnt.numel() + 1, dtype=torch.int64, device=cnt.device)
+    _lib.call("gnb_exclusive_scan_i32", cnt.data_ptr(), cnt.numel(), out.data_ptr(), _stream())
+    return out
+
+
+def radius_pairs(nbr: torch.Tensor, cnt: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(row, col) pair list in torch_cluster.radius order; sizes the output with one host read of the total."""
+    offs = exclusive_scan(cnt)
+    total = int(offs[-1].item())
+    row = torch.empty(total, dtype=torch.int64, device=nbr.device)
+    col = torch.empty(total, dtype=torch.int64, device=nbr.device)
+    _lib.call("gnb_radius_pairs", nbr.data_ptr(), cnt.data_ptr(), offs.data_ptr(), nbr.shape[0], nbr.shape[1],
+              row.data_ptr(), col.data_ptr(), _stream())
+    return row, col
+
+
+def knn(x: torch.Tensor, y: torch.Tensor, ptr_x: torch.Tensor, ptr_y: torch.Tensor, k: int):
+    x = _req(x, torch.float32, "x")
+    y = _req(y, torch.float32, "y")
+    Ny = y.shape[0]
+    idx = torch.empty((Ny, k), dtype=torch.int64, device=x.device)
+    d2 = torch.empty((Ny, k), dtype=torch.float32, device=x.device)
+    _lib.call("gnb_knn", x.data_ptr(), y.data_ptr(), ptr_x.data_ptr(), ptr_y.data_ptr(), ptr_x.numel() - 1, Ny, int(k),
+              idx.data_ptr(), d2.data_ptr(), _stream())
+    return idx, d2
+
+
+def knn_interpolate_into(feat: torch.Tensor, idx: torch.Tensor, d2: torch.Tensor, out: torch.Tensor) -> None:
+    """out[:, :C] = inverse-distance interpolation; ``out`` may be wider (the concat buffer)."""
+    feat, ldf = _rows(feat, "feat")
+    assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1
+    _lib.call("gnb_knn_interpolate", feat.data_ptr(), ldf, idx.data_ptr(), d2.data_ptr(), idx.shape[0], idx.shape[1],
+              feat.shape[1], out.data_ptr(), out.stride(0), _stream())
+
+
+def pointconv_edges(nbr: torch.Tensor, cnt: torch.Tensor) -> torch.Tensor:
+    """CSR offsets i64[M+1] of the PointConv edge set (ball query U self loop)."""
+    ecnt = torch.empty_like(cnt)
+    _lib.call("gnb_pointconv_edge_count", nbr.data_ptr(), cnt.data_ptr(), nbr.shape[0], nbr.shape[1], ecnt.data_ptr(),
+              _stream())
+    return exclusive_scan(ecnt)
+
+
+def pointconv_gather(x_feat: Optional[torch.Tensor], pos_x: torch.Tensor, pos_y: torch.Tensor, nbr: torch.Tensor,
+                     cnt: torch.Tensor, eoffs: torch.Tensor, edge: torch.Tensor) -> None:
+    if x_feat is not None:
+        x_feat, ldx = _rows(x_feat, "x_feat")
+        cin = x_feat.shape[1]
+    else:
+        ldx, cin = 0, 0
+    _lib.call("gnb_pointconv_gather", _ptr(x_feat), ldx, cin, pos_x.data_ptr(), pos_y.data_ptr(), nbr.data_ptr(),
+              cnt.data_ptr(), eoffs.data_ptr(), nbr.shape[0], nbr.shape[1], edge.data_ptr(), edge.stride(0), _stream())
+
+
+def segment_max(rows: torch.Tensor, offs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows, ldr = _rows(rows, "rows")
+    nseg = offs.numel() - 1
+    if out is None:
+        out = torch.empty((nseg, rows.shape[1]), dtype=torch.float32, device=rows.device)
+    _lib.call("gnb_segment_max", rows.data_ptr(), ldr, offs.data_ptr(), nseg, rows.shape[1], out.data_ptr(),
+              out.stride(0), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- dense ops
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+           bn_scale: Optional[torch.Tensor] = None, bn_shift: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None, rows_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    x, ldx = _rows(x, "x")
+    weight = _req(weight, torch.float32, "weight")
+    R, K = x.shape
+    N = weight.shape[0]
+    assert weight.shape[1] == K, f"weight {tuple(weight.shape)} vs input K={K}"
+    if out is None:
+        out = torch.empty((R, N), dtype=torch.float32, device=x.device)
+    assert out.stride(1) == 1 or N == 1
+    _lib.call("gnb_linear", x.data_ptr(), R, K, ldx, weight.data_ptr(), _ptr(bias), N, int(relu), _ptr(bn_scale),
+              _ptr(bn_shift), out.data_ptr(), out.stride(0), _ptr(rows_dev), _stream())
+    return out
+
+
+def nocs_head(logits: torch.Tensor, bins: int):
+    logits = _req(logits, torch.float32, "logits")
+    R = logits.shape[0]
+    dev = logits.device
+    b = torch.empty((R, 3), dtype=torch.int64, device=dev)
+    conf = torch.empty((R, 3), dtype=torch.float32, device=dev)
+    nocs = torch.empty((R, 3), dtype=torch.float32, device=dev)
+    _lib.call("gnb_nocs_head", logits.data_ptr(), R, int(bins), b.data_ptr(), conf.data_ptr(), nocs.data_ptr(), _stream())
+    return b, conf, nocs
+
+
+def scatter_reduce(src: torch.Tensor, index: torch.Tensor, dim_size: int, reduce: str,
+                   channels_last: bool = True) -> torch.Tensor:
+    """``src`` logical [C, N] (any strides), ``index`` i64[N] -> logical [C, dim_size].
+
+    With ``channels_last`` the result is physically [dim_size, C] (returned as a transposed view), which is what
+    lets the unchanged reference caller hand a channels-last volume straight to the UNet
+    (ref networks/conv_implicit_wnf.py:92-99)."""
+    src = _req(src, torch.float32, "src", contiguous=False)
+    index = _req(index, torch.int64, "index")
+    C, N = src.shape
+    dev = src.device
+    scratch = torch.empty(max(dim_size, 1), dtype=torch.int32, device=dev)
+    if channels_last:
+        phys = torch.empty((dim_size, C), dtype=torch.float32, device=dev)
+        out_sc, out_sm = 1, C
+    else:
+        phys = torch.empty((C, dim_size), dtype=torch.float32, device=dev)
+        out_sc, out_sm = dim_size, 1
+    _lib.call("gnb_scatter_reduce", src.data_ptr(), src.stride(0), src.stride(1), index.data_ptr(), N, C, dim_size,
+              REDUCE[reduce], phys.data_ptr(), out_sc, out_sm, scratch.data_ptr(), _stream())
+    return phys.t() if channels_last else phys
+
+
+def aggregator_features(feat, nocs, sim_points, conf, batch, G: int):
+    feat, ldf = _rows(feat, "feat")
+    nocs = _req(nocs, torch.float32, "nocs")
+    sim_points = _req(sim_points, torch.float32, "sim_points")
+    conf = _req(conf, torch.float32, "conf")
+    batch = _req(batch, torch.int64, "batch")
+    N, Cf = feat.shape
+    out = torch.empty((N, Cf + 9), dtype=torch.float32, device=feat.device)
+    flat = torch.empty((N,), dtype=torch.int64, device=feat.device)
+    _lib.call("gnb_aggregator_features", feat.data_ptr(), ldf, Cf, nocs.data_ptr(), sim_points.data_ptr(),
+              conf.data_ptr(), batch.data_ptr(), N, int(G), flat.data_ptr(), out.data_ptr(), out.stride(0), _stream())
+    return out, flat
+
+
+# ---------------------------------------------------------------------------------------------- UNet ops (NDHWC)
+def groupnorm_stats(x: torch.Tensor, groups: int, eps: float, gamma, beta):
+    """x contiguous [B,D,H,W,C] -> (scale, shift) f32[B,C] with GN(x) = x*scale + shift."""
+    B, C = x.shape[0], x.shape[-1]
+    voxels = x.numel() // (B * C)
+    scale = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    shift = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    ws = torch.empty((B * groups * 2,), dtype=torch.float64, device=x.device)
+    _lib.call("gnb_groupnorm_stats", x.data_ptr(), B, voxels, C, int(groups), float(eps), _ptr(gamma), _ptr(beta),
+              scale.data_ptr(), shift.data_ptr(), ws.data_ptr(), _stream())
+    return scale, shift
+
+
+def conv3d_k3(x: torch.Tensor, wt: torch.Tensor, scale=None, shift=None, relu: bool = True) -> torch.Tensor:
+    """x [B,D,H,W,Cin] contiguous, wt [27,Cin,Cout] -> [B,D,H,W,Cout]."""
+    B, D, H, W, Cin = x.shape
+    Cout = wt.shape[2]
+    y = torch.empty((B, D, H, W, Cout), dtype=torch.float32, device=x.device)
+    _lib.call("gnb_conv3d_k3", x.data_ptr(), B, D, H, W, Cin, _ptr(scale), _ptr(shift), wt.data_ptr(), Cout, int(relu),
+              y.data_ptr(), _stream())
+    return y
+
+
+def maxpool3d_2(x: torch.Tensor) -> torch.Tensor:
+    B, D, H, W, C = x.shape
+    y = torch.empty((B, D // 2, H // 2, W // 2, C), dtype=torch.float32, device=x.device)
+    _lib.call("gnb_maxpool3d_2", x.data_ptr(), B, D, H, W, C, y.data_ptr(), _stream())
+    return y
+
+
+def upsample_concat(skip: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    B, D, H, W, Cs = skip.shape
+    _, Dx, Hx, Wx, Cx = x.shape
+    y = torch.empty((B, D, H, W, Cs + Cx), dtype=torch.float32, device=x.device)
+    _lib.call("gnb_upsample_concat", skip.data_ptr(), Cs, x.data_ptr(), Cx, B, D, H, W, Dx, Hx, Wx, y.data_ptr(),
+              _stream())
+    return y
+
+
+def to_channels_last(x: torch.Tensor) -> torch.Tensor:
+    """logical NCDHW tensor with arbitrary strides -> contiguous [B,D,H,W,C] (no copy if it already is one)."""
+    x = _req(x, torch.float32, "x", contiguous=False)
+    B, C, D, H, W = x.shape
+    y_view = x.permute(0, 2, 3, 4, 1)
+    if y_view.is_contiguous():
+        return y_view
+    y = torch.empty((B, D, H, W, C), dtype=torch.float32, device=x.device)
+    sb, sc, sd, sh, sw = x.stride()
+    _lib.call("gnb_to_channels_last", x.data_ptr(), sb, sc, sd, sh, sw, B, C, D, H, W, y.data_ptr(), _stream())
+    return y
+
+
+# ---------------------------------------------------------------------------------------------- decoder ops
+def trilinear_sample(vol: torch.Tensor, q: torch.Tensor, flip: bool = False, bn_scale=None, bn_shift=None,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """vol [B,D,H,W,C] contiguous, q [B,M,3] -> [B*M, C]."""
+    B, D, H, W, C = vol.shape
+    q = _req(q, torch.float32, "q")
+    M = q.shape[1]
+    if out is None:
+        out = torch.empty((B * M, C), dtype=torch.float32, device=vol.device)
+    post = bn_scale is not None
+    _lib.call("gnb_trilinear_sample", vol.data_ptr(), B, D, H, W, C, q.data_ptr(), M, int(flip), int(post),
+              _ptr(bn_scale), _ptr(bn_shift), out.data_ptr(), out.stride(0), _stream())
+    return out
+
+
+def trilinear_sample_grid(vol: torch.Tensor, b: int, Q: int, m0: int, M: int, bn_scale=None, bn_shift=None,
+                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _, D, H, W, C = vol.shape
+    if out is None:
+        out = torch.empty((M, C), dtype=torch.float32, device=vol.device)
+    post = bn_scale is not None
+    _lib.call("gnb_trilinear_sample_grid", vol.data_ptr(), int(b), D, H, W, C, int(Q), int(m0), int(M), int(post),
+              _ptr(bn_scale), _ptr(bn_shift), out.data_ptr(), out.stride(0), _stream())
+    return out
+
+
+def gaussian_gradient_magnitude(v: torch.Tensor, sigma: float) -> torch.Tensor:
+    v = _req(v, torch.float32, "v")
+    D, H, W = v.shape
+    out = torch.empty_like(v)
+    tmp = torch.empty((2,) + tuple(v.shape), dtype=torch.float32, device=v.device)
+    _lib.call("gnb_gaussian_gradient_magnitude", v.data_ptr(), D, H, W, float(sigma), out.data_ptr(), tmp.data_ptr(),
+              _stream())
+    return out

@@ -1,0 +1,209 @@
+/*
+ * garmentnets_b200 -- C-ABI of the B200-native GarmentNets dense-inference hot path.
+ *
+ * One `extern "C"` entry point per native component the reference reaches through
+ * third-party binaries.  Every pointer is a DEVICE pointer unless
+ * the parameter name ends in `_host`; sizes are plain integers; `stream` is a
+ * `cudaStream_t` passed as `void*` (NULL = legacy default stream).  The caller owns and
+ * allocates every buffer (outputs worst-case sized).  All calls are asynchronous on
+ * `stream` unless stated otherwise.  Return value: 0 = OK, negative = `gnb_status`;
+ * `gnb_last_error()` returns a thread-local human-readable message.
+ *
+ * No torch types appear here: the Python host side (garmentnets_b200/_lib.py) binds this
+ * file with ctypes and passes `tensor.data_ptr()` / `torch.cuda.current_stream().cuda_stream`.
+ *
+ * "ref:" citations are relative to the reference repository root (real-stanford/garmentnets).
+ */
+#ifndef GARMENTNETS_B200_H
+#define GARMENTNETS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* every entry point below is exported; everything else in the library is hidden */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef enum gnb_status {
+    GNB_OK = 0,
+    GNB_ERR_INVALID = -1,      /* bad argument (shape, null pointer, unsupported size)       */
+    GNB_ERR_CUDA = -2,         /* CUDA runtime error; message holds cudaGetErrorString        */
+    GNB_ERR_UNSUPPORTED = -3,  /* valid request outside the compiled envelope                 */
+    GNB_ERR_NO_SURFACE = -4    /* marching cubes: level outside [min,max] / no vertices       */
+} gnb_status;
+
+typedef enum gnb_reduce { GNB_REDUCE_SUM = 0, GNB_REDUCE_MEAN = 1, GNB_REDUCE_MAX = 2, GNB_REDUCE_MIN = 3 } gnb_reduce;
+
+/* ---- library ------------------------------------------------------------------------ */
+int32_t gnb_version(void);                 /* major*10000 + minor*100 + patch */
+const char* gnb_last_error(void);          /* thread-local, never NULL        */
+int32_t gnb_device_sm_count(void);         /* SMs of the current device; <0 on error */
+
+/* ---- N1: farthest point sampling ------------------------------------------------------
+ * ref: components/pointnet2.py:26  `idx = fps(pos, batch, ratio=self.ratio)` (torch_cluster 1.5.9).
+ * pos   f32[sumN,3]; ptr i64[B+1] cloud offsets (batch vector is sorted, ref datasets/...:458-460);
+ * start i64[B] LOCAL start index per cloud (the reference's random start, injected; NULL = 0);
+ * out_ptr i64[B+1] offsets of the selected indices (m_b = ceil(ratio*n_b), computed by the caller);
+ * out   i64[sumM] GLOBAL indices into pos, in selection order.
+ * Distances are fp32 ((dx*dx + dy*dy) + dz*dz) without fused multiply-add; argmax ties -> lowest index.
+ * max_n_host = largest cloud size (<= 14336 points; one CTA keeps a cloud + its distances in shared memory). */
+int32_t gnb_fps(const float* pos, const int64_t* ptr, int32_t B, const int64_t* start,
+                const int64_t* out_ptr, int64_t* out, int32_t max_n_host, void* stream);
+
+/* ---- N2: ball query --------------------------------------------------------------------
+ * ref: components/pointnet2.py:28-29 `radius(pos, pos[idx], r, batch, batch[idx], max_num_neighbors=64)`.
+ * x f32[sumN,3] points, y f32[sumM,3] queries (centroids); ptr_x/ptr_y i64[B+1].
+ * For query q of cloud b: the first K points j of cloud b IN INDEX ORDER with d2(j,q) < (float)(r*r).
+ * nbr i64[sumM,K] global indices into x, -1 padded; cnt i32[sumM]. */
+int32_t gnb_ball_query(const float* x, const float* y, const int64_t* ptr_x, const int64_t* ptr_y,
+                       int32_t B, int64_t sumM, double r, int32_t K,
+                       int64_t* nbr, int32_t* cnt, void* stream);
+
+/* Compaction of (nbr,cnt) into the (row,col) pair list torch_cluster.radius returns
+ * (row = query index, col = point index; sorted by row then ascending col).
+ * offs i64[sumM+1] = exclusive prefix sum of cnt (see gnb_exclusive_scan_i32). */
+int32_t gnb_radius_pairs(const int64_t* nbr, const int32_t* cnt, const int64_t* offs,
+                         int64_t sumM, int32_t K, int64_t* row, int64_t* col, void* stream);
+
+/* out i64[n+1] = exclusive prefix sum of in i32[n]; out[n] = total.  n <= 2^24. */
+int32_t gnb_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* out, void* stream);
+
+/* ---- N3: k nearest neighbours + inverse-distance interpolation --------------------------
+ * ref: components/pointnet2.py:72 `knn_interpolate(x, pos, pos_skip, batch, batch_skip, k)` (PyG 1.7.2).
+ * gnb_knn: for every query y_i the k nearest x_j of the same cloud, ascending d2, ties -> lower j.
+ * idx i64[Ny,k] (-1 padded when the cloud has < k points), d2 f32[Ny,k].  k <= 16. */
+int32_t gnb_knn(const float* x, const float* y, const int64_t* ptr_x, const int64_t* ptr_y,
+                int32_t B, int64_t Ny, int32_t k, int64_t* idx, float* d2, void* stream);
+/* out[i, 0:C] = sum_j(feat[idx_ij] * w_ij) / sum_j(w_ij),  w = 1/max(d2,1e-16); sums in rank order,
+ * products rounded before adding (no FMA).  feat f32[Nx,C] row stride ldf; out row stride ldo (so the
+ * result can be written straight into the `cat([x, x_skip])` buffer of ref components/pointnet2.py:73-74). */
+int32_t gnb_knn_interpolate(const float* feat, int64_t ldf, const int64_t* idx, const float* d2,
+                            int64_t Ny, int32_t k, int32_t C, float* out, int64_t ldo, void* stream);
+
+/* ---- N4: PointConv grouping ------------------------------------------------------------
+ * ref: components/pointnet2.py:30-31 `PointConv(nn)(x, (pos, pos[idx]), edge_index)` (PyG 1.7.2,
+ * add_self_loops=True): the edge set of centroid i is ballquery(i) U {point with flat index i}.
+ * gnb_pointconv_edge_count: ecnt i32[sumM] = cnt[i] + (i not in nbr[i,:cnt[i]]).
+ * gnb_pointconv_gather: edge rows e in [eoffs[i], eoffs[i+1]) =
+ *     [x_feat[j, 0:Cin], pos_x[j]-pos_y[i]]  (row stride lde >= Cin+3), neighbours first, self loop last.
+ * gnb_segment_max: out[i, c] = max over the centroid's edge rows (0 when it has none). */
+int32_t gnb_pointconv_edge_count(const int64_t* nbr, const int32_t* cnt, int64_t sumM, int32_t K,
+                                 int32_t* ecnt, void* stream);
+int32_t gnb_pointconv_gather(const float* x_feat, int64_t ldx, int32_t Cin, const float* pos_x,
+                             const float* pos_y, const int64_t* nbr, const int32_t* cnt,
+                             const int64_t* eoffs, int64_t sumM, int32_t K,
+                             float* edge, int64_t lde, void* stream);
+int32_t gnb_segment_max(const float* rows, int64_t ldr, const int64_t* offs, int64_t nseg, int32_t C,
+                        float* out, int64_t ldo, void* stream);
+
+/* ---- N10: per-point Linear -> ReLU -> BatchNorm(eval) ----------------------------------
+ * ref: components/mlp.py:9-20 (one `Sequential(Linear, ReLU, PointBatchNorm1D)` block).
+ * Y[r, n] = post( sum_k X[r,k] * W[n,k] + bias[n] );  post(v) = (relu ? max(v,0) : v) * bn_scale[n] + bn_shift[n]
+ * (bn_scale/bn_shift NULL = identity; they are gamma/sqrt(var+eps) and beta - mean*scale).
+ * X f32[R,K] row stride ldx; W f32[N,K] contiguous; Y f32[R,N] row stride ldy.
+ * rows_dev (nullable): device i64 holding the number of valid rows (<= R); tiles beyond it exit early. */
+int32_t gnb_linear(const float* X, int64_t R, int32_t K, int64_t ldx, const float* W, const float* bias,
+                   int32_t N, int32_t relu, const float* bn_scale, const float* bn_shift,
+                   float* Y, int64_t ldy, const int64_t* rows_dev, void* stream);
+
+/* ---- N11: NOCS bin head ----------------------------------------------------------------
+ * ref: networks/conv_implicit_wnf.py:222-231.  logits f32[R, bins*3] viewed [R,bins,3]:
+ * bin i64[R,3] = argmax over bins (first max), conf f32[R,3] = softmax at the argmax,
+ * nocs f32[R,3] = bin * (float)(1/(bins-1)). */
+int32_t gnb_nocs_head(const float* logits, int64_t R, int32_t bins, int64_t* bin, float* conf,
+                      float* nocs, void* stream);
+
+/* ---- N5: scatter-reduce ----------------------------------------------------------------
+ * ref: networks/conv_implicit_wnf.py:92-94 / components/gridding.py:32-35
+ * `torch_scatter.scatter(src=features.T, index, dim=-1, dim_size, reduce)`.
+ * src element (c, n) at src[c*src_sc + n*src_sn]; out element (c, m) at out[c*out_sc + m*out_sm];
+ * index i64[N] in [0, dim_size).  Slots that receive nothing are 0.  `scratch` i32[dim_size]
+ * (owner/count workspace).  MAX/MIN are bit-exact and order independent; SUM/MEAN use fp32 atomics. */
+int32_t gnb_scatter_reduce(const float* src, int64_t src_sc, int64_t src_sn, const int64_t* index,
+                           int64_t N, int32_t C, int64_t dim_size, int32_t reduce,
+                           float* out, int64_t out_sc, int64_t out_sm, int32_t* scratch, void* stream);
+
+/* Aggregator glue, ref networks/conv_implicit_wnf.py:62-85 + components/gridding.py:161-206,230-256:
+ * voxel index of each point from its NOCS position (trunc((p-lc)*((G-1)/(uc-lc))), clamped), flat index
+ * b*G^3 + i0*G^2 + i1*G + i2, and the per-point feature row
+ * [feat(Cf) | p - voxel_origin (3) | sim_points (3) | confidence (3)] written with row stride ldo.
+ * (lower corner 0, upper corner 1 as shipped: config/train_pipeline_default.yaml:43-44.) */
+int32_t gnb_aggregator_features(const float* feat, int64_t ldf, int32_t Cf, const float* nocs,
+                                const float* sim_points, const float* conf, const int64_t* batch,
+                                int64_t N, int32_t G, int64_t* flat_idx, float* out, int64_t ldo, void* stream);
+
+/* ---- N6-N8: 3D-UNet layers on channels-last (NDHWC) activations ---------------------------
+ * ref: components/unet3d.py:43-72 ('gcr' SingleConv = GroupNorm -> Conv3d(3x3x3, pad 1, no bias) -> ReLU),
+ * :222 MaxPool3d(2), :325-330 nearest upsampling, :291 cat((encoder_features, x), 1), :437 final 1x1x1.
+ * gnb_groupnorm_stats: x f32[B,D,H,W,C] -> scale/shift f32[B,C] so that GN(x)[b,..,c] = x*scale + shift
+ *   (biased variance over the group's (C/groups)*D*H*W elements, eps).  ws f64[B*groups*2] workspace. */
+int32_t gnb_groupnorm_stats(const float* x, int32_t B, int64_t voxels, int32_t C, int32_t groups, float eps,
+                            const float* gamma, const float* beta, float* scale, float* shift,
+                            double* ws, void* stream);
+/* y[b,d,h,w,co] = relu?( sum_{tap,ci} (x[b,d+dz,h+dy,w+dx,ci]*scale[b,ci]+shift[b,ci]) * Wt[tap,ci,co] ) ; zero
+ * padding is applied AFTER the affine (the reference pads the GroupNorm output).  Wt f32[27,Cin,Cout] is the
+ * reference weight [Cout,Cin,3,3,3] permuted (tap = kd*9+kh*3+kw).  scale/shift NULL = identity. */
+int32_t gnb_conv3d_k3(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin,
+                      const float* scale, const float* shift, const float* Wt, int32_t Cout,
+                      int32_t relu, float* y, void* stream);
+int32_t gnb_maxpool3d_2(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, float* y, void* stream);
+/* y[b,d,h,w, 0:Cs] = skip[b,d,h,w,:];  y[..., Cs:Cs+Cx] = x[b, d*Dx/D, h*Hx/H, w*Wx/W, :] (nearest). */
+int32_t gnb_upsample_concat(const float* skip, int32_t Cs, const float* x, int32_t Cx, int32_t B,
+                            int32_t D, int32_t H, int32_t W, int32_t Dx, int32_t Hx, int32_t Wx,
+                            float* y, void* stream);
+/* NCDHW (arbitrary element strides, in elements) -> contiguous NDHWC, and back. */
+int32_t gnb_to_channels_last(const float* x, int64_t sb, int64_t sc, int64_t sd, int64_t sh, int64_t sw,
+                             int32_t B, int32_t C, int32_t D, int32_t H, int32_t W, float* y, void* stream);
+
+/* ---- N9+N10: implicit decoder ------------------------------------------------------------
+ * ref: networks/conv_implicit_wnf.py:128-149 (grid_sample trilinear/border/align_corners + MLP) and the dense
+ * 128^3 loop predict.py:145-158.
+ * gnb_trilinear_sample: vol f32[B,D,H,W,C] channels-last; q f32[B,M,3];  out f32[B*M, C] row stride ldo.
+ *   flip=0: q[...,0]->W, q[...,1]->H, q[...,2]->D  (the un-flipped convention of conv_implicit_wnf.py:137-142);
+ *   flip=1: q[...,0]->D, q[...,1]->H, q[...,2]->W  (components/gridding.py:69-70 nocs_grid_sample).
+ *   post: 0 = none, 1 = ReLU then *bn_scale+bn_shift (used when Linear1 is hoisted onto the feature grid).
+ * gnb_trilinear_sample_grid: same with the implicit regular query lattice q[i,j,k] = (i,j,k)/(Q-1)
+ *   (ref components/gridding.py:139-159), rows [m0, m0+M) of the flattened lattice of sample b. */
+int32_t gnb_trilinear_sample(const float* vol, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C,
+                             const float* q, int64_t M, int32_t flip, int32_t post,
+                             const float* bn_scale, const float* bn_shift,
+                             float* out, int64_t ldo, void* stream);
+int32_t gnb_trilinear_sample_grid(const float* vol, int32_t b, int32_t D, int32_t H, int32_t W, int32_t C,
+                                  int32_t Q, int64_t m0, int64_t M, int32_t post,
+                                  const float* bn_scale, const float* bn_shift,
+                                  float* out, int64_t ldo, void* stream);
+
+/* ---- N13: gaussian gradient magnitude ------------------------------------------------------
+ * ref: predict.py:162-163 `ni.gaussian_gradient_magnitude(wnf, sigma, mode="nearest")` (scipy 1.7).
+ * v f32[D,H,W] -> out f32[D,H,W]; tmp f32[2*D*H*W] workspace.  truncate = 4.0 (scipy default). */
+int32_t gnb_gaussian_gradient_magnitude(const float* v, int32_t D, int32_t H, int32_t W, double sigma,
+                                        float* out, float* tmp, void* stream);
+
+/* ---- N12: marching cubes -------------------------------------------------------------------
+ * ref: predict.py:172-181 `marching_cubes(wnf, level, spacing, gradient_direction, method='lewiner')`
+ * + the ggm lookup at trunc(vert/spacing).
+ * Two phases.  gnb_mc_count classifies the (D-1)(H-1)(W-1) cells and returns the vertex / face totals in
+ * counts_host[2] (it synchronises `stream`).  gnb_mc_emit writes
+ *   verts f32[V,3] (axis0,axis1,axis2)*spacing, faces i32[F,3], normals f32[V,3], values f32[V],
+ *   ggm_at_verts f32[V] (ggm may be NULL).
+ * Vertex numbering = first-use order of a sequential axis0->axis1->axis2 cell scan; faces in cell order.
+ * ws: workspace of gnb_mc_workspace_bytes(D,H,W) bytes, shared by both calls. */
+int64_t gnb_mc_workspace_bytes(int32_t D, int32_t H, int32_t W);
+int32_t gnb_mc_count(const float* v, int32_t D, int32_t H, int32_t W, float level, void* ws,
+                     int64_t* counts_host, void* stream);
+int32_t gnb_mc_emit(const float* v, int32_t D, int32_t H, int32_t W, float level, const double* spacing_host,
+                    int32_t ascent, const float* ggm, void* ws, float* verts, int32_t* faces,
+                    float* normals, float* values, float* ggm_at_verts, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GARMENTNETS_B200_H */

@@ -1,0 +1,207 @@
+"""Dense / gridding kernels vs the CPU oracle (torch CPU ATen ops + numpy), called through the C-ABI wrappers."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import nets as ON
+from oracle import pointops as P
+
+TOL = 1e-4  # north_star: fp32 fields within 1e-4 max-abs
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,K,N,relu,bn", [(1000, 6, 64, True, True), (257, 131, 128, True, True), (4096, 259, 256, True, True),
+                                           (64, 1280, 256, True, True), (513, 128, 192, False, False), (300, 256, 1, True, True),
+                                           (300, 256, 3, True, True), (1, 16, 16, True, False), (129, 137, 137, True, True)])
+def test_linear_block(dev, R, K, N, relu, bn):
+    from garmentnets_b200 import ops
+    g = torch.Generator().manual_seed(R + K + N)
+    x = torch.randn(R, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    sc = torch.rand(N, generator=g) + 0.5
+    sh = torch.randn(N, generator=g)
+    ref = F.linear(x, w, b)
+    if relu:
+        ref = F.relu(ref)
+    if bn:
+        ref = ref * sc + sh
+    got = ops.linear(x.to(dev), w.to(dev), b.to(dev), relu, sc.to(dev) if bn else None, sh.to(dev) if bn else None)
+    assert (got.cpu() - ref).abs().max().item() < 2e-5
+    # strided input / output and device-side row count
+    wide = torch.zeros(R, K + 5)
+    wide[:, :K] = x
+    out = torch.full((R, N + 3), 7.0, device=dev)
+    rows = torch.tensor([max(R - 3, 0)], dtype=torch.int64, device=dev)
+    ops.linear(wide.to(dev)[:, :K], w.to(dev), b.to(dev), relu, sc.to(dev) if bn else None, sh.to(dev) if bn else None,
+               out=out[:, :N], rows_dev=rows)
+    assert (out[:max(R - 3, 0), :N].cpu() - ref[:max(R - 3, 0)]).abs().max().item() < 2e-5 if R > 3 else True
+    assert torch.all(out[max(R - 3, 0):, :N] == 7.0) and torch.all(out[:, N:] == 7.0)
+
+
+@pytest.mark.gpu
+def test_mlp_module_matches_oracle(dev):
+    from garmentnets_b200 import synthetic
+    from garmentnets_b200.components.mlp import MLP
+    torch.manual_seed(0)
+    m = synthetic.randomize_(MLP([137, 137, 128]), 1).eval()
+    x = torch.randn(777, 137)
+    ref = ON.mlp(m.state_dict(), "", x)
+    got = m.to(dev)(x.to(dev))
+    assert (got.cpu() - ref).abs().max().item() < 2e-5
+    x3 = torch.randn(2, 50, 137)
+    assert (m(x3.to(dev)).cpu() - ON.mlp({k: v.cpu() for k, v in m.state_dict().items()}, "", x3)).abs().max() < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reduce", ["max", "min", "sum", "mean"])
+@pytest.mark.parametrize("channels_last", [True, False])
+def test_scatter_reduce(dev, reduce, channels_last):
+    from garmentnets_b200 import ops
+    rng = np.random.default_rng(5)
+    N, C, S = 3000, 19, 2000
+    feat = rng.normal(size=(N, C)).astype(np.float32)
+    feat[::7] = -np.abs(feat[::7])  # make sure all-negative slots exist (empty must stay 0, not -inf)
+    index = rng.integers(0, S, N).astype(np.int64)
+    index[index % 5 == 0] = 11  # heavy collisions
+    ref = P.scatter(feat.T, index, S, reduce)
+    got = ops.scatter_reduce(_t(feat, dev).t(), _t(index, dev), S, reduce, channels_last=channels_last)
+    assert got.shape == (C, S)
+    if reduce in ("max", "min"):
+        assert np.array_equal(got.cpu().numpy(), ref)  # bit-exact, order independent
+    else:
+        assert np.abs(got.cpu().numpy() - ref).max() < 1e-4
+    assert np.all(got.cpu().numpy()[:, np.setdiff1d(np.arange(S), index)] == 0)
+
+
+@pytest.mark.gpu
+def test_scatter_empty_input(dev):
+    from garmentnets_b200 import ops
+    got = ops.scatter_reduce(torch.zeros((4, 0), device=dev), torch.zeros(0, dtype=torch.int64, device=dev), 10, "max")
+    assert got.shape == (4, 10) and torch.all(got == 0)
+
+
+@pytest.mark.gpu
+def test_nocs_head_and_aggregator_features(dev):
+    from garmentnets_b200 import ops
+    rng = np.random.default_rng(3)
+    N, bins, G, B = 2000, 64, 32, 3
+    logits = rng.normal(size=(N, bins * 3)).astype(np.float32) * 3
+    logits[5, 10 * 3 + 1] = logits[5, 40 * 3 + 1] = 50.0  # exact tie -> first max
+    b_ref, conf_ref, nocs_ref = ON.nocs_head(logits, bins)
+    b, conf, nocs = ops.nocs_head(_t(logits, dev), bins)
+    assert np.array_equal(b.cpu().numpy(), b_ref) and b_ref[5, 1] == 10
+    assert np.array_equal(nocs.cpu().numpy(), nocs_ref)
+    assert np.abs(conf.cpu().numpy() - conf_ref).max() < 1e-6
+    # KATs from the reference's VirtualGrid
+    assert nocs_ref.max() <= 1.0 and np.float32(1) * (np.float32(1.0) / np.float32(63.0)) in nocs_ref
+    feat = rng.normal(size=(N, 128)).astype(np.float32)
+    sim = rng.normal(size=(N, 3)).astype(np.float32)
+    batch = np.sort(rng.integers(0, B, N)).astype(np.int64)
+    out, flat = ops.aggregator_features(_t(feat, dev), nocs, _t(sim, dev), conf, _t(batch, dev), G)
+    idx3 = ON.points_grid_idxs(nocs_ref, G)
+    k = np.arange(64)
+    assert np.array_equal(np.unique(ON.points_grid_idxs(np.stack([k * np.float32(1 / 63)] * 3, 1).astype(np.float32), 32)[:, 0]),
+                          np.arange(32))
+    flat_ref = batch * G ** 3 + idx3[:, 0] * G ** 2 + idx3[:, 1] * G + idx3[:, 2]
+    assert np.array_equal(flat.cpu().numpy(), flat_ref)
+    scales = (torch.ones(3) / (torch.tensor([G] * 3, dtype=torch.float32) - 1))
+    local = torch.from_numpy(nocs_ref) - torch.from_numpy(idx3) * scales
+    ref = np.concatenate([feat, local.numpy(), sim, conf.cpu().numpy()], 1)
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flip", [False, True])
+def test_trilinear_sample_matches_grid_sample(dev, flip):
+    from garmentnets_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    B, C, D, H, W, M = 2, 24, 5, 6, 7, 500
+    vol = torch.randn(B, C, D, H, W, generator=g)
+    q = torch.rand(B, M, 3, generator=g) * 1.2 - 0.1  # includes out-of-range -> border clamp
+    q[0, 0] = torch.tensor([0.0, 0.0, 1.0])
+    q[0, 1] = torch.tensor([1.0, 1.0, 1.0])
+    qn = 2.0 * q - 1.0
+    if flip:
+        qn = qn.flip(-1)
+    ref = F.grid_sample(vol, qn.view(B, M, 1, 1, 3), mode="bilinear", padding_mode="border", align_corners=True)
+    ref = ref.view(B, C, M).permute(0, 2, 1).reshape(B * M, C)
+    vol_cl = vol.permute(0, 2, 3, 4, 1).contiguous().to(dev)
+    got = ops.trilinear_sample(vol_cl, q.to(dev), flip=flip)
+    assert (got.cpu() - ref).abs().max().item() < 1e-5
+    if not flip:  # axis convention probe: un-flipped (0,0,1) reads volume[..., D=last, 0, 0]
+        assert torch.allclose(got[0].cpu(), vol[0, :, D - 1, 0, 0], atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_trilinear_grid_lattice_matches_explicit_points(dev):
+    from garmentnets_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    vol = torch.randn(2, 4, 4, 4, 16, generator=g).to(dev)
+    Q = 9
+    gp = ON.grid_points(Q).reshape(1, -1, 3)
+    assert torch.equal(gp[0, 1 * 81 + 2 * 9 + 3], torch.tensor([1.0, 2.0, 3.0]) * (torch.tensor(1.0) / torch.tensor(8.0)))
+    ref = ops.trilinear_sample(vol[1:2].contiguous(), gp.to(dev))
+    got = ops.trilinear_sample_grid(vol, 1, Q, 100, 500)
+    assert torch.equal(got, ref[100:600])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,sigma", [((16, 17, 18), 0.5), ((32, 32, 32), 0.5), ((9, 8, 7), 1.0)])
+def test_ggm_matches_scipy(dev, shape, sigma):
+    import scipy.ndimage as ni
+    from garmentnets_b200 import ops
+    v = np.random.default_rng(8).normal(size=shape).astype(np.float32)
+    ref = ni.gaussian_gradient_magnitude(v, sigma=sigma, mode="nearest")
+    got = ops.gaussian_gradient_magnitude(_t(v, dev), sigma).cpu().numpy()
+    assert ref.dtype == np.float32
+    assert np.abs(got - ref).max() <= 2e-7 * max(1.0, np.abs(ref).max())
+    assert (got == ref).mean() > 0.99  # double accumulation in the same order: bit-exact up to rare rounding ties
+
+
+@pytest.mark.gpu
+def test_ggm_impulse_kat(dev):
+    from garmentnets_b200 import ops
+    v = np.zeros((9, 9, 9), np.float32)
+    v[4, 4, 4] = 1.0
+    got = ops.gaussian_gradient_magnitude(_t(v, dev), 0.5).cpu().numpy()
+    assert abs(got[4, 4, 5] - 0.26344162) < 1e-7 and got[4, 4, 4] == 0 and abs(got[5, 5, 5] - 0.008357321) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,G,Cin,Cout,groups", [(2, 8, 32, 64, 8), (1, 6, 96, 32, 8), (1, 4, 128, 128, 8), (2, 5, 4, 16, 1)])
+def test_gn_conv_relu(dev, B, G, Cin, Cout, groups):
+    from garmentnets_b200 import ops
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = torch.randn(B, Cin, G, G, G + 1, generator=g) * 2 + 0.5
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5
+    gamma, beta = torch.rand(Cin, generator=g) + 0.5, torch.randn(Cin, generator=g) * 0.1
+    ref = F.relu(F.conv3d(F.group_norm(x, groups, gamma, beta, 1e-5), w, None, padding=1))
+    x_cl = ops.to_channels_last(x.to(dev))
+    assert torch.equal(x_cl.cpu(), x.permute(0, 2, 3, 4, 1).contiguous())
+    scale, shift = ops.groupnorm_stats(x_cl, groups, 1e-5, gamma.to(dev), beta.to(dev))
+    gn = x_cl * scale[:, None, None, None, :] + shift[:, None, None, None, :]
+    assert (gn.cpu() - F.group_norm(x, groups, gamma, beta, 1e-5).permute(0, 2, 3, 4, 1)).abs().max() < 2e-5
+    wt = w.permute(2, 3, 4, 1, 0).reshape(27, Cin, Cout).contiguous().to(dev)
+    y = ops.conv3d_k3(x_cl, wt, scale, shift, relu=True)
+    assert (y.cpu() - ref.permute(0, 2, 3, 4, 1)).abs().max().item() < 5e-5
+
+
+@pytest.mark.gpu
+def test_pool_upsample_concat(dev):
+    from garmentnets_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 12, 8, 6, 4, generator=g)
+    x_cl = ops.to_channels_last(x.to(dev))
+    p = ops.maxpool3d_2(x_cl)
+    assert torch.equal(p.cpu(), F.max_pool3d(x, 2).permute(0, 2, 3, 4, 1))
+    skip = torch.randn(2, 5, 8, 6, 4, generator=g)
+    up = F.interpolate(F.max_pool3d(x, 2), size=(8, 6, 4), mode="nearest")
+    ref = torch.cat((skip, up), 1).permute(0, 2, 3, 4, 1)
+    got = ops.upsample_concat(ops.to_channels_last(skip.to(dev)), p)
+    assert torch.equal(got.cpu(), ref)
