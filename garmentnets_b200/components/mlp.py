@@ -56,13 +56,35 @@ class _Block(nn.Sequential):
         if self.training:
             raise NotImplementedError("garmentnets_b200 implements the inference hot path only (eval mode)")
         lin = self[0]
+        lead = x.shape[:-1]
+        flat = x.reshape(-1, x.shape[-1]) if x.dim() != 2 else x
+        if _Block.calibrating and len(self) > 2:
+            y = self._calibrate(flat, out, rows_dev)
+            return y if x.dim() == 2 else y.view(*lead, y.shape[-1])
         scale = shift = None
         if len(self) > 2:
             scale, shift = self[2].folded_affine()
-        lead = x.shape[:-1]
-        flat = x.reshape(-1, x.shape[-1]) if x.dim() != 2 else x
         y = ops.linear(flat, lin.weight, lin.bias, True, scale, shift, out=out, rows_dev=rows_dev)
         return y if x.dim() == 2 else y.view(*lead, y.shape[-1])
+
+    # Synthetic-weight support (garmentnets_b200.synthetic.calibrate_bn_): set this block's BatchNorm running
+    # statistics to the statistics of the activations it actually sees, the way training would have.  Not a compute
+    # path: it only edits parameters, once, before any measurement.
+    calibrating = False
+
+    @torch.no_grad()
+    def _calibrate(self, flat, out, rows_dev):
+        lin, bn = self[0], self[2]
+        y = ops.linear(flat, lin.weight, lin.bias, True, None, None, rows_dev=rows_dev)
+        n = y.shape[0] if rows_dev is None else int(rows_dev.item())
+        bn.running_mean.copy_(y[:n].mean(0))
+        bn.running_var.copy_(y[:n].var(0, unbiased=False).clamp_min(1e-3))
+        scale, shift = bn.folded_affine()
+        res = y * scale + shift
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
 
 
 class FusedMLP(nn.Sequential):

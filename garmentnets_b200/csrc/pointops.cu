@@ -382,7 +382,7 @@ int32_t gnb_radius_pairs(const int64_t* nbr, const int32_t* cnt, const int64_t* 
 }
 
 int32_t gnb_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* out, void* stream) {
-    GNB_REQUIRE(in && out, "gnb_exclusive_scan_i32: null pointer");
+    GNB_REQUIRE(out && (in || n == 0), "gnb_exclusive_scan_i32: null pointer");
     GNB_REQUIRE(n >= 0 && n <= (1ll << 24), "gnb_exclusive_scan_i32: n out of range");
     scan_kernel<<<1, 1024, 0, as_stream(stream)>>>(in, n, out);
     return check_launch("gnb_exclusive_scan_i32");

@@ -1,0 +1,323 @@
+"""The GarmentNets inference pipeline on the sm_100a kernels.
+
+Two things live here:
+
+1. Plain ``nn.Module`` equivalents of the reference's stage modules with the SAME attribute paths and constructor
+   keywords, so a reference checkpoint's ``state_dict`` loads key for key
+   (``pointnet2_nocs.sa1_module.conv.local_nn.0.0.weight``, ``volume_agg.local_nn...``,
+   ``unet_3d.abstract_3d_unet.encoders...``, ``volume_decoder.mlp...``, ``surface_decoder.mlp...``):
+       PointNet2NOCS            ref networks/pointnet2_nocs.py:58-166
+       VolumeFeatureAggregator  ref networks/conv_implicit_wnf.py:23-100
+       UNet3D                   ref networks/conv_implicit_wnf.py:104-117
+       ImplicitWNFDecoder       ref networks/conv_implicit_wnf.py:121-149
+       ConvImplicitWNFPipeline  ref networks/conv_implicit_wnf.py:152-338 (forward stages only)
+   (The reference's own ``networks/conv_implicit_wnf.py`` also runs unchanged on ``garmentnets_b200.components``
+   through ``garmentnets_b200.shims``; these classes are what ships to machines that do not have the reference.)
+
+2. ``ConvImplicitWNFPipeline.predict`` -- the "fast tier" replacement of the reference's per-sample predict loop
+   (predict.py:138-187): batched PointNet++ and UNet, dense decode over the implicit 128^3 lattice without
+   materialising query points, Gaussian gradient magnitude, marching cubes and the surface (warp-field) decode,
+   all on the device.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .components.gridding import VirtualGrid
+from .components.mlp import MLP
+from .components.pointnet2 import CloudIndex, FPModule, GlobalSAModule, SAModule
+from .components.unet3d import Abstract3DUNet, DoubleConv
+
+
+class Batch:
+    """Minimal stand-in for ``torch_geometric.data.Batch`` (attribute bag with ``num_graphs`` and ``.to``)."""
+
+    def __init__(self, batch=None, **kwargs):
+        self.batch = batch
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @property
+    def num_graphs(self) -> int:
+        ng = self.__dict__.get("_num_graphs")
+        if ng is not None:
+            return ng
+        return int(self.batch.max().item()) + 1 if self.batch is not None and self.batch.numel() else 0
+
+    @num_graphs.setter
+    def num_graphs(self, v):
+        self.__dict__["_num_graphs"] = int(v)
+
+    @property
+    def keys(self):
+        return [k for k, v in self.__dict__.items() if not k.startswith("_") and v is not None]
+
+    def to(self, device, *args, **kwargs):
+        out = Batch()
+        for k, v in self.__dict__.items():
+            out.__dict__[k] = v.to(device, *args, **kwargs) if isinstance(v, torch.Tensor) else v
+        return out
+
+    def __contains__(self, key):
+        return key in self.__dict__
+
+    def __getitem__(self, key):
+        return self.__dict__[key]
+
+    def __setitem__(self, key, value):
+        self.__dict__[key] = value
+
+
+class PointNet2NOCS(nn.Module):
+    def __init__(self, feature_dim, batch_norm, dropout, sa1_ratio, sa1_r, sa2_ratio, sa2_r, fp3_k, fp2_k, fp1_k,
+                 symmetry_axis=None, nocs_bins=None, learning_rate=1e-4, nocs_loss_weight=1, grip_point_loss_weight=1,
+                 vis_per_items=0, max_vis_per_epoch_train=0, max_vis_per_epoch_val=0, batch_size=None):
+        super().__init__()
+        self.sa1_module = SAModule(sa1_ratio, sa1_r, MLP([3 + 3, 64, 64, 128], batch_norm=batch_norm))
+        self.sa2_module = SAModule(sa2_ratio, sa2_r, MLP([128 + 3, 128, 128, 256], batch_norm=batch_norm))
+        self.sa3_module = GlobalSAModule(nn=MLP([256 + 3, 256, 512, 1024], batch_norm=batch_norm))
+        self.fp3_module = FPModule(k=fp3_k, nn=MLP([1024 + 256, 256, 256], batch_norm=batch_norm))
+        self.fp2_module = FPModule(k=fp2_k, nn=MLP([256 + 128, 256, 128], batch_norm=batch_norm))
+        self.fp1_module = FPModule(k=fp1_k, nn=MLP([128 + 3, 128, 128, 128], batch_norm=batch_norm))
+        out_dim = 3 if nocs_bins is None else nocs_bins * 3
+        self.lin1 = nn.Linear(128, 128)
+        self.lin2 = nn.Linear(128, feature_dim)
+        self.lin3 = nn.Linear(feature_dim, out_dim)
+        self.global_lin1 = nn.Linear(1024, 1024)
+        self.global_lin2 = nn.Linear(1024, out_dim)
+        self.nocs_bins = nocs_bins
+        self.symmetry_axis = symmetry_axis
+        self.batch_size = batch_size
+
+    def set_random_start(self, flag: bool) -> None:
+        self.sa1_module.random_start = flag
+        self.sa2_module.random_start = flag
+
+    def get_virtual_grid(self, device=None):
+        return VirtualGrid(lower_corner=(0, 0, 0), upper_corner=(1, 1, 1), grid_shape=(self.nocs_bins,) * 3,
+                           batch_size=1, device=device or self.lin1.weight.device, int_dtype=torch.int64,
+                           float_dtype=torch.float32)
+
+    def forward(self, data, index: Optional[CloudIndex] = None, fps_starts=None, return_aux: bool = False):
+        """SA1 -> SA2 -> SA3 -> FP3 -> FP2 -> FP1 -> point head / global head (dropout = identity at inference)."""
+        x, pos, batch = data.x, data.pos, data.batch
+        index = index or CloudIndex.from_batch(batch)
+        s1 = s2 = None
+        if fps_starts is not None:
+            s1, s2 = fps_starts
+        x1, pos1, b1, idx1, aux1 = self.sa1_module(x, pos, batch, index=index, fps_start=s1, return_index=True)
+        x2, pos2, b2, idx2, aux2 = self.sa2_module(x1, pos1, b1, index=idx1, fps_start=s2, return_index=True)
+        x3, pos3, b3 = self.sa3_module(x2, pos2, b2, index=idx2)
+        idx3 = CloudIndex.uniform(idx2.num_graphs, 1, pos.device)
+        f3, _, _ = self.fp3_module(x3, pos3, b3, x2, pos2, b2, index=idx3, index_skip=idx2)
+        f2, _, _ = self.fp2_module(f3, pos2, b2, x1, pos1, b1, index=idx2, index_skip=idx1)
+        f1, _, _ = self.fp1_module(f2, pos1, b1, x, pos, batch, index=idx1, index_skip=index)
+        h = ops.linear(f1, self.lin1.weight, self.lin1.bias, relu=True)
+        features = ops.linear(h, self.lin2.weight, self.lin2.bias)
+        logits = ops.linear(features, self.lin3.weight, self.lin3.bias)
+        # global head: relu(global_feature) -> global_lin1 -> global_lin2
+        g = ops.linear(torch.relu(x3), self.global_lin1.weight, self.global_lin1.bias)
+        global_logits = ops.linear(g, self.global_lin2.weight, self.global_lin2.bias)
+        result = {"per_point_features": features, "per_point_logits": logits, "per_point_batch_idx": batch,
+                  "global_logits": global_logits, "global_feature": x3}
+        if return_aux:
+            result["aux"] = {"sa1": (x1, pos1, aux1), "sa2": (x2, pos2, aux2), "fp3": f3, "fp2": f2, "fp1": f1}
+        return result
+
+
+class VolumeFeatureAggregator(nn.Module):
+    def __init__(self, nn_channels=(1024, 1024, 128), batch_norm=True, lower_corner=(0, 0, 0), upper_corner=(1, 1, 1),
+                 grid_shape=(32, 32, 32), reduce_method='mean', include_point_feature=True,
+                 include_confidence_feature=False):
+        super().__init__()
+        self.local_nn = MLP(list(nn_channels), batch_norm=batch_norm)
+        self.lower_corner = tuple(lower_corner)
+        self.upper_corner = tuple(upper_corner)
+        self.grid_shape = tuple(grid_shape)
+        self.reduce_method = reduce_method
+        self.include_point_feature = include_point_feature
+        self.include_confidence_feature = include_confidence_feature
+
+    def forward(self, nocs_data) -> torch.Tensor:
+        """Per-point features [nocs features | offset inside the voxel | sim points | confidence] -> MLP ->
+        scatter-reduce into the voxel grid.  Returns logical [B,C,G,G,G] stored channels-last."""
+        G = self.grid_shape[0]
+        unit_cube = self.lower_corner == (0, 0, 0) and self.upper_corner == (1, 1, 1)
+        if not (unit_cube and len(set(self.grid_shape)) == 1 and self.include_point_feature
+                and self.include_confidence_feature):
+            raise NotImplementedError("VolumeFeatureAggregator: only the shipped configuration (unit cube, cubic grid, "
+                                      "point + confidence features) has a fused kernel")
+        B = int(nocs_data.num_graphs)
+        feats, flat = ops.aggregator_features(nocs_data.x, nocs_data.pos, nocs_data.sim_points,
+                                              nocs_data.pred_confidence, nocs_data.batch, G)
+        h = self.local_nn(feats)
+        vol = ops.scatter_reduce(h.t(), flat, B * G ** 3, self.reduce_method, channels_last=True)  # [C, B*G^3] view
+        C = h.shape[1]
+        return vol.reshape(C, B, G, G, G).permute(1, 0, 2, 3, 4)
+
+
+class UNet3D(nn.Module):
+    def __init__(self, in_channels, out_channels, f_maps=64, layer_order='gcr', num_groups=8, num_levels=4):
+        super().__init__()
+        self.abstract_3d_unet = Abstract3DUNet(in_channels=in_channels, out_channels=out_channels, final_sigmoid=False,
+                                               basic_module=DoubleConv, f_maps=f_maps, layer_order=layer_order,
+                                               num_groups=num_groups, num_levels=num_levels, is_segmentation=False)
+
+    def forward(self, data):
+        return self.abstract_3d_unet(data)
+
+
+class ImplicitWNFDecoder(nn.Module):
+    def __init__(self, nn_channels=(128, 512, 512, 1), batch_norm=True):
+        super().__init__()
+        self.mlp = MLP(list(nn_channels), batch_norm=batch_norm)
+
+    def hoisted(self, features_grid_ndhwc: torch.Tensor) -> torch.Tensor:
+        """Linear_1 commutes with trilinear interpolation (convex weights summing to 1): apply it once on the G^3
+        feature grid instead of once per query.  Returns [B,D,H,W,C1] = grid @ W1^T + b1."""
+        lin = self.mlp[0][0]
+        B, D, H, W, C = features_grid_ndhwc.shape
+        u = ops.linear(features_grid_ndhwc.reshape(-1, C), lin.weight, lin.bias)
+        return u.view(B, D, H, W, -1)
+
+    def _tail(self, h: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        blocks = list(self.mlp)[1:]
+        for i, block in enumerate(blocks):
+            h = block(h, out=out if i == len(blocks) - 1 else None)
+        return h
+
+    def forward(self, features_grid: torch.Tensor, query_points: torch.Tensor) -> torch.Tensor:
+        """features_grid (N,C,D,H,W), query_points (N,M,3) -> (N,M,Cout).  Query coordinate 0 indexes the volume's
+        LAST axis (the reference does not flip xyz for grid_sample, networks/conv_implicit_wnf.py:135-142)."""
+        vol = ops.to_channels_last(features_grid)
+        N, M = query_points.shape[:2]
+        u = self.hoisted(vol)
+        bn = self.mlp[0][2] if len(self.mlp[0]) > 2 else None
+        if bn is not None:
+            sc, sh = bn.folded_affine()
+        else:
+            sc = torch.ones(u.shape[-1], device=u.device)
+            sh = torch.zeros(u.shape[-1], device=u.device)
+        h = ops.trilinear_sample(u, query_points.contiguous(), flip=False, bn_scale=sc, bn_shift=sh)
+        return self._tail(h).view(N, M, -1)
+
+    def forward_lattice(self, u_grid: torch.Tensor, b: int, Q: int, m0: int, M: int,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Decode rows [m0, m0+M) of the implicit Q^3 lattice of sample ``b`` from the hoisted grid ``u_grid``."""
+        bn = self.mlp[0][2]
+        sc, sh = bn.folded_affine()
+        h = ops.trilinear_sample_grid(u_grid, b, Q, m0, M, bn_scale=sc, bn_shift=sh)
+        return self._tail(h, out=out)
+
+
+class ConvImplicitWNFPipeline(nn.Module):
+    def __init__(self, pointnet2_params, volume_agg_params, unet3d_params, volume_decoder_params,
+                 surface_decoder_params, mc_surface_decoder_params=None, learning_rate=1e-4, loss_type='l2',
+                 volume_loss_weight=1.0, surface_loss_weight=1.0, mc_surface_loss_weight=0, volume_classification=False,
+                 volume_task_space=False, vis_per_items=0, max_vis_per_epoch_train=0, max_vis_per_epoch_val=0,
+                 batch_size=None):
+        super().__init__()
+        self.pointnet2_nocs = PointNet2NOCS(**pointnet2_params)
+        self.volume_agg = VolumeFeatureAggregator(**volume_agg_params)
+        self.unet_3d = UNet3D(**unet3d_params)
+        self.volume_decoder = ImplicitWNFDecoder(**volume_decoder_params)
+        self.surface_decoder = ImplicitWNFDecoder(**surface_decoder_params)
+        self.mc_surface_decoder = None
+        if mc_surface_loss_weight > 0:
+            self.mc_surface_decoder = ImplicitWNFDecoder(**mc_surface_decoder_params)
+        self.volume_task_space = volume_task_space
+        self.batch_size = batch_size
+
+    @classmethod
+    def from_hparams(cls, hp: Dict) -> "ConvImplicitWNFPipeline":
+        return cls(pointnet2_params=hp["pointnet2"], volume_agg_params=hp["volume_agg"], unet3d_params=hp["unet3d"],
+                   volume_decoder_params=hp["volume_decoder"], surface_decoder_params=hp["surface_decoder"])
+
+    # ---- stages (same names / dict keys as the reference) --------------------------------------------------
+    def pointnet2_forward(self, data, index: Optional[CloudIndex] = None, fps_starts=None, return_aux=False):
+        res = self.pointnet2_nocs(data, index=index, fps_starts=fps_starts, return_aux=return_aux)
+        bins = self.pointnet2_nocs.nocs_bins
+        _, conf, nocs = ops.nocs_head(res["per_point_logits"], bins)
+        nocs_data = Batch(x=res["per_point_features"], pos=nocs, batch=res["per_point_batch_idx"], sim_points=data.pos,
+                          pred_confidence=conf)
+        if index is not None:
+            nocs_data.num_graphs = index.num_graphs
+        res["nocs_data"] = nocs_data
+        return res
+
+    def unet3d_forward(self, pointnet2_result):
+        vol_in = self.volume_agg(pointnet2_result["nocs_data"])
+        return {"out_feature_volume": self.unet_3d(vol_in), "in_feature_volume": vol_in}
+
+    def volume_decoder_forward(self, unet3d_result, query_points):
+        out = self.volume_decoder(unet3d_result["out_feature_volume"], query_points)
+        return {"out_features": out, "pred_volume_value": out.view(*out.shape[:-1])}
+
+    def surface_decoder_forward(self, unet3d_result, query_points):
+        return {"out_features": self.surface_decoder(unet3d_result["out_feature_volume"], query_points)}
+
+    def forward(self, data):
+        p = self.pointnet2_forward(data)
+        u = self.unet3d_forward(p)
+        return {"pointnet2_result": p, "unet3d_result": u,
+                "volume_decoder_result": self.volume_decoder_forward(u, data.volume_query_points),
+                "surface_decoder_result": self.surface_decoder_forward(u, data.surf_query_points)}
+
+    # ---- fast tier: the whole predict loop on the device ------------------------------------------------------
+    @torch.no_grad()
+    def dense_decode(self, out_feature_volume: torch.Tensor, volume_size: int = 128, rows_per_chunk: int = 1 << 19):
+        """[B,C,G,G,G] feature volume -> [B,Q,Q,Q] winding-number volume over the implicit lattice (i,j,k)/(Q-1)
+        (ref predict.py:145-158 without grid_points, chunk copies or H2D traffic)."""
+        vol = ops.to_channels_last(out_feature_volume)
+        B = vol.shape[0]
+        Q = int(volume_size)
+        u = self.volume_decoder.hoisted(vol)
+        total = Q ** 3
+        out = torch.empty((B, total), dtype=torch.float32, device=vol.device)
+        for b in range(B):
+            for m0 in range(0, total, rows_per_chunk):
+                M = min(rows_per_chunk, total - m0)
+                self.volume_decoder.forward_lattice(u, b, Q, m0, M, out=out[b, m0:m0 + M].view(M, -1))
+        return out.view(B, Q, Q, Q)
+
+    @torch.no_grad()
+    def predict(self, data, volume_size: int = 128, gradient_sigma: float = 0.5, iso_surface_level: float = 0.5,
+                gradient_direction: str = "ascent", index: Optional[CloudIndex] = None, fps_starts=None,
+                keep_volume: bool = False) -> List[Dict[str, torch.Tensor]]:
+        """Device version of the reference's per-sample loop predict.py:138-187, for a whole batch.
+        Returns one dict per sample with the arrays predict.py writes under ``marching_cubes_mesh`` / ``point_cloud``."""
+        p = self.pointnet2_forward(data, index=index, fps_starts=fps_starts)
+        u = self.unet3d_forward(p)
+        wnf = self.dense_decode(u["out_feature_volume"], volume_size)
+        B, Q = wnf.shape[0], wnf.shape[1]
+        spacing = 1 / (Q - 1)
+        fvol = ops.to_channels_last(u["out_feature_volume"])
+        nocs_data = p["nocs_data"]
+        results = []
+        for b in range(B):
+            ggm = ops.gaussian_gradient_magnitude(wnf[b], gradient_sigma)
+            r: Dict[str, torch.Tensor] = {}
+            try:
+                verts, faces, normals, values, ggm_at = ops.marching_cubes(wnf[b], iso_surface_level, (spacing,) * 3,
+                                                                           gradient_direction, ggm)
+                warp = self.surface_decoder(fvol[b:b + 1].permute(0, 4, 1, 2, 3), verts.view(1, -1, 3)).view(-1, 3)
+                r = {"verts": verts, "faces": faces, "normals": normals, "volume_value": values,
+                     "volume_gradient_magnitude": ggm_at, "warp_field": warp}
+            except ValueError:  # level outside the volume's range: NaN placeholder mesh (ref predict.py:165-189)
+                nan = float("nan")
+                dev = wnf.device
+                r = {"verts": torch.full((1, 3), nan, device=dev), "faces": torch.zeros((1, 3), dtype=torch.int32, device=dev),
+                     "normals": torch.full((1, 3), nan, device=dev), "volume_value": torch.full((1,), nan, device=dev),
+                     "volume_gradient_magnitude": torch.full((1,), nan, device=dev),
+                     "warp_field": torch.full((1, 3), nan, device=dev)}
+            if keep_volume:
+                r["wnf_volume"] = wnf[b]
+                r["wnf_ggm"] = ggm
+            results.append(r)
+        self._last_point_outputs = {"pred_nocs": nocs_data.pos, "pred_confidence": nocs_data.pred_confidence}
+        return results

@@ -77,3 +77,67 @@ def randomize_(module: torch.nn.Module, seed: int = 0) -> torch.nn.Module:
                 m.weight.copy_(1.0 + 0.1 * torch.randn(m.weight.shape, generator=g))
                 m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
     return module
+
+
+def build_pipeline(seed: int = 0, device=None, hparams=None):
+    """Seeded random-init pipeline with the shipped architecture (eval mode, deterministic FPS start)."""
+    from .pipeline import ConvImplicitWNFPipeline
+    hp = hparams or HPARAMS
+    torch.manual_seed(seed)
+    model = ConvImplicitWNFPipeline.from_hparams(hp)
+    randomize_(model, seed + 1)
+    model.eval().requires_grad_(False)
+    model.pointnet2_nocs.set_random_start(False)
+    if device is not None:
+        model = model.to(device)
+    return model
+
+
+@torch.no_grad()
+def calibrate_bn_(model, data, index=None, n_queries: int = 4096, seed: int = 0):
+    """Give every BatchNorm of the random-init pipeline the running statistics of the activations it actually sees
+    on ``data`` (what training would have produced).  Without this a random deep point network is numerically
+    almost constant across points: every point lands in the same NOCS bin / voxel and the pipeline degenerates."""
+    from .components.mlp import _Block
+    g = torch.Generator().manual_seed(seed)
+    _Block.calibrating = True
+    try:
+        p = model.pointnet2_forward(data, index=index)
+        u = model.unet3d_forward(p)
+        B = u["out_feature_volume"].shape[0]
+        q = torch.rand(B, n_queries, 3, generator=g).to(u["out_feature_volume"].device)
+        model.volume_decoder_forward(u, q)
+        model.surface_decoder_forward(u, q)
+    finally:
+        _Block.calibrating = False
+
+
+def prepare_model_(model, data, index=None, inside_fraction: float = 0.12):
+    """Seeded weights -> usable synthetic network: BN statistics from data, then the WNF level calibration."""
+    calibrate_bn_(model, data, index)
+    return calibrate_wnf_(model, data, index, inside_fraction)
+
+
+@torch.no_grad()
+def calibrate_wnf_(model, data, index=None, inside_fraction: float = 0.12, level: float = 0.5, probe_size: int = 32):
+    """Random weights give a winding-number field that never crosses the iso level, so marching cubes would find
+    nothing.  Re-centre the LAST BatchNorm of ``volume_decoder`` (running_mean := the (1-inside_fraction) quantile of
+    its input on a probe lattice of sample 0, var := 1, gamma := 1, beta := level) so that ``inside_fraction`` of the
+    volume lies above ``level``.  Deterministic for fixed seeds; the calibrated state_dict is what both the CUDA path
+    and the oracle consume."""
+    bn = model.volume_decoder.mlp[-1][2]
+    bn.running_mean.zero_()
+    bn.running_var.fill_(1.0 - bn.eps)
+    bn.weight.fill_(1.0)
+    bn.bias.zero_()
+    p = model.pointnet2_forward(data, index=index)
+    u = model.unet3d_forward(p)
+    vol = model.dense_decode(u["out_feature_volume"][:1], probe_size)
+    vals = vol.reshape(-1).float().cpu()
+    k = max(1, int(round((1.0 - inside_fraction) * vals.numel())))
+    q = torch.kthvalue(vals, k).values.item()
+    if not q > 0:  # more than (1-inside_fraction) of the ReLU outputs are zero: put the level just above zero
+        q = float(vals[vals > 0].min().item()) if bool((vals > 0).any()) else 0.0
+    bn.running_mean.fill_(q)
+    bn.bias.fill_(level)
+    return q

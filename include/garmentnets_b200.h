@@ -33,7 +33,7 @@ typedef enum gnb_status {
     GNB_ERR_INVALID = -1,      /* bad argument (shape, null pointer, unsupported size)       */
     GNB_ERR_CUDA = -2,         /* CUDA runtime error; message holds cudaGetErrorString        */
     GNB_ERR_UNSUPPORTED = -3,  /* valid request outside the compiled envelope                 */
-    GNB_ERR_NO_SURFACE = -4    /* marching cubes: level outside [min,max] / no vertices       */
+    GNB_ERR_NO_SURFACE = -4    /* marching cubes: level outside [min,max] (skimage: ValueError) */
 } gnb_status;
 
 typedef enum gnb_reduce { GNB_REDUCE_SUM = 0, GNB_REDUCE_MEAN = 1, GNB_REDUCE_MAX = 2, GNB_REDUCE_MIN = 3 } gnb_reduce;

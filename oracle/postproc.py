@@ -1,0 +1,80 @@
+"""Oracle (TEST INFRASTRUCTURE): the CPU tail of the reference's predict loop, ref predict.py:160-187.
+
+* ``gaussian_gradient_magnitude``: scipy.ndimage itself (scipy is installed; the reference pins 1.7.0) -- PINNED.
+* ``marching_cubes``: ctypes wrapper over ``mc_oracle.c`` (PARITY UNPINNED vs scikit-image, see that file), followed
+  by exactly the arithmetic skimage / predict.py apply to the raw vertices: ``vertices * np.r_[spacing]`` in float64,
+  the ggm lookup at ``(verts / spacing).astype(np.uint32)`` and the float32 / int32 casts of predict.py:192-199.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libmc_oracle.so")
+
+
+class _McResult(ctypes.Structure):
+    _fields_ = [("coords", ctypes.POINTER(ctypes.c_float)), ("faces", ctypes.POINTER(ctypes.c_int32)),
+                ("normals", ctypes.POINTER(ctypes.c_float)), ("values", ctypes.POINTER(ctypes.c_float)),
+                ("nv", ctypes.c_int64), ("nf", ctypes.c_int64), ("status", ctypes.c_int)]
+
+
+def _lib():
+    if not os.path.exists(_SO):
+        import subprocess
+        subprocess.check_call(["make", "-C", _HERE])
+    lib = ctypes.CDLL(_SO)
+    lib.mc_oracle.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
+                              ctypes.POINTER(_McResult)]
+    lib.mc_oracle.restype = ctypes.c_int
+    lib.mc_free.argtypes = [ctypes.POINTER(_McResult)]
+    return lib
+
+
+def gaussian_gradient_magnitude(volume: np.ndarray, sigma: float) -> np.ndarray:
+    """predict.py:162-163."""
+    import scipy.ndimage as ni
+    return ni.gaussian_gradient_magnitude(volume, sigma=sigma, mode="nearest")
+
+
+def marching_cubes(volume: np.ndarray, level: float, spacing=(1.0, 1.0, 1.0), gradient_direction: str = "ascent"):
+    """predict.py:172-177 call shape.  Returns (verts float64 [V,3], faces int32 [F,3], normals, values) like skimage
+    (verts are float64 because skimage multiplies float32 vertices by a float64 spacing vector).
+    Raises ValueError when ``level`` is outside the data range, RuntimeError when no surface is found."""
+    vol = np.ascontiguousarray(volume, dtype=np.float32)
+    if vol.ndim != 3 or min(vol.shape) < 2:
+        raise ValueError("Input volume should be a 3D numpy array.")
+    lib = _lib()
+    res = _McResult()
+    rc = lib.mc_oracle(vol.ctypes.data, vol.shape[0], vol.shape[1], vol.shape[2], float(level),
+                       1 if gradient_direction == "ascent" else 0, ctypes.byref(res))
+    if rc == -4:
+        raise ValueError("Surface level must be within volume data range.")
+    try:
+        nv, nf = int(res.nv), int(res.nf)
+        if nv == 0:
+            raise RuntimeError("No surface found at the given iso value.")
+        coords = np.ctypeslib.as_array(res.coords, shape=(nv, 3)).copy()
+        faces = np.ctypeslib.as_array(res.faces, shape=(nf, 3)).copy() if nf else np.zeros((0, 3), np.int32)
+        normals = np.ctypeslib.as_array(res.normals, shape=(nv, 3)).copy()
+        values = np.ctypeslib.as_array(res.values, shape=(nv,)).copy()
+    finally:
+        lib.mc_free(ctypes.byref(res))
+    verts = coords * np.r_[spacing]  # float32 * float64 -> float64, as in skimage
+    return verts, faces, normals, values
+
+
+def predict_tail(wnf_volume: np.ndarray, sigma: float = 0.5, level: float = 0.5, gradient_direction: str = "ascent"):
+    """predict.py:160-181 + the dtype casts of :192-197 (everything but the surface decoder)."""
+    volume_size = wnf_volume.shape[-1]
+    ggm = gaussian_gradient_magnitude(wnf_volume, sigma)
+    voxel_spacing = 1 / (volume_size - 1)
+    verts, faces, normals, values = marching_cubes(wnf_volume, level, (voxel_spacing,) * 3, gradient_direction)
+    nn_idx = (verts / voxel_spacing).astype(np.uint32)
+    verts_ggm = ggm[nn_idx[:, 0], nn_idx[:, 1], nn_idx[:, 2]]
+    return {"verts": verts.astype(np.float32), "faces": faces.astype(np.int32), "normals": normals.astype(np.float32),
+            "volume_value": values.astype(np.float32), "volume_gradient_magnitude": verts_ggm.astype(np.float32),
+            "ggm": ggm}

@@ -1,0 +1,155 @@
+"""Model-level parity: the CUDA pipeline (through the C-ABI) vs the CPU oracle on the same seeded weights/inputs.
+Stage-wise: every stage is fed the ORACLE's inputs so that a flipped argmax upstream cannot hide or fake an error."""
+import numpy as np
+import pytest
+import torch
+
+from garmentnets_b200 import synthetic
+from oracle import nets as ON
+from oracle import pipeline as OP
+from oracle import pointops as P
+
+TOL = 1e-4  # north_star tolerance for fp32 fields (max-abs)
+
+
+def _small_hparams():
+    import copy
+    hp = copy.deepcopy(synthetic.HPARAMS)
+    hp["prediction"]["volume_size"] = 32
+    return hp
+
+
+@pytest.fixture(scope="module")
+def setup(dev):
+    from garmentnets_b200.components.pointnet2 import CloudIndex
+    from garmentnets_b200.pipeline import Batch
+    hp = _small_hparams()
+    B, n = 2, 1024
+    d = synthetic.make_batch(B, n, "Tshirt", seed=5)
+    model = synthetic.build_pipeline(seed=3, device=dev, hparams=hp)
+    data = Batch(x=torch.from_numpy(d["x"]).to(dev), pos=torch.from_numpy(d["pos"]).to(dev),
+                 batch=torch.from_numpy(d["batch"]).to(dev))
+    index = CloudIndex.uniform(B, n, dev)
+    synthetic.prepare_model_(model, data, index)
+    sd = OP.to_cpu_state_dict(model)
+    starts = (np.array([5, 17]), np.array([3, 0]))
+    s1 = OP.stage1(sd, hp, d["x"], d["pos"], d["batch"], B, starts)
+    s2 = OP.stage2(sd, hp, s1, d["pos"], d["batch"], B)
+    return dict(hp=hp, B=B, n=n, d=d, model=model, data=data, index=index, sd=sd, starts=starts, s1=s1, s2=s2, dev=dev)
+
+
+@pytest.mark.gpu
+def test_state_dict_keys_follow_reference_names(setup):
+    keys = set(setup["sd"].keys())
+    for k in ["pointnet2_nocs.sa1_module.conv.local_nn.0.0.weight", "pointnet2_nocs.sa2_module.conv.local_nn.2.2.running_var",
+              "pointnet2_nocs.sa3_module.nn.1.0.bias", "pointnet2_nocs.fp3_module.nn.0.0.weight", "pointnet2_nocs.lin3.weight",
+              "pointnet2_nocs.global_lin2.bias", "volume_agg.local_nn.1.2.num_batches_tracked",
+              "unet_3d.abstract_3d_unet.encoders.0.basic_module.SingleConv1.groupnorm.weight",
+              "unet_3d.abstract_3d_unet.decoders.2.basic_module.SingleConv2.conv.weight",
+              "unet_3d.abstract_3d_unet.final_conv.bias", "volume_decoder.mlp.2.0.weight", "surface_decoder.mlp.2.2.bias"]:
+        assert k in keys, k
+    assert sum(v.numel() for k, v in setup["sd"].items() if k.startswith("unet_3d") ) == 4624640
+
+
+@pytest.mark.gpu
+def test_pointnet2_stage(setup):
+    s = setup
+    dev = s["dev"]
+    starts = tuple(torch.from_numpy(a.astype(np.int64)).to(dev) for a in s["starts"])
+    res = s["model"].pointnet2_forward(s["data"], index=s["index"], fps_starts=starts, return_aux=True)
+    s1 = s["s1"]
+    for name in ("sa1", "sa2"):
+        _, _, aux = res["aux"][name]
+        ref_aux = s1[name][3]
+        assert np.array_equal(aux["idx"].cpu().numpy(), ref_aux["idx"]), name       # FPS bit-exact
+        assert np.array_equal(aux["cnt"].cpu().numpy(), ref_aux["cnt"]), name       # ball query bit-exact
+        assert np.array_equal(aux["nbr"].cpu().numpy(), ref_aux["nbr"]), name
+        assert np.abs(res["aux"][name][0].cpu().numpy() - s1[name][0]).max() < TOL
+    for name in ("fp3", "fp2", "fp1"):
+        assert np.abs(res["aux"][name].cpu().numpy() - s1[name + "_x"]).max() < TOL, name
+    assert np.abs(res["global_feature"].cpu().numpy() - s1["global_feature"]).max() < TOL
+    assert np.abs(res["per_point_features"].cpu().numpy() - s1["per_point_features"]).max() < TOL
+    assert np.abs(res["per_point_logits"].cpu().numpy() - s1["per_point_logits"]).max() < TOL
+    assert np.abs(res["global_logits"].cpu().numpy() - s1["global_logits"]).max() < TOL
+    nd = res["nocs_data"]
+    same = (nd.pos.cpu().numpy() == s1["pred_nocs"]).all(axis=1)
+    assert same.mean() > 0.995  # argmax of near-tied logits may flip for a handful of points
+    assert np.abs(nd.pred_confidence.cpu().numpy() - s1["pred_confidence"])[same].max() < TOL
+
+
+@pytest.mark.gpu
+def test_aggregator_and_unet_stage(setup):
+    from garmentnets_b200.pipeline import Batch
+    s = setup
+    dev, s1, s2 = s["dev"], s["s1"], s["s2"]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    nocs_data = Batch(x=t(s1["per_point_features"]), pos=t(s1["pred_nocs"]), batch=s["data"].batch,
+                      sim_points=s["data"].pos, pred_confidence=t(s1["pred_confidence"]))
+    nocs_data.num_graphs = s["B"]
+    out = s["model"].unet3d_forward({"nocs_data": nocs_data})
+    vin = out["in_feature_volume"]
+    assert tuple(vin.shape) == (s["B"], 128, 32, 32, 32)
+    assert vin.permute(0, 2, 3, 4, 1).is_contiguous()  # channels-last all the way, no transposes
+    ref_in = s2["in_feature_volume"]
+    assert np.abs(vin.cpu().numpy() - ref_in).max() < TOL
+    assert np.array_equal(vin.cpu().numpy() == 0, ref_in == 0)  # same occupancy pattern; empty voxels are exactly 0
+    # UNet on the ORACLE's input volume
+    vout = s["model"].unet_3d(t(ref_in))
+    assert tuple(vout.shape) == (s["B"], 128, 32, 32, 32)
+    err = np.abs(vout.cpu().numpy() - s2["out_feature_volume"]).max()
+    assert err < TOL, err
+
+
+@pytest.mark.gpu
+def test_decoders(setup):
+    s = setup
+    dev, s2, sd = s["dev"], s["s2"], s["sd"]
+    fvol = torch.from_numpy(s2["out_feature_volume"]).to(dev)
+    g = torch.Generator().manual_seed(0)
+    q = torch.rand(s["B"], 700, 3, generator=g) * 1.1 - 0.05
+    ref_v = ON.implicit_decoder(sd, "volume_decoder.", s2["out_feature_volume"], q)
+    ref_s = ON.implicit_decoder(sd, "surface_decoder.", s2["out_feature_volume"], q)
+    u = {"out_feature_volume": fvol}
+    got_v = s["model"].volume_decoder_forward(u, q.to(dev))
+    got_s = s["model"].surface_decoder_forward(u, q.to(dev))
+    assert got_v["pred_volume_value"].shape == (s["B"], 700)
+    assert (got_v["out_features"].cpu() - ref_v).abs().max().item() < TOL
+    assert (got_s["out_features"].cpu() - ref_s).abs().max().item() < TOL
+    # dense lattice decode (predict.py:145-158) at Q=32 against the chunked oracle loop
+    Q = 32
+    ref_d = ON.dense_decode(sd, "volume_decoder.", s2["out_feature_volume"][:1], Q, 16)
+    got_d = s["model"].dense_decode(fvol[:1], Q)[0]
+    assert (got_d.cpu() - ref_d).abs().max().item() < TOL
+    assert (ref_d > 0.5).float().mean().item() > 0.02  # calibration gives a surface
+
+
+@pytest.mark.gpu
+def test_predict_end_to_end(setup):
+    """Whole predict loop vs the oracle on sample 0 (meshes compared on the ORACLE's wnf volume for exactness, then
+    end to end with tolerance-level statistics)."""
+    from garmentnets_b200 import ops
+    from garmentnets_b200.components.pointnet2 import CloudIndex
+    from garmentnets_b200.pipeline import Batch
+    s = setup
+    dev, hp, d, n = s["dev"], s["hp"], s["d"], s["n"]
+    ref = OP.predict_sample(s["sd"], hp, d["x"][:n], d["pos"][:n], (s["starts"][0][:1], s["starts"][1][:1]))
+    mesh = ref["mesh"]
+    # (1) CUDA tail on the oracle's volume: bit-exact topology
+    wnf = torch.from_numpy(ref["wnf_volume"]).to(dev)
+    ggm = ops.gaussian_gradient_magnitude(wnf, 0.5)
+    verts, faces, normals, values, ggm_at = ops.marching_cubes(wnf, 0.5, (1 / 31,) * 3, "ascent", ggm)
+    assert np.array_equal(faces.cpu().numpy(), mesh["faces"])
+    assert np.array_equal(verts.cpu().numpy(), mesh["verts"])
+    assert np.abs(ggm_at.cpu().numpy() - mesh["volume_gradient_magnitude"]).max() < 1e-6
+    fv = torch.from_numpy(ref["stage2"]["out_feature_volume"]).to(dev)
+    warp = s["model"].surface_decoder(fv, verts.view(1, -1, 3)).view(-1, 3)
+    assert np.abs(warp.cpu().numpy() - mesh["warp_field"]).max() < TOL
+    # (2) full CUDA predict for the single sample
+    one = Batch(x=s["data"].x[:n], pos=s["data"].pos[:n], batch=s["data"].batch[:n])
+    starts = tuple(torch.from_numpy(a[:1].astype(np.int64)).to(dev) for a in s["starts"])
+    out = s["model"].predict(one, volume_size=32, index=CloudIndex.uniform(1, n, dev), fps_starts=starts, keep_volume=True)[0]
+    diff = np.abs(out["wnf_volume"].cpu().numpy() - ref["wnf_volume"])
+    # a point whose NOCS argmax flips moves to another voxel: allow a small fraction of outliers, none if no flip
+    assert np.median(diff) < 1e-5 and (diff > TOL).mean() < 0.02
+    assert abs(len(out["verts"]) - len(mesh["verts"])) <= 0.05 * len(mesh["verts"]) + 8
+    assert out["faces"].dtype == torch.int32 and out["warp_field"].shape == (len(out["verts"]), 3)
