@@ -78,7 +78,7 @@ class _Block(nn.Sequential):
         y = ops.linear(flat, lin.weight, lin.bias, True, None, None, rows_dev=rows_dev)
         n = y.shape[0] if rows_dev is None else int(rows_dev.item())
         bn.running_mean.copy_(y[:n].mean(0))
-        bn.running_var.copy_(y[:n].var(0, unbiased=False).clamp_min(1e-3))
+        bn.running_var.copy_(y[:n].var(0, unbiased=False).clamp_min(1e-2))
         scale, shift = bn.folded_affine()
         res = y * scale + shift
         if out is not None:

@@ -203,6 +203,12 @@ class ImplicitWNFDecoder(nn.Module):
         else:
             sc = torch.ones(u.shape[-1], device=u.device)
             sh = torch.zeros(u.shape[-1], device=u.device)
+        from .components.mlp import _Block
+        if _Block.calibrating and bn is not None:  # synthetic-weight BN statistics for the hoisted first layer
+            pre = torch.relu(ops.trilinear_sample(u, query_points.contiguous(), flip=False))
+            bn.running_mean.copy_(pre.mean(0))
+            bn.running_var.copy_(pre.var(0, unbiased=False).clamp_min(1e-2))
+            sc, sh = bn.folded_affine()
         h = ops.trilinear_sample(u, query_points.contiguous(), flip=False, bn_scale=sc, bn_shift=sh)
         return self._tail(h).view(N, M, -1)
 
