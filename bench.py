@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the GarmentNets dense-inference hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Metric (BASELINE.json): garment volumes/sec -- one "volume" = one 4096-point cloud -> PointNet++ -> 32^3 gridding ->
+3D-UNet -> dense 128^3 winding-number decode -> Gaussian gradient magnitude -> marching cubes -> surface (warp)
+decode.  A step = one pass of that path over one batch of B synthetic clouds per rank (BASELINE.json configs[2]:
+"batch=32 full conv_implicit_wnf pipeline", the largest single-GPU configuration; weak scaling: every rank owns its
+own B clouds, no data-path collective, one all-gather of per-rank counters at the end).
+
+* `value`     : whole-job volumes/s with the inputs already resident in HBM (CUDA events, max over ranks).
+* `e2e`       : the same through the public API with HOST buffers: pinned-host clouds -> H2D, whole path, meshes and
+                per-point NOCS -> D2H, all inside the timed region.
+* `roofline`  : the dominant kernel (decoder layer-2 GEMM 256->256 over the 128^3 lattice) timed live with CUDA events.
+* `cpu_baseline` / `--impl reference`: the CPU oracle (a port of the reference's predict.py:138-187; the reference
+  itself cannot be imported here) timed on the host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "garment volumes/sec (4096 pts, 128^3 grid)"
+UNIT = "volumes/s"
+N_POINTS = 4096
+DECODE_L2_FLOP_PER_QUERY = 2 * 256 * 256  # algorithmic FLOPs of the dominant kernel per lattice query
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU (oracle) legs
+def _cpu_setup(seed=0):
+    """Seeded weights + one synthetic Tshirt cloud + the calibrated CPU state_dict (no GPU, no product kernels)."""
+    import copy
+    from garmentnets_b200 import synthetic
+    from oracle import nets as ON
+    from oracle import pipeline as OP
+    hp = copy.deepcopy(synthetic.HPARAMS)
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = synthetic.build_pipeline(seed=seed, hparams=hp)  # module tree on the CPU: parameters only, never run
+    sd = OP.to_cpu_state_dict(model)
+    pos, rgb = synthetic.make_cloud("Tshirt", N_POINTS, 0)
+    ON.CALIBRATE = True
+    try:
+        batch = np.zeros(N_POINTS, np.int64)
+        s1 = OP.stage1(sd, hp, rgb, pos, batch, 1, None)
+        s2 = OP.stage2(sd, hp, s1, pos, batch, 1)
+        q = torch.rand(1, 4096, 3, generator=torch.Generator().manual_seed(0))
+        ON.implicit_decoder(sd, "volume_decoder.", s2["out_feature_volume"], q)
+        ON.implicit_decoder(sd, "surface_decoder.", s2["out_feature_volume"], q)
+    finally:
+        ON.CALIBRATE = False
+    return hp, sd, pos, rgb
+
+
+def _cpu_sample(hp, sd, pos, rgb, wnf_full=None, decode_rows=131072):
+    """One bounded sample of predict.py:138-187 on the host cores.  The dense decode is timed on `decode_rows` of the
+    2,097,152 lattice queries (a [32,64,64] half chunk by default) and scaled; ggm + marching cubes + surface decode
+    run on `wnf_full`.  Returns (seconds per volume, per-stage seconds)."""
+    from oracle import nets as ON
+    from oracle import pipeline as OP
+    from oracle import postproc
+    pr = hp["prediction"]
+    Q = pr["volume_size"]
+    batch = np.zeros(len(pos), np.int64)
+    t0 = time.perf_counter()
+    s1 = OP.stage1(sd, hp, rgb, pos, batch, 1, None)
+    t1 = time.perf_counter()
+    s2 = OP.stage2(sd, hp, s1, pos, batch, 1)
+    t2 = time.perf_counter()
+    gp = ON.grid_points(Q)
+    nz = max(1, decode_rows // (64 * 64))
+    qpts = gp[:nz, :64, :64].reshape(1, -1, 3)
+    ON.implicit_decoder(sd, "volume_decoder.", s2["out_feature_volume"], qpts)
+    t3 = time.perf_counter()
+    decode = (t3 - t2) * (Q ** 3 / qpts.shape[1])
+    tail = postproc.predict_tail(wnf_full, pr["gradient_sigma"], pr["iso_surface_level"], pr["gradient_direction"])
+    t4 = time.perf_counter()
+    ON.implicit_decoder(sd, "surface_decoder.", s2["out_feature_volume"],
+                        torch.from_numpy(tail["verts"].astype(np.float32)).view(1, -1, 3))
+    t5 = time.perf_counter()
+    stages = {"pointnet2": t1 - t0, "unet3d": t2 - t1, "dense_decode_scaled": decode, "ggm_mc": t4 - t3,
+              "surface_decode": t5 - t4}
+    return sum(stages.values()), stages
+
+
+def _cpu_full_volume(hp, sd, pos, rgb, level=0.5, inside_fraction=0.12):
+    """Untimed set-up for the reference arm: the full 128^3 volume (so marching cubes has a real input) and the WNF
+    level calibration, all with the oracle on the CPU."""
+    from oracle import nets as ON
+    from oracle import pipeline as OP
+    batch = np.zeros(len(pos), np.int64)
+    for k, v in (("running_mean", 0.0), ("running_var", 1.0 - 1e-5), ("weight", 1.0), ("bias", 0.0)):
+        sd[f"volume_decoder.mlp.2.2.{k}"] = torch.full((1,), v)
+    s1 = OP.stage1(sd, hp, rgb, pos, batch, 1, None)
+    s2 = OP.stage2(sd, hp, s1, pos, batch, 1)
+    wnf = ON.dense_decode(sd, "volume_decoder.", s2["out_feature_volume"], hp["prediction"]["volume_size"], 64).numpy()
+    vals = np.sort(wnf.reshape(-1))
+    q = float(vals[int(round((1 - inside_fraction) * (len(vals) - 1)))])
+    if not q > 0:
+        q = float(vals[vals > 0].min()) if (vals > 0).any() else 0.0
+    sd["volume_decoder.mlp.2.2.running_mean"] = torch.full((1,), q)
+    sd["volume_decoder.mlp.2.2.bias"] = torch.full((1,), level)
+    scale = 1.0 / np.sqrt(1.0 - 1e-5 + 1e-5)
+    return ((wnf - q) * scale + level).astype(np.float32)
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the reference's CPU algorithm (oracle port) on the box's host cores, rank 0 only."""
+    if rank != 0:
+        return
+    t_setup = time.perf_counter()
+    hp, sd, pos, rgb = _cpu_setup()
+    wnf = _cpu_full_volume(hp, sd, pos, rgb)
+    cores = torch.get_num_threads()
+    for _ in range(args.warmup):
+        _cpu_sample(hp, sd, pos, rgb, wnf, args.cpu_decode_rows)
+    secs = []
+    for _ in range(args.steps):
+        s, stages = _cpu_sample(hp, sd, pos, rgb, wnf, args.cpu_decode_rows)
+        secs.append(s)
+    per_volume = float(np.mean(secs))
+    value = 1.0 / per_volume
+    sample = (f"1 synthetic Tshirt cloud (4096 pts) per step: PointNet++ + gridding + 3D-UNet(32^3) in full, dense decode "
+              f"timed on {args.cpu_decode_rows} of 2097152 lattice queries and scaled, ggm + marching cubes + surface "
+              f"decode on a full 128^3 volume")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_volume * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "full conv_implicit_wnf pipeline per volume (CPU oracle port of predict.py:138-187)",
+                       "points": N_POINTS, "unet_grid": 32, "volume_size": 128},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "stages_s": {k: round(v, 4) for k, v in stages.items()}},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "setup_s": round(time.perf_counter() - t_setup - sum(secs), 1)}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world):
+    import torch.distributed as dist
+    from garmentnets_b200 import _lib, profiling, synthetic
+    from garmentnets_b200.components.pointnet2 import CloudIndex
+    from garmentnets_b200.pipeline import Batch
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.load()
+    B = args.batch
+    hp = synthetic.HPARAMS
+    pr = hp["prediction"]
+    # every rank owns its own B clouds (sample-sharded data parallelism)
+    d = synthetic.make_batch(B, N_POINTS, "Tshirt", seed=100 + rank)
+    model = synthetic.build_pipeline(seed=0, device=dev)
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in d.items()}
+    data = Batch(x=host["x"].to(dev), pos=host["pos"].to(dev), batch=host["batch"].to(dev))
+    index = CloudIndex.uniform(B, N_POINTS, dev)
+    synthetic.prepare_model_(model, data, index)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        return model.predict(data, volume_size=pr["volume_size"], gradient_sigma=pr["gradient_sigma"],
+                             iso_surface_level=pr["iso_surface_level"], gradient_direction=pr["gradient_direction"],
+                             index=index)
+
+    def step_e2e():
+        dd = Batch(x=host["x"].to(dev, non_blocking=True), pos=host["pos"].to(dev, non_blocking=True),
+                   batch=host["batch"].to(dev, non_blocking=True))
+        res = model.predict(dd, volume_size=pr["volume_size"], gradient_sigma=pr["gradient_sigma"],
+                            iso_surface_level=pr["iso_surface_level"], gradient_direction=pr["gradient_direction"],
+                            index=index)
+        out_bytes = 0
+        outs = []
+        for r in res:
+            for k in ("verts", "faces", "normals", "volume_value", "volume_gradient_magnitude", "warp_field"):
+                t = r[k].cpu()
+                out_bytes += t.numel() * t.element_size()
+                outs.append(t)
+        for k, t in model._last_point_outputs.items():
+            t = t.cpu()
+            out_bytes += t.numel() * t.element_size()
+        return res, out_bytes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        res = step_resident()
+    barrier()
+    V = int(np.mean([len(r["verts"]) for r in res]))
+    F = int(np.mean([len(r["faces"]) for r in res]))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    timer = profiling.KernelTimer(["decode_l2"])
+    launches0 = _lib.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    with timer:
+        for s, e in ev:
+            flush.fill_(1)  # L2 flush between timed iterations (outside the event pair)
+            s.record()
+            step_resident()
+            e.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = (_lib.launch_count - launches0) // max(args.steps, 1)
+    total_ms = sum(s.elapsed_time(e) for s, e in ev)
+    ksum = timer.summary()
+
+    # end-to-end through the public API with host buffers
+    step_e2e()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        _, d2h = step_e2e()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)  # D2H copies block the host: take the larger
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+
+    # max over ranks (device-timed), sums of units
+    stats = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = stats.tolist()
+    if rank != 0:
+        return
+    ms_per_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms / 1e3)
+    e2e_value = world * B * e2e_steps / (e2e_ms / 1e3)
+
+    peaks = _peaks()
+    n_l2, ms_l2 = ksum.get("decode_l2", (0, 0.0))
+    queries_per_launch = (B * args.steps * pr["volume_size"] ** 3) / max(n_l2, 1)
+    achieved = DECODE_L2_FLOP_PER_QUERY * queries_per_launch / (ms_l2 / max(n_l2, 1) * 1e-3) / 1e12 if n_l2 else None
+    roofline = {"kernel": "gnb_linear (decoder layer 2: 256->256 GEMM + bias + ReLU + BN over the 128^3 lattice)",
+                "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": (achieved / peaks["bf16_tflops_sustained"]) if achieved else None, "traffic": None,
+                "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
+                "launches_timed": n_l2, "avg_launch_ms": ms_l2 / max(n_l2, 1), "share_of_step": ms_l2 / total_ms,
+                "note": "fp32 FFMA kernel in this round: the tensor-pipe fraction is the distance to the tcgen05 target"}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        # bounded CPU sample of the same workload; marching cubes runs on a GPU-produced volume of sample 0
+        hp_c, sd_c, pos_c, rgb_c = _cpu_setup()
+        wnf0 = model.predict(Batch(x=data.x[:N_POINTS], pos=data.pos[:N_POINTS], batch=data.batch[:N_POINTS]),
+                             volume_size=pr["volume_size"], index=CloudIndex.uniform(1, N_POINTS, dev),
+                             keep_volume=True)[0]["wnf_volume"].cpu().numpy()
+        _cpu_sample(hp_c, sd_c, pos_c, rgb_c, wnf0, args.cpu_decode_rows)
+        secs, stages = _cpu_sample(hp_c, sd_c, pos_c, rgb_c, wnf0, args.cpu_decode_rows)
+        cpu_baseline = {"value": 1.0 / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"1 cloud: PointNet++/gridding/UNet in full, dense decode on {args.cpu_decode_rows} of "
+                                  f"2097152 queries scaled, ggm+MC+surface decode on a full 128^3 volume",
+                        "stages_s": {k: round(v, 4) for k, v in stages.items()}}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: batch=32 full conv_implicit_wnf pipeline (PointNet++ + 32^3 "
+                                   "gridding + 3D-UNet + dense 128^3 decode + ggm + marching cubes + surface decode)",
+                       "batch_per_gpu": B, "points": N_POINTS, "unet_grid": 32, "volume_size": pr["volume_size"],
+                       "mean_verts": V, "mean_faces": F, "l2": "flushed between timed iterations (256 MiB write)",
+                       "parallelism": f"sample-sharded x{world}, no data-path collective"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": launches, "clocks": clocks, "wall_s": round(wall, 3)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="clouds per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-decode-rows", type=int, default=131072)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        dist.init_process_group("nccl")
+    try:
+        run_ours(args, rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

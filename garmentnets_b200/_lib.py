@@ -76,12 +76,26 @@ def last_error() -> str:
     return load().gnb_last_error().decode("utf-8", "replace")
 
 
+# kernels launched per entry point (for the launch counter bench.py reports); entry points not listed launch one
+KERNELS_PER_CALL = {"gnb_scatter_reduce": 2, "gnb_gaussian_gradient_magnitude": 9, "gnb_mc_count": 2, "gnb_mc_emit": 2,
+                    "gnb_groupnorm_stats": 2, "gnb_version": 0, "gnb_last_error": 0, "gnb_device_sm_count": 0,
+                    "gnb_mc_workspace_bytes": 0}
+launch_count = 0          # kernels launched through this binding since import (monotonic)
+_tag = None               # current profiling tag (see garmentnets_b200.profiling)
+_tag_sink = None          # callable(tag, name) -> context manager, installed by profiling.KernelTimer
+
+
 def call(name: str, *args):
     """Invoke ``name`` and raise on a negative status.  Pointers are passed as ints (``tensor.data_ptr()``)."""
+    global launch_count
     lib = load()
     fn = getattr(lib, name)
-    conv = [None if (a is None) else a for a in args]
-    status = fn(*conv)
+    launch_count += KERNELS_PER_CALL.get(name, 1)
+    if _tag_sink is not None and _tag is not None:
+        with _tag_sink(_tag, name):
+            status = fn(*args)
+    else:
+        status = fn(*args)
     if isinstance(status, int) and status < 0:
         msg = last_error()
         if status == -4:

@@ -1,0 +1,78 @@
+"""Multi-GPU plumbing: the path shards by independent units -- every stage is per cloud / per
+volume (BatchNorm in eval mode, GroupNorm per sample) -- so ranks own contiguous blocks of clouds, weights are
+replicated and there is NO data-path collective.  The only communication is one all-gather of a fixed-size per-rank
+record for the final metrics and, when the caller wants every mesh on rank 0 (BASELINE config 4), one padded
+all-gather of the variable-length meshes.  Works with NCCL (GPU tensors) and gloo (CPU tensors, used by the tests).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+RECORD_FIELDS = ("n_volumes", "elapsed_ms", "sum_verts", "sum_faces", "checksum")
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of ``total`` units owned by ``rank``; blocks differ in size by at most one."""
+    base, rem = divmod(int(total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _device():
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def gather_metrics(record: Dict[str, float]) -> List[Dict[str, float]]:
+    """One all-gather of the fixed-size per-rank record; every rank gets the list of all records."""
+    world = dist.get_world_size()
+    mine = torch.tensor([float(record.get(k, 0.0)) for k in RECORD_FIELDS], dtype=torch.float64, device=_device())
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    return [dict(zip(RECORD_FIELDS, t.tolist())) for t in out]
+
+
+def summarize(records: Sequence[Dict[str, float]]) -> Dict[str, float]:
+    """Whole-job numbers: units summed over ranks, time = max over ranks (never a wall clock)."""
+    n = sum(r["n_volumes"] for r in records)
+    t = max(r["elapsed_ms"] for r in records)
+    return {"n_volumes": n, "elapsed_ms": t, "volumes_per_s": n / (t / 1e3) if t > 0 else 0.0,
+            "sum_verts": sum(r["sum_verts"] for r in records), "sum_faces": sum(r["sum_faces"] for r in records),
+            "checksum": sum(r["checksum"] for r in records)}
+
+
+def gather_meshes(meshes: Sequence[Dict[str, torch.Tensor]]) -> List[List[Dict[str, torch.Tensor]]]:
+    """All-gather of this rank's list of meshes ({"verts" f32[V,3], "faces" i32[F,3], "warp_field" f32[V,3]}).
+    Two collectives: the per-sample (V, F) counts, then ONE padded buffer per rank.  Returns, on every rank, the
+    per-rank lists in rank order.  Every rank must pass the same number of meshes."""
+    world = dist.get_world_size()
+    dev = _device()
+    n = len(meshes)
+    counts = torch.tensor([[m["verts"].shape[0], m["faces"].shape[0]] for m in meshes], dtype=torch.int64,
+                          device=dev).reshape(n, 2)
+    all_counts = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts)
+    vmax = int(max(int(c[:, 0].max()) if n else 0 for c in all_counts))
+    fmax = int(max(int(c[:, 1].max()) if n else 0 for c in all_counts))
+    # one float32 payload per rank: [n, vmax, 6] (verts | warp) and one int32 payload [n, fmax, 3]
+    vbuf = torch.zeros((n, vmax, 6), dtype=torch.float32, device=dev)
+    fbuf = torch.zeros((n, fmax, 3), dtype=torch.int32, device=dev)
+    for i, m in enumerate(meshes):
+        V, F = m["verts"].shape[0], m["faces"].shape[0]
+        vbuf[i, :V, :3] = m["verts"].to(dev)
+        vbuf[i, :V, 3:] = m["warp_field"].to(dev)
+        fbuf[i, :F] = m["faces"].to(dev)
+    all_v = [torch.empty_like(vbuf) for _ in range(world)]
+    all_f = [torch.empty_like(fbuf) for _ in range(world)]
+    dist.all_gather(all_v, vbuf)
+    dist.all_gather(all_f, fbuf)
+    out = []
+    for r in range(world):
+        lst = []
+        for i in range(n):
+            V, F = int(all_counts[r][i, 0]), int(all_counts[r][i, 1])
+            lst.append({"verts": all_v[r][i, :V, :3], "warp_field": all_v[r][i, :V, 3:], "faces": all_f[r][i, :F]})
+        out.append(lst)
+    return out

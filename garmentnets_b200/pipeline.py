@@ -27,7 +27,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import ops
+from . import ops, profiling
 from .components.gridding import VirtualGrid
 from .components.mlp import MLP
 from .components.pointnet2 import CloudIndex, FPModule, GlobalSAModule, SAModule
@@ -176,6 +176,7 @@ class ImplicitWNFDecoder(nn.Module):
     def __init__(self, nn_channels=(128, 512, 512, 1), batch_norm=True):
         super().__init__()
         self.mlp = MLP(list(nn_channels), batch_norm=batch_norm)
+        self.profile_tag = "decoder"  # renamed per instance by the pipeline ("decode" / "surface")
 
     def hoisted(self, features_grid_ndhwc: torch.Tensor) -> torch.Tensor:
         """Linear_1 commutes with trilinear interpolation (convex weights summing to 1): apply it once on the G^3
@@ -188,7 +189,8 @@ class ImplicitWNFDecoder(nn.Module):
     def _tail(self, h: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         blocks = list(self.mlp)[1:]
         for i, block in enumerate(blocks):
-            h = block(h, out=out if i == len(blocks) - 1 else None)
+            with profiling.tag(f"{self.profile_tag}_l{i + 2}"):
+                h = block(h, out=out if i == len(blocks) - 1 else None)
         return h
 
     def forward(self, features_grid: torch.Tensor, query_points: torch.Tensor) -> torch.Tensor:
@@ -217,7 +219,8 @@ class ImplicitWNFDecoder(nn.Module):
         """Decode rows [m0, m0+M) of the implicit Q^3 lattice of sample ``b`` from the hoisted grid ``u_grid``."""
         bn = self.mlp[0][2]
         sc, sh = bn.folded_affine()
-        h = ops.trilinear_sample_grid(u_grid, b, Q, m0, M, bn_scale=sc, bn_shift=sh)
+        with profiling.tag(f"{self.profile_tag}_interp"):
+            h = ops.trilinear_sample_grid(u_grid, b, Q, m0, M, bn_scale=sc, bn_shift=sh)
         return self._tail(h, out=out)
 
 
@@ -238,6 +241,8 @@ class ConvImplicitWNFPipeline(nn.Module):
             self.mc_surface_decoder = ImplicitWNFDecoder(**mc_surface_decoder_params)
         self.volume_task_space = volume_task_space
         self.batch_size = batch_size
+        self.volume_decoder.profile_tag = "decode"
+        self.surface_decoder.profile_tag = "surface"
 
     @classmethod
     def from_hparams(cls, hp: Dict) -> "ConvImplicitWNFPipeline":

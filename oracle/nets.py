@@ -24,6 +24,10 @@ from . import pointops as P
 
 SD = Dict[str, torch.Tensor]
 
+# When True, ``mlp`` overwrites each BatchNorm's running statistics in ``sd`` with the statistics of its input (the
+# CPU twin of garmentnets_b200.synthetic.calibrate_bn_, used by ``bench.py --impl reference`` which has no GPU model).
+CALIBRATE = False
+
 
 def _t(a) -> torch.Tensor:
     return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
@@ -40,6 +44,9 @@ def mlp(sd: SD, prefix: str, x: torch.Tensor, batch_norm: bool = True) -> torch.
         x = F.linear(x, sd[p + "0.weight"], sd[p + "0.bias"])
         x = F.relu(x)
         if batch_norm and (p + "2.weight") in sd:
+            if CALIBRATE:  # synthetic-weight support: running statistics := statistics of the activations seen
+                sd[p + "2.running_mean"] = x.mean(0)
+                sd[p + "2.running_var"] = x.var(0, unbiased=False).clamp_min(1e-2)
             x = F.batch_norm(x, sd[p + "2.running_mean"], sd[p + "2.running_var"], sd[p + "2.weight"],
                              sd[p + "2.bias"], training=False, eps=1e-5)
         layer += 1

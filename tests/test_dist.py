@@ -1,0 +1,70 @@
+"""Host-side multi-rank logic on CPU: world_size-2 gloo processes (sharding, metric all-gather, padded mesh gather)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from garmentnets_b200 import dist as gd
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = gd.shard_range(7, rank, world)
+        recs = gd.gather_metrics({"n_volumes": hi - lo, "elapsed_ms": 10.0 * (rank + 1), "sum_verts": 100 * (rank + 1),
+                                  "sum_faces": 200 * (rank + 1), "checksum": float(rank)})
+        summary = gd.summarize(recs)
+        g = torch.Generator().manual_seed(rank)
+        meshes = []
+        for i in range(2):
+            V, F = 5 + 3 * rank + i, 4 + rank + 2 * i
+            meshes.append({"verts": torch.rand(V, 3, generator=g), "warp_field": torch.rand(V, 3, generator=g),
+                           "faces": torch.randint(0, V, (F, 3), generator=g, dtype=torch.int32)})
+        allm = gd.gather_meshes(meshes)
+        ok = all(torch.equal(allm[rank][i][k], meshes[i][k]) for i in range(2) for k in ("verts", "faces", "warp_field"))
+        shapes = [[tuple(m["verts"].shape) + tuple(m["faces"].shape) for m in lst] for lst in allm]
+        q.put((rank, (lo, hi), summary, ok, shapes))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_range_partitions_exactly():
+    for total in (0, 1, 7, 32, 256):
+        for world in (1, 2, 3, 8):
+            blocks = [gd.shard_range(total, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == total
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b[1] - b[0] for b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_gloo_world2_gather():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, b0, s0, ok0, sh0), (r1, b1, s1, ok1, sh1) = res
+    assert b0 == (0, 4) and b1 == (4, 7)
+    assert s0 == s1  # every rank sees the same whole-job summary
+    assert s0["n_volumes"] == 7 and s0["elapsed_ms"] == 20.0 and s0["sum_verts"] == 300 and s0["sum_faces"] == 600
+    assert abs(s0["volumes_per_s"] - 7 / 0.02) < 1e-9  # units of all ranks / max time over ranks
+    assert ok0 and ok1 and sh0 == sh1
+    assert sh0 == [[(5, 3, 4, 3), (6, 3, 6, 3)], [(8, 3, 5, 3), (9, 3, 7, 3)]]

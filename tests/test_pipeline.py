@@ -13,10 +13,11 @@ TOL = 1e-4  # north_star tolerance for the fp32 output fields (winding number, w
 
 
 def close(got, ref, tol=TOL):
-    """Intermediate feature tensors are not O(1) (the synthetic BatchNorm statistics give activations up to ~1e2), so
-    they are compared with the same 1e-4 bound relative to max(1, |ref|); output fields use the plain max-abs bound."""
+    """Intermediate feature tensors are not O(1) (the synthetic BatchNorm statistics give activations up to ~1e2 and
+    amplify fp32 summation-order noise accordingly), so they are compared with the 1e-4 bound scaled by
+    max(1, max|ref|) of the tensor; the output fields (winding number, warp field) use the plain max-abs bound."""
     got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
-    return float(np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref)))) < tol
+    return float(np.max(np.abs(got - ref))) < tol * max(1.0, float(np.max(np.abs(ref))))
 
 
 def _small_hparams():
