@@ -1,0 +1,466 @@
+// Implicit-decoder tail on the 5th-gen tensor cores (tcgen05 + TMEM), ref networks/conv_implicit_wnf.py:128-149 and the
+// dense 128^3 loop predict.py:145-158.
+//
+// One persistent, warp-specialised CTA per SM computes, for tiles of 128 queries,
+//     H1 = BN1(ReLU(trilinear(U)))            U = Linear1 hoisted onto the feature grid (fp32, channels-last)
+//     H2 = BN2(ReLU(H1 * W2^T + b2))          256 x 256 contraction on tcgen05, fp32 accumulators in TMEM
+//     y  = BN3(ReLU(H2 * W3^T + b3))          Cout in {1,2,3}: per-row dot products in the epilogue registers
+// and writes only y (4*Cout bytes per query); H1 / H2 never touch HBM.
+//
+// Precision: the reference runs fp32 and the parity bar is 1e-4 max-abs, which a single bf16/tf32 pass cannot meet
+// over K = 256.  Both operands are split into bf16 hi + lo (a = hi + lo + O(2^-17 a)) and the product is formed as
+// hi*hi + lo*hi + hi*lo with fp32 accumulation: three kind::f16 MMAs per K-step, ~2^-16 relative error per product.
+//
+// Pipeline (mbarrier producer/consumer rings, no __syncthreads in steady state):
+//   warps 0-3  A producers: warp w builds K-chunk w (64 channels) of the 128-row A tile, bf16 hi/lo, directly in the
+//              UMMA canonical K-major SWIZZLE_128B layout in shared memory (generic-proxy stores + fence.proxy.async).
+//              LATTICE: the tile is one lattice line (i,j,0..127): bilinear blend of the four (H,W) neighbours per
+//              D-slice held in registers, then a linear blend along D per row -- 4 coalesced 8-byte loads per slice.
+//              ROWS: the tile is 128 rows of a precomputed fp32 H1 matrix (arbitrary query sets, surface decoder).
+//   warp 9     B loader: W2 is pre-packed (gnb_pack_bf16_split) into 32 KB shared-memory images (K-chunk x {hi,lo});
+//              cp.async.bulk streams them from L2 through a 3-slot ring (complete_tx on an mbarrier).
+//   warp 8     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=256, K=16) and tcgen05.commit.
+//   warps 4-7  epilogue: tcgen05.ld of the accumulator rows (lane = row), bias/ReLU/BN2 folded with W3, store.
+// TMEM: 2 x 256 columns (accumulator double buffer: epilogue(t) overlaps MMA(t+1)); smem: A 128 KB + B ring 96 KB.
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace gnb {
+
+constexpr int TC_K = 256, TC_N = 256, TC_M = 128, TC_KCHUNK = 64, TC_NCHUNK = TC_K / TC_KCHUNK;
+constexpr int A_CHUNK_BYTES = TC_M * TC_KCHUNK * 2;      // 16 KB (one precision part)
+constexpr int B_PIECE_BYTES = TC_N * TC_KCHUNK * 2;      // 32 KB
+constexpr int B_SLOTS = 3;
+constexpr int TC_THREADS = 320;
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+struct TcSmem {
+    // offsets inside the dynamic shared memory block (1024-byte aligned base)
+    static constexpr int a_hi = 0;                                    // [4][16 KB]
+    static constexpr int a_lo = a_hi + TC_NCHUNK * A_CHUNK_BYTES;     // [4][16 KB]
+    static constexpr int b_ring = a_lo + TC_NCHUNK * A_CHUNK_BYTES;   // [3][32 KB]
+    static constexpr int bars = b_ring + B_SLOTS * B_PIECE_BYTES;     // mbarriers
+    static constexpr int n_bars = 4 + 4 + B_SLOTS + B_SLOTS + 2 + 2;
+    static constexpr int tmem_ptr = bars + n_bars * 8;
+    static constexpr int ztab = tmem_ptr + 16;                        // [128] {int z0, float wz1}
+    static constexpr int total = ztab + TC_M * 8;
+};
+static_assert(TcSmem::total + 1024 <= 227 * 1024, "shared memory budget");
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// K-major SWIZZLE_128B operand descriptor: 8-row groups 1024 B apart (SBO), 16-byte units, version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+        "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// byte offset of element (row r, K-column c) inside one [rows x 64] bf16 K-major SWIZZLE_128B tile
+__host__ __device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 3) ^ (r & 7)) & 7) << 4) + (c & 7) * 2);
+}
+
+// split two fp32 into bf16x2 hi and bf16x2 lo words (element 0 in the low half: ascending K order in memory)
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+struct TcParams {
+    const float* U;         // LATTICE: [B,G,G,G,256] hoisted grid ; ROWS: [R,256] H1 rows (row stride ldx)
+    int64_t ldx;
+    int B, G, Q;
+    int64_t R;              // ROWS: number of rows
+    const float* bn1_scale; // LATTICE only
+    const float* bn1_shift;
+    const uint8_t* w2_packed;  // [4 chunks][hi,lo][32 KB]
+    const float* b2;        // [256]
+    const float* w3s;       // [COUT][256] = W3 * bn2_scale
+    const float* tail;      // [COUT][4] = {c0 = sum(bn2_shift*W3) + b3, bn3_scale, bn3_shift, 0}
+    float* out;             // [rows, COUT]
+    int64_t num_tiles;
+};
+
+template <int COUT, bool LATTICE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+decode_tc_kernel(const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B atoms need a 1024-byte aligned base
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const uint32_t bar0 = sbase + TcSmem::bars;
+    auto a_full = [&](int c) { return bar0 + 8 * c; };
+    auto a_empty = [&](int c) { return bar0 + 8 * (4 + c); };
+    auto b_full = [&](int s) { return bar0 + 8 * (8 + s); };
+    auto b_empty = [&](int s) { return bar0 + 8 * (8 + B_SLOTS + s); };
+    auto d_full = [&](int s) { return bar0 + 8 * (8 + 2 * B_SLOTS + s); };
+    auto d_empty = [&](int s) { return bar0 + 8 * (8 + 2 * B_SLOTS + 2 + s); };
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + TcSmem::tmem_ptr);
+
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < 4; ++c) { mbar_init(a_full(c), 32); mbar_init(a_empty(c), 1); }
+        for (int s = 0; s < B_SLOTS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (LATTICE && threadIdx.x < TC_M) {
+        // per-row blend along D (independent of the tile): same fp32 arithmetic as gnb_trilinear_sample_grid
+        const int k = threadIdx.x;
+        const float s = __fdiv_rn(1.0f, (float)(p.Q - 1));
+        const float g = __fsub_rn(__fmul_rn(2.0f, __fmul_rn((float)k, s)), 1.0f);
+        float iz = ((g + 1.f) / 2.f) * (float)(p.G - 1);
+        iz = fminf((float)(p.G - 1), fmaxf(iz, 0.f));
+        const float fz = floorf(iz);
+        int* zt = reinterpret_cast<int*>(smem + TcSmem::ztab);
+        zt[2 * k] = (int)fz;
+        reinterpret_cast<float*>(zt)[2 * k + 1] = iz - fz;
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + TcSmem::tmem_ptr), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp < 4) {
+        // =========================== A producers ===========================
+        const int c0 = warp * TC_KCHUNK + 2 * lane;  // this thread's two channels
+        uint8_t* a_hi = smem + TcSmem::a_hi + warp * A_CHUNK_BYTES;
+        uint8_t* a_lo = smem + TcSmem::a_lo + warp * A_CHUNK_BYTES;
+        float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
+        if (LATTICE) { sc0 = p.bn1_scale[c0]; sc1 = p.bn1_scale[c0 + 1]; sh0 = p.bn1_shift[c0]; sh1 = p.bn1_shift[c0 + 1]; }
+        const int* zt = reinterpret_cast<const int*>(smem + TcSmem::ztab);
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            mbar_wait(a_empty(warp), (it & 1) ^ 1);
+            if (LATTICE) {
+                const int G = p.G, Q = p.Q;
+                const int j = (int)(tile % Q), i = (int)((tile / Q) % Q), b = (int)(tile / ((int64_t)Q * Q));
+                const float s = __fdiv_rn(1.0f, (float)(Q - 1));
+                // query coordinate 0 (i) -> W axis, coordinate 1 (j) -> H axis (un-flipped grid_sample convention)
+                const float gx = __fsub_rn(__fmul_rn(2.0f, __fmul_rn((float)i, s)), 1.0f);
+                const float gy = __fsub_rn(__fmul_rn(2.0f, __fmul_rn((float)j, s)), 1.0f);
+                float ix = fminf((float)(G - 1), fmaxf(((gx + 1.f) / 2.f) * (float)(G - 1), 0.f));
+                float iy = fminf((float)(G - 1), fmaxf(((gy + 1.f) / 2.f) * (float)(G - 1), 0.f));
+                const float fx = floorf(ix), fy = floorf(iy);
+                const int x0 = (int)fx, y0 = (int)fy;
+                const int x1 = x0 + 1 < G ? x0 + 1 : G - 1, y1 = y0 + 1 < G ? y0 + 1 : G - 1;
+                const float wx1 = ix - fx, wy1 = iy - fy, wx0 = (fx + 1.f) - ix, wy0 = (fy + 1.f) - iy;
+                const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+                const float* base = p.U + (int64_t)b * G * G * G * TC_K + c0;
+                const int64_t o00 = ((int64_t)y0 * G + x0) * TC_K, o10 = ((int64_t)y0 * G + x1) * TC_K;
+                const int64_t o01 = ((int64_t)y1 * G + x0) * TC_K, o11 = ((int64_t)y1 * G + x1) * TC_K;
+                const int64_t sd = (int64_t)G * G * TC_K;
+                auto slice = [&](int d) -> float2 {
+                    const float* q = base + d * sd;
+                    const float2 v00 = __ldg(reinterpret_cast<const float2*>(q + o00));
+                    const float2 v10 = __ldg(reinterpret_cast<const float2*>(q + o10));
+                    const float2 v01 = __ldg(reinterpret_cast<const float2*>(q + o01));
+                    const float2 v11 = __ldg(reinterpret_cast<const float2*>(q + o11));
+                    float2 r;
+                    r.x = v00.x * w00 + v10.x * w10 + v01.x * w01 + v11.x * w11;
+                    r.y = v00.y * w00 + v10.y * w10 + v01.y * w01 + v11.y * w11;
+                    return r;
+                };
+                float2 p0 = slice(0);
+                float2 p1 = slice(G > 1 ? 1 : 0);
+                int k = 0;
+                for (int d = 0; d < G; ++d) {
+                    // prefetch the slice after next while the rows of this D-cell are produced
+                    float2 p2 = p1;
+                    if (d + 2 < G) p2 = slice(d + 2);
+                    while (k < TC_M && zt[2 * k] == d) {
+                        const float wz1 = reinterpret_cast<const float*>(zt)[2 * k + 1];
+                        const float wz0 = 1.0f - wz1;
+                        float h0 = p0.x * wz0 + p1.x * wz1;
+                        float h1 = p0.y * wz0 + p1.y * wz1;
+                        h0 = fmaxf(h0, 0.f) * sc0 + sh0;
+                        h1 = fmaxf(h1, 0.f) * sc1 + sh1;
+                        uint32_t hi, lo;
+                        split_bf16x2(h0, h1, hi, lo);
+                        const uint32_t off = sw128_offset(k, 2 * lane);
+                        *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
+                        *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
+                        ++k;
+                    }
+                    p0 = p1;
+                    p1 = p2;
+                }
+            } else {
+                const int64_t r0 = tile * TC_M;
+#pragma unroll 4
+                for (int k = 0; k < TC_M; ++k) {
+                    float2 v = make_float2(0.f, 0.f);
+                    if (r0 + k < p.R) v = __ldg(reinterpret_cast<const float2*>(p.U + (r0 + k) * p.ldx + c0));
+                    uint32_t hi, lo;
+                    split_bf16x2(v.x, v.y, hi, lo);
+                    const uint32_t off = sw128_offset(k, 2 * lane);
+                    *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
+                    *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
+                }
+            }
+            fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+            mbar_arrive(a_full(warp));
+        }
+    } else if (warp < 8) {
+        // =========================== epilogue ===========================
+        const int q = warp - 4;  // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        float c_tail[COUT], bn3s[COUT], bn3h[COUT];
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) { c_tail[o] = p.tail[o * 4]; bn3s[o] = p.tail[o * 4 + 1]; bn3h[o] = p.tail[o * 4 + 2]; }
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int db = it & 1;
+            mbar_wait(d_full(db), (it >> 1) & 1);
+            tc_fence_after();
+            float dot[COUT];
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) dot[o] = 0.f;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(db * TC_N);
+#pragma unroll 1
+            for (int n0 = 0; n0 < TC_N; n0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(taddr + n0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    const float v = fmaxf(__uint_as_float(r[t]) + __ldg(p.b2 + n0 + t), 0.f);
+#pragma unroll
+                    for (int o = 0; o < COUT; ++o) dot[o] = fmaf(v, __ldg(p.w3s + o * TC_N + n0 + t), dot[o]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(d_empty(db));  // accumulator buffer drained: MMA of tile it+2 may overwrite it
+            const int64_t grow = tile * TC_M + row;
+            if (LATTICE || grow < p.R) {
+#pragma unroll
+                for (int o = 0; o < COUT; ++o)
+                    p.out[grow * COUT + o] = fmaxf(dot[o] + c_tail[o], 0.f) * bn3s[o] + bn3h[o];
+            }
+        }
+    } else if (warp == 8) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            int it = 0;
+            uint32_t piece = 0;
+            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int db = it & 1;
+                mbar_wait(d_empty(db), ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(db * TC_N);
+                for (int c = 0; c < TC_NCHUNK; ++c) {
+                    mbar_wait(a_full(c), it & 1);
+                    const uint32_t ahi = sbase + TcSmem::a_hi + c * A_CHUNK_BYTES;
+                    const uint32_t alo = sbase + TcSmem::a_lo + c * A_CHUNK_BYTES;
+                    // piece 0: W2_hi chunk c -> A_hi*B_hi and A_lo*B_hi
+                    {
+                        const int slot = piece % B_SLOTS;
+                        mbar_wait(b_full(slot), (piece / B_SLOTS) & 1);
+                        tc_fence_after();
+                        const uint32_t bs = sbase + TcSmem::b_ring + slot * B_PIECE_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < TC_KCHUNK / 16; ++kk)
+                            umma_f16(d_tmem, umma_desc(ahi + kk * 32), umma_desc(bs + kk * 32), TC_IDESC, (c | kk) != 0);
+#pragma unroll
+                        for (int kk = 0; kk < TC_KCHUNK / 16; ++kk)
+                            umma_f16(d_tmem, umma_desc(alo + kk * 32), umma_desc(bs + kk * 32), TC_IDESC, 1);
+                        umma_commit(b_empty(slot));
+                        ++piece;
+                    }
+                    // piece 1: W2_lo chunk c -> A_hi*B_lo
+                    {
+                        const int slot = piece % B_SLOTS;
+                        mbar_wait(b_full(slot), (piece / B_SLOTS) & 1);
+                        tc_fence_after();
+                        const uint32_t bs = sbase + TcSmem::b_ring + slot * B_PIECE_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < TC_KCHUNK / 16; ++kk)
+                            umma_f16(d_tmem, umma_desc(ahi + kk * 32), umma_desc(bs + kk * 32), TC_IDESC, 1);
+                        umma_commit(b_empty(slot));
+                        umma_commit(a_empty(c));  // every MMA that reads A chunk c of this tile has been issued
+                        ++piece;
+                    }
+                }
+                umma_commit(d_full(db));
+            }
+        }
+    } else {
+        // =========================== B loader ===========================
+        if (lane == 0) {
+            uint32_t piece = 0;
+            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                for (int pc = 0; pc < 2 * TC_NCHUNK; ++pc, ++piece) {
+                    const int slot = piece % B_SLOTS;
+                    mbar_wait(b_empty(slot), ((piece / B_SLOTS) & 1) ^ 1);
+                    mbar_expect_tx(b_full(slot), B_PIECE_BYTES);
+                    bulk_g2s(sbase + TcSmem::b_ring + slot * B_PIECE_BYTES, p.w2_packed + (size_t)pc * B_PIECE_BYTES,
+                             B_PIECE_BYTES, b_full(slot));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// W [N=256, K=256] fp32 -> [4 K-chunks][hi, lo] 32 KB shared-memory images (bf16, K-major, SWIZZLE_128B)
+__global__ void pack_bf16_split_kernel(const float* __restrict__ W, uint8_t* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= TC_N * TC_K) return;
+    const int n = t / TC_K, k = t % TC_K;
+    const float w = W[t];
+    const __nv_bfloat16 h = __float2bfloat16_rn(w);
+    const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+    const int c = k / TC_KCHUNK, kc = k % TC_KCHUNK;
+    const uint32_t off = sw128_offset(n, kc);
+    *reinterpret_cast<__nv_bfloat16*>(out + (size_t)(2 * c) * B_PIECE_BYTES + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(out + (size_t)(2 * c + 1) * B_PIECE_BYTES + off) = l;
+}
+
+// w3s[o][n] = W3[o][n]*bn2_scale[n];  tail[o] = {sum_n bn2_shift[n]*W3[o][n] + b3[o], bn3_scale[o], bn3_shift[o], 0}
+__global__ void fold_tail_kernel(const float* __restrict__ W3, const float* __restrict__ b3, const float* __restrict__ s2,
+                                 const float* __restrict__ h2, const float* __restrict__ s3, const float* __restrict__ h3,
+                                 int cout, float* __restrict__ w3s, float* __restrict__ tail) {
+    const int o = blockIdx.x;
+    __shared__ float red[TC_N];
+    const int n = threadIdx.x;
+    const float w = W3[o * TC_N + n];
+    w3s[o * TC_N + n] = w * (s2 ? s2[n] : 1.f);
+    red[n] = (h2 ? h2[n] : 0.f) * w;
+    __syncthreads();
+    for (int s = TC_N / 2; s > 0; s >>= 1) {
+        if (n < s) red[n] += red[n + s];
+        __syncthreads();
+    }
+    if (n == 0) {
+        tail[o * 4 + 0] = red[0] + (b3 ? b3[o] : 0.f);
+        tail[o * 4 + 1] = s3 ? s3[o] : 1.f;
+        tail[o * 4 + 2] = h3 ? h3[o] : 0.f;
+        tail[o * 4 + 3] = 0.f;
+    }
+}
+
+template <int COUT, bool LATTICE>
+static int32_t launch_decode_tc(const TcParams& p, cudaStream_t st) {
+    const int smem = TcSmem::total + 1024;
+    GNB_CUDA(cudaFuncSetAttribute(decode_tc_kernel<COUT, LATTICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int grid = sm_count();
+    if ((int64_t)grid > p.num_tiles) grid = (int)p.num_tiles;
+    decode_tc_kernel<COUT, LATTICE><<<grid, TC_THREADS, smem, st>>>(p);
+    return check_launch("gnb_decode_tc");
+}
+
+}  // namespace gnb
+
+using namespace gnb;
+
+extern "C" {
+
+int32_t gnb_pack_bf16_split(const float* W, int32_t N, int32_t K, void* packed, void* stream) {
+    GNB_REQUIRE(W && packed, "gnb_pack_bf16_split: null pointer");
+    GNB_REQUIRE(N == TC_N && K == TC_K, "gnb_pack_bf16_split: only 256x256 weights are supported (got %dx%d)", N, K);
+    pack_bf16_split_kernel<<<TC_N * TC_K / 256, 256, 0, as_stream(stream)>>>(W, reinterpret_cast<uint8_t*>(packed));
+    return check_launch("gnb_pack_bf16_split");
+}
+
+int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t Q, int64_t R, const float* bn1_scale,
+                      const float* bn1_shift, const void* w2_packed, const float* b2, const float* bn2_scale,
+                      const float* bn2_shift, const float* W3, const float* b3, const float* bn3_scale,
+                      const float* bn3_shift, int32_t Cout, float* scratch, float* out, void* stream) {
+    GNB_REQUIRE(U && w2_packed && b2 && W3 && scratch && out, "gnb_decode_tc: null pointer");
+    GNB_REQUIRE(Cout >= 1 && Cout <= 3, "gnb_decode_tc: Cout must be 1..3 (got %d)", Cout);
+    const bool lattice = Q > 0;
+    if (lattice) {
+        GNB_REQUIRE(Q == TC_M, "gnb_decode_tc: the lattice kernel needs volume_size == 128 (one lattice line per tile)");
+        GNB_REQUIRE(B > 0 && G >= 2 && bn1_scale && bn1_shift, "gnb_decode_tc: bad lattice arguments");
+    } else {
+        GNB_REQUIRE(R >= 0 && ldx >= TC_K && (ldx % 2) == 0, "gnb_decode_tc: bad row matrix");
+        if (R == 0) return GNB_OK;
+    }
+    cudaStream_t st = as_stream(stream);
+    float* w3s = scratch;
+    float* tail = scratch + 3 * TC_N;
+    fold_tail_kernel<<<Cout, TC_N, 0, st>>>(W3, b3, bn2_scale, bn2_shift, bn3_scale, bn3_shift, Cout, w3s, tail);
+    TcParams p;
+    p.U = U; p.ldx = ldx; p.B = B; p.G = G; p.Q = Q; p.R = R;
+    p.bn1_scale = bn1_scale; p.bn1_shift = bn1_shift;
+    p.w2_packed = reinterpret_cast<const uint8_t*>(w2_packed);
+    p.b2 = b2; p.w3s = w3s; p.tail = tail; p.out = out;
+    p.num_tiles = lattice ? (int64_t)B * Q * Q : ceil_div<int64_t>(R, TC_M);
+    if (lattice) {
+        if (Cout == 1) return launch_decode_tc<1, true>(p, st);
+        if (Cout == 2) return launch_decode_tc<2, true>(p, st);
+        return launch_decode_tc<3, true>(p, st);
+    }
+    if (Cout == 1) return launch_decode_tc<1, false>(p, st);
+    if (Cout == 2) return launch_decode_tc<2, false>(p, st);
+    return launch_decode_tc<3, false>(p, st);
+}
+
+}  // extern "C"

@@ -339,3 +339,39 @@ def marching_cubes(volume: torch.Tensor, level: float, spacing=(1.0, 1.0, 1.0), 
               1 if gradient_direction == "ascent" else 0, _ptr(ggm), ws.data_ptr(), verts.data_ptr(), faces.data_ptr(),
               normals.data_ptr(), values.data_ptr(), _ptr(ggm_at), _stream())
     return verts, faces, normals, values, ggm_at
+
+
+# ---------------------------------------------------------------------------------------------- tensor-core decoder tail
+def pack_bf16_split(weight: torch.Tensor) -> torch.Tensor:
+    """[256,256] fp32 weight -> bf16 hi/lo shared-memory images for ``decode_tc`` (uint8[N*K*4])."""
+    weight = _req(weight, torch.float32, "weight")
+    N, K = weight.shape
+    packed = torch.empty(N * K * 4, dtype=torch.uint8, device=weight.device)
+    _lib.call("gnb_pack_bf16_split", weight.data_ptr(), N, K, packed.data_ptr(), _stream())
+    return packed
+
+
+def decode_tc(w2_packed, b2, bn2, W3, b3, bn3, *, U=None, Q=0, bn1=None, X=None, out=None) -> torch.Tensor:
+    """Tensor-core decoder tail (``gnb_decode_tc``).  Lattice mode: ``U`` [B,G,G,G,256], ``Q`` = 128, ``bn1`` =
+    (scale, shift) -> [B, Q^3, Cout].  Row mode: ``X`` [R,256] -> [R, Cout].  bn2 / bn3 are (scale, shift) or None."""
+    Cout = W3.shape[0]
+    dev = W3.device
+    scratch = torch.empty(1024, dtype=torch.float32, device=dev)
+    s2, h2 = bn2 if bn2 is not None else (None, None)
+    s3, h3 = bn3 if bn3 is not None else (None, None)
+    if U is not None:
+        B, G = U.shape[0], U.shape[1]
+        assert U.is_contiguous() and U.shape[-1] == 256
+        if out is None:
+            out = torch.empty((B, Q ** 3, Cout), dtype=torch.float32, device=dev)
+        _lib.call("gnb_decode_tc", U.data_ptr(), 0, B, G, int(Q), 0, bn1[0].data_ptr(), bn1[1].data_ptr(),
+                  w2_packed.data_ptr(), b2.data_ptr(), _ptr(s2), _ptr(h2), W3.data_ptr(), _ptr(b3), _ptr(s3), _ptr(h3),
+                  Cout, scratch.data_ptr(), out.data_ptr(), _stream())
+        return out
+    X, ldx = _rows(X, "X")
+    R = X.shape[0]
+    if out is None:
+        out = torch.empty((R, Cout), dtype=torch.float32, device=dev)
+    _lib.call("gnb_decode_tc", X.data_ptr(), ldx, 0, 0, 0, R, None, None, w2_packed.data_ptr(), b2.data_ptr(), _ptr(s2),
+              _ptr(h2), W3.data_ptr(), _ptr(b3), _ptr(s3), _ptr(h3), Cout, scratch.data_ptr(), out.data_ptr(), _stream())
+    return out

@@ -186,7 +186,30 @@ class ImplicitWNFDecoder(nn.Module):
         u = ops.linear(features_grid_ndhwc.reshape(-1, C), lin.weight, lin.bias)
         return u.view(B, D, H, W, -1)
 
+    # ---- tensor-core tail (tcgen05): available for the shipped shape [C, 256, 256, Cout<=3] with BatchNorm --------
+    use_tensor_cores = True
+
+    def _tc_ready(self) -> bool:
+        from .components.mlp import _Block
+        if not self.use_tensor_cores or _Block.calibrating or len(self.mlp) != 3:
+            return False
+        l2, l3 = self.mlp[1][0], self.mlp[2][0]
+        return (l2.in_features == 256 and l2.out_features == 256 and l3.out_features <= 3
+                and all(len(b) > 2 for b in self.mlp))
+
+    def _tc_args(self):
+        l2, l3 = self.mlp[1][0], self.mlp[2][0]
+        key = (l2.weight._version, l2.weight.data_ptr())
+        cached = getattr(self, "_gnb_w2_packed", None)
+        if cached is None or cached[0] != key:
+            cached = (key, ops.pack_bf16_split(l2.weight))
+            self._gnb_w2_packed = cached
+        return (cached[1], l2.bias, self.mlp[1][2].folded_affine(), l3.weight, l3.bias, self.mlp[2][2].folded_affine())
+
     def _tail(self, h: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self._tc_ready():
+            with profiling.tag(f"{self.profile_tag}_tc"):
+                return ops.decode_tc(*self._tc_args(), X=h, out=out)
         blocks = list(self.mlp)[1:]
         for i, block in enumerate(blocks):
             with profiling.tag(f"{self.profile_tag}_l{i + 2}"):
@@ -289,6 +312,12 @@ class ConvImplicitWNFPipeline(nn.Module):
         Q = int(volume_size)
         u = self.volume_decoder.hoisted(vol)
         total = Q ** 3
+        dec = self.volume_decoder
+        if Q == 128 and dec._tc_ready() and dec.mlp[2][0].out_features == 1:
+            # fused lattice kernel: interpolation + BN1 + Linear2/BN2 + Linear3/BN3 in one launch for the whole batch
+            with profiling.tag("decode_tc"):
+                out = ops.decode_tc(*dec._tc_args(), U=u, Q=Q, bn1=dec.mlp[0][2].folded_affine())
+            return out.view(B, Q, Q, Q)
         out = torch.empty((B, total), dtype=torch.float32, device=vol.device)
         for b in range(B):
             for m0 in range(0, total, rows_per_chunk):

@@ -1,0 +1,84 @@
+"""Tensor-core (tcgen05) decoder tail vs fp32 references: the bf16 hi/lo split must keep the result within the 1e-4
+parity bound; lattice mode is checked against the oracle at the full BASELINE size (128^3)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from garmentnets_b200 import synthetic
+from oracle import nets as ON
+
+TOL = 1e-4
+
+
+def _decoder(dev, cout, seed):
+    from garmentnets_b200.pipeline import ImplicitWNFDecoder
+    torch.manual_seed(seed)
+    dec = synthetic.randomize_(ImplicitWNFDecoder(nn_channels=(128, 256, 256, cout)), seed + 1).eval().requires_grad_(False)
+    return dec.to(dev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,cout", [(1, 1), (127, 3), (128, 1), (1000, 3), (40000, 2), (148 * 128 * 3 + 5, 1)])
+def test_row_mode_matches_fp32(dev, R, cout):
+    from garmentnets_b200 import ops
+    dec = _decoder(dev, cout, 10 + cout)
+    g = torch.Generator().manual_seed(R)
+    X = torch.randn(R, 256, generator=g) * 1.5
+    sd = {k: v.cpu() for k, v in dec.state_dict().items()}
+    # reference: blocks 2 and 3 of the MLP in fp64 (what fp32 approximates), and in fp32 (the oracle)
+    ref32 = X
+    ref64 = X.double()
+    for l in (1, 2):
+        w, b = sd[f"mlp.{l}.0.weight"], sd[f"mlp.{l}.0.bias"]
+        ref32 = F.batch_norm(F.relu(F.linear(ref32, w, b)), sd[f"mlp.{l}.2.running_mean"], sd[f"mlp.{l}.2.running_var"],
+                             sd[f"mlp.{l}.2.weight"], sd[f"mlp.{l}.2.bias"], False, 0.0, 1e-5)
+        ref64 = F.batch_norm(F.relu(F.linear(ref64, w.double(), b.double())), sd[f"mlp.{l}.2.running_mean"].double(),
+                             sd[f"mlp.{l}.2.running_var"].double(), sd[f"mlp.{l}.2.weight"].double(),
+                             sd[f"mlp.{l}.2.bias"].double(), False, 0.0, 1e-5)
+    got = ops.decode_tc(*dec._tc_args(), X=X.to(dev)).cpu()
+    assert got.shape == (R, cout)
+    err32 = (got - ref32).abs().max().item()
+    err64 = (got.double() - ref64).abs().max().item()
+    assert err32 < TOL and err64 < TOL, (err32, err64)
+    # strided input rows (an [R, 300] buffer)
+    wide = torch.zeros(R, 300, device=dev)
+    wide[:, :256] = X.to(dev)
+    got2 = ops.decode_tc(*dec._tc_args(), X=wide[:, :256]).cpu()
+    assert torch.equal(got, got2)
+
+
+@pytest.mark.gpu
+def test_tail_dispatch_equals_fp32_path(dev):
+    dec = _decoder(dev, 3, 5)
+    g = torch.Generator().manual_seed(0)
+    fg = torch.randn(2, 128, 6, 6, 6, generator=g).to(dev)
+    q = torch.rand(2, 333, 3, generator=g).to(dev)
+    dec.use_tensor_cores = True
+    y_tc = dec(fg, q)
+    dec.use_tensor_cores = False
+    y_32 = dec(fg, q)
+    assert (y_tc - y_32).abs().max().item() < TOL
+    ref = ON.implicit_decoder({k: v.cpu() for k, v in dec.state_dict().items()}, "", fg.cpu(), q.cpu())
+    assert (y_tc.cpu() - ref).abs().max().item() < TOL
+
+
+@pytest.mark.gpu
+def test_lattice_mode_full_size_vs_oracle(dev):
+    """128^3 lattice (BASELINE size), one volume: fused tcgen05 kernel vs the oracle's chunked grid_sample + MLP."""
+    from garmentnets_b200 import ops
+    from garmentnets_b200.pipeline import ConvImplicitWNFPipeline
+    torch.manual_seed(1)
+    model = synthetic.randomize_(ConvImplicitWNFPipeline.from_hparams(synthetic.HPARAMS), 2).eval().requires_grad_(False).to(dev)
+    g = torch.Generator().manual_seed(3)
+    fvol = (torch.randn(2, 128, 32, 32, 32, generator=g) * 0.7).to(dev)
+    model.volume_decoder.use_tensor_cores = True
+    wnf_tc = model.dense_decode(fvol, 128)
+    model.volume_decoder.use_tensor_cores = False
+    wnf_32 = model.dense_decode(fvol[1:2], 128)
+    assert wnf_tc.shape == (2, 128, 128, 128)
+    assert (wnf_tc[1] - wnf_32[0]).abs().max().item() < TOL
+    sd = {k: v.cpu() for k, v in model.state_dict().items()}
+    ref = ON.dense_decode(sd, "volume_decoder.", fvol[:1].cpu().numpy(), 128, 64)
+    err = (wnf_tc[0].cpu() - ref).abs().max().item()
+    assert err < TOL, err
