@@ -8,22 +8,23 @@
 // and writes only y (4*Cout bytes per query); H1 / H2 never touch HBM.
 //
 // Precision: the reference runs fp32 and the parity bar is 1e-4 max-abs, which a single bf16/tf32 pass cannot meet
-// over K = 256.  Both operands are split into bf16 hi + lo (a = hi + lo + O(2^-17 a)) and the product is formed as
-// hi*hi + lo*hi + hi*lo with fp32 accumulation: three kind::f16 MMAs per K-step, ~2^-16 relative error per product.
+// over K = 256.  Both operands are split into fp16 hi + lo (a = hi + lo + O(2^-22 a)) and the product is formed as
+// hi*hi + lo*hi + hi*lo with fp32 accumulation: three kind::f16 MMAs per K-step, ~2^-21 relative error per product
+// (fp32-level), at the cost of 3x the tensor work.
 //
 // Pipeline (mbarrier producer/consumer rings, no __syncthreads in steady state):
-//   warps 0-3  A producers: warp w builds K-chunk w (64 channels) of the 128-row A tile, bf16 hi/lo, directly in the
+//   warps 0-3  A producers: warp w builds K-chunk w (64 channels) of the 128-row A tile, fp16 hi/lo, directly in the
 //              UMMA canonical K-major SWIZZLE_128B layout in shared memory (generic-proxy stores + fence.proxy.async).
 //              LATTICE: the tile is one lattice line (i,j,0..127): bilinear blend of the four (H,W) neighbours per
 //              D-slice held in registers, then a linear blend along D per row -- 4 coalesced 8-byte loads per slice.
 //              ROWS: the tile is 128 rows of a precomputed fp32 H1 matrix (arbitrary query sets, surface decoder).
-//   warp 9     B loader: W2 is pre-packed (gnb_pack_bf16_split) into 32 KB shared-memory images (K-chunk x {hi,lo});
+//   warp 9     B loader: W2 is pre-packed (gnb_pack_f16_split) into 32 KB shared-memory images (K-chunk x {hi,lo});
 //              cp.async.bulk streams them from L2 through a 3-slot ring (complete_tx on an mbarrier).
 //   warp 8     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=256, K=16) and tcgen05.commit.
 //   warps 4-7  epilogue: tcgen05.ld of the accumulator rows (lane = row), bias/ReLU/BN2 folded with W3, store.
 // TMEM: 2 x 256 columns (accumulator double buffer: epilogue(t) overlaps MMA(t+1)); smem: A 128 KB + B ring 96 KB.
 #include "common.cuh"
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace gnb {
 
@@ -32,7 +33,8 @@ constexpr int A_CHUNK_BYTES = TC_M * TC_KCHUNK * 2;      // 16 KB (one precision
 constexpr int B_PIECE_BYTES = TC_N * TC_KCHUNK * 2;      // 32 KB
 constexpr int B_SLOTS = 3;
 constexpr int TC_THREADS = 320;
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+// instruction descriptor: D = F32 (bits 4-5 = 1), A = B = F16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 struct TcSmem {
     // offsets inside the dynamic shared memory block (1024-byte aligned base)
@@ -108,16 +110,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// byte offset of element (row r, K-column c) inside one [rows x 64] bf16 K-major SWIZZLE_128B tile
+// byte offset of element (row r, K-column c) inside one [rows x 64] 16-bit K-major SWIZZLE_128B tile
 __host__ __device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 3) ^ (r & 7)) & 7) << 4) + (c & 7) * 2);
 }
 
-// split two fp32 into bf16x2 hi and bf16x2 lo words (element 0 in the low half: ascending K order in memory)
-__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-    const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+// split two fp32 into half2 hi and half2 lo words (element 0 in the low half: ascending K order in memory).
+// fp16 carries 11 significant bits, so hi + lo represents 22 bits of the fp32 value; inputs are clamped to the fp16
+// range (activations / weights of this network are O(1e2) at most).
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    x0 = fminf(fmaxf(x0, -65504.f), 65504.f);
+    x1 = fminf(fmaxf(x1, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -211,40 +217,61 @@ decode_tc_kernel(const TcParams p) {
                 const int64_t o00 = ((int64_t)y0 * G + x0) * TC_K, o10 = ((int64_t)y0 * G + x1) * TC_K;
                 const int64_t o01 = ((int64_t)y1 * G + x0) * TC_K, o11 = ((int64_t)y1 * G + x1) * TC_K;
                 const int64_t sd = (int64_t)G * G * TC_K;
-                auto slice = [&](int d) -> float2 {
-                    const float* q = base + d * sd;
-                    const float2 v00 = __ldg(reinterpret_cast<const float2*>(q + o00));
-                    const float2 v10 = __ldg(reinterpret_cast<const float2*>(q + o10));
-                    const float2 v01 = __ldg(reinterpret_cast<const float2*>(q + o01));
-                    const float2 v11 = __ldg(reinterpret_cast<const float2*>(q + o11));
+                // Slices are fetched NG at a time (4 x NG independent 8-byte loads in flight per thread) and the loads of
+                // the next group are issued before the rows of the current group are produced: the L2 latency of the
+                // gather is paid ~G/NG times per tile instead of G times.
+                constexpr int NG = 8;
+                float2 v[NG][4];
+                auto issue = [&](int dfirst) {
+#pragma unroll
+                    for (int s2 = 0; s2 < NG; ++s2) {
+                        int dd = dfirst + s2;
+                        dd = dd < G ? dd : G - 1;
+                        const float* q = base + dd * sd;
+                        v[s2][0] = __ldg(reinterpret_cast<const float2*>(q + o00));
+                        v[s2][1] = __ldg(reinterpret_cast<const float2*>(q + o10));
+                        v[s2][2] = __ldg(reinterpret_cast<const float2*>(q + o01));
+                        v[s2][3] = __ldg(reinterpret_cast<const float2*>(q + o11));
+                    }
+                };
+                auto blend = [&](const float2 (&c4)[4]) -> float2 {
                     float2 r;
-                    r.x = v00.x * w00 + v10.x * w10 + v01.x * w01 + v11.x * w11;
-                    r.y = v00.y * w00 + v10.y * w10 + v01.y * w01 + v11.y * w11;
+                    r.x = c4[0].x * w00 + c4[1].x * w10 + c4[2].x * w01 + c4[3].x * w11;
+                    r.y = c4[0].y * w00 + c4[1].y * w10 + c4[2].y * w01 + c4[3].y * w11;
                     return r;
                 };
-                float2 p0 = slice(0);
-                float2 p1 = slice(G > 1 ? 1 : 0);
+                float2 pc[NG + 1];
+                {
+                    const float* q = base;
+                    const float2 c4[4] = {__ldg(reinterpret_cast<const float2*>(q + o00)), __ldg(reinterpret_cast<const float2*>(q + o10)),
+                                          __ldg(reinterpret_cast<const float2*>(q + o01)), __ldg(reinterpret_cast<const float2*>(q + o11))};
+                    issue(1);
+                    pc[0] = blend(c4);
+                }
                 int k = 0;
-                for (int d = 0; d < G; ++d) {
-                    // prefetch the slice after next while the rows of this D-cell are produced
-                    float2 p2 = p1;
-                    if (d + 2 < G) p2 = slice(d + 2);
-                    while (k < TC_M && zt[2 * k] == d) {
-                        const float wz1 = reinterpret_cast<const float*>(zt)[2 * k + 1];
-                        const float wz0 = 1.0f - wz1;
-                        float h0 = p0.x * wz0 + p1.x * wz1;
-                        float h1 = p0.y * wz0 + p1.y * wz1;
-                        h0 = fmaxf(h0, 0.f) * sc0 + sh0;
-                        h1 = fmaxf(h1, 0.f) * sc1 + sh1;
-                        uint32_t hi, lo;
-                        split_bf16x2(h0, h1, hi, lo);
-                        const uint32_t off = sw128_offset(k, 2 * lane);
-                        *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
-                        *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
-                        ++k;
+                for (int d0 = 0; d0 < G; d0 += NG) {
+#pragma unroll
+                    for (int s2 = 0; s2 < NG; ++s2) pc[s2 + 1] = blend(v[s2]);   // P(d0+1 .. d0+NG)
+                    if (d0 + NG < G) issue(d0 + NG + 1);                        // next group's loads fly during the rows
+#pragma unroll
+                    for (int s2 = 0; s2 < NG; ++s2) {
+                        const int d = d0 + s2;
+                        while (k < TC_M && zt[2 * k] == d) {
+                            const float wz1 = reinterpret_cast<const float*>(zt)[2 * k + 1];
+                            const float wz0 = 1.0f - wz1;
+                            float h0 = pc[s2].x * wz0 + pc[s2 + 1].x * wz1;
+                            float h1 = pc[s2].y * wz0 + pc[s2 + 1].y * wz1;
+                            h0 = fmaxf(h0, 0.f) * sc0 + sh0;
+                            h1 = fmaxf(h1, 0.f) * sc1 + sh1;
+                            uint32_t hi, lo;
+                            split_f16x2(h0, h1, hi, lo);
+                            const uint32_t off = sw128_offset(k, 2 * lane);
+                            *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
+                            *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
+                            ++k;
+                        }
                     }
-                    p0 = p1;
-                    p1 = p2;
+                    pc[0] = pc[NG];
                 }
             } else {
                 const int64_t r0 = tile * TC_M;
@@ -253,7 +280,7 @@ decode_tc_kernel(const TcParams p) {
                     float2 v = make_float2(0.f, 0.f);
                     if (r0 + k < p.R) v = __ldg(reinterpret_cast<const float2*>(p.U + (r0 + k) * p.ldx + c0));
                     uint32_t hi, lo;
-                    split_bf16x2(v.x, v.y, hi, lo);
+                    split_f16x2(v.x, v.y, hi, lo);
                     const uint32_t off = sw128_offset(k, 2 * lane);
                     *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
                     *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
@@ -284,10 +311,15 @@ decode_tc_kernel(const TcParams p) {
                 tmem_ld32(taddr + n0, r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                    const float v = fmaxf(__uint_as_float(r[t]) + __ldg(p.b2 + n0 + t), 0.f);
+                for (int t = 0; t < 32; t += 4) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + n0 + t));
+                    const float v0 = fmaxf(__uint_as_float(r[t]) + bb.x, 0.f), v1 = fmaxf(__uint_as_float(r[t + 1]) + bb.y, 0.f);
+                    const float v2 = fmaxf(__uint_as_float(r[t + 2]) + bb.z, 0.f), v3 = fmaxf(__uint_as_float(r[t + 3]) + bb.w, 0.f);
 #pragma unroll
-                    for (int o = 0; o < COUT; ++o) dot[o] = fmaf(v, __ldg(p.w3s + o * TC_N + n0 + t), dot[o]);
+                    for (int o = 0; o < COUT; ++o) {
+                        const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w3s + o * TC_N + n0 + t));
+                        dot[o] = fmaf(v3, ww.w, fmaf(v2, ww.z, fmaf(v1, ww.y, fmaf(v0, ww.x, dot[o]))));
+                    }
                 }
             }
             tc_fence_before();
@@ -369,18 +401,18 @@ decode_tc_kernel(const TcParams p) {
     }
 }
 
-// W [N=256, K=256] fp32 -> [4 K-chunks][hi, lo] 32 KB shared-memory images (bf16, K-major, SWIZZLE_128B)
-__global__ void pack_bf16_split_kernel(const float* __restrict__ W, uint8_t* __restrict__ out) {
+// W [N=256, K=256] fp32 -> [4 K-chunks][hi, lo] 32 KB shared-memory images (fp16, K-major, SWIZZLE_128B)
+__global__ void pack_f16_split_kernel(const float* __restrict__ W, uint8_t* __restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= TC_N * TC_K) return;
     const int n = t / TC_K, k = t % TC_K;
-    const float w = W[t];
-    const __nv_bfloat16 h = __float2bfloat16_rn(w);
-    const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+    const float w = fminf(fmaxf(W[t], -65504.f), 65504.f);
+    const __half h = __float2half_rn(w);
+    const __half l = __float2half_rn(w - __half2float(h));
     const int c = k / TC_KCHUNK, kc = k % TC_KCHUNK;
     const uint32_t off = sw128_offset(n, kc);
-    *reinterpret_cast<__nv_bfloat16*>(out + (size_t)(2 * c) * B_PIECE_BYTES + off) = h;
-    *reinterpret_cast<__nv_bfloat16*>(out + (size_t)(2 * c + 1) * B_PIECE_BYTES + off) = l;
+    *reinterpret_cast<__half*>(out + (size_t)(2 * c) * B_PIECE_BYTES + off) = h;
+    *reinterpret_cast<__half*>(out + (size_t)(2 * c + 1) * B_PIECE_BYTES + off) = l;
 }
 
 // w3s[o][n] = W3[o][n]*bn2_scale[n];  tail[o] = {sum_n bn2_shift[n]*W3[o][n] + b3[o], bn3_scale[o], bn3_shift[o], 0}
@@ -422,11 +454,11 @@ using namespace gnb;
 
 extern "C" {
 
-int32_t gnb_pack_bf16_split(const float* W, int32_t N, int32_t K, void* packed, void* stream) {
-    GNB_REQUIRE(W && packed, "gnb_pack_bf16_split: null pointer");
-    GNB_REQUIRE(N == TC_N && K == TC_K, "gnb_pack_bf16_split: only 256x256 weights are supported (got %dx%d)", N, K);
-    pack_bf16_split_kernel<<<TC_N * TC_K / 256, 256, 0, as_stream(stream)>>>(W, reinterpret_cast<uint8_t*>(packed));
-    return check_launch("gnb_pack_bf16_split");
+int32_t gnb_pack_f16_split(const float* W, int32_t N, int32_t K, void* packed, void* stream) {
+    GNB_REQUIRE(W && packed, "gnb_pack_f16_split: null pointer");
+    GNB_REQUIRE(N == TC_N && K == TC_K, "gnb_pack_f16_split: only 256x256 weights are supported (got %dx%d)", N, K);
+    pack_f16_split_kernel<<<TC_N * TC_K / 256, 256, 0, as_stream(stream)>>>(W, reinterpret_cast<uint8_t*>(packed));
+    return check_launch("gnb_pack_f16_split");
 }
 
 int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t Q, int64_t R, const float* bn1_scale,

@@ -342,12 +342,12 @@ def marching_cubes(volume: torch.Tensor, level: float, spacing=(1.0, 1.0, 1.0), 
 
 
 # ---------------------------------------------------------------------------------------------- tensor-core decoder tail
-def pack_bf16_split(weight: torch.Tensor) -> torch.Tensor:
-    """[256,256] fp32 weight -> bf16 hi/lo shared-memory images for ``decode_tc`` (uint8[N*K*4])."""
+def pack_f16_split(weight: torch.Tensor) -> torch.Tensor:
+    """[256,256] fp32 weight -> fp16 hi/lo shared-memory images for ``decode_tc`` (uint8[N*K*4])."""
     weight = _req(weight, torch.float32, "weight")
     N, K = weight.shape
     packed = torch.empty(N * K * 4, dtype=torch.uint8, device=weight.device)
-    _lib.call("gnb_pack_bf16_split", weight.data_ptr(), N, K, packed.data_ptr(), _stream())
+    _lib.call("gnb_pack_f16_split", weight.data_ptr(), N, K, packed.data_ptr(), _stream())
     return packed
 
 

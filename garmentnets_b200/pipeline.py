@@ -202,7 +202,7 @@ class ImplicitWNFDecoder(nn.Module):
         key = (l2.weight._version, l2.weight.data_ptr())
         cached = getattr(self, "_gnb_w2_packed", None)
         if cached is None or cached[0] != key:
-            cached = (key, ops.pack_bf16_split(l2.weight))
+            cached = (key, ops.pack_f16_split(l2.weight))
             self._gnb_w2_packed = cached
         return (cached[1], l2.bias, self.mlp[1][2].folded_affine(), l3.weight, l3.bias, self.mlp[2][2].folded_affine())
 

@@ -179,15 +179,15 @@ int32_t gnb_trilinear_sample_grid(const float* vol, int32_t b, int32_t D, int32_
 
 /* Tensor-core (tcgen05 + TMEM) decoder tail for the shipped decoder shape [C, 256, 256, Cout<=3]:
  *     y = BN3(ReLU( BN2(ReLU(H1 * W2^T + b2)) * W3^T + b3 ))        (ref components/mlp.py:9-20 blocks 2 and 3)
- * with both GEMM operands split into bf16 hi+lo (three MMAs per product, fp32 accumulation in TMEM) so that the result
+ * with both GEMM operands split into fp16 hi+lo (three MMAs per product, fp32 accumulation in TMEM) so that the result
  * stays within the 1e-4 fp32 parity bound.  H1 is produced on the fly and never stored:
  *   Q  > 0 (lattice mode, needs Q == 128): H1 = BN1(ReLU(trilinear(U))) over the implicit regular query lattice
  *          (i,j,k)/(Q-1) of every sample b < B (ref predict.py:145-158); U f32[B,G,G,G,256] is Linear1 applied on the
  *          feature grid (it commutes with the interpolation); out f32[B, Q^3, Cout].
  *   Q == 0 (row mode): H1 = X f32[R,256] (row stride ldx, even) given explicitly; out f32[R, Cout].
- * w2_packed: W2 re-laid by gnb_pack_bf16_split (N*K*4 bytes).  scratch: f32[1024] workspace.  bn*_scale/shift may be
+ * w2_packed: W2 re-laid by gnb_pack_f16_split (N*K*4 bytes).  scratch: f32[1024] workspace.  bn*_scale/shift may be
  * NULL (= identity) except bn1 in lattice mode. */
-int32_t gnb_pack_bf16_split(const float* W, int32_t N, int32_t K, void* packed, void* stream);
+int32_t gnb_pack_f16_split(const float* W, int32_t N, int32_t K, void* packed, void* stream);
 int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t Q, int64_t R,
                       const float* bn1_scale, const float* bn1_shift, const void* w2_packed, const float* b2,
                       const float* bn2_scale, const float* bn2_shift, const float* W3, const float* b3,
