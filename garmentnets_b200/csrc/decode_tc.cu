@@ -13,15 +13,15 @@
 // (fp32-level), at the cost of 3x the tensor work.
 //
 // Pipeline (mbarrier producer/consumer rings, no __syncthreads in steady state):
-//   warps 0-3  A producers: warp w builds K-chunk w (64 channels) of the 128-row A tile, fp16 hi/lo, directly in the
+//   warps 0-7  A producers: two warps per K-chunk (64 channels) of the 128-row A tile, fp16 hi/lo, directly in the
 //              UMMA canonical K-major SWIZZLE_128B layout in shared memory (generic-proxy stores + fence.proxy.async).
 //              LATTICE: the tile is one lattice line (i,j,0..127): bilinear blend of the four (H,W) neighbours per
 //              D-slice held in registers, then a linear blend along D per row -- 4 coalesced 8-byte loads per slice.
 //              ROWS: the tile is 128 rows of a precomputed fp32 H1 matrix (arbitrary query sets, surface decoder).
-//   warp 9     B loader: W2 is pre-packed (gnb_pack_f16_split) into 32 KB shared-memory images (K-chunk x {hi,lo});
+//   warp 13    B loader: W2 is pre-packed (gnb_pack_f16_split) into 32 KB shared-memory images (K-chunk x {hi,lo});
 //              cp.async.bulk streams them from L2 through a 3-slot ring (complete_tx on an mbarrier).
-//   warp 8     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=256, K=16) and tcgen05.commit.
-//   warps 4-7  epilogue: tcgen05.ld of the accumulator rows (lane = row), bias/ReLU/BN2 folded with W3, store.
+//   warp 12    MMA issuer: one elected thread issues tcgen05.mma (M=128, N=256, K=16) and tcgen05.commit.
+//   warps 8-11 epilogue: tcgen05.ld of the accumulator rows (lane = row), bias/ReLU/BN2 folded with W3, store.
 // TMEM: 2 x 256 columns (accumulator double buffer: epilogue(t) overlaps MMA(t+1)); smem: A 128 KB + B ring 96 KB.
 #include "common.cuh"
 #include <cuda_fp16.h>
@@ -32,7 +32,8 @@ constexpr int TC_K = 256, TC_N = 256, TC_M = 128, TC_KCHUNK = 64, TC_NCHUNK = TC
 constexpr int A_CHUNK_BYTES = TC_M * TC_KCHUNK * 2;      // 16 KB (one precision part)
 constexpr int B_PIECE_BYTES = TC_N * TC_KCHUNK * 2;      // 32 KB
 constexpr int B_SLOTS = 3;
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;  // 8 producer + 4 epilogue + MMA + loader warps
+constexpr int TC_MAX_G = 64;
 // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = F16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
@@ -45,7 +46,8 @@ struct TcSmem {
     static constexpr int n_bars = 4 + 4 + B_SLOTS + B_SLOTS + 2 + 2;
     static constexpr int tmem_ptr = bars + n_bars * 8;
     static constexpr int ztab = tmem_ptr + 16;                        // [128] {int z0, float wz1}
-    static constexpr int total = ztab + TC_M * 8;
+    static constexpr int kstart = ztab + TC_M * 8;                    // [G+1] first row of every D-cell
+    static constexpr int total = kstart + (TC_MAX_G + 2) * 4;
 };
 static_assert(TcSmem::total + 1024 <= 227 * 1024, "shared memory budget");
 
@@ -162,7 +164,7 @@ decode_tc_kernel(const TcParams p) {
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + TcSmem::tmem_ptr);
 
     if (threadIdx.x == 0) {
-        for (int c = 0; c < 4; ++c) { mbar_init(a_full(c), 32); mbar_init(a_empty(c), 1); }
+        for (int c = 0; c < 4; ++c) { mbar_init(a_full(c), 64); mbar_init(a_empty(c), 1); }
         for (int s = 0; s < B_SLOTS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -179,7 +181,7 @@ decode_tc_kernel(const TcParams p) {
         zt[2 * k] = (int)fz;
         reinterpret_cast<float*>(zt)[2 * k + 1] = iz - fz;
     }
-    if (warp == 8) {
+    if (warp == 12) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + TcSmem::tmem_ptr), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -187,18 +189,29 @@ decode_tc_kernel(const TcParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (LATTICE && threadIdx.x <= p.G) {
+        // kstart[d] = first lattice row whose D-cell index is >= d (rows are monotone in k); kstart[G] = 128
+        const int* zt = reinterpret_cast<const int*>(smem + TcSmem::ztab);
+        int k = 0;
+        while (k < TC_M && zt[2 * k] < (int)threadIdx.x) ++k;
+        reinterpret_cast<int*>(smem + TcSmem::kstart)[threadIdx.x] = k;
+    }
+    __syncthreads();
 
-    if (warp < 4) {
+    if (warp < 8) {
         // =========================== A producers ===========================
-        const int c0 = warp * TC_KCHUNK + 2 * lane;  // this thread's two channels
-        uint8_t* a_hi = smem + TcSmem::a_hi + warp * A_CHUNK_BYTES;
-        uint8_t* a_lo = smem + TcSmem::a_lo + warp * A_CHUNK_BYTES;
+        // two warps per K-chunk: `half` 0 produces the rows of the lower half of the D range, 1 the upper half
+        const int chunk = warp & 3, half = warp >> 2;
+        const int c0 = chunk * TC_KCHUNK + 2 * lane;  // this thread's two channels
+        uint8_t* a_hi = smem + TcSmem::a_hi + chunk * A_CHUNK_BYTES;
+        uint8_t* a_lo = smem + TcSmem::a_lo + chunk * A_CHUNK_BYTES;
+        const int* kst = reinterpret_cast<const int*>(smem + TcSmem::kstart);
         float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
         if (LATTICE) { sc0 = p.bn1_scale[c0]; sc1 = p.bn1_scale[c0 + 1]; sh0 = p.bn1_shift[c0]; sh1 = p.bn1_shift[c0 + 1]; }
         const int* zt = reinterpret_cast<const int*>(smem + TcSmem::ztab);
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            mbar_wait(a_empty(warp), (it & 1) ^ 1);
+            mbar_wait(a_empty(chunk), (it & 1) ^ 1);
             if (LATTICE) {
                 const int G = p.G, Q = p.Q;
                 const int j = (int)(tile % Q), i = (int)((tile / Q) % Q), b = (int)(tile / ((int64_t)Q * Q));
@@ -220,7 +233,8 @@ decode_tc_kernel(const TcParams p) {
                 // Slices are fetched NG at a time (4 x NG independent 8-byte loads in flight per thread) and the loads of
                 // the next group are issued before the rows of the current group are produced: the L2 latency of the
                 // gather is paid ~G/NG times per tile instead of G times.
-                constexpr int NG = 8;
+                constexpr int NG = 4;
+                const int d_lo = half ? G / 2 : 0, d_hi = half ? G : G / 2;  // this warp's D-cells [d_lo, d_hi)
                 float2 v[NG][4];
                 auto issue = [&](int dfirst) {
 #pragma unroll
@@ -242,21 +256,23 @@ decode_tc_kernel(const TcParams p) {
                 };
                 float2 pc[NG + 1];
                 {
-                    const float* q = base;
+                    const float* q = base + d_lo * sd;
                     const float2 c4[4] = {__ldg(reinterpret_cast<const float2*>(q + o00)), __ldg(reinterpret_cast<const float2*>(q + o10)),
                                           __ldg(reinterpret_cast<const float2*>(q + o01)), __ldg(reinterpret_cast<const float2*>(q + o11))};
-                    issue(1);
+                    issue(d_lo + 1);
                     pc[0] = blend(c4);
                 }
-                int k = 0;
-                for (int d0 = 0; d0 < G; d0 += NG) {
+                const uint32_t lane_off = (uint32_t)((lane & 3) * 4);
+                for (int d0 = d_lo; d0 < d_hi; d0 += NG) {
 #pragma unroll
                     for (int s2 = 0; s2 < NG; ++s2) pc[s2 + 1] = blend(v[s2]);   // P(d0+1 .. d0+NG)
-                    if (d0 + NG < G) issue(d0 + NG + 1);                        // next group's loads fly during the rows
+                    if (d0 + NG < d_hi) issue(d0 + NG + 1);                     // next group's loads fly during the rows
 #pragma unroll
                     for (int s2 = 0; s2 < NG; ++s2) {
                         const int d = d0 + s2;
-                        while (k < TC_M && zt[2 * k] == d) {
+                        if (d >= d_hi) break;
+                        const int k_end = kst[d + 1];
+                        for (int k = kst[d]; k < k_end; ++k) {
                             const float wz1 = reinterpret_cast<const float*>(zt)[2 * k + 1];
                             const float wz0 = 1.0f - wz1;
                             float h0 = pc[s2].x * wz0 + pc[s2 + 1].x * wz1;
@@ -265,10 +281,9 @@ decode_tc_kernel(const TcParams p) {
                             h1 = fmaxf(h1, 0.f) * sc1 + sh1;
                             uint32_t hi, lo;
                             split_f16x2(h0, h1, hi, lo);
-                            const uint32_t off = sw128_offset(k, 2 * lane);
+                            const uint32_t off = (uint32_t)((k >> 3) * 1024 + (k & 7) * 128 + ((((lane >> 2) ^ k) & 7) << 4)) + lane_off;
                             *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
                             *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
-                            ++k;
                         }
                     }
                     pc[0] = pc[NG];
@@ -276,7 +291,7 @@ decode_tc_kernel(const TcParams p) {
             } else {
                 const int64_t r0 = tile * TC_M;
 #pragma unroll 4
-                for (int k = 0; k < TC_M; ++k) {
+                for (int k = half * (TC_M / 2); k < (half + 1) * (TC_M / 2); ++k) {
                     float2 v = make_float2(0.f, 0.f);
                     if (r0 + k < p.R) v = __ldg(reinterpret_cast<const float2*>(p.U + (r0 + k) * p.ldx + c0));
                     uint32_t hi, lo;
@@ -287,11 +302,11 @@ decode_tc_kernel(const TcParams p) {
                 }
             }
             fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
-            mbar_arrive(a_full(warp));
+            mbar_arrive(a_full(chunk));
         }
-    } else if (warp < 8) {
+    } else if (warp < 12) {
         // =========================== epilogue ===========================
-        const int q = warp - 4;  // TMEM lane quarter this warp may access
+        const int q = warp & 3;  // TMEM lane quarter this warp may access (warp id mod 4)
         const int row = q * 32 + lane;
         float c_tail[COUT], bn3s[COUT], bn3h[COUT];
 #pragma unroll
@@ -331,7 +346,7 @@ decode_tc_kernel(const TcParams p) {
                     p.out[grow * COUT + o] = fmaxf(dot[o] + c_tail[o], 0.f) * bn3s[o] + bn3h[o];
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == 12) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             int it = 0;
@@ -395,7 +410,7 @@ decode_tc_kernel(const TcParams p) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 12) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
@@ -470,7 +485,8 @@ int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t
     const bool lattice = Q > 0;
     if (lattice) {
         GNB_REQUIRE(Q == TC_M, "gnb_decode_tc: the lattice kernel needs volume_size == 128 (one lattice line per tile)");
-        GNB_REQUIRE(B > 0 && G >= 2 && bn1_scale && bn1_shift, "gnb_decode_tc: bad lattice arguments");
+        GNB_REQUIRE(B > 0 && G >= 2 && G <= TC_MAX_G && G % 2 == 0 && bn1_scale && bn1_shift,
+                    "gnb_decode_tc: bad lattice arguments (need an even feature grid 2 <= G <= 64)");
     } else {
         GNB_REQUIRE(R >= 0 && ldx >= TC_K && (ldx % 2) == 0, "gnb_decode_tc: bad row matrix");
         if (R == 0) return GNB_OK;
