@@ -274,6 +274,14 @@ def run_ours(args, rank, world):
     total_ms = sum(s.elapsed_time(e) for s, e in ev)
     ksum = timer.summary()
 
+    # per-stage device times of one extra (untimed) step, for the report only
+    model.stage_marks = []
+    step_resident()
+    torch.cuda.synchronize()
+    marks = model.stage_marks
+    model.stage_marks = None
+    stages_ms = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 3) for i in range(1, len(marks))}
+
     # end-to-end through the public API with host buffers
     step_e2e()
     barrier()
@@ -341,7 +349,7 @@ def run_ours(args, rank, world):
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
-            "gpu_launches": launches, "clocks": clocks, "wall_s": round(wall, 3)}
+            "gpu_launches": launches, "clocks": clocks, "wall_s": round(wall, 3), "stages_ms": stages_ms}
     print(json.dumps(line), flush=True)
 
 

@@ -331,9 +331,23 @@ class ConvImplicitWNFPipeline(nn.Module):
                 keep_volume: bool = False) -> List[Dict[str, torch.Tensor]]:
         """Device version of the reference's per-sample loop predict.py:138-187, for a whole batch.
         Returns one dict per sample with the arrays predict.py writes under ``marching_cubes_mesh`` / ``point_cloud``."""
+        marks = getattr(self, "stage_marks", None)  # optional [(name, cuda event)] sink used by bench.py
+
+        def mark(name):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
         p = self.pointnet2_forward(data, index=index, fps_starts=fps_starts)
-        u = self.unet3d_forward(p)
+        mark("pointnet2")
+        vol_in = self.volume_agg(p["nocs_data"])
+        mark("aggregator")
+        u = {"out_feature_volume": self.unet_3d(vol_in), "in_feature_volume": vol_in}
+        mark("unet3d")
         wnf = self.dense_decode(u["out_feature_volume"], volume_size)
+        mark("dense_decode")
         B, Q = wnf.shape[0], wnf.shape[1]
         spacing = 1 / (Q - 1)
         fvol = ops.to_channels_last(u["out_feature_volume"])
@@ -359,5 +373,6 @@ class ConvImplicitWNFPipeline(nn.Module):
                 r["wnf_volume"] = wnf[b]
                 r["wnf_ggm"] = ggm
             results.append(r)
+        mark("ggm_mc_surface")
         self._last_point_outputs = {"pred_nocs": nocs_data.pos, "pred_confidence": nocs_data.pred_confidence}
         return results
