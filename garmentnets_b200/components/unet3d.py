@@ -22,6 +22,10 @@ import torch.nn as nn
 from .. import ops
 
 
+# tensor-core (TMA + tcgen05) convolutions; False selects the fp32 FFMA kernel everywhere (used by the parity tests)
+USE_TENSOR_CORES = True
+
+
 def number_of_features_per_level(init_channel_number, num_levels):
     return [init_channel_number * 2 ** k for k in range(num_levels)]
 
@@ -91,7 +95,22 @@ class SingleConv(nn.Sequential):
             _unsupported(f"SingleConv(order='{self.order}')")
         gn = self.groupnorm
         scale, shift = ops.groupnorm_stats(x, gn.num_groups, gn.eps, gn.weight, gn.bias)
+        B, D, H, W, Cin = x.shape
+        Cout = self.conv.out_channels
+        if USE_TENSOR_CORES and ops.conv3d_tc_supported(B, D, H, W, Cin, Cout):
+            # TMA + tcgen05 implicit GEMM on the normalised activation written once as fp16 hi + lo
+            xh, xl = ops.gn_apply_split(x, scale, shift)
+            return ops.conv3d_tc(xh, xl, Cin, self.packed_weight_tc(), Cout, relu='r' in self.order)
         return ops.conv3d_k3(x, self.packed_weight(), scale, shift, relu='r' in self.order)
+
+    def packed_weight_tc(self) -> torch.Tensor:
+        w = self.conv.weight
+        key = (w._version, w.data_ptr())
+        cached = getattr(self, '_gnb_wt_tc', None)
+        if cached is None or cached[0] != key:
+            cached = (key, ops.conv3d_tc_pack_weights(w))
+            self._gnb_wt_tc = cached
+        return cached[1]
 
     def forward(self, x):
         out = self.forward_ndhwc(ops.to_channels_last(x))

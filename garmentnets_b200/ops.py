@@ -375,3 +375,37 @@ def decode_tc(w2_packed, b2, bn2, W3, b3, bn3, *, U=None, Q=0, bn1=None, X=None,
     _lib.call("gnb_decode_tc", X.data_ptr(), ldx, 0, 0, 0, R, None, None, w2_packed.data_ptr(), b2.data_ptr(), _ptr(s2),
               _ptr(h2), W3.data_ptr(), _ptr(b3), _ptr(s3), _ptr(h3), Cout, scratch.data_ptr(), out.data_ptr(), _stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------- tensor-core 3x3x3 conv
+def conv3d_tc_supported(B, D, H, W, Cin, Cout) -> bool:
+    return bool(_lib.call("gnb_conv3d_tc_supported", int(B), int(D), int(H), int(W), int(Cin), int(Cout)))
+
+
+def conv3d_tc_pack_weights(weight: torch.Tensor) -> torch.Tensor:
+    """[Cout,Cin,3,3,3] fp32 -> fp16 hi/lo shared-memory images per (tap, 64-channel chunk)."""
+    weight = _req(weight, torch.float32, "weight")
+    Cout, Cin = weight.shape[:2]
+    cpad = (Cin + 63) // 64 * 64
+    packed = torch.empty(27 * cpad * Cout * 4, dtype=torch.uint8, device=weight.device)
+    _lib.call("gnb_conv3d_tc_pack_weights", weight.data_ptr(), Cout, Cin, packed.data_ptr(), _stream())
+    return packed
+
+
+def gn_apply_split(x: torch.Tensor, scale, shift):
+    """x [B,D,H,W,C] fp32 -> (xh, xl) fp16 [B,D,H,W,Cpad] holding x*scale+shift as hi + lo."""
+    B, D, H, W, C = x.shape
+    cpad = (C + 63) // 64 * 64
+    xh = torch.empty((B, D, H, W, cpad), dtype=torch.float16, device=x.device)
+    xl = torch.empty((B, D, H, W, cpad), dtype=torch.float16, device=x.device)
+    _lib.call("gnb_gn_apply_split", x.data_ptr(), B, D * H * W, C, _ptr(scale), _ptr(shift), xh.data_ptr(), xl.data_ptr(),
+              _stream())
+    return xh, xl
+
+
+def conv3d_tc(xh: torch.Tensor, xl: torch.Tensor, cin: int, w_packed: torch.Tensor, cout: int, relu: bool = True):
+    B, D, H, W, _ = xh.shape
+    y = torch.empty((B, D, H, W, cout), dtype=torch.float32, device=xh.device)
+    _lib.call("gnb_conv3d_tc", xh.data_ptr(), xl.data_ptr(), B, D, H, W, int(cin), w_packed.data_ptr(), int(cout),
+              int(relu), y.data_ptr(), _stream())
+    return y

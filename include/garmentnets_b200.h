@@ -150,6 +150,18 @@ int32_t gnb_groupnorm_stats(const float* x, int32_t B, int64_t voxels, int32_t C
 int32_t gnb_conv3d_k3(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin,
                       const float* scale, const float* shift, const float* Wt, int32_t Cout,
                       int32_t relu, float* y, void* stream);
+/* Tensor-core (TMA + tcgen05) version of gnb_conv3d_k3 for power-of-two grids with at least 128 voxels in the batch and
+ * Cout in {32,64,...,256} (gnb_conv3d_tc_supported).  Three launches per 'gcr' SingleConv:
+ *   gnb_groupnorm_stats -> gnb_gn_apply_split (x*scale+shift written once as fp16 hi + lo, channels zero-padded to a
+ *   multiple of 64: xh, xl f16[B,D,H,W,Cpad]) -> gnb_conv3d_tc (per tap and 64-channel chunk two TMA box loads with
+ *   hardware zero fill = the conv padding, weights from the images made by gnb_conv3d_tc_pack_weights
+ *   (27 * Cpad * Cout * 4 bytes), products as hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM). */
+int32_t gnb_conv3d_tc_supported(int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout);
+int32_t gnb_conv3d_tc_pack_weights(const float* W, int32_t Cout, int32_t Cin, void* packed, void* stream);
+int32_t gnb_gn_apply_split(const float* x, int32_t B, int64_t voxels, int32_t C, const float* scale, const float* shift,
+                           void* xh, void* xl, void* stream);
+int32_t gnb_conv3d_tc(const void* xh, const void* xl, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin,
+                      const void* w_packed, int32_t Cout, int32_t relu, float* y, void* stream);
 int32_t gnb_maxpool3d_2(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, float* y, void* stream);
 /* y[b,d,h,w, 0:Cs] = skip[b,d,h,w,:];  y[..., Cs:Cs+Cx] = x[b, d*Dx/D, h*Hx/H, w*Wx/W, :] (nearest). */
 int32_t gnb_upsample_concat(const float* skip, int32_t Cs, const float* x, int32_t Cx, int32_t B,

@@ -1,0 +1,56 @@
+"""TMA + tcgen05 3x3x3 convolution vs torch CPU (GroupNorm -> Conv3d -> ReLU), all UNet layer shapes."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+TOL = 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,G,Cin,Cout", [(1, 8, 64, 64), (2, 8, 32, 32), (1, 16, 96, 32), (2, 4, 128, 256),
+                                          (1, 8, 192, 64), (4, 4, 256, 128), (1, 32, 128, 128), (1, 16, 32, 64)])
+def test_conv_tc_matches_torch(dev, B, G, Cin, Cout):
+    from garmentnets_b200 import ops
+    assert ops.conv3d_tc_supported(B, G, G, G, Cin, Cout)
+    g = torch.Generator().manual_seed(Cin * 7 + Cout)
+    x = torch.randn(B, Cin, G, G, G, generator=g) * 1.5 + 0.3
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5
+    gamma, beta = torch.rand(Cin, generator=g) + 0.5, torch.randn(Cin, generator=g) * 0.1
+    ref = F.relu(F.conv3d(F.group_norm(x, 8, gamma, beta, 1e-5), w, None, padding=1)).permute(0, 2, 3, 4, 1)
+    x_cl = ops.to_channels_last(x.to(dev))
+    scale, shift = ops.groupnorm_stats(x_cl, 8, 1e-5, gamma.to(dev), beta.to(dev))
+    xh, xl = ops.gn_apply_split(x_cl, scale, shift)
+    cpad = (Cin + 63) // 64 * 64
+    assert xh.shape[-1] == cpad
+    gn = (x_cl * scale[:, None, None, None, :] + shift[:, None, None, None, :])
+    assert ((xh[..., :Cin].float() + xl[..., :Cin].float()) - gn).abs().max().item() < 2e-6
+    assert cpad == Cin or torch.all(xh[..., Cin:] == 0)
+    y = ops.conv3d_tc(xh, xl, Cin, ops.conv3d_tc_pack_weights(w.to(dev)), Cout, relu=True)
+    err = (y.cpu() - ref).abs().max().item()
+    assert err < TOL, err
+    y32 = ops.conv3d_k3(x_cl, w.permute(2, 3, 4, 1, 0).reshape(27, Cin, Cout).contiguous().to(dev), scale, shift, relu=True)
+    assert (y - y32).abs().max().item() < TOL
+
+
+@pytest.mark.gpu
+def test_unet_tc_equals_fp32_path(dev):
+    from garmentnets_b200 import synthetic
+    from garmentnets_b200.components import unet3d
+    from oracle import nets as ON
+    torch.manual_seed(4)
+    net = synthetic.randomize_(unet3d.Abstract3DUNet(128, 128, False, unet3d.DoubleConv, f_maps=32, layer_order="gcr",
+                                                     num_groups=8, num_levels=4, is_segmentation=False), 5).eval().to(dev)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 128, 32, 32, 32, generator=g) * (torch.rand(2, 128, 32, 32, 32, generator=g) < 0.1)
+    unet3d.USE_TENSOR_CORES = True
+    y_tc = net(x.to(dev))
+    unet3d.USE_TENSOR_CORES = False
+    try:
+        y_32 = net(x.to(dev))
+    finally:
+        unet3d.USE_TENSOR_CORES = True
+    ref = ON.unet3d_forward({k: v.cpu() for k, v in net.state_dict().items()}, "", x).numpy()
+    scale = max(1.0, float(np.abs(ref).max()))
+    assert (y_tc - y_32).abs().max().item() < TOL * scale
+    assert np.abs(y_tc.cpu().numpy() - ref).max() < TOL * scale
