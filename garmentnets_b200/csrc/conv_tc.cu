@@ -100,6 +100,7 @@ struct ConvTcParams {
     int nchunk;                // Cpad / 64
     int nstages, stage_bytes, b_bytes;  // b_bytes = Cout*128 (one precision part of one weight piece)
     int relu;
+    float out_scale;           // 2^-s: undoes the power-of-two scaling applied to the packed weights
     const uint8_t* w_packed;   // [27][nchunk][hi,lo][Cout*128 B]
     float* y;                  // [B,D,H,W,Cout] fp32
     int64_t num_tiles;
@@ -223,8 +224,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 o;
-                    o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
-                    o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
+                    o.x = __uint_as_float(v[j]) * p.out_scale; o.y = __uint_as_float(v[j + 1]) * p.out_scale;
+                    o.z = __uint_as_float(v[j + 2]) * p.out_scale; o.w = __uint_as_float(v[j + 3]) * p.out_scale;
                     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     *reinterpret_cast<float4*>(dst + n0 + j) = o;
                 }
@@ -272,7 +273,7 @@ gn_apply_split_kernel(const float* __restrict__ x, int64_t rows, int64_t vox_per
 }
 
 // W fp32 [Cout, Cin, 3,3,3] -> [27][Cpad/64][hi,lo][Cout rows x 64 K] fp16 K-major SWIZZLE_128B images
-__global__ void pack_conv_weights_kernel(const float* __restrict__ W, int Cout, int Cin, int Cpad,
+__global__ void pack_conv_weights_kernel(const float* __restrict__ W, int Cout, int Cin, int Cpad, float wscale,
                                          uint8_t* __restrict__ out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)27 * Cpad * Cout;
@@ -281,7 +282,7 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ W, int Cout, 
     const int k = (int)((t / Cout) % Cpad);
     const int tap = (int)(t / ((int64_t)Cout * Cpad));
     float w = 0.f;
-    if (k < Cin) w = W[((int64_t)n * Cin + k) * 27 + tap];  // [Cout][Cin][kd][kh][kw], tap = kd*9+kh*3+kw
+    if (k < Cin) w = W[((int64_t)n * Cin + k) * 27 + tap] * wscale;  // [Cout][Cin][kd][kh][kw], tap = kd*9+kh*3+kw
     w = fminf(fmaxf(w, -65504.f), 65504.f);
     const __half h = __float2half_rn(w);
     const __half l = __float2half_rn(w - __half2float(h));
@@ -315,13 +316,14 @@ using namespace gnb;
 
 extern "C" {
 
-int32_t gnb_conv3d_tc_pack_weights(const float* W, int32_t Cout, int32_t Cin, void* packed, void* stream) {
+int32_t gnb_conv3d_tc_pack_weights(const float* W, int32_t Cout, int32_t Cin, int32_t scale_log2, void* packed,
+                                   void* stream) {
     GNB_REQUIRE(W && packed, "gnb_conv3d_tc_pack_weights: null pointer");
     GNB_REQUIRE(Cout % 32 == 0 && Cout >= 32 && Cout <= 256 && Cin > 0, "gnb_conv3d_tc_pack_weights: Cout must be a multiple of 32 in [32,256]");
     const int Cpad = ceil_div(Cin, CT_KC) * CT_KC;
     const int64_t total = (int64_t)27 * Cpad * Cout;
     pack_conv_weights_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, as_stream(stream)>>>(
-        W, Cout, Cin, Cpad, reinterpret_cast<uint8_t*>(packed));
+        W, Cout, Cin, Cpad, ldexpf(1.0f, scale_log2), reinterpret_cast<uint8_t*>(packed));
     return check_launch("gnb_conv3d_tc_pack_weights");
 }
 
@@ -346,13 +348,14 @@ int32_t gnb_conv3d_tc_supported(int32_t B, int32_t D, int32_t H, int32_t W, int3
 }
 
 int32_t gnb_conv3d_tc(const void* xh, const void* xl, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin,
-                      const void* w_packed, int32_t Cout, int32_t relu, float* y, void* stream) {
+                      const void* w_packed, int32_t scale_log2, int32_t Cout, int32_t relu, float* y, void* stream) {
     GNB_REQUIRE(xh && xl && w_packed && y, "gnb_conv3d_tc: null pointer");
     GNB_REQUIRE(gnb_conv3d_tc_supported(B, D, H, W, Cin, Cout), "gnb_conv3d_tc: unsupported shape B=%d D=%d H=%d W=%d Cin=%d Cout=%d", B, D, H, W, Cin, Cout);
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) { set_error("gnb_conv3d_tc: cuTensorMapEncodeTiled is not available from this driver"); return GNB_ERR_CUDA; }
     ConvTcParams p;
     p.B = B; p.D = D; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu;
+    p.out_scale = ldexpf(1.0f, -scale_log2);
     p.Cpad = ceil_div(Cin, CT_KC) * CT_KC;
     p.nchunk = p.Cpad / CT_KC;
     int rem = CT_M;

@@ -138,6 +138,7 @@ struct TcParams {
     const float* bn1_scale; // LATTICE only
     const float* bn1_shift;
     const uint8_t* w2_packed;  // [4 chunks][hi,lo][32 KB]
+    float acc_scale;        // 2^-s: undoes the power-of-two scaling applied to the packed W2
     const float* b2;        // [256]
     const float* w3s;       // [COUT][256] = W3 * bn2_scale
     const float* tail;      // [COUT][4] = {c0 = sum(bn2_shift*W3) + b3, bn3_scale, bn3_shift, 0}
@@ -328,8 +329,9 @@ decode_tc_kernel(const TcParams p) {
 #pragma unroll
                 for (int t = 0; t < 32; t += 4) {
                     const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + n0 + t));
-                    const float v0 = fmaxf(__uint_as_float(r[t]) + bb.x, 0.f), v1 = fmaxf(__uint_as_float(r[t + 1]) + bb.y, 0.f);
-                    const float v2 = fmaxf(__uint_as_float(r[t + 2]) + bb.z, 0.f), v3 = fmaxf(__uint_as_float(r[t + 3]) + bb.w, 0.f);
+                    const float as = p.acc_scale;
+                    const float v0 = fmaxf(fmaf(__uint_as_float(r[t]), as, bb.x), 0.f), v1 = fmaxf(fmaf(__uint_as_float(r[t + 1]), as, bb.y), 0.f);
+                    const float v2 = fmaxf(fmaf(__uint_as_float(r[t + 2]), as, bb.z), 0.f), v3 = fmaxf(fmaf(__uint_as_float(r[t + 3]), as, bb.w), 0.f);
 #pragma unroll
                     for (int o = 0; o < COUT; ++o) {
                         const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w3s + o * TC_N + n0 + t));
@@ -417,11 +419,11 @@ decode_tc_kernel(const TcParams p) {
 }
 
 // W [N=256, K=256] fp32 -> [4 K-chunks][hi, lo] 32 KB shared-memory images (fp16, K-major, SWIZZLE_128B)
-__global__ void pack_f16_split_kernel(const float* __restrict__ W, uint8_t* __restrict__ out) {
+__global__ void pack_f16_split_kernel(const float* __restrict__ W, float wscale, uint8_t* __restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= TC_N * TC_K) return;
     const int n = t / TC_K, k = t % TC_K;
-    const float w = fminf(fmaxf(W[t], -65504.f), 65504.f);
+    const float w = fminf(fmaxf(W[t] * wscale, -65504.f), 65504.f);
     const __half h = __float2half_rn(w);
     const __half l = __float2half_rn(w - __half2float(h));
     const int c = k / TC_KCHUNK, kc = k % TC_KCHUNK;
@@ -469,15 +471,16 @@ using namespace gnb;
 
 extern "C" {
 
-int32_t gnb_pack_f16_split(const float* W, int32_t N, int32_t K, void* packed, void* stream) {
+int32_t gnb_pack_f16_split(const float* W, int32_t N, int32_t K, int32_t scale_log2, void* packed, void* stream) {
     GNB_REQUIRE(W && packed, "gnb_pack_f16_split: null pointer");
     GNB_REQUIRE(N == TC_N && K == TC_K, "gnb_pack_f16_split: only 256x256 weights are supported (got %dx%d)", N, K);
-    pack_f16_split_kernel<<<TC_N * TC_K / 256, 256, 0, as_stream(stream)>>>(W, reinterpret_cast<uint8_t*>(packed));
+    pack_f16_split_kernel<<<TC_N * TC_K / 256, 256, 0, as_stream(stream)>>>(W, ldexpf(1.0f, scale_log2),
+                                                                            reinterpret_cast<uint8_t*>(packed));
     return check_launch("gnb_pack_f16_split");
 }
 
 int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t Q, int64_t R, const float* bn1_scale,
-                      const float* bn1_shift, const void* w2_packed, const float* b2, const float* bn2_scale,
+                      const float* bn1_shift, const void* w2_packed, int32_t w2_scale_log2, const float* b2, const float* bn2_scale,
                       const float* bn2_shift, const float* W3, const float* b3, const float* bn3_scale,
                       const float* bn3_shift, int32_t Cout, float* scratch, float* out, void* stream) {
     GNB_REQUIRE(U && w2_packed && b2 && W3 && scratch && out, "gnb_decode_tc: null pointer");
@@ -500,6 +503,7 @@ int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t
     p.bn1_scale = bn1_scale; p.bn1_shift = bn1_shift;
     p.w2_packed = reinterpret_cast<const uint8_t*>(w2_packed);
     p.b2 = b2; p.w3s = w3s; p.tail = tail; p.out = out;
+    p.acc_scale = ldexpf(1.0f, -w2_scale_log2);
     p.num_tiles = lattice ? (int64_t)B * Q * Q : ceil_div<int64_t>(R, TC_M);
     if (lattice) {
         if (Cout == 1) return launch_decode_tc<1, true>(p, st);

@@ -244,12 +244,12 @@ struct Taps { double w[33]; int radius; };
 // mode: 0 store v | 1 store v*v | 2 out += v*v | 3 out = sqrt(out + v*v)
 template <bool ANTI>
 __global__ void __launch_bounds__(256)
-filter1d_kernel(const float* __restrict__ in, int D, int H, int W, int axis, Taps tp, int mode,
+filter1d_kernel(const float* __restrict__ in, int nvol, int D, int H, int W, int axis, Taps tp, int mode,
                 float* __restrict__ out) {
-    const int64_t total = (int64_t)D * H * W;
+    const int64_t total = (int64_t)nvol * D * H * W;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int w = (int)(i % W), h = (int)((i / W) % H), d = (int)(i / ((int64_t)W * H));
+    const int w = (int)(i % W), h = (int)((i / W) % H), d = (int)((i / ((int64_t)W * H)) % D);
     const int len = axis == 0 ? D : (axis == 1 ? H : W);
     const int pos = axis == 0 ? d : (axis == 1 ? h : w);
     const int64_t stride = axis == 0 ? (int64_t)H * W : (axis == 1 ? W : 1);
@@ -373,11 +373,11 @@ static void gaussian_taps(double sigma, int order, Taps& tp) {
     }
 }
 
-int32_t gnb_gaussian_gradient_magnitude(const float* v, int32_t D, int32_t H, int32_t W, double sigma, float* out,
-                                        float* tmp, void* stream) {
+int32_t gnb_gaussian_gradient_magnitude_batched(const float* v, int32_t nvol, int32_t D, int32_t H, int32_t W,
+                                                double sigma, float* out, float* tmp, void* stream) {
     GNB_REQUIRE(v && out && tmp, "gnb_gaussian_gradient_magnitude: null pointer");
     GNB_REQUIRE(sigma > 0 && (int)(4.0 * sigma + 0.5) <= 16, "gnb_gaussian_gradient_magnitude: sigma out of range");
-    const int64_t total = (int64_t)D * H * W;
+    const int64_t total = (int64_t)nvol * D * H * W;
     if (total == 0) return GNB_OK;
     Taps g0, g1;
     gaussian_taps(sigma, 0, g0);
@@ -392,12 +392,17 @@ int32_t gnb_gaussian_gradient_magnitude(const float* v, int32_t D, int32_t H, in
             const bool last = ax == 2;
             float* dst = last ? out : (ax == 0 ? t1 : t2);
             const int mode = !last ? 0 : (a == 0 ? 1 : (a == 1 ? 2 : 3));
-            if (ax == a) filter1d_kernel<true><<<grid, 256, 0, st>>>(src, D, H, W, ax, g1, mode, dst);
-            else filter1d_kernel<false><<<grid, 256, 0, st>>>(src, D, H, W, ax, g0, mode, dst);
+            if (ax == a) filter1d_kernel<true><<<grid, 256, 0, st>>>(src, nvol, D, H, W, ax, g1, mode, dst);
+            else filter1d_kernel<false><<<grid, 256, 0, st>>>(src, nvol, D, H, W, ax, g0, mode, dst);
             src = dst;
         }
     }
     return check_launch("gnb_gaussian_gradient_magnitude");
+}
+
+int32_t gnb_gaussian_gradient_magnitude(const float* v, int32_t D, int32_t H, int32_t W, double sigma, float* out,
+                                        float* tmp, void* stream) {
+    return gnb_gaussian_gradient_magnitude_batched(v, 1, D, H, W, sigma, out, tmp, stream);
 }
 
 }  // extern "C"

@@ -549,9 +549,15 @@ int64_t gnb_mc_workspace_bytes(int32_t D, int32_t H, int32_t W) {
                      align256(sizeof(int32_t) * (3 + MC_MAX_CEN) * (size_t)D * H * W));
 }
 
+int64_t gnb_mc_totals_offset(int32_t D, int32_t H, int32_t W) {
+    if (D < 2 || H < 2 || W < 2) return 0;
+    McWs ws = carve(nullptr, D, H, W);
+    return (int64_t)(reinterpret_cast<char*>(ws.totals) - reinterpret_cast<char*>(0));
+}
+
 int32_t gnb_mc_count(const float* v, int32_t D, int32_t H, int32_t W, float level, void* ws_, int64_t* counts_host,
                      void* stream) {
-    GNB_REQUIRE(v && ws_ && counts_host, "gnb_mc_count: null pointer");
+    GNB_REQUIRE(v && ws_, "gnb_mc_count: null pointer");
     GNB_REQUIRE(D >= 2 && H >= 2 && W >= 2, "gnb_mc_count: volume must be at least 2x2x2");
     if (ensure_tables() != 0) { set_error("gnb_mc_count: table upload failed"); return GNB_ERR_CUDA; }
     cudaStream_t st = as_stream(stream);
@@ -562,6 +568,7 @@ int32_t gnb_mc_count(const float* v, int32_t D, int32_t H, int32_t W, float leve
     mc_scan_kernel<<<1, 1024, 0, st>>>(ws);
     int32_t rc = check_launch("gnb_mc_count");
     if (rc != GNB_OK) return rc;
+    if (counts_host == nullptr) return GNB_OK;  // asynchronous form: the caller reads the totals block itself
     struct { int64_t tot[2]; } h;
     unsigned mm[2];
     GNB_CUDA(cudaMemcpyAsync(&h, ws.totals, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -342,16 +342,25 @@ def marching_cubes(volume: torch.Tensor, level: float, spacing=(1.0, 1.0, 1.0), 
 
 
 # ---------------------------------------------------------------------------------------------- tensor-core decoder tail
-def pack_f16_split(weight: torch.Tensor) -> torch.Tensor:
-    """[256,256] fp32 weight -> fp16 hi/lo shared-memory images for ``decode_tc`` (uint8[N*K*4])."""
+def _pow2_scale(weight: torch.Tensor) -> int:
+    """Power-of-two exponent s with max|w| * 2^s in [2^12, 2^13): keeps the fp16 lo parts of the split out of the
+    subnormal range (one host read at pack time; packed weights are cached by the modules)."""
+    m = float(weight.abs().max().item())
+    return 0 if m == 0.0 else int(12 - math.floor(math.log2(m)))
+
+
+def pack_f16_split(weight: torch.Tensor):
+    """[256,256] fp32 weight -> (fp16 hi/lo shared-memory images for ``decode_tc`` uint8[N*K*4], scale_log2)."""
     weight = _req(weight, torch.float32, "weight")
     N, K = weight.shape
+    s = _pow2_scale(weight)
     packed = torch.empty(N * K * 4, dtype=torch.uint8, device=weight.device)
-    _lib.call("gnb_pack_f16_split", weight.data_ptr(), N, K, packed.data_ptr(), _stream())
-    return packed
+    _lib.call("gnb_pack_f16_split", weight.data_ptr(), N, K, s, packed.data_ptr(), _stream())
+    return packed, s
 
 
 def decode_tc(w2_packed, b2, bn2, W3, b3, bn3, *, U=None, Q=0, bn1=None, X=None, out=None) -> torch.Tensor:
+    w2_packed, w2_s = w2_packed
     """Tensor-core decoder tail (``gnb_decode_tc``).  Lattice mode: ``U`` [B,G,G,G,256], ``Q`` = 128, ``bn1`` =
     (scale, shift) -> [B, Q^3, Cout].  Row mode: ``X`` [R,256] -> [R, Cout].  bn2 / bn3 are (scale, shift) or None."""
     Cout = W3.shape[0]
@@ -365,14 +374,14 @@ def decode_tc(w2_packed, b2, bn2, W3, b3, bn3, *, U=None, Q=0, bn1=None, X=None,
         if out is None:
             out = torch.empty((B, Q ** 3, Cout), dtype=torch.float32, device=dev)
         _lib.call("gnb_decode_tc", U.data_ptr(), 0, B, G, int(Q), 0, bn1[0].data_ptr(), bn1[1].data_ptr(),
-                  w2_packed.data_ptr(), b2.data_ptr(), _ptr(s2), _ptr(h2), W3.data_ptr(), _ptr(b3), _ptr(s3), _ptr(h3),
+                  w2_packed.data_ptr(), w2_s, b2.data_ptr(), _ptr(s2), _ptr(h2), W3.data_ptr(), _ptr(b3), _ptr(s3), _ptr(h3),
                   Cout, scratch.data_ptr(), out.data_ptr(), _stream())
         return out
     X, ldx = _rows(X, "X")
     R = X.shape[0]
     if out is None:
         out = torch.empty((R, Cout), dtype=torch.float32, device=dev)
-    _lib.call("gnb_decode_tc", X.data_ptr(), ldx, 0, 0, 0, R, None, None, w2_packed.data_ptr(), b2.data_ptr(), _ptr(s2),
+    _lib.call("gnb_decode_tc", X.data_ptr(), ldx, 0, 0, 0, R, None, None, w2_packed.data_ptr(), w2_s, b2.data_ptr(), _ptr(s2),
               _ptr(h2), W3.data_ptr(), _ptr(b3), _ptr(s3), _ptr(h3), Cout, scratch.data_ptr(), out.data_ptr(), _stream())
     return out
 
@@ -382,14 +391,15 @@ def conv3d_tc_supported(B, D, H, W, Cin, Cout) -> bool:
     return bool(_lib.call("gnb_conv3d_tc_supported", int(B), int(D), int(H), int(W), int(Cin), int(Cout)))
 
 
-def conv3d_tc_pack_weights(weight: torch.Tensor) -> torch.Tensor:
-    """[Cout,Cin,3,3,3] fp32 -> fp16 hi/lo shared-memory images per (tap, 64-channel chunk)."""
+def conv3d_tc_pack_weights(weight: torch.Tensor):
+    """[Cout,Cin,3,3,3] fp32 -> (fp16 hi/lo shared-memory images per (tap, 64-channel chunk), scale_log2)."""
     weight = _req(weight, torch.float32, "weight")
     Cout, Cin = weight.shape[:2]
     cpad = (Cin + 63) // 64 * 64
+    s = _pow2_scale(weight)
     packed = torch.empty(27 * cpad * Cout * 4, dtype=torch.uint8, device=weight.device)
-    _lib.call("gnb_conv3d_tc_pack_weights", weight.data_ptr(), Cout, Cin, packed.data_ptr(), _stream())
-    return packed
+    _lib.call("gnb_conv3d_tc_pack_weights", weight.data_ptr(), Cout, Cin, s, packed.data_ptr(), _stream())
+    return packed, s
 
 
 def gn_apply_split(x: torch.Tensor, scale, shift):
@@ -403,9 +413,65 @@ def gn_apply_split(x: torch.Tensor, scale, shift):
     return xh, xl
 
 
-def conv3d_tc(xh: torch.Tensor, xl: torch.Tensor, cin: int, w_packed: torch.Tensor, cout: int, relu: bool = True):
+def conv3d_tc(xh: torch.Tensor, xl: torch.Tensor, cin: int, w_packed, cout: int, relu: bool = True):
+    w_packed, w_s = w_packed
     B, D, H, W, _ = xh.shape
     y = torch.empty((B, D, H, W, cout), dtype=torch.float32, device=xh.device)
-    _lib.call("gnb_conv3d_tc", xh.data_ptr(), xl.data_ptr(), B, D, H, W, int(cin), w_packed.data_ptr(), int(cout),
+    _lib.call("gnb_conv3d_tc", xh.data_ptr(), xl.data_ptr(), B, D, H, W, int(cin), w_packed.data_ptr(), w_s, int(cout),
               int(relu), y.data_ptr(), _stream())
     return y
+
+
+# ---------------------------------------------------------------------------------------------- batched predict tail
+def gaussian_gradient_magnitude_batched(v: torch.Tensor, sigma: float) -> torch.Tensor:
+    """v [N,D,H,W]: N independent volumes in one set of launches."""
+    v = _req(v, torch.float32, "v")
+    N, D, H, W = v.shape
+    out = torch.empty_like(v)
+    tmp = torch.empty((2,) + tuple(v.shape), dtype=torch.float32, device=v.device)
+    _lib.call("gnb_gaussian_gradient_magnitude_batched", v.data_ptr(), N, D, H, W, float(sigma), out.data_ptr(),
+              tmp.data_ptr(), _stream())
+    return out
+
+
+def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0, 1.0), gradient_direction: str = "ascent",
+                         ggm: Optional[torch.Tensor] = None):
+    """Marching cubes of N volumes [N,D,H,W] with ONE host synchronisation: all classify/scan passes are enqueued
+    first, the N (V, F, min, max) records come back in a single device->host copy, then the emit passes are enqueued.
+    Returns a list of (verts, faces, normals, values, ggm_at) or the exception skimage would raise for that volume
+    (ValueError: level outside the data range, RuntimeError: no surface)."""
+    import ctypes
+    import numpy as np
+    volumes = _req(volumes, torch.float32, "volumes")
+    N, D, H, W = volumes.shape
+    dev = volumes.device
+    lib = _lib.load()
+    ws_bytes = (int(lib.gnb_mc_workspace_bytes(D, H, W)) + 255) // 256 * 256
+    off = int(lib.gnb_mc_totals_offset(D, H, W))
+    ws = torch.empty((N, ws_bytes), dtype=torch.uint8, device=dev)
+    for i in range(N):
+        _lib.call("gnb_mc_count", volumes[i].data_ptr(), D, H, W, float(level), ws[i].data_ptr(), None, _stream())
+    rec = ws[:, off:off + 512].cpu().numpy()  # the one synchronisation
+    totals = rec[:, :16].copy().view(np.int64)
+    enc = rec[:, 256:264].copy().view(np.uint32)
+    sp = (ctypes.c_double * 3)(*[float(x) for x in spacing])
+    out = []
+    for i in range(N):
+        lo, hi = (np.where(e & 0x80000000, e & 0x7FFFFFFF, ~e).astype(np.uint32).view(np.float32) for e in (enc[i, :1], enc[i, 1:2]))
+        V, Fc = int(totals[i, 0]), int(totals[i, 1])
+        if level < float(lo[0]) or level > float(hi[0]):
+            out.append(ValueError("Surface level must be within volume data range."))
+            continue
+        if V == 0:
+            out.append(RuntimeError("No surface found at the given iso value."))
+            continue
+        verts = torch.empty((V, 3), dtype=torch.float32, device=dev)
+        faces = torch.empty((Fc, 3), dtype=torch.int32, device=dev)
+        normals = torch.empty((V, 3), dtype=torch.float32, device=dev)
+        values = torch.empty((V,), dtype=torch.float32, device=dev)
+        ggm_at = torch.empty((V,), dtype=torch.float32, device=dev) if ggm is not None else None
+        _lib.call("gnb_mc_emit", volumes[i].data_ptr(), D, H, W, float(level), ctypes.cast(sp, ctypes.c_void_p).value,
+                  1 if gradient_direction == "ascent" else 0, _ptr(ggm[i]) if ggm is not None else None, ws[i].data_ptr(),
+                  verts.data_ptr(), faces.data_ptr(), normals.data_ptr(), values.data_ptr(), _ptr(ggm_at), _stream())
+        out.append((verts, faces, normals, values, ggm_at))
+    return out

@@ -219,9 +219,11 @@ class ImplicitWNFDecoder(nn.Module):
     def forward(self, features_grid: torch.Tensor, query_points: torch.Tensor) -> torch.Tensor:
         """features_grid (N,C,D,H,W), query_points (N,M,3) -> (N,M,Cout).  Query coordinate 0 indexes the volume's
         LAST axis (the reference does not flip xyz for grid_sample, networks/conv_implicit_wnf.py:135-142)."""
-        vol = ops.to_channels_last(features_grid)
+        return self.forward_hoisted(self.hoisted(ops.to_channels_last(features_grid)), query_points)
+
+    def forward_hoisted(self, u: torch.Tensor, query_points: torch.Tensor) -> torch.Tensor:
+        """Same as ``forward`` with Linear1 already applied on the grid (``u`` = ``hoisted(features_grid)``)."""
         N, M = query_points.shape[:2]
-        u = self.hoisted(vol)
         bn = self.mlp[0][2] if len(self.mlp[0]) > 2 else None
         if bn is not None:
             sc, sh = bn.folded_affine()
@@ -234,7 +236,8 @@ class ImplicitWNFDecoder(nn.Module):
             bn.running_mean.copy_(pre.mean(0))
             bn.running_var.copy_(pre.var(0, unbiased=False).clamp_min(1e-2))
             sc, sh = bn.folded_affine()
-        h = ops.trilinear_sample(u, query_points.contiguous(), flip=False, bn_scale=sc, bn_shift=sh)
+        with profiling.tag(f"{self.profile_tag}_interp"):
+            h = ops.trilinear_sample(u, query_points.contiguous(), flip=False, bn_scale=sc, bn_shift=sh)
         return self._tail(h).view(N, M, -1)
 
     def forward_lattice(self, u_grid: torch.Tensor, b: int, Q: int, m0: int, M: int,
@@ -352,27 +355,35 @@ class ConvImplicitWNFPipeline(nn.Module):
         spacing = 1 / (Q - 1)
         fvol = ops.to_channels_last(u["out_feature_volume"])
         nocs_data = p["nocs_data"]
+        # tail for the whole batch: one set of ggm launches, one host synchronisation for all marching-cubes counts,
+        # Linear1 of the surface decoder hoisted onto the feature grids once
+        ggm = ops.gaussian_gradient_magnitude_batched(wnf, gradient_sigma)
+        mark("ggm")
+        mcs = ops.marching_cubes_batch(wnf, iso_surface_level, (spacing,) * 3, gradient_direction, ggm)
+        mark("marching_cubes")
+        dec = self.surface_decoder
+        u_surf = dec.hoisted(fvol)
         results = []
         for b in range(B):
-            ggm = ops.gaussian_gradient_magnitude(wnf[b], gradient_sigma)
-            r: Dict[str, torch.Tensor] = {}
-            try:
-                verts, faces, normals, values, ggm_at = ops.marching_cubes(wnf[b], iso_surface_level, (spacing,) * 3,
-                                                                           gradient_direction, ggm)
-                warp = self.surface_decoder(fvol[b:b + 1].permute(0, 4, 1, 2, 3), verts.view(1, -1, 3)).view(-1, 3)
-                r = {"verts": verts, "faces": faces, "normals": normals, "volume_value": values,
-                     "volume_gradient_magnitude": ggm_at, "warp_field": warp}
-            except ValueError:  # level outside the volume's range: NaN placeholder mesh (ref predict.py:165-189)
+            mc = mcs[b]
+            if isinstance(mc, ValueError):  # level outside the volume's range: NaN placeholder mesh (ref predict.py:165-189)
                 nan = float("nan")
                 dev = wnf.device
                 r = {"verts": torch.full((1, 3), nan, device=dev), "faces": torch.zeros((1, 3), dtype=torch.int32, device=dev),
                      "normals": torch.full((1, 3), nan, device=dev), "volume_value": torch.full((1,), nan, device=dev),
                      "volume_gradient_magnitude": torch.full((1,), nan, device=dev),
                      "warp_field": torch.full((1, 3), nan, device=dev)}
+            elif isinstance(mc, Exception):
+                raise mc  # skimage's RuntimeError ("No surface found") is not caught by the reference either
+            else:
+                verts, faces, normals, values, ggm_at = mc
+                warp = dec.forward_hoisted(u_surf[b:b + 1], verts.view(1, -1, 3)).view(-1, 3)
+                r = {"verts": verts, "faces": faces, "normals": normals, "volume_value": values,
+                     "volume_gradient_magnitude": ggm_at, "warp_field": warp}
             if keep_volume:
                 r["wnf_volume"] = wnf[b]
-                r["wnf_ggm"] = ggm
+                r["wnf_ggm"] = ggm[b]
             results.append(r)
-        mark("ggm_mc_surface")
+        mark("surface_decode")
         self._last_point_outputs = {"pred_nocs": nocs_data.pos, "pred_confidence": nocs_data.pred_confidence}
         return results

@@ -155,13 +155,16 @@ int32_t gnb_conv3d_k3(const float* x, int32_t B, int32_t D, int32_t H, int32_t W
  *   gnb_groupnorm_stats -> gnb_gn_apply_split (x*scale+shift written once as fp16 hi + lo, channels zero-padded to a
  *   multiple of 64: xh, xl f16[B,D,H,W,Cpad]) -> gnb_conv3d_tc (per tap and 64-channel chunk two TMA box loads with
  *   hardware zero fill = the conv padding, weights from the images made by gnb_conv3d_tc_pack_weights
- *   (27 * Cpad * Cout * 4 bytes), products as hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM). */
+ *   (27 * Cpad * Cout * 4 bytes, weights pre-multiplied by 2^scale_log2 so their fp16 lo parts stay normal; the
+ *   same scale_log2 is passed to gnb_conv3d_tc and undone exactly in its epilogue), products as hi*hi + lo*hi + hi*lo
+ *   with fp32 accumulation in TMEM). */
 int32_t gnb_conv3d_tc_supported(int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout);
-int32_t gnb_conv3d_tc_pack_weights(const float* W, int32_t Cout, int32_t Cin, void* packed, void* stream);
+int32_t gnb_conv3d_tc_pack_weights(const float* W, int32_t Cout, int32_t Cin, int32_t scale_log2, void* packed,
+                                   void* stream);
 int32_t gnb_gn_apply_split(const float* x, int32_t B, int64_t voxels, int32_t C, const float* scale, const float* shift,
                            void* xh, void* xl, void* stream);
 int32_t gnb_conv3d_tc(const void* xh, const void* xl, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin,
-                      const void* w_packed, int32_t Cout, int32_t relu, float* y, void* stream);
+                      const void* w_packed, int32_t scale_log2, int32_t Cout, int32_t relu, float* y, void* stream);
 int32_t gnb_maxpool3d_2(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, float* y, void* stream);
 /* y[b,d,h,w, 0:Cs] = skip[b,d,h,w,:];  y[..., Cs:Cs+Cx] = x[b, d*Dx/D, h*Hx/H, w*Wx/W, :] (nearest). */
 int32_t gnb_upsample_concat(const float* skip, int32_t Cs, const float* x, int32_t Cx, int32_t B,
@@ -197,11 +200,14 @@ int32_t gnb_trilinear_sample_grid(const float* vol, int32_t b, int32_t D, int32_
  *          (i,j,k)/(Q-1) of every sample b < B (ref predict.py:145-158); U f32[B,G,G,G,256] is Linear1 applied on the
  *          feature grid (it commutes with the interpolation); out f32[B, Q^3, Cout].
  *   Q == 0 (row mode): H1 = X f32[R,256] (row stride ldx, even) given explicitly; out f32[R, Cout].
- * w2_packed: W2 re-laid by gnb_pack_f16_split (N*K*4 bytes).  scratch: f32[1024] workspace.  bn*_scale/shift may be
+ * w2_packed: W2 * 2^scale_log2 re-laid by gnb_pack_f16_split (N*K*4 bytes); the power-of-two scale (chosen by the
+ * caller so that max|W2| * 2^s < 2^14) keeps the fp16 lo parts out of the subnormal range and is undone exactly in
+ * the epilogue (w2_scale_log2).  scratch: f32[1024] workspace.  bn*_scale/shift may be
  * NULL (= identity) except bn1 in lattice mode. */
-int32_t gnb_pack_f16_split(const float* W, int32_t N, int32_t K, void* packed, void* stream);
+int32_t gnb_pack_f16_split(const float* W, int32_t N, int32_t K, int32_t scale_log2, void* packed, void* stream);
 int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t Q, int64_t R,
-                      const float* bn1_scale, const float* bn1_shift, const void* w2_packed, const float* b2,
+                      const float* bn1_scale, const float* bn1_shift, const void* w2_packed, int32_t w2_scale_log2,
+                      const float* b2,
                       const float* bn2_scale, const float* bn2_shift, const float* W3, const float* b3,
                       const float* bn3_scale, const float* bn3_shift, int32_t Cout, float* scratch, float* out,
                       void* stream);
@@ -211,6 +217,9 @@ int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t
  * v f32[D,H,W] -> out f32[D,H,W]; tmp f32[2*D*H*W] workspace.  truncate = 4.0 (scipy default). */
 int32_t gnb_gaussian_gradient_magnitude(const float* v, int32_t D, int32_t H, int32_t W, double sigma,
                                         float* out, float* tmp, void* stream);
+/* nvol independent volumes v f32[nvol,D,H,W] in one set of launches; tmp f32[2*nvol*D*H*W]. */
+int32_t gnb_gaussian_gradient_magnitude_batched(const float* v, int32_t nvol, int32_t D, int32_t H, int32_t W,
+                                                double sigma, float* out, float* tmp, void* stream);
 
 /* ---- N12: marching cubes -------------------------------------------------------------------
  * ref: predict.py:172-181 `marching_cubes(wnf, level, spacing, gradient_direction, method='lewiner')`
@@ -222,6 +231,10 @@ int32_t gnb_gaussian_gradient_magnitude(const float* v, int32_t D, int32_t H, in
  * Vertex numbering = first-use order of a sequential axis0->axis1->axis2 cell scan; faces in cell order.
  * ws: workspace of gnb_mc_workspace_bytes(D,H,W) bytes, shared by both calls. */
 int64_t gnb_mc_workspace_bytes(int32_t D, int32_t H, int32_t W);
+/* Byte offset, inside the workspace, of the block {i64 V, i64 F} (+256: {u32 enc(min), u32 enc(max)} order-preserving
+ * encodings of the data range).  gnb_mc_count with counts_host == NULL is fully asynchronous; a caller that processes
+ * many volumes can then fetch all totals with ONE device->host copy instead of one synchronisation per volume. */
+int64_t gnb_mc_totals_offset(int32_t D, int32_t H, int32_t W);
 int32_t gnb_mc_count(const float* v, int32_t D, int32_t H, int32_t W, float level, void* ws,
                      int64_t* counts_host, void* stream);
 int32_t gnb_mc_emit(const float* v, int32_t D, int32_t H, int32_t W, float level, const double* spacing_host,

@@ -138,3 +138,20 @@ def test_mc_full_size_properties(dev):
     flat = f[:, ::-1].reshape(-1)  # 'ascent' stores (c,b,a); creation order is a,b,c
     np.minimum.at(first, flat, np.arange(len(flat)))
     assert np.all(np.diff(first) > 0)
+
+
+@pytest.mark.gpu
+def test_mc_batch_equals_single_and_reports_errors(dev):
+    """One-synchronisation batch API == per-volume API; per-volume errors are returned, not raised."""
+    from garmentnets_b200 import ops
+    vols = np.stack([_sphere(24), _torus(24), np.full((24, 24, 24), 0.1, np.float32), _noise((24, 24, 24), 7)])
+    vt = torch.from_numpy(vols).to(dev)
+    ggm = ops.gaussian_gradient_magnitude_batched(vt, 0.5)
+    for i in range(4):
+        assert torch.equal(ggm[i], ops.gaussian_gradient_magnitude(vt[i], 0.5))
+    res = ops.marching_cubes_batch(vt, 0.5, (1 / 23,) * 3, "ascent", ggm)
+    assert isinstance(res[2], ValueError)
+    for i in (0, 1, 3):
+        single = ops.marching_cubes(vt[i], 0.5, (1 / 23,) * 3, "ascent", ggm[i])
+        for a, b in zip(res[i], single):
+            assert torch.equal(a, b)
