@@ -12,7 +12,12 @@
 // the tap offset -- out-of-bounds rows/columns are zero-filled by the TMA unit, which is exactly the conv padding --
 // straight into the UMMA K-major SWIZZLE_128B layout, plus two bulk copies of the pre-packed weight images.
 // Like the decoder kernel, products are formed as hi*hi + lo*hi + hi*lo (fp32 accumulation in TMEM) to stay within the
-// 1e-4 fp32 parity bound.  Warp roles: TMA/bulk loader, MMA issuer, 4 epilogue warps (tcgen05.ld -> ReLU -> fp32 NDHWC
+// 1e-4 fp32 parity bound.  The tensor core's fp32 accumulator truncates on every accumulation, which is a systematic
+// bias of ~0.5 ulp per tcgen05.mma: over the 27*Cin/16*3 = 648 instructions of a 128-channel layer that is ~4e-5
+// relative per layer (measured: 2.3e-4 after the 15 layers of the UNet).  The accumulation chain is therefore cut:
+// the hi*hi products rotate over THREE accumulators (stage mod 3) and the two small cross terms go to a fourth, so no
+// accumulator sees more than 27*Cin/64*4/3 instructions of full-magnitude addends; the epilogue adds the four in fp32
+// with round-to-nearest.  Warp roles: TMA/bulk loader, MMA issuer, 4 epilogue warps (tcgen05.ld -> ReLU -> fp32 NDHWC
 // stores); accumulators are double-buffered in TMEM so the epilogue of tile t overlaps the MMAs of tile t+1.
 #include "common.cuh"
 #include <cuda.h>
@@ -92,6 +97,7 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
 }  // namespace ctc
 
 constexpr int CT_M = 128, CT_KC = 64, CT_THREADS = 192, CT_MAX_STAGES = 4;
+constexpr int CT_NACC = 4;  // 3 rotating hi*hi accumulators + 1 for the cross terms
 constexpr int CT_A_BYTES = CT_M * CT_KC * 2;  // 16 KB per precision part
 
 struct ConvTcParams {
@@ -100,6 +106,8 @@ struct ConvTcParams {
     int nchunk;                // Cpad / 64
     int nstages, stage_bytes, b_bytes;  // b_bytes = Cout*128 (one precision part of one weight piece)
     int relu;
+    int nbuf;                  // 2: accumulator sets double-buffered in TMEM (4*acc_stride*2 <= 512 columns), else 1
+    int acc_stride;            // TMEM columns between accumulators: Cout rounded up to a power of two (32/64/128)
     float out_scale;           // 2^-s: undoes the power-of-two scaling applied to the packed weights
     const uint8_t* w_packed;   // [27][nchunk][hi,lo][Cout*128 B]
     float* y;                  // [B,D,H,W,Cout] fp32
@@ -171,25 +179,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
             uint32_t st = 0;
             int it = 0;
             for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const int db = it & 1;
-                mbar_wait(d_empty(db), ((it >> 1) & 1) ^ 1);
+                const int db = it % p.nbuf;
+                mbar_wait(d_empty(db), ((it / p.nbuf) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(db * 256);
+                const uint32_t d_set = tmem_base + (uint32_t)(db * CT_NACC * p.acc_stride);
+                const uint32_t d_cross = d_set + 3u * p.acc_stride;
                 for (int ks = 0; ks < ksteps; ++ks, ++st) {
                     const int slot = st % p.nstages;
                     mbar_wait(full(slot), (st / p.nstages) & 1);
                     tc_fence_after();
                     const uint32_t ahi = sbase + slot * p.stage_bytes, alo = ahi + CT_A_BYTES;
                     const uint32_t bhi = ahi + 2 * CT_A_BYTES, blo = bhi + p.b_bytes;
+                    const uint32_t d_main = d_set + (uint32_t)((ks % 3) * p.acc_stride);
 #pragma unroll
                     for (int kk = 0; kk < CT_KC / 16; ++kk)
-                        umma_f16(d_tmem, umma_desc(ahi + kk * 32), umma_desc(bhi + kk * 32), idesc, (ks | kk) != 0);
+                        umma_f16(d_main, umma_desc(ahi + kk * 32), umma_desc(bhi + kk * 32), idesc, (ks >= 3) || kk != 0);
 #pragma unroll
                     for (int kk = 0; kk < CT_KC / 16; ++kk)
-                        umma_f16(d_tmem, umma_desc(alo + kk * 32), umma_desc(bhi + kk * 32), idesc, 1);
+                        umma_f16(d_cross, umma_desc(alo + kk * 32), umma_desc(bhi + kk * 32), idesc, (ks | kk) != 0);
 #pragma unroll
                     for (int kk = 0; kk < CT_KC / 16; ++kk)
-                        umma_f16(d_tmem, umma_desc(ahi + kk * 32), umma_desc(blo + kk * 32), idesc, 1);
+                        umma_f16(d_cross, umma_desc(ahi + kk * 32), umma_desc(blo + kk * 32), idesc, 1);
                     umma_commit(empty(slot));
                 }
                 umma_commit(d_full(db));
@@ -213,14 +223,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
             const int id = (int)(t % nbd); t /= nbd;
             const int64_t vox = ((((int64_t)t * p.bb + lb) * p.D + id * p.bd + ld) * p.H + ih * p.bh + lh) * p.W + iw * p.bw + lw;
             float* dst = p.y + vox * p.Cout;
-            const int db = it & 1;
-            mbar_wait(d_full(db), (it >> 1) & 1);
+            const int db = it % p.nbuf;
+            mbar_wait(d_full(db), (it / p.nbuf) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(db * 256);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(db * CT_NACC * p.acc_stride);
             for (int n0 = 0; n0 < p.Cout; n0 += 32) {
-                uint32_t v[32];
+                uint32_t v[32], u[32];
                 tmem_ld32(taddr + n0, v);
+                tmem_ld32(taddr + p.acc_stride + n0, u);
                 tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                tmem_ld32(taddr + 2 * p.acc_stride + n0, u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                tmem_ld32(taddr + 3 * p.acc_stride + n0, u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 o;
@@ -319,7 +340,7 @@ extern "C" {
 int32_t gnb_conv3d_tc_pack_weights(const float* W, int32_t Cout, int32_t Cin, int32_t scale_log2, void* packed,
                                    void* stream) {
     GNB_REQUIRE(W && packed, "gnb_conv3d_tc_pack_weights: null pointer");
-    GNB_REQUIRE(Cout % 32 == 0 && Cout >= 32 && Cout <= 256 && Cin > 0, "gnb_conv3d_tc_pack_weights: Cout must be a multiple of 32 in [32,256]");
+    GNB_REQUIRE(Cout % 32 == 0 && Cout >= 32 && Cout <= 128 && Cin > 0, "gnb_conv3d_tc_pack_weights: Cout must be a multiple of 32 in [32,128]");
     const int Cpad = ceil_div(Cin, CT_KC) * CT_KC;
     const int64_t total = (int64_t)27 * Cpad * Cout;
     pack_conv_weights_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, as_stream(stream)>>>(
@@ -343,7 +364,7 @@ int32_t gnb_conv3d_tc_supported(int32_t B, int32_t D, int32_t H, int32_t W, int3
     auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
     if (!(pow2(D) && pow2(H) && pow2(W) && pow2(B))) return 0;
     if ((int64_t)B * D * H * W < CT_M) return 0;
-    if (Cout % 32 != 0 || Cout < 32 || Cout > 256 || Cin < 1) return 0;
+    if (Cout % 32 != 0 || Cout < 32 || Cout > 128 || Cin < 1) return 0;  // 4 accumulators x Cout columns <= 512
     return 1;
 }
 
@@ -356,6 +377,8 @@ int32_t gnb_conv3d_tc(const void* xh, const void* xl, int32_t B, int32_t D, int3
     ConvTcParams p;
     p.B = B; p.D = D; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu;
     p.out_scale = ldexpf(1.0f, -scale_log2);
+    p.acc_stride = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
+    p.nbuf = (CT_NACC * p.acc_stride * 2 <= 512) ? 2 : 1;
     p.Cpad = ceil_div(Cin, CT_KC) * CT_KC;
     p.nchunk = p.Cpad / CT_KC;
     int rem = CT_M;

@@ -151,7 +151,7 @@ int32_t gnb_conv3d_k3(const float* x, int32_t B, int32_t D, int32_t H, int32_t W
                       const float* scale, const float* shift, const float* Wt, int32_t Cout,
                       int32_t relu, float* y, void* stream);
 /* Tensor-core (TMA + tcgen05) version of gnb_conv3d_k3 for power-of-two grids with at least 128 voxels in the batch and
- * Cout in {32,64,...,256} (gnb_conv3d_tc_supported).  Three launches per 'gcr' SingleConv:
+ * Cout in {32,64,96,128} (gnb_conv3d_tc_supported).  Three launches per 'gcr' SingleConv:
  *   gnb_groupnorm_stats -> gnb_gn_apply_split (x*scale+shift written once as fp16 hi + lo, channels zero-padded to a
  *   multiple of 64: xh, xl f16[B,D,H,W,Cpad]) -> gnb_conv3d_tc (per tap and 64-channel chunk two TMA box loads with
  *   hardware zero fill = the conv padding, weights from the images made by gnb_conv3d_tc_pack_weights
