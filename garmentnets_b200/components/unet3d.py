@@ -262,13 +262,17 @@ class Abstract3DUNet(nn.Module):
         else:
             self.final_activation = None
 
-    def forward_ndhwc(self, x: torch.Tensor) -> torch.Tensor:
+    def forward_ndhwc(self, x: torch.Tensor, apply_final: bool = True) -> torch.Tensor:
+        """``apply_final=False`` stops before ``final_conv`` (the fast tier folds that 1x1x1 convolution into the
+        implicit decoders' first Linear: two affine maps in a row are one)."""
         skips = []
         for enc in self.encoders:
             x = enc.forward_ndhwc(x)
             skips.append(x)
         for dec, skip in zip(self.decoders, reversed(skips[:-1])):
             x = dec.forward_ndhwc(skip, x)
+        if not apply_final:
+            return x
         # 1x1x1 convolution with bias == per-voxel linear layer on channels-last data
         B, D, H, W, C = x.shape
         w = self.final_conv.weight.view(self.final_conv.out_channels, C)

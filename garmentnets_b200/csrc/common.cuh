@@ -50,4 +50,33 @@ __device__ __forceinline__ float sqdist_nofma(float ax, float ay, float az, floa
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// ---- trilinear sampling set-up (grid_sample: bilinear, padding border, align_corners), shared by gridding.cu and
+// decode_tc.cu so that both paths blend with identical weights
+struct TriW { int64_t off[8]; float w[8]; };
+
+// coordinates in [-1,1] along (W,H,D) -> 8 corner offsets (in voxels*C units) and weights, ATen order
+// tnw,tne,tsw,tse,bnw,bne,bsw,bse.  Out-of-range corners (index == size) get weight 0 and a clamped offset.
+__device__ __forceinline__ void trilinear_setup(float gx, float gy, float gz, int D, int H, int W, int C, TriW& t) {
+    float ix = ((gx + 1.f) / 2.f) * (float)(W - 1);
+    float iy = ((gy + 1.f) / 2.f) * (float)(H - 1);
+    float iz = ((gz + 1.f) / 2.f) * (float)(D - 1);
+    ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
+    iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
+    iz = fminf((float)(D - 1), fmaxf(iz, 0.f));
+    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const float x1w = ix - fx, y1w = iy - fy, z1w = iz - fz;          // (ix - ix_tnw)
+    const float x0w = (fx + 1.f) - ix, y0w = (fy + 1.f) - iy, z0w = (fz + 1.f) - iz;  // (ix_bse - ix)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
+        const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
+        const bool ok = xx < W && yy < H && zz < D;
+        const float w = (dx ? x1w : x0w) * (dy ? y1w : y0w) * (dz ? z1w : z0w);
+        t.w[k] = ok ? w : 0.f;
+        const int xc = xx < W ? xx : W - 1, yc = yy < H ? yy : H - 1, zc = zz < D ? zz : D - 1;
+        t.off[k] = (((int64_t)zc * H + yc) * W + xc) * C;
+    }
+}
+
 }  // namespace gnb

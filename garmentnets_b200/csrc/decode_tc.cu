@@ -34,6 +34,7 @@ constexpr int B_PIECE_BYTES = TC_N * TC_KCHUNK * 2;      // 32 KB
 constexpr int B_SLOTS = 3;
 constexpr int TC_THREADS = 448;  // 8 producer + 4 epilogue + MMA + loader warps
 constexpr int TC_MAX_G = 64;
+constexpr int TC_MAX_B = 128;   // QUERY mode: samples per launch (row offsets cached in shared memory)
 // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = F16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
@@ -47,7 +48,9 @@ struct TcSmem {
     static constexpr int tmem_ptr = bars + n_bars * 8;
     static constexpr int ztab = tmem_ptr + 16;                        // [128] {int z0, float wz1}
     static constexpr int kstart = ztab + TC_M * 8;                    // [G+1] first row of every D-cell
+    static constexpr int qptr = ztab;                                 // QUERY: [TC_MAX_B + 1] i64 sample row offsets (aliases ztab/kstart)
     static constexpr int total = kstart + (TC_MAX_G + 2) * 4;
+    static_assert((TC_MAX_B + 1) * 8 <= total - ztab, "qptr table must fit in the lattice tables it aliases");
 };
 static_assert(TcSmem::total + 1024 <= 227 * 1024, "shared memory budget");
 
@@ -144,11 +147,16 @@ struct TcParams {
     const float* tail;      // [COUT][4] = {c0 = sum(bn2_shift*W3) + b3, bn3_scale, bn3_shift, 0}
     float* out;             // [rows, COUT]
     int64_t num_tiles;
+    const float* q;         // QUERY: [R,3] query points in [0,1]^3 (coordinate 0 -> W axis, un-flipped grid_sample)
+    const int64_t* qptr;    // QUERY: [B+1] first row of every sample (rows of sample b sample U[b])
 };
 
-template <int COUT, bool LATTICE>
+// MODE 0: rows of a given H1 matrix; 1: implicit 128^3 lattice; 2: explicit query points (ragged per sample)
+template <int COUT, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 decode_tc_kernel(const TcParams p) {
+    constexpr bool LATTICE = MODE == 1;
+    constexpr bool QUERY = MODE == 2;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms need a 1024-byte aligned base
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -182,6 +190,10 @@ decode_tc_kernel(const TcParams p) {
         zt[2 * k] = (int)fz;
         reinterpret_cast<float*>(zt)[2 * k + 1] = iz - fz;
     }
+    if (QUERY) {
+        int64_t* qp = reinterpret_cast<int64_t*>(smem + TcSmem::qptr);
+        for (int i = threadIdx.x; i <= p.B; i += TC_THREADS) qp[i] = p.qptr[i];
+    }
     if (warp == 12) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + TcSmem::tmem_ptr), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -208,7 +220,7 @@ decode_tc_kernel(const TcParams p) {
         uint8_t* a_lo = smem + TcSmem::a_lo + chunk * A_CHUNK_BYTES;
         const int* kst = reinterpret_cast<const int*>(smem + TcSmem::kstart);
         float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
-        if (LATTICE) { sc0 = p.bn1_scale[c0]; sc1 = p.bn1_scale[c0 + 1]; sh0 = p.bn1_shift[c0]; sh1 = p.bn1_shift[c0 + 1]; }
+        if (LATTICE || QUERY) { sc0 = p.bn1_scale[c0]; sc1 = p.bn1_scale[c0 + 1]; sh0 = p.bn1_shift[c0]; sh1 = p.bn1_shift[c0 + 1]; }
         const int* zt = reinterpret_cast<const int*>(smem + TcSmem::ztab);
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -288,6 +300,70 @@ decode_tc_kernel(const TcParams p) {
                         }
                     }
                     pc[0] = pc[NG];
+                }
+            } else if (QUERY) {
+                // Each lane prepares the interpolation of two of this warp's 64 rows (corner offsets + weights, same
+                // arithmetic as gnb_trilinear_sample), then the warp walks the rows: the set-up of row r is broadcast
+                // with shuffles and every lane gathers its two channels of the 8 corners (8-byte loads, two rows =
+                // 16 loads in flight), blends, applies ReLU + BN1 and stores the fp16 hi/lo pair.
+                const int64_t r0 = tile * TC_M + half * (TC_M / 2);
+                const int G = p.G;
+                const int64_t* qp = reinterpret_cast<const int64_t*>(smem + TcSmem::qptr);
+                int off[2][8];
+                float wgt[2][8];
+                int64_t sbase_off[2];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int64_t r = r0 + h2 * 32 + lane;
+                    sbase_off[h2] = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { off[h2][k] = 0; wgt[h2][k] = 0.f; }
+                    if (r < p.R) {
+                        int lo_b = 0, hi_b = p.B;  // largest b with qptr[b] <= r
+                        while (hi_b - lo_b > 1) { const int mid = (lo_b + hi_b) >> 1; if (qp[mid] <= r) lo_b = mid; else hi_b = mid; }
+                        sbase_off[h2] = (int64_t)lo_b * G * G * G * TC_K;
+                        const float g0 = __fsub_rn(__fmul_rn(2.0f, __ldg(p.q + r * 3)), 1.0f);
+                        const float g1 = __fsub_rn(__fmul_rn(2.0f, __ldg(p.q + r * 3 + 1)), 1.0f);
+                        const float g2 = __fsub_rn(__fmul_rn(2.0f, __ldg(p.q + r * 3 + 2)), 1.0f);
+                        TriW t;
+                        trilinear_setup(g0, g1, g2, G, G, G, TC_K, t);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { off[h2][k] = (int)t.off[k]; wgt[h2][k] = t.w[k]; }
+                    }
+                }
+                const float* ubase = p.U + c0;
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+#pragma unroll 1
+                    for (int src = 0; src < 32; src += 2) {
+                        float2 v[2][8];
+                        float w[2][8];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int64_t sb = __shfl_sync(0xffffffffu, sbase_off[h2], src + u);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int o = __shfl_sync(0xffffffffu, off[h2][k], src + u);
+                                w[u][k] = __shfl_sync(0xffffffffu, wgt[h2][k], src + u);
+                                v[u][k] = __ldg(reinterpret_cast<const float2*>(ubase + sb + o));
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            float h0 = 0.f, h1 = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) { h0 = fmaf(v[u][k].x, w[u][k], h0); h1 = fmaf(v[u][k].y, w[u][k], h1); }
+                            h0 = fmaxf(h0, 0.f) * sc0 + sh0;
+                            h1 = fmaxf(h1, 0.f) * sc1 + sh1;
+                            const int k = half * (TC_M / 2) + h2 * 32 + src + u;
+                            if (tile * TC_M + k >= p.R) { h0 = 0.f; h1 = 0.f; }
+                            uint32_t hi, lo;
+                            split_f16x2(h0, h1, hi, lo);
+                            const uint32_t o2 = sw128_offset(k, 2 * lane);
+                            *reinterpret_cast<uint32_t*>(a_hi + o2) = hi;
+                            *reinterpret_cast<uint32_t*>(a_lo + o2) = lo;
+                        }
+                    }
                 }
             } else {
                 const int64_t r0 = tile * TC_M;
@@ -455,13 +531,13 @@ __global__ void fold_tail_kernel(const float* __restrict__ W3, const float* __re
     }
 }
 
-template <int COUT, bool LATTICE>
+template <int COUT, int MODE>
 static int32_t launch_decode_tc(const TcParams& p, cudaStream_t st) {
     const int smem = TcSmem::total + 1024;
-    GNB_CUDA(cudaFuncSetAttribute(decode_tc_kernel<COUT, LATTICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GNB_CUDA(cudaFuncSetAttribute(decode_tc_kernel<COUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = sm_count();
     if ((int64_t)grid > p.num_tiles) grid = (int)p.num_tiles;
-    decode_tc_kernel<COUT, LATTICE><<<grid, TC_THREADS, smem, st>>>(p);
+    decode_tc_kernel<COUT, MODE><<<grid, TC_THREADS, smem, st>>>(p);
     return check_launch("gnb_decode_tc");
 }
 
@@ -505,14 +581,44 @@ int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t
     p.b2 = b2; p.w3s = w3s; p.tail = tail; p.out = out;
     p.acc_scale = ldexpf(1.0f, -w2_scale_log2);
     p.num_tiles = lattice ? (int64_t)B * Q * Q : ceil_div<int64_t>(R, TC_M);
+    p.q = nullptr; p.qptr = nullptr;
     if (lattice) {
-        if (Cout == 1) return launch_decode_tc<1, true>(p, st);
-        if (Cout == 2) return launch_decode_tc<2, true>(p, st);
-        return launch_decode_tc<3, true>(p, st);
+        if (Cout == 1) return launch_decode_tc<1, 1>(p, st);
+        if (Cout == 2) return launch_decode_tc<2, 1>(p, st);
+        return launch_decode_tc<3, 1>(p, st);
     }
-    if (Cout == 1) return launch_decode_tc<1, false>(p, st);
-    if (Cout == 2) return launch_decode_tc<2, false>(p, st);
-    return launch_decode_tc<3, false>(p, st);
+    if (Cout == 1) return launch_decode_tc<1, 0>(p, st);
+    if (Cout == 2) return launch_decode_tc<2, 0>(p, st);
+    return launch_decode_tc<3, 0>(p, st);
+}
+
+int32_t gnb_decode_tc_query(const float* U, int32_t B, int32_t G, const float* q, const int64_t* qptr, int64_t R,
+                            const float* bn1_scale, const float* bn1_shift, const void* w2_packed, int32_t w2_scale_log2,
+                            const float* b2, const float* bn2_scale, const float* bn2_shift, const float* W3,
+                            const float* b3, const float* bn3_scale, const float* bn3_shift, int32_t Cout,
+                            float* scratch, float* out, void* stream) {
+    GNB_REQUIRE(U && q && qptr && bn1_scale && bn1_shift && w2_packed && b2 && W3 && scratch && out,
+                "gnb_decode_tc_query: null pointer");
+    GNB_REQUIRE(Cout >= 1 && Cout <= 3, "gnb_decode_tc_query: Cout must be 1..3 (got %d)", Cout);
+    GNB_REQUIRE(B >= 1 && B <= TC_MAX_B && G >= 2 && (int64_t)G * G * G * TC_K < (1ll << 31),
+                "gnb_decode_tc_query: need 1 <= B <= %d samples and a feature grid below 2^31 elements", TC_MAX_B);
+    GNB_REQUIRE(R >= 0, "gnb_decode_tc_query: negative row count");
+    if (R == 0) return GNB_OK;
+    cudaStream_t st = as_stream(stream);
+    float* w3s = scratch;
+    float* tail = scratch + 3 * TC_N;
+    fold_tail_kernel<<<Cout, TC_N, 0, st>>>(W3, b3, bn2_scale, bn2_shift, bn3_scale, bn3_shift, Cout, w3s, tail);
+    TcParams p;
+    p.U = U; p.ldx = 0; p.B = B; p.G = G; p.Q = 0; p.R = R;
+    p.bn1_scale = bn1_scale; p.bn1_shift = bn1_shift;
+    p.w2_packed = reinterpret_cast<const uint8_t*>(w2_packed);
+    p.b2 = b2; p.w3s = w3s; p.tail = tail; p.out = out;
+    p.acc_scale = ldexpf(1.0f, -w2_scale_log2);
+    p.num_tiles = ceil_div<int64_t>(R, TC_M);
+    p.q = q; p.qptr = qptr;
+    if (Cout == 1) return launch_decode_tc<1, 2>(p, st);
+    if (Cout == 2) return launch_decode_tc<2, 2>(p, st);
+    return launch_decode_tc<3, 2>(p, st);
 }
 
 }  // extern "C"

@@ -170,33 +170,6 @@ nocs_head_kernel(const float* __restrict__ logits, int64_t R, int bins, int64_t*
 }
 
 // ---- trilinear sampling (grid_sample: bilinear, padding border, align_corners) ------------------------
-struct TriW { int64_t off[8]; float w[8]; };
-
-// coordinates in [-1,1] along (W,H,D) -> 8 corner offsets (in voxels*C units) and weights, ATen order
-// tnw,tne,tsw,tse,bnw,bne,bsw,bse.  Out-of-range corners (index == size) get weight 0 and a clamped offset.
-__device__ __forceinline__ void trilinear_setup(float gx, float gy, float gz, int D, int H, int W, int C, TriW& t) {
-    float ix = ((gx + 1.f) / 2.f) * (float)(W - 1);
-    float iy = ((gy + 1.f) / 2.f) * (float)(H - 1);
-    float iz = ((gz + 1.f) / 2.f) * (float)(D - 1);
-    ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
-    iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
-    iz = fminf((float)(D - 1), fmaxf(iz, 0.f));
-    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
-    const float x1w = ix - fx, y1w = iy - fy, z1w = iz - fz;          // (ix - ix_tnw)
-    const float x0w = (fx + 1.f) - ix, y0w = (fy + 1.f) - iy, z0w = (fz + 1.f) - iz;  // (ix_bse - ix)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
-        const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
-        const bool ok = xx < W && yy < H && zz < D;
-        const float w = (dx ? x1w : x0w) * (dy ? y1w : y0w) * (dz ? z1w : z0w);
-        t.w[k] = ok ? w : 0.f;
-        const int xc = xx < W ? xx : W - 1, yc = yy < H ? yy : H - 1, zc = zz < D ? zz : D - 1;
-        t.off[k] = (((int64_t)zc * H + yc) * W + xc) * C;
-    }
-}
-
 template <bool GRID>
 __global__ void __launch_bounds__(256)
 trilinear_kernel(const float* __restrict__ vol, int b_fixed, int D, int H, int W, int C, const float* __restrict__ q,
@@ -234,41 +207,6 @@ trilinear_kernel(const float* __restrict__ vol, int b_fixed, int D, int H, int W
         if (post) acc = fmaxf(acc, 0.f) * bn_scale[c] + bn_shift[c];
         dst[c] = acc;
     }
-}
-
-// ---- gaussian gradient magnitude ---------------------------------------------------------------------
-struct Taps { double w[33]; int radius; };
-
-// one 1-D correlation pass along `axis` with edge replication ('nearest'), double accumulation like scipy's
-// NI_Correlate1D (symmetric / anti-symmetric pairing), float32 storage after every pass.
-// mode: 0 store v | 1 store v*v | 2 out += v*v | 3 out = sqrt(out + v*v)
-template <bool ANTI>
-__global__ void __launch_bounds__(256)
-filter1d_kernel(const float* __restrict__ in, int nvol, int D, int H, int W, int axis, Taps tp, int mode,
-                float* __restrict__ out) {
-    const int64_t total = (int64_t)nvol * D * H * W;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int w = (int)(i % W), h = (int)((i / W) % H), d = (int)((i / ((int64_t)W * H)) % D);
-    const int len = axis == 0 ? D : (axis == 1 ? H : W);
-    const int pos = axis == 0 ? d : (axis == 1 ? h : w);
-    const int64_t stride = axis == 0 ? (int64_t)H * W : (axis == 1 ? W : 1);
-    const float* line = in + i - (int64_t)pos * stride;
-    const int R = tp.radius;
-    double acc = ANTI ? 0.0 : (double)line[(int64_t)pos * stride] * tp.w[R];
-    for (int k = R; k >= 1; --k) {  // farthest pair first, like NI_Correlate1D
-        int lo = pos - k; lo = lo < 0 ? 0 : lo;
-        int hi = pos + k; hi = hi > len - 1 ? len - 1 : hi;
-        const double a = (double)line[(int64_t)lo * stride], b = (double)line[(int64_t)hi * stride];
-        // correlation weights fw[R - k] multiplies in[pos - k]; symmetric: fw[R-k]==fw[R+k]; anti: fw[R-k]==-fw[R+k]
-        if (ANTI) acc += (a - b) * tp.w[R - k];
-        else acc += (a + b) * tp.w[R - k];
-    }
-    const float v = (float)acc;
-    if (mode == 0) out[i] = v;
-    else if (mode == 1) out[i] = __fmul_rn(v, v);
-    else if (mode == 2) out[i] = __fadd_rn(out[i], __fmul_rn(v, v));
-    else out[i] = __fsqrt_rn(__fadd_rn(out[i], __fmul_rn(v, v)));
 }
 
 }  // namespace gnb
@@ -356,53 +294,6 @@ int32_t gnb_trilinear_sample_grid(const float* vol, int32_t b, int32_t D, int32_
     trilinear_kernel<true><<<(unsigned)ceil_div<int64_t>(M, 8), 256, 0, as_stream(stream)>>>(
         vol, b, D, H, W, C, nullptr, Q, m0, M, M, 0, post, bn_scale, bn_shift, out, ldo);
     return check_launch("gnb_trilinear_sample_grid");
-}
-
-static void gaussian_taps(double sigma, int order, Taps& tp) {
-    // scipy.ndimage._filters._gaussian_kernel1d (order 0 / 1), reversed for correlate1d
-    const int R = (int)(4.0 * sigma + 0.5);
-    tp.radius = R;
-    double sum = 0.0;
-    double phi[33];
-    for (int x = -R; x <= R; ++x) { phi[x + R] = exp(-0.5 / (sigma * sigma) * (double)x * (double)x); sum += phi[x + R]; }
-    for (int x = -R; x <= R; ++x) phi[x + R] /= sum;
-    for (int x = -R; x <= R; ++x) {
-        double v = phi[x + R];
-        if (order == 1) v = ((double)x * (-1.0 / (sigma * sigma))) * v;
-        tp.w[R - x] = v;  // [::-1]
-    }
-}
-
-int32_t gnb_gaussian_gradient_magnitude_batched(const float* v, int32_t nvol, int32_t D, int32_t H, int32_t W,
-                                                double sigma, float* out, float* tmp, void* stream) {
-    GNB_REQUIRE(v && out && tmp, "gnb_gaussian_gradient_magnitude: null pointer");
-    GNB_REQUIRE(sigma > 0 && (int)(4.0 * sigma + 0.5) <= 16, "gnb_gaussian_gradient_magnitude: sigma out of range");
-    const int64_t total = (int64_t)nvol * D * H * W;
-    if (total == 0) return GNB_OK;
-    Taps g0, g1;
-    gaussian_taps(sigma, 0, g0);
-    gaussian_taps(sigma, 1, g1);
-    cudaStream_t st = as_stream(stream);
-    const unsigned grid = (unsigned)ceil_div<int64_t>(total, 256);
-    float* t1 = tmp;
-    float* t2 = tmp + total;
-    for (int a = 0; a < 3; ++a) {
-        const float* src = v;
-        for (int ax = 0; ax < 3; ++ax) {
-            const bool last = ax == 2;
-            float* dst = last ? out : (ax == 0 ? t1 : t2);
-            const int mode = !last ? 0 : (a == 0 ? 1 : (a == 1 ? 2 : 3));
-            if (ax == a) filter1d_kernel<true><<<grid, 256, 0, st>>>(src, nvol, D, H, W, ax, g1, mode, dst);
-            else filter1d_kernel<false><<<grid, 256, 0, st>>>(src, nvol, D, H, W, ax, g0, mode, dst);
-            src = dst;
-        }
-    }
-    return check_launch("gnb_gaussian_gradient_magnitude");
-}
-
-int32_t gnb_gaussian_gradient_magnitude(const float* v, int32_t D, int32_t H, int32_t W, double sigma, float* out,
-                                        float* tmp, void* stream) {
-    return gnb_gaussian_gradient_magnitude_batched(v, 1, D, H, W, sigma, out, tmp, stream);
 }
 
 }  // extern "C"

@@ -192,28 +192,52 @@ static int ensure_tables() {
 }
 
 // ---- workspace --------------------------------------------------------------------------------------------
+// One block of gnb_mc_workspace_bytes(D,H,W) bytes per volume (batch: N blocks `ws_stride` bytes apart).
 constexpr int MC_BLOCK = 256;
+struct McRec {          // 512-byte record, read back by the host in ONE copy for the whole batch
+    int64_t V, F, A;    // vertices, faces, active cells (cube index not 0 / 255)
+    int64_t vbase, fbase;  // first row of this volume in the concatenated vertex / face outputs of the batch
+    int64_t pad0[27];
+    unsigned min_enc, max_enc;  // byte 256: order-preserving encodings of the data range
+    unsigned pad1[62];
+};
+static_assert(sizeof(McRec) == 512, "McRec layout");
 struct McWs {
     uint16_t* codes;    // [ncells] cube index | face bits << 8
-    int32_t* blockV;    // [nb] -> exclusive offsets after the scan
+    int32_t* blockV;    // [nb] per-block counts -> exclusive offsets after the scan
     int32_t* blockF;    // [nb]
-    int64_t* totals;    // [2] V, F
-    unsigned* minmax;   // [2] order-preserving encodings of min / max
+    int32_t* blockA;    // [nb]
+    McRec* rec;
+    int4* active;       // [A] compacted active cells in scan order: {cell, first vertex id, first face id, code}
     int32_t* edge_map;  // [(3+MC_MAX_CEN)*D*H*W] global edge / cell centre -> vertex id
-    int64_t ncells, nb;
 };
+struct McGeom { int64_t ncells, nb; int64_t o_blockV, o_blockF, o_blockA, o_rec, o_active, o_edge, total; };
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-static McWs carve(void* ws, int D, int H, int W) {
+static McGeom geom(int D, int H, int W) {
+    McGeom g;
+    g.ncells = (int64_t)(D - 1) * (H - 1) * (W - 1);
+    g.nb = ceil_div<int64_t>(g.ncells, MC_BLOCK);
+    size_t p = align256(sizeof(uint16_t) * g.ncells);
+    g.o_blockV = p; p += align256(sizeof(int32_t) * g.nb);
+    g.o_blockF = p; p += align256(sizeof(int32_t) * g.nb);
+    g.o_blockA = p; p += align256(sizeof(int32_t) * g.nb);
+    g.o_rec = p; p += sizeof(McRec);
+    g.o_active = p; p += align256(sizeof(int4) * g.ncells);
+    g.o_edge = p; p += align256(sizeof(int32_t) * (3 + MC_MAX_CEN) * (size_t)D * H * W);
+    g.total = p;
+    return g;
+}
+struct McBatch { char* base; int64_t stride; McGeom g; };
+__host__ __device__ __forceinline__ McWs carve(const McBatch& b, int vol) {
+    char* p = b.base + (int64_t)vol * b.stride;
     McWs w;
-    w.ncells = (int64_t)(D - 1) * (H - 1) * (W - 1);
-    w.nb = ceil_div<int64_t>(w.ncells, MC_BLOCK);
-    char* p = reinterpret_cast<char*>(ws);
-    w.codes = reinterpret_cast<uint16_t*>(p); p += align256(sizeof(uint16_t) * w.ncells);
-    w.blockV = reinterpret_cast<int32_t*>(p); p += align256(sizeof(int32_t) * w.nb);
-    w.blockF = reinterpret_cast<int32_t*>(p); p += align256(sizeof(int32_t) * w.nb);
-    w.totals = reinterpret_cast<int64_t*>(p); p += 256;
-    w.minmax = reinterpret_cast<unsigned*>(p); p += 256;
-    w.edge_map = reinterpret_cast<int32_t*>(p);
+    w.codes = reinterpret_cast<uint16_t*>(p);
+    w.blockV = reinterpret_cast<int32_t*>(p + b.g.o_blockV);
+    w.blockF = reinterpret_cast<int32_t*>(p + b.g.o_blockF);
+    w.blockA = reinterpret_cast<int32_t*>(p + b.g.o_blockA);
+    w.rec = reinterpret_cast<McRec*>(p + b.g.o_rec);
+    w.active = reinterpret_cast<int4*>(p + b.g.o_active);
+    w.edge_map = reinterpret_cast<int32_t*>(p + b.g.o_edge);
     return w;
 }
 
@@ -244,36 +268,43 @@ __device__ __forceinline__ CellPos cell_pos(int64_t c, int H, int W) {
     return p;
 }
 
-__device__ __forceinline__ int block_exclusive_scan(int v, int* total_out) {
-    __shared__ int wsum[MC_BLOCK / 32];
+// exclusive scan of three small per-thread counts across the CTA (one pass: the counts are packed into one 64-bit word,
+// 21 bits each -- a CTA of 256 cells holds at most 256 * 14 vertices)
+__device__ __forceinline__ void block_exclusive_scan3(int a, int b, int c, int& oa, int& ob, int& oc, int& ta, int& tb,
+                                                      int& tc) {
+    __shared__ unsigned long long wsum[MC_BLOCK / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int incl = v;
+    const unsigned long long v = (unsigned long long)a | ((unsigned long long)b << 21) | ((unsigned long long)c << 42);
+    unsigned long long incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
     __syncthreads();  // protect wsum reuse across calls
     if (lane == 31) wsum[warp] = incl;
     __syncthreads();
-    int base = 0, tot = 0;
+    unsigned long long base = 0, tot = 0;
 #pragma unroll
     for (int w = 0; w < MC_BLOCK / 32; ++w) {
-        const int s = wsum[w];
+        const unsigned long long s = wsum[w];
         if (w < warp) base += s;
         tot += s;
     }
-    *total_out = tot;
-    return base + incl - v;
+    const unsigned long long ex = base + incl - v;
+    oa = (int)(ex & 0x1FFFFF); ob = (int)((ex >> 21) & 0x1FFFFF); oc = (int)(ex >> 42);
+    ta = (int)(tot & 0x1FFFFF); tb = (int)((tot >> 21) & 0x1FFFFF); tc = (int)(tot >> 42);
 }
 
 // ---- kernel 1: classify --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MC_BLOCK)
-mc_classify_kernel(const float* __restrict__ v, int D, int H, int W, float level, McWs ws) {
+mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float level, McBatch batch) {
+    const McWs ws = carve(batch, blockIdx.y);
+    const float* __restrict__ v = vols + (int64_t)blockIdx.y * D * H * W;
     const int64_t c = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
-    int nv = 0, nf = 0;
+    int nv = 0, nf = 0, na = 0;
     float lo = INFINITY, hi = -INFINITY;
-    if (c < ws.ncells) {
+    if (c < batch.g.ncells) {
         const CellPos p = cell_pos(c, H, W);
         float val[8];
         int idx = 0;
@@ -304,40 +335,51 @@ mc_classify_kernel(const float* __restrict__ v, int D, int H, int W, float level
         }
         ws.codes[c] = (uint16_t)(idx | (fb << 8));
         if (idx != 0 && idx != 255) {
+            na = 1;
             nf = d_mc_table[idx * 64 + fb].ntri;
             nv = __popc(d_mc_edgemask[idx] & owned_mask(p.z, p.y, p.x)) + d_mc_table[idx * 64 + fb].ncen;
         }
     }
     // block totals
-    int tv, tf;
-    block_exclusive_scan(nv, &tv);
-    block_exclusive_scan(nf, &tf);
-    if (threadIdx.x == 0) { ws.blockV[blockIdx.x] = tv; ws.blockF[blockIdx.x] = tf; }
-    // min / max of the volume (every voxel is a corner of some cell when D,H,W >= 2)
+    int ov, of, oa, tv, tf, ta;
+    block_exclusive_scan3(nv, nf, na, ov, of, oa, tv, tf, ta);
+    if (threadIdx.x == 0) { ws.blockV[blockIdx.x] = tv; ws.blockF[blockIdx.x] = tf; ws.blockA[blockIdx.x] = ta; }
+    // min / max of the volume (every voxel is a corner of some cell when D,H,W >= 2): one atomic pair per CTA
+    __shared__ float s_lo[MC_BLOCK / 32], s_hi[MC_BLOCK / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
         hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if ((threadIdx.x & 31) == 0 && lo <= hi) {
-        atomicMin(ws.minmax + 0, mc_enc(lo));
-        atomicMax(ws.minmax + 1, mc_enc(hi));
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < MC_BLOCK / 32; ++w) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
+        if (lo <= hi) {
+            atomicMin(&ws.rec->min_enc, mc_enc(lo));
+            atomicMax(&ws.rec->max_enc, mc_enc(hi));
+        }
     }
 }
 
-// ---- kernel 2: single-CTA exclusive scan of the block counts ----------------------------------------------------
+// ---- kernel 2: one CTA per volume, exclusive scan of the block counts --------------------------------------------
 __global__ void __launch_bounds__(1024)
-mc_scan_kernel(McWs ws) {
-    __shared__ long long wsum[2][32];
-    __shared__ long long ctot[2];
+mc_scan_kernel(McBatch batch) {
+    const McWs ws = carve(batch, blockIdx.x);
+    const int64_t nb = batch.g.nb;
+    __shared__ long long wsum[3][32];
+    __shared__ long long ctot[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    long long carry[2] = {0, 0};
-    for (int64_t base = 0; base < ws.nb; base += 1024) {
+    long long carry[3] = {0, 0, 0};
+    int32_t* arr[3] = {ws.blockV, ws.blockF, ws.blockA};
+    for (int64_t base = 0; base < nb; base += 1024) {
         const int64_t i = base + tid;
-        long long val[2] = {i < ws.nb ? ws.blockV[i] : 0, i < ws.nb ? ws.blockF[i] : 0};
-        long long incl[2] = {val[0], val[1]};
+        long long val[3], incl[3];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 3; ++k) {
+            val[k] = i < nb ? arr[k][i] : 0;
+            incl[k] = val[k];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 long long t = __shfl_up_sync(0xffffffffu, incl[k], o);
@@ -346,7 +388,7 @@ mc_scan_kernel(McWs ws) {
             if (lane == 31) wsum[k][warp] = incl[k];
         }
         __syncthreads();
-        if (warp < 2) {
+        if (warp < 3) {
             const long long w = wsum[warp][lane];
             long long wi = w;
 #pragma unroll
@@ -358,18 +400,53 @@ mc_scan_kernel(McWs ws) {
             if (lane == 31) ctot[warp] = wi;
         }
         __syncthreads();
-        if (i < ws.nb) {
-            ws.blockV[i] = (int32_t)(carry[0] + wsum[0][warp] + incl[0] - val[0]);
-            ws.blockF[i] = (int32_t)(carry[1] + wsum[1][warp] + incl[1] - val[1]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (i < nb) arr[k][i] = (int32_t)(carry[k] + wsum[k][warp] + incl[k] - val[k]);
+            carry[k] += ctot[k];
         }
-        carry[0] += ctot[0];
-        carry[1] += ctot[1];
         __syncthreads();
     }
-    if (tid == 0) { ws.totals[0] = carry[0]; ws.totals[1] = carry[1]; }
+    if (tid == 0) { ws.rec->V = carry[0]; ws.rec->F = carry[1]; ws.rec->A = carry[2]; }
 }
 
-// ---- kernel 3: vertices --------------------------------------------------------------------------------------
+// first output row of every volume in the concatenated vertex / face arrays of the batch
+__global__ void mc_bases_kernel(McBatch batch, int N) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int64_t v = 0, f = 0;
+    for (int i = 0; i < N; ++i) {
+        McRec* r = carve(batch, i).rec;
+        r->vbase = v; r->fbase = f;
+        v += r->V; f += r->F;
+    }
+}
+
+// ---- kernel 3: compaction of the active cells (order preserving) -------------------------------------------------
+__global__ void __launch_bounds__(MC_BLOCK)
+mc_compact_kernel(int H, int W, McBatch batch) {
+    const McWs ws = carve(batch, blockIdx.y);
+    const int64_t nb = batch.g.nb;
+    const int a0 = ws.blockA[blockIdx.x];
+    const int a1 = blockIdx.x + 1 < nb ? ws.blockA[blockIdx.x + 1] : (int)ws.rec->A;
+    if (a1 == a0) return;  // no active cell in this block (uniform branch)
+    const int64_t c = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
+    int nv = 0, nf = 0, na = 0, code = 0;
+    if (c < batch.g.ncells) {
+        code = ws.codes[c];
+        const int idx = code & 255;
+        if (idx != 0 && idx != 255) {
+            const CellPos p = cell_pos(c, H, W);
+            na = 1;
+            nf = d_mc_table[idx * 64 + (code >> 8)].ntri;
+            nv = __popc(d_mc_edgemask[idx] & owned_mask(p.z, p.y, p.x)) + d_mc_table[idx * 64 + (code >> 8)].ncen;
+        }
+    }
+    int ov, of, oa, tv, tf, ta;
+    block_exclusive_scan3(nv, nf, na, ov, of, oa, tv, tf, ta);
+    if (na) ws.active[a0 + oa] = make_int4((int)c, ws.blockV[blockIdx.x] + ov, ws.blockF[blockIdx.x] + of, code);
+}
+
+// ---- kernel 4: vertices --------------------------------------------------------------------------------------
 __device__ __forceinline__ float vol_at(const float* __restrict__ v, int D, int H, int W, int z, int y, int x) {
     z = z < 0 ? 0 : (z > D - 1 ? D - 1 : z);
     y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
@@ -394,55 +471,50 @@ __device__ __forceinline__ void edge_vertex(const float* __restrict__ v, int H, 
     c[k] = (float)((double)lo[k] + t);
 }
 
-__device__ __forceinline__ void store_vertex(int vid, const float c[3], float g[3], float val, const Spacing& sp,
+__device__ __forceinline__ void store_vertex(int64_t row, const float c[3], float g[3], float val, const Spacing& sp,
                                              const float* __restrict__ ggm, int D, int H, int W,
                                              float* __restrict__ verts, float* __restrict__ normals,
                                              float* __restrict__ values, float* __restrict__ ggm_at) {
     const double o0 = (double)c[0] * sp.s[0], o1 = (double)c[1] * sp.s[1], o2 = (double)c[2] * sp.s[2];
-    verts[(int64_t)vid * 3 + 0] = (float)o0;
-    verts[(int64_t)vid * 3 + 1] = (float)o1;
-    verts[(int64_t)vid * 3 + 2] = (float)o2;
+    verts[row * 3 + 0] = (float)o0;
+    verts[row * 3 + 1] = (float)o1;
+    verts[row * 3 + 2] = (float)o2;
     if (ggm_at != nullptr && ggm != nullptr) {
         // predict.py:179-181: (mc_verts / voxel_spacing).astype(np.uint32), float64 arithmetic
         long long i0 = (long long)(o0 / sp.s[0]), i1 = (long long)(o1 / sp.s[1]), i2 = (long long)(o2 / sp.s[2]);
         i0 = i0 < 0 ? 0 : (i0 > D - 1 ? D - 1 : i0);
         i1 = i1 < 0 ? 0 : (i1 > H - 1 ? H - 1 : i1);
         i2 = i2 < 0 ? 0 : (i2 > W - 1 ? W - 1 : i2);
-        ggm_at[vid] = ggm[(i0 * H + i1) * W + i2];
+        ggm_at[row] = ggm[(i0 * H + i1) * W + i2];
     }
     const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(g[0], g[0]), __fmul_rn(g[1], g[1])), __fmul_rn(g[2], g[2]));
     const float nrm = __fsqrt_rn(n2);
     if (nrm > 0.f) { g[0] = __fdiv_rn(g[0], nrm); g[1] = __fdiv_rn(g[1], nrm); g[2] = __fdiv_rn(g[2], nrm); }
-    normals[(int64_t)vid * 3 + 0] = g[0];
-    normals[(int64_t)vid * 3 + 1] = g[1];
-    normals[(int64_t)vid * 3 + 2] = g[2];
-    values[vid] = val;
+    normals[row * 3 + 0] = g[0];
+    normals[row * 3 + 1] = g[1];
+    normals[row * 3 + 2] = g[2];
+    values[row] = val;
 }
 
+// one thread per ACTIVE cell (compacted list: no idle lanes on the ~95 % of cells the surface does not cross)
 __global__ void __launch_bounds__(MC_BLOCK)
-mc_vertices_kernel(const float* __restrict__ v, int D, int H, int W, float level, Spacing sp,
-                   const float* __restrict__ ggm, McWs ws, float* __restrict__ verts, float* __restrict__ normals,
+mc_vertices_kernel(const float* __restrict__ vols, int D, int H, int W, float level, Spacing sp,
+                   const float* __restrict__ ggms, McBatch batch, float* __restrict__ verts, float* __restrict__ normals,
                    float* __restrict__ values, float* __restrict__ ggm_at) {
-    const int64_t c = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
-    int nv = 0;
-    unsigned own = 0;
-    int code = 0;
-    CellPos p = {0, 0, 0};
-    if (c < ws.ncells) {
-        code = ws.codes[c];
-        const int idx = code & 255;
-        if (idx != 0 && idx != 255) {
-            p = cell_pos(c, H, W);
-            own = d_mc_edgemask[idx] & owned_mask(p.z, p.y, p.x);
-            nv = __popc(own) + d_mc_table[idx * 64 + (code >> 8)].ncen;
-        }
-    }
-    int tot;
-    const int off = block_exclusive_scan(nv, &tot);
-    if (nv == 0) return;
-    const McEntry& en = d_mc_table[(code & 255) * 64 + (code >> 8)];
-    int vid = ws.blockV[blockIdx.x] + off;
+    const McWs ws = carve(batch, blockIdx.y);
+    const int64_t a = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
+    if (a >= ws.rec->A) return;
     const int64_t vol_n = (int64_t)D * H * W;
+    const float* __restrict__ v = vols + (int64_t)blockIdx.y * vol_n;
+    const float* __restrict__ ggm = ggms ? ggms + (int64_t)blockIdx.y * vol_n : nullptr;
+    const int4 act = ws.active[a];
+    const int code = act.w;
+    const CellPos p = cell_pos(act.x, H, W);
+    const unsigned own = d_mc_edgemask[code & 255] & owned_mask(p.z, p.y, p.x);
+    const McEntry& en = d_mc_table[(code & 255) * 64 + (code >> 8)];
+    if (own == 0 && en.ncen == 0) return;
+    const int64_t vbase = ws.rec->vbase;
+    int vid = act.y;
     for (int k = 0; k < en.nedge; ++k) {
         const int e = en.order[k];
         if (e >= 12) {
@@ -466,7 +538,7 @@ mc_vertices_kernel(const float* __restrict__ v, int D, int H, int W, float level
             g[0] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(val[4] - val[0], val[5] - val[1]), val[6] - val[2]), val[7] - val[3]), 0.25f);
             g[1] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(val[3] - val[0], val[2] - val[1]), val[7] - val[4]), val[6] - val[5]), 0.25f);
             g[2] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(val[1] - val[0], val[2] - val[3]), val[5] - val[4]), val[6] - val[7]), 0.25f);
-            store_vertex(vid, cc, g, vmax, sp, ggm, D, H, W, verts, normals, values, ggm_at);
+            store_vertex(vbase + vid, cc, g, vmax, sp, ggm, D, H, W, verts, normals, values, ggm_at);
             ws.edge_map[(int64_t)(3 + ci) * vol_n + ((int64_t)p.z * H + p.y) * W + p.x] = vid;
             ++vid;
             continue;
@@ -491,27 +563,24 @@ mc_vertices_kernel(const float* __restrict__ v, int D, int H, int W, float level
             const float g1 = vol_at(v, D, H, W, hi[0] + dz, hi[1] + dy, hi[2] + dx) - vol_at(v, D, H, W, hi[0] - dz, hi[1] - dy, hi[2] - dx);
             g[q] = __fadd_rn(__fmul_rn(g0, 1.0f - tt), __fmul_rn(g1, tt));
         }
-        store_vertex(vid, cc, g, vmax, sp, ggm, D, H, W, verts, normals, values, ggm_at);
+        store_vertex(vbase + vid, cc, g, vmax, sp, ggm, D, H, W, verts, normals, values, ggm_at);
         ws.edge_map[(int64_t)ax * vol_n + ((int64_t)lo[0] * H + lo[1]) * W + lo[2]] = vid;
         ++vid;
     }
 }
 
-// ---- kernel 4: faces -------------------------------------------------------------------------------------------
+// ---- kernel 5: faces -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MC_BLOCK)
-mc_faces_kernel(int D, int H, int W, int ascent, McWs ws, int32_t* __restrict__ faces) {
-    const int64_t c = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
-    int nf = 0, code = 0;
-    if (c < ws.ncells) {
-        code = ws.codes[c];
-        const int idx = code & 255;
-        if (idx != 0 && idx != 255) nf = d_mc_table[idx * 64 + (code >> 8)].ntri;
-    }
-    int tot;
-    const int off = block_exclusive_scan(nf, &tot);
-    if (nf == 0) return;
-    const CellPos p = cell_pos(c, H, W);
+mc_faces_kernel(int D, int H, int W, int ascent, McBatch batch, int32_t* __restrict__ faces) {
+    const McWs ws = carve(batch, blockIdx.y);
+    const int64_t a = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
+    if (a >= ws.rec->A) return;
+    const int4 act = ws.active[a];
+    const int code = act.w;
     const McEntry& en = d_mc_table[(code & 255) * 64 + (code >> 8)];
+    const int nf = en.ntri;
+    if (nf == 0) return;
+    const CellPos p = cell_pos(act.x, H, W);
     const int64_t vol_n = (int64_t)D * H * W;
     int32_t vid[12 + MC_MAX_CEN];
 #pragma unroll
@@ -525,14 +594,49 @@ mc_faces_kernel(int D, int H, int W, int ascent, McWs ws, int32_t* __restrict__ 
             vid[e] = ws.edge_map[(int64_t)c_edge_axis[e] * vol_n + ((int64_t)z0 * H + y0) * W + x0];
         }
     }
-    int64_t f = (int64_t)ws.blockF[blockIdx.x] + off;
+    int64_t f = ws.rec->fbase + act.z;
     for (int t = 0; t < nf; ++t, ++f) {
-        const int a = vid[en.tri[t * 3]], b = vid[en.tri[t * 3 + 1]], cc = vid[en.tri[t * 3 + 2]];
+        const int a0 = vid[en.tri[t * 3]], b = vid[en.tri[t * 3 + 1]], cc = vid[en.tri[t * 3 + 2]];
         // native winding: right-hand normal towards lower values ('descent'); 'ascent' reverses the columns
-        faces[f * 3 + 0] = ascent ? cc : a;
+        faces[f * 3 + 0] = ascent ? cc : a0;
         faces[f * 3 + 1] = b;
-        faces[f * 3 + 2] = ascent ? a : cc;
+        faces[f * 3 + 2] = ascent ? a0 : cc;
     }
+}
+
+// resets the per-volume records (totals, bases, data range) before a classification pass
+__global__ void mc_init_kernel(McBatch batch, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    McRec* r = carve(batch, i).rec;
+    r->V = r->F = r->A = r->vbase = r->fbase = 0;
+    r->min_enc = 0xFFFFFFFFu;
+    r->max_enc = 0u;
+}
+
+static int32_t count_batch(const float* v, int N, int D, int H, int W, float level, void* ws_, int64_t ws_stride,
+                           cudaStream_t st) {
+    if (ensure_tables() != 0) { set_error("gnb_mc_count: table upload failed"); return GNB_ERR_CUDA; }
+    McBatch b = {reinterpret_cast<char*>(ws_), ws_stride, geom(D, H, W)};
+    mc_init_kernel<<<ceil_div(N, 128), 128, 0, st>>>(b, N);
+    mc_classify_kernel<<<dim3((unsigned)b.g.nb, N), MC_BLOCK, 0, st>>>(v, D, H, W, level, b);
+    mc_scan_kernel<<<N, 1024, 0, st>>>(b);
+    mc_bases_kernel<<<1, 32, 0, st>>>(b, N);
+    mc_compact_kernel<<<dim3((unsigned)b.g.nb, N), MC_BLOCK, 0, st>>>(H, W, b);
+    return check_launch("gnb_mc_count");
+}
+
+static int32_t emit_batch(const float* v, int N, int D, int H, int W, float level, const double* spacing_host,
+                          int ascent, const float* ggm, void* ws_, int64_t ws_stride, int64_t max_active, float* verts,
+                          int32_t* faces, float* normals, float* values, float* ggm_at, cudaStream_t st) {
+    McBatch b = {reinterpret_cast<char*>(ws_), ws_stride, geom(D, H, W)};
+    if (max_active <= 0) return GNB_OK;
+    if (max_active > b.g.ncells) max_active = b.g.ncells;
+    Spacing sp = {{spacing_host[0], spacing_host[1], spacing_host[2]}};
+    const dim3 grid((unsigned)ceil_div<int64_t>(max_active, MC_BLOCK), N);
+    mc_vertices_kernel<<<grid, MC_BLOCK, 0, st>>>(v, D, H, W, level, sp, ggm, b, verts, normals, values, ggm_at);
+    mc_faces_kernel<<<grid, MC_BLOCK, 0, st>>>(D, H, W, ascent, b, faces);
+    return check_launch("gnb_mc_emit");
 }
 
 }  // namespace gnb
@@ -542,42 +646,31 @@ using namespace gnb;
 extern "C" {
 
 int64_t gnb_mc_workspace_bytes(int32_t D, int32_t H, int32_t W) {
-    if (D < 2 || H < 2 || W < 2) return 256;
-    const int64_t ncells = (int64_t)(D - 1) * (H - 1) * (W - 1);
-    const int64_t nb = ceil_div<int64_t>(ncells, MC_BLOCK);
-    return (int64_t)(align256(sizeof(uint16_t) * ncells) + 2 * align256(sizeof(int32_t) * nb) + 512 +
-                     align256(sizeof(int32_t) * (3 + MC_MAX_CEN) * (size_t)D * H * W));
+    if (D < 2 || H < 2 || W < 2) return 512;
+    return geom(D, H, W).total;
 }
 
 int64_t gnb_mc_totals_offset(int32_t D, int32_t H, int32_t W) {
     if (D < 2 || H < 2 || W < 2) return 0;
-    McWs ws = carve(nullptr, D, H, W);
-    return (int64_t)(reinterpret_cast<char*>(ws.totals) - reinterpret_cast<char*>(0));
+    return geom(D, H, W).o_rec;
 }
 
 int32_t gnb_mc_count(const float* v, int32_t D, int32_t H, int32_t W, float level, void* ws_, int64_t* counts_host,
                      void* stream) {
     GNB_REQUIRE(v && ws_, "gnb_mc_count: null pointer");
     GNB_REQUIRE(D >= 2 && H >= 2 && W >= 2, "gnb_mc_count: volume must be at least 2x2x2");
-    if (ensure_tables() != 0) { set_error("gnb_mc_count: table upload failed"); return GNB_ERR_CUDA; }
     cudaStream_t st = as_stream(stream);
-    McWs ws = carve(ws_, D, H, W);
-    const unsigned init[2] = {0xFFFFFFFFu, 0u};
-    GNB_CUDA(cudaMemcpyAsync(ws.minmax, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    mc_classify_kernel<<<(unsigned)ws.nb, MC_BLOCK, 0, st>>>(v, D, H, W, level, ws);
-    mc_scan_kernel<<<1, 1024, 0, st>>>(ws);
-    int32_t rc = check_launch("gnb_mc_count");
+    const McGeom g = geom(D, H, W);
+    int32_t rc = count_batch(v, 1, D, H, W, level, ws_, g.total, st);
     if (rc != GNB_OK) return rc;
-    if (counts_host == nullptr) return GNB_OK;  // asynchronous form: the caller reads the totals block itself
-    struct { int64_t tot[2]; } h;
-    unsigned mm[2];
-    GNB_CUDA(cudaMemcpyAsync(&h, ws.totals, sizeof(h), cudaMemcpyDeviceToHost, st));
-    GNB_CUDA(cudaMemcpyAsync(mm, ws.minmax, sizeof(mm), cudaMemcpyDeviceToHost, st));
+    if (counts_host == nullptr) return GNB_OK;  // asynchronous form: the caller reads the record itself
+    McRec h;
+    GNB_CUDA(cudaMemcpyAsync(&h, reinterpret_cast<char*>(ws_) + g.o_rec, sizeof(h), cudaMemcpyDeviceToHost, st));
     GNB_CUDA(cudaStreamSynchronize(st));
-    counts_host[0] = h.tot[0];
-    counts_host[1] = h.tot[1];
+    counts_host[0] = h.V;
+    counts_host[1] = h.F;
     auto dec = [](unsigned e) { unsigned b = (e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e; float f; memcpy(&f, &b, 4); return f; };
-    const float lo = dec(mm[0]), hi = dec(mm[1]);
+    const float lo = dec(h.min_enc), hi = dec(h.max_enc);
     if (level < lo || level > hi) {
         set_error("Surface level must be within volume data range.");
         return GNB_ERR_NO_SURFACE;
@@ -590,13 +683,31 @@ int32_t gnb_mc_emit(const float* v, int32_t D, int32_t H, int32_t W, float level
                     float* values, float* ggm_at_verts, void* stream) {
     GNB_REQUIRE(v && ws_ && verts && faces && normals && values && spacing_host, "gnb_mc_emit: null pointer");
     GNB_REQUIRE(D >= 2 && H >= 2 && W >= 2, "gnb_mc_emit: volume must be at least 2x2x2");
-    cudaStream_t st = as_stream(stream);
-    McWs ws = carve(ws_, D, H, W);
-    Spacing sp = {{spacing_host[0], spacing_host[1], spacing_host[2]}};
-    mc_vertices_kernel<<<(unsigned)ws.nb, MC_BLOCK, 0, st>>>(v, D, H, W, level, sp, ggm, ws, verts, normals, values,
-                                                           ggm_at_verts);
-    mc_faces_kernel<<<(unsigned)ws.nb, MC_BLOCK, 0, st>>>(D, H, W, ascent, ws, faces);
-    return check_launch("gnb_mc_emit");
+    const McGeom g = geom(D, H, W);
+    // the active-cell count lives on the device; the grid covers the worst case and surplus CTAs exit at once
+    return emit_batch(v, 1, D, H, W, level, spacing_host, ascent, ggm, ws_, g.total, g.ncells, verts, faces, normals,
+                      values, ggm_at_verts, as_stream(stream));
+}
+
+int32_t gnb_mc_count_batch(const float* v, int32_t N, int32_t D, int32_t H, int32_t W, float level, void* ws,
+                           int64_t ws_stride, void* stream) {
+    GNB_REQUIRE(v && ws, "gnb_mc_count_batch: null pointer");
+    GNB_REQUIRE(N >= 1 && N <= 65535, "gnb_mc_count_batch: 1 <= N <= 65535 volumes");
+    GNB_REQUIRE(D >= 2 && H >= 2 && W >= 2, "gnb_mc_count_batch: volumes must be at least 2x2x2");
+    GNB_REQUIRE(ws_stride >= geom(D, H, W).total && ws_stride % 256 == 0,
+                "gnb_mc_count_batch: ws_stride must be a multiple of 256 >= gnb_mc_workspace_bytes");
+    return count_batch(v, N, D, H, W, level, ws, ws_stride, as_stream(stream));
+}
+
+int32_t gnb_mc_emit_batch(const float* v, int32_t N, int32_t D, int32_t H, int32_t W, float level,
+                          const double* spacing_host, int32_t ascent, const float* ggm, void* ws, int64_t ws_stride,
+                          int64_t max_active, float* verts, int32_t* faces, float* normals, float* values,
+                          float* ggm_at_verts, void* stream) {
+    GNB_REQUIRE(v && ws && verts && faces && normals && values && spacing_host, "gnb_mc_emit_batch: null pointer");
+    GNB_REQUIRE(N >= 1 && N <= 65535, "gnb_mc_emit_batch: 1 <= N <= 65535 volumes");
+    GNB_REQUIRE(D >= 2 && H >= 2 && W >= 2, "gnb_mc_emit_batch: volumes must be at least 2x2x2");
+    return emit_batch(v, N, D, H, W, level, spacing_host, ascent, ggm, ws, ws_stride, max_active, verts, faces, normals,
+                      values, ggm_at_verts, as_stream(stream));
 }
 
 }  // extern "C"

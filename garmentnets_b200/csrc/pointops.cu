@@ -310,20 +310,49 @@ pointconv_gather_kernel(const float* __restrict__ xf, int64_t ldx, int Cin, cons
     }
 }
 
+// one warp per (segment, block of 128 channels): each lane owns 4 consecutive channels (16-byte loads when the rows
+// are 16-byte aligned), four rows in flight.  Empty segments produce 0 (torch_scatter's fill for 'max').
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 segment_max_kernel(const float* __restrict__ rows, int64_t ldr, const int64_t* __restrict__ offs, int64_t nseg,
                    int C, float* __restrict__ out, int64_t ldo) {
     const int lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= nseg) return;
+    const int c = blockIdx.y * 128 + lane * 4;
+    if (c >= C) return;
     const int64_t e0 = offs[i], e1 = offs[i + 1];
-    for (int c = lane; c < C; c += 32) {
-        float m = 0.f;
+    float m[4] = {0.f, 0.f, 0.f, 0.f};
+    if (VEC) {
         if (e1 > e0) {
-            m = rows[e0 * ldr + c];
-            for (int64_t e = e0 + 1; e < e1; ++e) m = fmaxf(m, rows[e * ldr + c]);
+            const float* p = rows + c;
+            float4 a = __ldg(reinterpret_cast<const float4*>(p + e0 * ldr));
+            int64_t e = e0 + 1;
+            for (; e + 3 < e1; e += 4) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p + e * ldr));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p + (e + 1) * ldr));
+                const float4 b2 = __ldg(reinterpret_cast<const float4*>(p + (e + 2) * ldr));
+                const float4 b3 = __ldg(reinterpret_cast<const float4*>(p + (e + 3) * ldr));
+                a.x = fmaxf(fmaxf(fmaxf(a.x, b0.x), fmaxf(b1.x, b2.x)), b3.x);
+                a.y = fmaxf(fmaxf(fmaxf(a.y, b0.y), fmaxf(b1.y, b2.y)), b3.y);
+                a.z = fmaxf(fmaxf(fmaxf(a.z, b0.z), fmaxf(b1.z, b2.z)), b3.z);
+                a.w = fmaxf(fmaxf(fmaxf(a.w, b0.w), fmaxf(b1.w, b2.w)), b3.w);
+            }
+            for (; e < e1; ++e) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p + e * ldr));
+                a.x = fmaxf(a.x, b0.x); a.y = fmaxf(a.y, b0.y); a.z = fmaxf(a.z, b0.z); a.w = fmaxf(a.w, b0.w);
+            }
+            m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
         }
-        out[i * ldo + c] = m;
+        *reinterpret_cast<float4*>(out + i * ldo + c) = make_float4(m[0], m[1], m[2], m[3]);
+    } else {
+        const int nc = C - c < 4 ? C - c : 4;
+        if (e1 > e0) {
+            for (int k = 0; k < nc; ++k) m[k] = rows[e0 * ldr + c + k];
+            for (int64_t e = e0 + 1; e < e1; ++e)
+                for (int k = 0; k < nc; ++k) m[k] = fmaxf(m[k], rows[e * ldr + c + k]);
+        }
+        for (int k = 0; k < nc; ++k) out[i * ldo + c + k] = m[k];
     }
 }
 
@@ -436,8 +465,11 @@ int32_t gnb_segment_max(const float* rows, int64_t ldr, const int64_t* offs, int
                         int64_t ldo, void* stream) {
     GNB_REQUIRE(rows && offs && out, "gnb_segment_max: null pointer");
     if (nseg == 0 || C == 0) return GNB_OK;
-    segment_max_kernel<<<(unsigned)ceil_div<int64_t>(nseg, 8), 256, 0, as_stream(stream)>>>(rows, ldr, offs, nseg, C,
-                                                                                         out, ldo);
+    const dim3 grid((unsigned)ceil_div<int64_t>(nseg, 8), (unsigned)ceil_div(C, 128));
+    const bool vec = C % 4 == 0 && ldr % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (vec) segment_max_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(rows, ldr, offs, nseg, C, out, ldo);
+    else segment_max_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(rows, ldr, offs, nseg, C, out, ldo);
     return check_launch("gnb_segment_max");
 }
 

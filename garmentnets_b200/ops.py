@@ -296,12 +296,20 @@ def trilinear_sample_grid(vol: torch.Tensor, b: int, Q: int, m0: int, M: int, bn
     return out
 
 
+def _ggm_tmp(v: torch.Tensor, sigma: float) -> Optional[torch.Tensor]:
+    """Workspace of the multi-pass form; the fused single-pass kernel (filter radius int(4*sigma + 0.5) <= 4, which
+    covers the shipped sigma = 0.5) needs none."""
+    if int(4.0 * float(sigma) + 0.5) <= 4:
+        return None
+    return torch.empty((2,) + tuple(v.shape), dtype=torch.float32, device=v.device)
+
+
 def gaussian_gradient_magnitude(v: torch.Tensor, sigma: float) -> torch.Tensor:
     v = _req(v, torch.float32, "v")
     D, H, W = v.shape
     out = torch.empty_like(v)
-    tmp = torch.empty((2,) + tuple(v.shape), dtype=torch.float32, device=v.device)
-    _lib.call("gnb_gaussian_gradient_magnitude", v.data_ptr(), D, H, W, float(sigma), out.data_ptr(), tmp.data_ptr(),
+    tmp = _ggm_tmp(v, sigma)
+    _lib.call("gnb_gaussian_gradient_magnitude", v.data_ptr(), D, H, W, float(sigma), out.data_ptr(), _ptr(tmp),
               _stream())
     return out
 
@@ -386,6 +394,28 @@ def decode_tc(w2_packed, b2, bn2, W3, b3, bn3, *, U=None, Q=0, bn1=None, X=None,
     return out
 
 
+def decode_tc_query(w2_packed, b2, bn2, W3, b3, bn3, *, U, q, qptr, bn1, out=None) -> torch.Tensor:
+    """Query mode of the tensor-core decoder (``gnb_decode_tc_query``): ``U`` [B,G,G,G,256] hoisted grids, ``q`` [R,3]
+    query points of all samples back to back, ``qptr`` device i64[B+1] row offsets -> [R, Cout]."""
+    w2_packed, w2_s = w2_packed
+    Cout = W3.shape[0]
+    dev = W3.device
+    q = _req(q, torch.float32, "q")
+    qptr = _req(qptr, torch.int64, "qptr")
+    B, G = U.shape[0], U.shape[1]
+    assert U.is_contiguous() and U.shape[-1] == 256 and qptr.numel() == B + 1
+    R = q.shape[0]
+    if out is None:
+        out = torch.empty((R, Cout), dtype=torch.float32, device=dev)
+    s2, h2 = bn2 if bn2 is not None else (None, None)
+    s3, h3 = bn3 if bn3 is not None else (None, None)
+    scratch = torch.empty(1024, dtype=torch.float32, device=dev)
+    _lib.call("gnb_decode_tc_query", U.data_ptr(), B, G, q.data_ptr(), qptr.data_ptr(), R, bn1[0].data_ptr(),
+              bn1[1].data_ptr(), w2_packed.data_ptr(), w2_s, b2.data_ptr(), _ptr(s2), _ptr(h2), W3.data_ptr(), _ptr(b3),
+              _ptr(s3), _ptr(h3), Cout, scratch.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- tensor-core 3x3x3 conv
 def conv3d_tc_supported(B, D, H, W, Cin, Cout) -> bool:
     return bool(_lib.call("gnb_conv3d_tc_supported", int(B), int(D), int(H), int(W), int(Cin), int(Cout)))
@@ -428,50 +458,61 @@ def gaussian_gradient_magnitude_batched(v: torch.Tensor, sigma: float) -> torch.
     v = _req(v, torch.float32, "v")
     N, D, H, W = v.shape
     out = torch.empty_like(v)
-    tmp = torch.empty((2,) + tuple(v.shape), dtype=torch.float32, device=v.device)
+    tmp = _ggm_tmp(v, sigma)
     _lib.call("gnb_gaussian_gradient_magnitude_batched", v.data_ptr(), N, D, H, W, float(sigma), out.data_ptr(),
-              tmp.data_ptr(), _stream())
+              _ptr(tmp), _stream())
     return out
 
 
 def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0, 1.0), gradient_direction: str = "ascent",
-                         ggm: Optional[torch.Tensor] = None):
-    """Marching cubes of N volumes [N,D,H,W] with ONE host synchronisation: all classify/scan passes are enqueued
-    first, the N (V, F, min, max) records come back in a single device->host copy, then the emit passes are enqueued.
-    Returns a list of (verts, faces, normals, values, ggm_at) or the exception skimage would raise for that volume
-    (ValueError: level outside the data range, RuntimeError: no surface)."""
+                         ggm: Optional[torch.Tensor] = None, return_packed: bool = False):
+    """Marching cubes of N volumes [N,D,H,W] in seven launches and ONE host synchronisation: classify / scan / compact
+    for the whole batch, the N 512-byte records come back in a single device->host copy, then one vertex and one face
+    launch over the compacted active cells write every mesh into shared [sum V] / [sum F] buffers.
+    Returns a list of (verts, faces, normals, values, ggm_at) views or the exception skimage would raise for that volume
+    (ValueError: level outside the data range, RuntimeError: no surface).  ``return_packed`` adds the shared buffers:
+    ``{"verts": f32[sum V,3], "vptr": host i64[N+1] row offsets}`` (volumes without a mesh own zero rows)."""
     import ctypes
     import numpy as np
     volumes = _req(volumes, torch.float32, "volumes")
+    if ggm is not None:
+        ggm = _req(ggm, torch.float32, "ggm")
+    if gradient_direction not in ("ascent", "descent"):
+        raise ValueError("Incorrect input %s in `gradient_direction`" % gradient_direction)
     N, D, H, W = volumes.shape
     dev = volumes.device
     lib = _lib.load()
     ws_bytes = (int(lib.gnb_mc_workspace_bytes(D, H, W)) + 255) // 256 * 256
     off = int(lib.gnb_mc_totals_offset(D, H, W))
     ws = torch.empty((N, ws_bytes), dtype=torch.uint8, device=dev)
-    for i in range(N):
-        _lib.call("gnb_mc_count", volumes[i].data_ptr(), D, H, W, float(level), ws[i].data_ptr(), None, _stream())
+    _lib.call("gnb_mc_count_batch", volumes.data_ptr(), N, D, H, W, float(level), ws.data_ptr(), ws_bytes, _stream())
     rec = ws[:, off:off + 512].cpu().numpy()  # the one synchronisation
-    totals = rec[:, :16].copy().view(np.int64)
+    totals = rec[:, :40].copy().view(np.int64)  # V, F, A, vbase, fbase
     enc = rec[:, 256:264].copy().view(np.uint32)
-    sp = (ctypes.c_double * 3)(*[float(x) for x in spacing])
+    dec = np.where(enc & 0x80000000, enc & 0x7FFFFFFF, ~enc).astype(np.uint32).view(np.float32)
+    sumV, sumF = int(totals[:, 0].sum()), int(totals[:, 1].sum())
+    verts = torch.empty((sumV, 3), dtype=torch.float32, device=dev)
+    faces = torch.empty((sumF, 3), dtype=torch.int32, device=dev)
+    normals = torch.empty((sumV, 3), dtype=torch.float32, device=dev)
+    values = torch.empty((sumV,), dtype=torch.float32, device=dev)
+    ggm_at = torch.empty((sumV,), dtype=torch.float32, device=dev) if ggm is not None else None
+    if sumV > 0:
+        sp = (ctypes.c_double * 3)(*[float(x) for x in spacing])
+        _lib.call("gnb_mc_emit_batch", volumes.data_ptr(), N, D, H, W, float(level), ctypes.cast(sp, ctypes.c_void_p).value,
+                  1 if gradient_direction == "ascent" else 0, _ptr(ggm), ws.data_ptr(), ws_bytes, int(totals[:, 2].max()),
+                  verts.data_ptr(), faces.data_ptr(), normals.data_ptr(), values.data_ptr(), _ptr(ggm_at), _stream())
     out = []
     for i in range(N):
-        lo, hi = (np.where(e & 0x80000000, e & 0x7FFFFFFF, ~e).astype(np.uint32).view(np.float32) for e in (enc[i, :1], enc[i, 1:2]))
-        V, Fc = int(totals[i, 0]), int(totals[i, 1])
-        if level < float(lo[0]) or level > float(hi[0]):
+        V, Fc, _, vb, fb = (int(t) for t in totals[i])
+        if level < float(dec[i, 0]) or level > float(dec[i, 1]):
             out.append(ValueError("Surface level must be within volume data range."))
-            continue
-        if V == 0:
+        elif V == 0:
             out.append(RuntimeError("No surface found at the given iso value."))
-            continue
-        verts = torch.empty((V, 3), dtype=torch.float32, device=dev)
-        faces = torch.empty((Fc, 3), dtype=torch.int32, device=dev)
-        normals = torch.empty((V, 3), dtype=torch.float32, device=dev)
-        values = torch.empty((V,), dtype=torch.float32, device=dev)
-        ggm_at = torch.empty((V,), dtype=torch.float32, device=dev) if ggm is not None else None
-        _lib.call("gnb_mc_emit", volumes[i].data_ptr(), D, H, W, float(level), ctypes.cast(sp, ctypes.c_void_p).value,
-                  1 if gradient_direction == "ascent" else 0, _ptr(ggm[i]) if ggm is not None else None, ws[i].data_ptr(),
-                  verts.data_ptr(), faces.data_ptr(), normals.data_ptr(), values.data_ptr(), _ptr(ggm_at), _stream())
-        out.append((verts, faces, normals, values, ggm_at))
+        else:
+            out.append((verts[vb:vb + V], faces[fb:fb + Fc], normals[vb:vb + V], values[vb:vb + V],
+                        ggm_at[vb:vb + V] if ggm_at is not None else None))
+    if return_packed:
+        vptr = np.zeros(N + 1, np.int64)
+        np.cumsum(totals[:, 0], out=vptr[1:])
+        return out, {"verts": verts, "vptr": vptr}
     return out

@@ -186,6 +186,26 @@ class ImplicitWNFDecoder(nn.Module):
         u = ops.linear(features_grid_ndhwc.reshape(-1, C), lin.weight, lin.bias)
         return u.view(B, D, H, W, -1)
 
+    def hoisted_folded(self, x_ndhwc: torch.Tensor, final_conv: nn.Conv3d) -> torch.Tensor:
+        """``hoisted(final_conv(x))`` as ONE affine map: grid @ (W1 Wf)^T + (W1 bf + b1).  ``x`` is the last UNet
+        decoder's output [B,D,H,W,Cf] (Cf = 32): the 128-channel feature volume is never materialised and the
+        per-voxel contraction runs over 32 instead of 128 channels (ref components/unet3d.py:467 followed by
+        networks/conv_implicit_wnf.py:148, first Linear of the MLP)."""
+        lin = self.mlp[0][0]
+        wf = final_conv.weight.view(final_conv.out_channels, -1)
+        key = (lin.weight._version, lin.weight.data_ptr(), wf._version, wf.data_ptr(),
+               None if final_conv.bias is None else final_conv.bias._version)
+        cached = getattr(self, "_gnb_folded", None)
+        if cached is None or cached[0] != key:
+            w = ops.linear(wf.t().contiguous(), lin.weight).t().contiguous()          # [C1, Cf] = W1 @ Wf
+            bf = final_conv.bias if final_conv.bias is not None else torch.zeros_like(wf[:, 0])
+            b = ops.linear(bf.view(1, -1), lin.weight, lin.bias).view(-1)             # W1 bf + b1
+            cached = (key, w, b)
+            self._gnb_folded = cached
+        B, D, H, W, C = x_ndhwc.shape
+        u = ops.linear(x_ndhwc.reshape(-1, C), cached[1], cached[2])
+        return u.view(B, D, H, W, -1)
+
     # ---- tensor-core tail (tcgen05): available for the shipped shape [C, 256, 256, Cout<=3] with BatchNorm --------
     use_tensor_cores = True
 
@@ -239,6 +259,28 @@ class ImplicitWNFDecoder(nn.Module):
         with profiling.tag(f"{self.profile_tag}_interp"):
             h = ops.trilinear_sample(u, query_points.contiguous(), flip=False, bn_scale=sc, bn_shift=sh)
         return self._tail(h).view(N, M, -1)
+
+    def forward_hoisted_ragged(self, u: torch.Tensor, q_all: torch.Tensor, qptr_host) -> torch.Tensor:
+        """Query points of all samples back to back (``q_all`` [R,3]; sample b owns rows qptr[b]..qptr[b+1]-1) ->
+        [R, Cout] in one fused launch per 128 samples (gather + BN1 + tensor-core tail)."""
+        B = u.shape[0]
+        R = q_all.shape[0]
+        bn = self.mlp[0][2] if len(self.mlp[0]) > 2 else None
+        if not (self._tc_ready() and bn is not None and u.shape[-1] == 256):
+            outs = [self.forward_hoisted(u[b:b + 1], q_all[int(qptr_host[b]):int(qptr_host[b + 1])].view(1, -1, 3)).view(
+                -1, self.mlp[-1][0].out_features) for b in range(B) if qptr_host[b + 1] > qptr_host[b]]
+            return torch.cat(outs) if outs else q_all.new_empty((0, self.mlp[-1][0].out_features))
+        out = torch.empty((R, self.mlp[2][0].out_features), dtype=torch.float32, device=u.device)
+        for b0 in range(0, B, 128):
+            b1 = min(B, b0 + 128)
+            r0, r1 = int(qptr_host[b0]), int(qptr_host[b1])
+            if r1 == r0:
+                continue
+            qptr = torch.as_tensor([int(x) - r0 for x in qptr_host[b0:b1 + 1]], dtype=torch.int64).to(u.device)
+            with profiling.tag(f"{self.profile_tag}_tc"):
+                ops.decode_tc_query(*self._tc_args(), U=u[b0:b1], q=q_all[r0:r1], qptr=qptr, bn1=bn.folded_affine(),
+                                    out=out[r0:r1])
+        return out
 
     def forward_lattice(self, u_grid: torch.Tensor, b: int, Q: int, m0: int, M: int,
                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -307,13 +349,18 @@ class ConvImplicitWNFPipeline(nn.Module):
 
     # ---- fast tier: the whole predict loop on the device ------------------------------------------------------
     @torch.no_grad()
-    def dense_decode(self, out_feature_volume: torch.Tensor, volume_size: int = 128, rows_per_chunk: int = 1 << 19):
+    def dense_decode(self, out_feature_volume: Optional[torch.Tensor], volume_size: int = 128,
+                     rows_per_chunk: int = 1 << 19, hoisted: Optional[torch.Tensor] = None):
         """[B,C,G,G,G] feature volume -> [B,Q,Q,Q] winding-number volume over the implicit lattice (i,j,k)/(Q-1)
-        (ref predict.py:145-158 without grid_points, chunk copies or H2D traffic)."""
-        vol = ops.to_channels_last(out_feature_volume)
-        B = vol.shape[0]
+        (ref predict.py:145-158 without grid_points, chunk copies or H2D traffic).  ``hoisted`` = the decoder's first
+        Linear already applied on the feature grid ([B,G,G,G,C1]); then ``out_feature_volume`` is not needed."""
+        if hoisted is None:
+            vol = ops.to_channels_last(out_feature_volume)
+            u = self.volume_decoder.hoisted(vol)
+        else:
+            u = hoisted
+        B = u.shape[0]
         Q = int(volume_size)
-        u = self.volume_decoder.hoisted(vol)
         total = Q ** 3
         dec = self.volume_decoder
         if Q == 128 and dec._tc_ready() and dec.mlp[2][0].out_features == 1:
@@ -321,7 +368,7 @@ class ConvImplicitWNFPipeline(nn.Module):
             with profiling.tag("decode_tc"):
                 out = ops.decode_tc(*dec._tc_args(), U=u, Q=Q, bn1=dec.mlp[0][2].folded_affine())
             return out.view(B, Q, Q, Q)
-        out = torch.empty((B, total), dtype=torch.float32, device=vol.device)
+        out = torch.empty((B, total), dtype=torch.float32, device=u.device)
         for b in range(B):
             for m0 in range(0, total, rows_per_chunk):
                 M = min(rows_per_chunk, total - m0)
@@ -347,22 +394,27 @@ class ConvImplicitWNFPipeline(nn.Module):
         mark("pointnet2")
         vol_in = self.volume_agg(p["nocs_data"])
         mark("aggregator")
-        u = {"out_feature_volume": self.unet_3d(vol_in), "in_feature_volume": vol_in}
+        # UNet up to the last decoder; final_conv (1x1x1, affine) is folded into each implicit decoder's first Linear
+        unet = self.unet_3d.abstract_3d_unet
+        x_last = unet.forward_ndhwc(ops.to_channels_last(vol_in), apply_final=False)
         mark("unet3d")
-        wnf = self.dense_decode(u["out_feature_volume"], volume_size)
+        wnf = self.dense_decode(None, volume_size, hoisted=self.volume_decoder.hoisted_folded(x_last, unet.final_conv))
         mark("dense_decode")
         B, Q = wnf.shape[0], wnf.shape[1]
         spacing = 1 / (Q - 1)
-        fvol = ops.to_channels_last(u["out_feature_volume"])
         nocs_data = p["nocs_data"]
         # tail for the whole batch: one set of ggm launches, one host synchronisation for all marching-cubes counts,
         # Linear1 of the surface decoder hoisted onto the feature grids once
         ggm = ops.gaussian_gradient_magnitude_batched(wnf, gradient_sigma)
         mark("ggm")
-        mcs = ops.marching_cubes_batch(wnf, iso_surface_level, (spacing,) * 3, gradient_direction, ggm)
+        mcs, packed = ops.marching_cubes_batch(wnf, iso_surface_level, (spacing,) * 3, gradient_direction, ggm,
+                                               return_packed=True)
         mark("marching_cubes")
+        # warp field of every mesh vertex of the batch in one fused launch (gather + MLP on tcgen05)
         dec = self.surface_decoder
-        u_surf = dec.hoisted(fvol)
+        u_surf = dec.hoisted_folded(x_last, unet.final_conv)
+        vptr = packed["vptr"]
+        warp_all = dec.forward_hoisted_ragged(u_surf, packed["verts"], vptr)
         results = []
         for b in range(B):
             mc = mcs[b]
@@ -377,7 +429,7 @@ class ConvImplicitWNFPipeline(nn.Module):
                 raise mc  # skimage's RuntimeError ("No surface found") is not caught by the reference either
             else:
                 verts, faces, normals, values, ggm_at = mc
-                warp = dec.forward_hoisted(u_surf[b:b + 1], verts.view(1, -1, 3)).view(-1, 3)
+                warp = warp_all[int(vptr[b]):int(vptr[b + 1])]
                 r = {"verts": verts, "faces": faces, "normals": normals, "volume_value": values,
                      "volume_gradient_magnitude": ggm_at, "warp_field": warp}
             if keep_volume:

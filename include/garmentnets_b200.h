@@ -211,13 +211,26 @@ int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t
                       const float* bn2_scale, const float* bn2_shift, const float* W3, const float* b3,
                       const float* bn3_scale, const float* bn3_shift, int32_t Cout, float* scratch, float* out,
                       void* stream);
+/* Query mode of the same kernel (the surface / warp-field decoder, ref predict.py:184-187 and
+ * networks/conv_implicit_wnf.py:263-269): H1 = BN1(ReLU(trilinear(U[b], q_r))) for explicit query points q f32[R,3] in
+ * [0,1]^3 (coordinate 0 -> W axis: the reference does not flip xyz, :135-142).  Rows are ragged per sample: rows
+ * qptr[b] .. qptr[b+1]-1 (device i64[B+1], qptr[0] = 0, qptr[B] = R) sample U[b]; 1 <= B <= 128 per call.  The
+ * 8-corner gather runs inside the A-operand producer warps, so neither the interpolated features nor the hidden
+ * activations touch HBM.  out f32[R, Cout]. */
+int32_t gnb_decode_tc_query(const float* U, int32_t B, int32_t G, const float* q, const int64_t* qptr, int64_t R,
+                            const float* bn1_scale, const float* bn1_shift, const void* w2_packed,
+                            int32_t w2_scale_log2, const float* b2, const float* bn2_scale, const float* bn2_shift,
+                            const float* W3, const float* b3, const float* bn3_scale, const float* bn3_shift,
+                            int32_t Cout, float* scratch, float* out, void* stream);
 
 /* ---- N13: gaussian gradient magnitude ------------------------------------------------------
  * ref: predict.py:162-163 `ni.gaussian_gradient_magnitude(wnf, sigma, mode="nearest")` (scipy 1.7).
- * v f32[D,H,W] -> out f32[D,H,W]; tmp f32[2*D*H*W] workspace.  truncate = 4.0 (scipy default). */
+ * v f32[D,H,W] -> out f32[D,H,W].  truncate = 4.0 (scipy default), so the filter radius is int(4*sigma + 0.5).
+ * Radius <= 4 (sigma = 0.5 ships) runs as ONE fused pass over the volume and tmp may be NULL; larger radii run the
+ * nine separable passes and need tmp f32[2*D*H*W]. */
 int32_t gnb_gaussian_gradient_magnitude(const float* v, int32_t D, int32_t H, int32_t W, double sigma,
                                         float* out, float* tmp, void* stream);
-/* nvol independent volumes v f32[nvol,D,H,W] in one set of launches; tmp f32[2*nvol*D*H*W]. */
+/* nvol independent volumes v f32[nvol,D,H,W] in one launch; tmp f32[2*nvol*D*H*W] or NULL as above. */
 int32_t gnb_gaussian_gradient_magnitude_batched(const float* v, int32_t nvol, int32_t D, int32_t H, int32_t W,
                                                 double sigma, float* out, float* tmp, void* stream);
 
@@ -231,8 +244,8 @@ int32_t gnb_gaussian_gradient_magnitude_batched(const float* v, int32_t nvol, in
  * Vertex numbering = first-use order of a sequential axis0->axis1->axis2 cell scan; faces in cell order.
  * ws: workspace of gnb_mc_workspace_bytes(D,H,W) bytes, shared by both calls. */
 int64_t gnb_mc_workspace_bytes(int32_t D, int32_t H, int32_t W);
-/* Byte offset, inside the workspace, of the block {i64 V, i64 F} (+256: {u32 enc(min), u32 enc(max)} order-preserving
- * encodings of the data range).  gnb_mc_count with counts_host == NULL is fully asynchronous; a caller that processes
+/* Byte offset, inside the workspace, of the 512-byte record {i64 V, i64 F, ...} (+256: {u32 enc(min), u32 enc(max)}
+ * order-preserving encodings of the data range).  gnb_mc_count with counts_host == NULL is fully asynchronous; a caller that processes
  * many volumes can then fetch all totals with ONE device->host copy instead of one synchronisation per volume. */
 int64_t gnb_mc_totals_offset(int32_t D, int32_t H, int32_t W);
 int32_t gnb_mc_count(const float* v, int32_t D, int32_t H, int32_t W, float level, void* ws,
@@ -240,6 +253,20 @@ int32_t gnb_mc_count(const float* v, int32_t D, int32_t H, int32_t W, float leve
 int32_t gnb_mc_emit(const float* v, int32_t D, int32_t H, int32_t W, float level, const double* spacing_host,
                     int32_t ascent, const float* ggm, void* ws, float* verts, int32_t* faces,
                     float* normals, float* values, float* ggm_at_verts, void* stream);
+/* Batch form: N volumes v f32[N,D,H,W] (ggm likewise or NULL), one workspace block per volume `ws_stride` bytes apart
+ * (a multiple of 256, >= gnb_mc_workspace_bytes).  gnb_mc_count_batch is asynchronous: it classifies every volume, scans
+ * and compacts the active cells, and leaves one 512-byte record per volume at gnb_mc_totals_offset inside its block:
+ *   i64 V, F, A (active cells), vbase, fbase (first row of the volume in the concatenated outputs = exclusive prefix
+ *   sums of V and F over the batch); byte 256: u32 enc(min), enc(max).
+ * The caller fetches the N records with one strided device->host copy, sizes verts f32[sum V,3], faces i32[sum F,3],
+ * normals, values, ggm_at_verts for the whole batch, and calls gnb_mc_emit_batch with max_active = max_i A_i.  Face
+ * indices are local to their volume (0 .. V_i-1).  Five launches per batch instead of four per volume. */
+int32_t gnb_mc_count_batch(const float* v, int32_t N, int32_t D, int32_t H, int32_t W, float level, void* ws,
+                           int64_t ws_stride, void* stream);
+int32_t gnb_mc_emit_batch(const float* v, int32_t N, int32_t D, int32_t H, int32_t W, float level,
+                          const double* spacing_host, int32_t ascent, const float* ggm, void* ws, int64_t ws_stride,
+                          int64_t max_active, float* verts, int32_t* faces, float* normals, float* values,
+                          float* ggm_at_verts, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

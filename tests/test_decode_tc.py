@@ -82,3 +82,33 @@ def test_lattice_mode_full_size_vs_oracle(dev):
     ref = ON.dense_decode(sd, "volume_decoder.", fvol[:1].cpu().numpy(), 128, 64)
     err = (wnf_tc[0].cpu() - ref).abs().max().item()
     assert err < TOL, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("counts,cout", [([333, 0, 1, 700], 3), ([5], 1), ([128, 128], 2), ([0, 0, 9000], 3)])
+def test_query_mode_matches_oracle_and_row_mode(dev, counts, cout):
+    """Ragged query mode (gather fused into the tcgen05 producer) == trilinear_sample + row mode, and within 1e-4 of the
+    oracle's grid_sample + MLP; samples without rows and tiles that straddle two samples included."""
+    from garmentnets_b200 import ops
+    dec = _decoder(dev, cout, 20 + cout)
+    B = len(counts)
+    g = torch.Generator().manual_seed(sum(counts) + cout)
+    fg = (torch.randn(B, 128, 6, 6, 6, generator=g) * 0.8).to(dev)
+    qs = [torch.rand(n, 3, generator=g) for n in counts]
+    # a few points exactly on / outside the border (padding_mode='border' clamps them)
+    if counts[-1] >= 4:
+        qs[-1][:4] = torch.tensor([[0, 0, 0], [1, 1, 1], [1.2, -0.1, 0.5], [0.5, 1.0, 0.0]])
+    q_all = torch.cat(qs).to(dev)
+    qptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    u = dec.hoisted(ops.to_channels_last(fg))
+    got = dec.forward_hoisted_ragged(u, q_all, qptr).cpu()
+    assert got.shape == (sum(counts), cout)
+    sd = {k: v.cpu() for k, v in dec.state_dict().items()}
+    for b, n in enumerate(counts):
+        if n == 0:
+            continue
+        sl = slice(int(qptr[b]), int(qptr[b + 1]))
+        ref = ON.implicit_decoder(sd, "", fg[b:b + 1].cpu(), qs[b].view(1, -1, 3))[0]
+        assert (got[sl] - ref).abs().max().item() < TOL
+        rows = dec.forward_hoisted(u[b:b + 1], qs[b].view(1, -1, 3).to(dev)).view(n, cout).cpu()
+        assert (got[sl] - rows).abs().max().item() < 2e-5

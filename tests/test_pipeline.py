@@ -160,3 +160,21 @@ def test_predict_end_to_end(setup):
     assert np.median(diff) < 1e-5 and (diff > TOL).mean() < 0.02
     assert abs(len(out["verts"]) - len(mesh["verts"])) <= 0.05 * len(mesh["verts"]) + 8
     assert out["faces"].dtype == torch.int32 and out["warp_field"].shape == (len(out["verts"]), 3)
+
+
+@pytest.mark.gpu
+def test_folded_final_conv_equals_two_step(setup):
+    """predict() folds the UNet's 1x1x1 final_conv into each decoder's first Linear (two affine maps = one): the folded
+    32 -> 256 map must reproduce hoisted(final_conv(x)) (ref components/unet3d.py:467, networks/conv_implicit_wnf.py:148)."""
+    from garmentnets_b200 import ops
+    s = setup
+    model, dev = s["model"], s["dev"]
+    unet = model.unet_3d.abstract_3d_unet
+    vol_in = torch.from_numpy(np.ascontiguousarray(s["s2"]["in_feature_volume"])).to(dev)
+    x_last = unet.forward_ndhwc(ops.to_channels_last(vol_in), apply_final=False)
+    full = unet.forward_ndhwc(ops.to_channels_last(vol_in))
+    assert x_last.shape[-1] == 32 and full.shape[-1] == 128
+    for dec in (model.volume_decoder, model.surface_decoder):
+        two_step = dec.hoisted(full)
+        folded = dec.hoisted_folded(x_last, unet.final_conv)
+        assert close(folded.cpu().numpy(), two_step.cpu().numpy(), 2e-5)

@@ -165,3 +165,22 @@ def test_exclusive_scan(dev, n):
     out = ops.exclusive_scan(v).cpu().numpy()
     ref = np.concatenate([[0], np.cumsum(v.cpu().numpy().astype(np.int64))])
     assert np.array_equal(out, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nseg,C,maxlen", [(32, 1024, 512), (1000, 128, 70), (17, 6, 9), (5, 130, 40)])
+def test_segment_max_shapes(dev, nseg, C, maxlen):
+    """Segment max over CSR rows (PointConv aggregation and global_max_pool, ref components/pointnet2.py:31,49): wide
+    channel counts, channel counts that are not a multiple of 4, empty segments (-> 0) -- bit-exact."""
+    from garmentnets_b200 import ops
+    rng = np.random.default_rng(nseg + C)
+    lens = rng.integers(0, maxlen + 1, nseg)
+    lens[0] = 0
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    rows = rng.normal(size=(int(offs[-1]), C)).astype(np.float32)
+    got = ops.segment_max(torch.from_numpy(rows).to(dev), torch.from_numpy(offs).to(dev)).cpu().numpy()
+    ref = np.zeros((nseg, C), np.float32)
+    for i in range(nseg):
+        if lens[i]:
+            ref[i] = rows[offs[i]:offs[i + 1]].max(0)
+    assert np.array_equal(got, ref)
