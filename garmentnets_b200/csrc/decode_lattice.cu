@@ -1,0 +1,593 @@
+// Dense lattice decode, second generation (ref predict.py:145-158 + networks/conv_implicit_wnf.py:128-149).
+//
+// Same math as decode_tc_kernel<COUT, 1> (decode_tc.cu) -- H1 = BN1(ReLU(trilinear(U))) over the implicit 128^3 lattice,
+// Linear2 on tcgen05 with fp16 hi/lo split operands, Linear3 folded into the epilogue -- restructured around what the
+// first-generation kernel was actually bound by (ncu: tensor pipe 25 % active, producers stalled on L2 gathers, and
+// 387 KB of L2->SM traffic per 128-row tile against a ~42 B/clk/SM L2 port):
+//
+//   * a work item is a PAIR of adjacent lattice lines (i, 2jp) and (i, 2jp+1): 2 x 128 rows, two TMEM accumulators
+//     (2 x 256 columns = all of TMEM).  Every W2 piece streamed from L2 feeds both tiles (B traffic halves to 128 KB
+//     per tile) and the two lines share their four (x, y) corner columns three times out of four (gather traffic
+//     131 -> ~74 KB per tile).
+//   * the pipeline is K-chunk major: a two-slot ring of 64 KB A chunks (2 tiles x {hi, lo} x 128 rows x 64 channels);
+//     all eight producer warps fill chunk c+1 while the tensor core consumes chunk c, so the producers have the full
+//     MMA time of a chunk (24 MMAs) instead of a quarter of a tile.
+//   * producer mapping: an 8-lane group owns ONE D-cell of the feature grid for both lines and 8 consecutive channels
+//     per lane: 16-byte gathers (16 per lane per chunk, all issued before the slot wait), separable x/y blend in
+//     registers, one 16-byte swizzled shared-memory store per row and precision part.
+//   * BN1 is folded into W2 / b2 on the host (it follows the ReLU, so it is linear in front of Linear2): the A operand
+//     is ReLU(interp) only; the power-of-two weight scale is folded into b2 and W3 so the epilogue is add / max / fma.
+//
+// Warp roles (448 threads): 0-7 A producers, 8-11 epilogue (TMEM lane quarter = warp % 4), 12 MMA issuer, 13 B loader.
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace gnb {
+
+namespace dl2 {
+
+constexpr int K = 256, N = 256, M = 128, KCHUNK = 64, NCHUNK = K / KCHUNK;
+constexpr int PART_BYTES = M * KCHUNK * 2;          // 16 KB: one tile, one precision part, one K chunk
+constexpr int SLOT_BYTES = 4 * PART_BYTES;          // 64 KB: {tile0 hi, tile0 lo, tile1 hi, tile1 lo}
+constexpr int A_SLOTS = 2;
+constexpr int B_PIECE_BYTES = N * KCHUNK * 2;       // 32 KB
+constexpr int B_SLOTS = 3;
+constexpr int THREADS = 448;
+constexpr int MAX_G = 32;   // one cell pair per 16-lane producer group
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+
+struct Smem {
+    static constexpr int a = 0;                                   // [2 slots][64 KB]
+    static constexpr int b_ring = a + A_SLOTS * SLOT_BYTES;       // [3][32 KB]
+    static constexpr int bars = b_ring + B_SLOTS * B_PIECE_BYTES;
+    static constexpr int n_bars = 2 + 2 + B_SLOTS + B_SLOTS + 2 + 2;
+    static constexpr int tmem_ptr = bars + n_bars * 8;
+    static constexpr int rowtab = tmem_ptr + 16;                  // [128] {float wz1, u32 byte offset of row k inside a swizzled tile}
+    static constexpr int kstart = rowtab + M * 8;                 // [G+1]
+    static constexpr int pairs = kstart + (MAX_G + 2) * 4;        // [Q/2][2] u8: the two lines of every pair
+    static constexpr int total = pairs + M;
+};
+static_assert(Smem::total + 1024 <= 227 * 1024, "shared memory budget");
+
+struct Params {
+    const float* U;            // [B,G,G,G,256] hoisted grid (Linear1 applied on the feature grid), fp32 channels-last
+    int B, G, Q;
+    const uint8_t* w2_packed;  // (W2 * diag(bn1_scale)) * 2^s, gnb_pack_f16_split layout
+    const float* b2s;          // [256] (b2 + W2 bn1_shift) * 2^s
+    const float* w3s;          // [COUT][256] W3 * bn2_scale * 2^-s
+    const float* tail;         // [COUT][4] {c0, bn3_scale, bn3_shift, 0}
+    float* out;                // [B, Q^3, COUT]
+    int64_t num_pairs;         // B * Q * Q / 2
+    int dbg;                   // profiling aid (GNB_DL2_DBG): 1 producers idle, 2 no W2 copies, 4 epilogue math skipped
+};
+
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 issue two fp32 operations per instruction) ---------
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+// two fp32 -> packed fp16x2 (first argument in the low half), saturating to +-65504 instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+// relu + fp16 hi/lo split of two fp32 values (ascending channel order inside the 32-bit words)
+__device__ __forceinline__ void relu_split2(float2 h, uint32_t& hi, uint32_t& lo) {
+    const float x0 = fmaxf(h.x, 0.f), x1 = fmaxf(h.y, 0.f);
+    hi = pack_f16x2_sat(x0, x1);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    const float2 r = sub2(make_float2(x0, x1), hf);
+    lo = pack_f16x2_sat(r.x, r.y);
+}
+
+// mbarrier wait with a suspend-time hint: the waiting thread sleeps in hardware instead of spinning through the issue
+// slots the producer warps need
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP_S:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_S;\n\t"
+        "bra WAIT_LOOP_S;\n\t"
+        "DONE_S:\n\t"
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680)
+        : "memory");
+}
+
+// lattice index -> feature-grid cell and weights along one axis (same fp32 arithmetic as gnb_trilinear_sample_grid)
+__device__ __forceinline__ void axis_cell(int idx, float sq, int G, int& c0, int& c1, float& w0, float& w1) {
+    const float g = __fsub_rn(__fmul_rn(2.0f, __fmul_rn((float)idx, sq)), 1.0f);
+    const float f = fminf((float)(G - 1), fmaxf(((g + 1.f) / 2.f) * (float)(G - 1), 0.f));
+    const float fl = floorf(f);
+    c0 = (int)fl;
+    c1 = c0 + 1 < G ? c0 + 1 : G - 1;
+    w1 = f - fl;
+    w0 = (fl + 1.f) - f;
+}
+
+// Warp roles (448 threads): 0-7 A producers | 8-11 epilogue (TMEM lane quarter = warp % 4) | 12 MMA issuer | 13 B loader.
+// Issue priority on sm_100 goes to the HIGHEST warp id: the MMA issuer and the loader (latency critical, a handful of
+// instructions per MMA) come first, then the epilogue (it gates the reuse of the accumulators), and the producers fill
+// the remaining issue slots.  The epilogue sleeps on its barrier instead of spinning through those slots.
+template <int COUT>
+__global__ void __launch_bounds__(THREADS, 1)
+decode_lattice_kernel(const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const uint32_t bar0 = sbase + Smem::bars;
+    auto a_full = [&](int s) { return bar0 + 8 * s; };
+    auto a_empty = [&](int s) { return bar0 + 8 * (2 + s); };
+    auto b_full = [&](int s) { return bar0 + 8 * (4 + s); };
+    auto b_empty = [&](int s) { return bar0 + 8 * (4 + B_SLOTS + s); };
+    auto d_full = [&](int t) { return bar0 + 8 * (4 + 2 * B_SLOTS + t); };
+    auto d_empty = [&](int t) { return bar0 + 8 * (6 + 2 * B_SLOTS + t); };
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
+    const int Q = p.Q, G = p.G, QH = Q >> 1;
+    const float sq = __fdiv_rn(1.0f, (float)(Q - 1));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < A_SLOTS; ++s) { mbar_init(a_full(s), 8); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < B_SLOTS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(d_full(t), 1); mbar_init(d_empty(t), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x == 416) {
+        // pairing of the Q lattice lines of one i-plane: two lines of the same y-cell share their corner columns, so
+        // pairs are formed inside the runs of equal y-cell; the few left-over lines are paired with each other
+        uint8_t* pt = smem + Smem::pairs;
+        uint8_t left[M];
+        int np = 0, nl = 0, j = 0;
+        while (j < Q) {
+            int c0, c1, e = j;
+            float w0, w1;
+            axis_cell(j, sq, G, c0, c1, w0, w1);
+            for (;;) {
+                int d0, d1;
+                if (e >= Q) break;
+                axis_cell(e, sq, G, d0, d1, w0, w1);
+                if (d0 != c0) break;
+                ++e;
+            }
+            for (; j + 1 < e; j += 2) { pt[2 * np] = (uint8_t)j; pt[2 * np + 1] = (uint8_t)(j + 1); ++np; }
+            if (j < e) left[nl++] = (uint8_t)j++;
+        }
+        for (int a = 0; a + 1 < nl; a += 2) { pt[2 * np] = left[a]; pt[2 * np + 1] = left[a + 1]; ++np; }
+    }
+    if (threadIdx.x < M) {
+        // per-row blend along D (independent of the tile)
+        const int k = threadIdx.x;
+        int z0, z1;
+        float w0, w1;
+        axis_cell(k, sq, G, z0, z1, w0, w1);
+        reinterpret_cast<uint2*>(smem + Smem::rowtab)[k] =
+            make_uint2(__float_as_uint(w1), (uint32_t)((k >> 3) * 1024 + (k & 7) * 128));
+    }
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Smem::tmem_ptr), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    if (threadIdx.x <= G) {
+        // kstart[d] = first lattice row whose D-cell index is >= d (rows are monotone in k); kstart[G] = 128
+        int k = 0;
+        for (; k < M; ++k) {
+            int z0, z1;
+            float w0, w1;
+            axis_cell(k, sq, G, z0, z1, w0, w1);
+            if (z0 >= (int)threadIdx.x) break;
+        }
+        reinterpret_cast<int*>(smem + Smem::kstart)[threadIdx.x] = k;
+    }
+    __syncthreads();
+    const uint8_t* pairs = smem + Smem::pairs;
+
+    if (warp < 8) {
+        // =========================== A producers ===========================
+        // A 16-lane group owns two adjacent D-cells (three slices) of both lines and 4 consecutive channels per lane.
+        const int pw = warp;
+        const int cp = pw * 2 + (lane >> 4);      // cell pair: cells 2cp, 2cp+1
+        const int l16 = lane & 15;
+        const bool active = 2 * cp < G;           // G < 32: the surplus groups only pace the barriers
+        const int dA = 2 * cp < G ? 2 * cp : G - 1;
+        const int ds[3] = {dA, dA + 1 < G ? dA + 1 : G - 1, dA + 2 < G ? dA + 2 : G - 1};
+        const int* kst = reinterpret_cast<const int*>(smem + Smem::kstart);
+        const int64_t sd = (int64_t)G * G * K;
+        // byte offset of this lane's 8-byte store inside a 128-byte swizzled row: 16-byte unit (l16 >> 1) ^ (k & 7)
+        const uint32_t unit = (uint32_t)(l16 >> 1), sub8 = (uint32_t)(l16 & 1) * 8u;
+
+        struct Item { int b, i, j0, j1; };
+        auto item_of = [&](int64_t pr) {
+            Item it;
+            const int jp = (int)(pr % QH);
+            it.i = (int)((pr / QH) % Q);
+            it.b = (int)(pr / ((int64_t)QH * Q));
+            it.j0 = pairs[2 * jp];
+            it.j1 = pairs[2 * jp + 1];
+            return it;
+        };
+        // gathers of line `j` for chunk c: [slice][y][x] 16-byte loads
+        auto issue = [&](const Item& it, int j, int c, float4 (&r)[3][2][2]) {
+            int x0, x1, y0, y1;
+            float t0, t1;
+            axis_cell(it.i, sq, G, x0, x1, t0, t1);
+            axis_cell(j, sq, G, y0, y1, t0, t1);
+            const float* ub = p.U + (int64_t)it.b * G * sd + c * KCHUNK + l16 * 4;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const float* sp = ub + ds[s] * sd;
+                r[s][0][0] = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)y0 * G + x0) * K));
+                r[s][0][1] = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)y0 * G + x1) * K));
+                r[s][1][0] = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)y1 * G + x0) * K));
+                r[s][1][1] = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)y1 * G + x1) * K));
+            }
+        };
+
+        float4 nxt[3][2][2];
+        uint32_t q = 0;  // running chunk counter (slot = q & 1)
+        int64_t pair = blockIdx.x;
+        if (pair < p.num_pairs && active && !(p.dbg & 1)) issue(item_of(pair), item_of(pair).j0, 0, nxt);
+        for (; pair < p.num_pairs; pair += gridDim.x) {
+            const Item it = item_of(pair);
+            int x0, x1, ya0, ya1, yb0, yb1;
+            float wx0, wx1, wy0[2], wy1[2];
+            axis_cell(it.i, sq, G, x0, x1, wx0, wx1);
+            axis_cell(it.j0, sq, G, ya0, ya1, wy0[0], wy1[0]);
+            axis_cell(it.j1, sq, G, yb0, yb1, wy0[1], wy1[1]);
+            const bool same_y = ya0 == yb0;
+
+
+#pragma unroll 1
+            for (int c = 0; c < NCHUNK; ++c, ++q) {
+                const int slot = q & 1;
+                if (active && !(p.dbg & 1)) {
+                    // 1. x-blend of the prefetched corners: X[s][y] (4 channels as two packed pairs)
+                    float2 X[3][2][2];
+                    const float2 vx0 = make_float2(wx0, wx0), vx1 = make_float2(wx1, wx1);
+#pragma unroll
+                    for (int s = 0; s < 3; ++s)
+#pragma unroll
+                        for (int yy = 0; yy < 2; ++yy) {
+                            const float4 a = nxt[s][yy][0], bq = nxt[s][yy][1];
+                            X[s][yy][0] = fma2(make_float2(bq.x, bq.y), vx1, mul2(make_float2(a.x, a.y), vx0));
+                            X[s][yy][1] = fma2(make_float2(bq.z, bq.w), vx1, mul2(make_float2(a.z, a.w), vx0));
+                        }
+                    // 2. prefetch the corners of the next chunk (or of the next pair's first chunk)
+                    if (c + 1 < NCHUNK) issue(it, it.j0, c + 1, nxt);
+                    else if (pair + gridDim.x < p.num_pairs) { const Item ni = item_of(pair + gridDim.x); issue(ni, ni.j0, 0, nxt); }
+                    // 3. (x, y)-blended slices of both lines: P[l][s] (4 channels as two packed pairs)
+                    float2 P[2][3][2];
+#pragma unroll
+                    for (int l = 0; l < 2; ++l) {
+                        const float2 vy0 = make_float2(wy0[l], wy0[l]), vy1 = make_float2(wy1[l], wy1[l]);
+                        if (l == 0 || same_y) {
+#pragma unroll
+                            for (int s = 0; s < 3; ++s)
+#pragma unroll
+                                for (int h2 = 0; h2 < 2; ++h2) P[l][s][h2] = fma2(X[s][1][h2], vy1, mul2(X[s][0][h2], vy0));
+                        } else {
+                            // line 1 lies in another y-cell (left-over lines, ~3 % of the pairs): its own gathers
+                            const float* ub = p.U + (int64_t)it.b * G * sd + c * KCHUNK + l16 * 4;
+#pragma unroll
+                            for (int s = 0; s < 3; ++s) {
+                                const float* sp = ub + ds[s] * sd;
+                                const float4 a00 = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)yb0 * G + x0) * K));
+                                const float4 a10 = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)yb0 * G + x1) * K));
+                                const float4 a01 = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)yb1 * G + x0) * K));
+                                const float4 a11 = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)yb1 * G + x1) * K));
+                                const float2 xa0 = fma2(make_float2(a10.x, a10.y), vx1, mul2(make_float2(a00.x, a00.y), vx0));
+                                const float2 xa1 = fma2(make_float2(a10.z, a10.w), vx1, mul2(make_float2(a00.z, a00.w), vx0));
+                                const float2 xb0 = fma2(make_float2(a11.x, a11.y), vx1, mul2(make_float2(a01.x, a01.y), vx0));
+                                const float2 xb1 = fma2(make_float2(a11.z, a11.w), vx1, mul2(make_float2(a01.z, a01.w), vx0));
+                                P[l][s][0] = fma2(xb0, vy1, mul2(xa0, vy0));
+                                P[l][s][1] = fma2(xb1, vy1, mul2(xa1, vy0));
+                            }
+                        }
+                    }
+                    // 4. the slot must have been consumed by the tensor core (chunk q - 2)
+                    mbar_wait(a_empty(slot), ((q >> 1) & 1) ^ 1);
+                    const uint32_t a_addr = sbase + Smem::a + slot * SLOT_BYTES + sub8;  // + part * PART_BYTES + row offset
+#pragma unroll
+                    for (int cell = 0; cell < 2; ++cell) {
+                        const int d = 2 * cp + cell;
+                        if (d >= G) break;
+                        float2 sl[2][2];
+#pragma unroll
+                        for (int l = 0; l < 2; ++l) { sl[l][0] = sub2(P[l][cell + 1][0], P[l][cell][0]); sl[l][1] = sub2(P[l][cell + 1][1], P[l][cell][1]); }
+                        const int k_end = kst[d + 1];
+                        auto row = [&](int k) {
+                            uint2 rt;
+                            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rt.x), "=r"(rt.y) : "r"(sbase + Smem::rowtab + k * 8));
+                            const float wz = __uint_as_float(rt.x);
+                            const float2 vz = make_float2(wz, wz);
+                            const uint32_t addr = a_addr + rt.y + ((unit << 4) ^ ((rt.y >> 3) & 0x70u));
+#pragma unroll
+                            for (int l = 0; l < 2; ++l) {
+                                uint32_t hi0, lo0, hi1, lo1;
+                                relu_split2(fma2(sl[l][0], vz, P[l][cell][0]), hi0, lo0);
+                                relu_split2(fma2(sl[l][1], vz, P[l][cell][1]), hi1, lo1);
+                                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + (2 * l) * PART_BYTES), "r"(hi0), "r"(hi1) : "memory");
+                                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + (2 * l + 1) * PART_BYTES), "r"(lo0), "r"(lo1) : "memory");
+                            }
+                        };
+                        int k = kst[d];
+#pragma unroll 1
+                        for (; k + 1 < k_end; k += 2) { row(k); row(k + 1); }   // two rows = eight independent chains in flight
+                        if (k < k_end) row(k);
+                    }
+                } else {
+                    // no D-cell (G < 32): still pace on the slot, or an early arrival for the NEXT use of this slot would be
+                    // counted into the current phase of a_full
+                    mbar_wait(a_empty(slot), ((q >> 1) & 1) ^ 1);
+                }
+                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full(slot));
+            }
+        }
+    } else if (warp < 12) {
+        // =========================== epilogue ===========================
+        const int qd = warp & 3;  // TMEM lane quarter this warp may access (warp id mod 4)
+        const int row = qd * 32 + lane;
+        float c_tail[COUT], bn3s[COUT], bn3h[COUT];
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) { c_tail[o] = p.tail[o * 4]; bn3s[o] = p.tail[o * 4 + 1]; bn3h[o] = p.tail[o * 4 + 2]; }
+        int it = 0;
+        for (int64_t pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x, ++it) {
+            const int jp = (int)(pair % QH);
+            const int64_t plane = pair / QH;  // b * Q + i
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                mbar_wait_sleep(d_full(t), it & 1);
+                tc_fence_after();
+                float2 dot[COUT][2];
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) dot[o][0] = dot[o][1] = make_float2(0.f, 0.f);
+                const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(t * N);
+                const int ncol = (p.dbg & 4) ? 64 : N;
+                // software pipeline: the next 32 columns are in flight (tcgen05.ld) while the current 32 are folded
+                uint32_t r0[32], r1[32];
+                auto fold = [&](const uint32_t (&r)[32], int n0) {
+#pragma unroll
+                    for (int u = 0; u < 32; u += 4) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2s + n0 + u));
+                        float2 v0 = add2(make_float2(__uint_as_float(r[u]), __uint_as_float(r[u + 1])), make_float2(bb.x, bb.y));
+                        float2 v1 = add2(make_float2(__uint_as_float(r[u + 2]), __uint_as_float(r[u + 3])), make_float2(bb.z, bb.w));
+                        v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f);
+#pragma unroll
+                        for (int o = 0; o < COUT; ++o) {
+                            const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w3s + o * N + n0 + u));
+                            dot[o][0] = fma2(v0, make_float2(ww.x, ww.y), dot[o][0]);
+                            dot[o][1] = fma2(v1, make_float2(ww.z, ww.w), dot[o][1]);
+                        }
+                    }
+                };
+                tmem_ld32(taddr, r0);
+#pragma unroll 1
+                for (int n0 = 0; n0 < ncol; n0 += 64) {
+                    tmem_ld_wait();
+                    tmem_ld32(taddr + n0 + 32, r1);
+                    fold(r0, n0);
+                    tmem_ld_wait();
+                    if (n0 + 64 < ncol) {
+                        tmem_ld32(taddr + n0 + 64, r0);
+                    } else {
+                        // every TMEM read of accumulator t has completed: the next pair's MMAs may overwrite it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(d_empty(t));
+                    }
+                    fold(r1, n0 + 32);
+                }
+                const int64_t grow = (plane * Q + pairs[2 * jp + t]) * M + row;
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) {
+                    const float2 dd = add2(dot[o][0], dot[o][1]);
+                    p.out[grow * COUT + o] = fmaxf((dd.x + dd.y) + c_tail[o], 0.f) * bn3s[o] + bn3h[o];
+                }
+            }
+        }
+    } else if (warp == 12) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            int it = 0;
+            uint32_t piece = 0, q = 0;
+            for (int64_t pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x, ++it) {
+                for (int c = 0; c < NCHUNK; ++c, ++q) {
+                    const int slot = q & 1;
+                    mbar_wait(a_full(slot), (q >> 1) & 1);
+                    const uint32_t a_slot = sbase + Smem::a + slot * SLOT_BYTES;
+                    const int s_hi = piece % B_SLOTS, s_lo = (piece + 1) % B_SLOTS;
+                    const uint32_t b_hi = sbase + Smem::b_ring + s_hi * B_PIECE_BYTES, b_lo = sbase + Smem::b_ring + s_lo * B_PIECE_BYTES;
+                    // hi*hi + lo*hi of tile t against the W2_hi piece; hi*lo against the W2_lo piece
+                    // descriptors of the first K-step; the next K-steps add 32 bytes = 2 address units (no carry: the tiles
+                    // are 1024-byte aligned and far below the 14-bit address field's wrap)
+                    const uint64_t dbh = umma_desc(b_hi), dbl = umma_desc(b_lo);
+                    auto mma_hi = [&](int t) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(t * N);
+                        const uint64_t dah = umma_desc(a_slot + (2 * t) * PART_BYTES), dal = umma_desc(a_slot + (2 * t + 1) * PART_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < KCHUNK / 16; ++kk) umma_f16(d_tmem, dah + 2 * kk, dbh + 2 * kk, IDESC, (c | kk) != 0);
+#pragma unroll
+                        for (int kk = 0; kk < KCHUNK / 16; ++kk) umma_f16(d_tmem, dal + 2 * kk, dbh + 2 * kk, IDESC, 1);
+                    };
+                    auto mma_lo = [&](int t) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(t * N);
+                        const uint64_t dah = umma_desc(a_slot + (2 * t) * PART_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < KCHUNK / 16; ++kk) umma_f16(d_tmem, dah + 2 * kk, dbl + 2 * kk, IDESC, 1);
+                    };
+                    mbar_wait(b_full(s_hi), (piece / B_SLOTS) & 1);
+                    tc_fence_after();
+                    if (c == 0 || c == NCHUNK - 1) {
+                        // tile-major: accumulator 0 is released to / taken from the epilogue a whole tile (12 MMAs) before
+                        // accumulator 1, so draining one tile overlaps the other tile's MMAs
+                        if (c == 0) { mbar_wait(d_empty(0), (it & 1) ^ 1); tc_fence_after(); }
+                        mma_hi(0);
+                        mbar_wait(b_full(s_lo), ((piece + 1) / B_SLOTS) & 1);
+                        tc_fence_after();
+                        mma_lo(0);
+                        if (c == NCHUNK - 1) umma_commit(d_full(0));
+                        if (c == 0) { mbar_wait(d_empty(1), (it & 1) ^ 1); tc_fence_after(); }
+                        mma_hi(1);
+                        umma_commit(b_empty(s_hi));
+                        mma_lo(1);
+                        umma_commit(b_empty(s_lo));
+                        umma_commit(a_empty(slot));
+                        if (c == NCHUNK - 1) umma_commit(d_full(1));
+                    } else {
+                        mma_hi(0);
+                        mma_hi(1);
+                        umma_commit(b_empty(s_hi));
+                        mbar_wait(b_full(s_lo), ((piece + 1) / B_SLOTS) & 1);
+                        tc_fence_after();
+                        mma_lo(0);
+                        mma_lo(1);
+                        umma_commit(b_empty(s_lo));
+                        umma_commit(a_empty(slot));  // every MMA that reads this A slot has been issued
+                    }
+                    piece += 2;
+                }
+            }
+        }
+    } else {
+        // =========================== B loader ===========================
+        if (lane == 0) {
+            uint32_t piece = 0;
+            for (int64_t pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x) {
+                for (int pc = 0; pc < 2 * NCHUNK; ++pc, ++piece) {
+                    const int slot = piece % B_SLOTS;
+                    mbar_wait(b_empty(slot), ((piece / B_SLOTS) & 1) ^ 1);
+                    if (p.dbg & 2) { mbar_arrive(b_full(slot)); continue; }
+                    mbar_expect_tx(b_full(slot), B_PIECE_BYTES);
+                    bulk_g2s(sbase + Smem::b_ring + slot * B_PIECE_BYTES, p.w2_packed + (size_t)pc * B_PIECE_BYTES,
+                             B_PIECE_BYTES, b_full(slot));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// prep: b2s = (b2 + W2 bn1_shift) * 2^s ; w3s[o][n] = W3[o][n] * bn2_scale[n] * 2^-s ;
+//       tail[o] = {sum_n bn2_shift[n] W3[o][n] + b3[o], bn3_scale[o], bn3_shift[o], 0}
+__global__ void lattice_prep_kernel(const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ bn1_shift,
+                                    const float* __restrict__ W3, const float* __restrict__ b3, const float* __restrict__ s2,
+                                    const float* __restrict__ h2, const float* __restrict__ s3, const float* __restrict__ h3,
+                                    int cout, float wscale, float* __restrict__ b2s, float* __restrict__ w3s,
+                                    float* __restrict__ tail) {
+    const int n = threadIdx.x;  // 256 threads
+    __shared__ float red[N];
+    if (blockIdx.x == 0) {
+        float acc = b2[n];
+        for (int k = 0; k < K; ++k) acc = fmaf(W2[n * K + k], bn1_shift[k], acc);
+        b2s[n] = acc * wscale;
+        return;
+    }
+    const int o = blockIdx.x - 1;
+    const float w = W3[o * N + n];
+    w3s[o * N + n] = w * (s2 ? s2[n] : 1.f) / wscale;
+    red[n] = (h2 ? h2[n] : 0.f) * w;
+    __syncthreads();
+    for (int s = N / 2; s > 0; s >>= 1) {
+        if (n < s) red[n] += red[n + s];
+        __syncthreads();
+    }
+    if (n == 0) {
+        tail[o * 4 + 0] = red[0] + (b3 ? b3[o] : 0.f);
+        tail[o * 4 + 1] = s3 ? s3[o] : 1.f;
+        tail[o * 4 + 2] = h3 ? h3[o] : 0.f;
+        tail[o * 4 + 3] = 0.f;
+    }
+}
+
+template <int COUT>
+static int32_t launch(const Params& p, cudaStream_t st) {
+    const int smem = Smem::total + 1024;
+    GNB_CUDA(cudaFuncSetAttribute(decode_lattice_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int grid = sm_count();
+    if ((int64_t)grid > p.num_pairs) grid = (int)p.num_pairs;
+    decode_lattice_kernel<COUT><<<grid, THREADS, smem, st>>>(p);
+    return check_launch("gnb_decode_lattice");
+}
+
+}  // namespace dl2
+}  // namespace gnb
+
+using namespace gnb;
+
+extern "C" {
+
+int32_t gnb_decode_lattice(const float* U, int32_t B, int32_t G, int32_t Q, const float* W2, const void* w2f_packed,
+                           int32_t w2f_scale_log2, const float* b2, const float* bn1_shift, const float* bn2_scale,
+                           const float* bn2_shift, const float* W3, const float* b3, const float* bn3_scale,
+                           const float* bn3_shift, int32_t Cout, float* scratch, float* out, void* stream) {
+    GNB_REQUIRE(U && W2 && w2f_packed && b2 && bn1_shift && W3 && scratch && out, "gnb_decode_lattice: null pointer");
+    GNB_REQUIRE(Cout >= 1 && Cout <= 3, "gnb_decode_lattice: Cout must be 1..3 (got %d)", Cout);
+    GNB_REQUIRE(Q == dl2::M, "gnb_decode_lattice: volume_size must be 128 (one lattice line per 128-row tile)");
+    GNB_REQUIRE(B > 0 && G >= 2 && G <= dl2::MAX_G, "gnb_decode_lattice: need B > 0 and a feature grid 2 <= G <= 32");
+    GNB_REQUIRE((reinterpret_cast<uintptr_t>(U) & 15) == 0, "gnb_decode_lattice: U must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    float* b2s = scratch;                 // [256]
+    float* w3s = scratch + dl2::N;        // [3][256]
+    float* tail = scratch + 4 * dl2::N;   // [3][4]
+    dl2::lattice_prep_kernel<<<1 + Cout, dl2::N, 0, st>>>(W2, b2, bn1_shift, W3, b3, bn2_scale, bn2_shift, bn3_scale, bn3_shift,
+                                                         Cout, ldexpf(1.0f, w2f_scale_log2), b2s, w3s, tail);
+    dl2::Params p;
+    p.U = U; p.B = B; p.G = G; p.Q = Q;
+    p.w2_packed = reinterpret_cast<const uint8_t*>(w2f_packed);
+    p.b2s = b2s; p.w3s = w3s; p.tail = tail; p.out = out;
+    p.num_pairs = (int64_t)B * Q * (Q / 2);
+    { const char* e = getenv("GNB_DL2_DBG"); p.dbg = e ? atoi(e) : 0; }
+    if (Cout == 1) return dl2::launch<1>(p, st);
+    if (Cout == 2) return dl2::launch<2>(p, st);
+    return dl2::launch<3>(p, st);
+}
+
+}  // extern "C"

@@ -394,6 +394,25 @@ def decode_tc(w2_packed, b2, bn2, W3, b3, bn3, *, U=None, Q=0, bn1=None, X=None,
     return out
 
 
+def decode_lattice(W2, w2f_packed, b2, bn1_shift, bn2, W3, b3, bn3, *, U, Q, out=None) -> torch.Tensor:
+    """Pair-tile lattice kernel (``gnb_decode_lattice``): ``U`` [B,G,G,G,256] hoisted grid, ``w2f_packed`` =
+    ``pack_f16_split(W2 * bn1_scale[None, :])`` -> [B, Q^3, Cout]."""
+    w2f, w2f_s = w2f_packed
+    Cout = W3.shape[0]
+    dev = W3.device
+    B, G = U.shape[0], U.shape[1]
+    assert U.is_contiguous() and U.shape[-1] == 256
+    if out is None:
+        out = torch.empty((B, Q ** 3, Cout), dtype=torch.float32, device=dev)
+    s2, h2 = bn2 if bn2 is not None else (None, None)
+    s3, h3 = bn3 if bn3 is not None else (None, None)
+    scratch = torch.empty(2048, dtype=torch.float32, device=dev)
+    _lib.call("gnb_decode_lattice", U.data_ptr(), B, G, int(Q), W2.data_ptr(), w2f.data_ptr(), w2f_s, b2.data_ptr(),
+              bn1_shift.data_ptr(), _ptr(s2), _ptr(h2), W3.data_ptr(), _ptr(b3), _ptr(s3), _ptr(h3), Cout,
+              scratch.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
 def decode_tc_query(w2_packed, b2, bn2, W3, b3, bn3, *, U, q, qptr, bn1, out=None) -> torch.Tensor:
     """Query mode of the tensor-core decoder (``gnb_decode_tc_query``): ``U`` [B,G,G,G,256] hoisted grids, ``q`` [R,3]
     query points of all samples back to back, ``qptr`` device i64[B+1] row offsets -> [R, Cout]."""

@@ -226,6 +226,23 @@ class ImplicitWNFDecoder(nn.Module):
             self._gnb_w2_packed = cached
         return (cached[1], l2.bias, self.mlp[1][2].folded_affine(), l3.weight, l3.bias, self.mlp[2][2].folded_affine())
 
+    def _lattice_args(self):
+        """Arguments of the pair-tile lattice kernel: BN1 (it follows the ReLU, so it is a linear map in front of
+        Linear2) folded into W2's columns, packed as fp16 hi/lo; cached per weight version."""
+        l2, l3 = self.mlp[1][0], self.mlp[2][0]
+        bn1 = self.mlp[0][2]
+        key = (l2.weight._version, l2.weight.data_ptr(), bn1.weight._version, bn1.bias._version,
+               bn1.running_mean._version, bn1.running_var._version)
+        cached = getattr(self, "_gnb_w2f_packed", None)
+        if cached is None or cached[0] != key:
+            sc, sh = bn1.folded_affine()
+            cached = (key, ops.pack_f16_split((l2.weight * sc[None, :]).contiguous()), sh.contiguous())
+            self._gnb_w2f_packed = cached
+        return (l2.weight, cached[1], l2.bias, cached[2], self.mlp[1][2].folded_affine(), l3.weight, l3.bias,
+                self.mlp[2][2].folded_affine())
+
+    use_pair_lattice = True   # False: first-generation lattice kernel (decode_tc_kernel<COUT, 1>)
+
     def _tail(self, h: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self._tc_ready():
             with profiling.tag(f"{self.profile_tag}_tc"):
@@ -366,7 +383,10 @@ class ConvImplicitWNFPipeline(nn.Module):
         if Q == 128 and dec._tc_ready() and dec.mlp[2][0].out_features == 1:
             # fused lattice kernel: interpolation + BN1 + Linear2/BN2 + Linear3/BN3 in one launch for the whole batch
             with profiling.tag("decode_tc"):
-                out = ops.decode_tc(*dec._tc_args(), U=u, Q=Q, bn1=dec.mlp[0][2].folded_affine())
+                if dec.use_pair_lattice and u.shape[1] <= 32:
+                    out = ops.decode_lattice(*dec._lattice_args(), U=u, Q=Q)
+                else:
+                    out = ops.decode_tc(*dec._tc_args(), U=u, Q=Q, bn1=dec.mlp[0][2].folded_affine())
             return out.view(B, Q, Q, Q)
         out = torch.empty((B, total), dtype=torch.float32, device=u.device)
         for b in range(B):

@@ -211,6 +211,16 @@ int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t
                       const float* bn2_scale, const float* bn2_shift, const float* W3, const float* b3,
                       const float* bn3_scale, const float* bn3_shift, int32_t Cout, float* scratch, float* out,
                       void* stream);
+/* Second-generation lattice kernel (same math as gnb_decode_tc with Q == 128, restructured for L2 traffic): a work item
+ * is a PAIR of adjacent lattice lines (two TMEM accumulators), the pipeline is K-chunk major with a two-slot A ring, the
+ * producers gather 16 bytes per lane and share the corner columns of the two lines, and BN1 is folded into W2:
+ *   w2f_packed = gnb_pack_f16_split(W2 * diag(bn1_scale)) with its power-of-two scale w2f_scale_log2;
+ *   W2 (unfolded, f32[256,256]) and bn1_shift are used once per call to form b2 + W2 bn1_shift.
+ * U f32[B,G,G,G,256] (16-byte aligned), 2 <= G <= 64, Q == 128; scratch f32[2048]; out f32[B, Q^3, Cout]. */
+int32_t gnb_decode_lattice(const float* U, int32_t B, int32_t G, int32_t Q, const float* W2, const void* w2f_packed,
+                           int32_t w2f_scale_log2, const float* b2, const float* bn1_shift, const float* bn2_scale,
+                           const float* bn2_shift, const float* W3, const float* b3, const float* bn3_scale,
+                           const float* bn3_shift, int32_t Cout, float* scratch, float* out, void* stream);
 /* Query mode of the same kernel (the surface / warp-field decoder, ref predict.py:184-187 and
  * networks/conv_implicit_wnf.py:263-269): H1 = BN1(ReLU(trilinear(U[b], q_r))) for explicit query points q f32[R,3] in
  * [0,1]^3 (coordinate 0 -> W axis: the reference does not flip xyz, :135-142).  Rows are ragged per sample: rows

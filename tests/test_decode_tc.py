@@ -64,8 +64,10 @@ def test_tail_dispatch_equals_fp32_path(dev):
 
 
 @pytest.mark.gpu
-def test_lattice_mode_full_size_vs_oracle(dev):
-    """128^3 lattice (BASELINE size), one volume: fused tcgen05 kernel vs the oracle's chunked grid_sample + MLP."""
+@pytest.mark.parametrize("pair_kernel", [True, False])
+def test_lattice_mode_full_size_vs_oracle(dev, pair_kernel):
+    """128^3 lattice (BASELINE size), one volume: fused tcgen05 kernels (pair-tile generation and the first one) vs the
+    oracle's chunked grid_sample + MLP."""
     from garmentnets_b200 import ops
     from garmentnets_b200.pipeline import ConvImplicitWNFPipeline
     torch.manual_seed(1)
@@ -73,6 +75,7 @@ def test_lattice_mode_full_size_vs_oracle(dev):
     g = torch.Generator().manual_seed(3)
     fvol = (torch.randn(2, 128, 32, 32, 32, generator=g) * 0.7).to(dev)
     model.volume_decoder.use_tensor_cores = True
+    model.volume_decoder.use_pair_lattice = pair_kernel
     wnf_tc = model.dense_decode(fvol, 128)
     model.volume_decoder.use_tensor_cores = False
     wnf_32 = model.dense_decode(fvol[1:2], 128)
@@ -112,3 +115,21 @@ def test_query_mode_matches_oracle_and_row_mode(dev, counts, cout):
         assert (got[sl] - ref).abs().max().item() < TOL
         rows = dec.forward_hoisted(u[b:b + 1], qs[b].view(1, -1, 3).to(dev)).view(n, cout).cpu()
         assert (got[sl] - rows).abs().max().item() < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("G,B", [(32, 3), (8, 1), (16, 2), (5, 2), (31, 1)])
+def test_pair_lattice_equals_first_generation(dev, G, B):
+    """Pair-tile lattice kernel vs decode_tc lattice mode on other grid sizes (G < 32: idle producer groups; G > 32:
+    two D-cells per group; odd G) and an odd batch (odd number of work items per CTA)."""
+    from garmentnets_b200 import ops
+    dec = _decoder(dev, 1, 31)
+    g = torch.Generator().manual_seed(G * 7 + B)
+    u = (torch.randn(B, G, G, G, 256, generator=g) * 0.9).to(dev)
+    if G % 2 == 0:
+        ref = ops.decode_tc(*dec._tc_args(), U=u, Q=128, bn1=dec.mlp[0][2].folded_affine())
+    else:  # the first-generation kernel needs an even G: reference = explicit sampling + row mode
+        ref = torch.stack([dec.forward_lattice(u, b, 128, 0, 128 ** 3) for b in range(B)])
+    got = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
+    assert got.shape == (B, 128 ** 3, 1)
+    assert (got - ref.view_as(got)).abs().max().item() < 2e-5

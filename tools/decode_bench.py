@@ -1,0 +1,42 @@
+"""Device time of the dense lattice decode kernels at the benchmark size (B x 128^3 queries), CUDA events, best of 5.
+    python tools/decode_bench.py [B]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from garmentnets_b200 import ops, synthetic
+from garmentnets_b200.pipeline import ImplicitWNFDecoder
+
+dev = torch.device("cuda:0")
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+torch.manual_seed(0)
+dec = synthetic.randomize_(ImplicitWNFDecoder(nn_channels=(128, 256, 256, 1)), 1).eval().requires_grad_(False).to(dev)
+u = torch.randn(B, 32, 32, 32, 256, device=dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(name, fn, n=5):
+    fn()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(n):
+        flush.fill_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        best = min(best, s.elapsed_time(e))
+    flop = B * 128 ** 3 * (2 * 256 * 256 + 512)
+    print(f"{name:44s} {best:8.3f} ms   {flop / best / 1e9:7.1f} TFLOP/s algorithmic  ({3 * flop / best / 1e9:7.1f} executed)")
+    return best
+
+
+out1 = ops.decode_tc(*dec._tc_args(), U=u, Q=128, bn1=dec.mlp[0][2].folded_affine())
+out2 = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
+print("max |pair - gen1| =", (out1 - out2).abs().max().item())
+timeit("decode_tc lattice (gen 1)", lambda: ops.decode_tc(*dec._tc_args(), U=u, Q=128, bn1=dec.mlp[0][2].folded_affine()))
+timeit("decode_lattice (pair tiles)", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128))
