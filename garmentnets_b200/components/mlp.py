@@ -61,11 +61,14 @@ class _Block(nn.Sequential):
         if _Block.calibrating and len(self) > 2:
             y = self._calibrate(flat, out, rows_dev)
             return y if x.dim() == 2 else y.view(*lead, y.shape[-1])
-        scale = shift = None
-        if len(self) > 2:
-            scale, shift = self[2].folded_affine()
-        y = ops.linear(flat, lin.weight, lin.bias, True, scale, shift, out=out, rows_dev=rows_dev)
-        return y if x.dim() == 2 else y.view(*lead, y.shape[-1])
+        bn = self[2] if len(self) > 2 else None
+        if ops.USE_LINEAR_TC and flat.shape[0] >= ops.LINEAR_TC_MIN_ROWS:
+            w = ops.packed_linear_for(self, "block", lin.weight, lin.bias, bn)
+            y = ops.linear_tc(flat, w, True, out=out, rows_dev=rows_dev)
+        else:
+            scale, shift = bn.folded_affine() if bn is not None else (None, None)
+            y = ops.linear(flat, lin.weight, lin.bias, True, scale, shift, out=out, rows_dev=rows_dev)
+        return y if x.dim() == 2 else y.reshape(*lead, y.shape[-1])
 
     # Synthetic-weight support (garmentnets_b200.synthetic.calibrate_bn_): set this block's BatchNorm running
     # statistics to the statistics of the activations it actually sees, the way training would have.  Not a compute

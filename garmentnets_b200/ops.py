@@ -170,6 +170,78 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out
 
 
+class PackedLinear:
+    """Weight of one Linear(+bias, +folded BatchNorm affine) packed for ``gnb_linear_tc`` (fp16 hi/lo shared-memory
+    images + padded per-column epilogue parameters)."""
+    __slots__ = ("packed", "cparams", "scale_log2", "N", "K")
+
+    def __init__(self, packed, cparams, scale_log2, N, K):
+        self.packed, self.cparams, self.scale_log2, self.N, self.K = packed, cparams, scale_log2, N, K
+
+
+def pack_linear_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn_scale: Optional[torch.Tensor] = None,
+                   bn_shift: Optional[torch.Tensor] = None) -> PackedLinear:
+    weight = _req(weight, torch.float32, "weight")
+    N, K = weight.shape
+    lib = _lib.load()
+    s = _pow2_scale(weight)
+    packed = torch.empty(int(lib.gnb_linear_tc_packed_bytes(N, K)), dtype=torch.uint8, device=weight.device)
+    cparams = torch.empty(3 * int(lib.gnb_linear_tc_padded_cols(N, K)), dtype=torch.float32, device=weight.device)
+    _lib.call("gnb_linear_tc_pack", weight.data_ptr(), N, K, _ptr(bias), _ptr(bn_scale), _ptr(bn_shift), s,
+              packed.data_ptr(), cparams.data_ptr(), _stream())
+    return PackedLinear(packed, cparams, s, N, K)
+
+
+def _version_key(*tensors):
+    return tuple(None if t is None else (t.data_ptr(), t._version) for t in tensors)
+
+
+def packed_linear_for(owner, slot: str, weight, bias=None, bn=None) -> PackedLinear:
+    """``pack_linear_tc`` cached on ``owner`` (any object) under ``slot`` until a parameter / running statistic of the
+    Linear or of its BatchNorm (an object with ``folded_affine()``) changes."""
+    bn_t = () if bn is None else (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = _version_key(weight, bias, *bn_t)
+    cache = owner.__dict__.setdefault("_gnb_packed_linear", {})
+    hit = cache.get(slot)
+    if hit is None or hit[0] != key:
+        sc, sh = bn.folded_affine() if bn is not None else (None, None)
+        hit = (key, pack_linear_tc(weight, bias, sc, sh))
+        cache[slot] = hit
+    return hit[1]
+
+
+USE_LINEAR_TC = True       # False: every Linear block runs on the fp32 FFMA kernel (gnb_linear)
+LINEAR_TC_MIN_ROWS = 1024   # below this the fp32 kernel is used (a 128-row tensor-core tile per SM would idle most SMs)
+
+
+def padded_rows(R: int, N: int, device) -> torch.Tensor:
+    """[R, N] fp32 view whose row stride is a multiple of 4 floats (16-byte aligned rows for vector stores)."""
+    ld = (N + 3) // 4 * 4
+    buf = torch.empty((R, ld), dtype=torch.float32, device=device)
+    return buf if ld == N else buf[:, :N]
+
+
+def linear_tc(x: torch.Tensor, w: PackedLinear, relu: bool = False, out: Optional[torch.Tensor] = None,
+              rows_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Tensor-core Linear block (``gnb_linear_tc``): x [R,K] (any row stride) -> [R,N]."""
+    x, ldx = _rows(x, "x")
+    R, K = x.shape
+    assert K == w.K, f"packed weight K={w.K} vs input K={K}"
+    if out is None:
+        out = padded_rows(R, w.N, x.device)
+    assert out.stride(1) == 1 or w.N == 1
+    _lib.call("gnb_linear_tc", x.data_ptr(), R, K, ldx, w.packed.data_ptr(), w.cparams.data_ptr(), w.scale_log2, w.N,
+              int(relu), out.data_ptr(), out.stride(0), _ptr(rows_dev), _stream())
+    return out
+
+
+def linear_module(owner, slot: str, x: torch.Tensor, weight, bias=None, relu: bool = False) -> torch.Tensor:
+    """A plain ``nn.Linear`` (optionally + ReLU) applied to rows: tensor cores for large row counts, fp32 kernel below."""
+    if USE_LINEAR_TC and x.shape[0] >= LINEAR_TC_MIN_ROWS:
+        return linear_tc(x, packed_linear_for(owner, slot, weight, bias), relu)
+    return linear(x, weight, bias, relu)
+
+
 def nocs_head(logits: torch.Tensor, bins: int):
     logits = _req(logits, torch.float32, "logits")
     R = logits.shape[0]
@@ -490,7 +562,8 @@ def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0,
     launch over the compacted active cells write every mesh into shared [sum V] / [sum F] buffers.
     Returns a list of (verts, faces, normals, values, ggm_at) views or the exception skimage would raise for that volume
     (ValueError: level outside the data range, RuntimeError: no surface).  ``return_packed`` adds the shared buffers:
-    ``{"verts": f32[sum V,3], "vptr": host i64[N+1] row offsets}`` (volumes without a mesh own zero rows)."""
+    ``{"verts": f32[sum V,3], "vptr": host i64[N+1] row offsets, "faces": i32[sum F,3], "fptr", "normals", "values",
+    "ggm_at"}`` (volumes without a mesh own zero rows)."""
     import ctypes
     import numpy as np
     volumes = _req(volumes, torch.float32, "volumes")
@@ -533,5 +606,8 @@ def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0,
     if return_packed:
         vptr = np.zeros(N + 1, np.int64)
         np.cumsum(totals[:, 0], out=vptr[1:])
-        return out, {"verts": verts, "vptr": vptr}
+        fptr = np.zeros(N + 1, np.int64)
+        np.cumsum(totals[:, 1], out=fptr[1:])
+        return out, {"verts": verts, "vptr": vptr, "faces": faces, "fptr": fptr, "normals": normals, "values": values,
+                     "ggm_at": ggm_at}
     return out

@@ -110,6 +110,22 @@ int32_t gnb_linear(const float* X, int64_t R, int32_t K, int64_t ldx, const floa
                    int32_t N, int32_t relu, const float* bn_scale, const float* bn_shift,
                    float* Y, int64_t ldy, const int64_t* rows_dev, void* stream);
 
+/* ---- N10 on the tensor cores: the same Linear -> ReLU -> BatchNorm block through tcgen05 ----------
+ * ref: components/mlp.py:9-20.  Same contract as gnb_linear; the weight is pre-packed once per parameter version:
+ * gnb_linear_tc_pack writes fp16 hi/lo shared-memory images of W (scaled by 2^scale_log2) into `packed`
+ * (gnb_linear_tc_packed_bytes(N,K) bytes) and bias | bn_scale | bn_shift (NULL = 0 | 1 | 0) into
+ * `cparams` f32[3 * gnb_linear_tc_padded_cols(N,K)].  Products are formed as hi*hi + lo*hi + hi*lo with fp32
+ * accumulation (fp32-level accuracy).  No alignment requirement on X / ldx; Y rows are written with 16-byte
+ * stores when Y and ldy allow it. */
+int64_t gnb_linear_tc_packed_bytes(int32_t N, int32_t K);
+int64_t gnb_linear_tc_padded_cols(int32_t N, int32_t K);
+int32_t gnb_linear_tc_pack(const float* W, int32_t N, int32_t K, const float* bias, const float* bn_scale,
+                           const float* bn_shift, int32_t scale_log2, void* packed, float* cparams,
+                           void* stream);
+int32_t gnb_linear_tc(const float* X, int64_t R, int32_t K, int64_t ldx, const void* packed,
+                      const float* cparams, int32_t scale_log2, int32_t N, int32_t relu,
+                      float* Y, int64_t ldy, const int64_t* rows_dev, void* stream);
+
 /* ---- N11: NOCS bin head ----------------------------------------------------------------
  * ref: networks/conv_implicit_wnf.py:222-231.  logits f32[R, bins*3] viewed [R,bins,3]:
  * bin i64[R,3] = argmax over bins (first max), conf f32[R,3] = softmax at the argmax,

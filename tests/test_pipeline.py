@@ -151,14 +151,34 @@ def test_predict_end_to_end(setup):
     fv = torch.from_numpy(ref["stage2"]["out_feature_volume"]).to(dev)
     warp = s["model"].surface_decoder(fv, verts.view(1, -1, 3)).view(-1, 3)
     assert np.abs(warp.cpu().numpy() - mesh["warp_field"]).max() < TOL
-    # (2) full CUDA predict for the single sample
+    # (2) full CUDA predict for the single sample.  A NOCS argmax whose two best logits tie within rounding may land on
+    # the other bin; that point then feeds another voxel and, through GroupNorm, perturbs the whole volume.  So: (a) every
+    # flipped bin must be such a near-tie in the ORACLE's logits, and (b) the oracle continues from the CUDA stage-1
+    # outputs (identical voxel assignment by construction) and must reproduce the CUDA volume.
     one = Batch(x=s["data"].x[:n], pos=s["data"].pos[:n], batch=s["data"].batch[:n])
     starts = tuple(torch.from_numpy(a[:1].astype(np.int64)).to(dev) for a in s["starts"])
-    out = s["model"].predict(one, volume_size=32, index=CloudIndex.uniform(1, n, dev), fps_starts=starts, keep_volume=True)[0]
-    diff = np.abs(out["wnf_volume"].cpu().numpy() - ref["wnf_volume"])
-    # a point whose NOCS argmax flips moves to another voxel: allow a small fraction of outliers, none if no flip
-    assert np.median(diff) < 1e-5 and (diff > TOL).mean() < 0.02
-    assert abs(len(out["verts"]) - len(mesh["verts"])) <= 0.05 * len(mesh["verts"]) + 8
+    index1 = CloudIndex.uniform(1, n, dev)
+    out = s["model"].predict(one, volume_size=32, index=index1, fps_starts=starts, keep_volume=True)[0]
+    p1 = s["model"].pointnet2_forward(one, index=index1, fps_starts=starts)
+    nocs_gpu = p1["nocs_data"].pos.cpu().numpy()
+    s1_ref = ref["stage1"]
+    logits_ref = s1_ref["per_point_logits"].reshape(n, 64, 3)
+    bins_gpu = np.rint(nocs_gpu * 63).astype(np.int64)
+    flipped = np.argwhere(bins_gpu != s1_ref["nocs_bin"])
+    assert len(flipped) <= 0.01 * n
+    scale = max(1.0, float(np.abs(logits_ref).max()))
+    for pt, ax in flipped:
+        gap = logits_ref[pt, :, ax].max() - logits_ref[pt, bins_gpu[pt, ax], ax]
+        assert gap < TOL * scale, (pt, ax, gap)
+    s1_gpu = {"per_point_features": p1["per_point_features"].cpu().numpy(), "pred_nocs": nocs_gpu,
+              "pred_confidence": p1["nocs_data"].pred_confidence.cpu().numpy()}
+    batch0 = np.zeros(n, np.int64)
+    s2_cont = OP.stage2(s["sd"], hp, s1_gpu, d["pos"][:n], batch0, 1)
+    wnf_cont = ON.dense_decode(s["sd"], "volume_decoder.", s2_cont["out_feature_volume"], 32, 16).numpy()
+    diff = np.abs(out["wnf_volume"].cpu().numpy() - wnf_cont)
+    assert np.median(diff) < 1e-5 and (diff > TOL).mean() < 0.02 and diff.max() < 1e-3, (np.median(diff), (diff > TOL).mean(), diff.max())
+    if len(flipped) == 0:
+        assert abs(len(out["verts"]) - len(mesh["verts"])) <= 0.05 * len(mesh["verts"]) + 8
     assert out["faces"].dtype == torch.int32 and out["warp_field"].shape == (len(out["verts"]), 3)
 
 
@@ -178,3 +198,25 @@ def test_folded_final_conv_equals_two_step(setup):
         two_step = dec.hoisted(full)
         folded = dec.hoisted_folded(x_last, unet.final_conv)
         assert close(folded.cpu().numpy(), two_step.cpu().numpy(), 2e-5)
+
+
+@pytest.mark.gpu
+def test_host_predictor_matches_device_predict(setup):
+    """The host-buffer API (pinned staging, copy stream, double buffering) returns exactly what predict() leaves on the
+    device, for every sample and for consecutive overlapping submissions."""
+    from garmentnets_b200.pipeline import HostPredictor
+    model, d, index = setup["model"], setup["d"], setup["index"]
+    ref = model.predict(setup["data"], volume_size=32, index=index)   # synthetic.build_pipeline fixes the FPS starts
+    ref = [{k: v.cpu().numpy() for k, v in r.items()} for r in ref]
+    nocs_ref = model._last_point_outputs["pred_nocs"].cpu().numpy()
+    hp = HostPredictor(model, depth=2, volume_size=32)
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in d.items()}
+    tickets = [hp.submit(host["x"], host["pos"], host["batch"], index=index) for _ in range(2)]
+    for t in tickets:
+        res = hp.result(t)
+        assert len(res) == len(ref)
+        for got, want in zip(res, ref):
+            for k in ("verts", "faces", "normals", "volume_value", "volume_gradient_magnitude", "warp_field"):
+                assert got[k].dtype == want[k].dtype and np.array_equal(got[k], want[k]), k
+        assert np.array_equal(hp.point_outputs(t)["pred_nocs"], nocs_ref)
+        assert t["d2h_bytes"] == sum(v.nbytes for r in ref for v in r.values()) + 2 * nocs_ref.nbytes
