@@ -50,6 +50,7 @@ struct TcSmem {
     static constexpr int qptr = ztab;                                 // QUERY: [TC_MAX_B + 1] i64 sample row offsets (aliases ztab/kstart)
     static constexpr int total = kstart + (TC_MAX_G + 2) * 4;
     static_assert((TC_MAX_B + 1) * 8 <= total - ztab, "qptr table must fit in the lattice tables it aliases");
+    static constexpr int xs = b_ring + 2 * B_PIECE_BYTES;             // FUSED: [128][32] fp32 interpolated inputs (the B ring has 2 slots)
 };
 static_assert(TcSmem::total + 1024 <= 227 * 1024, "shared memory budget");
 
@@ -69,14 +70,20 @@ struct TcParams {
     int64_t num_tiles;
     const float* q;         // QUERY: [R,3] query points in [0,1]^3 (coordinate 0 -> W axis, un-flipped grid_sample)
     const int64_t* qptr;    // QUERY: [B+1] first row of every sample (rows of sample b sample U[b])
+    const float* w1;        // FUSED: [256][32] first Linear (final_conv folded in), applied per query in the producers
+    const float* b1;        // FUSED: [256]
 };
 
-// MODE 0: rows of a given H1 matrix; 1: implicit 128^3 lattice; 2: explicit query points (ragged per sample)
+// MODE 0: rows of a given H1 matrix; 1: implicit 128^3 lattice; 2: explicit query points (ragged per sample) on the hoisted
+// 256-channel grid; 3 (FUSED): explicit query points on the 32-channel grid -- the producers interpolate 32 channels
+// (128-byte coalesced corner loads instead of 8 x 1 KB per query) and apply Linear1 themselves with packed FFMA2.
 template <int COUT, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 decode_tc_kernel(const TcParams p) {
     constexpr bool LATTICE = MODE == 1;
-    constexpr bool QUERY = MODE == 2;
+    constexpr bool FUSED = MODE == 3;
+    constexpr bool QUERY = MODE == 2 || FUSED;
+    constexpr int NBS = FUSED ? 2 : B_SLOTS;   // B ring slots (FUSED gives the third slot to the interpolated inputs)
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms need a 1024-byte aligned base
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -143,9 +150,105 @@ decode_tc_kernel(const TcParams p) {
         if (LATTICE || QUERY) { sc0 = p.bn1_scale[c0]; sc1 = p.bn1_scale[c0 + 1]; sh0 = p.bn1_shift[c0]; sh1 = p.bn1_shift[c0 + 1]; }
         const int* zt = reinterpret_cast<const int*>(smem + TcSmem::ztab);
         int it = 0;
+        // FUSED: this thread's two rows of W1 (output channels c0, c0+1) stay in registers for the whole kernel
+        float2 w1r[FUSED ? 32 : 1];
+        float2 b1r = make_float2(0.f, 0.f);
+        if (FUSED) {
+#pragma unroll
+            for (int k = 0; k < (FUSED ? 32 : 1); ++k) w1r[k] = make_float2(__ldg(p.w1 + c0 * 32 + k), __ldg(p.w1 + (c0 + 1) * 32 + k));
+            b1r = make_float2(__ldg(p.b1 + c0), __ldg(p.b1 + c0 + 1));
+        }
         for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            mbar_wait(a_empty(chunk), (it & 1) ^ 1);
-            if (LATTICE) {
+            if (!FUSED) mbar_wait(a_empty(chunk), (it & 1) ^ 1);
+            if (FUSED) {
+                // ---- phase 0: xs[row][0..31] = trilinear(X32) for the tile's 128 rows.  Warp w owns rows 16w..16w+15: lane l
+                // sets up row 16w + (l & 15); the gather runs with 8 lanes per row (one float4 = 4 channels each), so one
+                // warp-wide LDG.128 fetches one corner of FOUR rows (4 x 128 contiguous bytes) and all 8 corners of those
+                // rows are in flight together.
+                const uint32_t xs_addr = sbase + TcSmem::xs;
+                const int G = p.G;
+                const int64_t* qp = reinterpret_cast<const int64_t*>(smem + TcSmem::qptr);
+                int off[8];
+                float wgt[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { off[k] = 0; wgt[k] = 0.f; }
+                {
+                    const int64_t r = tile * TC_M + warp * 16 + (lane & 15);
+                    if (r < p.R) {
+                        int lo_b = 0, hi_b = p.B;  // largest b with qptr[b] <= r
+                        while (hi_b - lo_b > 1) { const int mid = (lo_b + hi_b) >> 1; if (qp[mid] <= r) lo_b = mid; else hi_b = mid; }
+                        const float g0 = __fsub_rn(__fmul_rn(2.0f, __ldg(p.q + r * 3)), 1.0f);
+                        const float g1 = __fsub_rn(__fmul_rn(2.0f, __ldg(p.q + r * 3 + 1)), 1.0f);
+                        const float g2 = __fsub_rn(__fmul_rn(2.0f, __ldg(p.q + r * 3 + 2)), 1.0f);
+                        TriW t;
+                        trilinear_setup(g0, g1, g2, G, G, G, 32, t);
+                        const int sb = lo_b * G * G * G * 32;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { off[k] = sb + (int)t.off[k]; wgt[k] = t.w[k]; }
+                    }
+                }
+                const float* xbase = p.U + 4 * (lane & 7);
+#pragma unroll 1
+                for (int grp = 0; grp < 4; ++grp) {
+                    const int src = grp * 4 + (lane >> 3);      // row (within the warp's 16) this lane gathers for
+                    float4 v[8];
+                    float w[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int o = __shfl_sync(0xffffffffu, off[k], src);
+                        w[k] = __shfl_sync(0xffffffffu, wgt[k], src);
+                        v[k] = __ldg(reinterpret_cast<const float4*>(xbase + o));
+                    }
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        a.x = fmaf(v[k].x, w[k], a.x); a.y = fmaf(v[k].y, w[k], a.y);
+                        a.z = fmaf(v[k].z, w[k], a.z); a.w = fmaf(v[k].w, w[k], a.w);
+                    }
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(xs_addr + (uint32_t)(((warp * 16 + src) * 32 + 4 * (lane & 7)) * 4)),
+                                 "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // all 128 interpolated rows are in shared memory
+                mbar_wait(a_empty(chunk), (it & 1) ^ 1);
+                // ---- phase 1: H1 = BN1(ReLU(xs * W1^T + b1)) for this warp's 64 rows x this thread's 2 channels
+#pragma unroll 1
+                for (int rr = 0; rr < TC_M / 2; rr += 4) {
+                    const int k0 = half * (TC_M / 2) + rr;
+                    unsigned long long acc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) asm("mov.b64 %0, {%1, %2};" : "=l"(acc[u]) : "f"(b1r.x), "f"(b1r.y));
+#pragma unroll
+                    for (int k4 = 0; k4 < 32; k4 += 4) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float4 xv;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xv.x), "=f"(xv.y), "=f"(xv.z), "=f"(xv.w)
+                                         : "r"(xs_addr + (uint32_t)(((k0 + u) * 32 + k4) * 4)));
+                            const float xk[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                unsigned long long ww, xx;
+                                asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w1r[k4 + j].x), "f"(w1r[k4 + j].y));
+                                asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(xk[j]));
+                                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[u]) : "l"(ww), "l"(xx));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float h0, h1;
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(acc[u]));
+                        h0 = fmaxf(h0, 0.f) * sc0 + sh0;
+                        h1 = fmaxf(h1, 0.f) * sc1 + sh1;
+                        uint32_t hi, lo;
+                        split_f16x2(h0, h1, hi, lo);
+                        const uint32_t o2 = sw128_offset(k0 + u, 2 * lane);
+                        *reinterpret_cast<uint32_t*>(a_hi + o2) = hi;
+                        *reinterpret_cast<uint32_t*>(a_lo + o2) = lo;
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // xs may be overwritten by the next tile's phase 0
+            } else if (LATTICE) {
                 const int G = p.G, Q = p.Q;
                 const int j = (int)(tile % Q), i = (int)((tile / Q) % Q), b = (int)(tile / ((int64_t)Q * Q));
                 const float s = __fdiv_rn(1.0f, (float)(Q - 1));
@@ -360,8 +463,8 @@ decode_tc_kernel(const TcParams p) {
                     const uint32_t alo = sbase + TcSmem::a_lo + c * A_CHUNK_BYTES;
                     // piece 0: W2_hi chunk c -> A_hi*B_hi and A_lo*B_hi
                     {
-                        const int slot = piece % B_SLOTS;
-                        mbar_wait(b_full(slot), (piece / B_SLOTS) & 1);
+                        const int slot = piece % NBS;
+                        mbar_wait(b_full(slot), (piece / NBS) & 1);
                         tc_fence_after();
                         const uint32_t bs = sbase + TcSmem::b_ring + slot * B_PIECE_BYTES;
 #pragma unroll
@@ -375,8 +478,8 @@ decode_tc_kernel(const TcParams p) {
                     }
                     // piece 1: W2_lo chunk c -> A_hi*B_lo
                     {
-                        const int slot = piece % B_SLOTS;
-                        mbar_wait(b_full(slot), (piece / B_SLOTS) & 1);
+                        const int slot = piece % NBS;
+                        mbar_wait(b_full(slot), (piece / NBS) & 1);
                         tc_fence_after();
                         const uint32_t bs = sbase + TcSmem::b_ring + slot * B_PIECE_BYTES;
 #pragma unroll
@@ -396,8 +499,8 @@ decode_tc_kernel(const TcParams p) {
             uint32_t piece = 0;
             for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 for (int pc = 0; pc < 2 * TC_NCHUNK; ++pc, ++piece) {
-                    const int slot = piece % B_SLOTS;
-                    mbar_wait(b_empty(slot), ((piece / B_SLOTS) & 1) ^ 1);
+                    const int slot = piece % NBS;
+                    mbar_wait(b_empty(slot), ((piece / NBS) & 1) ^ 1);
                     mbar_expect_tx(b_full(slot), B_PIECE_BYTES);
                     bulk_g2s(sbase + TcSmem::b_ring + slot * B_PIECE_BYTES, p.w2_packed + (size_t)pc * B_PIECE_BYTES,
                              B_PIECE_BYTES, b_full(slot));
@@ -501,7 +604,7 @@ int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t
     p.b2 = b2; p.w3s = w3s; p.tail = tail; p.out = out;
     p.acc_scale = ldexpf(1.0f, -w2_scale_log2);
     p.num_tiles = lattice ? (int64_t)B * Q * Q : ceil_div<int64_t>(R, TC_M);
-    p.q = nullptr; p.qptr = nullptr;
+    p.q = nullptr; p.qptr = nullptr; p.w1 = nullptr; p.b1 = nullptr;
     if (lattice) {
         if (Cout == 1) return launch_decode_tc<1, 1>(p, st);
         if (Cout == 2) return launch_decode_tc<2, 1>(p, st);
@@ -535,10 +638,41 @@ int32_t gnb_decode_tc_query(const float* U, int32_t B, int32_t G, const float* q
     p.b2 = b2; p.w3s = w3s; p.tail = tail; p.out = out;
     p.acc_scale = ldexpf(1.0f, -w2_scale_log2);
     p.num_tiles = ceil_div<int64_t>(R, TC_M);
-    p.q = q; p.qptr = qptr;
+    p.q = q; p.qptr = qptr; p.w1 = nullptr; p.b1 = nullptr;
     if (Cout == 1) return launch_decode_tc<1, 2>(p, st);
     if (Cout == 2) return launch_decode_tc<2, 2>(p, st);
     return launch_decode_tc<3, 2>(p, st);
+}
+
+int32_t gnb_decode_tc_query_fused(const float* X, int32_t B, int32_t G, int32_t C0, const float* W1, const float* b1,
+                                  const float* q, const int64_t* qptr, int64_t R, const float* bn1_scale,
+                                  const float* bn1_shift, const void* w2_packed, int32_t w2_scale_log2, const float* b2,
+                                  const float* bn2_scale, const float* bn2_shift, const float* W3, const float* b3,
+                                  const float* bn3_scale, const float* bn3_shift, int32_t Cout, float* scratch,
+                                  float* out, void* stream) {
+    GNB_REQUIRE(X && W1 && b1 && q && qptr && bn1_scale && bn1_shift && w2_packed && b2 && W3 && scratch && out,
+                "gnb_decode_tc_query_fused: null pointer");
+    GNB_REQUIRE(C0 == 32, "gnb_decode_tc_query_fused: the feature grid must have 32 channels (got %d)", C0);
+    GNB_REQUIRE(Cout >= 1 && Cout <= 3, "gnb_decode_tc_query_fused: Cout must be 1..3 (got %d)", Cout);
+    GNB_REQUIRE(B >= 1 && B <= TC_MAX_B && G >= 2 && (int64_t)B * G * G * G * C0 < (1ll << 31),
+                "gnb_decode_tc_query_fused: need 1 <= B <= %d samples and feature grids below 2^31 elements in total", TC_MAX_B);
+    GNB_REQUIRE(R >= 0, "gnb_decode_tc_query_fused: negative row count");
+    if (R == 0) return GNB_OK;
+    cudaStream_t st = as_stream(stream);
+    float* w3s = scratch;
+    float* tail = scratch + 3 * TC_N;
+    fold_tail_kernel<<<Cout, TC_N, 0, st>>>(W3, b3, bn2_scale, bn2_shift, bn3_scale, bn3_shift, Cout, w3s, tail);
+    TcParams p;
+    p.U = X; p.ldx = 0; p.B = B; p.G = G; p.Q = 0; p.R = R;
+    p.bn1_scale = bn1_scale; p.bn1_shift = bn1_shift;
+    p.w2_packed = reinterpret_cast<const uint8_t*>(w2_packed);
+    p.b2 = b2; p.w3s = w3s; p.tail = tail; p.out = out;
+    p.acc_scale = ldexpf(1.0f, -w2_scale_log2);
+    p.num_tiles = ceil_div<int64_t>(R, TC_M);
+    p.q = q; p.qptr = qptr; p.w1 = W1; p.b1 = b1;
+    if (Cout == 1) return launch_decode_tc<1, 3>(p, st);
+    if (Cout == 2) return launch_decode_tc<2, 3>(p, st);
+    return launch_decode_tc<3, 3>(p, st);
 }
 
 }  // extern "C"

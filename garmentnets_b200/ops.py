@@ -507,6 +507,31 @@ def decode_tc_query(w2_packed, b2, bn2, W3, b3, bn3, *, U, q, qptr, bn1, out=Non
     return out
 
 
+def decode_tc_query_fused(W1, b1, w2_packed, b2, bn2, W3, b3, bn3, *, X, q, qptr, bn1, out=None) -> torch.Tensor:
+    """Query mode on the 32-channel grid (``gnb_decode_tc_query_fused``): ``X`` [B,G,G,G,32] channels-last, ``W1`` [256,32]
+    / ``b1`` [256] = the decoder's first Linear (with the UNet's final_conv folded in), applied per query inside the
+    kernel; ``q`` [R,3] query points of all samples back to back, ``qptr`` device i64[B+1] -> [R, Cout]."""
+    w2_packed, w2_s = w2_packed
+    Cout = W3.shape[0]
+    dev = W3.device
+    q = _req(q, torch.float32, "q")
+    qptr = _req(qptr, torch.int64, "qptr")
+    X = _req(X, torch.float32, "X")
+    W1 = _req(W1, torch.float32, "W1")
+    B, G, C0 = X.shape[0], X.shape[1], X.shape[-1]
+    assert W1.shape == (256, C0) and qptr.numel() == B + 1
+    R = q.shape[0]
+    if out is None:
+        out = torch.empty((R, Cout), dtype=torch.float32, device=dev)
+    s2, h2 = bn2 if bn2 is not None else (None, None)
+    s3, h3 = bn3 if bn3 is not None else (None, None)
+    scratch = torch.empty(1024, dtype=torch.float32, device=dev)
+    _lib.call("gnb_decode_tc_query_fused", X.data_ptr(), B, G, C0, W1.data_ptr(), b1.data_ptr(), q.data_ptr(), qptr.data_ptr(),
+              R, bn1[0].data_ptr(), bn1[1].data_ptr(), w2_packed.data_ptr(), w2_s, b2.data_ptr(), _ptr(s2), _ptr(h2),
+              W3.data_ptr(), _ptr(b3), _ptr(s3), _ptr(h3), Cout, scratch.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- tensor-core 3x3x3 conv
 def conv3d_tc_supported(B, D, H, W, Cin, Cout) -> bool:
     return bool(_lib.call("gnb_conv3d_tc_supported", int(B), int(D), int(H), int(W), int(Cin), int(Cout)))

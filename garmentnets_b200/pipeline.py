@@ -186,11 +186,9 @@ class ImplicitWNFDecoder(nn.Module):
         u = ops.linear_module(self, "hoisted", features_grid_ndhwc.reshape(-1, C), lin.weight, lin.bias)
         return u.view(B, D, H, W, -1)
 
-    def hoisted_folded(self, x_ndhwc: torch.Tensor, final_conv: nn.Conv3d) -> torch.Tensor:
-        """``hoisted(final_conv(x))`` as ONE affine map: grid @ (W1 Wf)^T + (W1 bf + b1).  ``x`` is the last UNet
-        decoder's output [B,D,H,W,Cf] (Cf = 32): the 128-channel feature volume is never materialised and the
-        per-voxel contraction runs over 32 instead of 128 channels (ref components/unet3d.py:467 followed by
-        networks/conv_implicit_wnf.py:148, first Linear of the MLP)."""
+    def folded_first_linear(self, final_conv: nn.Conv3d):
+        """(W1 Wf [C1, Cf], W1 bf + b1 [C1]): the UNet's 1x1x1 final_conv followed by this decoder's first Linear as ONE
+        affine map; cached per parameter version."""
         lin = self.mlp[0][0]
         wf = final_conv.weight.view(final_conv.out_channels, -1)
         key = (lin.weight._version, lin.weight.data_ptr(), wf._version, wf.data_ptr(),
@@ -202,9 +200,43 @@ class ImplicitWNFDecoder(nn.Module):
             b = ops.linear(bf.view(1, -1), lin.weight, lin.bias).view(-1)             # W1 bf + b1
             cached = (key, w, b)
             self._gnb_folded = cached
+        return cached[1], cached[2]
+
+    def hoisted_folded(self, x_ndhwc: torch.Tensor, final_conv: nn.Conv3d) -> torch.Tensor:
+        """``hoisted(final_conv(x))`` as ONE affine map: grid @ (W1 Wf)^T + (W1 bf + b1).  ``x`` is the last UNet
+        decoder's output [B,D,H,W,Cf] (Cf = 32): the 128-channel feature volume is never materialised and the
+        per-voxel contraction runs over 32 instead of 128 channels (ref components/unet3d.py:467 followed by
+        networks/conv_implicit_wnf.py:148, first Linear of the MLP)."""
+        w, b = self.folded_first_linear(final_conv)
         B, D, H, W, C = x_ndhwc.shape
-        u = ops.linear_module(self, "hoisted_folded", x_ndhwc.reshape(-1, C), cached[1], cached[2])
+        u = ops.linear_module(self, "hoisted_folded", x_ndhwc.reshape(-1, C), w, b)
         return u.view(B, D, H, W, -1)
+
+    def forward_fused_ragged(self, x_ndhwc: torch.Tensor, final_conv: nn.Conv3d, q_all: torch.Tensor, qptr_host):
+        """Like ``forward_hoisted_ragged`` but WITHOUT the hoisted 256-channel grid: the kernel interpolates the 32-channel
+        grid ``x`` (the UNet's last decoder level) at the query points and applies the folded first Linear per query
+        (interpolation commutes with an affine map), then the tensor-core tail.  [R,3] -> [R, Cout]."""
+        B = x_ndhwc.shape[0]
+        R = q_all.shape[0]
+        bn = self.mlp[0][2]
+        w1, b1 = self.folded_first_linear(final_conv)
+        out = torch.empty((R, self.mlp[2][0].out_features), dtype=torch.float32, device=x_ndhwc.device)
+        for b0 in range(0, B, 128):
+            b1_ = min(B, b0 + 128)
+            r0, r1 = int(qptr_host[b0]), int(qptr_host[b1_])
+            if r1 == r0:
+                continue
+            qptr = torch.as_tensor([int(x) - r0 for x in qptr_host[b0:b1_ + 1]], dtype=torch.int64).to(x_ndhwc.device)
+            with profiling.tag(f"{self.profile_tag}_tc"):
+                ops.decode_tc_query_fused(w1, b1, *self._tc_args(), X=x_ndhwc[b0:b1_], q=q_all[r0:r1], qptr=qptr,
+                                          bn1=bn.folded_affine(), out=out[r0:r1])
+        return out
+
+    def fused_query_ready(self, x_ndhwc: torch.Tensor) -> bool:
+        return (self.use_fused_query and self._tc_ready() and len(self.mlp[0]) > 2 and x_ndhwc.shape[-1] == 32
+                and self.mlp[0][0].out_features == 256 and x_ndhwc.is_contiguous())
+
+    use_fused_query = True   # False: hoist Linear1 onto a 256-channel grid and gather that (gnb_decode_tc_query)
 
     # ---- tensor-core tail (tcgen05): available for the shipped shape [C, 256, 256, Cout<=3] with BatchNorm --------
     use_tensor_cores = True
@@ -432,9 +464,12 @@ class ConvImplicitWNFPipeline(nn.Module):
         mark("marching_cubes")
         # warp field of every mesh vertex of the batch in one fused launch (gather + MLP on tcgen05)
         dec = self.surface_decoder
-        u_surf = dec.hoisted_folded(x_last, unet.final_conv)
         vptr = packed["vptr"]
-        warp_all = dec.forward_hoisted_ragged(u_surf, packed["verts"], vptr)
+        if dec.fused_query_ready(x_last):
+            warp_all = dec.forward_fused_ragged(x_last, unet.final_conv, packed["verts"], vptr)
+        else:
+            u_surf = dec.hoisted_folded(x_last, unet.final_conv)
+            warp_all = dec.forward_hoisted_ragged(u_surf, packed["verts"], vptr)
         results = []
         for b in range(B):
             mc = mcs[b]

@@ -249,6 +249,18 @@ int32_t gnb_decode_tc_query(const float* U, int32_t B, int32_t G, const float* q
                             const float* W3, const float* b3, const float* bn3_scale, const float* bn3_shift,
                             int32_t Cout, float* scratch, float* out, void* stream);
 
+/* Query mode on the 32-channel feature grid (FUSED): the decoder's first Linear is applied per query inside the kernel
+ * instead of being hoisted onto the grid -- trilinear interpolation commutes with the affine map, so
+ * interp(X) W1^T + b1 == interp(X W1^T + b1).  X f32[B,G,G,G,32] (channels-last; the UNet's last decoder level when
+ * final_conv is folded into W1), W1 f32[256,32], b1 f32[256].  The gather shrinks from 8 x 1 KB to 8 x 128 B per
+ * query; everything else as gnb_decode_tc_query. */
+int32_t gnb_decode_tc_query_fused(const float* X, int32_t B, int32_t G, int32_t C0, const float* W1, const float* b1,
+                                  const float* q, const int64_t* qptr, int64_t R, const float* bn1_scale,
+                                  const float* bn1_shift, const void* w2_packed, int32_t w2_scale_log2,
+                                  const float* b2, const float* bn2_scale, const float* bn2_shift,
+                                  const float* W3, const float* b3, const float* bn3_scale,
+                                  const float* bn3_shift, int32_t Cout, float* scratch, float* out, void* stream);
+
 /* ---- N13: gaussian gradient magnitude ------------------------------------------------------
  * ref: predict.py:162-163 `ni.gaussian_gradient_magnitude(wnf, sigma, mode="nearest")` (scipy 1.7).
  * v f32[D,H,W] -> out f32[D,H,W].  truncate = 4.0 (scipy default), so the filter radius is int(4*sigma + 0.5).

@@ -118,6 +118,39 @@ def test_query_mode_matches_oracle_and_row_mode(dev, counts, cout):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("counts,cout,G", [([333, 0, 1, 700], 3, 6), ([5], 1, 4), ([128, 128], 2, 8), ([0, 0, 9000], 3, 32),
+                                           ([20000, 30000], 3, 32)])
+def test_fused_query_mode_matches_oracle(dev, counts, cout, G):
+    """FUSED query mode (32-channel gather + Linear1 applied per query in the producers + tcgen05 tail) against the oracle
+    run the reference's way: final_conv (1x1x1) -> grid_sample -> MLP (ref components/unet3d.py:467,
+    networks/conv_implicit_wnf.py:128-149), and against the hoisted 256-channel query kernel."""
+    from garmentnets_b200 import ops
+    dec = _decoder(dev, cout, 30 + cout)
+    B = len(counts)
+    g = torch.Generator().manual_seed(sum(counts) + cout)
+    x32 = (torch.randn(B, G, G, G, 32, generator=g) * 0.8).to(dev)           # channels-last last UNet level
+    final_conv = torch.nn.Conv3d(32, 128, 1).to(dev).requires_grad_(False)
+    qs = [torch.rand(n, 3, generator=g) for n in counts]
+    if counts[-1] >= 4:
+        qs[-1][:4] = torch.tensor([[0, 0, 0], [1, 1, 1], [1.2, -0.1, 0.5], [0.5, 1.0, 0.0]])
+    q_all = torch.cat(qs).to(dev)
+    qptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    assert dec.fused_query_ready(x32)
+    got = dec.forward_fused_ragged(x32, final_conv, q_all, qptr).cpu()
+    assert got.shape == (sum(counts), cout)
+    hoisted = dec.forward_hoisted_ragged(dec.hoisted_folded(x32, final_conv), q_all, qptr).cpu()
+    assert (got - hoisted).abs().max().item() < 5e-5
+    sd = {k: v.cpu() for k, v in dec.state_dict().items()}
+    fv = F.conv3d(x32.permute(0, 4, 1, 2, 3).cpu(), final_conv.weight.cpu(), final_conv.bias.cpu())   # [B,128,G,G,G]
+    for b, n in enumerate(counts):
+        if n == 0:
+            continue
+        sl = slice(int(qptr[b]), int(qptr[b + 1]))
+        ref = ON.implicit_decoder(sd, "", fv[b:b + 1], qs[b].view(1, -1, 3))[0]
+        assert (got[sl] - ref).abs().max().item() < TOL
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("G,B", [(32, 3), (8, 1), (16, 2), (5, 2), (31, 1)])
 def test_pair_lattice_equals_first_generation(dev, G, B):
     """Pair-tile lattice kernel vs decode_tc lattice mode on other grid sizes (G < 32: idle producer groups; G > 32:

@@ -205,3 +205,17 @@ def test_pool_upsample_concat(dev):
     ref = torch.cat((skip, up), 1).permute(0, 2, 3, 4, 1)
     got = ops.upsample_concat(ops.to_channels_last(skip.to(dev)), p)
     assert torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Cs,Cx,size,small", [(32, 64, (8, 8, 8), (4, 4, 4)), (64, 128, (4, 6, 2), (2, 3, 1)), (8, 4, (5, 7, 3), (2, 3, 1))])
+def test_upsample_concat_vectorised(dev, Cs, Cx, size, small):
+    """16-byte path of gnb_upsample_concat (channel counts divisible by 4; ref components/unet3d.py:291,325-330),
+    including non-integer nearest-neighbour ratios."""
+    from garmentnets_b200 import ops
+    g = torch.Generator().manual_seed(Cs + Cx)
+    skip = torch.randn(3, Cs, *size, generator=g)
+    low = torch.randn(3, Cx, *small, generator=g)
+    ref = torch.cat((skip, F.interpolate(low, size=size, mode="nearest")), 1).permute(0, 2, 3, 4, 1)
+    got = ops.upsample_concat(ops.to_channels_last(skip.to(dev)), ops.to_channels_last(low.to(dev)))
+    assert torch.equal(got.cpu(), ref)
