@@ -24,6 +24,7 @@ from .. import ops
 
 # tensor-core (TMA + tcgen05) convolutions; False selects the fp32 FFMA kernel everywhere (used by the parity tests)
 USE_TENSOR_CORES = True
+USE_STACKED_DX = True    # Cout == 32 layers: stacked-kw tensor-core kernel (gnb_conv3d_tc_dx)
 
 
 def number_of_features_per_level(init_channel_number, num_levels):
@@ -100,16 +101,20 @@ class SingleConv(nn.Sequential):
         if USE_TENSOR_CORES and ops.conv3d_tc_supported(B, D, H, W, Cin, Cout):
             # TMA + tcgen05 implicit GEMM on the normalised activation written once as fp16 hi + lo
             xh, xl = ops.gn_apply_split(x, scale, shift)
+            if USE_STACKED_DX and ops.conv3d_tc_dx_supported(B, D, H, W, Cin, Cout):
+                # narrow layer: the three kw taps share one activation box (shift applied to the output)
+                return ops.conv3d_tc_dx(xh, xl, Cin, self.packed_weight_tc(dx=True), Cout, relu='r' in self.order)
             return ops.conv3d_tc(xh, xl, Cin, self.packed_weight_tc(), Cout, relu='r' in self.order)
         return ops.conv3d_k3(x, self.packed_weight(), scale, shift, relu='r' in self.order)
 
-    def packed_weight_tc(self) -> torch.Tensor:
+    def packed_weight_tc(self, dx: bool = False) -> torch.Tensor:
         w = self.conv.weight
         key = (w._version, w.data_ptr())
-        cached = getattr(self, '_gnb_wt_tc', None)
+        attr = '_gnb_wt_tc_dx' if dx else '_gnb_wt_tc'
+        cached = getattr(self, attr, None)
         if cached is None or cached[0] != key:
-            cached = (key, ops.conv3d_tc_pack_weights(w))
-            self._gnb_wt_tc = cached
+            cached = (key, ops.conv3d_tc_dx_pack_weights(w) if dx else ops.conv3d_tc_pack_weights(w))
+            setattr(self, attr, cached)
         return cached[1]
 
     def forward(self, x):

@@ -263,6 +263,199 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     }
 }
 
+// ---- stacked-dx variant for the narrow layers (Cout = 32) ---------------------------------------------------------------
+// With N = Cout = 32 every tcgen05.mma reads a 4 KB A slab from shared memory for 64 K MACs: the layer is bound by the
+// operand traffic (27 shifted copies of the activation through L2 -> smem -> tensor core), not by the tensor pipe.
+// Here the three kw taps of a (kd, kh) pair share ONE unshifted activation box: their weights are stacked along N,
+//     Z[v, j*32 + n] = sum_c X[v + (kd, kh, 0), c] * W[n, c, kd, kh, j]            (j = kw, N = 96)
+// and the shift along W is applied to the OUTPUT in the epilogue,  y[w] = Z_0[w-1] + Z_1[w] + Z_2[w+1], with warp
+// shuffles: a tile row is a whole W line (box width == W), so the neighbours are adjacent TMEM lanes of the same warp and
+// the line ends are exactly the zero padding.  The fp16 split costs 2 MMAs per K-step instead of 3: A_hi x [W_hi | W_lo]
+// (N = 192: hi*hi in columns 0..95, hi*lo in 96..191) and A_lo x W_hi (N = 96) accumulated onto columns 96..191.
+// Per output voxel that is 9 activation boxes instead of 27 and 18 MMAs per 64 channels instead of 81; the accumulation
+// chain of full-magnitude addends is 9*Cin/16 instructions long, so no accumulator rotation is needed.
+struct ConvDxParams {
+    int B, D, H, W, Cpad, Cout;
+    int bw, bh, bd, bb;
+    int nchunk, nstages, stage_bytes, b_bytes;   // b_bytes = 2 * 3 * Cout * 128 (hi rows then lo rows of one (kd,kh,chunk) piece)
+    int relu;
+    float out_scale;
+    const uint8_t* w_packed;   // [9][nchunk][hi: 3*Cout rows, lo: 3*Cout rows][128 B]
+    float* y;
+    int64_t num_tiles;
+};
+
+__global__ void __launch_bounds__(CT_THREADS, 1)
+conv_tc_dx_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                  const ConvDxParams p) {
+    using namespace ctc;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ __align__(8) uint64_t bars[2 * CT_MAX_STAGES + 4];
+    __shared__ uint32_t tmem_ptr_smem;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full = [&](int s) { return bar0 + 8 * s; };
+    auto empty = [&](int s) { return bar0 + 8 * (CT_MAX_STAGES + s); };
+    auto d_full = [&](int s) { return bar0 + 8 * (2 * CT_MAX_STAGES + s); };
+    auto d_empty = [&](int s) { return bar0 + 8 * (2 * CT_MAX_STAGES + 2 + s); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CT_MAX_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr_smem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_ptr_smem);
+
+    const int nbw = p.W / p.bw, nbh = p.H / p.bh, nbd = p.D / p.bd;
+    const int ksteps = 9 * p.nchunk;
+    const int NJ = 3 * p.Cout;   // stacked columns of one precision part (96)
+    const uint32_t idesc_wide = (1u << 4) | ((uint32_t)((2 * NJ) >> 3) << 17) | ((uint32_t)(CT_M >> 4) << 24);
+    const uint32_t idesc_half = (1u << 4) | ((uint32_t)(NJ >> 3) << 17) | ((uint32_t)(CT_M >> 4) << 24);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t st = 0;
+            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int64_t t = tile;
+                const int iw = (int)(t % nbw); t /= nbw;
+                const int ih = (int)(t % nbh); t /= nbh;
+                const int id = (int)(t % nbd); t /= nbd;
+                const int w0 = iw * p.bw, h0 = ih * p.bh, d0 = id * p.bd, b0 = (int)t * p.bb;
+                for (int ks = 0; ks < ksteps; ++ks, ++st) {
+                    const int tap = ks / p.nchunk, cc = ks - tap * p.nchunk;   // tap = kd*3 + kh
+                    const int dz = tap / 3 - 1, dy = tap % 3 - 1;
+                    const int slot = st % p.nstages;
+                    mbar_wait(empty(slot), ((st / p.nstages) & 1) ^ 1);
+                    mbar_expect_tx(full(slot), (uint32_t)p.stage_bytes);
+                    const uint32_t sa = sbase + slot * p.stage_bytes;
+                    tma_load_5d(sa, &map_hi, full(slot), cc * CT_KC, w0, h0 + dy, d0 + dz, b0);
+                    tma_load_5d(sa + CT_A_BYTES, &map_lo, full(slot), cc * CT_KC, w0, h0 + dy, d0 + dz, b0);
+                    bulk_g2s(sa + 2 * CT_A_BYTES, p.w_packed + (size_t)ks * p.b_bytes, (uint32_t)p.b_bytes, full(slot));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t st = 0;
+            int it = 0;
+            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int db = it & 1;
+                mbar_wait(d_empty(db), ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_set = tmem_base + (uint32_t)(db * 256);
+                for (int ks = 0; ks < ksteps; ++ks, ++st) {
+                    const int slot = st % p.nstages;
+                    mbar_wait(full(slot), (st / p.nstages) & 1);
+                    tc_fence_after();
+                    const uint32_t ahi = sbase + slot * p.stage_bytes, alo = ahi + CT_A_BYTES;
+                    const uint32_t bw_ = ahi + 2 * CT_A_BYTES;   // rows 0..NJ-1 = hi, NJ..2NJ-1 = lo
+#pragma unroll
+                    for (int kk = 0; kk < CT_KC / 16; ++kk) {
+                        umma_f16(d_set, umma_desc(ahi + kk * 32), umma_desc(bw_ + kk * 32), idesc_wide, (ks | kk) != 0);
+                        umma_f16(d_set + (uint32_t)NJ, umma_desc(alo + kk * 32), umma_desc(bw_ + kk * 32), idesc_half, 1);
+                    }
+                    umma_commit(empty(slot));
+                }
+                umma_commit(d_full(db));
+            }
+        }
+    } else {
+        // =========================== epilogue (warps 2..5): lane = voxel along W inside a line ===========================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int r = row;
+        const int lw = r % p.bw; r /= p.bw;
+        const int lh = r % p.bh; r /= p.bh;
+        const int ld = r % p.bd; r /= p.bd;
+        const int lb = r;
+        const bool first = lw == 0, last = lw == p.bw - 1;   // line ends: the shifted neighbour is the zero padding
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            int64_t t = tile;
+            const int iw = (int)(t % nbw); t /= nbw;
+            const int ih = (int)(t % nbh); t /= nbh;
+            const int id = (int)(t % nbd); t /= nbd;
+            const int64_t vox = ((((int64_t)t * p.bb + lb) * p.D + id * p.bd + ld) * p.H + ih * p.bh + lh) * p.W + iw * p.bw + lw;
+            float* dst = p.y + vox * p.Cout;
+            const int db = it & 1;
+            mbar_wait(d_full(db), (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(db * 256);
+            for (int n0 = 0; n0 < p.Cout; n0 += 32) {
+                float acc[32];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    uint32_t v[32], u[32];
+                    tmem_ld32(taddr + j * p.Cout + n0, v);
+                    tmem_ld32(taddr + NJ + j * p.Cout + n0, u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float z = __uint_as_float(v[i]) + __uint_as_float(u[i]);
+                        if (j == 0) {            // Z_0[w-1]
+                            z = __shfl_up_sync(0xffffffffu, z, 1);
+                            acc[i] = first ? 0.f : z;
+                        } else if (j == 1) {     // Z_1[w]
+                            acc[i] += z;
+                        } else {                 // Z_2[w+1]
+                            z = __shfl_down_sync(0xffffffffu, z, 1);
+                            acc[i] += last ? 0.f : z;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    o.x = acc[j] * p.out_scale; o.y = acc[j + 1] * p.out_scale;
+                    o.z = acc[j + 2] * p.out_scale; o.w = acc[j + 3] * p.out_scale;
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    *reinterpret_cast<float4*>(dst + n0 + j) = o;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(d_empty(db));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// W fp32 [Cout, Cin, 3,3,3] -> [9 (kd,kh)][Cpad/64][hi rows j*Cout+n (j = kw), then lo rows][64 K] fp16 SWIZZLE_128B images
+__global__ void pack_conv_weights_dx_kernel(const float* __restrict__ W, int Cout, int Cin, int Cpad, float wscale,
+                                            uint8_t* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)27 * Cpad * Cout;
+    if (t >= total) return;
+    const int n = (int)(t % Cout);
+    const int k = (int)((t / Cout) % Cpad);
+    const int tap = (int)(t / ((int64_t)Cout * Cpad));   // kd*9 + kh*3 + kw
+    float w = 0.f;
+    if (k < Cin) w = W[((int64_t)n * Cin + k) * 27 + tap] * wscale;
+    w = fminf(fmaxf(w, -65504.f), 65504.f);
+    const __half h = __float2half_rn(w);
+    const __half l = __float2half_rn(w - __half2float(h));
+    const int nchunk = Cpad / CT_KC;
+    const int cc = k / CT_KC, kc = k % CT_KC;
+    const int pair = tap / 3, j = tap % 3;
+    const int NJ = 3 * Cout;
+    uint8_t* piece = out + ((size_t)pair * nchunk + cc) * (size_t)(2 * NJ * 128);
+    *reinterpret_cast<__half*>(piece + ctc::sw128_offset(j * Cout + n, kc)) = h;
+    *reinterpret_cast<__half*>(piece + ctc::sw128_offset(NJ + j * Cout + n, kc)) = l;
+}
+
 // x fp32 [rows, C] (rows = B*voxels), scale/shift [B, C] -> xh, xl fp16 [rows, Cpad] (zero padded channels)
 __global__ void __launch_bounds__(256)
 gn_apply_split_kernel(const float* __restrict__ x, int64_t rows, int64_t vox_per_sample, int C, int Cpad,
@@ -414,6 +607,68 @@ int32_t gnb_conv3d_tc(const void* xh, const void* xl, int32_t B, int32_t D, int3
     if ((int64_t)grid > p.num_tiles) grid = (int)p.num_tiles;
     conv_tc_kernel<<<grid, CT_THREADS, smem, as_stream(stream)>>>(maps[0], maps[1], p);
     return check_launch("gnb_conv3d_tc");
+}
+
+int32_t gnb_conv3d_tc_dx_supported(int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout) {
+    if (!gnb_conv3d_tc_supported(B, D, H, W, Cin, Cout)) return 0;
+    // a tile row must be a whole W line (the shift along W is a warp shuffle) and the stacked accumulators must fit
+    return (Cout == 32 && (W == 32 || W == 16 || W == 8) && (int64_t)W <= CT_M) ? 1 : 0;
+}
+
+int32_t gnb_conv3d_tc_dx_pack_weights(const float* W, int32_t Cout, int32_t Cin, int32_t scale_log2, void* packed,
+                                      void* stream) {
+    GNB_REQUIRE(W && packed, "gnb_conv3d_tc_dx_pack_weights: null pointer");
+    GNB_REQUIRE(Cout == 32 && Cin > 0, "gnb_conv3d_tc_dx_pack_weights: Cout must be 32");
+    const int Cpad = ceil_div(Cin, CT_KC) * CT_KC;
+    const int64_t total = (int64_t)27 * Cpad * Cout;
+    pack_conv_weights_dx_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, as_stream(stream)>>>(
+        W, Cout, Cin, Cpad, ldexpf(1.0f, scale_log2), reinterpret_cast<uint8_t*>(packed));
+    return check_launch("gnb_conv3d_tc_dx_pack_weights");
+}
+
+int32_t gnb_conv3d_tc_dx(const void* xh, const void* xl, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin,
+                         const void* w_packed, int32_t scale_log2, int32_t Cout, int32_t relu, float* y, void* stream) {
+    GNB_REQUIRE(xh && xl && w_packed && y, "gnb_conv3d_tc_dx: null pointer");
+    GNB_REQUIRE(gnb_conv3d_tc_dx_supported(B, D, H, W, Cin, Cout), "gnb_conv3d_tc_dx: unsupported shape B=%d D=%d H=%d W=%d Cin=%d Cout=%d", B, D, H, W, Cin, Cout);
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) { set_error("gnb_conv3d_tc_dx: cuTensorMapEncodeTiled is not available from this driver"); return GNB_ERR_CUDA; }
+    ConvDxParams p;
+    p.B = B; p.D = D; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu;
+    p.out_scale = ldexpf(1.0f, -scale_log2);
+    p.Cpad = ceil_div(Cin, CT_KC) * CT_KC;
+    p.nchunk = p.Cpad / CT_KC;
+    int rem = CT_M;
+    p.bw = W; rem /= p.bw;
+    p.bh = H < rem ? H : rem; rem /= p.bh;
+    p.bd = D < rem ? D : rem; rem /= p.bd;
+    p.bb = rem;
+    GNB_REQUIRE(p.bb <= B && B % p.bb == 0, "gnb_conv3d_tc_dx: batch too small for a 128-voxel tile");
+    p.b_bytes = 2 * 3 * Cout * 128;
+    p.stage_bytes = 2 * CT_A_BYTES + p.b_bytes;
+    p.nstages = (220 * 1024) / p.stage_bytes;
+    if (p.nstages > CT_MAX_STAGES) p.nstages = CT_MAX_STAGES;
+    p.w_packed = reinterpret_cast<const uint8_t*>(w_packed);
+    p.y = y;
+    p.num_tiles = (int64_t)B * D * H * W / CT_M;
+    CUtensorMap maps[2];
+    const cuuint64_t gdim[5] = {(cuuint64_t)p.Cpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+    const cuuint64_t gstr[4] = {(cuuint64_t)p.Cpad * 2, (cuuint64_t)W * p.Cpad * 2, (cuuint64_t)H * W * p.Cpad * 2,
+                                (cuuint64_t)D * H * W * p.Cpad * 2};
+    const cuuint32_t box[5] = {(cuuint32_t)CT_KC, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd, (cuuint32_t)p.bb};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const void* srcs[2] = {xh, xl};
+    for (int i = 0; i < 2; ++i) {
+        CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(srcs[i]), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("gnb_conv3d_tc_dx: cuTensorMapEncodeTiled failed (%d)", (int)r); return GNB_ERR_CUDA; }
+    }
+    const int smem = p.nstages * p.stage_bytes + 1024;
+    GNB_CUDA(cudaFuncSetAttribute(conv_tc_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int grid = sm_count();
+    if ((int64_t)grid > p.num_tiles) grid = (int)p.num_tiles;
+    conv_tc_dx_kernel<<<grid, CT_THREADS, smem, as_stream(stream)>>>(maps[0], maps[1], p);
+    return check_launch("gnb_conv3d_tc_dx");
 }
 
 }  // extern "C"

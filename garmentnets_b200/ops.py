@@ -548,6 +548,31 @@ def conv3d_tc_pack_weights(weight: torch.Tensor):
     return packed, s
 
 
+def conv3d_tc_dx_supported(B, D, H, W, Cin, Cout) -> bool:
+    return bool(_lib.call("gnb_conv3d_tc_dx_supported", int(B), int(D), int(H), int(W), int(Cin), int(Cout)))
+
+
+def conv3d_tc_dx_pack_weights(weight: torch.Tensor):
+    """[32,Cin,3,3,3] fp32 -> (stacked-kw fp16 hi/lo images per ((kd,kh), 64-channel chunk), scale_log2)."""
+    weight = _req(weight, torch.float32, "weight")
+    Cout, Cin = weight.shape[:2]
+    cpad = (Cin + 63) // 64 * 64
+    s = _pow2_scale(weight)
+    packed = torch.empty(27 * cpad * Cout * 4, dtype=torch.uint8, device=weight.device)
+    _lib.call("gnb_conv3d_tc_dx_pack_weights", weight.data_ptr(), Cout, Cin, s, packed.data_ptr(), _stream())
+    return packed, s
+
+
+def conv3d_tc_dx(xh: torch.Tensor, xl: torch.Tensor, cin: int, w_packed, cout: int, relu: bool = True):
+    """Stacked-dx tensor-core convolution for Cout == 32 (``gnb_conv3d_tc_dx``); same contract as ``conv3d_tc``."""
+    w_packed, w_s = w_packed
+    B, D, H, W, _ = xh.shape
+    y = torch.empty((B, D, H, W, cout), dtype=torch.float32, device=xh.device)
+    _lib.call("gnb_conv3d_tc_dx", xh.data_ptr(), xl.data_ptr(), B, D, H, W, int(cin), w_packed.data_ptr(), w_s, int(cout),
+              int(relu), y.data_ptr(), _stream())
+    return y
+
+
 def gn_apply_split(x: torch.Tensor, scale, shift):
     """x [B,D,H,W,C] fp32 -> (xh, xl) fp16 [B,D,H,W,Cpad] holding x*scale+shift as hi + lo."""
     B, D, H, W, C = x.shape

@@ -181,6 +181,16 @@ int32_t gnb_gn_apply_split(const float* x, int32_t B, int64_t voxels, int32_t C,
                            void* xh, void* xl, void* stream);
 int32_t gnb_conv3d_tc(const void* xh, const void* xl, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin,
                       const void* w_packed, int32_t scale_log2, int32_t Cout, int32_t relu, float* y, void* stream);
+
+/* Stacked-dx variant of gnb_conv3d_tc for the narrow layers (Cout == 32, W in {8,16,32}): the three kw taps of a
+ * (kd,kh) pair share one activation box, their weights are stacked along N and the shift along W is applied to the
+ * output with warp shuffles; 9 instead of 27 activation boxes per tile and 2 instead of 3 MMAs per fp16-split product.
+ * Same arguments and results as gnb_conv3d_tc; weights packed by gnb_conv3d_tc_dx_pack_weights (same byte size). */
+int32_t gnb_conv3d_tc_dx_supported(int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout);
+int32_t gnb_conv3d_tc_dx_pack_weights(const float* W, int32_t Cout, int32_t Cin, int32_t scale_log2, void* packed,
+                                      void* stream);
+int32_t gnb_conv3d_tc_dx(const void* xh, const void* xl, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin,
+                         const void* w_packed, int32_t scale_log2, int32_t Cout, int32_t relu, float* y, void* stream);
 int32_t gnb_maxpool3d_2(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, float* y, void* stream);
 /* y[b,d,h,w, 0:Cs] = skip[b,d,h,w,:];  y[..., Cs:Cs+Cx] = x[b, d*Dx/D, h*Hx/H, w*Wx/W, :] (nearest). */
 int32_t gnb_upsample_concat(const float* skip, int32_t Cs, const float* x, int32_t Cx, int32_t B,

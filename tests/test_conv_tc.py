@@ -34,6 +34,27 @@ def test_conv_tc_matches_torch(dev, B, G, Cin, Cout):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B,D,H,W,Cin", [(2, 8, 8, 8, 32), (1, 16, 16, 16, 96), (1, 32, 32, 32, 128), (4, 2, 4, 16, 40),
+                                         (1, 4, 8, 32, 64)])
+def test_conv_tc_stacked_dx_matches_torch(dev, B, D, H, W, Cin):
+    """Stacked-kw kernel (Cout = 32): the shift along W applied to the output must reproduce zero padding at both ends of
+    every line, for every tile geometry (W = 8 / 16 / 32)."""
+    from garmentnets_b200 import ops
+    Cout = 32
+    assert ops.conv3d_tc_dx_supported(B, D, H, W, Cin, Cout)
+    g = torch.Generator().manual_seed(Cin * 5 + W)
+    x = torch.randn(B, Cin, D, H, W, generator=g) * 1.5 + 0.3
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5
+    ref = F.relu(F.conv3d(x.double(), w.double(), None, padding=1)).float().permute(0, 2, 3, 4, 1)
+    xh, xl = ops.gn_apply_split(ops.to_channels_last(x.to(dev)), None, None)
+    y = ops.conv3d_tc_dx(xh, xl, Cin, ops.conv3d_tc_dx_pack_weights(w.to(dev)), Cout, relu=True)
+    err = (y.cpu() - ref).abs().max().item()
+    assert err < 2e-5, err
+    y3 = ops.conv3d_tc(xh, xl, Cin, ops.conv3d_tc_pack_weights(w.to(dev)), Cout, relu=True)
+    assert (y - y3).abs().max().item() < 2e-5
+
+
+@pytest.mark.gpu
 def test_unet_tc_equals_fp32_path(dev):
     from garmentnets_b200 import synthetic
     from garmentnets_b200.components import unet3d
