@@ -24,7 +24,7 @@ from .. import ops
 
 # tensor-core (TMA + tcgen05) convolutions; False selects the fp32 FFMA kernel everywhere (used by the parity tests)
 USE_TENSOR_CORES = True
-USE_STACKED_DX = True    # Cout == 32 layers: stacked-kw tensor-core kernel (gnb_conv3d_tc_dx)
+USE_STACKED_DX = True    # Cout in {32, 64} layers: stacked-kw tensor-core kernel (gnb_conv3d_tc_dx)
 
 
 def number_of_features_per_level(init_channel_number, num_levels):

@@ -272,6 +272,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 // shuffles: a tile row is a whole W line (box width == W), so the neighbours are adjacent TMEM lanes of the same warp and
 // the line ends are exactly the zero padding.  The fp16 split costs 2 MMAs per K-step instead of 3: A_hi x [W_hi | W_lo]
 // (N = 192: hi*hi in columns 0..95, hi*lo in 96..191) and A_lo x W_hi (N = 96) accumulated onto columns 96..191.
+// Cout = 64 stacks to N = 192 per precision part (three MMAs per K-step, one accumulator set, no double buffering).
 // Per output voxel that is 9 activation boxes instead of 27 and 18 MMAs per 64 channels instead of 81; the accumulation
 // chain of full-magnitude addends is 9*Cin/16 instructions long, so no accumulator rotation is needed.
 struct ConvDxParams {
@@ -317,7 +318,9 @@ conv_tc_dx_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
 
     const int nbw = p.W / p.bw, nbh = p.H / p.bh, nbd = p.D / p.bd;
     const int ksteps = 9 * p.nchunk;
-    const int NJ = 3 * p.Cout;   // stacked columns of one precision part (96)
+    const int NJ = 3 * p.Cout;   // stacked columns of one precision part (96 or 192)
+    const bool wide = 2 * NJ <= 256;          // Cout = 32: [W_hi | W_lo] fits one N = 192 instruction
+    const int nbuf = 4 * NJ <= 512 ? 2 : 1;   // accumulator sets (2*NJ columns each) double-buffered when TMEM has room
     const uint32_t idesc_wide = (1u << 4) | ((uint32_t)((2 * NJ) >> 3) << 17) | ((uint32_t)(CT_M >> 4) << 24);
     const uint32_t idesc_half = (1u << 4) | ((uint32_t)(NJ >> 3) << 17) | ((uint32_t)(CT_M >> 4) << 24);
 
@@ -348,8 +351,8 @@ conv_tc_dx_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             uint32_t st = 0;
             int it = 0;
             for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const int db = it & 1;
-                mbar_wait(d_empty(db), ((it >> 1) & 1) ^ 1);
+                const int db = it % nbuf;
+                mbar_wait(d_empty(db), ((it / nbuf) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_set = tmem_base + (uint32_t)(db * 256);
                 for (int ks = 0; ks < ksteps; ++ks, ++st) {
@@ -358,10 +361,20 @@ conv_tc_dx_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                     tc_fence_after();
                     const uint32_t ahi = sbase + slot * p.stage_bytes, alo = ahi + CT_A_BYTES;
                     const uint32_t bw_ = ahi + 2 * CT_A_BYTES;   // rows 0..NJ-1 = hi, NJ..2NJ-1 = lo
+                    if (wide) {
 #pragma unroll
-                    for (int kk = 0; kk < CT_KC / 16; ++kk) {
-                        umma_f16(d_set, umma_desc(ahi + kk * 32), umma_desc(bw_ + kk * 32), idesc_wide, (ks | kk) != 0);
-                        umma_f16(d_set + (uint32_t)NJ, umma_desc(alo + kk * 32), umma_desc(bw_ + kk * 32), idesc_half, 1);
+                        for (int kk = 0; kk < CT_KC / 16; ++kk) {
+                            umma_f16(d_set, umma_desc(ahi + kk * 32), umma_desc(bw_ + kk * 32), idesc_wide, (ks | kk) != 0);
+                            umma_f16(d_set + (uint32_t)NJ, umma_desc(alo + kk * 32), umma_desc(bw_ + kk * 32), idesc_half, 1);
+                        }
+                    } else {
+                        const uint32_t blo = bw_ + (uint32_t)NJ * 128;
+#pragma unroll
+                        for (int kk = 0; kk < CT_KC / 16; ++kk) {
+                            umma_f16(d_set, umma_desc(ahi + kk * 32), umma_desc(bw_ + kk * 32), idesc_half, (ks | kk) != 0);
+                            umma_f16(d_set + (uint32_t)NJ, umma_desc(alo + kk * 32), umma_desc(bw_ + kk * 32), idesc_half, (ks | kk) != 0);
+                            umma_f16(d_set + (uint32_t)NJ, umma_desc(ahi + kk * 32), umma_desc(blo + kk * 32), idesc_half, 1);
+                        }
                     }
                     umma_commit(empty(slot));
                 }
@@ -386,8 +399,8 @@ conv_tc_dx_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             const int id = (int)(t % nbd); t /= nbd;
             const int64_t vox = ((((int64_t)t * p.bb + lb) * p.D + id * p.bd + ld) * p.H + ih * p.bh + lh) * p.W + iw * p.bw + lw;
             float* dst = p.y + vox * p.Cout;
-            const int db = it & 1;
-            mbar_wait(d_full(db), (it >> 1) & 1);
+            const int db = it % nbuf;
+            mbar_wait(d_full(db), (it / nbuf) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(db * 256);
             for (int n0 = 0; n0 < p.Cout; n0 += 32) {
@@ -612,13 +625,13 @@ int32_t gnb_conv3d_tc(const void* xh, const void* xl, int32_t B, int32_t D, int3
 int32_t gnb_conv3d_tc_dx_supported(int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout) {
     if (!gnb_conv3d_tc_supported(B, D, H, W, Cin, Cout)) return 0;
     // a tile row must be a whole W line (the shift along W is a warp shuffle) and the stacked accumulators must fit
-    return (Cout == 32 && (W == 32 || W == 16 || W == 8) && (int64_t)W <= CT_M) ? 1 : 0;
+    return ((Cout == 32 || Cout == 64) && (W == 32 || W == 16 || W == 8) && (int64_t)W <= CT_M) ? 1 : 0;
 }
 
 int32_t gnb_conv3d_tc_dx_pack_weights(const float* W, int32_t Cout, int32_t Cin, int32_t scale_log2, void* packed,
                                       void* stream) {
     GNB_REQUIRE(W && packed, "gnb_conv3d_tc_dx_pack_weights: null pointer");
-    GNB_REQUIRE(Cout == 32 && Cin > 0, "gnb_conv3d_tc_dx_pack_weights: Cout must be 32");
+    GNB_REQUIRE((Cout == 32 || Cout == 64) && Cin > 0, "gnb_conv3d_tc_dx_pack_weights: Cout must be 32 or 64");
     const int Cpad = ceil_div(Cin, CT_KC) * CT_KC;
     const int64_t total = (int64_t)27 * Cpad * Cout;
     pack_conv_weights_dx_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, as_stream(stream)>>>(

@@ -50,7 +50,12 @@ struct TcSmem {
     static constexpr int qptr = ztab;                                 // QUERY: [TC_MAX_B + 1] i64 sample row offsets (aliases ztab/kstart)
     static constexpr int total = kstart + (TC_MAX_G + 2) * 4;
     static_assert((TC_MAX_B + 1) * 8 <= total - ztab, "qptr table must fit in the lattice tables it aliases");
-    static constexpr int xs = b_ring + 2 * B_PIECE_BYTES;             // FUSED: [128][32] fp32 interpolated inputs (the B ring has 2 slots)
+    // FUSED carves the 96 KB B region differently: 3 slots x 16 KB (half pieces: 128 of the 256 W2 rows), the interpolated
+    // inputs and W1
+    static constexpr int fb_piece = B_PIECE_BYTES / 2;                // 16 KB
+    static constexpr int xs = b_ring + 3 * fb_piece;                  // [128][32] fp32 interpolated inputs (16 KB)
+    static constexpr int w1s = xs + TC_M * 32 * 4;                    // [4 chunks][32 k][32 lanes] float2 = W1 pairs (32 KB)
+    static_assert(w1s + TC_N * 32 * 4 <= bars, "FUSED carve-up must fit the B region");
 };
 static_assert(TcSmem::total + 1024 <= 227 * 1024, "shared memory budget");
 
@@ -83,7 +88,8 @@ decode_tc_kernel(const TcParams p) {
     constexpr bool LATTICE = MODE == 1;
     constexpr bool FUSED = MODE == 3;
     constexpr bool QUERY = MODE == 2 || FUSED;
-    constexpr int NBS = FUSED ? 2 : B_SLOTS;   // B ring slots (FUSED gives the third slot to the interpolated inputs)
+    constexpr int NBS = B_SLOTS;
+    constexpr int PB = FUSED ? TcSmem::fb_piece : B_PIECE_BYTES;   // bytes per B ring slot
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms need a 1024-byte aligned base
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -100,7 +106,7 @@ decode_tc_kernel(const TcParams p) {
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + TcSmem::tmem_ptr);
 
     if (threadIdx.x == 0) {
-        for (int c = 0; c < 4; ++c) { mbar_init(a_full(c), 64); mbar_init(a_empty(c), 1); }
+        for (int c = 0; c < 4; ++c) { mbar_init(a_full(c), FUSED ? 256 : 64); mbar_init(a_empty(c), 1); }
         for (int s = 0; s < B_SLOTS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -120,6 +126,15 @@ decode_tc_kernel(const TcParams p) {
     if (QUERY) {
         int64_t* qp = reinterpret_cast<int64_t*>(smem + TcSmem::qptr);
         for (int i = threadIdx.x; i <= p.B; i += TC_THREADS) qp[i] = p.qptr[i];
+    }
+    if (FUSED) {
+        // W1 pairs (w[c0][k], w[c0+1][k]) laid out [chunk][k][lane]: a warp reads 256 contiguous bytes per (chunk, k)
+        float2* w1s = reinterpret_cast<float2*>(smem + TcSmem::w1s);
+        for (int i = threadIdx.x; i < 4 * 32 * 32; i += TC_THREADS) {
+            const int ln = i & 31, k = (i >> 5) & 31, c = i >> 10;
+            const int ch = c * TC_KCHUNK + 2 * ln;
+            w1s[i] = make_float2(__ldg(p.w1 + ch * 32 + k), __ldg(p.w1 + (ch + 1) * 32 + k));
+        }
     }
     if (warp == 12) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + TcSmem::tmem_ptr), "r"(512));
@@ -150,14 +165,6 @@ decode_tc_kernel(const TcParams p) {
         if (LATTICE || QUERY) { sc0 = p.bn1_scale[c0]; sc1 = p.bn1_scale[c0 + 1]; sh0 = p.bn1_shift[c0]; sh1 = p.bn1_shift[c0 + 1]; }
         const int* zt = reinterpret_cast<const int*>(smem + TcSmem::ztab);
         int it = 0;
-        // FUSED: this thread's two rows of W1 (output channels c0, c0+1) stay in registers for the whole kernel
-        float2 w1r[FUSED ? 32 : 1];
-        float2 b1r = make_float2(0.f, 0.f);
-        if (FUSED) {
-#pragma unroll
-            for (int k = 0; k < (FUSED ? 32 : 1); ++k) w1r[k] = make_float2(__ldg(p.w1 + c0 * 32 + k), __ldg(p.w1 + (c0 + 1) * 32 + k));
-            b1r = make_float2(__ldg(p.b1 + c0), __ldg(p.b1 + c0 + 1));
-        }
         for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             if (!FUSED) mbar_wait(a_empty(chunk), (it & 1) ^ 1);
             if (FUSED) {
@@ -209,43 +216,63 @@ decode_tc_kernel(const TcParams p) {
                                  "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");   // all 128 interpolated rows are in shared memory
-                mbar_wait(a_empty(chunk), (it & 1) ^ 1);
-                // ---- phase 1: H1 = BN1(ReLU(xs * W1^T + b1)) for this warp's 64 rows x this thread's 2 channels
+                // ---- phase 1, chunk by chunk: H1[:, 64c..64c+63] = BN1(ReLU(xs * W1^T + b1)).  ALL eight warps work on the
+                // same K-chunk (warp w: rows 16w..16w+15, lane: two channels), so chunk c is handed to the tensor core
+                // while chunk c+1 is being computed, and chunk c of the NEXT tile can be refilled as soon as this tile's
+                // MMAs have consumed it.
+                const uint32_t w1_addr = sbase + TcSmem::w1s;
 #pragma unroll 1
-                for (int rr = 0; rr < TC_M / 2; rr += 4) {
-                    const int k0 = half * (TC_M / 2) + rr;
-                    unsigned long long acc[4];
+                for (int c = 0; c < TC_NCHUNK; ++c) {
+                    const int ch = c * TC_KCHUNK + 2 * lane;
+                    float2 w1r[32];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) asm("mov.b64 %0, {%1, %2};" : "=l"(acc[u]) : "f"(b1r.x), "f"(b1r.y));
+                    for (int k = 0; k < 32; ++k)
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(w1r[k].x), "=f"(w1r[k].y)
+                                     : "r"(w1_addr + (uint32_t)(((c * 32 + k) * 32 + lane) * 8)));
+                    const float2 b1r = make_float2(__ldg(p.b1 + ch), __ldg(p.b1 + ch + 1));
+                    const float s0 = __ldg(p.bn1_scale + ch), s1 = __ldg(p.bn1_scale + ch + 1);
+                    const float h0s = __ldg(p.bn1_shift + ch), h1s = __ldg(p.bn1_shift + ch + 1);
+                    uint8_t* ah = smem + TcSmem::a_hi + c * A_CHUNK_BYTES;
+                    uint8_t* al = smem + TcSmem::a_lo + c * A_CHUNK_BYTES;
+                    mbar_wait(a_empty(c), (it & 1) ^ 1);
+#pragma unroll 1
+                    for (int rr = 0; rr < 16; rr += 4) {
+                        const int k0 = warp * 16 + rr;
+                        unsigned long long acc[4];
 #pragma unroll
-                    for (int k4 = 0; k4 < 32; k4 += 4) {
+                        for (int u = 0; u < 4; ++u) asm("mov.b64 %0, {%1, %2};" : "=l"(acc[u]) : "f"(b1r.x), "f"(b1r.y));
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            float4 xv;
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xv.x), "=f"(xv.y), "=f"(xv.z), "=f"(xv.w)
-                                         : "r"(xs_addr + (uint32_t)(((k0 + u) * 32 + k4) * 4)));
-                            const float xk[4] = {xv.x, xv.y, xv.z, xv.w};
+                        for (int k4 = 0; k4 < 32; k4 += 4) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                unsigned long long ww, xx;
-                                asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w1r[k4 + j].x), "f"(w1r[k4 + j].y));
-                                asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(xk[j]));
-                                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[u]) : "l"(ww), "l"(xx));
+                            for (int u = 0; u < 4; ++u) {
+                                float4 xv;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xv.x), "=f"(xv.y), "=f"(xv.z), "=f"(xv.w)
+                                             : "r"(xs_addr + (uint32_t)(((k0 + u) * 32 + k4) * 4)));
+                                const float xk[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    unsigned long long ww, xx;
+                                    asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w1r[k4 + j].x), "f"(w1r[k4 + j].y));
+                                    asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(xk[j]));
+                                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[u]) : "l"(ww), "l"(xx));
+                                }
                             }
                         }
-                    }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float h0, h1;
-                        asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(acc[u]));
-                        h0 = fmaxf(h0, 0.f) * sc0 + sh0;
-                        h1 = fmaxf(h1, 0.f) * sc1 + sh1;
-                        uint32_t hi, lo;
-                        split_f16x2(h0, h1, hi, lo);
-                        const uint32_t o2 = sw128_offset(k0 + u, 2 * lane);
-                        *reinterpret_cast<uint32_t*>(a_hi + o2) = hi;
-                        *reinterpret_cast<uint32_t*>(a_lo + o2) = lo;
+                        for (int u = 0; u < 4; ++u) {
+                            float h0, h1;
+                            asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(acc[u]));
+                            h0 = fmaxf(h0, 0.f) * s0 + h0s;
+                            h1 = fmaxf(h1, 0.f) * s1 + h1s;
+                            uint32_t hi, lo;
+                            split_f16x2(h0, h1, hi, lo);
+                            const uint32_t o2 = sw128_offset(k0 + u, 2 * lane);
+                            *reinterpret_cast<uint32_t*>(ah + o2) = hi;
+                            *reinterpret_cast<uint32_t*>(al + o2) = lo;
+                        }
                     }
+                    fence_proxy_async();
+                    mbar_arrive(a_full(c));
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");   // xs may be overwritten by the next tile's phase 0
             } else if (LATTICE) {
@@ -401,8 +428,10 @@ decode_tc_kernel(const TcParams p) {
                     *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
                 }
             }
-            fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
-            mbar_arrive(a_full(chunk));
+            if (!FUSED) {
+                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+                mbar_arrive(a_full(chunk));
+            }
         }
     } else if (warp < 12) {
         // =========================== epilogue ===========================

@@ -553,7 +553,7 @@ def conv3d_tc_dx_supported(B, D, H, W, Cin, Cout) -> bool:
 
 
 def conv3d_tc_dx_pack_weights(weight: torch.Tensor):
-    """[32,Cin,3,3,3] fp32 -> (stacked-kw fp16 hi/lo images per ((kd,kh), 64-channel chunk), scale_log2)."""
+    """[32|64,Cin,3,3,3] fp32 -> (stacked-kw fp16 hi/lo images per ((kd,kh), 64-channel chunk), scale_log2)."""
     weight = _req(weight, torch.float32, "weight")
     Cout, Cin = weight.shape[:2]
     cpad = (Cin + 63) // 64 * 64
@@ -564,7 +564,7 @@ def conv3d_tc_dx_pack_weights(weight: torch.Tensor):
 
 
 def conv3d_tc_dx(xh: torch.Tensor, xl: torch.Tensor, cin: int, w_packed, cout: int, relu: bool = True):
-    """Stacked-dx tensor-core convolution for Cout == 32 (``gnb_conv3d_tc_dx``); same contract as ``conv3d_tc``."""
+    """Stacked-dx tensor-core convolution for Cout in {32, 64} (``gnb_conv3d_tc_dx``); same contract as ``conv3d_tc``."""
     w_packed, w_s = w_packed
     B, D, H, W, _ = xh.shape
     y = torch.empty((B, D, H, W, cout), dtype=torch.float32, device=xh.device)

@@ -182,7 +182,7 @@ int32_t gnb_gn_apply_split(const float* x, int32_t B, int64_t voxels, int32_t C,
 int32_t gnb_conv3d_tc(const void* xh, const void* xl, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin,
                       const void* w_packed, int32_t scale_log2, int32_t Cout, int32_t relu, float* y, void* stream);
 
-/* Stacked-dx variant of gnb_conv3d_tc for the narrow layers (Cout == 32, W in {8,16,32}): the three kw taps of a
+/* Stacked-dx variant of gnb_conv3d_tc for the narrow layers (Cout in {32,64}, W in {8,16,32}): the three kw taps of a
  * (kd,kh) pair share one activation box, their weights are stacked along N and the shift along W is applied to the
  * output with warp shuffles; 9 instead of 27 activation boxes per tile and 2 instead of 3 MMAs per fp16-split product.
  * Same arguments and results as gnb_conv3d_tc; weights packed by gnb_conv3d_tc_dx_pack_weights (same byte size). */

@@ -34,13 +34,13 @@ def test_conv_tc_matches_torch(dev, B, G, Cin, Cout):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,D,H,W,Cin", [(2, 8, 8, 8, 32), (1, 16, 16, 16, 96), (1, 32, 32, 32, 128), (4, 2, 4, 16, 40),
-                                         (1, 4, 8, 32, 64)])
-def test_conv_tc_stacked_dx_matches_torch(dev, B, D, H, W, Cin):
-    """Stacked-kw kernel (Cout = 32): the shift along W applied to the output must reproduce zero padding at both ends of
+@pytest.mark.parametrize("B,D,H,W,Cin,Cout", [(2, 8, 8, 8, 32, 32), (1, 16, 16, 16, 96, 32), (1, 32, 32, 32, 128, 32),
+                                              (4, 2, 4, 16, 40, 32), (1, 4, 8, 32, 64, 32), (2, 16, 16, 16, 192, 64),
+                                              (1, 16, 16, 16, 32, 64), (2, 8, 8, 8, 64, 64)])
+def test_conv_tc_stacked_dx_matches_torch(dev, B, D, H, W, Cin, Cout):
+    """Stacked-kw kernel (Cout = 32 / 64): the shift along W applied to the output must reproduce zero padding at both ends of
     every line, for every tile geometry (W = 8 / 16 / 32)."""
     from garmentnets_b200 import ops
-    Cout = 32
     assert ops.conv3d_tc_dx_supported(B, D, H, W, Cin, Cout)
     g = torch.Generator().manual_seed(Cin * 5 + W)
     x = torch.randn(B, Cin, D, H, W, generator=g) * 1.5 + 0.3
