@@ -114,21 +114,6 @@ __device__ __forceinline__ void relu_split2(float2 h, uint32_t& hi, uint32_t& lo
     lo = pack_f16x2_sat(r.x, r.y);
 }
 
-// mbarrier wait with a suspend-time hint: the waiting thread sleeps in hardware instead of spinning through the issue
-// slots the producer warps need
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP_S:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra DONE_S;\n\t"
-        "bra WAIT_LOOP_S;\n\t"
-        "DONE_S:\n\t"
-        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680)
-        : "memory");
-}
-
 // lattice index -> feature-grid cell and weights along one axis (same fp32 arithmetic as gnb_trilinear_sample_grid)
 __device__ __forceinline__ void axis_cell(int idx, float sq, int G, int& c0, int& c1, float& w0, float& w1) {
     const float g = __fsub_rn(__fmul_rn(2.0f, __fmul_rn((float)idx, sq)), 1.0f);
@@ -390,13 +375,13 @@ decode_lattice_kernel(const Params p) {
                 auto fold = [&](const uint32_t (&r)[32], int n0) {
 #pragma unroll
                     for (int u = 0; u < 32; u += 4) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2s + n0 + u));
+                        const float4 bb = ldg_keep(p.b2s + n0 + u);
                         float2 v0 = add2(make_float2(__uint_as_float(r[u]), __uint_as_float(r[u + 1])), make_float2(bb.x, bb.y));
                         float2 v1 = add2(make_float2(__uint_as_float(r[u + 2]), __uint_as_float(r[u + 3])), make_float2(bb.z, bb.w));
                         v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f);
 #pragma unroll
                         for (int o = 0; o < COUT; ++o) {
-                            const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w3s + o * N + n0 + u));
+                            const float4 ww = ldg_keep(p.w3s + o * N + n0 + u);
                             dot[o][0] = fma2(v0, make_float2(ww.x, ww.y), dot[o][0]);
                             dot[o][1] = fma2(v1, make_float2(ww.z, ww.w), dot[o][1]);
                         }

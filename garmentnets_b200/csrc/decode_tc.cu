@@ -24,6 +24,7 @@
 //   warps 8-11 epilogue: tcgen05.ld of the accumulator rows (lane = row), bias/ReLU/BN2 folded with W3, store.
 // TMEM: 2 x 256 columns (accumulator double buffer: epilogue(t) overlaps MMA(t+1)); smem: A 128 KB + B ring 96 KB.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace gnb {
 
@@ -31,6 +32,7 @@ constexpr int TC_K = 256, TC_N = 256, TC_M = 128, TC_KCHUNK = 64, TC_NCHUNK = TC
 constexpr int A_CHUNK_BYTES = TC_M * TC_KCHUNK * 2;      // 16 KB (one precision part)
 constexpr int B_PIECE_BYTES = TC_N * TC_KCHUNK * 2;      // 32 KB
 constexpr int B_SLOTS = 3;
+constexpr int B_SLOTS_MAX = 7;  // FUSED mode: seven 16 KB half pieces in flight
 constexpr int TC_THREADS = 448;  // 8 producer + 4 epilogue + MMA + loader warps
 constexpr int TC_MAX_G = 64;
 constexpr int TC_MAX_B = 128;   // QUERY mode: samples per launch (row offsets cached in shared memory)
@@ -43,19 +45,23 @@ struct TcSmem {
     static constexpr int a_lo = a_hi + TC_NCHUNK * A_CHUNK_BYTES;     // [4][16 KB]
     static constexpr int b_ring = a_lo + TC_NCHUNK * A_CHUNK_BYTES;   // [3][32 KB]
     static constexpr int bars = b_ring + B_SLOTS * B_PIECE_BYTES;     // mbarriers
-    static constexpr int n_bars = 4 + 4 + B_SLOTS + B_SLOTS + 2 + 2;
+    static constexpr int n_bars = 4 + 4 + B_SLOTS_MAX + B_SLOTS_MAX + 2 + 2;
     static constexpr int tmem_ptr = bars + n_bars * 8;
     static constexpr int ztab = tmem_ptr + 16;                        // [128] {int z0, float wz1}
     static constexpr int kstart = ztab + TC_M * 8;                    // [G+1] first row of every D-cell
     static constexpr int qptr = ztab;                                 // QUERY: [TC_MAX_B + 1] i64 sample row offsets (aliases ztab/kstart)
     static constexpr int total = kstart + (TC_MAX_G + 2) * 4;
     static_assert((TC_MAX_B + 1) * 8 <= total - ztab, "qptr table must fit in the lattice tables it aliases");
-    // FUSED carves the 96 KB B region differently: 3 slots x 16 KB (half pieces: 128 of the 256 W2 rows), the interpolated
-    // inputs and W1
-    static constexpr int fb_piece = B_PIECE_BYTES / 2;                // 16 KB
-    static constexpr int xs = b_ring + 3 * fb_piece;                  // [128][32] fp32 interpolated inputs (16 KB)
-    static constexpr int w1s = xs + TC_M * 32 * 4;                    // [4 chunks][32 k][32 lanes] float2 = W1 pairs (32 KB)
-    static_assert(w1s + TC_N * 32 * 4 <= bars, "FUSED carve-up must fit the B region");
+    // FUSED re-carves the 224 KB: the A operand is a RING of two K-chunks (the producers fill chunk c+1 while the tensor core
+    // consumes chunk c), which frees 64 KB for a deep W2 ring -- seven 16 KB half pieces (128 of the 256 W2 rows) in
+    // flight; with three the stream was latency-bound (~15k clk per tile for 256 KB).
+    static constexpr int fa_slot = 2 * A_CHUNK_BYTES;                  // 32 KB: one K-chunk, hi then lo
+    static constexpr int fa = 0;                                       // [2][32 KB]
+    static constexpr int fb_piece = B_PIECE_BYTES / 2;                 // 16 KB
+    static constexpr int fb_ring = fa + 2 * fa_slot;                   // [7][16 KB]
+    static constexpr int xs = fb_ring + B_SLOTS_MAX * fb_piece;        // [128][32] fp32 interpolated inputs (16 KB)
+    static constexpr int w1s = xs + TC_M * 32 * 4;                     // [4 chunks][32 k][32 lanes] float2 = W1 pairs (32 KB)
+    static_assert(w1s + TC_N * 32 * 4 <= bars, "FUSED carve-up must fit in front of the barriers");
 };
 static_assert(TcSmem::total + 1024 <= 227 * 1024, "shared memory budget");
 
@@ -77,6 +83,7 @@ struct TcParams {
     const int64_t* qptr;    // QUERY: [B+1] first row of every sample (rows of sample b sample U[b])
     const float* w1;        // FUSED: [256][32] first Linear (final_conv folded in), applied per query in the producers
     const float* b1;        // FUSED: [256]
+    int dbg;                // profiling aid (GNB_TC_DBG, FUSED mode): 1 skip the gather, 2 skip Linear1 math, 4 skip the epilogue math, 8 no W2 copies
 };
 
 // MODE 0: rows of a given H1 matrix; 1: implicit 128^3 lattice; 2: explicit query points (ragged per sample) on the hoisted
@@ -88,8 +95,9 @@ decode_tc_kernel(const TcParams p) {
     constexpr bool LATTICE = MODE == 1;
     constexpr bool FUSED = MODE == 3;
     constexpr bool QUERY = MODE == 2 || FUSED;
-    constexpr int NBS = B_SLOTS;
+    constexpr int NBS = FUSED ? B_SLOTS_MAX : B_SLOTS;
     constexpr int PB = FUSED ? TcSmem::fb_piece : B_PIECE_BYTES;   // bytes per B ring slot
+    constexpr int BR = FUSED ? TcSmem::fb_ring : TcSmem::b_ring;     // offset of the B ring
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms need a 1024-byte aligned base
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -100,14 +108,14 @@ decode_tc_kernel(const TcParams p) {
     auto a_full = [&](int c) { return bar0 + 8 * c; };
     auto a_empty = [&](int c) { return bar0 + 8 * (4 + c); };
     auto b_full = [&](int s) { return bar0 + 8 * (8 + s); };
-    auto b_empty = [&](int s) { return bar0 + 8 * (8 + B_SLOTS + s); };
-    auto d_full = [&](int s) { return bar0 + 8 * (8 + 2 * B_SLOTS + s); };
-    auto d_empty = [&](int s) { return bar0 + 8 * (8 + 2 * B_SLOTS + 2 + s); };
+    auto b_empty = [&](int s) { return bar0 + 8 * (8 + B_SLOTS_MAX + s); };
+    auto d_full = [&](int s) { return bar0 + 8 * (8 + 2 * B_SLOTS_MAX + s); };
+    auto d_empty = [&](int s) { return bar0 + 8 * (8 + 2 * B_SLOTS_MAX + 2 + s); };
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + TcSmem::tmem_ptr);
 
     if (threadIdx.x == 0) {
         for (int c = 0; c < 4; ++c) { mbar_init(a_full(c), FUSED ? 256 : 64); mbar_init(a_empty(c), 1); }
-        for (int s = 0; s < B_SLOTS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < B_SLOTS_MAX; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -162,7 +170,19 @@ decode_tc_kernel(const TcParams p) {
         uint8_t* a_lo = smem + TcSmem::a_lo + chunk * A_CHUNK_BYTES;
         const int* kst = reinterpret_cast<const int*>(smem + TcSmem::kstart);
         float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
-        if (LATTICE || QUERY) { sc0 = p.bn1_scale[c0]; sc1 = p.bn1_scale[c0 + 1]; sh0 = p.bn1_shift[c0]; sh1 = p.bn1_shift[c0 + 1]; }
+        if ((LATTICE || QUERY) && !FUSED) { sc0 = p.bn1_scale[c0]; sc1 = p.bn1_scale[c0 + 1]; sh0 = p.bn1_shift[c0]; sh1 = p.bn1_shift[c0 + 1]; }
+        // FUSED: this thread's first-layer bias for its two channels of every K-chunk, loaded once (BN1 is normally folded
+        // into W2 / b2 by the caller; bn1 pointers are then NULL)
+        float2 b1c[FUSED ? TC_NCHUNK : 1];
+        if (FUSED) {
+#pragma unroll
+            for (int c = 0; c < (FUSED ? TC_NCHUNK : 1); ++c) b1c[c] = make_float2(__ldg(p.b1 + c * TC_KCHUNK + 2 * lane), __ldg(p.b1 + c * TC_KCHUNK + 2 * lane + 1));
+        }
+        float qn[3] = {0.f, 0.f, 0.f};   // FUSED: query point of this lane's row of the NEXT tile (loaded one tile ahead)
+        if (FUSED) {
+            const int64_t r = (int64_t)blockIdx.x * TC_M + warp * 16 + (lane & 15);
+            if (r < p.R) { qn[0] = __ldg(p.q + r * 3); qn[1] = __ldg(p.q + r * 3 + 1); qn[2] = __ldg(p.q + r * 3 + 2); }
+        }
         const int* zt = reinterpret_cast<const int*>(smem + TcSmem::ztab);
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -184,19 +204,22 @@ decode_tc_kernel(const TcParams p) {
                     if (r < p.R) {
                         int lo_b = 0, hi_b = p.B;  // largest b with qptr[b] <= r
                         while (hi_b - lo_b > 1) { const int mid = (lo_b + hi_b) >> 1; if (qp[mid] <= r) lo_b = mid; else hi_b = mid; }
-                        const float g0 = __fsub_rn(__fmul_rn(2.0f, __ldg(p.q + r * 3)), 1.0f);
-                        const float g1 = __fsub_rn(__fmul_rn(2.0f, __ldg(p.q + r * 3 + 1)), 1.0f);
-                        const float g2 = __fsub_rn(__fmul_rn(2.0f, __ldg(p.q + r * 3 + 2)), 1.0f);
+                        const float g0 = __fsub_rn(__fmul_rn(2.0f, qn[0]), 1.0f);
+                        const float g1 = __fsub_rn(__fmul_rn(2.0f, qn[1]), 1.0f);
+                        const float g2 = __fsub_rn(__fmul_rn(2.0f, qn[2]), 1.0f);
                         TriW t;
                         trilinear_setup(g0, g1, g2, G, G, G, 32, t);
                         const int sb = lo_b * G * G * G * 32;
 #pragma unroll
                         for (int k = 0; k < 8; ++k) { off[k] = sb + (int)t.off[k]; wgt[k] = t.w[k]; }
                     }
+                    // the next tile's query point: its HBM latency is hidden behind this tile's gather and Linear1
+                    const int64_t rn = (tile + gridDim.x) * TC_M + warp * 16 + (lane & 15);
+                    if (rn < p.R) { qn[0] = __ldg(p.q + rn * 3); qn[1] = __ldg(p.q + rn * 3 + 1); qn[2] = __ldg(p.q + rn * 3 + 2); }
                 }
                 const float* xbase = p.U + 4 * (lane & 7);
 #pragma unroll 1
-                for (int grp = 0; grp < 4; ++grp) {
+                for (int grp = 0; grp < ((p.dbg & 1) ? 0 : 4); ++grp) {
                     const int src = grp * 4 + (lane >> 3);      // row (within the warp's 16) this lane gathers for
                     float4 v[8];
                     float w[8];
@@ -221,7 +244,7 @@ decode_tc_kernel(const TcParams p) {
                 // while chunk c+1 is being computed, and chunk c of the NEXT tile can be refilled as soon as this tile's
                 // MMAs have consumed it.
                 const uint32_t w1_addr = sbase + TcSmem::w1s;
-#pragma unroll 1
+#pragma unroll
                 for (int c = 0; c < TC_NCHUNK; ++c) {
                     const int ch = c * TC_KCHUNK + 2 * lane;
                     float2 w1r[32];
@@ -229,12 +252,16 @@ decode_tc_kernel(const TcParams p) {
                     for (int k = 0; k < 32; ++k)
                         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(w1r[k].x), "=f"(w1r[k].y)
                                      : "r"(w1_addr + (uint32_t)(((c * 32 + k) * 32 + lane) * 8)));
-                    const float2 b1r = make_float2(__ldg(p.b1 + ch), __ldg(p.b1 + ch + 1));
-                    const float s0 = __ldg(p.bn1_scale + ch), s1 = __ldg(p.bn1_scale + ch + 1);
-                    const float h0s = __ldg(p.bn1_shift + ch), h1s = __ldg(p.bn1_shift + ch + 1);
-                    uint8_t* ah = smem + TcSmem::a_hi + c * A_CHUNK_BYTES;
-                    uint8_t* al = smem + TcSmem::a_lo + c * A_CHUNK_BYTES;
-                    mbar_wait(a_empty(c), (it & 1) ^ 1);
+                    const float2 b1r = b1c[c];
+                    float s0 = 1.f, s1 = 1.f, h0s = 0.f, h1s = 0.f;
+                    if (p.bn1_scale != nullptr) {   // un-folded BatchNorm1 (slow path: four dependent global loads per chunk)
+                        s0 = __ldg(p.bn1_scale + ch); s1 = __ldg(p.bn1_scale + ch + 1);
+                        h0s = __ldg(p.bn1_shift + ch); h1s = __ldg(p.bn1_shift + ch + 1);
+                    }
+                    const uint32_t cc = (uint32_t)it * TC_NCHUNK + c;      // running chunk counter: ring slot cc & 1
+                    uint8_t* ah = smem + TcSmem::fa + (cc & 1) * TcSmem::fa_slot;
+                    uint8_t* al = ah + A_CHUNK_BYTES;
+                    mbar_wait(a_empty(cc & 1), ((cc >> 1) & 1) ^ 1);
 #pragma unroll 1
                     for (int rr = 0; rr < 16; rr += 4) {
                         const int k0 = warp * 16 + rr;
@@ -242,7 +269,7 @@ decode_tc_kernel(const TcParams p) {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) asm("mov.b64 %0, {%1, %2};" : "=l"(acc[u]) : "f"(b1r.x), "f"(b1r.y));
 #pragma unroll
-                        for (int k4 = 0; k4 < 32; k4 += 4) {
+                        for (int k4 = 0; k4 < ((p.dbg & 2) ? 4 : 32); k4 += 4) {
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 float4 xv;
@@ -272,7 +299,7 @@ decode_tc_kernel(const TcParams p) {
                         }
                     }
                     fence_proxy_async();
-                    mbar_arrive(a_full(c));
+                    mbar_arrive(a_full(cc & 1));
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");   // xs may be overwritten by the next tile's phase 0
             } else if (LATTICE) {
@@ -443,26 +470,26 @@ decode_tc_kernel(const TcParams p) {
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int db = it & 1;
-            mbar_wait(d_full(db), (it >> 1) & 1);
+            mbar_wait_sleep(d_full(db), (it >> 1) & 1);
             tc_fence_after();
             float dot[COUT];
 #pragma unroll
             for (int o = 0; o < COUT; ++o) dot[o] = 0.f;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(db * TC_N);
 #pragma unroll 1
-            for (int n0 = 0; n0 < TC_N; n0 += 32) {
+            for (int n0 = 0; n0 < ((p.dbg & 4) ? 32 : TC_N); n0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(taddr + n0, r);
                 tmem_ld_wait();
 #pragma unroll
                 for (int t = 0; t < 32; t += 4) {
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + n0 + t));
+                    const float4 bb = ldg_keep(p.b2 + n0 + t);
                     const float as = p.acc_scale;
                     const float v0 = fmaxf(fmaf(__uint_as_float(r[t]), as, bb.x), 0.f), v1 = fmaxf(fmaf(__uint_as_float(r[t + 1]), as, bb.y), 0.f);
                     const float v2 = fmaxf(fmaf(__uint_as_float(r[t + 2]), as, bb.z), 0.f), v3 = fmaxf(fmaf(__uint_as_float(r[t + 3]), as, bb.w), 0.f);
 #pragma unroll
                     for (int o = 0; o < COUT; ++o) {
-                        const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w3s + o * TC_N + n0 + t));
+                        const float4 ww = ldg_keep(p.w3s + o * TC_N + n0 + t);
                         dot[o] = fmaf(v3, ww.w, fmaf(v2, ww.z, fmaf(v1, ww.y, fmaf(v0, ww.x, dot[o]))));
                     }
                 }
@@ -483,17 +510,47 @@ decode_tc_kernel(const TcParams p) {
             uint32_t piece = 0;
             for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const int db = it & 1;
-                mbar_wait(d_empty(db), ((it >> 1) & 1) ^ 1);
+                mbar_wait_sleep(d_empty(db), ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(db * TC_N);
                 for (int c = 0; c < TC_NCHUNK; ++c) {
-                    mbar_wait(a_full(c), it & 1);
-                    const uint32_t ahi = sbase + TcSmem::a_hi + c * A_CHUNK_BYTES;
-                    const uint32_t alo = sbase + TcSmem::a_lo + c * A_CHUNK_BYTES;
+                    const uint32_t cc = (uint32_t)it * TC_NCHUNK + c;
+                    if (FUSED) mbar_wait_sleep(a_full(cc & 1), (cc >> 1) & 1);
+                    else mbar_wait_sleep(a_full(c), it & 1);
+                    const uint32_t ahi = FUSED ? sbase + TcSmem::fa + (cc & 1) * TcSmem::fa_slot : sbase + TcSmem::a_hi + c * A_CHUNK_BYTES;
+                    const uint32_t alo = FUSED ? ahi + A_CHUNK_BYTES : sbase + TcSmem::a_lo + c * A_CHUNK_BYTES;
+                    if (FUSED) {
+                        // half pieces (128 of the 256 W2 rows = 128 accumulator columns each): hi.n0, hi.n1, lo.n0, lo.n1
+                        constexpr uint32_t IDESC_H = (1u << 4) | ((uint32_t)((TC_N / 2) >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+#pragma unroll 1
+                        for (int hp = 0; hp < 4; ++hp, ++piece) {
+                            const int slot = piece % NBS;
+                            mbar_wait_sleep(b_full(slot), (piece / NBS) & 1);
+                            tc_fence_after();
+                            const uint32_t bs = sbase + BR + slot * PB;
+                            const uint32_t dd = d_tmem + (uint32_t)((hp & 1) * (TC_N / 2));
+                            if (p.dbg & 16) {   // profiling: no tensor work at all
+                            } else if (hp < 2) {
+#pragma unroll
+                                for (int kk = 0; kk < TC_KCHUNK / 16; ++kk)
+                                    umma_f16(dd, umma_desc(ahi + kk * 32), umma_desc(bs + kk * 32), IDESC_H, (c | kk) != 0);
+#pragma unroll
+                                for (int kk = 0; kk < TC_KCHUNK / 16; ++kk)
+                                    umma_f16(dd, umma_desc(alo + kk * 32), umma_desc(bs + kk * 32), IDESC_H, 1);
+                            } else {
+#pragma unroll
+                                for (int kk = 0; kk < TC_KCHUNK / 16; ++kk)
+                                    umma_f16(dd, umma_desc(ahi + kk * 32), umma_desc(bs + kk * 32), IDESC_H, 1);
+                            }
+                            umma_commit(b_empty(slot));
+                        }
+                        umma_commit(a_empty(cc & 1));
+                        continue;
+                    }
                     // piece 0: W2_hi chunk c -> A_hi*B_hi and A_lo*B_hi
                     {
                         const int slot = piece % NBS;
-                        mbar_wait(b_full(slot), (piece / NBS) & 1);
+                        mbar_wait_sleep(b_full(slot), (piece / NBS) & 1);
                         tc_fence_after();
                         const uint32_t bs = sbase + TcSmem::b_ring + slot * B_PIECE_BYTES;
 #pragma unroll
@@ -508,7 +565,7 @@ decode_tc_kernel(const TcParams p) {
                     // piece 1: W2_lo chunk c -> A_hi*B_lo
                     {
                         const int slot = piece % NBS;
-                        mbar_wait(b_full(slot), (piece / NBS) & 1);
+                        mbar_wait_sleep(b_full(slot), (piece / NBS) & 1);
                         tc_fence_after();
                         const uint32_t bs = sbase + TcSmem::b_ring + slot * B_PIECE_BYTES;
 #pragma unroll
@@ -527,12 +584,13 @@ decode_tc_kernel(const TcParams p) {
         if (lane == 0) {
             uint32_t piece = 0;
             for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                for (int pc = 0; pc < 2 * TC_NCHUNK; ++pc, ++piece) {
+                // FUSED streams half pieces: the packed image of (chunk, hi|lo) is 256 rows x 128 B, rows 0..127 first
+                for (int pc = 0; pc < (FUSED ? 4 : 2) * TC_NCHUNK; ++pc, ++piece) {
                     const int slot = piece % NBS;
-                    mbar_wait(b_empty(slot), ((piece / NBS) & 1) ^ 1);
-                    mbar_expect_tx(b_full(slot), B_PIECE_BYTES);
-                    bulk_g2s(sbase + TcSmem::b_ring + slot * B_PIECE_BYTES, p.w2_packed + (size_t)pc * B_PIECE_BYTES,
-                             B_PIECE_BYTES, b_full(slot));
+                    mbar_wait_sleep(b_empty(slot), ((piece / NBS) & 1) ^ 1);
+                    if (FUSED && (p.dbg & 8) && tile != blockIdx.x) { mbar_arrive(b_full(slot)); continue; }   // profiling: W2 stream off
+                    mbar_expect_tx(b_full(slot), PB);
+                    bulk_g2s(sbase + BR + slot * PB, p.w2_packed + (size_t)pc * PB, PB, b_full(slot));
                 }
             }
         }
@@ -633,7 +691,7 @@ int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t
     p.b2 = b2; p.w3s = w3s; p.tail = tail; p.out = out;
     p.acc_scale = ldexpf(1.0f, -w2_scale_log2);
     p.num_tiles = lattice ? (int64_t)B * Q * Q : ceil_div<int64_t>(R, TC_M);
-    p.q = nullptr; p.qptr = nullptr; p.w1 = nullptr; p.b1 = nullptr;
+    p.q = nullptr; p.qptr = nullptr; p.w1 = nullptr; p.b1 = nullptr; p.dbg = 0;
     if (lattice) {
         if (Cout == 1) return launch_decode_tc<1, 1>(p, st);
         if (Cout == 2) return launch_decode_tc<2, 1>(p, st);
@@ -667,7 +725,7 @@ int32_t gnb_decode_tc_query(const float* U, int32_t B, int32_t G, const float* q
     p.b2 = b2; p.w3s = w3s; p.tail = tail; p.out = out;
     p.acc_scale = ldexpf(1.0f, -w2_scale_log2);
     p.num_tiles = ceil_div<int64_t>(R, TC_M);
-    p.q = q; p.qptr = qptr; p.w1 = nullptr; p.b1 = nullptr;
+    p.q = q; p.qptr = qptr; p.w1 = nullptr; p.b1 = nullptr; p.dbg = 0;
     if (Cout == 1) return launch_decode_tc<1, 2>(p, st);
     if (Cout == 2) return launch_decode_tc<2, 2>(p, st);
     return launch_decode_tc<3, 2>(p, st);
@@ -679,8 +737,8 @@ int32_t gnb_decode_tc_query_fused(const float* X, int32_t B, int32_t G, int32_t 
                                   const float* bn2_scale, const float* bn2_shift, const float* W3, const float* b3,
                                   const float* bn3_scale, const float* bn3_shift, int32_t Cout, float* scratch,
                                   float* out, void* stream) {
-    GNB_REQUIRE(X && W1 && b1 && q && qptr && bn1_scale && bn1_shift && w2_packed && b2 && W3 && scratch && out,
-                "gnb_decode_tc_query_fused: null pointer");
+    GNB_REQUIRE(X && W1 && b1 && q && qptr && w2_packed && b2 && W3 && scratch && out, "gnb_decode_tc_query_fused: null pointer");
+    GNB_REQUIRE((bn1_scale == nullptr) == (bn1_shift == nullptr), "gnb_decode_tc_query_fused: bn1_scale and bn1_shift go together");
     GNB_REQUIRE(C0 == 32, "gnb_decode_tc_query_fused: the feature grid must have 32 channels (got %d)", C0);
     GNB_REQUIRE(Cout >= 1 && Cout <= 3, "gnb_decode_tc_query_fused: Cout must be 1..3 (got %d)", Cout);
     GNB_REQUIRE(B >= 1 && B <= TC_MAX_B && G >= 2 && (int64_t)B * G * G * G * C0 < (1ll << 31),
@@ -699,6 +757,7 @@ int32_t gnb_decode_tc_query_fused(const float* X, int32_t B, int32_t G, int32_t 
     p.acc_scale = ldexpf(1.0f, -w2_scale_log2);
     p.num_tiles = ceil_div<int64_t>(R, TC_M);
     p.q = q; p.qptr = qptr; p.w1 = W1; p.b1 = b1;
+    { const char* e = getenv("GNB_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
     if (Cout == 1) return launch_decode_tc<1, 3>(p, st);
     if (Cout == 2) return launch_decode_tc<2, 3>(p, st);
     return launch_decode_tc<3, 3>(p, st);

@@ -148,7 +148,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
             // Full tiles are written by the TMA unit (coalesced, asynchronous); the tile that contains the device-side
             // row count falls back to per-thread stores so rows >= R are never touched.
             const bool tma_tile = p.use_tma && row0 + LT_M <= R;
-            mbar_wait(d_full(db), (it >> 1) & 1);
+            mbar_wait_sleep(d_full(db), (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(db * 256);
             const float* cb = p.cparams + nb * p.Npad;
@@ -223,7 +223,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
             int it = 0;
             for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 const int db = it & 1;
-                mbar_wait(d_empty(db), ((it >> 1) & 1) ^ 1);
+                mbar_wait_sleep(d_empty(db), ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(db * 256);
                 for (int c = 0; c < p.nchunk; ++c, ++st, ++piece) {
@@ -231,12 +231,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
                     int bslot;
                     if (p.resident) {
                         bslot = c;
-                        mbar_wait(b_full(bslot), 0);       // completes once; stays complete for every later tile
+                        mbar_wait_sleep(b_full(bslot), 0);       // completes once; stays complete for every later tile
                     } else {
                         bslot = piece % p.nb;
-                        mbar_wait(b_full(bslot), (piece / p.nb) & 1);
+                        mbar_wait_sleep(b_full(bslot), (piece / p.nb) & 1);
                     }
-                    mbar_wait(a_full(slot), (st / p.na) & 1);
+                    mbar_wait_sleep(a_full(slot), (st / p.na) & 1);
                     tc_fence_after();
                     const uint32_t ahi = sbase + slot * LT_A_STAGE, alo = ahi + LT_A_PART;
                     const uint32_t bhi = b_ring + bslot * p.piece_bytes, blo = bhi + p.piece_bytes / 2;
@@ -274,7 +274,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
                     const int nb = (int)(tile % p.n_blocks);
                     for (int c = 0; c < p.nchunk; ++c, ++piece) {
                         const int slot = piece % p.nb;
-                        mbar_wait(b_empty(slot), ((piece / p.nb) & 1) ^ 1);
+                        mbar_wait_sleep(b_empty(slot), ((piece / p.nb) & 1) ^ 1);
                         mbar_expect_tx(b_full(slot), (uint32_t)p.piece_bytes);
                         bulk_g2s(b_ring + slot * p.piece_bytes, p.w_packed + ((size_t)nb * p.nchunk + c) * p.piece_bytes,
                                  (uint32_t)p.piece_bytes, b_full(slot));

@@ -218,7 +218,6 @@ class ImplicitWNFDecoder(nn.Module):
         (interpolation commutes with an affine map), then the tensor-core tail.  [R,3] -> [R, Cout]."""
         B = x_ndhwc.shape[0]
         R = q_all.shape[0]
-        bn = self.mlp[0][2]
         w1, b1 = self.folded_first_linear(final_conv)
         out = torch.empty((R, self.mlp[2][0].out_features), dtype=torch.float32, device=x_ndhwc.device)
         for b0 in range(0, B, 128):
@@ -228,9 +227,24 @@ class ImplicitWNFDecoder(nn.Module):
                 continue
             qptr = torch.as_tensor([int(x) - r0 for x in qptr_host[b0:b1_ + 1]], dtype=torch.int64).to(x_ndhwc.device)
             with profiling.tag(f"{self.profile_tag}_tc"):
-                ops.decode_tc_query_fused(w1, b1, *self._tc_args(), X=x_ndhwc[b0:b1_], q=q_all[r0:r1], qptr=qptr,
-                                          bn1=bn.folded_affine(), out=out[r0:r1])
+                ops.decode_tc_query_fused(w1, b1, *self._tc_args_bn1_folded(), X=x_ndhwc[b0:b1_], q=q_all[r0:r1],
+                                          qptr=qptr, bn1=None, out=out[r0:r1])
         return out
+
+    def _tc_args_bn1_folded(self):
+        """``_tc_args`` with BatchNorm1 folded into Linear2: BN1 follows the ReLU, so it is a linear map in front of
+        Linear2 -- W2' = W2 diag(scale1), b2' = b2 + W2 shift1 (packed fp16 hi/lo, cached per parameter version)."""
+        l2, l3 = self.mlp[1][0], self.mlp[2][0]
+        bn1 = self.mlp[0][2]
+        key = ops._version_key(l2.weight, l2.bias, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var)
+        cached = getattr(self, "_gnb_w2_bn1_folded", None)
+        if cached is None or cached[0] != key:
+            sc, sh = bn1.folded_affine()
+            w2f = (l2.weight * sc[None, :]).contiguous()
+            b2f = ops.linear(sh.view(1, -1).contiguous(), l2.weight, l2.bias).view(-1).contiguous()   # W2 shift1 + b2
+            cached = (key, ops.pack_f16_split(w2f), b2f)
+            self._gnb_w2_bn1_folded = cached
+        return (cached[1], cached[2], self.mlp[1][2].folded_affine(), l3.weight, l3.bias, self.mlp[2][2].folded_affine())
 
     def fused_query_ready(self, x_ndhwc: torch.Tensor) -> bool:
         return (self.use_fused_query and self._tc_ready() and len(self.mlp[0]) > 2 and x_ndhwc.shape[-1] == 32

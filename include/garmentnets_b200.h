@@ -263,7 +263,9 @@ int32_t gnb_decode_tc_query(const float* U, int32_t B, int32_t G, const float* q
  * instead of being hoisted onto the grid -- trilinear interpolation commutes with the affine map, so
  * interp(X) W1^T + b1 == interp(X W1^T + b1).  X f32[B,G,G,G,32] (channels-last; the UNet's last decoder level when
  * final_conv is folded into W1), W1 f32[256,32], b1 f32[256].  The gather shrinks from 8 x 1 KB to 8 x 128 B per
- * query; everything else as gnb_decode_tc_query. */
+ * query; everything else as gnb_decode_tc_query.  bn1_scale / bn1_shift may be NULL when the caller has folded
+ * BatchNorm1 (it follows the ReLU, so it is linear in front of Linear2) into w2_packed / b2: W2' = W2 diag(scale),
+ * b2' = b2 + W2 shift -- the fast path. */
 int32_t gnb_decode_tc_query_fused(const float* X, int32_t B, int32_t G, int32_t C0, const float* W1, const float* b1,
                                   const float* q, const int64_t* qptr, int64_t R, const float* bn1_scale,
                                   const float* bn1_shift, const void* w2_packed, int32_t w2_scale_log2,
