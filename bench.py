@@ -13,7 +13,8 @@ own B clouds, no data-path collective, one all-gather of per-rank counters at th
 * `e2e`       : the same through the public host-buffer API (pipeline.HostPredictor): pinned-host clouds -> H2D, whole
                 path, every mesh array and the per-point NOCS prediction -> D2H into pinned staging on a copy stream
                 (the copies of batch i overlap the kernels of batch i+1), all inside the timed region.
-* `roofline`  : the dominant kernel (fused tcgen05 lattice decode) timed live with CUDA events on its launching stream.
+* `roofline`  : the dominant kernel (fused tcgen05 lattice decode) timed live with CUDA events on its launching stream;
+                `unet3d` reports the 3D-UNet stage against the HBM and tensor peaks (BASELINE.json's second metric).
 * `cpu_baseline` / `--impl reference`: the CPU oracle (a port of the reference's predict.py:138-187; the reference
   itself cannot be imported here) timed on the host cores on a bounded sample.
 """
@@ -49,6 +50,20 @@ def _peaks():
         return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
                 "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def _unet_report(ms, B, peaks):
+    """BASELINE.json also asks for the 3D-UNet against the roofline: algorithmic activation + weight bytes and FLOPs of the
+    32^3 UNet (111.968 MB and 50.38 GFLOP per volume, 18.5 MB of weights per batch) over the
+    device time of the stage.  At an arithmetic intensity of ~450 FLOP/B the UNet is tensor-bound on B200, so the HBM
+    fraction is small by construction; the tensor fraction counts ALGORITHMIC FLOPs (the fp16 split executes 3x)."""
+    if not ms:
+        return None
+    gbs = (111.968e6 * B + 18.5e6) / (ms * 1e-3) / 1e9
+    tf = 50.38e9 * B / (ms * 1e-3) / 1e12
+    return {"ms": ms, "hbm_gbs_algorithmic": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4),
+            "tflops_algorithmic": round(tf, 1), "frac_of_bf16_sustained": round(tf / peaks["bf16_tflops_sustained"], 4),
+            "executed_tensor_frac": round(3 * tf / peaks["bf16_tflops_sustained"], 4)}
 
 
 class ClockSampler:
@@ -314,10 +329,20 @@ def run_ours(args, rank, world):
     # one event pair per gnb_decode_tc call (it brackets fold_tail, ~2 us, and the decode kernel)
     queries_per_launch = (B * args.steps * pr["volume_size"] ** 3) / max(n_k, 1)
     achieved = DECODE_FLOP_PER_QUERY * queries_per_launch / (ms_k / max(n_k, 1) * 1e-3) / 1e12 if n_k else None
-    roofline = {"kernel": "decode_tc_kernel<1,true> (fused lattice decode: trilinear + BN1 + Linear2 on tcgen05 + BN2 + "
-                          "Linear3 + BN3 for B x 128^3 queries in one launch)",
+    # DRAM traffic of one launch of that kernel, from the committed `ncu --set full` capture (profiles/ncu_traffic_r01.json,
+    # written by tools/ncu_traffic.py from the .ncu-rep); null when the capture does not match this batch size
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)).get("decode_lattice_kernel")
+        if tj and tj.get("batch") == B:
+            traffic = tj["dram_bytes_per_launch"]
+    roofline = {"kernel": "dl2::decode_lattice_kernel<1> (fused lattice decode: trilinear gather + ReLU + Linear2 (BN1 folded) on "
+                          "tcgen05 + BN2 + Linear3 + BN3 for B x 128^3 queries in one launch, pair tiles)",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": (achieved / peaks["bf16_tflops_sustained"]) if achieved else None, "traffic": None,
+                "frac": (achieved / peaks["bf16_tflops_sustained"]) if achieved else None, "traffic": traffic,
+                "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
+                "algorithmic_bytes_per_launch": B * (32 ** 3 * 256 * 4 + pr["volume_size"] ** 3 * 4),
                 "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
                 "launches_timed": n_k, "avg_launch_ms": ms_k / max(n_k, 1), "share_of_step": ms_k / total_ms,
                 "executed_tensor_frac": (3 * achieved / peaks["bf16_tflops_sustained"]) if achieved else None,
@@ -349,7 +374,8 @@ def run_ours(args, rank, world):
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
-            "gpu_launches": launches, "clocks": clocks, "wall_s": round(wall, 3), "stages_ms": stages_ms}
+            "gpu_launches": launches, "clocks": clocks, "wall_s": round(wall, 3), "stages_ms": stages_ms,
+            "unet3d": _unet_report(stages_ms.get("unet3d"), B, peaks)}
     print(json.dumps(line), flush=True)
 
 

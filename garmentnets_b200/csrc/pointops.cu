@@ -28,6 +28,15 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
     return v;
 }
 
+// Same result as warp_max_u64 (every lane gets the maximum key) in two hardware warp reductions (REDUX) instead of five
+// 64-bit shuffle rounds: max of the distance bits, then max of the inverted index among the lanes that hold that distance.
+__device__ __forceinline__ unsigned long long warp_argmax_key(unsigned long long v) {
+    const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+
 template <int T, int PPT>
 __global__ void __launch_bounds__(T, 1)
 fps_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, const int64_t* __restrict__ start,
@@ -96,11 +105,11 @@ fps_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, const
                 best = key > best ? key : best;
             }
         }
-        best = warp_max_u64(best);
+        best = warp_argmax_key(best);
         if (lane == 0) wbest[s & 1][warp] = best;
         __syncthreads();
         unsigned long long k2 = lane < NW ? wbest[s & 1][lane] : 0ull;
-        k2 = warp_max_u64(k2);
+        k2 = warp_argmax_key(k2);
         cur = (int)(0xFFFFFFFFu - (unsigned)(k2 & 0xFFFFFFFFull));
         if (tid == 0) out[o0 + s] = p0 + cur;
     }
