@@ -68,7 +68,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
     auto d_empty = [&](int s) { return bar0 + 8 * (2 * LT_MAX_A + 2 * LT_MAX_B + 2 + s); };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < LT_MAX_A; ++s) { mbar_init(a_full(s), 256); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < LT_MAX_A; ++s) { mbar_init(a_full(s), 128); mbar_init(a_empty(s), 1); }
         for (int s = 0; s < LT_MAX_B; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 32 * LT_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -91,10 +91,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
 
     if (warp < 8) {
         // =========================== A producers ===========================
+        // Two groups of four warps take alternate stages (group g: stages with st % 2 == g; warp w of the group: rows
+        // 32w..32w+31), so the global loads of two stages are in flight at the same time.
+        const int grp = warp >> 2, wq = warp & 3;
         uint32_t st = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int64_t r0 = (tile / p.n_blocks) * LT_M + warp * 16;
+            const int64_t r0 = (tile / p.n_blocks) * LT_M + wq * 32;
             for (int c = 0; c < p.nchunk; ++c, ++st) {
+                if ((int)(st & 1) != grp) continue;
                 const int slot = st % p.na;
                 mbar_wait(a_empty(slot), ((st / p.na) & 1) ^ 1);
                 uint8_t* ah = smem + slot * LT_A_STAGE;
@@ -103,7 +107,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
                 const bool has0 = k0 < p.K, has1 = k1 < p.K;
                 const bool any1 = c * LT_KC + 32 < p.K;   // warp-uniform: the upper 32 channels of this chunk exist
 #pragma unroll
-                for (int rb = 0; rb < 2; ++rb) {
+                for (int rb = 0; rb < 4; ++rb) {
                     float v0[8], v1[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -114,7 +118,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int row = warp * 16 + rb * 8 + j;
+                        const int row = wq * 32 + rb * 8 + j;
                         const float x0 = fminf(fmaxf(v0[j], -65504.f), 65504.f);
                         const float x1 = fminf(fmaxf(v1[j], -65504.f), 65504.f);
                         const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);

@@ -262,6 +262,15 @@ __device__ __forceinline__ unsigned owned_mask(int z, int y, int x) {
 struct CellPos { int z, y, x; };
 __device__ __forceinline__ CellPos cell_pos(int64_t c, int H, int W) {
     CellPos p;
+    if (c < (1ll << 31)) {   // 32-bit divisions (a 128^3 volume has 2 M cells); the 64-bit ones are emulated and ~5x slower
+        const unsigned cu = (unsigned)c, wx = (unsigned)(W - 1), hy = (unsigned)(H - 1);
+        const unsigned row = cu / wx;
+        p.x = (int)(cu - row * wx);
+        const unsigned z = row / hy;
+        p.y = (int)(row - z * hy);
+        p.z = (int)z;
+        return p;
+    }
     p.x = (int)(c % (W - 1));
     p.y = (int)((c / (W - 1)) % (H - 1));
     p.z = (int)(c / ((int64_t)(W - 1) * (H - 1)));
@@ -313,7 +322,7 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
             val[i] = v[((int64_t)(p.z + c_corner_dz[i]) * H + (p.y + c_corner_dy[i])) * W + (p.x + c_corner_dx[i])];
             lo = fminf(lo, val[i]);
             hi = fmaxf(hi, val[i]);
-            if ((double)val[i] - (double)level > 0.0) idx |= 1 << i;
+            if (val[i] > level) idx |= 1 << i;   // == ((double)v - (double)level > 0): both operands are exact in double
         }
         unsigned fb = 0;
         const unsigned am = d_mc_ambig[idx];
