@@ -292,30 +292,56 @@ pointconv_gather_kernel(const float* __restrict__ xf, int64_t ldx, int Cin, cons
                         const float* __restrict__ pos_y, const int64_t* __restrict__ nbr,
                         const int32_t* __restrict__ cnt, const int64_t* __restrict__ eoffs, int64_t sumM, int K,
                         float* __restrict__ edge, int64_t lde) {
-    const int lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // One warp per centroid.  The edge list (ball-query hits minus j == i, plus the self loop appended last) is compacted
+    // with ballots, 32 candidate slots per round, so the index loads are coalesced and independent; narrow rows
+    // (Cin <= 8, SA1) are then written one edge per lane, wide rows (SA2) are copied one row per warp iteration, four
+    // rows in flight.
+    __shared__ int64_t jlist[8][72];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     if (i >= sumM) return;
     const int c = cnt[i];
     const int64_t e0 = eoffs[i];
     const int ne = (int)(eoffs[i + 1] - e0);
     const float cx = pos_y[i * 3], cy = pos_y[i * 3 + 1], cz = pos_y[i * 3 + 2];
-    int w = 0;  // write cursor (edges with j == i are skipped and appended once at the end)
-    for (int t = 0; t <= c; ++t) {
-        int64_t j;
-        if (t < c) {
-            j = nbr[i * K + t];
-            if (j == i) continue;
-        } else {
-            j = i;  // the self loop added by PointConv (flat point index i, see header)
+    const bool narrow = Cin <= 8;
+    int base_w = 0;
+    for (int t0 = 0; t0 <= c; t0 += 32) {
+        const int t = t0 + lane;
+        int64_t j = i;                       // t == c: the self loop added by PointConv (flat point index i, see header)
+        if (t < c) j = nbr[i * K + t];
+        const bool keep = t <= c && !(t < c && j == i);
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        const int w = base_w + __popc(mask & ((1u << lane) - 1u));
+        if (keep && w < ne) {
+            if (narrow) {
+                float* dst = edge + (e0 + w) * lde;
+                for (int ch = 0; ch < Cin; ++ch) dst[ch] = xf[j * ldx + ch];
+                dst[Cin + 0] = __fsub_rn(pos_x[j * 3 + 0], cx);
+                dst[Cin + 1] = __fsub_rn(pos_x[j * 3 + 1], cy);
+                dst[Cin + 2] = __fsub_rn(pos_x[j * 3 + 2], cz);
+            } else if (w < 72) {
+                jlist[wib][w] = j;
+            }
         }
-        if (w >= ne) break;
-        float* dst = edge + (e0 + w) * lde;
-        for (int ch = lane; ch < Cin; ch += 32) dst[ch] = xf[j * ldx + ch];
-        if (lane < 3) {
-            const float pc = lane == 0 ? cx : (lane == 1 ? cy : cz);
-            dst[Cin + lane] = __fsub_rn(pos_x[j * 3 + lane], pc);
+        base_w += __popc(mask);
+    }
+    if (narrow) return;
+    __syncwarp();
+    const int n = ne < base_w ? ne : base_w;
+    for (int w0 = 0; w0 < n; w0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int w = w0 + u;
+            if (w >= n) break;
+            const int64_t j = jlist[wib][w];
+            float* dst = edge + (e0 + w) * lde;
+            for (int ch = lane; ch < Cin; ch += 32) dst[ch] = __ldg(xf + j * ldx + ch);
+            if (lane < 3) {
+                const float pc = lane == 0 ? cx : (lane == 1 ? cy : cz);
+                dst[Cin + lane] = __fsub_rn(__ldg(pos_x + j * 3 + lane), pc);
+            }
         }
-        ++w;
     }
 }
 
@@ -464,6 +490,7 @@ int32_t gnb_pointconv_gather(const float* x_feat, int64_t ldx, int32_t Cin, cons
     GNB_REQUIRE(pos_x && pos_y && nbr && cnt && eoffs && edge, "gnb_pointconv_gather: null pointer");
     GNB_REQUIRE(Cin == 0 || x_feat, "gnb_pointconv_gather: null features");
     GNB_REQUIRE(lde >= Cin + 3, "gnb_pointconv_gather: lde too small");
+    GNB_REQUIRE(K >= 1 && (K <= 71 || Cin <= 8), "gnb_pointconv_gather: at most 71 neighbours per centroid for feature rows wider than 8 (got K=%d)", K);
     if (sumM == 0) return GNB_OK;
     pointconv_gather_kernel<<<(unsigned)ceil_div<int64_t>(sumM, 8), 256, 0, as_stream(stream)>>>(
         x_feat, ldx, Cin, pos_x, pos_y, nbr, cnt, eoffs, sumM, K, edge, lde);

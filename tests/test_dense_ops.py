@@ -75,7 +75,9 @@ def test_scatter_reduce(dev, reduce, channels_last):
     if reduce in ("max", "min"):
         assert np.array_equal(got.cpu().numpy(), ref)  # bit-exact, order independent
     else:
-        assert np.abs(got.cpu().numpy() - ref).max() < 1e-4
+        # atomic accumulation order is nondeterministic: slot 11 sums ~600 values, so the fp32 rounding error scales with
+        # the magnitude of the sums (same max(1, max|ref|) convention as the model-level tests)
+        assert np.abs(got.cpu().numpy() - ref).max() < 1e-4 * max(1.0, float(np.abs(ref).max()))
     assert np.all(got.cpu().numpy()[:, np.setdiff1d(np.arange(S), index)] == 0)
 
 

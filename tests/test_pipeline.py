@@ -220,3 +220,36 @@ def test_host_predictor_matches_device_predict(setup):
                 assert got[k].dtype == want[k].dtype and np.array_equal(got[k], want[k]), k
         assert np.array_equal(hp.point_outputs(t)["pred_nocs"], nocs_ref)
         assert t["d2h_bytes"] == sum(v.nbytes for r in ref for v in r.values()) + 2 * nocs_ref.nbytes
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("category", synthetic.CATEGORIES)
+def test_pointnet2_stage_six_categories_ragged(setup, category):
+    """BASELINE.json configs[4] (six-category sweep) as a parity case: the category generators only change the
+    neighbour-count statistics (ball-query truncation rate).  Ragged batch (two clouds of different size): FPS and
+    ball-query indices bit-exact against the oracle, features / logits within tolerance."""
+    from garmentnets_b200.components.pointnet2 import CloudIndex
+    from garmentnets_b200.pipeline import Batch
+    s = setup
+    dev, hp = s["dev"], s["hp"]
+    cat_id = synthetic.CATEGORIES.index(category)
+    sizes = [900 + 17 * cat_id, 640]
+    clouds = [synthetic.make_cloud(category, n, 40 + i) for i, n in enumerate(sizes)]
+    pos = np.concatenate([c[0] for c in clouds]).astype(np.float32)
+    rgb = np.concatenate([c[1] for c in clouds]).astype(np.float32)
+    batch = np.repeat(np.arange(2), sizes).astype(np.int64)
+    starts = (np.array([3, 11]), np.array([0, 5]))
+    s1 = OP.stage1(s["sd"], hp, rgb, pos, batch, 2, starts)
+    data = Batch(x=torch.from_numpy(rgb).to(dev), pos=torch.from_numpy(pos).to(dev), batch=torch.from_numpy(batch).to(dev))
+    index = CloudIndex.from_batch(data.batch)
+    st = tuple(torch.from_numpy(a.astype(np.int64)).to(dev) for a in starts)
+    res = s["model"].pointnet2_forward(data, index=index, fps_starts=st, return_aux=True)
+    for name in ("sa1", "sa2"):
+        _, _, aux = res["aux"][name]
+        ref_aux = s1[name][3]
+        assert np.array_equal(aux["idx"].cpu().numpy(), ref_aux["idx"]), name
+        assert np.array_equal(aux["cnt"].cpu().numpy(), ref_aux["cnt"]), name
+        assert np.array_equal(aux["nbr"].cpu().numpy(), ref_aux["nbr"]), name
+        assert close(res["aux"][name][0].cpu().numpy(), s1[name][0]), name
+    assert close(res["per_point_features"].cpu().numpy(), s1["per_point_features"])
+    assert close(res["per_point_logits"].cpu().numpy(), s1["per_point_logits"])
