@@ -49,6 +49,11 @@ struct Smem {
 };
 static_assert(Smem::total + 1024 <= 227 * 1024, "shared memory budget");
 
+// Epilogue constants (b2s[256] | w3s[COUT][256]) live in constant memory: the epilogue warps consume them as immediate
+// c[bank][offset] operands of FADD / FFMA -- no load instructions, no L1 traffic competing with the producers' gathers.
+// Filled per launch by a stream-ordered device-to-device copy from the prep kernel's scratch (one stream at a time).
+__constant__ float c_epi[4 * 256];
+
 struct Params {
     const float* U;            // [B,G,G,G,256] hoisted grid (Linear1 applied on the feature grid), fp32 channels-last
     int B, G, Q;
@@ -365,36 +370,29 @@ decode_lattice_kernel(const Params p) {
             for (int t = 0; t < 2; ++t) {
                 mbar_wait_sleep(d_full(t), it & 1);
                 tc_fence_after();
-                float2 dot[COUT][2];
-#pragma unroll
-                for (int o = 0; o < COUT; ++o) dot[o][0] = dot[o][1] = make_float2(0.f, 0.f);
                 const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(t * N);
-                const int ncol = (p.dbg & 4) ? 64 : N;
-                // software pipeline: the next 32 columns are in flight (tcgen05.ld) while the current 32 are folded
+                // software pipeline: the next 32 columns are in flight (tcgen05.ld) while the current 32 are folded.  The
+                // column loop is fully unrolled so that every b2s / w3s value is an immediate constant-bank operand.
                 uint32_t r0[32], r1[32];
-                auto fold = [&](const uint32_t (&r)[32], int n0) {
+                float dsum[COUT][4];
 #pragma unroll
-                    for (int u = 0; u < 32; u += 4) {
-                        const float4 bb = ldg_keep(p.b2s + n0 + u);
-                        float2 v0 = add2(make_float2(__uint_as_float(r[u]), __uint_as_float(r[u + 1])), make_float2(bb.x, bb.y));
-                        float2 v1 = add2(make_float2(__uint_as_float(r[u + 2]), __uint_as_float(r[u + 3])), make_float2(bb.z, bb.w));
-                        v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f);
+                for (int o = 0; o < COUT; ++o)
 #pragma unroll
-                        for (int o = 0; o < COUT; ++o) {
-                            const float4 ww = ldg_keep(p.w3s + o * N + n0 + u);
-                            dot[o][0] = fma2(v0, make_float2(ww.x, ww.y), dot[o][0]);
-                            dot[o][1] = fma2(v1, make_float2(ww.z, ww.w), dot[o][1]);
-                        }
-                    }
-                };
+                    for (int q4 = 0; q4 < 4; ++q4) dsum[o][q4] = 0.f;
                 tmem_ld32(taddr, r0);
-#pragma unroll 1
-                for (int n0 = 0; n0 < ncol; n0 += 64) {
+#pragma unroll
+                for (int n0 = 0; n0 < N; n0 += 64) {
+                    if ((p.dbg & 4) && n0 >= 64) break;
                     tmem_ld_wait();
                     tmem_ld32(taddr + n0 + 32, r1);
-                    fold(r0, n0);
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) {
+                        const float v = fmaxf(__uint_as_float(r0[u]) + c_epi[n0 + u], 0.f);
+#pragma unroll
+                        for (int o = 0; o < COUT; ++o) dsum[o][u & 3] = fmaf(v, c_epi[(1 + o) * N + n0 + u], dsum[o][u & 3]);
+                    }
                     tmem_ld_wait();
-                    if (n0 + 64 < ncol) {
+                    if (n0 + 64 < N && !((p.dbg & 4) && n0 + 64 >= 64)) {
                         tmem_ld32(taddr + n0 + 64, r0);
                     } else {
                         // every TMEM read of accumulator t has completed: the next pair's MMAs may overwrite it
@@ -402,7 +400,18 @@ decode_lattice_kernel(const Params p) {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(d_empty(t));
                     }
-                    fold(r1, n0 + 32);
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) {
+                        const float v = fmaxf(__uint_as_float(r1[u]) + c_epi[n0 + 32 + u], 0.f);
+#pragma unroll
+                        for (int o = 0; o < COUT; ++o) dsum[o][u & 3] = fmaf(v, c_epi[(1 + o) * N + n0 + 32 + u], dsum[o][u & 3]);
+                    }
+                }
+                float2 dot[COUT][2];
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) {
+                    dot[o][0] = make_float2(dsum[o][0], dsum[o][1]);
+                    dot[o][1] = make_float2(dsum[o][2], dsum[o][3]);
                 }
                 const int64_t grow = (plane * Q + pairs[2 * jp + t]) * M + row;
 #pragma unroll
@@ -564,6 +573,8 @@ int32_t gnb_decode_lattice(const float* U, int32_t B, int32_t G, int32_t Q, cons
     float* tail = scratch + 4 * dl2::N;   // [3][4]
     dl2::lattice_prep_kernel<<<1 + Cout, dl2::N, 0, st>>>(W2, b2, bn1_shift, W3, b3, bn2_scale, bn2_shift, bn3_scale, bn3_shift,
                                                          Cout, ldexpf(1.0f, w2f_scale_log2), b2s, w3s, tail);
+    // b2s (256 floats) and w3s (Cout x 256) are contiguous in the scratch: one stream-ordered copy into constant memory
+    GNB_CUDA(cudaMemcpyToSymbolAsync(dl2::c_epi, b2s, sizeof(float) * dl2::N * (1 + Cout), 0, cudaMemcpyDeviceToDevice, st));
     dl2::Params p;
     p.U = U; p.B = B; p.G = G; p.Q = Q;
     p.w2_packed = reinterpret_cast<const uint8_t*>(w2f_packed);
