@@ -34,6 +34,11 @@ constexpr int LT_EPI_WARPS = 8;                  // two per TMEM lane quarter, a
 constexpr int LT_STAGE_BYTES = 32 * 32 * 4;      // 4 KB per epilogue warp: one 32-row x 32-column fp32 box staged for a TMA store
 constexpr int LT_SMEM_BUDGET = 225 * 1024 - LT_EPI_WARPS * LT_STAGE_BYTES;  // dynamic shared memory available to the A / W rings
 
+// Per-column epilogue parameters (bias | bn_scale | bn_shift, padded) in constant memory: read as uniform constant-bank
+// operands instead of 24 global loads per 32-column group (filled per launch, stream-ordered device-to-device copy).
+constexpr int LT_MAX_COLS = 1024;
+__constant__ float c_lt[3 * LT_MAX_COLS];
+
 struct LtParams {
     const float* X;
     int64_t R, ldx;
@@ -48,6 +53,7 @@ struct LtParams {
     int64_t m_tiles;
     int vec_store;             // Y rows are 16-byte aligned: float4 stores
     int use_tma;               // Y rows are 16-byte aligned: full tiles leave through TMA stores of 128 x 32 boxes
+    int use_const;             // cparams fit in c_lt (n_blocks * Npad <= LT_MAX_COLS)
     int split;                 // Npad <= 128: the lo*hi + hi*lo cross terms accumulate in their own TMEM columns (+Npad)
 };
 
@@ -177,11 +183,19 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
                     __syncwarp();
                 }
                 if (tma_tile || grow < R) {
+                    const int cidx = nb * p.Npad + n0;
 #pragma unroll
                     for (int t = 0; t < 32; t += 4) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(cb + n0 + t));
-                        const float4 sc = __ldg(reinterpret_cast<const float4*>(cb + ntot + n0 + t));
-                        const float4 sh = __ldg(reinterpret_cast<const float4*>(cb + 2 * ntot + n0 + t));
+                        float4 bb, sc, sh;
+                        if (p.use_const) {
+                            bb = make_float4(c_lt[cidx + t], c_lt[cidx + t + 1], c_lt[cidx + t + 2], c_lt[cidx + t + 3]);
+                            sc = make_float4(c_lt[ntot + cidx + t], c_lt[ntot + cidx + t + 1], c_lt[ntot + cidx + t + 2], c_lt[ntot + cidx + t + 3]);
+                            sh = make_float4(c_lt[2 * ntot + cidx + t], c_lt[2 * ntot + cidx + t + 1], c_lt[2 * ntot + cidx + t + 2], c_lt[2 * ntot + cidx + t + 3]);
+                        } else {
+                            bb = __ldg(reinterpret_cast<const float4*>(cb + n0 + t));
+                            sc = __ldg(reinterpret_cast<const float4*>(cb + ntot + n0 + t));
+                            sh = __ldg(reinterpret_cast<const float4*>(cb + 2 * ntot + n0 + t));
+                        }
                         float4 o;
                         o.x = fmaf(__uint_as_float(r[t]), p.acc_scale, bb.x);
                         o.y = fmaf(__uint_as_float(r[t + 1]), p.acc_scale, bb.y);
@@ -429,6 +443,9 @@ int32_t gnb_linear_tc(const float* X, int64_t R, int32_t K, int64_t ldx, const v
         if (r != CUDA_SUCCESS) { set_error("gnb_linear_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return GNB_ERR_CUDA; }
         p.use_tma = 1;
     }
+    p.use_const = l.n_blocks * l.Npad <= LT_MAX_COLS ? 1 : 0;
+    if (p.use_const)
+        GNB_CUDA(cudaMemcpyToSymbolAsync(c_lt, cparams, sizeof(float) * 3 * l.n_blocks * l.Npad, 0, cudaMemcpyDeviceToDevice, as_stream(stream)));
     const int smem = p.na * LT_A_STAGE + p.nb * l.piece_bytes + LT_EPI_WARPS * LT_STAGE_BYTES + 1024;
     GNB_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int64_t tiles = p.m_tiles * l.n_blocks;
