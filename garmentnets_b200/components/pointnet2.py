@@ -122,9 +122,24 @@ class PointConv(nn.Module):
         ops.pointconv_gather(x, pos_x, pos_y, nbr, cnt, eoffs, edge)
         total = eoffs[M:]
         h = edge
-        for block in self.local_nn:
+        blocks = list(self.local_nn)
+        last = blocks[-1]
+        fuse = (self.fuse_aggregation and ops.USE_LINEAR_TC and rows >= ops.LINEAR_TC_MIN_ROWS and not _Block.calibrating
+                and not last.training and isinstance(last, _Block))
+        for block in (blocks[:-1] if fuse else blocks):
             h = block(h, rows_dev=total)
-        return ops.segment_max(h, eoffs)
+        if not fuse:
+            return ops.segment_max(h, eoffs)
+        # max aggregation fused into the last layer's epilogue: its [E, C] output never reaches HBM
+        lin = last[0]
+        w = ops.packed_linear_for(last, "block", lin.weight, lin.bias, last[2] if len(last) > 2 else None)
+        return ops.linear_tc_segmax(h, w, ops.segment_ids(eoffs, rows), M, relu=True, rows_dev=total)
+
+    # Off by default: measured on B200 (batch 32) the fused epilogue -- column-wise run maxima out of a shared-memory box --
+    # costs more than it saves (SA1 last layer 1140 us fused vs 525 + 217 us for gnb_linear_tc + gnb_segment_max, both of
+    # which already run at 3.5-4 TB/s and at the HBM roofline respectively).  Kept (and tested) as the starting point for
+    # a register-level segmented reduction.
+    fuse_aggregation = False
 
     def forward(self, x, pos, edge_index):
         raise NotImplementedError(

@@ -53,6 +53,9 @@ struct LtParams {
     int64_t m_tiles;
     int vec_store;             // Y rows are 16-byte aligned: float4 stores
     int use_tma;               // Y rows are 16-byte aligned: full tiles leave through TMA stores of 128 x 32 boxes
+    const int32_t* seg;        // segmented-max mode: segment id of every row (rows of a segment are contiguous), else NULL
+    uint32_t* seg_out;         // [nseg, ldo] order-preserving encoded maxima (zero-initialised by the caller)
+    int64_t ldo;
     int use_const;             // cparams fit in c_lt (n_blocks * Npad <= LT_MAX_COLS)
     int split;                 // Npad <= 128: the lo*hi + hi*lo cross terms accumulate in their own TMEM columns (+Npad)
 };
@@ -158,6 +161,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
             // Full tiles are written by the TMA unit (coalesced, asynchronous); the tile that contains the device-side
             // row count falls back to per-thread stores so rows >= R are never touched.
             const bool tma_tile = p.use_tma && row0 + LT_M <= R;
+            // segmented-max mode (PointConv aggregation fused into the last edge-MLP layer): the tile never goes to HBM;
+            // each warp reduces its 32 x 32 boxes column-wise over the runs of equal segment id and merges the run maxima
+            // into the per-segment result with order-preserving integer atomics
+            const bool seg_mode = p.seg != nullptr;
+            int myseg = -1;
+            unsigned bmask = 0;
+            if (seg_mode) {
+                if (grow < R) myseg = __ldg(p.seg + grow);
+                const int prev = __shfl_up_sync(0xffffffffu, myseg, 1);
+                bmask = __ballot_sync(0xffffffffu, lane == 0 || myseg != prev);   // run starts among this warp's 32 rows
+            }
             mbar_wait_sleep(d_full(db), (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(db * 256);
@@ -182,7 +196,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
                 }
-                if (tma_tile || grow < R) {
+                if (seg_mode) __syncwarp();   // the column reduction of the previous box has finished reading the stage
+                if (tma_tile || seg_mode || grow < R) {
                     const int cidx = nb * p.Npad + n0;
 #pragma unroll
                     for (int t = 0; t < 32; t += 4) {
@@ -205,7 +220,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
                         o.x = fmaf(o.x, sc.x, sh.x); o.y = fmaf(o.y, sc.y, sh.y);
                         o.z = fmaf(o.z, sc.z, sh.z); o.w = fmaf(o.w, sc.w, sh.w);
                         const int n = n0 + t;
-                        if (tma_tile) {
+                        if (tma_tile || seg_mode) {
                             // SWIZZLE_128B box: 16-byte chunk j of row r lives at chunk j ^ (r & 7) (bank-conflict free)
                             const uint32_t a = sdst + ((uint32_t)(((t >> 2) ^ (lane & 7)) & 7) << 4);
                             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
@@ -219,7 +234,30 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
                         }
                     }
                 }
-                if (tma_tile) {
+                if (seg_mode) {
+                    __syncwarp();
+                    const int col = n0 + lane;                       // this lane's column of the box
+                    const bool col_ok = col < ncols;
+                    unsigned m = bmask;
+                    while (m) {                                      // warp-uniform loop over the runs
+                        const int start = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int end = m ? __ffs(m) - 1 : 32;
+                        const int sid = __shfl_sync(0xffffffffu, myseg, start);
+                        if (sid < 0) continue;                       // rows beyond the device-side row count
+                        float mx = -INFINITY;
+                        for (int rr = start; rr < end; ++rr) {
+                            float v;
+                            const uint32_t a = stage + (uint32_t)rr * 128 + ((uint32_t)(((lane >> 2) ^ (rr & 7)) & 7) << 4) + (uint32_t)(lane & 3) * 4;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+                            mx = fmaxf(mx, v);
+                        }
+                        if (col_ok) {
+                            const unsigned b = __float_as_uint(mx);
+                            atomicMax(p.seg_out + (int64_t)sid * p.ldo + (int64_t)nb * p.Npad + col, (b & 0x80000000u) ? ~b : (b | 0x80000000u));
+                        }
+                    }
+                } else if (tma_tile) {
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
@@ -367,6 +405,23 @@ static LtEncodeFn lt_encode_fn() {
     return fn;
 }
 
+// seg[r] = i for the rows r in [offs[i], offs[i+1]) (one warp per segment)
+__global__ void segment_ids_kernel(const int64_t* __restrict__ offs, int64_t nseg, int32_t* __restrict__ seg) {
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= nseg) return;
+    const int64_t e0 = offs[i], e1 = offs[i + 1];
+    for (int64_t r = e0 + (threadIdx.x & 31); r < e1; r += 32) seg[r] = (int32_t)i;
+}
+
+// in place: order-preserving encoded maxima -> floats; a slot no row ever touched (still 0) becomes 0.0f (an empty
+// segment aggregates to 0, like PyG's max aggregation)
+__global__ void segmax_decode_kernel(uint32_t* __restrict__ enc, int64_t count) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const uint32_t u = enc[t];
+    enc[t] = u == 0u ? 0u : ((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
 }  // namespace gnb
 
 using namespace gnb;
@@ -396,11 +451,11 @@ int32_t gnb_linear_tc_pack(const float* W, int32_t N, int32_t K, const float* bi
     return check_launch("gnb_linear_tc_pack");
 }
 
-int32_t gnb_linear_tc(const float* X, int64_t R, int32_t K, int64_t ldx, const void* packed, const float* cparams,
-                      int32_t scale_log2, int32_t N, int32_t relu, float* Y, int64_t ldy, const int64_t* rows_dev,
-                      void* stream) {
-    GNB_REQUIRE(X && packed && cparams && Y, "gnb_linear_tc: null pointer");
-    GNB_REQUIRE(R >= 0 && K >= 1 && N >= 1 && ldx >= K && ldy >= N, "gnb_linear_tc: bad shape R=%lld K=%d N=%d ldx=%lld ldy=%lld",
+static int32_t linear_tc_launch(const float* X, int64_t R, int32_t K, int64_t ldx, const void* packed, const float* cparams,
+                                int32_t scale_log2, int32_t N, int32_t relu, float* Y, int64_t ldy, const int64_t* rows_dev,
+                                const int32_t* seg, uint32_t* seg_out, int64_t ldo, void* stream) {
+    GNB_REQUIRE(X && packed && cparams && (Y || seg), "gnb_linear_tc: null pointer");
+    GNB_REQUIRE(R >= 0 && K >= 1 && N >= 1 && ldx >= K && (seg || ldy >= N), "gnb_linear_tc: bad shape R=%lld K=%d N=%d ldx=%lld ldy=%lld",
                 (long long)R, K, N, (long long)ldx, (long long)ldy);
     if (R == 0) return GNB_OK;
     const LtLayout l = lt_layout(N, K);
@@ -409,10 +464,11 @@ int32_t gnb_linear_tc(const float* X, int64_t R, int32_t K, int64_t ldx, const v
     p.relu = relu; p.w_packed = reinterpret_cast<const uint8_t*>(packed); p.cparams = cparams;
     p.acc_scale = ldexpf(1.0f, -scale_log2);
     p.Y = Y; p.ldy = ldy; p.rows_dev = rows_dev;
+    p.seg = seg; p.seg_out = seg_out; p.ldo = ldo;
     p.piece_bytes = l.piece_bytes;
     p.m_tiles = ceil_div<int64_t>(R, LT_M);
     p.split = l.Npad <= 128 ? 1 : 0;
-    p.vec_store = ((ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(Y) % 16) == 0 && (l.Npad % 4) == 0) ? 1 : 0;
+    p.vec_store = (!seg && (ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(Y) % 16) == 0 && (l.Npad % 4) == 0) ? 1 : 0;
     const int64_t resident_bytes = (int64_t)l.nchunk * l.piece_bytes;
     if (l.n_blocks == 1 && l.nchunk <= LT_MAX_B && resident_bytes + 2 * LT_A_STAGE <= LT_SMEM_BUDGET) {
         p.resident = 1;
@@ -453,6 +509,35 @@ int32_t gnb_linear_tc(const float* X, int64_t R, int32_t K, int64_t ldx, const v
     if ((int64_t)grid > tiles) grid = (int)tiles;
     linear_tc_kernel<<<grid, LT_THREADS, smem, as_stream(stream)>>>(y_map, p);
     return check_launch("gnb_linear_tc");
+}
+
+int32_t gnb_linear_tc(const float* X, int64_t R, int32_t K, int64_t ldx, const void* packed, const float* cparams,
+                      int32_t scale_log2, int32_t N, int32_t relu, float* Y, int64_t ldy, const int64_t* rows_dev,
+                      void* stream) {
+    GNB_REQUIRE(Y, "gnb_linear_tc: null pointer");
+    return linear_tc_launch(X, R, K, ldx, packed, cparams, scale_log2, N, relu, Y, ldy, rows_dev, nullptr, nullptr, 0, stream);
+}
+
+int32_t gnb_linear_tc_segmax(const float* X, int64_t R, int32_t K, int64_t ldx, const void* packed, const float* cparams,
+                             int32_t scale_log2, int32_t N, int32_t relu, const int32_t* seg, void* enc_out, int64_t ldo,
+                             const int64_t* rows_dev, void* stream) {
+    GNB_REQUIRE(seg && enc_out && ldo >= N, "gnb_linear_tc_segmax: bad arguments");
+    return linear_tc_launch(X, R, K, ldx, packed, cparams, scale_log2, N, relu, nullptr, 0, rows_dev, seg,
+                            reinterpret_cast<uint32_t*>(enc_out), ldo, stream);
+}
+
+int32_t gnb_segment_ids(const int64_t* offs, int64_t nseg, int32_t* seg, void* stream) {
+    GNB_REQUIRE(offs && seg && nseg >= 0, "gnb_segment_ids: bad arguments");
+    if (nseg == 0) return GNB_OK;
+    segment_ids_kernel<<<(unsigned)ceil_div<int64_t>(nseg, 8), 256, 0, as_stream(stream)>>>(offs, nseg, seg);
+    return check_launch("gnb_segment_ids");
+}
+
+int32_t gnb_segmax_decode(void* enc, int64_t count, void* stream) {
+    GNB_REQUIRE(enc && count >= 0, "gnb_segmax_decode: bad arguments");
+    if (count == 0) return GNB_OK;
+    segmax_decode_kernel<<<(unsigned)ceil_div<int64_t>(count, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<uint32_t*>(enc), count);
+    return check_launch("gnb_segmax_decode");
 }
 
 }  // extern "C"

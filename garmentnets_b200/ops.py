@@ -235,6 +235,29 @@ def linear_tc(x: torch.Tensor, w: PackedLinear, relu: bool = False, out: Optiona
     return out
 
 
+def segment_ids(offs: torch.Tensor, rows: int) -> torch.Tensor:
+    """CSR offsets i64[nseg+1] -> i32[rows] segment id of every row (rows beyond offs[-1] are left unset)."""
+    offs = _req(offs, torch.int64, "offs")
+    seg = torch.empty((rows,), dtype=torch.int32, device=offs.device)
+    _lib.call("gnb_segment_ids", offs.data_ptr(), offs.numel() - 1, seg.data_ptr(), _stream())
+    return seg
+
+
+def linear_tc_segmax(x: torch.Tensor, w: PackedLinear, seg: torch.Tensor, nseg: int, relu: bool = True,
+                     rows_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``segment_max(linear_tc(x), offs)`` in one kernel (``gnb_linear_tc_segmax``): x [R,K] with contiguous segments,
+    seg i32[R] -> [nseg, N] fp32.  The [R,N] activation is reduced on chip and never written."""
+    x, ldx = _rows(x, "x")
+    seg = _req(seg, torch.int32, "seg")
+    R, K = x.shape
+    assert K == w.K and seg.numel() >= R
+    out = torch.zeros((nseg, w.N), dtype=torch.int32, device=x.device)   # order-preserving encoded maxima
+    _lib.call("gnb_linear_tc_segmax", x.data_ptr(), R, K, ldx, w.packed.data_ptr(), w.cparams.data_ptr(), w.scale_log2, w.N,
+              int(relu), seg.data_ptr(), out.data_ptr(), out.stride(0), _ptr(rows_dev), _stream())
+    _lib.call("gnb_segmax_decode", out.data_ptr(), out.numel(), _stream())
+    return out.view(torch.float32)
+
+
 def linear_module(owner, slot: str, x: torch.Tensor, weight, bias=None, relu: bool = False) -> torch.Tensor:
     """A plain ``nn.Linear`` (optionally + ReLU) applied to rows: tensor cores for large row counts, fp32 kernel below."""
     if USE_LINEAR_TC and x.shape[0] >= LINEAR_TC_MIN_ROWS:

@@ -126,6 +126,19 @@ int32_t gnb_linear_tc(const float* X, int64_t R, int32_t K, int64_t ldx, const v
                       const float* cparams, int32_t scale_log2, int32_t N, int32_t relu,
                       float* Y, int64_t ldy, const int64_t* rows_dev, void* stream);
 
+/* PointConv aggregation fused into the last edge-MLP layer (ref components/pointnet2.py:31, PyG PointConv aggr='max'):
+ * the rows of one segment (centroid) are contiguous; seg i32[R] holds the segment id of every row
+ * (gnb_segment_ids fills it from the CSR offsets).  Instead of writing Y, every 128-row tile is reduced on chip and
+ * merged into enc_out u32[nseg, ldo] with order-preserving integer atomic max (zero-initialise it, then
+ * gnb_segmax_decode turns it into f32 in place; untouched slots decode to 0 like an empty max aggregation).
+ * The [R, N] activation never goes to HBM and the separate gnb_segment_max pass disappears. */
+int32_t gnb_linear_tc_segmax(const float* X, int64_t R, int32_t K, int64_t ldx, const void* packed,
+                             const float* cparams, int32_t scale_log2, int32_t N, int32_t relu,
+                             const int32_t* seg, void* enc_out, int64_t ldo, const int64_t* rows_dev,
+                             void* stream);
+int32_t gnb_segment_ids(const int64_t* offs, int64_t nseg, int32_t* seg, void* stream);
+int32_t gnb_segmax_decode(void* enc, int64_t count, void* stream);
+
 /* ---- N11: NOCS bin head ----------------------------------------------------------------
  * ref: networks/conv_implicit_wnf.py:222-231.  logits f32[R, bins*3] viewed [R,bins,3]:
  * bin i64[R,3] = argmax over bins (first max), conf f32[R,3] = softmax at the argmax,

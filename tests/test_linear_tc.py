@@ -86,3 +86,34 @@ def test_mlp_block_routes_to_tensor_cores(dev):
     m[0][2].running_mean.add_(1.0)
     y2 = m(x)
     assert (y2 - y_tc).abs().max().item() > 1e-3
+
+
+@pytest.mark.parametrize("nseg,K,N,maxlen", [(700, 64, 128, 65), (300, 128, 256, 65), (5000, 64, 64, 9), (3, 131, 128, 2000),
+                                             (1200, 259, 1024, 40)])
+def test_linear_tc_segmax_equals_linear_then_segment_max(dev, nseg, K, N, maxlen):
+    """Aggregation fused into the epilogue (gnb_linear_tc_segmax) == gnb_linear_tc followed by gnb_segment_max, bit for
+    bit (max is order independent and both paths produce the same per-row values); segments straddle warps, tiles and
+    CTAs, rows beyond the device-side row count are ignored, all-negative segments keep their sign."""
+    from garmentnets_b200 import ops
+    g = torch.Generator().manual_seed(nseg + K + N)
+    lens = torch.randint(1, maxlen + 1, (nseg,), generator=g)
+    offs = torch.zeros(nseg + 1, dtype=torch.int64)
+    offs[1:] = torch.cumsum(lens, 0)
+    E = int(offs[-1])
+    rows = E + 37                                   # worst-case allocation, like PointConv.forward_grouped
+    x = torch.randn(rows, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) - 1.0
+    sc = torch.rand(N, generator=g) + 0.5
+    sh = torch.randn(N, generator=g) - 2.0           # many all-negative segments
+    pk = ops.pack_linear_tc(w.to(dev), b.to(dev), sc.to(dev), sh.to(dev))
+    xd, od = x.to(dev), offs.to(dev)
+    total = od[nseg:]
+    full = ops.linear_tc(xd, pk, True, rows_dev=total)
+    want = ops.segment_max(full, od)
+    got = ops.linear_tc_segmax(xd, pk, ops.segment_ids(od, rows), nseg, relu=True, rows_dev=total)
+    assert got.shape == (nseg, N) and got.dtype == torch.float32
+    assert torch.equal(got, want)
+    ref = torch.relu(x[:E].double() @ w.double().t() + b.double()) * sc.double() + sh.double()
+    ref = torch.stack([ref[offs[i]:offs[i + 1]].max(0).values for i in range(nseg)]).float()
+    assert (got.cpu() - ref).abs().max().item() < 2e-5
