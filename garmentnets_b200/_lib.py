@@ -82,7 +82,8 @@ KERNELS_PER_CALL = {"gnb_scatter_reduce": 2, "gnb_gaussian_gradient_magnitude": 
                     "gnb_mc_count": 5, "gnb_mc_emit": 2, "gnb_mc_count_batch": 5, "gnb_mc_emit_batch": 2,
                     "gnb_groupnorm_stats": 2, "gnb_decode_tc": 2, "gnb_decode_tc_query": 2, "gnb_decode_tc_query_fused": 2, "gnb_decode_lattice": 2, "gnb_version": 0, "gnb_last_error": 0, "gnb_device_sm_count": 0,
                     "gnb_mc_workspace_bytes": 0, "gnb_linear_tc_packed_bytes": 0,
-                    "gnb_linear_tc_padded_cols": 0}
+                    "gnb_linear_tc_padded_cols": 0, "gnb_mesh_cleanup_workspace_bytes": 0, "gnb_mesh_cleanup_count": 8,
+                    "gnb_mesh_cleanup_emit": 2, "gnb_linear_tc_segmax": 1}
 launch_count = 0          # kernels launched through this binding since import (monotonic)
 _tag = None               # current profiling tag (see garmentnets_b200.profiling)
 _tag_sink = None          # callable(tag, name) -> context manager, installed by profiling.KernelTimer

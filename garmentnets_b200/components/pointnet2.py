@@ -44,15 +44,32 @@ class CloudIndex:
         ptr = ops.batch_to_ptr(batch)
         return CloudIndex(ptr, ptr.cpu().numpy())
 
+    # Device copies of small host offset arrays, keyed by content.  A pageable host->device copy synchronises the stream
+    # before it starts, so creating the same CSR offsets again on every forward (three times per step: SA1, SA2 and the
+    # global level) drained the launch queue each time; with the cache the steady state issues no such copy.
+    _device_cache: dict = {}
+
+    @staticmethod
+    def _to_device(host: np.ndarray, device) -> torch.Tensor:
+        host = np.ascontiguousarray(host, dtype=np.int64)
+        key = (host.tobytes(), str(device))
+        hit = CloudIndex._device_cache.get(key)
+        if hit is None:
+            if len(CloudIndex._device_cache) >= 512:
+                CloudIndex._device_cache.clear()
+            hit = torch.from_numpy(host.copy()).to(device)
+            CloudIndex._device_cache[key] = hit
+        return hit
+
     @staticmethod
     def uniform(B: int, n: int, device) -> "CloudIndex":
         host = np.arange(B + 1, dtype=np.int64) * n
-        return CloudIndex(torch.from_numpy(host).to(device), host)
+        return CloudIndex(CloudIndex._to_device(host, device), host)
 
     def subsample(self, ratio: float) -> "CloudIndex":
         counts = ops.fps_counts(self.ptr_host, ratio)
         host = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-        return CloudIndex(torch.from_numpy(host).to(self.ptr.device), host)
+        return CloudIndex(CloudIndex._to_device(host, self.ptr.device), host)
 
     def batch_vector(self) -> torch.Tensor:
         counts = torch.from_numpy(np.diff(self.ptr_host)).to(self.ptr.device)

@@ -225,7 +225,7 @@ class ImplicitWNFDecoder(nn.Module):
             r0, r1 = int(qptr_host[b0]), int(qptr_host[b1_])
             if r1 == r0:
                 continue
-            qptr = torch.as_tensor([int(x) - r0 for x in qptr_host[b0:b1_ + 1]], dtype=torch.int64).to(x_ndhwc.device)
+            qptr = self._qptr_to_device([int(x) - r0 for x in qptr_host[b0:b1_ + 1]], x_ndhwc.device)
             with profiling.tag(f"{self.profile_tag}_tc"):
                 ops.decode_tc_query_fused(w1, b1, *self._tc_args_bn1_folded(), X=x_ndhwc[b0:b1_], q=q_all[r0:r1],
                                           qptr=qptr, bn1=None, out=out[r0:r1])
@@ -245,6 +245,19 @@ class ImplicitWNFDecoder(nn.Module):
             cached = (key, ops.pack_f16_split(w2f), b2f)
             self._gnb_w2_bn1_folded = cached
         return (cached[1], cached[2], self.mlp[1][2].folded_affine(), l3.weight, l3.bias, self.mlp[2][2].folded_affine())
+
+    def _qptr_to_device(self, offsets, device) -> torch.Tensor:
+        """Row offsets of the samples -> device, through a small ring of pinned staging buffers and an asynchronous copy
+        (a pageable copy would synchronise the stream and stall the launch queue)."""
+        ring = getattr(self, "_gnb_qptr_ring", None)
+        if ring is None:
+            ring = [[torch.empty(130, dtype=torch.int64, pin_memory=True) for _ in range(8)], 0]
+            self._gnb_qptr_ring = ring
+        buf = ring[0][ring[1] % len(ring[0])]
+        ring[1] += 1
+        n = len(offsets)
+        buf[:n] = torch.as_tensor(offsets, dtype=torch.int64)
+        return buf[:n].to(device, non_blocking=True)
 
     def fused_query_ready(self, x_ndhwc: torch.Tensor) -> bool:
         return (self.use_fused_query and self._tc_ready() and len(self.mlp[0]) > 2 and x_ndhwc.shape[-1] == 32
@@ -339,7 +352,7 @@ class ImplicitWNFDecoder(nn.Module):
             r0, r1 = int(qptr_host[b0]), int(qptr_host[b1])
             if r1 == r0:
                 continue
-            qptr = torch.as_tensor([int(x) - r0 for x in qptr_host[b0:b1 + 1]], dtype=torch.int64).to(u.device)
+            qptr = self._qptr_to_device([int(x) - r0 for x in qptr_host[b0:b1 + 1]], u.device)
             with profiling.tag(f"{self.profile_tag}_tc"):
                 ops.decode_tc_query(*self._tc_args(), U=u[b0:b1], q=q_all[r0:r1], qptr=qptr, bn1=bn.folded_affine(),
                                     out=out[r0:r1])

@@ -331,6 +331,21 @@ int32_t gnb_mc_emit_batch(const float* v, int32_t N, int32_t D, int32_t H, int32
                           int64_t max_active, float* verts, int32_t* faces, float* normals, float* values,
                           float* ggm_at_verts, void* stream);
 
+/* ---- next row: mesh clean-up after marching cubes ----------------------
+ * ref: common/marching_cubes_util.py:19-35 (inside wnf_to_mesh) and :38-52 (delete_invalid_verts); eval.py:532-546.
+ * A face survives iff all three of its vertices are flagged in on_surface u8[V]; vertices no surviving face uses are
+ * deleted and the faces re-indexed (ascending original order, like np.unique).  Batched over the packed output of
+ * gnb_mc_emit_batch: faces i32[F,3] hold per-sample LOCAL vertex ids, vptr / fptr i64[B+1] (device) are the row
+ * offsets of the samples.  Two phases around the one host read of rec i64[2(B+1)] = new vptr | new fptr:
+ * gnb_mesh_cleanup_count (mark, prefix sums) and gnb_mesh_cleanup_emit (keep i64[Vnew] = surviving GLOBAL vertex
+ * rows in ascending order -- gather any per-vertex array with it -- and out_faces i32[Fnew,3] re-indexed, local). */
+int64_t gnb_mesh_cleanup_workspace_bytes(int64_t V, int64_t F);
+int32_t gnb_mesh_cleanup_count(const int32_t* faces, const int64_t* fptr, const int64_t* vptr, int32_t B, int64_t V,
+                               int64_t F, const uint8_t* on_surface, void* workspace, int64_t* rec, void* stream);
+int32_t gnb_mesh_cleanup_emit(const int32_t* faces, const int64_t* fptr, const int64_t* vptr, int32_t B, int64_t V,
+                              int64_t F, void* workspace, const int64_t* rec, int64_t* keep, int32_t* out_faces,
+                              void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -78,3 +78,31 @@ def predict_tail(wnf_volume: np.ndarray, sigma: float = 0.5, level: float = 0.5,
     return {"verts": verts.astype(np.float32), "faces": faces.astype(np.int32), "normals": normals.astype(np.float32),
             "volume_value": values.astype(np.float32), "volume_gradient_magnitude": verts_ggm.astype(np.float32),
             "ggm": ggm}
+
+
+def delete_invalid_verts(mc_verts: np.ndarray, mc_faces: np.ndarray, is_vert_on_surface: np.ndarray):
+    """ref common/marching_cubes_util.py:38-52, restated line for line (``np.bool`` -> ``bool``: the alias was removed from
+    numpy; the reference file cannot be imported here because its module top imports scikit-image)."""
+    is_face_valid = np.ones(len(mc_faces), dtype=bool)
+    for i in range(3):
+        is_face_valid_i = is_vert_on_surface[mc_faces[:, i]]
+        is_face_valid = is_face_valid & is_face_valid_i
+    raw_valid_faces = mc_faces[is_face_valid]
+    raw_valid_vert_idx = np.unique(raw_valid_faces.flatten())
+    valid_verts = mc_verts[raw_valid_vert_idx]
+    valid_vert_idx = np.arange(len(valid_verts))
+    vert_raw_idx_valid_idx_map = np.zeros(len(mc_verts), dtype=mc_faces.dtype)
+    vert_raw_idx_valid_idx_map[raw_valid_vert_idx] = valid_vert_idx
+    valid_faces = vert_raw_idx_valid_idx_map[raw_valid_faces]
+    return valid_verts, valid_faces
+
+
+def wnf_to_mesh(wnf_volume: np.ndarray, iso_surface_level=0.5, gradient_threshold=0.25, sigma=0.5):
+    """ref common/marching_cubes_util.py:5-35 on the oracle's marching cubes (sigma is ignored there too, :7-8)."""
+    volume_size = wnf_volume.shape[-1]
+    wnf_ggm = gaussian_gradient_magnitude(wnf_volume, 0.5)
+    voxel_spacing = 1 / (volume_size - 1)
+    mc_verts, mc_faces, _, _ = marching_cubes(wnf_volume, iso_surface_level, (voxel_spacing,) * 3, "ascent")
+    idx = (mc_verts / voxel_spacing).astype(np.uint32)
+    mc_verts_ggm = wnf_ggm[idx[:, 0], idx[:, 1], idx[:, 2]]
+    return delete_invalid_verts(mc_verts, mc_faces, mc_verts_ggm > gradient_threshold)
