@@ -72,3 +72,28 @@ def test_wnf_to_mesh_matches_oracle(dev):
     assert 100 < len(f_ref) < 10000   # the steep inner sheet survives, the weak outer sheets are removed (20180 raw faces)
     assert np.array_equal(f.cpu().numpy(), f_ref)
     assert np.array_equal(v.cpu().numpy(), v_ref.astype(np.float32))
+
+
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mesh_cleanup.npz"))
+
+
+def test_oracle_pinned_to_reference_function():
+    """tests/golden/mesh_cleanup.npz was produced by the reference's own delete_invalid_verts
+    (oracle/make_golden_mesh_cleanup.py executes its unmodified source): the restatement must reproduce it bit for bit."""
+    g = _golden()
+    for i in range(int(g["cases"])):
+        v, f = postproc.delete_invalid_verts(g[f"verts{i}"], g[f"faces{i}"], g[f"on{i}"])
+        assert np.array_equal(v, g[f"valid_verts{i}"]) and np.array_equal(np.asarray(f).reshape(-1, 3), g[f"valid_faces{i}"])
+
+
+@pytest.mark.gpu
+def test_cuda_against_reference_golden(dev):
+    from garmentnets_b200.common.marching_cubes_util import delete_invalid_verts
+    g = _golden()
+    for i in range(int(g["cases"])):
+        v, f = delete_invalid_verts(torch.from_numpy(g[f"verts{i}"]).to(dev), torch.from_numpy(g[f"faces{i}"]).to(dev),
+                                    torch.from_numpy(g[f"on{i}"]).to(dev))
+        assert np.array_equal(v.cpu().numpy(), g[f"valid_verts{i}"])
+        assert np.array_equal(f.cpu().numpy().reshape(-1, 3), g[f"valid_faces{i}"])
