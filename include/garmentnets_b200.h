@@ -346,6 +346,17 @@ int32_t gnb_mesh_cleanup_emit(const int32_t* faces, const int64_t* fptr, const i
                               int64_t F, void* workspace, const int64_t* rec, int64_t* keep, int32_t* out_faces,
                               void* stream);
 
+/* ---- next row: chamfer / hybrid chamfer nearest-neighbour core -----------
+ * ref: eval.py:259-271 (get_chamfer in compute_chamfer) and :381-401 (get_chamfer in compute_hybrid_chamfer), which use
+ * scipy cKDTree.query(k=1).  For every query point q_i of sample b (rows ptr_q[b]..ptr_q[b+1]-1 of q f32[.,3]) the
+ * nearest reference point r_j of the same sample (ties -> lowest index) -> idx i64 (local index j, nullable),
+ * dist f64 (nullable) and sums f64[B] = sum_i dist_i (nullable; divide by the query count for the chamfer term).
+ * dist_i = |q_i - r_j| in double, or |qa_i - rb_j| when qa / rb (f32, same row layout) are given (hybrid chamfer:
+ * match in NOCS space, distance in simulation space).  max_q = largest query count of a sample (sizes the grid). */
+int32_t gnb_nn1_distance(const float* q, const int64_t* ptr_q, const float* r, const int64_t* ptr_r, int32_t B,
+                         int64_t max_q, const float* qa, const float* rb, int64_t* idx, double* dist, double* sums,
+                         void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

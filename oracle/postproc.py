@@ -106,3 +106,25 @@ def wnf_to_mesh(wnf_volume: np.ndarray, iso_surface_level=0.5, gradient_threshol
     idx = (mc_verts / voxel_spacing).astype(np.uint32)
     mc_verts_ggm = wnf_ggm[idx[:, 0], idx[:, 1], idx[:, 2]]
     return delete_invalid_verts(mc_verts, mc_faces, mc_verts_ggm > gradient_threshold)
+
+
+def chamfer(pred_points: np.ndarray, gt_points: np.ndarray) -> dict:
+    """ref eval.py:259-271 (get_chamfer inside compute_chamfer), restated; scipy's cKDTree is installed."""
+    from scipy.spatial import cKDTree
+    forward_distance, _ = cKDTree(gt_points).query(pred_points, k=1)
+    backward_distance, _ = cKDTree(pred_points).query(gt_points, k=1)
+    forward_chamfer, backward_chamfer = np.mean(forward_distance), np.mean(backward_distance)
+    return {"chamfer_forward": forward_chamfer, "chamfer_backward": backward_chamfer,
+            "chamfer_symmetrical": np.mean([forward_chamfer, backward_chamfer])}
+
+
+def hybrid_chamfer(pred_nocs_points, gt_nocs_points, pred_sim_points, gt_sim_points) -> dict:
+    """ref eval.py:381-401 (get_chamfer inside compute_hybrid_chamfer), restated."""
+    from scipy.spatial import cKDTree
+    _, forward_nn_idx = cKDTree(gt_nocs_points).query(pred_nocs_points, k=1)
+    _, backward_nn_idx = cKDTree(pred_nocs_points).query(gt_nocs_points, k=1)
+    forward_distance = np.linalg.norm(pred_sim_points - gt_sim_points[forward_nn_idx], axis=1)
+    backward_distance = np.linalg.norm(gt_sim_points - pred_sim_points[backward_nn_idx], axis=1)
+    forward_chamfer, backward_chamfer = np.mean(forward_distance), np.mean(backward_distance)
+    return {"hybrid_chamfer_forward": forward_chamfer, "hybrid_chamfer_backward": backward_chamfer,
+            "hybrid_chamfer_symmetrical": np.mean([forward_chamfer, backward_chamfer])}
