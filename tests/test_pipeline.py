@@ -253,3 +253,46 @@ def test_pointnet2_stage_six_categories_ragged(setup, category):
         assert close(res["aux"][name][0].cpu().numpy(), s1[name][0]), name
     assert close(res["per_point_features"].cpu().numpy(), s1["per_point_features"])
     assert close(res["per_point_logits"].cpu().numpy(), s1["per_point_logits"])
+
+
+@pytest.mark.gpu
+def test_config1_full_size_pointnet_and_gridding(setup):
+    """BASELINE.json configs[1] as a parity case at its full size: batch = 16 clouds x 4096 points through PointNet++
+    SA/FP and the 32^3 scatter-gridding.  FPS and ball-query indices bit-exact against the oracle for all 16 clouds
+    (2048 + 512 serial FPS rounds and 64-neighbour truncation at the real density); the gridded volume on the oracle's
+    per-point outputs: identical occupancy, values within tolerance."""
+    from garmentnets_b200.components.pointnet2 import CloudIndex
+    from garmentnets_b200.pipeline import Batch
+    s = setup
+    dev, hp = s["dev"], s["hp"]
+    B, n = 16, 4096
+    d = synthetic.make_batch(B, n, "Tshirt", seed=77)
+    rng = np.random.default_rng(1)
+    starts = (rng.integers(0, n, B), rng.integers(0, n // 2, B))
+    s1 = OP.stage1(s["sd"], hp, d["x"], d["pos"], d["batch"], B, starts)
+    data = Batch(x=torch.from_numpy(d["x"]).to(dev), pos=torch.from_numpy(d["pos"]).to(dev),
+                 batch=torch.from_numpy(d["batch"]).to(dev))
+    index = CloudIndex.uniform(B, n, dev)
+    st = tuple(torch.from_numpy(a.astype(np.int64)).to(dev) for a in starts)
+    res = s["model"].pointnet2_forward(data, index=index, fps_starts=st, return_aux=True)
+    for name, m in (("sa1", 2048), ("sa2", 512)):
+        _, _, aux = res["aux"][name]
+        ref_aux = s1[name][3]
+        assert aux["idx"].shape[0] == B * m
+        assert np.array_equal(aux["idx"].cpu().numpy(), ref_aux["idx"]), name
+        assert np.array_equal(aux["cnt"].cpu().numpy(), ref_aux["cnt"]), name
+        assert np.array_equal(aux["nbr"].cpu().numpy(), ref_aux["nbr"]), name
+    assert int(res["aux"]["sa1"][2]["cnt"].max()) == 64          # the truncation at 64 neighbours is exercised
+    assert close(res["per_point_logits"].cpu().numpy(), s1["per_point_logits"])
+    # gridding on the oracle's stage-1 outputs (a flipped argmax upstream would move a point to another voxel)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    nocs_data = Batch(x=t(s1["per_point_features"]), pos=t(s1["pred_nocs"]), batch=data.batch, sim_points=data.pos,
+                      pred_confidence=t(s1["pred_confidence"]))
+    nocs_data.num_graphs = B
+    vin = s["model"].volume_agg(nocs_data)
+    assert tuple(vin.shape) == (B, 128, 32, 32, 32)
+    ref_in = ON.volume_feature_aggregator(s["sd"], "volume_agg.", s1["per_point_features"], s1["pred_nocs"], d["pos"],
+                                          s1["pred_confidence"], d["batch"], B, 32)[0]
+    got = vin.cpu().numpy()
+    assert np.array_equal(got == 0, ref_in == 0)
+    assert close(got, ref_in)
