@@ -74,3 +74,31 @@ def hybrid_chamfer_batch(pred_nocs: Sequence[torch.Tensor], gt_nocs: Sequence[to
 
 def hybrid_chamfer(pred_nocs_points, gt_nocs_points, pred_sim_points, gt_sim_points) -> Dict[str, float]:
     return hybrid_chamfer_batch([pred_nocs_points], [gt_nocs_points], [pred_sim_points], [gt_sim_points])[0]
+
+
+def optimal_gradient_threshold(gt_mc_verts: torch.Tensor, gt_is_on_surface: torch.Tensor, pred_mc_verts: torch.Tensor,
+                               pred_mc_gm: torch.Tensor, precision_weight: float = 0.85) -> Dict[str, float]:
+    """ref eval.py:58-102 (``compute_optimal_gradient_treshold``): label every predicted marching-cubes vertex with the
+    on-surface flag of its nearest ground-truth vertex (``gnb_nn1_distance``), then pick the gradient-magnitude threshold
+    (a decision stump over the sorted magnitudes) that maximises ``precision * w + recall * (1 - w)``.  The sort / prefix
+    sums run on the device in float64 like numpy's; one host read for the result."""
+    idx, _, _, _ = nearest_neighbor([pred_mc_verts], [gt_mc_verts])
+    nn_is_on_surface = ops._req(gt_is_on_surface, torch.bool, "gt_is_on_surface")[idx]
+    gm = ops._req(pred_mc_gm, torch.float32, "pred_mc_gm")
+    sorted_idx = torch.argsort(gm, stable=True)
+    s = nn_is_on_surface[sorted_idx]
+    false_negative = torch.cumsum(s.to(torch.int64), 0)
+    true_positive = torch.flip(torch.cumsum(torch.flip(s, [0]).to(torch.int64), 0), [0])
+    false_positive = torch.flip(torch.cumsum(torch.flip(~s, [0]).to(torch.int64), 0), [0])
+    precision = true_positive.double() / (true_positive + false_positive).double()
+    recall = true_positive.double() / (true_positive + false_negative).double()
+    score = precision * precision_weight + recall * (1 - precision_weight)
+    finite = torch.isfinite(score)
+    if bool(finite.any()):
+        # np.argmax treats NaN as the maximum; the reference only reaches argmax when some score is finite, and NaN
+        # (0/0) can only occur where true_positive + false_positive == 0, which cannot happen (the suffix is never empty)
+        max_score_idx = int(torch.argmax(torch.where(finite, score, torch.full_like(score, -float("inf")))).item())
+        thr = float(gm[sorted_idx[max_score_idx]].item())
+    else:
+        thr = float(gm.min().item())
+    return {"optimal_wnf_gradient_threshold": thr}

@@ -128,3 +128,24 @@ def hybrid_chamfer(pred_nocs_points, gt_nocs_points, pred_sim_points, gt_sim_poi
     forward_chamfer, backward_chamfer = np.mean(forward_distance), np.mean(backward_distance)
     return {"hybrid_chamfer_forward": forward_chamfer, "hybrid_chamfer_backward": backward_chamfer,
             "hybrid_chamfer_symmetrical": np.mean([forward_chamfer, backward_chamfer])}
+
+
+def optimal_gradient_threshold(gt_mc_verts, gt_mc_is_on_surface, pred_mc_verts, pred_mc_gm, precision_weight=0.85):
+    """ref eval.py:58-102 (compute_optimal_gradient_treshold) on plain arrays, restated line for line."""
+    from scipy.spatial import cKDTree
+    _, nn_vert_idx = cKDTree(gt_mc_verts).query(pred_mc_verts, k=1)
+    nn_is_on_surface = gt_mc_is_on_surface[nn_vert_idx]
+    sorted_idx = np.argsort(pred_mc_gm)
+    sorted_nn_is_on_surface = nn_is_on_surface[sorted_idx]
+    false_negative = np.cumsum(sorted_nn_is_on_surface)
+    true_positive = np.cumsum(sorted_nn_is_on_surface[::-1])[::-1]
+    false_positive = np.cumsum(~sorted_nn_is_on_surface[::-1])[::-1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        precision = true_positive / (true_positive + false_positive)
+        recall = true_positive / (true_positive + false_negative)
+    score = precision * precision_weight + recall * (1 - precision_weight)
+    if np.any(np.isfinite(score)):
+        max_score_threshold = pred_mc_gm[sorted_idx[np.argmax(score)]]
+    else:
+        max_score_threshold = pred_mc_gm.min()
+    return {"optimal_wnf_gradient_threshold": max_score_threshold}
