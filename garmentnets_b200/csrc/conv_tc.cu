@@ -568,8 +568,13 @@ int32_t gnb_gn_apply_split(const float* x, int32_t B, int64_t voxels, int32_t C,
 
 int32_t gnb_conv3d_tc_supported(int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout) {
     auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
-    if (!(pow2(D) && pow2(H) && pow2(W) && pow2(B))) return 0;
+    if (!(pow2(D) && pow2(H) && pow2(W)) || B < 1) return 0;
     if ((int64_t)B * D * H * W < CT_M) return 0;
+    // a 128-voxel tile spans bb samples when a sample has fewer than 128 voxels: the batch must be a multiple of bb
+    // (any batch size works for the levels with >= 128 voxels per sample)
+    const int64_t vox = (int64_t)D * H * W;
+    const int bb = vox >= CT_M ? 1 : (int)(CT_M / vox);
+    if (B % bb != 0) return 0;
     if (Cout % 32 != 0 || Cout < 32 || Cout > 128 || Cin < 1) return 0;  // 4 accumulators x Cout columns <= 512
     return 1;
 }

@@ -9,7 +9,8 @@ TOL = 1e-4
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,G,Cin,Cout", [(1, 8, 64, 64), (2, 8, 32, 32), (1, 16, 96, 32), (2, 4, 128, 128),
-                                          (1, 8, 192, 64), (4, 4, 256, 96), (1, 32, 128, 128), (1, 16, 32, 64)])
+                                          (1, 8, 192, 64), (4, 4, 256, 96), (1, 32, 128, 128), (1, 16, 32, 64),
+                                          (5, 8, 64, 128), (3, 16, 32, 96), (6, 4, 64, 128)])   # batches that are not powers of two
 def test_conv_tc_matches_torch(dev, B, G, Cin, Cout):
     from garmentnets_b200 import ops
     assert ops.conv3d_tc_supported(B, G, G, G, Cin, Cout)
@@ -36,7 +37,7 @@ def test_conv_tc_matches_torch(dev, B, G, Cin, Cout):
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,D,H,W,Cin,Cout", [(2, 8, 8, 8, 32, 32), (1, 16, 16, 16, 96, 32), (1, 32, 32, 32, 128, 32),
                                               (4, 2, 4, 16, 40, 32), (1, 4, 8, 32, 64, 32), (2, 16, 16, 16, 192, 64),
-                                              (1, 16, 16, 16, 32, 64), (2, 8, 8, 8, 64, 64)])
+                                              (1, 16, 16, 16, 32, 64), (2, 8, 8, 8, 64, 64), (3, 16, 16, 16, 96, 32), (5, 8, 8, 8, 64, 64)])
 def test_conv_tc_stacked_dx_matches_torch(dev, B, D, H, W, Cin, Cout):
     """Stacked-kw kernel (Cout = 32 / 64): the shift along W applied to the output must reproduce zero padding at both ends of
     every line, for every tile geometry (W = 8 / 16 / 32)."""
