@@ -259,7 +259,8 @@ decode_tc_kernel(const TcParams p) {
                                      : "r"(w1_addr + (uint32_t)(((c * 32 + k) * 32 + lane) * 8)));
                     const float2 b1r = b1c[c];
                     float s0 = 1.f, s1 = 1.f, h0s = 0.f, h1s = 0.f;
-                    if (p.bn1_scale != nullptr) {   // un-folded BatchNorm1 (slow path: four dependent global loads per chunk)
+                    const bool folded_bn1 = p.bn1_scale == nullptr;
+                    if (!folded_bn1) {   // un-folded BatchNorm1 (slow path: four dependent global loads per chunk)
                         s0 = __ldg(p.bn1_scale + ch); s1 = __ldg(p.bn1_scale + ch + 1);
                         h0s = __ldg(p.bn1_shift + ch); h1s = __ldg(p.bn1_shift + ch + 1);
                     }
@@ -290,15 +291,22 @@ decode_tc_kernel(const TcParams p) {
                                 }
                             }
                         }
+                        // rows k0..k0+3 share (row >> 3) and differ in (row & 7): one base offset per group of four rows
+                        const uint32_t obase = (uint32_t)((k0 >> 3) * 1024 + (lane & 3) * 4);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             float h0, h1;
                             asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(acc[u]));
-                            h0 = fmaxf(h0, 0.f) * s0 + h0s;
-                            h1 = fmaxf(h1, 0.f) * s1 + h1s;
                             uint32_t hi, lo;
-                            split_f16x2(h0, h1, hi, lo);
-                            const uint32_t o2 = sw128_offset(k0 + u, 2 * lane);
+                            if (folded_bn1) {
+                                relu_split_f16x2(h0, h1, hi, lo);
+                            } else {
+                                h0 = fmaxf(h0, 0.f) * s0 + h0s;
+                                h1 = fmaxf(h1, 0.f) * s1 + h1s;
+                                split_f16x2(h0, h1, hi, lo);
+                            }
+                            const int r7 = (k0 + u) & 7;
+                            const uint32_t o2 = obase + (uint32_t)(r7 * 128 + ((((lane >> 2) ^ r7) & 7) << 4));
                             *reinterpret_cast<uint32_t*>(ah + o2) = hi;
                             *reinterpret_cast<uint32_t*>(al + o2) = lo;
                         }

@@ -89,6 +89,20 @@ __device__ __forceinline__ float4 ldg_keep(const float* p) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// two fp32 -> packed fp16x2 (first argument in the low half), saturating to +-65504 instead of overflowing to inf
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+// ReLU + fp16 hi/lo split of two fp32 values in 7 instructions (saturating conversions instead of explicit clamps)
+__device__ __forceinline__ void relu_split_f16x2(float h0, float h1, uint32_t& hi, uint32_t& lo) {
+    const float x0 = fmaxf(h0, 0.f), x1 = fmaxf(h1, 0.f);
+    hi = cvt_f16x2_sat(x0, x1);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    lo = cvt_f16x2_sat(x0 - hf.x, x1 - hf.y);
+}
+
 // byte offset of element (row r, K-column c) inside one [rows x 64] 16-bit K-major SWIZZLE_128B tile
 __host__ __device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 3) ^ (r & 7)) & 7) << 4) + (c & 7) * 2);
