@@ -58,8 +58,8 @@ struct Params {
     const float* U;            // [B,G,G,G,256] hoisted grid (Linear1 applied on the feature grid), fp32 channels-last
     int B, G, Q;
     const uint8_t* w2_packed;  // (W2 * diag(bn1_scale)) * 2^s, gnb_pack_f16_split layout
-    const float* b2s;          // [256] (b2 + W2 bn1_shift) * 2^s
-    const float* w3s;          // [COUT][256] W3 * bn2_scale * 2^-s
+    const float* b2s;          // [256] (b2 + W2 bn1_shift) * 2^s          (scratch; the kernel reads the copy in c_epi)
+    const float* w3s;          // [COUT][256] W3 * bn2_scale * 2^-s        (scratch; the kernel reads the copy in c_epi)
     const float* tail;         // [COUT][4] {c0, bn3_scale, bn3_shift, 0}
     float* out;                // [B, Q^3, COUT]
     int64_t num_pairs;         // B * Q * Q / 2

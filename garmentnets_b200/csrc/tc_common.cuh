@@ -80,13 +80,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
-// 16-byte read-only load of a small, hot parameter vector (epilogue constants): kept in L1 with evict_last priority so the
-// producers' streaming gathers do not push it out between two uses
-__device__ __forceinline__ float4 ldg_keep(const float* p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // two fp32 -> packed fp16x2 (first argument in the low half), saturating to +-65504 instead of overflowing to inf
