@@ -474,9 +474,10 @@ static int32_t linear_tc_launch(const float* X, int64_t R, int32_t K, int64_t ld
     p.seg = seg; p.seg_out = seg_out; p.ldo = ldo;
     p.piece_bytes = l.piece_bytes;
     p.m_tiles = ceil_div<int64_t>(R, LT_M);
-    // separate cross-term accumulator only for long contractions (short chains do not accumulate a visible truncation
-    // bias, and the epilogue saves a TMEM load and 32 adds per box)
-    p.split = (l.Npad <= 128 && l.nchunk > 2) ? 1 : 0;
+    // separate cross-term accumulator whenever TMEM has room -- also for short contractions: measured on the PointNet++
+    // chain (smoke configuration), sharing one accumulator doubles the end-to-end error (per-point logits 6.0e-5 ->
+    // 1.15e-4 against the oracle) because EVERY tcgen05.mma truncates the full accumulator, however small its addend
+    p.split = l.Npad <= 128 ? 1 : 0;
     p.vec_store = (!seg && (ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(Y) % 16) == 0 && (l.Npad % 4) == 0) ? 1 : 0;
     const int64_t resident_bytes = (int64_t)l.nchunk * l.piece_bytes;
     if (l.n_blocks == 1 && l.nchunk <= LT_MAX_B && resident_bytes + 2 * LT_A_STAGE <= LT_SMEM_BUDGET) {
