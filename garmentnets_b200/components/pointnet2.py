@@ -159,9 +159,35 @@ class PointConv(nn.Module):
     fuse_aggregation = False
 
     def forward(self, x, pos, edge_index):
-        raise NotImplementedError(
-            "PointConv.forward(edge_index) is served through SAModule (ball query and grouping are fused); "
-            "call SAModule.forward or PointConv.forward_grouped")
+        """The PyG call shape the reference's own ``SAModule`` uses (ref components/pointnet2.py:30-31):
+        ``x`` [Nx,C] or None (or a pair), ``pos`` = (pos_x [Nx,3], pos_y [M,3]) or one tensor, ``edge_index`` i64[2,E] =
+        [source j into x / pos_x, target i into pos_y].  PyG 1.7.2 semantics: with ``add_self_loops`` the edges whose two
+        INDICES coincide are dropped and (i, i) is appended for i < M -- also in the bipartite case, where source i is a
+        different point than centre i; message = local_nn([x_j, pos_j - pos_i]); max aggregation over the targets.
+        Arbitrary edge order is accepted (edges are grouped by target with a stable device sort); the edge MLP and the
+        segmented max are the same kernels ``forward_grouped`` uses."""
+        if isinstance(x, (tuple, list)):
+            x = x[0]
+        pos_x, pos_y = (pos, pos) if isinstance(pos, torch.Tensor) else pos
+        M = pos_y.shape[0]
+        src, dst = edge_index[0], edge_index[1]
+        if self.add_self_loops:
+            keep = src != dst
+            loop = torch.arange(M, dtype=src.dtype, device=src.device)
+            src, dst = torch.cat([src[keep], loop]), torch.cat([dst[keep], loop])
+        dst, perm = torch.sort(dst, stable=True)
+        src = src[perm]
+        eoffs = ops.batch_to_ptr(dst, M)
+        msg = pos_x[src] - pos_y[dst]
+        edge = msg if x is None else torch.cat([x[src], msg], dim=1)
+        h = edge.contiguous()
+        for block in self.local_nn:
+            h = block(h)
+        out = ops.segment_max(h, eoffs)
+        if not self.add_self_loops:   # PyG's max aggregation leaves 0 for targets without any edge
+            empty = (eoffs[1:] == eoffs[:-1])
+            out[empty] = 0.0
+        return out
 
 
 # ------------------------------------------------------------------------------------------------ modules

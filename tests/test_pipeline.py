@@ -176,7 +176,7 @@ def test_predict_end_to_end(setup):
     s2_cont = OP.stage2(s["sd"], hp, s1_gpu, d["pos"][:n], batch0, 1)
     wnf_cont = ON.dense_decode(s["sd"], "volume_decoder.", s2_cont["out_feature_volume"], 32, 16).numpy()
     diff = np.abs(out["wnf_volume"].cpu().numpy() - wnf_cont)
-    assert np.median(diff) < 1e-5 and (diff > TOL).mean() < 0.02 and diff.max() < 1e-3, (np.median(diff), (diff > TOL).mean(), diff.max())
+    assert np.median(diff) < 1e-5 and diff.max() < TOL, (np.median(diff), (diff > TOL).mean(), diff.max())
     if len(flipped) == 0:
         assert abs(len(out["verts"]) - len(mesh["verts"])) <= 0.05 * len(mesh["verts"]) + 8
     assert out["faces"].dtype == torch.int32 and out["warp_field"].shape == (len(out["verts"]), 3)
@@ -296,3 +296,157 @@ def test_config1_full_size_pointnet_and_gridding(setup):
     got = vin.cpu().numpy()
     assert np.array_equal(got == 0, ref_in == 0)
     assert close(got, ref_in)
+
+
+@pytest.mark.gpu
+def test_config2_full_size_stagewise(setup):
+    """BASELINE.json configs[2] at its full per-cloud size (4096 points -> 32^3 UNet -> 128^3 dense decode -> marching
+    cubes -> surface decode), two clouds, stage by stage on the ORACLE's inputs: FPS / ball-query indices bit-exact, the
+    128^3 winding-number volume within 1e-4 max-abs of the chunked oracle loop (both the module path and predict()'s
+    folded path), marching cubes of the PREDICTED 128^3 volume bit-exact against the C oracle (faces, vertices, ggm
+    lookup), warp field at the mesh vertices within 1e-4."""
+    from garmentnets_b200 import ops
+    from garmentnets_b200.components.pointnet2 import CloudIndex
+    from garmentnets_b200.pipeline import Batch
+    from oracle import postproc
+    s = setup
+    dev, hp, sd, model = s["dev"], s["hp"], s["sd"], s["model"]
+    B, n, Q = 2, 4096, 128
+    d = synthetic.make_batch(B, n, "Tshirt", seed=91)
+    rng = np.random.default_rng(7)
+    starts = (rng.integers(0, n, B), rng.integers(0, n // 2, B))
+    s1 = OP.stage1(sd, hp, d["x"], d["pos"], d["batch"], B, starts)
+    data = Batch(x=torch.from_numpy(d["x"]).to(dev), pos=torch.from_numpy(d["pos"]).to(dev),
+                 batch=torch.from_numpy(d["batch"]).to(dev))
+    index = CloudIndex.uniform(B, n, dev)
+    st = tuple(torch.from_numpy(a.astype(np.int64)).to(dev) for a in starts)
+    res = model.pointnet2_forward(data, index=index, fps_starts=st, return_aux=True)
+    for name in ("sa1", "sa2"):
+        aux, ref_aux = res["aux"][name][2], s1[name][3]
+        assert np.array_equal(aux["idx"].cpu().numpy(), ref_aux["idx"]), name
+        assert np.array_equal(aux["nbr"].cpu().numpy(), ref_aux["nbr"]), name
+        assert np.array_equal(aux["cnt"].cpu().numpy(), ref_aux["cnt"]), name
+    assert close(res["per_point_logits"].cpu().numpy(), s1["per_point_logits"])
+    # aggregator + UNet on the oracle's stage-1 outputs
+    s2 = OP.stage2(sd, hp, s1, d["pos"], d["batch"], B)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    nocs_data = Batch(x=t(s1["per_point_features"]), pos=t(s1["pred_nocs"]), batch=data.batch, sim_points=data.pos,
+                      pred_confidence=t(s1["pred_confidence"]))
+    nocs_data.num_graphs = B
+    u = model.unet3d_forward({"nocs_data": nocs_data})
+    assert np.array_equal(u["in_feature_volume"].cpu().numpy() == 0, s2["in_feature_volume"] == 0)
+    assert close(u["out_feature_volume"].cpu().numpy(), s2["out_feature_volume"])
+    # 128^3 dense decode on the oracle's feature volume: the module path and predict()'s folded path
+    fv_ref = s2["out_feature_volume"]
+    wnf_ref = np.stack([ON.dense_decode(sd, "volume_decoder.", fv_ref[b:b + 1], Q, 64).numpy() for b in range(B)])
+    wnf_a = model.dense_decode(t(fv_ref), Q)
+    assert np.abs(wnf_a.cpu().numpy() - wnf_ref).max() < TOL
+    unet = model.unet_3d.abstract_3d_unet
+    x_last = unet.forward_ndhwc(ops.to_channels_last(t(s2["in_feature_volume"])), apply_final=False)
+    wnf_b = model.dense_decode(None, Q, hoisted=model.volume_decoder.hoisted_folded(x_last, unet.final_conv))
+    err_b = np.abs(wnf_b.cpu().numpy() - wnf_ref).max()
+    assert err_b < TOL, err_b
+    assert 0.02 < float((wnf_ref > 0.5).mean()) < 0.5
+    # marching cubes of the predicted 128^3 volumes: bit-exact against the C oracle
+    ggm = ops.gaussian_gradient_magnitude_batched(wnf_b, 0.5)
+    mcs, packed = ops.marching_cubes_batch(wnf_b, 0.5, (1 / (Q - 1),) * 3, "ascent", ggm, return_packed=True)
+    vol_host = wnf_b.cpu().numpy()
+    for b in range(B):
+        mesh = postproc.predict_tail(vol_host[b], 0.5, 0.5, "ascent")
+        verts, faces, normals, values, ggm_at = mcs[b]
+        assert len(mesh["verts"]) > 10000
+        assert np.array_equal(faces.cpu().numpy(), mesh["faces"]), b
+        assert np.array_equal(verts.cpu().numpy(), mesh["verts"]), b
+        assert np.abs(ggm_at.cpu().numpy() - mesh["volume_gradient_magnitude"]).max() < 1e-6
+        # warp field at those vertices from the oracle's feature volume (fused query decoder) vs the oracle decoder
+        # (~190 k vertices; the synthetic last BatchNorm gives a warp field of magnitude up to ~5, so the yardstick is a
+        # FLOAT64 evaluation of the oracle decoder: within 1e-4 * max(1, max|field|) of it and no further from it than
+        # 3x the float32 oracle's own distance)
+        q = torch.from_numpy(mesh["verts"]).view(1, -1, 3)
+        warp_ref = ON.implicit_decoder(sd, "surface_decoder.", fv_ref[b:b + 1], q).view(-1, 3).numpy()
+        sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items() if k.startswith("surface_decoder.")}
+        warp64 = ON.implicit_decoder(sd64, "surface_decoder.", torch.from_numpy(fv_ref[b:b + 1]).double(), q.double()).view(-1, 3).numpy()
+        warp = model.surface_decoder.forward_fused_ragged(x_last[b:b + 1], unet.final_conv, verts.contiguous(),
+                                                          [0, len(verts)])
+        e_gpu = np.abs(warp.cpu().numpy() - warp64).max()
+        e_o32 = np.abs(warp_ref - warp64).max()
+        print(f"warp field sample {b}: |gpu-f64| {e_gpu:.3e} |oracle32-f64| {e_o32:.3e} max|field| {np.abs(warp64).max():.2f}")
+        assert e_gpu < TOL * max(1.0, float(np.abs(warp64).max())), (b, e_gpu)
+        assert e_gpu < 3.0 * e_o32 + 1e-6, (b, e_gpu, e_o32)
+
+
+def _stage2_in(sd, hp, s1_gpu, pos, batch, B, dtype):
+    """Oracle stage 2 + dense decode continued from given stage-1 outputs, in float32 or float64."""
+    sd_t = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+    cast = lambda a: np.asarray(a, dtype=np.float64 if dtype == torch.float64 else np.float32)
+    s1c = {k: cast(v) for k, v in s1_gpu.items()}
+    G = hp["volume_agg"]["grid_shape"][0]
+    # voxel assignment from the float32 NOCS points (they are exact multiples of 1/63 in float32 either way)
+    vol_in, flat, feats, h = ON.volume_feature_aggregator(sd_t, "volume_agg.", s1c["per_point_features"],
+                                                          s1_gpu["pred_nocs"].astype(np.float32), cast(pos),
+                                                          s1c["pred_confidence"], batch, B, G) \
+        if dtype == torch.float32 else _agg64(sd_t, s1c, s1_gpu, pos, batch, B, G)
+    out = ON.unet3d_forward(sd_t, "unet_3d.abstract_3d_unet.", torch.from_numpy(vol_in).to(dtype), hp["unet3d"]["num_levels"],
+                            hp["unet3d"]["num_groups"])
+    return out
+
+
+def _agg64(sd_t, s1c, s1_gpu, pos, batch, B, G):
+    """Float64 aggregator: same voxel indices as the float32 restatement, features / MLP / max in float64."""
+    idx3 = ON.points_grid_idxs(s1_gpu["pred_nocs"].astype(np.float32), G)
+    flat = (np.asarray(batch, np.int64) * G ** 3 + idx3[:, 0] * G ** 2 + idx3[:, 1] * G + idx3[:, 2])
+    scales32 = (torch.ones(3) / (torch.tensor([G] * 3, dtype=torch.float32) - 1)).numpy()
+    origin = (idx3.astype(np.float32) * scales32).astype(np.float32)
+    local_offset = (s1_gpu["pred_nocs"].astype(np.float32) - origin).astype(np.float64)   # the fp32 offset IS the input
+    feats = np.concatenate([s1c["per_point_features"], local_offset, np.asarray(pos, np.float64),
+                            s1c["pred_confidence"]], axis=-1)
+    h = ON.mlp(sd_t, "volume_agg.local_nn.", torch.from_numpy(feats)).numpy()
+    C = h.shape[1]
+    vol = np.zeros((C, B * G ** 3), np.float64)
+    tmp = np.full((C, B * G ** 3), -np.inf)
+    np.maximum.at(tmp, (slice(None), flat), h.T)
+    touched = np.zeros(B * G ** 3, bool)
+    touched[flat] = True
+    vol[:, touched] = tmp[:, touched]
+    vol = np.ascontiguousarray(vol.reshape(C, B, G, G, G).transpose(1, 0, 2, 3, 4))
+    return vol, flat, feats, h
+
+
+@pytest.mark.gpu
+def test_chained_wnf_error_is_fp32_rounding_noise(setup):
+    """End to end (stage 1.5 -> UNet -> dense decode chained on the device, no oracle restart in between) the CUDA
+    winding-number volume is compared with a FLOAT64 evaluation of the oracle continued from the same stage-1 outputs:
+    it must be as close to that truth as the float32 oracle itself is (factor 3 + 1e-6), and within the north-star 1e-4
+    max-abs of it.  (Two float32 evaluations of a GroupNorm UNet differ by summation order; comparing them with each other
+    doubles that noise, which is why the float64 truth is the yardstick.)"""
+    from garmentnets_b200.components.pointnet2 import CloudIndex
+    from garmentnets_b200.pipeline import Batch
+    s = setup
+    dev, hp, d, n, sd = s["dev"], s["hp"], s["d"], s["n"], s["sd"]
+    one = Batch(x=s["data"].x[:n], pos=s["data"].pos[:n], batch=s["data"].batch[:n])
+    starts = tuple(torch.from_numpy(a[:1].astype(np.int64)).to(dev) for a in s["starts"])
+    index1 = CloudIndex.uniform(1, n, dev)
+    out = s["model"].predict(one, volume_size=32, index=index1, fps_starts=starts, keep_volume=True)[0]
+    p1 = s["model"].pointnet2_forward(one, index=index1, fps_starts=starts)
+    s1_gpu = {"per_point_features": p1["per_point_features"].cpu().numpy(), "pred_nocs": p1["nocs_data"].pos.cpu().numpy(),
+              "pred_confidence": p1["nocs_data"].pred_confidence.cpu().numpy()}
+    batch0 = np.zeros(n, np.int64)
+    vols = {}
+    for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        fv = _stage2_in(sd, hp, s1_gpu, d["pos"][:n], batch0, 1, dt)
+        sd_t = {k: (v.to(dt) if v.is_floating_point() else v) for k, v in sd.items()}
+        vols[name] = ON.dense_decode(sd_t, "volume_decoder.", fv, 32, 16).double().numpy() if dt == torch.float32 else \
+            _dense64(sd_t, fv, 32)
+    gpu = out["wnf_volume"].cpu().numpy().astype(np.float64)
+    e_gpu = np.abs(gpu - vols["f64"]).max()
+    e_o32 = np.abs(vols["f32"] - vols["f64"]).max()
+    print(f"chained wnf: |gpu-f64| {e_gpu:.3e}  |oracle32-f64| {e_o32:.3e}  field std {vols['f64'].std():.3f} "
+          f"range [{vols['f64'].min():.2f}, {vols['f64'].max():.2f}]")
+    assert e_gpu < TOL, e_gpu
+    assert e_gpu < 3.0 * e_o32 + 1e-6, (e_gpu, e_o32)
+
+
+def _dense64(sd_t, fv, Q):
+    ax = torch.arange(Q, dtype=torch.float64) * float(np.float32(1.0) / np.float32(Q - 1))   # the fp32 lattice spacing
+    gp = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), dim=-1)
+    return ON.implicit_decoder(sd_t, "volume_decoder.", fv, gp.reshape(1, -1, 3)).view(Q, Q, Q).numpy()
