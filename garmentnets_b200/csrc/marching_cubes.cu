@@ -12,7 +12,12 @@
 //   * vertex position = inverse-|value| weighted mean of the edge end points (FLT_EPSILON guard), double arithmetic,
 //     stored as float32 in voxel units, then * spacing in double, cast to float32 (predict.py:193);
 //   * 'ascent' and 'descent' differ by the face column order; ValueError when level is outside [min,max].
-// Interior ("tunnel") tests and the extra centre vertex of MC33 are not reproduced.
+// MC33 structure: ambiguous faces are resolved by the face test (asymptotic decider with Lewiner's FLT_EPSILON band), the
+// interior ambiguity of sub-cases 4.1 / 6.1 / 7.4 / 10.1 / 12.1 / 13.5 by Chernyaev's interior test (the form Lewiner's
+// test_interior uses for cases 4 and 10, applied to every tunnel-capable configuration; it equals the true connectivity of
+// the trilinear interpolant, tests/test_mc33.py); a joined pair of regions replaces two caps by a tube (4.1.2, 6.1.2, 7.4.2,
+// 10.1.2, 12.1.2, 13.5.2).  Tilings never put an edge inside a cube face other than the iso-contour segments, so cells
+// sharing a face cannot collide; loops / tubes without such a triangulation get extra centre vertices.
 //
 // Kernels: classify (cube code per cell + per-block vertex/face counts + min/max), single-CTA scan of the block
 // counts, vertex emission by owner cells (+ edge -> vertex map), face emission.  All integer/byte work, HBM-bound:
@@ -23,7 +28,7 @@
 
 namespace gnb {
 
-constexpr int MC_MAX_TRI = 12, MC_MAX_CEN = 2;
+constexpr int MC_MAX_TRI = 14, MC_MAX_CEN = 2, MC_MAX_TUN = 160;
 struct McEntry {
     uint8_t ntri, nedge, ncen, pad0;
     uint8_t order[12 + MC_MAX_CEN];      // distinct vertex ids in first-use order (0..11 cube edges, 12+ loop centres)
@@ -31,9 +36,18 @@ struct McEntry {
     uint8_t cen_n[MC_MAX_CEN];           // loop length of each centre vertex
     uint8_t cen_loop[MC_MAX_CEN][12];    // the loop's edges, in loop order
 };
-static_assert(sizeof(McEntry) == 4 + 14 + 36 + 2 + 24, "McEntry layout");
+static_assert(sizeof(McEntry) == 4 + 14 + 3 * MC_MAX_TRI + 2 + 24, "McEntry layout");
+// interior-test descriptor of one (cube index, face decisions) configuration with annular regions
+struct McTunDesc {
+    uint8_t nann, npair[2], pad;
+    int8_t sigma[2];            // sign of the two regions the tunnel would join
+    uint8_t col[2][3][8];       // per annulus, per candidate corner pair: corner ids A0 A1 B0 B1 C0 C1 D0 D1 (sweep columns)
+};
 
 __device__ McEntry d_mc_table[256 * 64];
+__device__ McEntry d_mc_tun_table[MC_MAX_TUN];     // tunnel tilings: entry d_mc_tun_index[key] + annulus
+__device__ McTunDesc d_mc_tun_desc[MC_MAX_TUN];    // descriptor at d_mc_tun_index[key]
+__device__ int16_t d_mc_tun_index[256 * 64];       // -1: no interior ambiguity
 __device__ uint16_t d_mc_edgemask[256];
 __device__ uint8_t d_mc_ambig[256];  // bit f set: face f is ambiguous for this cube index
 
@@ -99,75 +113,364 @@ static int triangulate_loop(const int* poly, int n, int (*tris)[3]) {
     return nt;
 }
 
-static void build_tables(McEntry* table, uint16_t* edgemask, uint8_t* ambig) {
+// ---- host: MC33 configuration analysis ---------------------------------------------------------------------------
+static const int8_t h_corner_xyz[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+static int corner_dist(int a, int b) {
+    int d = 0;
+    for (int i = 0; i < 3; ++i) d += h_corner_xyz[a][i] != h_corner_xyz[b][i];
+    return d;
+}
+static int corner_flip(int c, int axis) {
+    int q[3] = {h_corner_xyz[c][0], h_corner_xyz[c][1], h_corner_xyz[c][2]};
+    q[axis] ^= 1;
+    for (int k = 0; k < 8; ++k)
+        if (h_corner_xyz[k][0] == q[0] && h_corner_xyz[k][1] == q[1] && h_corner_xyz[k][2] == q[2]) return k;
+    return -1;
+}
+
+struct CellConfig {
+    int nloop = 0, len[4] = {0, 0, 0, 0}, loop[4][12];
+    uint8_t region_of[8];        // region id of every corner = smallest corner index of its region
+    uint8_t side[4][2];          // the two regions a loop separates
+    int nann = 0, ann_loop[2][2], ann_npair[2] = {0, 0}, ann_pair[2][3][2];
+};
+
+// loops of iso-contour segments (directed: positive side on the left seen from outside), the regions they cut the cube
+// surface into, the annular regions and the corner pairs the interior test examines
+static CellConfig analyse_config(int idx, int fb, int am) {
+    CellConfig cc;
+    int succ[12];
+    for (int e = 0; e < 12; ++e) succ[e] = -1;
+    // regions as corner bitmasks, merged until stable
+    uint8_t mask[8];
+    for (int c = 0; c < 8; ++c) mask[c] = (uint8_t)(1u << c);
+    auto merge = [&](int a, int b) {
+        const uint8_t m = mask[a] | mask[b];
+        for (int c = 0; c < 8; ++c)
+            if ((m >> c) & 1) mask[c] = m;
+    };
+    for (int e = 0; e < 12; ++e) {
+        const int a = h_edge_corner[e][0], b = h_edge_corner[e][1];
+        if (((idx >> a) & 1) == ((idx >> b) & 1)) merge(a, b);
+    }
+    for (int f = 0; f < 6; ++f) {
+        int s[4], np = 0;
+        for (int i = 0; i < 4; ++i) { s[i] = (idx >> h_face_corner[f][i]) & 1; np += s[i]; }
+        if (np == 0 || np == 4) continue;
+        const int8_t* fe = h_face_edge[f];
+        const int8_t* fc = h_face_corner[f];
+        if (!((am >> f) & 1)) {
+            int i0 = -1, j0 = -1;  // positive run i0..j0 (ccw)
+            for (int i = 0; i < 4; ++i) {
+                if (s[i] && !s[(i + 3) & 3]) i0 = i;
+                if (s[i] && !s[(i + 1) & 3]) j0 = i;
+            }
+            succ[fe[j0]] = fe[(i0 + 3) & 3];
+        } else if (!((fb >> f) & 1)) {  // positive corners separated: the negative diagonal is connected
+            for (int q = 0; q < 4; ++q)
+                if (s[q]) succ[fe[q]] = fe[(q + 3) & 3];
+            merge(fc[s[0] ? 1 : 0], fc[s[0] ? 3 : 2]);
+        } else {  // positive corners connected: the negative corners are cut off
+            for (int n = 0; n < 4; ++n)
+                if (!s[n]) succ[fe[(n + 3) & 3]] = fe[n];
+            merge(fc[s[0] ? 0 : 1], fc[s[0] ? 2 : 3]);
+        }
+    }
+    for (int c = 0; c < 8; ++c) {
+        int r = 0;
+        while (!((mask[c] >> r) & 1)) ++r;
+        cc.region_of[c] = (uint8_t)r;
+    }
+    bool seen[12] = {false};
+    for (int e0 = 0; e0 < 12; ++e0) {
+        if (succ[e0] < 0 || seen[e0]) continue;
+        int n = 0;
+        for (int e = e0; !seen[e]; e = succ[e]) { seen[e] = true; cc.loop[cc.nloop][n++] = e; }
+        cc.len[cc.nloop] = n;
+        cc.side[cc.nloop][0] = cc.region_of[h_edge_corner[e0][0]];
+        cc.side[cc.nloop][1] = cc.region_of[h_edge_corner[e0][1]];
+        ++cc.nloop;
+    }
+    // annuli (regions bounded by exactly two loops), by region id
+    int ann_region[4], ann_l[4][2], nann_all = 0;
+    for (int r = 0; r < 8; ++r) {
+        if (cc.region_of[r] != r) continue;
+        int cnt = 0, l2[2] = {-1, -1};
+        for (int l = 0; l < cc.nloop; ++l)
+            if (cc.side[l][0] == r || cc.side[l][1] == r) { if (cnt < 2) l2[cnt] = l; ++cnt; }
+        if (cnt == 2) { ann_region[nann_all] = r; ann_l[nann_all][0] = l2[0]; ann_l[nann_all][1] = l2[1]; ++nann_all; }
+    }
+    for (int k = 0; k < nann_all; ++k) {
+        const int r = ann_region[k], la = ann_l[k][0], lb = ann_l[k][1];
+        const int ra = cc.side[la][0] == r ? cc.side[la][1] : cc.side[la][0];
+        const int rb = cc.side[lb][0] == r ? cc.side[lb][1] : cc.side[lb][0];
+        int want = 0;
+        for (int a = 0; a < 8; ++a)
+            for (int b = 0; b < 8; ++b)
+                if (cc.region_of[a] == ra && cc.region_of[b] == rb && corner_dist(a, b) == 3) want = 3;
+        if (!want && nann_all == 2) want = 2;   // case 13.5: nested annuli, face-diagonal pairs
+        if (!want) continue;
+        const int o = cc.nann++;
+        cc.ann_loop[o][0] = la; cc.ann_loop[o][1] = lb;
+        for (int a = 0; a < 8; ++a)
+            for (int b = 0; b < 8; ++b)
+                if (cc.region_of[a] == ra && cc.region_of[b] == rb && corner_dist(a, b) == want) {
+                    if (cc.ann_npair[o] >= 3) { fprintf(stderr, "mc table: too many interior-test pairs\n"); abort(); }
+                    cc.ann_pair[o][cc.ann_npair[o]][0] = a; cc.ann_pair[o][cc.ann_npair[o]][1] = b;
+                    ++cc.ann_npair[o];
+                }
+    }
+    return cc;
+}
+
+// sweep columns of the interior test for the corner pair (p, q): A0 A1 B0 B1 C0 C1 D0 D1
+static void sweep_columns(int p, int q, uint8_t col[8]) {
+    int axis = 2;
+    if (corner_dist(p, q) == 2)
+        for (int i = 0; i < 3; ++i)
+            if (h_corner_xyz[p][i] == h_corner_xyz[q][i]) axis = i;
+    const int A0 = p, C0 = h_corner_xyz[q][axis] == h_corner_xyz[p][axis] ? q : corner_flip(q, axis);
+    int other[2], no = 0;
+    for (int c = 0; c < 8; ++c)
+        if (h_corner_xyz[c][axis] == h_corner_xyz[p][axis] && c != A0 && c != C0) other[no++] = c;
+    col[0] = (uint8_t)A0; col[1] = (uint8_t)corner_flip(A0, axis);
+    col[2] = (uint8_t)other[0]; col[3] = (uint8_t)corner_flip(other[0], axis);
+    col[4] = (uint8_t)C0; col[5] = (uint8_t)corner_flip(C0, axis);
+    col[6] = (uint8_t)other[1]; col[7] = (uint8_t)corner_flip(other[1], axis);
+}
+
+// ---- host: tube between two loops -----------------------------------------------------------------------------------
+// Edge midpoints in units of 1/5040 (the mean of 3..10 of them stays integral): integer costs, no rounding.
+static void mid_of(int e, long long m[3]) {
+    for (int i = 0; i < 3; ++i) m[i] = (long long)(h_corner_xyz[h_edge_corner[e][0]][i] + h_corner_xyz[h_edge_corner[e][1]][i]) * 2520;
+}
+static long long mid_dist2(int e1, int e2) {
+    long long a[3], b[3], d = 0;
+    mid_of(e1, a); mid_of(e2, b);
+    for (int i = 0; i < 3; ++i) d += (a[i] - b[i]) * (a[i] - b[i]);
+    return d;
+}
+struct Triangulation {
+    int n = 0;
+    long long cost = 0;
+    uint8_t v[16][3];
+    bool less_than(const Triangulation& o) const {   // (cost, emitted vertex sequence)
+        if (cost != o.cost) return cost < o.cost;
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k)
+                if (v[i][k] != o.v[i][k]) return v[i][k] < o.v[i][k];
+        return false;
+    }
+    bool simplicial() const {                         // every oriented edge at most once, no degenerate triangle
+        bool used[16][16] = {{false}};
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k) {
+                const int a = v[i][k], b = v[i][(k + 1) % 3];
+                if (a == b || used[a][b]) return false;
+                used[a][b] = true;
+            }
+        return true;
+    }
+};
+// all triangulations of the polygon P[lo..hi] (closing chord lo-hi), appended to `cur` in the order (lo,k,hi), left, right;
+// `todo` holds the intervals still to split (the last one is split next)
+static void enumerate_polygon(const int* P, int m, int (*todo)[2], int ntodo, Triangulation& cur, Triangulation& best,
+                              bool& have) {
+    while (ntodo > 0 && todo[ntodo - 1][1] - todo[ntodo - 1][0] < 2) --ntodo;
+    if (ntodo == 0) {
+        if (cur.simplicial() && (!have || cur.less_than(best))) { best = cur; have = true; }
+        return;
+    }
+    const int lo = todo[ntodo - 1][0], hi = todo[ntodo - 1][1];
+    auto side_ok = [&](int a, int b) {
+        if (b == a + 1 || (a == 0 && b == m - 1)) return true;
+        return P[a] != P[b] && !cofacial(P[a], P[b]);
+    };
+    auto side_cost = [&](int a, int b) -> long long {
+        if (b == a + 1 || (a == 0 && b == m - 1)) return 0;
+        return mid_dist2(P[a], P[b]);
+    };
+    for (int k = lo + 1; k < hi; ++k) {
+        if (!side_ok(lo, k) || !side_ok(k, hi)) continue;
+        if (P[lo] == P[k] || P[k] == P[hi] || P[lo] == P[hi]) continue;
+        int next[16][2];
+        for (int i = 0; i < ntodo - 1; ++i) { next[i][0] = todo[i][0]; next[i][1] = todo[i][1]; }
+        next[ntodo - 1][0] = k; next[ntodo - 1][1] = hi;
+        next[ntodo][0] = lo; next[ntodo][1] = k;
+        Triangulation t = cur;
+        t.v[t.n][0] = (uint8_t)P[lo]; t.v[t.n][1] = (uint8_t)P[k]; t.v[t.n][2] = (uint8_t)P[hi];
+        ++t.n;
+        t.cost += side_cost(lo, k) + side_cost(k, hi);
+        enumerate_polygon(P, m, next, ntodo + 1, t, best, have);
+    }
+}
+// Triangulates the annulus between the directed loops L1, L2.  Vertex ids 0..11 are cube edges, 12 + c0 (+1) extra
+// vertices whose definitions go to cen_n / cen_loop.  Returns false if no tiling exists (never for the MC33 cases).
+static bool tube_between(const int* L1, int n1, const int* L2, int n2, int c0, Triangulation& out, int& ncen_used,
+                         uint8_t* cen_n, uint8_t (*cen_loop)[12]) {
+    bool have = false;
+    Triangulation best;
+    for (int i = 0; i < n1; ++i)
+        for (int j = 0; j < n2; ++j) {   // bridge L1[i] - L2[j] cuts the annulus open into one polygon
+            if (cofacial(L1[i], L2[j])) continue;
+            int P[16], m = 0;
+            for (int k = 0; k < n1; ++k) P[m++] = L1[(i + k) % n1];
+            P[m++] = L1[i];
+            for (int k = 0; k < n2; ++k) P[m++] = L2[(j + k) % n2];
+            P[m++] = L2[j];
+            Triangulation cur, b;
+            cur.cost = mid_dist2(L1[i], L2[j]);
+            bool h = false;
+            int todo[16][2] = {{0, m - 1}};
+            enumerate_polygon(P, m, todo, 1, cur, b, h);
+            if (h && (!have || b.cost < best.cost)) { best = b; have = true; }   // ties: the first bridge wins
+        }
+    ncen_used = 0;
+    if (have) { out = best; return true; }
+    // two fans around two extra vertices: vertex 1 over L1[a..a+k1] + L2[p..p+k2], vertex 2 over the rest
+    long long best_cost = -1;
+    int sel[4] = {0, 0, 0, 0};
+    auto fan_cost = [&](const int* ring, int d) {
+        long long c[3] = {0, 0, 0}, m3[3], sum = 0;
+        for (int t = 0; t < d; ++t) { mid_of(ring[t], m3); c[0] += m3[0]; c[1] += m3[1]; c[2] += m3[2]; }
+        for (int i = 0; i < 3; ++i) c[i] /= d;
+        for (int t = 0; t < d; ++t) {
+            mid_of(ring[t], m3);
+            for (int i = 0; i < 3; ++i) sum += (c[i] - m3[i]) * (c[i] - m3[i]);
+        }
+        return sum;
+    };
+    auto rings = [&](int a, int k1, int p, int k2, int* link, int& d1, int* rest, int& d2) {
+        const int b = (a + k1) % n1, q = (p + k2) % n2;
+        d1 = d2 = 0;
+        for (int t = 0; t <= k1; ++t) link[d1++] = L1[(a + t) % n1];
+        for (int t = 0; t <= k2; ++t) link[d1++] = L2[(p + t) % n2];
+        for (int t = 0; t <= n1 - k1; ++t) rest[d2++] = L1[(b + t) % n1];
+        for (int t = 0; t <= n2 - k2; ++t) rest[d2++] = L2[(q + t) % n2];
+    };
+    for (int a = 0; a < n1; ++a)
+        for (int k1 = 1; k1 < n1; ++k1)
+            for (int p = 0; p < n2; ++p)
+                for (int k2 = 1; k2 < n2; ++k2) {
+                    const int b = (a + k1) % n1, q = (p + k2) % n2;
+                    if (cofacial(L1[b], L2[p]) || cofacial(L2[q], L1[a])) continue;
+                    int link[16], rest[16], d1, d2;
+                    rings(a, k1, p, k2, link, d1, rest, d2);
+                    const long long c = mid_dist2(L1[b], L2[p]) + mid_dist2(L2[q], L1[a]) + fan_cost(link, d1) + fan_cost(rest, d2);
+                    if (best_cost < 0 || c < best_cost) { best_cost = c; sel[0] = a; sel[1] = k1; sel[2] = p; sel[3] = k2; }
+                }
+    if (best_cost < 0) return false;
+    int link[16], rest[16], d1, d2;
+    rings(sel[0], sel[1], sel[2], sel[3], link, d1, rest, d2);
+    out = Triangulation();
+    for (int pass = 0; pass < 2; ++pass) {
+        const int* ring = pass ? rest : link;
+        const int d = pass ? d2 : d1, cid = c0 + pass;
+        if (cid >= MC_MAX_CEN || d > 12) { fprintf(stderr, "mc table overflow (tube centres)\n"); abort(); }
+        cen_n[cid] = (uint8_t)d;
+        for (int t = 0; t < d; ++t) cen_loop[cid][t] = (uint8_t)ring[t];
+        for (int t = 0; t < d; ++t) {
+            out.v[out.n][0] = (uint8_t)(12 + cid); out.v[out.n][1] = (uint8_t)ring[t]; out.v[out.n][2] = (uint8_t)ring[(t + 1) % d];
+            ++out.n;
+        }
+    }
+    ncen_used = 2;
+    return true;
+}
+
+// tiling of one configuration; tunnel >= 0 selects the annulus whose two loops are joined by a tube
+static void build_entry(const CellConfig& cc, int tunnel, McEntry& en) {
+    memset(&en, 0, sizeof(en));
+    int nt = 0, nc = 0;
+    const int ta = tunnel >= 0 ? cc.ann_loop[tunnel][0] : -1, tb = tunnel >= 0 ? cc.ann_loop[tunnel][1] : -1;
+    for (int l = 0; l < cc.nloop; ++l) {
+        if (l == tb) continue;
+        const int* poly = cc.loop[l];
+        const int n = cc.len[l];
+        if (l == ta) {
+            Triangulation t;
+            int used = 0;
+            if (!tube_between(cc.loop[ta], cc.len[ta], cc.loop[tb], cc.len[tb], nc, t, used, en.cen_n, en.cen_loop)) {
+                fprintf(stderr, "mc table: no tube tiling\n"); abort();
+            }
+            if (nt + t.n > MC_MAX_TRI) { fprintf(stderr, "mc table overflow (tube)\n"); abort(); }
+            for (int i = 0; i < t.n; ++i, ++nt)
+                for (int q = 0; q < 3; ++q) en.tri[nt * 3 + q] = t.v[i][q];
+            nc += used;
+            continue;
+        }
+        int tris[12][3];
+        const int k = triangulate_loop(poly, n, tris);
+        if (k > 0) {
+            if (nt + k > MC_MAX_TRI) { fprintf(stderr, "mc table overflow\n"); abort(); }
+            for (int t = 0; t < k; ++t, ++nt)
+                for (int q = 0; q < 3; ++q) en.tri[nt * 3 + q] = (uint8_t)tris[t][q];
+        } else {  // no diagonal-safe triangulation: fan around an extra centre vertex
+            if (nc >= MC_MAX_CEN || nt + n > MC_MAX_TRI) { fprintf(stderr, "mc table overflow\n"); abort(); }
+            en.cen_n[nc] = (uint8_t)n;
+            for (int i = 0; i < n; ++i) en.cen_loop[nc][i] = (uint8_t)poly[i];
+            for (int i = 0; i < n; ++i, ++nt) {
+                en.tri[nt * 3 + 0] = (uint8_t)(12 + nc);
+                en.tri[nt * 3 + 1] = (uint8_t)poly[i];
+                en.tri[nt * 3 + 2] = (uint8_t)poly[(i + 1) % n];
+            }
+            ++nc;
+        }
+    }
+    en.ncen = (uint8_t)nc;
+    en.ntri = (uint8_t)nt;
+    bool used[12 + MC_MAX_CEN] = {false};
+    int no = 0;
+    for (int t = 0; t < nt * 3; ++t)
+        if (!used[en.tri[t]]) { used[en.tri[t]] = true; en.order[no++] = en.tri[t]; }
+    en.nedge = (uint8_t)no;
+}
+
+struct McTables {
+    McEntry table[256 * 64];
+    McEntry tun_table[MC_MAX_TUN];
+    McTunDesc tun_desc[MC_MAX_TUN];
+    int16_t tun_index[256 * 64];
+    uint16_t edgemask[256];
+    uint8_t ambig[256];
+    int ntun = 0;
+};
+
+static void build_tables(McTables& T) {
+    T.ntun = 0;
+    memset(T.tun_table, 0, sizeof(T.tun_table));
+    memset(T.tun_desc, 0, sizeof(T.tun_desc));
     for (int idx = 0; idx < 256; ++idx) {
         uint16_t em = 0;
         for (int e = 0; e < 12; ++e)
             if (((idx >> h_edge_corner[e][0]) & 1) != ((idx >> h_edge_corner[e][1]) & 1)) em |= (uint16_t)(1u << e);
-        edgemask[idx] = em;
+        T.edgemask[idx] = em;
         uint8_t am = 0;
         for (int f = 0; f < 6; ++f) {
             int s[4];
             for (int i = 0; i < 4; ++i) s[i] = (idx >> h_face_corner[f][i]) & 1;
             if (s[0] == s[2] && s[1] == s[3] && s[0] != s[1]) am |= (uint8_t)(1u << f);
         }
-        ambig[idx] = am;
+        T.ambig[idx] = am;
         for (int fb = 0; fb < 64; ++fb) {
-            McEntry& en = table[idx * 64 + fb];
+            McEntry& en = T.table[idx * 64 + fb];
             memset(&en, 0, sizeof(en));
-            if (fb & ~am) continue;  // decision bits only exist for ambiguous faces
-            int succ[12];
-            for (int e = 0; e < 12; ++e) succ[e] = -1;
-            for (int f = 0; f < 6; ++f) {
-                int s[4], np = 0;
-                for (int i = 0; i < 4; ++i) { s[i] = (idx >> h_face_corner[f][i]) & 1; np += s[i]; }
-                if (np == 0 || np == 4) continue;
-                const int8_t* fe = h_face_edge[f];
-                if (!((am >> f) & 1)) {
-                    int i0 = -1, j0 = -1;  // positive run i0..j0 (ccw)
-                    for (int i = 0; i < 4; ++i) {
-                        if (s[i] && !s[(i + 3) & 3]) i0 = i;
-                        if (s[i] && !s[(i + 1) & 3]) j0 = i;
-                    }
-                    succ[fe[j0]] = fe[(i0 + 3) & 3];
-                } else if (!((fb >> f) & 1)) {  // positive corners separated
-                    for (int p = 0; p < 4; ++p)
-                        if (s[p]) succ[fe[p]] = fe[(p + 3) & 3];
-                } else {  // positive corners connected: the negative corners are cut off
-                    for (int n = 0; n < 4; ++n)
-                        if (!s[n]) succ[fe[(n + 3) & 3]] = fe[n];
-                }
+            T.tun_index[idx * 64 + fb] = -1;
+            if ((fb & ~am) || idx == 0 || idx == 255) continue;  // decision bits only exist for ambiguous faces
+            const CellConfig cc = analyse_config(idx, fb, am);
+            build_entry(cc, -1, en);
+            if (cc.nann == 0) continue;
+            if (T.ntun + cc.nann > MC_MAX_TUN) { fprintf(stderr, "mc table overflow (tunnel entries)\n"); abort(); }
+            T.tun_index[idx * 64 + fb] = (int16_t)T.ntun;
+            McTunDesc& d = T.tun_desc[T.ntun];
+            d.nann = (uint8_t)cc.nann;
+            for (int k = 0; k < cc.nann; ++k) {
+                d.npair[k] = (uint8_t)cc.ann_npair[k];
+                d.sigma[k] = ((idx >> cc.ann_pair[k][0][0]) & 1) ? 1 : -1;
+                for (int q = 0; q < cc.ann_npair[k]; ++q) sweep_columns(cc.ann_pair[k][q][0], cc.ann_pair[k][q][1], d.col[k][q]);
+                build_entry(cc, k, T.tun_table[T.ntun + k]);
             }
-            bool seen[12] = {false};
-            int nt = 0, nc = 0;
-            for (int e0 = 0; e0 < 12; ++e0) {
-                if (succ[e0] < 0 || seen[e0]) continue;
-                int poly[12], n = 0;
-                for (int e = e0; !seen[e]; e = succ[e]) { seen[e] = true; poly[n++] = e; }
-                int tris[12][3];
-                const int k = triangulate_loop(poly, n, tris);
-                if (k > 0) {
-                    for (int t = 0; t < k; ++t, ++nt)
-                        for (int q = 0; q < 3; ++q) en.tri[nt * 3 + q] = (uint8_t)tris[t][q];
-                } else {  // no diagonal-safe triangulation: fan around an extra centre vertex
-                    if (nc >= MC_MAX_CEN || nt + n > MC_MAX_TRI) { fprintf(stderr, "mc table overflow\n"); abort(); }
-                    en.cen_n[nc] = (uint8_t)n;
-                    for (int i = 0; i < n; ++i) en.cen_loop[nc][i] = (uint8_t)poly[i];
-                    for (int i = 0; i < n; ++i, ++nt) {
-                        en.tri[nt * 3 + 0] = (uint8_t)(12 + nc);
-                        en.tri[nt * 3 + 1] = (uint8_t)poly[i];
-                        en.tri[nt * 3 + 2] = (uint8_t)poly[(i + 1) % n];
-                    }
-                    ++nc;
-                }
-            }
-            en.ncen = (uint8_t)nc;
-            en.ntri = (uint8_t)nt;
-            bool used[12 + MC_MAX_CEN] = {false};
-            int no = 0;
-            for (int t = 0; t < nt * 3; ++t)
-                if (!used[en.tri[t]]) { used[en.tri[t]] = true; en.order[no++] = en.tri[t]; }
-            en.nedge = (uint8_t)no;
+            T.ntun += cc.nann;
         }
     }
 }
@@ -177,16 +480,17 @@ static int ensure_tables() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
     if (done[dev]) return 0;
-    static McEntry* table = nullptr;
-    static uint16_t edgemask[256];
-    static uint8_t ambig[256];
-    if (!table) {
-        table = new McEntry[256 * 64];
-        build_tables(table, edgemask, ambig);
+    static McTables* T = nullptr;
+    if (!T) {
+        T = new McTables();
+        build_tables(*T);
     }
-    if (cudaMemcpyToSymbol(d_mc_table, table, sizeof(McEntry) * 256 * 64) != cudaSuccess) return -1;
-    if (cudaMemcpyToSymbol(d_mc_edgemask, edgemask, sizeof(edgemask)) != cudaSuccess) return -1;
-    if (cudaMemcpyToSymbol(d_mc_ambig, ambig, sizeof(ambig)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(d_mc_table, T->table, sizeof(T->table)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(d_mc_tun_table, T->tun_table, sizeof(T->tun_table)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(d_mc_tun_desc, T->tun_desc, sizeof(T->tun_desc)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(d_mc_tun_index, T->tun_index, sizeof(T->tun_index)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(d_mc_edgemask, T->edgemask, sizeof(T->edgemask)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(d_mc_ambig, T->ambig, sizeof(T->ambig)) != cudaSuccess) return -1;
     done[dev] = true;
     return 0;
 }
@@ -305,6 +609,50 @@ __device__ __forceinline__ void block_exclusive_scan3(int a, int b, int c, int& 
     ta = (int)(tot & 0x1FFFFF); tb = (int)((tot >> 21) & 0x1FFFFF); tc = (int)(tot >> 42);
 }
 
+// cube code word: bits 0-7 cube index, 8-13 face decisions, 14-15 tunnel (0 none, k+1 = annulus k)
+__device__ __forceinline__ const McEntry& mc_entry(int code) {
+    const int key = (code & 255) * 64 + ((code >> 8) & 63);
+    const int tun = code >> 14;
+    return tun ? d_mc_tun_table[d_mc_tun_index[key] + tun - 1] : d_mc_table[key];
+}
+
+// Interior test of one corner pair (columns A0 A1 B0 B1 C0 C1 D0 D1 of the sweep, see build_tables): every operation
+// individually rounded in double (no FMA contraction), the same sequence as oracle/mc_oracle.c.
+#ifndef __CUDA_ARCH__   // host build of the same functions (gnb_mc_cell_tiling_host): x86-64 without -mfma never contracts
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+#endif
+__host__ __device__ __forceinline__ bool interior_joined(const float* val, float level, const uint8_t* col, double sigma) {
+    double c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = __dmul_rn(sigma, __dsub_rn((double)val[col[i]], (double)level));
+    const double a0 = c[0], b0 = c[2], c0 = c[4], d0 = c[6];
+    const double da = __dsub_rn(c[1], a0), db = __dsub_rn(c[3], b0), dc = __dsub_rn(c[5], c0), dd = __dsub_rn(c[7], d0);
+    const double a = __dsub_rn(__dmul_rn(da, dc), __dmul_rn(db, dd));
+    const double b = __dsub_rn(__dsub_rn(__dadd_rn(__dmul_rn(c0, da), __dmul_rn(a0, dc)), __dmul_rn(d0, db)), __dmul_rn(b0, dd));
+    if (!(a < 0.0)) return false;
+    const double t = __ddiv_rn(-b, __dmul_rn(2.0, a));
+    if (!(t > 0.0 && t < 1.0)) return false;
+    const double At = __dadd_rn(a0, __dmul_rn(da, t)), Bt = __dadd_rn(b0, __dmul_rn(db, t));
+    const double Ct = __dadd_rn(c0, __dmul_rn(dc, t)), Dt = __dadd_rn(d0, __dmul_rn(dd, t));
+    if (At < 0.0 || Ct < 0.0) return false;
+    if (Bt >= 0.0 || Dt >= 0.0) return true;
+    return __dsub_rn(__dmul_rn(At, Ct), __dmul_rn(Bt, Dt)) >= (double)FLT_EPSILON;
+}
+
+// face test of one ambiguous face given its four corner values (ccw): positive corners connected?
+__host__ __device__ __forceinline__ bool face_connected(float v0, float v1, float v2, float v3, float level) {
+    const double a = (double)v0 - (double)level, b = (double)v1 - (double)level;
+    const double cc = (double)v2 - (double)level, d = (double)v3 - (double)level;
+    // asymptotic decider with Lewiner's FLT_EPSILON band: connected iff (product of the positive pair) -
+    // (product of the negative pair) > -FLT_EPSILON; fp32 x fp32 products are exact in double.
+    const bool pos02 = a > 0.0;
+    const double pp = pos02 ? __dmul_rn(a, cc) : __dmul_rn(b, d), nn = pos02 ? __dmul_rn(b, d) : __dmul_rn(a, cc);
+    return __dsub_rn(pp, nn) > -(double)FLT_EPSILON;
+}
+
 // ---- kernel 1: classify --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MC_BLOCK)
 mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float level, McBatch batch) {
@@ -330,23 +678,26 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
 #pragma unroll
             for (int f = 0; f < 6; ++f) {
                 if ((am >> f) & 1) {
-                    const double a = (double)val[c_face_corner[f][0]] - (double)level;
-                    const double b = (double)val[c_face_corner[f][1]] - (double)level;
-                    const double cc = (double)val[c_face_corner[f][2]] - (double)level;
-                    const double d = (double)val[c_face_corner[f][3]] - (double)level;
-                    // asymptotic decider: positive corners are connected iff (product of the positive pair) >
-                    // (product of the negative pair); fp32 x fp32 products are exact in double.
-                    const bool pos02 = a > 0.0;
-                    const double pp = pos02 ? a * cc : b * d, nn = pos02 ? b * d : a * cc;
-                    if (pp > nn) fb |= 1u << f;
+                    if (face_connected(val[c_face_corner[f][0]], val[c_face_corner[f][1]], val[c_face_corner[f][2]],
+                                       val[c_face_corner[f][3]], level)) fb |= 1u << f;
                 }
             }
         }
-        ws.codes[c] = (uint16_t)(idx | (fb << 8));
+        unsigned tun = 0;
+        const int ti = (idx != 0 && idx != 255) ? d_mc_tun_index[idx * 64 + fb] : -1;
+        if (ti >= 0) {   // interior ambiguity (rare): first annulus whose regions are joined through the cell
+            const McTunDesc& td = d_mc_tun_desc[ti];
+            for (int k = 0; k < td.nann && tun == 0; ++k)
+                for (int q = 0; q < td.npair[k]; ++q)
+                    if (interior_joined(val, level, td.col[k][q], (double)td.sigma[k])) { tun = k + 1; break; }
+        }
+        const int code = idx | (fb << 8) | (tun << 14);
+        ws.codes[c] = (uint16_t)code;
         if (idx != 0 && idx != 255) {
+            const McEntry& en = mc_entry(code);
             na = 1;
-            nf = d_mc_table[idx * 64 + fb].ntri;
-            nv = __popc(d_mc_edgemask[idx] & owned_mask(p.z, p.y, p.x)) + d_mc_table[idx * 64 + fb].ncen;
+            nf = en.ntri;
+            nv = __popc(d_mc_edgemask[idx] & owned_mask(p.z, p.y, p.x)) + en.ncen;
         }
     }
     // block totals
@@ -446,8 +797,9 @@ mc_compact_kernel(int H, int W, McBatch batch) {
         if (idx != 0 && idx != 255) {
             const CellPos p = cell_pos(c, H, W);
             na = 1;
-            nf = d_mc_table[idx * 64 + (code >> 8)].ntri;
-            nv = __popc(d_mc_edgemask[idx] & owned_mask(p.z, p.y, p.x)) + d_mc_table[idx * 64 + (code >> 8)].ncen;
+            const McEntry& en = mc_entry(code);
+            nf = en.ntri;
+            nv = __popc(d_mc_edgemask[idx] & owned_mask(p.z, p.y, p.x)) + en.ncen;
         }
     }
     int ov, of, oa, tv, tf, ta;
@@ -520,7 +872,7 @@ mc_vertices_kernel(const float* __restrict__ vols, int D, int H, int W, float le
     const int code = act.w;
     const CellPos p = cell_pos(act.x, H, W);
     const unsigned own = d_mc_edgemask[code & 255] & owned_mask(p.z, p.y, p.x);
-    const McEntry& en = d_mc_table[(code & 255) * 64 + (code >> 8)];
+    const McEntry& en = mc_entry(code);
     if (own == 0 && en.ncen == 0) return;
     const int64_t vbase = ws.rec->vbase;
     int vid = act.y;
@@ -586,7 +938,7 @@ mc_faces_kernel(int D, int H, int W, int ascent, McBatch batch, int32_t* __restr
     if (a >= ws.rec->A) return;
     const int4 act = ws.active[a];
     const int code = act.w;
-    const McEntry& en = d_mc_table[(code & 255) * 64 + (code >> 8)];
+    const McEntry& en = mc_entry(code);
     const int nf = en.ntri;
     if (nf == 0) return;
     const CellPos p = cell_pos(act.x, H, W);
@@ -719,26 +1071,61 @@ int32_t gnb_mc_emit_batch(const float* v, int32_t N, int32_t D, int32_t H, int32
                       values, ggm_at_verts, as_stream(stream));
 }
 
+int32_t gnb_mc_cell_tiling_host(const float* corner_values, float level, int32_t* code_out, int32_t* ntri_out,
+                                uint8_t* tri_out, int32_t* nvert_out, uint8_t* order_out, int32_t* ncen_out, uint8_t* cen_n_out,
+                                uint8_t* cen_loop_out) {
+    GNB_REQUIRE(corner_values && code_out && ntri_out && tri_out && nvert_out && order_out, "gnb_mc_cell_tiling_host: null pointer");
+    static McTables* T = nullptr;
+    if (!T) { T = new McTables(); build_tables(*T); }
+    int idx = 0;
+    for (int i = 0; i < 8; ++i)
+        if (corner_values[i] > level) idx |= 1 << i;
+    unsigned fb = 0, tun = 0;
+    for (int f = 0; f < 6; ++f)
+        if ((T->ambig[idx] >> f) & 1)
+            if (face_connected(corner_values[h_face_corner[f][0]], corner_values[h_face_corner[f][1]],
+                               corner_values[h_face_corner[f][2]], corner_values[h_face_corner[f][3]], level)) fb |= 1u << f;
+    const int ti = (idx != 0 && idx != 255) ? T->tun_index[idx * 64 + fb] : -1;
+    if (ti >= 0) {
+        const McTunDesc& td = T->tun_desc[ti];
+        for (int k = 0; k < td.nann && tun == 0; ++k)
+            for (int q = 0; q < td.npair[k]; ++q)
+                if (interior_joined(corner_values, level, td.col[k][q], (double)td.sigma[k])) { tun = k + 1; break; }
+    }
+    const McEntry& en = tun ? T->tun_table[ti + tun - 1] : T->table[idx * 64 + fb];
+    *code_out = idx | (fb << 8) | (tun << 14);
+    *ntri_out = en.ntri;
+    memcpy(tri_out, en.tri, 3 * MC_MAX_TRI);
+    *nvert_out = en.nedge;
+    memcpy(order_out, en.order, 12 + MC_MAX_CEN);
+    if (ncen_out) *ncen_out = en.ncen;
+    if (cen_n_out) memcpy(cen_n_out, en.cen_n, MC_MAX_CEN);
+    if (cen_loop_out) memcpy(cen_loop_out, en.cen_loop, MC_MAX_CEN * 12);
+    return GNB_OK;
+}
+
 }  // extern "C"
 
 #ifdef GNB_MC_TABLE_MAIN
 // host-only self check of the generated tables: nvcc -DGNB_MC_TABLE_MAIN marching_cubes.cu capi.cu -o mctab
 int main() {
-    static gnb::McEntry table[256 * 64];
-    uint16_t em[256];
-    uint8_t am[256];
-    gnb::build_tables(table, em, am);
-    int max_tri = 0, max_cen = 0, with_cen = 0, valid = 0;
-    for (int idx = 0; idx < 256; ++idx)
+    static gnb::McTables T;
+    gnb::build_tables(T);
+    int max_tri = 0, max_cen = 0, with_cen = 0, valid = 0, tun_cfg = 0;
+    for (int idx = 1; idx < 255; ++idx)
         for (int fb = 0; fb < 64; ++fb) {
-            if (fb & ~am[idx]) continue;
-            const gnb::McEntry& e = table[idx * 64 + fb];
+            if (fb & ~T.ambig[idx]) continue;
+            const gnb::McEntry& e = T.table[idx * 64 + fb];
             ++valid;
             if (e.ntri > max_tri) max_tri = e.ntri;
             if (e.ncen > max_cen) max_cen = e.ncen;
             with_cen += e.ncen > 0;
+            tun_cfg += T.tun_index[idx * 64 + fb] >= 0;
         }
-    printf("entries %d max_tri %d max_cen %d entries_with_centre %d\n", valid, max_tri, max_cen, with_cen);
+    int tmax = 0;
+    for (int i = 0; i < T.ntun; ++i) if (T.tun_table[i].ntri > tmax) tmax = T.tun_table[i].ntri;
+    printf("entries %d max_tri %d max_cen %d entries_with_centre %d tunnel_configs %d tunnel_entries %d max_tunnel_tri %d\n", valid,
+           max_tri, max_cen, with_cen, tun_cfg, T.ntun, tmax);
     return 0;
 }
 #endif

@@ -411,7 +411,10 @@ def gaussian_gradient_magnitude(v: torch.Tensor, sigma: float) -> torch.Tensor:
 
 def marching_cubes(volume: torch.Tensor, level: float, spacing=(1.0, 1.0, 1.0), gradient_direction: str = "ascent",
                    ggm: Optional[torch.Tensor] = None):
-    """Device marching cubes (call shape of ``skimage.measure.marching_cubes``, ref predict.py:172-177).
+    """Device marching cubes (call shape of ``skimage.measure.marching_cubes``, ref predict.py:172-177): MC33 structure
+    (face test, interior test, tunnel tilings) with scikit-image's conventions.  PARITY UNPINNED vs scikit-image: triangle
+    order / vertex numbering inside a cell and the tunnel tilings can differ from its Lewiner tables (INTEGRATION.md
+    section 5), so per-vertex outputs are not index-compatible with a scikit-image run.
 
     Returns (verts f32[V,3], faces i32[F,3], normals f32[V,3], values f32[V], ggm_at_verts f32[V] or None), all on the
     device.  Raises ValueError if ``level`` is outside the data range and RuntimeError if no surface is found, like

@@ -136,7 +136,9 @@ def install(force: bool = False) -> None:
 
         def marching_cubes(volume, level=None, spacing=(1.0, 1.0, 1.0), gradient_direction="descent", step_size=1,
                            allow_degenerate=True, method="lewiner", mask=None):
-            """``skimage.measure.marching_cubes`` call shape on the device kernel (ref predict.py:172-177).
+            """``skimage.measure.marching_cubes`` call shape on the device kernel (ref predict.py:172-177).  Same MC33
+            structure and conventions as scikit-image's Lewiner implementation, NOT its exact tables: vertex / face
+            numbering can differ (parity unpinned).
             Accepts a CUDA tensor or a numpy array (copied to the current device); returns numpy arrays like skimage:
             float64 verts (float32 * float64 spacing), int32 faces, float32 normals / values."""
             import numpy as np

@@ -331,6 +331,16 @@ int32_t gnb_mc_emit_batch(const float* v, int32_t N, int32_t D, int32_t H, int32
                           int64_t max_active, float* verts, int32_t* faces, float* normals, float* values,
                           float* ggm_at_verts, void* stream);
 
+/* Host-side diagnostic (no device work): the tiling the kernels apply to ONE cell with the given eight corner values
+ * (corner i at (x,y,z) = {000,100,110,010,001,101,111,011}, scikit-image's numbering): cube index, face-test and
+ * interior-test decisions and the table entry they select.  code = index | face bits << 8 | tunnel << 14;
+ * tri u8[3*14] vertex ids (0..11 cube edges, 12.. extra centre vertices), order u8[14] the ids in first-use order,
+ * cen_n u8[2] / cen_loop u8[2*12] the cube edges whose iso-vertices a centre vertex averages.  Used by the CPU tests to
+ * compare every (code, decisions) configuration with the oracle without a GPU. */
+int32_t gnb_mc_cell_tiling_host(const float* corner_values, float level, int32_t* code_out, int32_t* ntri_out,
+                                uint8_t* tri_out, int32_t* nvert_out, uint8_t* order_out, int32_t* ncen_out,
+                                uint8_t* cen_n_out, uint8_t* cen_loop_out);
+
 /* ---- next row: mesh clean-up after marching cubes ----------------------
  * ref: common/marching_cubes_util.py:19-35 (inside wnf_to_mesh) and :38-52 (delete_invalid_verts); eval.py:532-546.
  * A face survives iff all three of its vertices are flagged in on_surface u8[V]; vertices no surviving face uses are

@@ -105,6 +105,54 @@ def test_mc_matches_oracle_bit_exact(dev, case, direction):
     assert np.abs(ggm_at.cpu().numpy() - ref["volume_gradient_magnitude"]).max() <= 1e-6
 
 
+def _heavy_noise(shape, seed):
+    """heavy-tailed signed noise: many body-diagonal configurations whose interior test says "tunnel"."""
+    rng = np.random.default_rng(seed)
+    return (rng.uniform(0.02, 1.0, shape) ** 3 * rng.choice([-1.0, 1.0], shape) + 0.5).astype(np.float32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 1])
+def test_mc33_tunnel_cells_match_oracle_bit_exact(dev, seed):
+    """MC33 interior test + tunnel tilings on the device: a field with hundreds of tunnel cells (4.1.2, 6.1.2, 7.4.2,
+    10.1.2, 12.1.2, 13.5.2 all occur), faces / vertices / normals / values bit-exact against the oracle."""
+    import ctypes
+    from garmentnets_b200 import ops
+    vol = _heavy_noise((40, 41, 43), seed)
+    ref = postproc.predict_tail(vol, 0.5, 0.5, "ascent")
+    lib = postproc._lib()
+    lib.mc_oracle_tunnel_cells.restype = ctypes.c_int64
+    assert int(lib.mc_oracle_tunnel_cells()) > 100
+    vt = torch.from_numpy(vol).to(dev)
+    verts, faces, normals, values, _ = ops.marching_cubes(vt, 0.5, (1 / 42,) * 3, "ascent")
+    assert np.array_equal(faces.cpu().numpy(), ref["faces"])
+    assert np.array_equal(verts.cpu().numpy(), ref["verts"])
+    assert np.array_equal(values.cpu().numpy(), ref["volume_value"])
+    assert np.array_equal(normals.cpu().numpy(), ref["normals"])
+
+
+@pytest.mark.gpu
+def test_mc_batch32_at_128_cubed_bit_exact(dev):
+    """BASELINE.json configs[2] size of the marching-cubes stage: 32 volumes of 128^3 in one batched call, every mesh
+    bit-exact against the oracle (smooth blobs + a noise component so that ambiguous / tunnel cells occur)."""
+    import scipy.ndimage as ni
+    from garmentnets_b200 import ops
+    rng = np.random.default_rng(11)
+    base = np.stack([_sphere(128, 0.55 + 0.01 * i) for i in range(4)])
+    vols = np.empty((32, 128, 128, 128), np.float32)
+    for i in range(32):
+        noise = ni.gaussian_filter(rng.normal(size=(128, 128, 128)).astype(np.float32), 1.0)
+        vols[i] = base[i % 4] + (0.6 + 0.1 * (i % 5)) * noise
+    vt = torch.from_numpy(vols).to(dev)
+    res = ops.marching_cubes_batch(vt, 0.5, (1 / 127,) * 3, "ascent", None)
+    for i in range(32):
+        v, f, n, val = postproc.marching_cubes(vols[i], 0.5, (1 / 127,) * 3, "ascent")
+        verts, faces, normals, values, _ = res[i]
+        assert np.array_equal(faces.cpu().numpy(), f), i
+        assert np.array_equal(verts.cpu().numpy(), v.astype(np.float32)), i
+        assert np.array_equal(values.cpu().numpy(), val), i
+
+
 @pytest.mark.gpu
 def test_mc_errors(dev):
     from garmentnets_b200 import ops
