@@ -131,10 +131,11 @@ def _cpu_setup(seed=0):
     return hp, sd, pos, rgb
 
 
-def _cpu_sample(hp, sd, pos, rgb, wnf_full=None, decode_rows=131072):
-    """One bounded sample of predict.py:138-187 on the host cores.  The dense decode is timed on `decode_rows` of the
-    2,097,152 lattice queries (a [32,64,64] half chunk by default) and scaled; ggm + marching cubes + surface decode
-    run on `wnf_full`.  Returns (seconds per volume, per-stage seconds)."""
+def _cpu_sample(hp, sd, pos, rgb, wnf_full=None, decode_rows=0):
+    """One sample (= one volume) of predict.py:138-187 on the host cores, nothing extrapolated by default: PointNet++,
+    gridding, UNet, the dense decode of all 2,097,152 lattice queries in the reference's 64^3 chunks, ggm + marching cubes
+    + surface decode on `wnf_full`.  `decode_rows` > 0 (opt-in, for quick smoke runs) times the decode on that many
+    queries and scales it.  Returns (seconds per volume, per-stage seconds)."""
     from oracle import nets as ON
     from oracle import pipeline as OP
     from oracle import postproc
@@ -146,18 +147,23 @@ def _cpu_sample(hp, sd, pos, rgb, wnf_full=None, decode_rows=131072):
     t1 = time.perf_counter()
     s2 = OP.stage2(sd, hp, s1, pos, batch, 1)
     t2 = time.perf_counter()
-    gp = ON.grid_points(Q)
-    nz = max(1, decode_rows // (64 * 64))
-    qpts = gp[:nz, :64, :64].reshape(1, -1, 3)
-    ON.implicit_decoder(sd, "volume_decoder.", s2["out_feature_volume"], qpts)
-    t3 = time.perf_counter()
-    decode = (t3 - t2) * (Q ** 3 / qpts.shape[1])
+    if decode_rows and decode_rows < Q ** 3:
+        gp = ON.grid_points(Q)
+        nz = max(1, decode_rows // (64 * 64))
+        qpts = gp[:nz, :64, :64].reshape(1, -1, 3)
+        ON.implicit_decoder(sd, "volume_decoder.", s2["out_feature_volume"], qpts)
+        t3 = time.perf_counter()
+        decode = (t3 - t2) * (Q ** 3 / qpts.shape[1])
+    else:
+        ON.dense_decode(sd, "volume_decoder.", s2["out_feature_volume"], Q, 64)   # predict.py:145-158, all 8 chunks
+        t3 = time.perf_counter()
+        decode = t3 - t2
     tail = postproc.predict_tail(wnf_full, pr["gradient_sigma"], pr["iso_surface_level"], pr["gradient_direction"])
     t4 = time.perf_counter()
     ON.implicit_decoder(sd, "surface_decoder.", s2["out_feature_volume"],
                         torch.from_numpy(tail["verts"].astype(np.float32)).view(1, -1, 3))
     t5 = time.perf_counter()
-    stages = {"pointnet2": t1 - t0, "unet3d": t2 - t1, "dense_decode_scaled": decode, "ggm_mc": t4 - t3,
+    stages = {"pointnet2": t1 - t0, "unet3d": t2 - t1, "dense_decode": decode, "ggm_mc": t4 - t3,
               "surface_decode": t5 - t4}
     return sum(stages.values()), stages
 
@@ -183,38 +189,164 @@ def _cpu_full_volume(hp, sd, pos, rgb, level=0.5, inside_fraction=0.12):
     return ((wnf - q) * scale + level).astype(np.float32)
 
 
+def _workload_config(B, world, V=None, F=None):
+    """`config` of the bench line -- shared by both arms (the reference arm times a bounded sample of this workload)."""
+    from garmentnets_b200 import synthetic
+    pr = synthetic.HPARAMS["prediction"]
+    cfg = {"workload": "BASELINE configs[2]: batch=32 full conv_implicit_wnf pipeline (PointNet++ + 32^3 "
+                       "gridding + 3D-UNet + dense 128^3 decode + ggm + marching cubes + surface decode)",
+           "batch_per_gpu": B, "points": N_POINTS, "unet_grid": 32, "volume_size": pr["volume_size"],
+           "category": "Tshirt", "l2": "flushed between timed iterations (256 MiB write)",
+           "parallelism": f"sample-sharded x{world}, no data-path collective"}
+    if V is not None:
+        cfg.update({"mean_verts": V, "mean_faces": F})
+    return cfg
+
+
+def _decode_sample_text(rows):
+    if rows and rows < 128 ** 3:
+        return f"dense decode timed on {rows} of 2097152 lattice queries and scaled (opt-in --cpu-decode-rows)"
+    return "dense decode of all 2097152 lattice queries (8 chunks of 64^3, as predict.py:145-158), nothing extrapolated"
+
+
 def run_reference(args, rank):
-    """`--impl reference`: the reference's CPU algorithm (oracle port) on the box's host cores, rank 0 only."""
+    """`--impl reference`: the reference's CPU algorithm (oracle port) on the box's host cores, rank 0 only.  A step is
+    ONE volume of the workload (predict.py is a batch-1 loop), run in full."""
     if rank != 0:
         return
-    t_setup = time.perf_counter()
+    t_start = time.perf_counter()
     hp, sd, pos, rgb = _cpu_setup()
     wnf = _cpu_full_volume(hp, sd, pos, rgb)
+    setup_s = time.perf_counter() - t_start
     cores = torch.get_num_threads()
     for _ in range(args.warmup):
         _cpu_sample(hp, sd, pos, rgb, wnf, args.cpu_decode_rows)
     secs = []
+    t_timed = time.perf_counter()
     for _ in range(args.steps):
         s, stages = _cpu_sample(hp, sd, pos, rgb, wnf, args.cpu_decode_rows)
         secs.append(s)
+    timed_wall = time.perf_counter() - t_timed
     per_volume = float(np.mean(secs))
     value = 1.0 / per_volume
-    sample = (f"1 synthetic Tshirt cloud (4096 pts) per step: PointNet++ + gridding + 3D-UNet(32^3) in full, dense decode "
-              f"timed on {args.cpu_decode_rows} of 2097152 lattice queries and scaled, ggm + marching cubes + surface "
-              f"decode on a full 128^3 volume")
+    sample = (f"one step = 1 of the workload's 32 synthetic Tshirt clouds (4096 pts) through the whole path: PointNet++ + "
+              f"gridding + 3D-UNet(32^3), {_decode_sample_text(args.cpu_decode_rows)}, ggm + marching cubes + surface "
+              f"decode on the full 128^3 volume")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_volume * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "full conv_implicit_wnf pipeline per volume (CPU oracle port of predict.py:138-187)",
-                       "points": N_POINTS, "unet_grid": 32, "volume_size": 128},
+            "config": _workload_config(args.batch, max(args.gpus, 1)),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "stages_s": {k: round(v, 4) for k, v in stages.items()}},
+                             "volumes_per_step": 1, "stages_s": {k: round(v, 4) for k, v in stages.items()}},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "setup_s": round(time.perf_counter() - t_setup - sum(secs), 1)}
+            "gpu_launches": 0, "setup_s": round(setup_s, 1), "timed_wall_s": round(timed_wall, 1),
+            "note": "reference = CPU oracle port of predict.py:138-187 (the reference's own third-party binaries are not "
+                    "installable offline, DESIGN.md section 7); a reported baseline, not the optimisation target"}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def _timed_steps(fn, steps, flush):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s, e in ev:
+        flush.fill_(1)
+        s.record()
+        fn()
+        e.record()
+    torch.cuda.synchronize()
+    return sum(s.elapsed_time(e) for s, e in ev)
+
+
+def _category_sweep(args, model, dev, rank, world, B, flush, step_kwargs, dist):
+    """BASELINE.json configs[4]: six-category sweep, per-category volumes/s (same weights, same batch size per GPU; the
+    category generators differ in extent and aspect, i.e. in neighbour counts, occupied voxels and mesh size)."""
+    if args.category != "all":
+        return None
+    from garmentnets_b200 import synthetic
+    from garmentnets_b200.pipeline import Batch
+    out, steps = {}, max(1, min(args.steps, 3))
+    for cat in synthetic.CATEGORIES:
+        d = synthetic.make_batch(B, N_POINTS, cat, seed=300 + rank)
+        data = Batch(x=torch.from_numpy(d["x"]).to(dev), pos=torch.from_numpy(d["pos"]).to(dev),
+                     batch=torch.from_numpy(d["batch"]).to(dev))
+        try:
+            res = model.predict(data, **step_kwargs)   # warm-up (allocator, caches)
+            torch.cuda.synchronize()
+            ms = _timed_steps(lambda: model.predict(data, **step_kwargs), steps, flush)
+            verts = float(np.mean([len(r["verts"]) for r in res]))
+            err = None
+        except Exception as ex:   # e.g. skimage's "No surface found" for a category the synthetic level calibration misses
+            ms, verts, err = float("nan"), 0.0, f"{type(ex).__name__}: {ex}"
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out[cat] = {"value": (world * B * steps / (ms / 1e3)) if ms == ms else None, "unit": UNIT,
+                    "ms_per_step": ms / steps if ms == ms else None, "steps": steps, "mean_verts": verts, "error": err}
+    return out
+
+
+def _gather_meshes_leg(args, model, dev, world, B, flush, step_resident, dist):
+    """BASELINE.json configs[3]: the sharded pipeline followed by an NCCL gather of every rank's meshes (packed verts /
+    warp field / faces of the whole batch: one small and two large all_gather_into_tensor).  Device-timed, max over
+    ranks; reported next to the headline (which has no data-path collective)."""
+    if args.no_gather_meshes:
+        return None
+    from garmentnets_b200 import dist as gd
+    nbytes = [0]
+
+    def step():
+        step_resident()
+        pk = model._last_packed
+        nbytes[0] = gd.gather_packed(pk, pk["warp_field"], pk["vptr"], pk["fptr"])["bytes"]
+
+    step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, 5))
+    ms = _timed_steps(step, steps, flush)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"value": world * B * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "gathered_bytes_per_rank_per_step": nbytes[0],
+            "collective": "NCCL all_gather_into_tensor x3 (offsets i64, verts|warp f32[Vmax,6], faces i32[Fmax,3])",
+            "workload": f"BASELINE configs[3]: batch={world * B} full pipeline sharded over {world} GPUs + gather of meshes"}
+
+
+def _unet_g128_report(model, dev, peaks, B=2):
+    """the 3D-UNet at grid_shape 128^3 (a constructor parameter of the reference,
+    networks/conv_implicit_wnf.py:29,38; the shipped configuration is 32^3) reported separately: same weights, B volumes
+    of 128^3 x 128 channels with 4096 occupied voxels each.  Algorithmic work = 64x the 32^3 figures per volume."""
+    try:
+        from garmentnets_b200 import ops
+        unet = model.unet_3d.abstract_3d_unet
+        g = torch.Generator(device="cpu").manual_seed(0)
+        x = torch.zeros((B, 128, 128, 128, 128), dtype=torch.float32, device=dev)   # NDHWC, 1 GiB per volume
+        for b in range(B):
+            idx = torch.randint(0, 128 ** 3, (N_POINTS,), generator=g).to(dev)
+            x[b].view(-1, 128)[idx] = torch.randn(N_POINTS, 128, generator=g).to(dev)
+        unet.forward_ndhwc(x, apply_final=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = unet.forward_ndhwc(x, apply_final=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        del x, y
+        torch.cuda.empty_cache()
+        gbs = (111.968e6 * 64 * B + 18.5e6) / (ms * 1e-3) / 1e9
+        tf = 50.38e9 * 64 * B / (ms * 1e-3) / 1e12
+        return {"grid": 128, "batch": B, "ms": round(ms, 3), "volumes_per_s": round(B / (ms * 1e-3), 2),
+                "hbm_gbs_algorithmic": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4),
+                "tflops_algorithmic": round(tf, 1), "frac_of_bf16_sustained": round(tf / peaks["bf16_tflops_sustained"], 4),
+                "executed_tensor_frac": round(3 * tf / peaks["bf16_tflops_sustained"], 4)}
+    except Exception as ex:
+        torch.cuda.empty_cache()
+        return {"grid": 128, "error": f"{type(ex).__name__}: {ex}"}
+
+
 def run_ours(args, rank, world):
     import torch.distributed as dist
     from garmentnets_b200 import _lib, profiling, synthetic
@@ -236,10 +368,11 @@ def run_ours(args, rank, world):
     synthetic.prepare_model_(model, data, index)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    step_kwargs = dict(volume_size=pr["volume_size"], gradient_sigma=pr["gradient_sigma"],
+                       iso_surface_level=pr["iso_surface_level"], gradient_direction=pr["gradient_direction"], index=index)
+
     def step_resident():
-        return model.predict(data, volume_size=pr["volume_size"], gradient_sigma=pr["gradient_sigma"],
-                             iso_surface_level=pr["iso_surface_level"], gradient_direction=pr["gradient_direction"],
-                             index=index)
+        return model.predict(data, **step_kwargs)
 
     from garmentnets_b200.pipeline import HostPredictor
     host_api = HostPredictor(model, depth=2, volume_size=pr["volume_size"], gradient_sigma=pr["gradient_sigma"],
@@ -318,13 +451,11 @@ def run_ours(args, rank, world):
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = stats.tolist()
-    if rank != 0:
-        return
+    peaks = _peaks()
     ms_per_step = total_ms / args.steps
     value = world * B * args.steps / (total_ms / 1e3)
     e2e_value = world * B * e2e_steps / (e2e_ms / 1e3)
 
-    peaks = _peaks()
     n_k, ms_k = ksum.get("decode_tc", (0, 0.0))
     # one event pair per gnb_decode_tc call (it brackets fold_tail, ~2 us, and the decode kernel)
     queries_per_launch = (B * args.steps * pr["volume_size"] ** 3) / max(n_k, 1)
@@ -349,6 +480,10 @@ def run_ours(args, rank, world):
                 "note": "achieved counts ALGORITHMIC fp32 FLOPs; the tensor pipe executes 3 fp16 MMAs per product "
                         "(hi*hi + lo*hi + hi*lo) to stay within the 1e-4 fp32 parity bound"}
 
+    per_category = _category_sweep(args, model, dev, rank, world, B, flush, step_kwargs, dist if world > 1 else None)
+    gather = _gather_meshes_leg(args, model, dev, world, B, flush, step_resident, dist) if world > 1 else None
+    unet_g128 = _unet_g128_report(model, dev, peaks) if (world == 1 and not args.no_unet_g128) else None
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         # bounded CPU sample of the same workload; marching cubes runs on a GPU-produced volume of sample 0
@@ -359,24 +494,22 @@ def run_ours(args, rank, world):
         _cpu_sample(hp_c, sd_c, pos_c, rgb_c, wnf0, args.cpu_decode_rows)
         secs, stages = _cpu_sample(hp_c, sd_c, pos_c, rgb_c, wnf0, args.cpu_decode_rows)
         cpu_baseline = {"value": 1.0 / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"1 cloud: PointNet++/gridding/UNet in full, dense decode on {args.cpu_decode_rows} of "
-                                  f"2097152 queries scaled, ggm+MC+surface decode on a full 128^3 volume",
+                        "sample": f"1 cloud through the whole path: PointNet++/gridding/UNet in full, "
+                                  f"{_decode_sample_text(args.cpu_decode_rows)}, ggm+MC+surface decode on a full 128^3 volume",
                         "stages_s": {k: round(v, 4) for k, v in stages.items()}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2]: batch=32 full conv_implicit_wnf pipeline (PointNet++ + 32^3 "
-                                   "gridding + 3D-UNet + dense 128^3 decode + ggm + marching cubes + surface decode)",
-                       "batch_per_gpu": B, "points": N_POINTS, "unet_grid": 32, "volume_size": pr["volume_size"],
-                       "mean_verts": V, "mean_faces": F, "l2": "flushed between timed iterations (256 MiB write)",
-                       "parallelism": f"sample-sharded x{world}, no data-path collective"},
+            "config": _workload_config(B, world, V, F),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "wall_s": round(wall, 3), "stages_ms": stages_ms,
-            "unet3d": _unet_report(stages_ms.get("unet3d"), B, peaks)}
-    print(json.dumps(line), flush=True)
+            "unet3d": _unet_report(stages_ms.get("unet3d"), B, peaks), "unet3d_g128": unet_g128,
+            "per_category": per_category, "gather_meshes": gather}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 def main():
@@ -386,8 +519,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="clouds per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-decode-rows", type=int, default=131072)
+    ap.add_argument("--cpu-decode-rows", type=int, default=0,
+                    help="0 = the full 2,097,152-query decode (default); >0 = time that many queries and scale (smoke runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--category", default="all", choices=["all", "Tshirt"],
+                    help="all: add the six-category sweep of BASELINE configs[4] (a few short steps per category)")
+    ap.add_argument("--no-gather-meshes", action="store_true", help="skip the NCCL mesh gather leg (N > 1 only)")
+    ap.add_argument("--no-unet-g128", action="store_true", help="skip the 128^3 3D-UNet side report (N = 1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -76,3 +76,43 @@ def gather_meshes(meshes: Sequence[Dict[str, torch.Tensor]]) -> List[List[Dict[s
             lst.append({"verts": all_v[r][i, :V, :3], "warp_field": all_v[r][i, :V, 3:], "faces": all_f[r][i, :F]})
         out.append(lst)
     return out
+
+
+def _all_gather_rows(out: torch.Tensor, mine: torch.Tensor) -> None:
+    """out[r] = rank r's ``mine`` (same shape on every rank): one collective.  NCCL takes the stacked output tensor; gloo
+    (CPU tests) wants the flat form."""
+    dist.all_gather_into_tensor(out.view(-1), mine.reshape(-1))
+
+
+def gather_packed(packed: Dict[str, torch.Tensor], warp_field: torch.Tensor, vptr, fptr) -> Dict[str, object]:
+    """All-gather of the PACKED meshes of a whole batch (the layout ``ConvImplicitWNFPipeline.predict`` leaves on the
+    device: verts f32[sum V,3], faces i32[sum F,3] with per-sample local ids, warp_field f32[sum V,3], host row offsets
+    ``vptr`` / ``fptr`` i64[B+1]).  Three collectives for any batch size: the offsets of every rank (one small
+    all-gather, one host read to size the payloads), then ONE ``all_gather_into_tensor`` per dtype over buffers padded to
+    the largest rank (float32 [Vmax, 6] = verts | warp field, int32 [Fmax, 3]).  Returns ``{"vptr": [world][B+1],
+    "fptr": ..., "verts": [world] views, "warp_field": ..., "faces": ..., "bytes": payload bytes received}``.
+    BASELINE.json configs[3] ("NCCL gather of meshes")."""
+    world = dist.get_world_size()
+    dev = _device()
+    offs = torch.cat([torch.as_tensor(vptr, dtype=torch.int64), torch.as_tensor(fptr, dtype=torch.int64)]).to(dev)
+    all_offs = torch.empty((world, offs.numel()), dtype=torch.int64, device=dev)
+    _all_gather_rows(all_offs, offs)
+    all_offs = all_offs.cpu()
+    nb = len(vptr)
+    vtot, ftot = all_offs[:, nb - 1], all_offs[:, 2 * nb - 1]
+    vmax, fmax = int(vtot.max()), int(ftot.max())
+    V, F = int(vptr[-1]), int(fptr[-1])
+    vbuf = torch.empty((vmax, 6), dtype=torch.float32, device=dev)
+    fbuf = torch.empty((fmax, 3), dtype=torch.int32, device=dev)
+    vbuf[:V, :3] = packed["verts"].to(dev)
+    vbuf[:V, 3:] = warp_field.to(dev)
+    fbuf[:F] = packed["faces"].to(dev)
+    all_v = torch.empty((world, vmax, 6), dtype=torch.float32, device=dev)
+    all_f = torch.empty((world, fmax, 3), dtype=torch.int32, device=dev)
+    _all_gather_rows(all_v, vbuf)
+    _all_gather_rows(all_f, fbuf)
+    return {"vptr": [all_offs[r, :nb].numpy() for r in range(world)], "fptr": [all_offs[r, nb:].numpy() for r in range(world)],
+            "verts": [all_v[r, :int(vtot[r]), :3] for r in range(world)],
+            "warp_field": [all_v[r, :int(vtot[r]), 3:] for r in range(world)],
+            "faces": [all_f[r, :int(ftot[r])] for r in range(world)],
+            "bytes": int(all_v.numel() * 4 + all_f.numel() * 4 + all_offs.numel() * 8)}

@@ -34,6 +34,18 @@ def _worker(rank, world, port, q):
                            "faces": torch.randint(0, V, (F, 3), generator=g, dtype=torch.int32)})
         allm = gd.gather_meshes(meshes)
         ok = all(torch.equal(allm[rank][i][k], meshes[i][k]) for i in range(2) for k in ("verts", "faces", "warp_field"))
+        # packed form (what predict() leaves on the device): one payload per dtype for the whole batch
+        import numpy as np
+        vptr = np.concatenate([[0], np.cumsum([m["verts"].shape[0] for m in meshes])]).astype(np.int64)
+        fptr = np.concatenate([[0], np.cumsum([m["faces"].shape[0] for m in meshes])]).astype(np.int64)
+        packed = {"verts": torch.cat([m["verts"] for m in meshes]), "faces": torch.cat([m["faces"] for m in meshes])}
+        gp = gd.gather_packed(packed, torch.cat([m["warp_field"] for m in meshes]), vptr, fptr)
+        for r in range(world):
+            for i in range(2):
+                v0, v1, f0, f1 = gp["vptr"][r][i], gp["vptr"][r][i + 1], gp["fptr"][r][i], gp["fptr"][r][i + 1]
+                ok = ok and torch.equal(gp["verts"][r][v0:v1], allm[r][i]["verts"])
+                ok = ok and torch.equal(gp["warp_field"][r][v0:v1], allm[r][i]["warp_field"])
+                ok = ok and torch.equal(gp["faces"][r][f0:f1], allm[r][i]["faces"])
         shapes = [[tuple(m["verts"].shape) + tuple(m["faces"].shape) for m in lst] for lst in allm]
         q.put((rank, (lo, hi), summary, ok, shapes))
     finally:
