@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "../../include/garmentnets_b200.h"
 
 namespace gnb {
@@ -42,6 +43,36 @@ template <typename T>
 __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
 int sm_count();  // cached SM count of the current device (148 on B200)
+
+// Serialises the users of one __constant__ operand bank.  Three launch families (lattice decode, query / row decode,
+// Linear blocks) refresh a per-device constant array with a stream-ordered copy in front of every launch; on ONE stream
+// that is ordered by the stream itself.  A launch of the same family on ANOTHER stream (or from another host thread)
+// would overwrite the bank under a running kernel, so the guard (a) holds a host mutex from the copy to the launch and
+// (b) makes the new stream wait, on the device, for the event the previous user recorded after its kernel.  Same-stream
+// sequences pay one cudaEventRecord per launch; nothing is serialised on the host.
+enum ConstBank { BANK_LATTICE = 0, BANK_DECODE_TC = 1, BANK_LINEAR_TC = 2, BANK_COUNT = 3 };
+class ConstBankGuard {
+public:
+    ConstBankGuard(ConstBank bank, cudaStream_t st);
+    ~ConstBankGuard();
+    ConstBankGuard(const ConstBankGuard&) = delete;
+    ConstBankGuard& operator=(const ConstBankGuard&) = delete;
+private:
+    int bank_, dev_;
+    cudaStream_t st_;
+};
+
+// Debug / profiling knock-out switches of the tensor-core decoders (GNB_DL2_DBG, GNB_TC_DBG) exist only in builds with
+// -DGNB_PROFILE_KNOBS; the shipped library never reads the environment on the launch path.
+inline int profile_knob(const char* name) {
+#ifdef GNB_PROFILE_KNOBS
+    const char* e = getenv(name);
+    return e ? atoi(e) : 0;
+#else
+    (void)name;
+    return 0;
+#endif
+}
 
 // fp32 squared distance with every product and sum individually rounded (no FMA contraction), so the CPU
 // oracle (numpy float32) reproduces it bit for bit:  ((dx*dx + dy*dy) + dz*dz).

@@ -574,13 +574,15 @@ int32_t gnb_decode_lattice(const float* U, int32_t B, int32_t G, int32_t Q, cons
     dl2::lattice_prep_kernel<<<1 + Cout, dl2::N, 0, st>>>(W2, b2, bn1_shift, W3, b3, bn2_scale, bn2_shift, bn3_scale, bn3_shift,
                                                          Cout, ldexpf(1.0f, w2f_scale_log2), b2s, w3s, tail);
     // b2s (256 floats) and w3s (Cout x 256) are contiguous in the scratch: one stream-ordered copy into constant memory
+    // (guarded: another stream launching this family waits for this kernel before it refreshes the bank)
+    ConstBankGuard guard(BANK_LATTICE, st);
     GNB_CUDA(cudaMemcpyToSymbolAsync(dl2::c_epi, b2s, sizeof(float) * dl2::N * (1 + Cout), 0, cudaMemcpyDeviceToDevice, st));
     dl2::Params p;
     p.U = U; p.B = B; p.G = G; p.Q = Q;
     p.w2_packed = reinterpret_cast<const uint8_t*>(w2f_packed);
     p.b2s = b2s; p.w3s = w3s; p.tail = tail; p.out = out;
     p.num_pairs = (int64_t)B * Q * (Q / 2);
-    { const char* e = getenv("GNB_DL2_DBG"); p.dbg = e ? atoi(e) : 0; }
+    p.dbg = profile_knob("GNB_DL2_DBG");
     if (Cout == 1) return dl2::launch<1>(p, st);
     if (Cout == 2) return dl2::launch<2>(p, st);
     return dl2::launch<3>(p, st);

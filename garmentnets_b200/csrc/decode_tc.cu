@@ -705,6 +705,7 @@ int32_t gnb_decode_tc(const float* U, int64_t ldx, int32_t B, int32_t G, int32_t
     float* w3s = scratch;
     float* tail = scratch + 3 * TC_N;
     fold_tail_kernel<<<Cout, TC_N, 0, st>>>(W3, b3, bn2_scale, bn2_shift, bn3_scale, bn3_shift, Cout, w3s, tail);
+    ConstBankGuard guard(BANK_DECODE_TC, st);
     { const int32_t rc = upload_epilogue_constants(b2, w3s, Cout, st); if (rc != GNB_OK) return rc; }
     TcParams p;
     p.U = U; p.ldx = ldx; p.B = B; p.G = G; p.Q = Q; p.R = R;
@@ -740,6 +741,7 @@ int32_t gnb_decode_tc_query(const float* U, int32_t B, int32_t G, const float* q
     float* w3s = scratch;
     float* tail = scratch + 3 * TC_N;
     fold_tail_kernel<<<Cout, TC_N, 0, st>>>(W3, b3, bn2_scale, bn2_shift, bn3_scale, bn3_shift, Cout, w3s, tail);
+    ConstBankGuard guard(BANK_DECODE_TC, st);
     { const int32_t rc = upload_epilogue_constants(b2, w3s, Cout, st); if (rc != GNB_OK) return rc; }
     TcParams p;
     p.U = U; p.ldx = 0; p.B = B; p.G = G; p.Q = 0; p.R = R;
@@ -772,6 +774,7 @@ int32_t gnb_decode_tc_query_fused(const float* X, int32_t B, int32_t G, int32_t 
     float* w3s = scratch;
     float* tail = scratch + 3 * TC_N;
     fold_tail_kernel<<<Cout, TC_N, 0, st>>>(W3, b3, bn2_scale, bn2_shift, bn3_scale, bn3_shift, Cout, w3s, tail);
+    ConstBankGuard guard(BANK_DECODE_TC, st);
     { const int32_t rc = upload_epilogue_constants(b2, w3s, Cout, st); if (rc != GNB_OK) return rc; }
     TcParams p;
     p.U = X; p.ldx = 0; p.B = B; p.G = G; p.Q = 0; p.R = R;
@@ -781,7 +784,7 @@ int32_t gnb_decode_tc_query_fused(const float* X, int32_t B, int32_t G, int32_t 
     p.acc_scale = ldexpf(1.0f, -w2_scale_log2);
     p.num_tiles = ceil_div<int64_t>(R, TC_M);
     p.q = q; p.qptr = qptr; p.w1 = W1; p.b1 = b1;
-    { const char* e = getenv("GNB_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+    p.dbg = profile_knob("GNB_TC_DBG");
     if (Cout == 1) return launch_decode_tc<1, 3>(p, st);
     if (Cout == 2) return launch_decode_tc<2, 3>(p, st);
     return launch_decode_tc<3, 3>(p, st);

@@ -510,6 +510,7 @@ static int32_t linear_tc_launch(const float* X, int64_t R, int32_t K, int64_t ld
         p.use_tma = 1;
     }
     p.use_const = l.n_blocks * l.Npad <= LT_MAX_COLS ? 1 : 0;
+    ConstBankGuard guard(BANK_LINEAR_TC, as_stream(stream));   // the launch below reads c_lt
     if (p.use_const)
         GNB_CUDA(cudaMemcpyToSymbolAsync(c_lt, cparams, sizeof(float) * 3 * l.n_blocks * l.Npad, 0, cudaMemcpyDeviceToDevice, as_stream(stream)));
     const int smem = p.na * LT_A_STAGE + p.nb * l.piece_bytes + LT_EPI_WARPS * LT_STAGE_BYTES + 1024;

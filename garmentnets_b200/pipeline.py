@@ -191,8 +191,7 @@ class ImplicitWNFDecoder(nn.Module):
         affine map; cached per parameter version."""
         lin = self.mlp[0][0]
         wf = final_conv.weight.view(final_conv.out_channels, -1)
-        key = (lin.weight._version, lin.weight.data_ptr(), wf._version, wf.data_ptr(),
-               None if final_conv.bias is None else final_conv.bias._version)
+        key = ops._version_key(lin.weight, lin.bias, final_conv.weight, final_conv.bias)
         cached = getattr(self, "_gnb_folded", None)
         if cached is None or cached[0] != key:
             w = ops.linear(wf.t().contiguous(), lin.weight).t().contiguous()          # [C1, Cf] = W1 @ Wf
@@ -251,13 +250,20 @@ class ImplicitWNFDecoder(nn.Module):
         (a pageable copy would synchronise the stream and stall the launch queue)."""
         ring = getattr(self, "_gnb_qptr_ring", None)
         if ring is None:
-            ring = [[torch.empty(130, dtype=torch.int64, pin_memory=True) for _ in range(8)], 0]
+            ring = [[torch.empty(130, dtype=torch.int64, pin_memory=True) for _ in range(8)], 0, [None] * 8]
             self._gnb_qptr_ring = ring
-        buf = ring[0][ring[1] % len(ring[0])]
+        slot = ring[1] % len(ring[0])
+        buf = ring[0][slot]
         ring[1] += 1
+        if ring[2][slot] is not None:
+            ring[2][slot].synchronize()   # the asynchronous copy that last read this slot must have left the host buffer
         n = len(offsets)
         buf[:n] = torch.as_tensor(offsets, dtype=torch.int64)
-        return buf[:n].to(device, non_blocking=True)
+        out = buf[:n].to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        ring[2][slot] = ev
+        return out
 
     def fused_query_ready(self, x_ndhwc: torch.Tensor) -> bool:
         return (self.use_fused_query and self._tc_ready() and len(self.mlp[0]) > 2 and x_ndhwc.shape[-1] == 32

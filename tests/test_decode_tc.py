@@ -166,3 +166,32 @@ def test_pair_lattice_equals_first_generation(dev, G, B):
     got = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
     assert got.shape == (B, 128 ** 3, 1)
     assert (got - ref.view_as(got)).abs().max().item() < 2e-5
+
+
+@pytest.mark.gpu
+def test_two_streams_do_not_race_on_the_constant_operand_banks(dev):
+    """The decoders / Linear blocks keep their per-column epilogue operands in __constant__ banks refreshed in front of
+    every launch.  Two streams launching the same family with DIFFERENT operands (volume vs surface decoder, two Linear
+    blocks) must still each see their own: the library orders such launches on the device (ConstBankGuard)."""
+    from garmentnets_b200 import ops
+    dec_a, dec_b = _decoder(dev, 1, 31), _decoder(dev, 3, 32)
+    g = torch.Generator().manual_seed(1)
+    Xa = (torch.randn(60000, 256, generator=g) * 1.5).to(dev)
+    Xb = (torch.randn(50000, 256, generator=g) * 1.5).to(dev)
+    wa = ops.pack_linear_tc(dec_a.mlp[1][0].weight, dec_a.mlp[1][0].bias, *dec_a.mlp[1][2].folded_affine())
+    wb = ops.pack_linear_tc(dec_b.mlp[1][0].weight, dec_b.mlp[1][0].bias, *dec_b.mlp[1][2].folded_affine())
+    args_a, args_b = dec_a._tc_args(), dec_b._tc_args()
+    ref_a, ref_b = ops.decode_tc(*args_a, X=Xa), ops.decode_tc(*args_b, X=Xb)
+    lin_a, lin_b = ops.linear_tc(Xa, wa, relu=True), ops.linear_tc(Xb, wb, relu=True)
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(20):
+        with torch.cuda.stream(sa):
+            ya = ops.decode_tc(*args_a, X=Xa)
+            la = ops.linear_tc(Xa, wa, relu=True)
+        with torch.cuda.stream(sb):
+            yb = ops.decode_tc(*args_b, X=Xb)
+            lb = ops.linear_tc(Xb, wb, relu=True)
+        torch.cuda.synchronize()
+        assert torch.equal(ya, ref_a) and torch.equal(yb, ref_b)
+        assert torch.equal(la, lin_a) and torch.equal(lb, lin_b)

@@ -122,3 +122,43 @@ def test_cuda_unet_and_decoder_match_reference_fixtures(dev):
     assert np.abs(y.cpu().numpy() - z["y"]).max() < 1e-4
     ys = nocs_grid_sample(torch.from_numpy(z["fg"]).to(dev), torch.from_numpy(z["q"]).to(dev))
     assert np.abs(ys.cpu().numpy() - z["nocs_sampled"]).max() < 1e-5
+
+
+def _b2v_case():
+    z = np.load(os.path.join(G, "batch_to_volume.npz"))
+    return z
+
+
+def test_oracle_batch_to_volume_index_arithmetic_matches_reference():
+    """Row a9: the restated voxel-index arithmetic of ref components/gridding.py:18-27 against the reference function's
+    own outputs (occupancy pattern and values, all four reduce modes)."""
+    from oracle import pointops as P
+    z = _b2v_case()
+    Gs, B = int(z["G"]), int(z["B"])
+    ijk = np.clip((z["pos"] * np.float32(Gs)).astype(np.int64), 0, Gs - 1)
+    flat = z["batch"] * Gs ** 3 + ijk[:, 0] * Gs ** 2 + ijk[:, 1] * Gs + ijk[:, 2]
+    for reduce in ("mean", "max", "sum", "min"):
+        vol = P.scatter(z["x"].T, flat, B * Gs ** 3, reduce).reshape(-1, B, Gs, Gs, Gs).transpose(1, 0, 2, 3, 4)
+        assert np.array_equal(vol, z["vol_" + reduce]), reduce
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reduce", ["mean", "max", "sum", "min"])
+def test_cuda_batch_to_volume_matches_reference_function(dev, reduce):
+    """Row a9 on the device: ``components.gridding.batch_to_volume`` (same name / signature as the reference's) against
+    the reference function's own output."""
+    from garmentnets_b200.components.gridding import batch_to_volume
+    from garmentnets_b200.pipeline import Batch
+    z = _b2v_case()
+    batch = Batch(x=torch.from_numpy(z["x"]).to(dev), pos=torch.from_numpy(z["pos"]).to(dev),
+                  batch=torch.from_numpy(z["batch"]).to(dev))
+    batch.num_graphs = int(z["B"])
+    vol = batch_to_volume(batch, int(z["G"]), reduce=reduce)
+    ref = z["vol_" + reduce]
+    assert tuple(vol.shape) == ref.shape
+    got = vol.cpu().numpy()
+    assert np.array_equal(got == 0, ref == 0)
+    if reduce in ("max", "min"):
+        assert np.array_equal(got, ref)
+    else:
+        assert np.abs(got - ref).max() < 1e-5

