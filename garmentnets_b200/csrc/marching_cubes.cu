@@ -48,6 +48,8 @@ __device__ McEntry d_mc_table[256 * 64];
 __device__ McEntry d_mc_tun_table[MC_MAX_TUN];     // tunnel tilings: entry d_mc_tun_index[key] + annulus
 __device__ McTunDesc d_mc_tun_desc[MC_MAX_TUN];    // descriptor at d_mc_tun_index[key]
 __device__ int16_t d_mc_tun_index[256 * 64];       // -1: no interior ambiguity
+__device__ uint8_t d_mc_cnt[256 * 64];             // triangles | centre vertices << 4 of d_mc_table (1 byte instead of 86)
+__device__ uint8_t d_mc_tun_cnt[MC_MAX_TUN];
 __device__ uint16_t d_mc_edgemask[256];
 __device__ uint8_t d_mc_ambig[256];  // bit f set: face f is ambiguous for this cube index
 
@@ -489,6 +491,13 @@ static int ensure_tables() {
     if (cudaMemcpyToSymbol(d_mc_tun_table, T->tun_table, sizeof(T->tun_table)) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(d_mc_tun_desc, T->tun_desc, sizeof(T->tun_desc)) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(d_mc_tun_index, T->tun_index, sizeof(T->tun_index)) != cudaSuccess) return -1;
+    {
+        static uint8_t cnt[256 * 64], tcnt[MC_MAX_TUN];
+        for (int i = 0; i < 256 * 64; ++i) cnt[i] = (uint8_t)(T->table[i].ntri | (T->table[i].ncen << 4));
+        for (int i = 0; i < MC_MAX_TUN; ++i) tcnt[i] = (uint8_t)(T->tun_table[i].ntri | (T->tun_table[i].ncen << 4));
+        if (cudaMemcpyToSymbol(d_mc_cnt, cnt, sizeof(cnt)) != cudaSuccess) return -1;
+        if (cudaMemcpyToSymbol(d_mc_tun_cnt, tcnt, sizeof(tcnt)) != cudaSuccess) return -1;
+    }
     if (cudaMemcpyToSymbol(d_mc_edgemask, T->edgemask, sizeof(T->edgemask)) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(d_mc_ambig, T->ambig, sizeof(T->ambig)) != cudaSuccess) return -1;
     done[dev] = true;
@@ -497,7 +506,12 @@ static int ensure_tables() {
 
 // ---- workspace --------------------------------------------------------------------------------------------
 // One block of gnb_mc_workspace_bytes(D,H,W) bytes per volume (batch: N blocks `ws_stride` bytes apart).
-constexpr int MC_BLOCK = 256;
+// A cell is named by the voxel index of its lower corner, c = (z*H + y)*W + x ("padded" cell space: the cells with
+// x = W-1, y = H-1 or z = D-1 do not exist and stay inactive), so rows of cells are rows of the volume.
+// Work is cut into ITEMS = (volume row, 128-value segment): one warp classifies one item with four 16-byte loads per
+// lane (the rows y, y+1 of the slices z, z+1) and gets the x+1 corners of its last cell from the next lane by shuffle.
+// A count block = MC_WARPS consecutive items = a contiguous range of padded cells.
+constexpr int MC_WARPS = 8, MC_BLOCK = MC_WARPS * 32, MC_SEG = 128;
 struct McRec {          // 512-byte record, read back by the host in ONE copy for the whole batch
     int64_t V, F, A;    // vertices, faces, active cells (cube index not 0 / 255)
     int64_t vbase, fbase;  // first row of this volume in the concatenated vertex / face outputs of the batch
@@ -507,7 +521,7 @@ struct McRec {          // 512-byte record, read back by the host in ONE copy fo
 };
 static_assert(sizeof(McRec) == 512, "McRec layout");
 struct McWs {
-    uint16_t* codes;    // [ncells] cube index | face bits << 8
+    uint16_t* codes;    // [D*H*W] cube index | face bits << 8 | tunnel << 14 (0 for the padding cells)
     int32_t* blockV;    // [nb] per-block counts -> exclusive offsets after the scan
     int32_t* blockF;    // [nb]
     int32_t* blockA;    // [nb]
@@ -515,19 +529,21 @@ struct McWs {
     int4* active;       // [A] compacted active cells in scan order: {cell, first vertex id, first face id, code}
     int32_t* edge_map;  // [(3+MC_MAX_CEN)*D*H*W] global edge / cell centre -> vertex id
 };
-struct McGeom { int64_t ncells, nb; int64_t o_blockV, o_blockF, o_blockA, o_rec, o_active, o_edge, total; };
+struct McGeom { int64_t nvox, nseg, nitems, nb; int64_t o_blockV, o_blockF, o_blockA, o_rec, o_active, o_edge, total; };
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static McGeom geom(int D, int H, int W) {
     McGeom g;
-    g.ncells = (int64_t)(D - 1) * (H - 1) * (W - 1);
-    g.nb = ceil_div<int64_t>(g.ncells, MC_BLOCK);
-    size_t p = align256(sizeof(uint16_t) * g.ncells);
+    g.nvox = (int64_t)D * H * W;
+    g.nseg = ceil_div<int64_t>(W, MC_SEG);
+    g.nitems = (int64_t)D * H * g.nseg;
+    g.nb = ceil_div<int64_t>(g.nitems, MC_WARPS);
+    size_t p = align256(sizeof(uint16_t) * g.nvox);
     g.o_blockV = p; p += align256(sizeof(int32_t) * g.nb);
     g.o_blockF = p; p += align256(sizeof(int32_t) * g.nb);
     g.o_blockA = p; p += align256(sizeof(int32_t) * g.nb);
     g.o_rec = p; p += sizeof(McRec);
-    g.o_active = p; p += align256(sizeof(int4) * g.ncells);
-    g.o_edge = p; p += align256(sizeof(int32_t) * (3 + MC_MAX_CEN) * (size_t)D * H * W);
+    g.o_active = p; p += align256(sizeof(int4) * g.nvox);
+    g.o_edge = p; p += align256(sizeof(int32_t) * (3 + MC_MAX_CEN) * (size_t)g.nvox);
     g.total = p;
     return g;
 }
@@ -564,49 +580,19 @@ __device__ __forceinline__ unsigned owned_mask(int z, int y, int x) {
 }
 
 struct CellPos { int z, y, x; };
-__device__ __forceinline__ CellPos cell_pos(int64_t c, int H, int W) {
+__device__ __forceinline__ CellPos cell_pos(int64_t c, int H, int W) {   // c = (z*H + y)*W + x
     CellPos p;
     if (c < (1ll << 31)) {   // 32-bit divisions (a 128^3 volume has 2 M cells); the 64-bit ones are emulated and ~5x slower
-        const unsigned cu = (unsigned)c, wx = (unsigned)(W - 1), hy = (unsigned)(H - 1);
-        const unsigned row = cu / wx;
-        p.x = (int)(cu - row * wx);
-        const unsigned z = row / hy;
-        p.y = (int)(row - z * hy);
+        const unsigned cu = (unsigned)c, row = cu / (unsigned)W, z = row / (unsigned)H;
+        p.x = (int)(cu - row * (unsigned)W);
+        p.y = (int)(row - z * (unsigned)H);
         p.z = (int)z;
         return p;
     }
-    p.x = (int)(c % (W - 1));
-    p.y = (int)((c / (W - 1)) % (H - 1));
-    p.z = (int)(c / ((int64_t)(W - 1) * (H - 1)));
+    p.x = (int)(c % W);
+    p.y = (int)((c / W) % H);
+    p.z = (int)(c / ((int64_t)W * H));
     return p;
-}
-
-// exclusive scan of three small per-thread counts across the CTA (one pass: the counts are packed into one 64-bit word,
-// 21 bits each -- a CTA of 256 cells holds at most 256 * 14 vertices)
-__device__ __forceinline__ void block_exclusive_scan3(int a, int b, int c, int& oa, int& ob, int& oc, int& ta, int& tb,
-                                                      int& tc) {
-    __shared__ unsigned long long wsum[MC_BLOCK / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned long long v = (unsigned long long)a | ((unsigned long long)b << 21) | ((unsigned long long)c << 42);
-    unsigned long long incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    __syncthreads();  // protect wsum reuse across calls
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    unsigned long long base = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < MC_BLOCK / 32; ++w) {
-        const unsigned long long s = wsum[w];
-        if (w < warp) base += s;
-        tot += s;
-    }
-    const unsigned long long ex = base + incl - v;
-    oa = (int)(ex & 0x1FFFFF); ob = (int)((ex >> 21) & 0x1FFFFF); oc = (int)(ex >> 42);
-    ta = (int)(tot & 0x1FFFFF); tb = (int)((tot >> 21) & 0x1FFFFF); tc = (int)(tot >> 42);
 }
 
 // cube code word: bits 0-7 cube index, 8-13 face decisions, 14-15 tunnel (0 none, k+1 = annulus k)
@@ -614,6 +600,12 @@ __device__ __forceinline__ const McEntry& mc_entry(int code) {
     const int key = (code & 255) * 64 + ((code >> 8) & 63);
     const int tun = code >> 14;
     return tun ? d_mc_tun_table[d_mc_tun_index[key] + tun - 1] : d_mc_table[key];
+}
+// (triangles | centre vertices << 4) of a code word from the compact count tables
+__device__ __forceinline__ unsigned mc_counts(int code) {
+    const int key = (code & 255) * 64 + ((code >> 8) & 63);
+    const int tun = code >> 14;
+    return tun ? d_mc_tun_cnt[d_mc_tun_index[key] + tun - 1] : d_mc_cnt[key];
 }
 
 // Interior test of one corner pair (columns A0 A1 B0 B1 C0 C1 D0 D1 of the sweep, see build_tables): every operation
@@ -653,70 +645,157 @@ __host__ __device__ __forceinline__ bool face_connected(float v0, float v1, floa
     return __dsub_rn(pp, nn) > -(double)FLT_EPSILON;
 }
 
+// face / interior decisions of one ACTIVE cell (the rare slow path of the classifier); val[] in corner order
+__device__ __noinline__ int mc_resolve(const float* val, float level, int idx) {
+    unsigned fb = 0, tun = 0;
+    const unsigned am = d_mc_ambig[idx];
+    for (int f = 0; f < 6; ++f)
+        if ((am >> f) & 1)
+            if (face_connected(val[c_face_corner[f][0]], val[c_face_corner[f][1]], val[c_face_corner[f][2]],
+                               val[c_face_corner[f][3]], level)) fb |= 1u << f;
+    const int ti = d_mc_tun_index[idx * 64 + fb];
+    if (ti >= 0) {   // interior ambiguity: first annulus whose regions are joined through the cell
+        const McTunDesc& td = d_mc_tun_desc[ti];
+        for (int k = 0; k < td.nann && tun == 0; ++k)
+            for (int q = 0; q < td.npair[k]; ++q)
+                if (interior_joined(val, level, td.col[k][q], (double)td.sigma[k])) { tun = k + 1; break; }
+    }
+    return idx | (fb << 8) | (tun << 14);
+}
+
+// item -> (row = z*H + y, first x of the lane); returns false beyond the last item
+struct ItemPos { int z, y, x0; int64_t row; bool ok; };
+__device__ __forceinline__ ItemPos item_pos(int64_t item, int lane, int H, const McGeom& g) {
+    ItemPos p;
+    p.ok = item < g.nitems;
+    const int64_t it = p.ok ? item : 0;
+    p.row = it / g.nseg;
+    const int seg = (int)(it - p.row * g.nseg);
+    p.z = (int)(p.row / H);
+    p.y = (int)(p.row - (int64_t)p.z * H);
+    p.x0 = seg * MC_SEG + lane * 4;
+    return p;
+}
+
+// warp-inclusive scan of three small counts packed into one 64-bit word (21 bits each: a block holds 1024 cells with at
+// most 14 + 2 vertices / 14 faces each)
+__device__ __forceinline__ unsigned long long pack3(int a, int b, int c) {
+    return (unsigned long long)a | ((unsigned long long)b << 21) | ((unsigned long long)c << 42);
+}
+__device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
 // ---- kernel 1: classify --------------------------------------------------------------------------------------
+// VEC: W % 4 == 0 and a 16-byte aligned volume -> float4 loads and 8-byte code stores
+template <bool VEC>
 __global__ void __launch_bounds__(MC_BLOCK)
 mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float level, McBatch batch) {
     const McWs ws = carve(batch, blockIdx.y);
-    const float* __restrict__ v = vols + (int64_t)blockIdx.y * D * H * W;
-    const int64_t c = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
-    int nv = 0, nf = 0, na = 0;
+    const int64_t nvox = batch.g.nvox;
+    const float* __restrict__ v = vols + (int64_t)blockIdx.y * nvox;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const ItemPos ip = item_pos((int64_t)blockIdx.x * MC_WARPS + warp, lane, H, batch.g);
+    const bool row_ok = ip.ok && ip.z < D - 1 && ip.y < H - 1;
     float lo = INFINITY, hi = -INFINITY;
-    if (c < batch.g.ncells) {
-        const CellPos p = cell_pos(c, H, W);
-        float val[8];
-        int idx = 0;
+    int nv = 0, nf = 0, na = 0;
+    unsigned codes4[4] = {0u, 0u, 0u, 0u};
+    // a[r][k]: rows (z,y) (z,y+1) (z+1,y) (z+1,y+1), k = 0..3 own values, k = 4 the next lane's first value
+    float a[4][5];
+    if (row_ok) {
+        const float* __restrict__ r0 = v + ip.row * W;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            val[i] = v[((int64_t)(p.z + c_corner_dz[i]) * H + (p.y + c_corner_dy[i])) * W + (p.x + c_corner_dx[i])];
-            lo = fminf(lo, val[i]);
-            hi = fmaxf(hi, val[i]);
-            if (val[i] > level) idx |= 1 << i;   // == ((double)v - (double)level > 0): both operands are exact in double
+        for (int r = 0; r < 4; ++r) {
+            const float* __restrict__ p = r0 + (r & 1 ? W : 0) + (r & 2 ? (int64_t)H * W : 0);
+            if (VEC) {
+                if (ip.x0 + 3 < W) {
+                    const float4 q = *reinterpret_cast<const float4*>(p + ip.x0);
+                    a[r][0] = q.x; a[r][1] = q.y; a[r][2] = q.z; a[r][3] = q.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) a[r][k] = 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[r][k] = ip.x0 + k < W ? p[ip.x0 + k] : 0.f;
+            }
         }
-        unsigned fb = 0;
-        const unsigned am = d_mc_ambig[idx];
-        if (am) {
+    } else {
 #pragma unroll
-            for (int f = 0; f < 6; ++f) {
-                if ((am >> f) & 1) {
-                    if (face_connected(val[c_face_corner[f][0]], val[c_face_corner[f][1]], val[c_face_corner[f][2]],
-                                       val[c_face_corner[f][3]], level)) fb |= 1u << f;
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[r][k] = 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) a[r][4] = __shfl_down_sync(0xffffffffu, a[r][0], 1);
+    if (row_ok) {
+        if (lane == 31 && ip.x0 + 4 < W) {   // a wider row continues in the next segment: fetch its first value
+            const float* __restrict__ r0 = v + ip.row * W;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r][4] = r0[(r & 1 ? W : 0) + (r & 2 ? (int64_t)H * W : 0) + ip.x0 + 4];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int x = ip.x0 + k;
+            if (x < W) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { lo = fminf(lo, a[r][k]); hi = fmaxf(hi, a[r][k]); }
+            }
+            if (x < W - 1) {
+                // corner i at (dx,dy,dz): 0:000 1:100 2:110 3:010 4:001 5:101 6:111 7:011 ; rows: r = dy + 2 dz
+                const float val[8] = {a[0][k], a[0][k + 1], a[1][k + 1], a[1][k], a[2][k], a[2][k + 1], a[3][k + 1], a[3][k]};
+                int idx = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (val[i] > level) idx |= 1 << i;   // == ((double)v - (double)level > 0): both operands are exact in double
+                if (idx != 0 && idx != 255) {
+                    int code = idx;
+                    if (d_mc_ambig[idx] != 0 || d_mc_tun_index[idx * 64] >= 0) code = mc_resolve(val, level, idx);
+                    codes4[k] = (unsigned)code;
+                    const unsigned cnt = mc_counts(code);
+                    na += 1;
+                    nf += cnt & 15;
+                    nv += __popc(d_mc_edgemask[idx] & owned_mask(ip.z, ip.y, x)) + (cnt >> 4);
                 }
             }
         }
-        unsigned tun = 0;
-        const int ti = (idx != 0 && idx != 255) ? d_mc_tun_index[idx * 64 + fb] : -1;
-        if (ti >= 0) {   // interior ambiguity (rare): first annulus whose regions are joined through the cell
-            const McTunDesc& td = d_mc_tun_desc[ti];
-            for (int k = 0; k < td.nann && tun == 0; ++k)
-                for (int q = 0; q < td.npair[k]; ++q)
-                    if (interior_joined(val, level, td.col[k][q], (double)td.sigma[k])) { tun = k + 1; break; }
-        }
-        const int code = idx | (fb << 8) | (tun << 14);
-        ws.codes[c] = (uint16_t)code;
-        if (idx != 0 && idx != 255) {
-            const McEntry& en = mc_entry(code);
-            na = 1;
-            nf = en.ntri;
-            nv = __popc(d_mc_edgemask[idx] & owned_mask(p.z, p.y, p.x)) + en.ncen;
+    }
+    if (ip.ok) {   // code words of the lane's four cells (padding cells / rows: 0)
+        uint16_t* __restrict__ dst = ws.codes + ip.row * W + ip.x0;
+        if (VEC) {
+            if (ip.x0 + 3 < W)
+                *reinterpret_cast<uint2*>(dst) = make_uint2(codes4[0] | (codes4[1] << 16), codes4[2] | (codes4[3] << 16));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (ip.x0 + k < W) dst[k] = (uint16_t)codes4[k];
         }
     }
-    // block totals
-    int ov, of, oa, tv, tf, ta;
-    block_exclusive_scan3(nv, nf, na, ov, of, oa, tv, tf, ta);
-    if (threadIdx.x == 0) { ws.blockV[blockIdx.x] = tv; ws.blockF[blockIdx.x] = tf; ws.blockA[blockIdx.x] = ta; }
-    // min / max of the volume (every voxel is a corner of some cell when D,H,W >= 2): one atomic pair per CTA
-    __shared__ float s_lo[MC_BLOCK / 32], s_hi[MC_BLOCK / 32];
+    // block totals + data range
+    __shared__ unsigned long long s_cnt[MC_WARPS];
+    __shared__ float s_lo[MC_WARPS], s_hi[MC_WARPS];
+    unsigned long long tot = pack3(nv, nf, na);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
+        tot += __shfl_xor_sync(0xffffffffu, tot, o);
         lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
         hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    if (lane == 0) { s_cnt[warp] = tot; s_lo[warp] = lo; s_hi[warp] = hi; }
     __syncthreads();
     if (threadIdx.x == 0) {
+        unsigned long long t = 0;
 #pragma unroll
-        for (int w = 1; w < MC_BLOCK / 32; ++w) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
-        if (lo <= hi) {
+        for (int w = 0; w < MC_WARPS; ++w) { t += s_cnt[w]; lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
+        ws.blockV[blockIdx.x] = (int)(t & 0x1FFFFF);
+        ws.blockF[blockIdx.x] = (int)((t >> 21) & 0x1FFFFF);
+        ws.blockA[blockIdx.x] = (int)(t >> 42);
+        if (lo <= hi) {   // every voxel is a corner of some cell when D,H,W >= 2: one atomic pair per CTA
             atomicMin(&ws.rec->min_enc, mc_enc(lo));
             atomicMax(&ws.rec->max_enc, mc_enc(hi));
         }
@@ -781,30 +860,70 @@ __global__ void mc_bases_kernel(McBatch batch, int N) {
     }
 }
 
-// ---- kernel 3: compaction of the active cells (order preserving) -------------------------------------------------
+// ---- kernel 3: compaction of the active cells (order preserving) + the vertex work list ---------------------------
+// Same item mapping as the classifier.  Besides the active-cell records it leaves, in the (still unwritten) output row of
+// every vertex, the pair (cell, vertex slot) that the vertex kernel consumes: one thread per VERTEX there, no divergence
+// over cells that own 0..5 vertices.
 __global__ void __launch_bounds__(MC_BLOCK)
-mc_compact_kernel(int H, int W, McBatch batch) {
+mc_compact_kernel(int D, int H, int W, McBatch batch, float* __restrict__ verts) {
     const McWs ws = carve(batch, blockIdx.y);
     const int64_t nb = batch.g.nb;
     const int a0 = ws.blockA[blockIdx.x];
     const int a1 = blockIdx.x + 1 < nb ? ws.blockA[blockIdx.x + 1] : (int)ws.rec->A;
     if (a1 == a0) return;  // no active cell in this block (uniform branch)
-    const int64_t c = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
-    int nv = 0, nf = 0, na = 0, code = 0;
-    if (c < batch.g.ncells) {
-        code = ws.codes[c];
-        const int idx = code & 255;
-        if (idx != 0 && idx != 255) {
-            const CellPos p = cell_pos(c, H, W);
-            na = 1;
-            const McEntry& en = mc_entry(code);
-            nf = en.ntri;
-            nv = __popc(d_mc_edgemask[idx] & owned_mask(p.z, p.y, p.x)) + en.ncen;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const ItemPos ip = item_pos((int64_t)blockIdx.x * MC_WARPS + warp, lane, H, batch.g);
+    int code[4] = {0, 0, 0, 0}, cv[4] = {0, 0, 0, 0}, cf[4] = {0, 0, 0, 0};
+    int nv = 0, nf = 0, na = 0;
+    if (ip.ok) {
+        const uint16_t* __restrict__ src = ws.codes + ip.row * W + ip.x0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (ip.x0 + k < W - 1) code[k] = src[k];
+            const int idx = code[k] & 255;
+            if (idx != 0 && idx != 255) {
+                const unsigned cnt = mc_counts(code[k]);
+                cf[k] = cnt & 15;
+                cv[k] = __popc(d_mc_edgemask[idx] & owned_mask(ip.z, ip.y, ip.x0 + k)) + (cnt >> 4);
+                nv += cv[k]; nf += cf[k]; na += 1;
+            }
         }
     }
-    int ov, of, oa, tv, tf, ta;
-    block_exclusive_scan3(nv, nf, na, ov, of, oa, tv, tf, ta);
-    if (na) ws.active[a0 + oa] = make_int4((int)c, ws.blockV[blockIdx.x] + ov, ws.blockF[blockIdx.x] + of, code);
+    __shared__ unsigned long long s_w[MC_WARPS];
+    const unsigned long long mine = pack3(nv, nf, na);
+    const unsigned long long incl = warp_incl_scan(mine, lane);
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned long long base = 0;
+#pragma unroll
+    for (int w = 0; w < MC_WARPS; ++w)
+        if (w < warp) base += s_w[w];
+    const unsigned long long ex = base + incl - mine;
+    int ov = ws.blockV[blockIdx.x] + (int)(ex & 0x1FFFFF), of = ws.blockF[blockIdx.x] + (int)((ex >> 21) & 0x1FFFFF);
+    int oa = a0 + (int)(ex >> 42);
+    const int64_t vbase = ws.rec->vbase;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = code[k] & 255;
+        if (idx == 0 || idx == 255) continue;
+        const int x = ip.x0 + k;
+        const int cell = (int)(ip.row * W + x);
+        ws.active[oa] = make_int4(cell, ov, of, code[k]);
+        if (cv[k]) {   // vertex work list, in first-use order of the cell's tiling
+            const McEntry& en = mc_entry(code[k]);
+            const unsigned own = d_mc_edgemask[idx] & owned_mask(ip.z, ip.y, x);
+            int vid = ov;
+            for (int j = 0; j < en.nedge; ++j) {
+                const int e = en.order[j];
+                if (e < 12 && !((own >> e) & 1)) continue;
+                float* __restrict__ row = verts + (vbase + vid) * 3;
+                row[0] = __int_as_float(cell);
+                row[1] = __int_as_float(e);
+                ++vid;
+            }
+        }
+        ++oa; ov += cv[k]; of += cf[k];
+    }
 }
 
 // ---- kernel 4: vertices --------------------------------------------------------------------------------------
@@ -857,77 +976,67 @@ __device__ __forceinline__ void store_vertex(int64_t row, const float c[3], floa
     values[row] = val;
 }
 
-// one thread per ACTIVE cell (compacted list: no idle lanes on the ~95 % of cells the surface does not cross)
+// one thread per VERTEX (work list left in the vertex rows by the compaction kernel)
 __global__ void __launch_bounds__(MC_BLOCK)
 mc_vertices_kernel(const float* __restrict__ vols, int D, int H, int W, float level, Spacing sp,
                    const float* __restrict__ ggms, McBatch batch, float* __restrict__ verts, float* __restrict__ normals,
                    float* __restrict__ values, float* __restrict__ ggm_at) {
     const McWs ws = carve(batch, blockIdx.y);
-    const int64_t a = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
-    if (a >= ws.rec->A) return;
-    const int64_t vol_n = (int64_t)D * H * W;
+    const int64_t vid = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
+    if (vid >= ws.rec->V) return;
+    const int64_t vol_n = batch.g.nvox;
     const float* __restrict__ v = vols + (int64_t)blockIdx.y * vol_n;
     const float* __restrict__ ggm = ggms ? ggms + (int64_t)blockIdx.y * vol_n : nullptr;
-    const int4 act = ws.active[a];
-    const int code = act.w;
-    const CellPos p = cell_pos(act.x, H, W);
-    const unsigned own = d_mc_edgemask[code & 255] & owned_mask(p.z, p.y, p.x);
-    const McEntry& en = mc_entry(code);
-    if (own == 0 && en.ncen == 0) return;
-    const int64_t vbase = ws.rec->vbase;
-    int vid = act.y;
-    for (int k = 0; k < en.nedge; ++k) {
-        const int e = en.order[k];
-        if (e >= 12) {
-            // centre vertex of a loop: mean of the loop's vertices (double sum in loop order, float32 result)
-            const int ci = e - 12, n = en.cen_n[ci];
-            double acc[3] = {0.0, 0.0, 0.0};
-            for (int i = 0; i < n; ++i) {
-                float cc[3]; double t; int lo[3], hi[3];
-                edge_vertex(v, H, W, level, p, en.cen_loop[ci][i], cc, t, lo, hi);
-                acc[0] += (double)cc[0]; acc[1] += (double)cc[1]; acc[2] += (double)cc[2];
-            }
-            const float cc[3] = {(float)(acc[0] / (double)n), (float)(acc[1] / (double)n), (float)(acc[2] / (double)n)};
-            float val[8], vmax = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                val[i] = v[((int64_t)(p.z + c_corner_dz[i]) * H + (p.y + c_corner_dy[i])) * W + (p.x + c_corner_dx[i])];
-                vmax = fmaxf(vmax, val[i]);
-            }
-            // cell-centre gradient: mean of the four parallel edge differences per axis
-            float g[3];
-            g[0] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(val[4] - val[0], val[5] - val[1]), val[6] - val[2]), val[7] - val[3]), 0.25f);
-            g[1] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(val[3] - val[0], val[2] - val[1]), val[7] - val[4]), val[6] - val[5]), 0.25f);
-            g[2] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(val[1] - val[0], val[2] - val[3]), val[5] - val[4]), val[6] - val[7]), 0.25f);
-            store_vertex(vbase + vid, cc, g, vmax, sp, ggm, D, H, W, verts, normals, values, ggm_at);
-            ws.edge_map[(int64_t)(3 + ci) * vol_n + ((int64_t)p.z * H + p.y) * W + p.x] = vid;
-            ++vid;
-            continue;
+    const int64_t row = ws.rec->vbase + vid;
+    const int cell = __float_as_int(verts[row * 3 + 0]), e = __float_as_int(verts[row * 3 + 1]);
+    const CellPos p = cell_pos(cell, H, W);
+    if (e >= 12) {
+        // centre vertex of a loop / tube fan: mean of the listed iso-vertices (double sum in list order, float32 result)
+        const McEntry& en = mc_entry(ws.codes[cell]);
+        const int ci = e - 12, n = en.cen_n[ci];
+        double acc[3] = {0.0, 0.0, 0.0};
+        for (int i = 0; i < n; ++i) {
+            float cc[3]; double t; int lo[3], hi[3];
+            edge_vertex(v, H, W, level, p, en.cen_loop[ci][i], cc, t, lo, hi);
+            acc[0] += (double)cc[0]; acc[1] += (double)cc[1]; acc[2] += (double)cc[2];
         }
-        if (!((own >> e) & 1)) continue;
-        const int ax = c_edge_axis[e];
-        float cc[3]; double t; int lo[3], hi[3];
-        edge_vertex(v, H, W, level, p, e, cc, t, lo, hi);
-        // values: max of the data over the cells that share the edge (local maximum near the vertex)
-        float vmax = -INFINITY;
-        for (int dz = (ax == 2 ? 0 : -1); dz <= 1; ++dz)
-            for (int dy = (ax == 1 ? 0 : -1); dy <= 1; ++dy)
-                for (int dx = (ax == 0 ? 0 : -1); dx <= 1; ++dx)
-                    vmax = fmaxf(vmax, vol_at(v, D, H, W, lo[0] + dz, lo[1] + dy, lo[2] + dx));
-        // normals: central-difference gradient at the two end points, blended with t, normalised
+        const float cc[3] = {(float)(acc[0] / (double)n), (float)(acc[1] / (double)n), (float)(acc[2] / (double)n)};
+        float val[8], vmax = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            val[i] = v[((int64_t)(p.z + c_corner_dz[i]) * H + (p.y + c_corner_dy[i])) * W + (p.x + c_corner_dx[i])];
+            vmax = fmaxf(vmax, val[i]);
+        }
+        // cell-centre gradient: mean of the four parallel edge differences per axis
         float g[3];
-        const float tt = (float)t;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const int dz = q == 0, dy = q == 1, dx = q == 2;
-            const float g0 = vol_at(v, D, H, W, lo[0] + dz, lo[1] + dy, lo[2] + dx) - vol_at(v, D, H, W, lo[0] - dz, lo[1] - dy, lo[2] - dx);
-            const float g1 = vol_at(v, D, H, W, hi[0] + dz, hi[1] + dy, hi[2] + dx) - vol_at(v, D, H, W, hi[0] - dz, hi[1] - dy, hi[2] - dx);
-            g[q] = __fadd_rn(__fmul_rn(g0, 1.0f - tt), __fmul_rn(g1, tt));
-        }
-        store_vertex(vbase + vid, cc, g, vmax, sp, ggm, D, H, W, verts, normals, values, ggm_at);
-        ws.edge_map[(int64_t)ax * vol_n + ((int64_t)lo[0] * H + lo[1]) * W + lo[2]] = vid;
-        ++vid;
+        g[0] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(val[4] - val[0], val[5] - val[1]), val[6] - val[2]), val[7] - val[3]), 0.25f);
+        g[1] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(val[3] - val[0], val[2] - val[1]), val[7] - val[4]), val[6] - val[5]), 0.25f);
+        g[2] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(val[1] - val[0], val[2] - val[3]), val[5] - val[4]), val[6] - val[7]), 0.25f);
+        store_vertex(row, cc, g, vmax, sp, ggm, D, H, W, verts, normals, values, ggm_at);
+        ws.edge_map[(int64_t)(3 + ci) * vol_n + cell] = (int)vid;
+        return;
     }
+    const int ax = c_edge_axis[e];
+    float cc[3]; double t; int lo[3], hi[3];
+    edge_vertex(v, H, W, level, p, e, cc, t, lo, hi);
+    // values: max of the data over the cells that share the edge (local maximum near the vertex)
+    float vmax = -INFINITY;
+    for (int dz = (ax == 2 ? 0 : -1); dz <= 1; ++dz)
+        for (int dy = (ax == 1 ? 0 : -1); dy <= 1; ++dy)
+            for (int dx = (ax == 0 ? 0 : -1); dx <= 1; ++dx)
+                vmax = fmaxf(vmax, vol_at(v, D, H, W, lo[0] + dz, lo[1] + dy, lo[2] + dx));
+    // normals: central-difference gradient at the two end points, blended with t, normalised
+    float g[3];
+    const float tt = (float)t;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int dz = q == 0, dy = q == 1, dx = q == 2;
+        const float g0 = vol_at(v, D, H, W, lo[0] + dz, lo[1] + dy, lo[2] + dx) - vol_at(v, D, H, W, lo[0] - dz, lo[1] - dy, lo[2] - dx);
+        const float g1 = vol_at(v, D, H, W, hi[0] + dz, hi[1] + dy, hi[2] + dx) - vol_at(v, D, H, W, hi[0] - dz, hi[1] - dy, hi[2] - dx);
+        g[q] = __fadd_rn(__fmul_rn(g0, 1.0f - tt), __fmul_rn(g1, tt));
+    }
+    store_vertex(row, cc, g, vmax, sp, ggm, D, H, W, verts, normals, values, ggm_at);
+    ws.edge_map[(int64_t)ax * vol_n + ((int64_t)lo[0] * H + lo[1]) * W + lo[2]] = (int)vid;
 }
 
 // ---- kernel 5: faces -------------------------------------------------------------------------------------------
@@ -942,14 +1051,14 @@ mc_faces_kernel(int D, int H, int W, int ascent, McBatch batch, int32_t* __restr
     const int nf = en.ntri;
     if (nf == 0) return;
     const CellPos p = cell_pos(act.x, H, W);
-    const int64_t vol_n = (int64_t)D * H * W;
+    const int64_t vol_n = batch.g.nvox;
     int32_t vid[12 + MC_MAX_CEN];
 #pragma unroll
     for (int e = 0; e < 12 + MC_MAX_CEN; ++e) vid[e] = -1;
     for (int k = 0; k < en.nedge; ++k) {
         const int e = en.order[k];
         if (e >= 12) {
-            vid[e] = ws.edge_map[(int64_t)(3 + (e - 12)) * vol_n + ((int64_t)p.z * H + p.y) * W + p.x];
+            vid[e] = ws.edge_map[(int64_t)(3 + (e - 12)) * vol_n + act.x];
         } else {
             const int z0 = p.z + c_edge_dz[e], y0 = p.y + c_edge_dy[e], x0 = p.x + c_edge_dx[e];
             vid[e] = ws.edge_map[(int64_t)c_edge_axis[e] * vol_n + ((int64_t)z0 * H + y0) * W + x0];
@@ -980,23 +1089,27 @@ static int32_t count_batch(const float* v, int N, int D, int H, int W, float lev
     if (ensure_tables() != 0) { set_error("gnb_mc_count: table upload failed"); return GNB_ERR_CUDA; }
     McBatch b = {reinterpret_cast<char*>(ws_), ws_stride, geom(D, H, W)};
     mc_init_kernel<<<ceil_div(N, 128), 128, 0, st>>>(b, N);
-    mc_classify_kernel<<<dim3((unsigned)b.g.nb, N), MC_BLOCK, 0, st>>>(v, D, H, W, level, b);
+    const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0) && ((reinterpret_cast<uintptr_t>(ws_) & 7) == 0) &&
+                     (ws_stride % 8 == 0);
+    const dim3 grid((unsigned)b.g.nb, N);
+    if (vec) mc_classify_kernel<true><<<grid, MC_BLOCK, 0, st>>>(v, D, H, W, level, b);
+    else mc_classify_kernel<false><<<grid, MC_BLOCK, 0, st>>>(v, D, H, W, level, b);
     mc_scan_kernel<<<N, 1024, 0, st>>>(b);
     mc_bases_kernel<<<1, 32, 0, st>>>(b, N);
-    mc_compact_kernel<<<dim3((unsigned)b.g.nb, N), MC_BLOCK, 0, st>>>(H, W, b);
     return check_launch("gnb_mc_count");
 }
 
 static int32_t emit_batch(const float* v, int N, int D, int H, int W, float level, const double* spacing_host,
-                          int ascent, const float* ggm, void* ws_, int64_t ws_stride, int64_t max_active, float* verts,
-                          int32_t* faces, float* normals, float* values, float* ggm_at, cudaStream_t st) {
+                          int ascent, const float* ggm, void* ws_, int64_t ws_stride, int64_t max_active, int64_t max_verts,
+                          float* verts, int32_t* faces, float* normals, float* values, float* ggm_at, cudaStream_t st) {
     McBatch b = {reinterpret_cast<char*>(ws_), ws_stride, geom(D, H, W)};
-    if (max_active <= 0) return GNB_OK;
-    if (max_active > b.g.ncells) max_active = b.g.ncells;
+    if (max_active <= 0 || max_verts <= 0) return GNB_OK;
+    if (max_active > b.g.nvox) max_active = b.g.nvox;
     Spacing sp = {{spacing_host[0], spacing_host[1], spacing_host[2]}};
-    const dim3 grid((unsigned)ceil_div<int64_t>(max_active, MC_BLOCK), N);
-    mc_vertices_kernel<<<grid, MC_BLOCK, 0, st>>>(v, D, H, W, level, sp, ggm, b, verts, normals, values, ggm_at);
-    mc_faces_kernel<<<grid, MC_BLOCK, 0, st>>>(D, H, W, ascent, b, faces);
+    mc_compact_kernel<<<dim3((unsigned)b.g.nb, N), MC_BLOCK, 0, st>>>(D, H, W, b, verts);
+    mc_vertices_kernel<<<dim3((unsigned)ceil_div<int64_t>(max_verts, MC_BLOCK), N), MC_BLOCK, 0, st>>>(
+        v, D, H, W, level, sp, ggm, b, verts, normals, values, ggm_at);
+    mc_faces_kernel<<<dim3((unsigned)ceil_div<int64_t>(max_active, MC_BLOCK), N), MC_BLOCK, 0, st>>>(D, H, W, ascent, b, faces);
     return check_launch("gnb_mc_emit");
 }
 
@@ -1020,6 +1133,7 @@ int32_t gnb_mc_count(const float* v, int32_t D, int32_t H, int32_t W, float leve
                      void* stream) {
     GNB_REQUIRE(v && ws_, "gnb_mc_count: null pointer");
     GNB_REQUIRE(D >= 2 && H >= 2 && W >= 2, "gnb_mc_count: volume must be at least 2x2x2");
+    GNB_REQUIRE((int64_t)D * H * W < (1ll << 31), "gnb_mc_count: volumes of 2^31 voxels or more are not supported");
     cudaStream_t st = as_stream(stream);
     const McGeom g = geom(D, H, W);
     int32_t rc = count_batch(v, 1, D, H, W, level, ws_, g.total, st);
@@ -1030,6 +1144,7 @@ int32_t gnb_mc_count(const float* v, int32_t D, int32_t H, int32_t W, float leve
     GNB_CUDA(cudaStreamSynchronize(st));
     counts_host[0] = h.V;
     counts_host[1] = h.F;
+    counts_host[2] = h.A;
     auto dec = [](unsigned e) { unsigned b = (e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e; float f; memcpy(&f, &b, 4); return f; };
     const float lo = dec(h.min_enc), hi = dec(h.max_enc);
     if (level < lo || level > hi) {
@@ -1040,13 +1155,12 @@ int32_t gnb_mc_count(const float* v, int32_t D, int32_t H, int32_t W, float leve
 }
 
 int32_t gnb_mc_emit(const float* v, int32_t D, int32_t H, int32_t W, float level, const double* spacing_host,
-                    int32_t ascent, const float* ggm, void* ws_, float* verts, int32_t* faces, float* normals,
-                    float* values, float* ggm_at_verts, void* stream) {
+                    int32_t ascent, const float* ggm, void* ws_, int64_t n_active, int64_t n_verts, float* verts,
+                    int32_t* faces, float* normals, float* values, float* ggm_at_verts, void* stream) {
     GNB_REQUIRE(v && ws_ && verts && faces && normals && values && spacing_host, "gnb_mc_emit: null pointer");
     GNB_REQUIRE(D >= 2 && H >= 2 && W >= 2, "gnb_mc_emit: volume must be at least 2x2x2");
     const McGeom g = geom(D, H, W);
-    // the active-cell count lives on the device; the grid covers the worst case and surplus CTAs exit at once
-    return emit_batch(v, 1, D, H, W, level, spacing_host, ascent, ggm, ws_, g.total, g.ncells, verts, faces, normals,
+    return emit_batch(v, 1, D, H, W, level, spacing_host, ascent, ggm, ws_, g.total, n_active, n_verts, verts, faces, normals,
                       values, ggm_at_verts, as_stream(stream));
 }
 
@@ -1055,6 +1169,7 @@ int32_t gnb_mc_count_batch(const float* v, int32_t N, int32_t D, int32_t H, int3
     GNB_REQUIRE(v && ws, "gnb_mc_count_batch: null pointer");
     GNB_REQUIRE(N >= 1 && N <= 65535, "gnb_mc_count_batch: 1 <= N <= 65535 volumes");
     GNB_REQUIRE(D >= 2 && H >= 2 && W >= 2, "gnb_mc_count_batch: volumes must be at least 2x2x2");
+    GNB_REQUIRE((int64_t)D * H * W < (1ll << 31), "gnb_mc_count_batch: volumes of 2^31 voxels or more are not supported");
     GNB_REQUIRE(ws_stride >= geom(D, H, W).total && ws_stride % 256 == 0,
                 "gnb_mc_count_batch: ws_stride must be a multiple of 256 >= gnb_mc_workspace_bytes");
     return count_batch(v, N, D, H, W, level, ws, ws_stride, as_stream(stream));
@@ -1062,13 +1177,13 @@ int32_t gnb_mc_count_batch(const float* v, int32_t N, int32_t D, int32_t H, int3
 
 int32_t gnb_mc_emit_batch(const float* v, int32_t N, int32_t D, int32_t H, int32_t W, float level,
                           const double* spacing_host, int32_t ascent, const float* ggm, void* ws, int64_t ws_stride,
-                          int64_t max_active, float* verts, int32_t* faces, float* normals, float* values,
-                          float* ggm_at_verts, void* stream) {
+                          int64_t max_active, int64_t max_verts, float* verts, int32_t* faces, float* normals,
+                          float* values, float* ggm_at_verts, void* stream) {
     GNB_REQUIRE(v && ws && verts && faces && normals && values && spacing_host, "gnb_mc_emit_batch: null pointer");
     GNB_REQUIRE(N >= 1 && N <= 65535, "gnb_mc_emit_batch: 1 <= N <= 65535 volumes");
     GNB_REQUIRE(D >= 2 && H >= 2 && W >= 2, "gnb_mc_emit_batch: volumes must be at least 2x2x2");
-    return emit_batch(v, N, D, H, W, level, spacing_host, ascent, ggm, ws, ws_stride, max_active, verts, faces, normals,
-                      values, ggm_at_verts, as_stream(stream));
+    return emit_batch(v, N, D, H, W, level, spacing_host, ascent, ggm, ws, ws_stride, max_active, max_verts, verts, faces,
+                      normals, values, ggm_at_verts, as_stream(stream));
 }
 
 int32_t gnb_mc_cell_tiling_host(const float* corner_values, float level, int32_t* code_out, int32_t* ntri_out,

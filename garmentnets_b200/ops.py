@@ -429,10 +429,10 @@ def marching_cubes(volume: torch.Tensor, level: float, spacing=(1.0, 1.0, 1.0), 
     dev = volume.device
     ws_bytes = _lib.load().gnb_mc_workspace_bytes(D, H, W)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    counts = (ctypes.c_int64 * 2)()
+    counts = (ctypes.c_int64 * 3)()
     _lib.call("gnb_mc_count", volume.data_ptr(), D, H, W, float(level), ws.data_ptr(),
               ctypes.cast(counts, ctypes.c_void_p).value, _stream())
-    V, Fc = int(counts[0]), int(counts[1])
+    V, Fc, A = int(counts[0]), int(counts[1]), int(counts[2])
     if V == 0:
         raise RuntimeError("No surface found at the given iso value.")
     verts = torch.empty((V, 3), dtype=torch.float32, device=dev)
@@ -442,7 +442,7 @@ def marching_cubes(volume: torch.Tensor, level: float, spacing=(1.0, 1.0, 1.0), 
     ggm_at = torch.empty((V,), dtype=torch.float32, device=dev) if ggm is not None else None
     sp = (ctypes.c_double * 3)(*[float(s) for s in spacing])
     _lib.call("gnb_mc_emit", volume.data_ptr(), D, H, W, float(level), ctypes.cast(sp, ctypes.c_void_p).value,
-              1 if gradient_direction == "ascent" else 0, _ptr(ggm), ws.data_ptr(), verts.data_ptr(), faces.data_ptr(),
+              1 if gradient_direction == "ascent" else 0, _ptr(ggm), ws.data_ptr(), A, V, verts.data_ptr(), faces.data_ptr(),
               normals.data_ptr(), values.data_ptr(), _ptr(ggm_at), _stream())
     return verts, faces, normals, values, ggm_at
 
@@ -634,9 +634,10 @@ def gaussian_gradient_magnitude_batched(v: torch.Tensor, sigma: float) -> torch.
 
 def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0, 1.0), gradient_direction: str = "ascent",
                          ggm: Optional[torch.Tensor] = None, return_packed: bool = False):
-    """Marching cubes of N volumes [N,D,H,W] in seven launches and ONE host synchronisation: classify / scan / compact
-    for the whole batch, the N 512-byte records come back in a single device->host copy, then one vertex and one face
-    launch over the compacted active cells write every mesh into shared [sum V] / [sum F] buffers.
+    """Marching cubes of N volumes [N,D,H,W] in seven launches and ONE host synchronisation: classify / scan for the
+    whole batch, the N 512-byte records come back in a single device->host copy, then compaction, one vertex launch (a
+    thread per vertex) and one face launch (a thread per active cell) write every mesh into shared [sum V] / [sum F]
+    buffers.
     Returns a list of (verts, faces, normals, values, ggm_at) views or the exception skimage would raise for that volume
     (ValueError: level outside the data range, RuntimeError: no surface).  ``return_packed`` adds the shared buffers:
     ``{"verts": f32[sum V,3], "vptr": host i64[N+1] row offsets, "faces": i32[sum F,3], "fptr", "normals", "values",
@@ -669,7 +670,7 @@ def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0,
         sp = (ctypes.c_double * 3)(*[float(x) for x in spacing])
         _lib.call("gnb_mc_emit_batch", volumes.data_ptr(), N, D, H, W, float(level), ctypes.cast(sp, ctypes.c_void_p).value,
                   1 if gradient_direction == "ascent" else 0, _ptr(ggm), ws.data_ptr(), ws_bytes, int(totals[:, 2].max()),
-                  verts.data_ptr(), faces.data_ptr(), normals.data_ptr(), values.data_ptr(), _ptr(ggm_at), _stream())
+                  int(totals[:, 0].max()), verts.data_ptr(), faces.data_ptr(), normals.data_ptr(), values.data_ptr(), _ptr(ggm_at), _stream())
     out = []
     for i in range(N):
         V, Fc, _, vb, fb = (int(t) for t in totals[i])

@@ -300,36 +300,39 @@ int32_t gnb_gaussian_gradient_magnitude_batched(const float* v, int32_t nvol, in
 /* ---- N12: marching cubes -------------------------------------------------------------------
  * ref: predict.py:172-181 `marching_cubes(wnf, level, spacing, gradient_direction, method='lewiner')`
  * + the ggm lookup at trunc(vert/spacing).
- * Two phases.  gnb_mc_count classifies the (D-1)(H-1)(W-1) cells and returns the vertex / face totals in
- * counts_host[2] (it synchronises `stream`).  gnb_mc_emit writes
+ * MC33 structure (face test, interior test, tunnel tilings; PARITY UNPINNED vs scikit-image's tables).
+ * Two phases.  gnb_mc_count classifies the (D-1)(H-1)(W-1) cells (one warp per volume row: 16-byte loads, neighbour
+ * corners by shuffle), scans the per-block counts and returns the vertex / face / active-cell totals in counts_host[3]
+ * (it synchronises `stream`).  gnb_mc_emit (n_active, n_verts = those totals) compacts the active cells, then writes
  *   verts f32[V,3] (axis0,axis1,axis2)*spacing, faces i32[F,3], normals f32[V,3], values f32[V],
- *   ggm_at_verts f32[V] (ggm may be NULL).
+ *   ggm_at_verts f32[V] (ggm may be NULL)
+ * with one thread per vertex / per active cell.
  * Vertex numbering = first-use order of a sequential axis0->axis1->axis2 cell scan; faces in cell order.
- * ws: workspace of gnb_mc_workspace_bytes(D,H,W) bytes, shared by both calls. */
+ * ws: workspace of gnb_mc_workspace_bytes(D,H,W) bytes, shared by both calls.  D*H*W < 2^31. */
 int64_t gnb_mc_workspace_bytes(int32_t D, int32_t H, int32_t W);
-/* Byte offset, inside the workspace, of the 512-byte record {i64 V, i64 F, ...} (+256: {u32 enc(min), u32 enc(max)}
+/* Byte offset, inside the workspace, of the 512-byte record {i64 V, i64 F, i64 A, ...} (+256: {u32 enc(min), u32 enc(max)}
  * order-preserving encodings of the data range).  gnb_mc_count with counts_host == NULL is fully asynchronous; a caller that processes
  * many volumes can then fetch all totals with ONE device->host copy instead of one synchronisation per volume. */
 int64_t gnb_mc_totals_offset(int32_t D, int32_t H, int32_t W);
 int32_t gnb_mc_count(const float* v, int32_t D, int32_t H, int32_t W, float level, void* ws,
                      int64_t* counts_host, void* stream);
 int32_t gnb_mc_emit(const float* v, int32_t D, int32_t H, int32_t W, float level, const double* spacing_host,
-                    int32_t ascent, const float* ggm, void* ws, float* verts, int32_t* faces,
-                    float* normals, float* values, float* ggm_at_verts, void* stream);
+                    int32_t ascent, const float* ggm, void* ws, int64_t n_active, int64_t n_verts, float* verts,
+                    int32_t* faces, float* normals, float* values, float* ggm_at_verts, void* stream);
 /* Batch form: N volumes v f32[N,D,H,W] (ggm likewise or NULL), one workspace block per volume `ws_stride` bytes apart
- * (a multiple of 256, >= gnb_mc_workspace_bytes).  gnb_mc_count_batch is asynchronous: it classifies every volume, scans
- * and compacts the active cells, and leaves one 512-byte record per volume at gnb_mc_totals_offset inside its block:
+ * (a multiple of 256, >= gnb_mc_workspace_bytes).  gnb_mc_count_batch is asynchronous: it classifies every volume and scans
+ * the counts, and leaves one 512-byte record per volume at gnb_mc_totals_offset inside its block:
  *   i64 V, F, A (active cells), vbase, fbase (first row of the volume in the concatenated outputs = exclusive prefix
  *   sums of V and F over the batch); byte 256: u32 enc(min), enc(max).
  * The caller fetches the N records with one strided device->host copy, sizes verts f32[sum V,3], faces i32[sum F,3],
- * normals, values, ggm_at_verts for the whole batch, and calls gnb_mc_emit_batch with max_active = max_i A_i.  Face
- * indices are local to their volume (0 .. V_i-1).  Five launches per batch instead of four per volume. */
+ * normals, values, ggm_at_verts for the whole batch, and calls gnb_mc_emit_batch with max_active = max_i A_i and
+ * max_verts = max_i V_i.  Face indices are local to their volume (0 .. V_i-1).  Seven launches per batch. */
 int32_t gnb_mc_count_batch(const float* v, int32_t N, int32_t D, int32_t H, int32_t W, float level, void* ws,
                            int64_t ws_stride, void* stream);
 int32_t gnb_mc_emit_batch(const float* v, int32_t N, int32_t D, int32_t H, int32_t W, float level,
                           const double* spacing_host, int32_t ascent, const float* ggm, void* ws, int64_t ws_stride,
-                          int64_t max_active, float* verts, int32_t* faces, float* normals, float* values,
-                          float* ggm_at_verts, void* stream);
+                          int64_t max_active, int64_t max_verts, float* verts, int32_t* faces, float* normals,
+                          float* values, float* ggm_at_verts, void* stream);
 
 /* Host-side diagnostic (no device work): the tiling the kernels apply to ONE cell with the given eight corner values
  * (corner i at (x,y,z) = {000,100,110,010,001,101,111,011}, scikit-image's numbering): cube index, face-test and
