@@ -50,6 +50,9 @@ __device__ McTunDesc d_mc_tun_desc[MC_MAX_TUN];    // descriptor at d_mc_tun_ind
 __device__ int16_t d_mc_tun_index[256 * 64];       // -1: no interior ambiguity
 __device__ uint8_t d_mc_cnt[256 * 64];             // triangles | centre vertices << 4 of d_mc_table (1 byte instead of 86)
 __device__ uint8_t d_mc_tun_cnt[MC_MAX_TUN];
+// per cube index, for the common cells without any ambiguity: {edge mask, counts of the fb = 0 tiling, needs_resolve}
+struct McFast { uint16_t edgemask; uint8_t cnt0; uint8_t resolve; };
+__device__ McFast d_mc_fast[256];
 __device__ uint16_t d_mc_edgemask[256];
 __device__ uint8_t d_mc_ambig[256];  // bit f set: face f is ambiguous for this cube index
 
@@ -498,6 +501,15 @@ static int ensure_tables() {
         if (cudaMemcpyToSymbol(d_mc_cnt, cnt, sizeof(cnt)) != cudaSuccess) return -1;
         if (cudaMemcpyToSymbol(d_mc_tun_cnt, tcnt, sizeof(tcnt)) != cudaSuccess) return -1;
     }
+    {
+        static McFast fast[256];
+        for (int i = 0; i < 256; ++i) {
+            fast[i].edgemask = T->edgemask[i];
+            fast[i].cnt0 = (uint8_t)(T->table[i * 64].ntri | (T->table[i * 64].ncen << 4));
+            fast[i].resolve = (uint8_t)((T->ambig[i] != 0 || T->tun_index[i * 64] >= 0) ? 1 : 0);
+        }
+        if (cudaMemcpyToSymbol(d_mc_fast, fast, sizeof(fast)) != cudaSuccess) return -1;
+    }
     if (cudaMemcpyToSymbol(d_mc_edgemask, T->edgemask, sizeof(T->edgemask)) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(d_mc_ambig, T->ambig, sizeof(T->ambig)) != cudaSuccess) return -1;
     done[dev] = true;
@@ -700,6 +712,11 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
     const int64_t nvox = batch.g.nvox;
     const float* __restrict__ v = vols + (int64_t)blockIdx.y * nvox;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the per-index table of the cells without ambiguity (99 % of the active ones) lives in shared memory: a global
+    // table look-up per active cell made this kernel latency-bound (744 us for 32 x 128^3 against ~100 us of HBM time)
+    __shared__ McFast s_fast[256];
+    s_fast[threadIdx.x] = d_mc_fast[threadIdx.x];
+    __syncthreads();
     const ItemPos ip = item_pos((int64_t)blockIdx.x * MC_WARPS + warp, lane, H, batch.g);
     const bool row_ok = ip.ok && ip.z < D - 1 && ip.y < H - 1;
     float lo = INFINITY, hi = -INFINITY;
@@ -748,19 +765,23 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
             }
             if (x < W - 1) {
                 // corner i at (dx,dy,dz): 0:000 1:100 2:110 3:010 4:001 5:101 6:111 7:011 ; rows: r = dy + 2 dz
-                const float val[8] = {a[0][k], a[0][k + 1], a[1][k + 1], a[1][k], a[2][k], a[2][k + 1], a[3][k + 1], a[3][k]};
-                int idx = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (val[i] > level) idx |= 1 << i;   // == ((double)v - (double)level > 0): both operands are exact in double
+                // (v > level) == ((double)v - (double)level > 0): both operands are exact in double
+                const int idx = (a[0][k] > level ? 1 : 0) | (a[0][k + 1] > level ? 2 : 0) | (a[1][k + 1] > level ? 4 : 0) |
+                                (a[1][k] > level ? 8 : 0) | (a[2][k] > level ? 16 : 0) | (a[2][k + 1] > level ? 32 : 0) |
+                                (a[3][k + 1] > level ? 64 : 0) | (a[3][k] > level ? 128 : 0);
                 if (idx != 0 && idx != 255) {
+                    const McFast fe = s_fast[idx];
                     int code = idx;
-                    if (d_mc_ambig[idx] != 0 || d_mc_tun_index[idx * 64] >= 0) code = mc_resolve(val, level, idx);
+                    unsigned cnt = fe.cnt0;
+                    if (fe.resolve) {   // ambiguous faces / interior ambiguity: the rare slow path
+                        const float val[8] = {a[0][k], a[0][k + 1], a[1][k + 1], a[1][k], a[2][k], a[2][k + 1], a[3][k + 1], a[3][k]};
+                        code = mc_resolve(val, level, idx);
+                        cnt = mc_counts(code);
+                    }
                     codes4[k] = (unsigned)code;
-                    const unsigned cnt = mc_counts(code);
                     na += 1;
                     nf += cnt & 15;
-                    nv += __popc(d_mc_edgemask[idx] & owned_mask(ip.z, ip.y, x)) + (cnt >> 4);
+                    nv += __popc(fe.edgemask & owned_mask(ip.z, ip.y, x)) + (cnt >> 4);
                 }
             }
         }
@@ -864,6 +885,7 @@ __global__ void mc_bases_kernel(McBatch batch, int N) {
 // Same item mapping as the classifier.  Besides the active-cell records it leaves, in the (still unwritten) output row of
 // every vertex, the pair (cell, vertex slot) that the vertex kernel consumes: one thread per VERTEX there, no divergence
 // over cells that own 0..5 vertices.
+template <bool VEC>
 __global__ void __launch_bounds__(MC_BLOCK)
 mc_compact_kernel(int D, int H, int W, McBatch batch, float* __restrict__ verts) {
     const McWs ws = carve(batch, blockIdx.y);
@@ -872,19 +894,32 @@ mc_compact_kernel(int D, int H, int W, McBatch batch, float* __restrict__ verts)
     const int a1 = blockIdx.x + 1 < nb ? ws.blockA[blockIdx.x + 1] : (int)ws.rec->A;
     if (a1 == a0) return;  // no active cell in this block (uniform branch)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ McFast s_fast[256];
+    s_fast[threadIdx.x] = d_mc_fast[threadIdx.x];
+    __syncthreads();
     const ItemPos ip = item_pos((int64_t)blockIdx.x * MC_WARPS + warp, lane, H, batch.g);
     int code[4] = {0, 0, 0, 0}, cv[4] = {0, 0, 0, 0}, cf[4] = {0, 0, 0, 0};
     int nv = 0, nf = 0, na = 0;
     if (ip.ok) {
         const uint16_t* __restrict__ src = ws.codes + ip.row * W + ip.x0;
+        if (VEC) {
+            if (ip.x0 + 3 < W) {
+                const uint2 q = *reinterpret_cast<const uint2*>(src);
+                code[0] = q.x & 0xFFFF; code[1] = q.x >> 16; code[2] = q.y & 0xFFFF; code[3] = q.y >> 16;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (ip.x0 + k < W - 1) code[k] = src[k];
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (ip.x0 + k < W - 1) code[k] = src[k];
             const int idx = code[k] & 255;
             if (idx != 0 && idx != 255) {
-                const unsigned cnt = mc_counts(code[k]);
+                const McFast fe = s_fast[idx];
+                const unsigned cnt = (code[k] >> 8) ? mc_counts(code[k]) : fe.cnt0;
                 cf[k] = cnt & 15;
-                cv[k] = __popc(d_mc_edgemask[idx] & owned_mask(ip.z, ip.y, ip.x0 + k)) + (cnt >> 4);
+                cv[k] = __popc(fe.edgemask & owned_mask(ip.z, ip.y, ip.x0 + k)) + (cnt >> 4);
                 nv += cv[k]; nf += cf[k]; na += 1;
             }
         }
@@ -911,7 +946,7 @@ mc_compact_kernel(int D, int H, int W, McBatch batch, float* __restrict__ verts)
         ws.active[oa] = make_int4(cell, ov, of, code[k]);
         if (cv[k]) {   // vertex work list, in first-use order of the cell's tiling
             const McEntry& en = mc_entry(code[k]);
-            const unsigned own = d_mc_edgemask[idx] & owned_mask(ip.z, ip.y, x);
+            const unsigned own = s_fast[idx].edgemask & owned_mask(ip.z, ip.y, x);
             int vid = ov;
             for (int j = 0; j < en.nedge; ++j) {
                 const int e = en.order[j];
@@ -1106,7 +1141,9 @@ static int32_t emit_batch(const float* v, int N, int D, int H, int W, float leve
     if (max_active <= 0 || max_verts <= 0) return GNB_OK;
     if (max_active > b.g.nvox) max_active = b.g.nvox;
     Spacing sp = {{spacing_host[0], spacing_host[1], spacing_host[2]}};
-    mc_compact_kernel<<<dim3((unsigned)b.g.nb, N), MC_BLOCK, 0, st>>>(D, H, W, b, verts);
+    const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(ws_) & 7) == 0) && (ws_stride % 8 == 0);
+    if (vec) mc_compact_kernel<true><<<dim3((unsigned)b.g.nb, N), MC_BLOCK, 0, st>>>(D, H, W, b, verts);
+    else mc_compact_kernel<false><<<dim3((unsigned)b.g.nb, N), MC_BLOCK, 0, st>>>(D, H, W, b, verts);
     mc_vertices_kernel<<<dim3((unsigned)ceil_div<int64_t>(max_verts, MC_BLOCK), N), MC_BLOCK, 0, st>>>(
         v, D, H, W, level, sp, ggm, b, verts, normals, values, ggm_at);
     mc_faces_kernel<<<dim3((unsigned)ceil_div<int64_t>(max_active, MC_BLOCK), N), MC_BLOCK, 0, st>>>(D, H, W, ascent, b, faces);
