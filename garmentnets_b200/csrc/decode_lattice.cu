@@ -30,17 +30,18 @@ constexpr int K = 256, N = 256, M = 128, KCHUNK = 64, NCHUNK = K / KCHUNK;
 constexpr int PART_BYTES = M * KCHUNK * 2;          // 16 KB: one tile, one precision part, one K chunk
 constexpr int SLOT_BYTES = 4 * PART_BYTES;          // 64 KB: {tile0 hi, tile0 lo, tile1 hi, tile1 lo}
 constexpr int A_SLOTS = 2;
-constexpr int B_PIECE_BYTES = N * KCHUNK * 2;       // 32 KB
-constexpr int B_SLOTS = 3;
+constexpr int B_PIECE_BYTES = N * KCHUNK * 2;       // 32 KB (one CTA); a CTA pair keeps one 16 KB half (128 of the 256 columns) per CTA
+constexpr int B_SLOTS = 3;                          // single CTA: 3 x 32 KB; CTA pair: 6 x 16 KB in the same 96 KB
 constexpr int THREADS = 448;
 constexpr int MAX_G = 32;   // one cell pair per 16-lane producer group
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+constexpr uint32_t IDESC_PAIR = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * M) >> 4) << 24);   // M = 256 over two CTAs
 
 struct Smem {
     static constexpr int a = 0;                                   // [2 slots][64 KB]
     static constexpr int b_ring = a + A_SLOTS * SLOT_BYTES;       // [3][32 KB]
     static constexpr int bars = b_ring + B_SLOTS * B_PIECE_BYTES;
-    static constexpr int n_bars = 2 + 2 + B_SLOTS + B_SLOTS + 2 + 2;
+    static constexpr int n_bars = 8 + 3 * (2 * B_SLOTS);   // a_full/a_empty[2], b_full/b_empty/b_peer[<=6], d_full/d_empty[2]
     static constexpr int tmem_ptr = bars + n_bars * 8;
     static constexpr int rowtab = tmem_ptr + 16;                  // [128] {float wz1, u32 byte offset of row k inside a swizzled tile}
     static constexpr int kstart = rowtab + M * 8;                 // [G+1]
@@ -134,7 +135,14 @@ __device__ __forceinline__ void axis_cell(int idx, float sq, int G, int& c0, int
 // Issue priority on sm_100 goes to the HIGHEST warp id: the MMA issuer and the loader (latency critical, a handful of
 // instructions per MMA) come first, then the epilogue (it gates the reuse of the accumulators), and the producers fill
 // the remaining issue slots.  The epilogue sleeps on its barrier instead of spinning through those slots.
-template <int COUT>
+// PAIR: the kernel runs as clusters of two CTAs (one TPC).  Each CTA keeps its own pair of lattice lines (A operand,
+// accumulators, producers, epilogue exactly as in the single-CTA form) but only HALF of every W2 piece; the leader CTA
+// issues tcgen05.mma.cta_group::2 (M = 256: both CTAs' tiles at once, N = 256 read as 128 columns from either CTA), so the
+// per-SM shared-memory operand traffic of an MMA drops from 12 KB to 8 KB and the W2 stream per SM halves -- the port the
+// producers' stores compete for.  Cross-CTA hand-shakes: the peer's producers / epilogue arrive remotely on the leader's
+// a_full / d_empty barriers, the leader's commits are multicast to both CTAs' a_empty / b_empty / d_full barriers, and the
+// peer reports the landing of its W2 halves on the leader's b_peer barriers.
+template <int COUT, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 decode_lattice_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -142,21 +150,30 @@ decode_lattice_kernel(const Params p) {
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    constexpr int BS = PAIR ? 2 * B_SLOTS : B_SLOTS;                  // W2 ring slots
+    constexpr int BPB = PAIR ? B_PIECE_BYTES / 2 : B_PIECE_BYTES;     // bytes of a W2 piece held by this CTA
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;              // 0 = leader (issues the MMAs)
     const uint32_t bar0 = sbase + Smem::bars;
     auto a_full = [&](int s) { return bar0 + 8 * s; };
     auto a_empty = [&](int s) { return bar0 + 8 * (2 + s); };
     auto b_full = [&](int s) { return bar0 + 8 * (4 + s); };
-    auto b_empty = [&](int s) { return bar0 + 8 * (4 + B_SLOTS + s); };
-    auto d_full = [&](int t) { return bar0 + 8 * (4 + 2 * B_SLOTS + t); };
-    auto d_empty = [&](int t) { return bar0 + 8 * (6 + 2 * B_SLOTS + t); };
+    auto b_empty = [&](int s) { return bar0 + 8 * (4 + BS + s); };
+    auto d_full = [&](int t) { return bar0 + 8 * (4 + 2 * BS + t); };
+    auto d_empty = [&](int t) { return bar0 + 8 * (6 + 2 * BS + t); };
+    auto b_peer = [&](int s) { return bar0 + 8 * (8 + 2 * BS + s); };   // leader only: the peer's half of piece s has landed
+    // arrive on a barrier of the LEADER (local for the leader itself)
+    auto arrive_leader = [&](uint32_t bar) {
+        if (PAIR && rank != 0) mbar_arrive_remote(mapa_cluster(bar, 0));
+        else mbar_arrive(bar);
+    };
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
     const int Q = p.Q, G = p.G, QH = Q >> 1;
     const float sq = __fdiv_rn(1.0f, (float)(Q - 1));
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < A_SLOTS; ++s) { mbar_init(a_full(s), 8); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < B_SLOTS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(d_full(t), 1); mbar_init(d_empty(t), 4); }
+        for (int s = 0; s < A_SLOTS; ++s) { mbar_init(a_full(s), PAIR ? 16 : 8); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); mbar_init(b_peer(s), 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(d_full(t), 1); mbar_init(d_empty(t), PAIR ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x == 416) {
@@ -191,11 +208,17 @@ decode_lattice_kernel(const Params p) {
             make_uint2(__float_as_uint(w1), (uint32_t)((k >> 3) * 1024 + (k & 7) * 128));
     }
     if (warp == 12) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Smem::tmem_ptr), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Smem::tmem_ptr), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Smem::tmem_ptr), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anybody arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     if (threadIdx.x <= G) {
@@ -352,7 +375,7 @@ decode_lattice_kernel(const Params p) {
                 }
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a_full(slot));
+                if (lane == 0) arrive_leader(a_full(slot));
             }
         }
     } else if (warp < 12) {
@@ -398,7 +421,7 @@ decode_lattice_kernel(const Params p) {
                         // every TMEM read of accumulator t has completed: the next pair's MMAs may overwrite it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(d_empty(t));
+                        if (lane == 0) arrive_leader(d_empty(t));
                     }
 #pragma unroll
                     for (int u = 0; u < 32; ++u) {
@@ -422,17 +445,35 @@ decode_lattice_kernel(const Params p) {
             }
         }
     } else if (warp == 12) {
-        // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        // =========================== MMA issuer (leader CTA) / W2 landing notifier (peer CTA) ===========================
+        if (lane == 0 && rank == 0) {
             int it = 0;
             uint32_t piece = 0, q = 0;
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+                if (PAIR) umma_f16_pair(d, da, db, IDESC_PAIR, acc);
+                else umma_f16(d, da, db, IDESC, acc);
+            };
+            auto commit = [&](uint32_t bar) {
+                if (PAIR) umma_commit_pair(bar);
+                else umma_commit(bar);
+            };
+            // barriers the peer CTA arrives on need a cluster-scope acquire
+            auto wait_x = [&](uint32_t bar, uint32_t parity) {
+                if (PAIR) mbar_wait_cluster(bar, parity);
+                else mbar_wait(bar, parity);
+            };
+            auto wait_b = [&](uint32_t pc) {   // W2 piece pc (this CTA's part and, in a pair, the peer's)
+                mbar_wait(b_full(pc % BS), (pc / BS) & 1);
+                if (PAIR) mbar_wait_cluster(b_peer(pc % BS), (pc / BS) & 1);
+                tc_fence_after();
+            };
             for (int64_t pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x, ++it) {
                 for (int c = 0; c < NCHUNK; ++c, ++q) {
                     const int slot = q & 1;
-                    mbar_wait(a_full(slot), (q >> 1) & 1);
+                    wait_x(a_full(slot), (q >> 1) & 1);
                     const uint32_t a_slot = sbase + Smem::a + slot * SLOT_BYTES;
-                    const int s_hi = piece % B_SLOTS, s_lo = (piece + 1) % B_SLOTS;
-                    const uint32_t b_hi = sbase + Smem::b_ring + s_hi * B_PIECE_BYTES, b_lo = sbase + Smem::b_ring + s_lo * B_PIECE_BYTES;
+                    const int s_hi = piece % BS, s_lo = (piece + 1) % BS;
+                    const uint32_t b_hi = sbase + Smem::b_ring + s_hi * BPB, b_lo = sbase + Smem::b_ring + s_lo * BPB;
                     // hi*hi + lo*hi of tile t against the W2_hi piece; hi*lo against the W2_lo piece
                     // descriptors of the first K-step; the next K-steps add 32 bytes = 2 address units (no carry: the tiles
                     // are 1024-byte aligned and far below the 14-bit address field's wrap)
@@ -441,48 +482,53 @@ decode_lattice_kernel(const Params p) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)(t * N);
                         const uint64_t dah = umma_desc(a_slot + (2 * t) * PART_BYTES), dal = umma_desc(a_slot + (2 * t + 1) * PART_BYTES);
 #pragma unroll
-                        for (int kk = 0; kk < KCHUNK / 16; ++kk) umma_f16(d_tmem, dah + 2 * kk, dbh + 2 * kk, IDESC, (c | kk) != 0);
+                        for (int kk = 0; kk < KCHUNK / 16; ++kk) mma(d_tmem, dah + 2 * kk, dbh + 2 * kk, (c | kk) != 0);
 #pragma unroll
-                        for (int kk = 0; kk < KCHUNK / 16; ++kk) umma_f16(d_tmem, dal + 2 * kk, dbh + 2 * kk, IDESC, 1);
+                        for (int kk = 0; kk < KCHUNK / 16; ++kk) mma(d_tmem, dal + 2 * kk, dbh + 2 * kk, 1);
                     };
                     auto mma_lo = [&](int t) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)(t * N);
                         const uint64_t dah = umma_desc(a_slot + (2 * t) * PART_BYTES);
 #pragma unroll
-                        for (int kk = 0; kk < KCHUNK / 16; ++kk) umma_f16(d_tmem, dah + 2 * kk, dbl + 2 * kk, IDESC, 1);
+                        for (int kk = 0; kk < KCHUNK / 16; ++kk) mma(d_tmem, dah + 2 * kk, dbl + 2 * kk, 1);
                     };
-                    mbar_wait(b_full(s_hi), (piece / B_SLOTS) & 1);
-                    tc_fence_after();
+                    wait_b(piece);
                     if (c == 0 || c == NCHUNK - 1) {
                         // tile-major: accumulator 0 is released to / taken from the epilogue a whole tile (12 MMAs) before
                         // accumulator 1, so draining one tile overlaps the other tile's MMAs
-                        if (c == 0) { mbar_wait(d_empty(0), (it & 1) ^ 1); tc_fence_after(); }
+                        if (c == 0) { wait_x(d_empty(0), (it & 1) ^ 1); tc_fence_after(); }
                         mma_hi(0);
-                        mbar_wait(b_full(s_lo), ((piece + 1) / B_SLOTS) & 1);
-                        tc_fence_after();
+                        wait_b(piece + 1);
                         mma_lo(0);
-                        if (c == NCHUNK - 1) umma_commit(d_full(0));
-                        if (c == 0) { mbar_wait(d_empty(1), (it & 1) ^ 1); tc_fence_after(); }
+                        if (c == NCHUNK - 1) commit(d_full(0));
+                        if (c == 0) { wait_x(d_empty(1), (it & 1) ^ 1); tc_fence_after(); }
                         mma_hi(1);
-                        umma_commit(b_empty(s_hi));
+                        commit(b_empty(s_hi));
                         mma_lo(1);
-                        umma_commit(b_empty(s_lo));
-                        umma_commit(a_empty(slot));
-                        if (c == NCHUNK - 1) umma_commit(d_full(1));
+                        commit(b_empty(s_lo));
+                        commit(a_empty(slot));
+                        if (c == NCHUNK - 1) commit(d_full(1));
                     } else {
                         mma_hi(0);
                         mma_hi(1);
-                        umma_commit(b_empty(s_hi));
-                        mbar_wait(b_full(s_lo), ((piece + 1) / B_SLOTS) & 1);
-                        tc_fence_after();
+                        commit(b_empty(s_hi));
+                        wait_b(piece + 1);
                         mma_lo(0);
                         mma_lo(1);
-                        umma_commit(b_empty(s_lo));
-                        umma_commit(a_empty(slot));  // every MMA that reads this A slot has been issued
+                        commit(b_empty(s_lo));
+                        commit(a_empty(slot));  // every MMA that reads this A slot has been issued
                     }
                     piece += 2;
                 }
             }
+        } else if (PAIR && lane == 0 && rank != 0) {
+            // peer CTA: tell the leader when each of this CTA's W2 halves has landed (in order)
+            uint32_t piece = 0;
+            for (int64_t pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x)
+                for (int pc = 0; pc < 2 * NCHUNK; ++pc, ++piece) {
+                    mbar_wait(b_full(piece % BS), (piece / BS) & 1);
+                    mbar_arrive_remote(mapa_cluster(b_peer(piece % BS), 0));
+                }
         }
     } else {
         // =========================== B loader ===========================
@@ -490,12 +536,13 @@ decode_lattice_kernel(const Params p) {
             uint32_t piece = 0;
             for (int64_t pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x) {
                 for (int pc = 0; pc < 2 * NCHUNK; ++pc, ++piece) {
-                    const int slot = piece % B_SLOTS;
-                    mbar_wait(b_empty(slot), ((piece / B_SLOTS) & 1) ^ 1);
+                    const int slot = piece % BS;
+                    mbar_wait(b_empty(slot), ((piece / BS) & 1) ^ 1);
                     if (p.dbg & 2) { mbar_arrive(b_full(slot)); continue; }
-                    mbar_expect_tx(b_full(slot), B_PIECE_BYTES);
-                    bulk_g2s(sbase + Smem::b_ring + slot * B_PIECE_BYTES, p.w2_packed + (size_t)pc * B_PIECE_BYTES,
-                             B_PIECE_BYTES, b_full(slot));
+                    mbar_expect_tx(b_full(slot), BPB);
+                    // a CTA pair splits every piece by output column: rows [rank * 128, rank * 128 + 128) of the K-major image
+                    bulk_g2s(sbase + Smem::b_ring + slot * BPB, p.w2_packed + (size_t)pc * B_PIECE_BYTES + (size_t)rank * BPB, BPB,
+                             b_full(slot));
                 }
             }
         }
@@ -503,9 +550,11 @@ decode_lattice_kernel(const Params p) {
 
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // both CTAs have drained their accumulators before the pair's TMEM is released
     if (warp == 12) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -541,13 +590,35 @@ __global__ void lattice_prep_kernel(const float* __restrict__ W2, const float* _
     }
 }
 
+// CTA pairs need an even grid and an even number of line pairs (both CTAs of a cluster run the same number of items)
+static bool g_use_pair = true;
+static bool g_force_single = false;   // gnb_decode_lattice_set_mode(0): the single-CTA kernel (A/B measurements, tests)
+
 template <int COUT>
 static int32_t launch(const Params& p, cudaStream_t st) {
     const int smem = Smem::total + 1024;
-    GNB_CUDA(cudaFuncSetAttribute(decode_lattice_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = sm_count();
     if ((int64_t)grid > p.num_pairs) grid = (int)p.num_pairs;
-    decode_lattice_kernel<COUT><<<grid, THREADS, smem, st>>>(p);
+    if (g_use_pair && grid >= 2 && (p.num_pairs % 2) == 0) {
+        grid &= ~1;
+        GNB_CUDA(cudaFuncSetAttribute(decode_lattice_kernel<COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        GNB_CUDA(cudaLaunchKernelEx(&cfg, decode_lattice_kernel<COUT, true>, p));
+        return check_launch("gnb_decode_lattice");
+    }
+    GNB_CUDA(cudaFuncSetAttribute(decode_lattice_kernel<COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    decode_lattice_kernel<COUT, false><<<grid, THREADS, smem, st>>>(p);
     return check_launch("gnb_decode_lattice");
 }
 
@@ -583,9 +654,15 @@ int32_t gnb_decode_lattice(const float* U, int32_t B, int32_t G, int32_t Q, cons
     p.b2s = b2s; p.w3s = w3s; p.tail = tail; p.out = out;
     p.num_pairs = (int64_t)B * Q * (Q / 2);
     p.dbg = profile_knob("GNB_DL2_DBG");
+    dl2::g_use_pair = !(profile_knob("GNB_DL2_SINGLE") != 0 || dl2::g_force_single);
     if (Cout == 1) return dl2::launch<1>(p, st);
     if (Cout == 2) return dl2::launch<2>(p, st);
     return dl2::launch<3>(p, st);
+}
+
+int32_t gnb_decode_lattice_set_mode(int32_t cta_pair) {
+    dl2::g_force_single = cta_pair == 0;
+    return GNB_OK;
 }
 
 }  // extern "C"

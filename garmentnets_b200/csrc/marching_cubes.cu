@@ -51,8 +51,15 @@ __device__ int16_t d_mc_tun_index[256 * 64];       // -1: no interior ambiguity
 __device__ uint8_t d_mc_cnt[256 * 64];             // triangles | centre vertices << 4 of d_mc_table (1 byte instead of 86)
 __device__ uint8_t d_mc_tun_cnt[MC_MAX_TUN];
 // per cube index, for the common cells without any ambiguity: {edge mask, counts of the fb = 0 tiling, needs_resolve}
-struct McFast { uint16_t edgemask; uint8_t cnt0; uint8_t resolve; };
+struct McFast { uint16_t edgemask; uint8_t cnt0; uint8_t resolve; uint16_t eid0; uint16_t pad; };   // eid0: compact id of the fb = 0 tiling
 __device__ McFast d_mc_fast[256];
+// all tilings back to back (the 656 valid (index, face decision) entries, then the tunnel entries) for kernels that keep the
+// whole table in shared memory; d_mc_entry_id maps index * 64 + face bits -> position, tunnel entry k of a key follows at
+// d_mc_n_base + d_mc_tun_index[key] + k
+constexpr int MC_MAX_ENTRIES = 700 + MC_MAX_TUN;
+__device__ McEntry d_mc_compact[MC_MAX_ENTRIES];
+__device__ uint16_t d_mc_entry_id[256 * 64];
+__device__ int d_mc_n_base;
 __device__ uint16_t d_mc_edgemask[256];
 __device__ uint8_t d_mc_ambig[256];  // bit f set: face f is ambiguous for this cube index
 
@@ -480,6 +487,8 @@ static void build_tables(McTables& T) {
     }
 }
 
+static int g_mc_n_entries = 0;   // entries of d_mc_compact (host copy: sizes the shared-memory table of the emit kernels)
+
 static int ensure_tables() {
     static bool done[64] = {false};
     int dev = 0;
@@ -507,8 +516,34 @@ static int ensure_tables() {
             fast[i].edgemask = T->edgemask[i];
             fast[i].cnt0 = (uint8_t)(T->table[i * 64].ntri | (T->table[i * 64].ncen << 4));
             fast[i].resolve = (uint8_t)((T->ambig[i] != 0 || T->tun_index[i * 64] >= 0) ? 1 : 0);
+            // compact id of (i, fb = 0): the number of valid entries in front of it (same enumeration as below)
+            int n = 0;
+            for (int idx = 0; idx < i; ++idx)
+                for (int fb = 0; fb < 64; ++fb)
+                    if (!((fb & ~T->ambig[idx]) || idx == 0 || idx == 255)) ++n;
+            fast[i].eid0 = (uint16_t)n;
+            fast[i].pad = 0;
         }
         if (cudaMemcpyToSymbol(d_mc_fast, fast, sizeof(fast)) != cudaSuccess) return -1;
+    }
+    {
+        static McEntry compact[MC_MAX_ENTRIES];
+        static uint16_t eid[256 * 64];
+        int n = 0;
+        for (int idx = 0; idx < 256; ++idx)
+            for (int fb = 0; fb < 64; ++fb) {
+                eid[idx * 64 + fb] = 0;
+                if ((fb & ~T->ambig[idx]) || idx == 0 || idx == 255) continue;
+                eid[idx * 64 + fb] = (uint16_t)n;
+                compact[n++] = T->table[idx * 64 + fb];
+            }
+        const int n_base = n;
+        for (int i = 0; i < T->ntun; ++i) compact[n++] = T->tun_table[i];
+        if (n > MC_MAX_ENTRIES) return -1;
+        g_mc_n_entries = n;
+        if (cudaMemcpyToSymbol(d_mc_compact, compact, sizeof(McEntry) * n) != cudaSuccess) return -1;
+        if (cudaMemcpyToSymbol(d_mc_entry_id, eid, sizeof(eid)) != cudaSuccess) return -1;
+        if (cudaMemcpyToSymbol(d_mc_n_base, &n_base, sizeof(int)) != cudaSuccess) return -1;
     }
     if (cudaMemcpyToSymbol(d_mc_edgemask, T->edgemask, sizeof(T->edgemask)) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(d_mc_ambig, T->ambig, sizeof(T->ambig)) != cudaSuccess) return -1;
@@ -706,7 +741,7 @@ __device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long 
 // ---- kernel 1: classify --------------------------------------------------------------------------------------
 // VEC: W % 4 == 0 and a 16-byte aligned volume -> float4 loads and 8-byte code stores
 template <bool VEC>
-__global__ void __launch_bounds__(MC_BLOCK)
+__global__ void __launch_bounds__(MC_BLOCK, 4)
 mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float level, McBatch batch) {
     const McWs ws = carve(batch, blockIdx.y);
     const int64_t nvox = batch.g.nvox;
@@ -715,9 +750,14 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
     // the per-index table of the cells without ambiguity (99 % of the active ones) lives in shared memory: a global
     // table look-up per active cell made this kernel latency-bound (744 us for 32 x 128^3 against ~100 us of HBM time)
     __shared__ McFast s_fast[256];
+    __shared__ unsigned long long s_cnt[MC_WARPS];
+    __shared__ float s_lo[MC_WARPS], s_hi[MC_WARPS];
     s_fast[threadIdx.x] = d_mc_fast[threadIdx.x];
     __syncthreads();
-    const ItemPos ip = item_pos((int64_t)blockIdx.x * MC_WARPS + warp, lane, H, batch.g);
+    float vol_lo = INFINITY, vol_hi = -INFINITY;   // data range over every count block this CTA visits
+    // persistent over the count blocks of the volume: the table is staged once per CTA
+    for (int64_t cb = blockIdx.x; cb < batch.g.nb; cb += gridDim.x) {
+    const ItemPos ip = item_pos(cb * MC_WARPS + warp, lane, H, batch.g);
     const bool row_ok = ip.ok && ip.z < D - 1 && ip.y < H - 1;
     float lo = INFINITY, hi = -INFINITY;
     int nv = 0, nf = 0, na = 0;
@@ -798,8 +838,6 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
         }
     }
     // block totals + data range
-    __shared__ unsigned long long s_cnt[MC_WARPS];
-    __shared__ float s_lo[MC_WARPS], s_hi[MC_WARPS];
     unsigned long long tot = pack3(nv, nf, na);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -813,13 +851,17 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
         unsigned long long t = 0;
 #pragma unroll
         for (int w = 0; w < MC_WARPS; ++w) { t += s_cnt[w]; lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
-        ws.blockV[blockIdx.x] = (int)(t & 0x1FFFFF);
-        ws.blockF[blockIdx.x] = (int)((t >> 21) & 0x1FFFFF);
-        ws.blockA[blockIdx.x] = (int)(t >> 42);
-        if (lo <= hi) {   // every voxel is a corner of some cell when D,H,W >= 2: one atomic pair per CTA
-            atomicMin(&ws.rec->min_enc, mc_enc(lo));
-            atomicMax(&ws.rec->max_enc, mc_enc(hi));
-        }
+        ws.blockV[cb] = (int)(t & 0x1FFFFF);
+        ws.blockF[cb] = (int)((t >> 21) & 0x1FFFFF);
+        ws.blockA[cb] = (int)(t >> 42);
+        vol_lo = fminf(vol_lo, lo);
+        vol_hi = fmaxf(vol_hi, hi);
+    }
+    __syncthreads();   // s_cnt / s_lo / s_hi are reused by the next count block
+    }
+    if (threadIdx.x == 0 && vol_lo <= vol_hi) {   // every voxel is a corner of some cell when D,H,W >= 2: one atomic pair per CTA
+        atomicMin(&ws.rec->min_enc, mc_enc(vol_lo));
+        atomicMax(&ws.rec->max_enc, mc_enc(vol_hi));
     }
 }
 
@@ -887,77 +929,94 @@ __global__ void mc_bases_kernel(McBatch batch, int N) {
 // over cells that own 0..5 vertices.
 template <bool VEC>
 __global__ void __launch_bounds__(MC_BLOCK)
-mc_compact_kernel(int D, int H, int W, McBatch batch, float* __restrict__ verts) {
+mc_compact_kernel(int D, int H, int W, McBatch batch, int n_entries, float* __restrict__ verts) {
+    // persistent CTAs; the tiling table (vertex order of every tiling) and the per-index fast table live in shared memory
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    McEntry* s_tab = reinterpret_cast<McEntry*>(s_raw);
+    __shared__ McFast s_fast[256];
+    __shared__ unsigned long long s_w[MC_WARPS];
+    {
+        const int words = (n_entries * (int)sizeof(McEntry) + 3) / 4;
+        const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(d_mc_compact);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_raw);
+        for (int i = threadIdx.x; i < words; i += MC_BLOCK) dst[i] = src[i];
+        s_fast[threadIdx.x] = d_mc_fast[threadIdx.x];
+    }
+    __syncthreads();
     const McWs ws = carve(batch, blockIdx.y);
     const int64_t nb = batch.g.nb;
-    const int a0 = ws.blockA[blockIdx.x];
-    const int a1 = blockIdx.x + 1 < nb ? ws.blockA[blockIdx.x + 1] : (int)ws.rec->A;
-    if (a1 == a0) return;  // no active cell in this block (uniform branch)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ McFast s_fast[256];
-    s_fast[threadIdx.x] = d_mc_fast[threadIdx.x];
-    __syncthreads();
-    const ItemPos ip = item_pos((int64_t)blockIdx.x * MC_WARPS + warp, lane, H, batch.g);
-    int code[4] = {0, 0, 0, 0}, cv[4] = {0, 0, 0, 0}, cf[4] = {0, 0, 0, 0};
-    int nv = 0, nf = 0, na = 0;
-    if (ip.ok) {
-        const uint16_t* __restrict__ src = ws.codes + ip.row * W + ip.x0;
-        if (VEC) {
-            if (ip.x0 + 3 < W) {
-                const uint2 q = *reinterpret_cast<const uint2*>(src);
-                code[0] = q.x & 0xFFFF; code[1] = q.x >> 16; code[2] = q.y & 0xFFFF; code[3] = q.y >> 16;
-            }
-        } else {
+    const int n_base = d_mc_n_base;
+    const int64_t vbase = ws.rec->vbase;
+    const int total_active = (int)ws.rec->A;
+    for (int64_t cb = blockIdx.x; cb < nb; cb += gridDim.x) {
+        const int a0 = ws.blockA[cb];
+        const int a1 = cb + 1 < nb ? ws.blockA[cb + 1] : total_active;
+        if (a1 == a0) continue;  // no active cell in this count block (uniform branch)
+        const ItemPos ip = item_pos(cb * MC_WARPS + warp, lane, H, batch.g);
+        int code[4] = {0, 0, 0, 0}, cv[4] = {0, 0, 0, 0}, cf[4] = {0, 0, 0, 0};
+        int nv = 0, nf = 0, na = 0;
+        if (ip.ok) {
+            const uint16_t* __restrict__ src = ws.codes + ip.row * W + ip.x0;
+            if (VEC) {
+                if (ip.x0 + 3 < W) {
+                    const uint2 q = *reinterpret_cast<const uint2*>(src);
+                    code[0] = q.x & 0xFFFF; code[1] = q.x >> 16; code[2] = q.y & 0xFFFF; code[3] = q.y >> 16;
+                }
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (ip.x0 + k < W - 1) code[k] = src[k];
+                for (int k = 0; k < 4; ++k)
+                    if (ip.x0 + k < W - 1) code[k] = src[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int idx = code[k] & 255;
+                if (idx != 0 && idx != 255) {
+                    const McFast fe = s_fast[idx];
+                    const unsigned cnt = (code[k] >> 8) ? mc_counts(code[k]) : fe.cnt0;
+                    cf[k] = cnt & 15;
+                    cv[k] = __popc(fe.edgemask & owned_mask(ip.z, ip.y, ip.x0 + k)) + (cnt >> 4);
+                    nv += cv[k]; nf += cf[k]; na += 1;
+                }
+            }
         }
+        const unsigned long long mine = pack3(nv, nf, na);
+        const unsigned long long incl = warp_incl_scan(mine, lane);
+        __syncthreads();   // s_w of the previous count block has been consumed
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        unsigned long long base = 0;
+#pragma unroll
+        for (int w = 0; w < MC_WARPS; ++w)
+            if (w < warp) base += s_w[w];
+        const unsigned long long ex = base + incl - mine;
+        int ov = ws.blockV[cb] + (int)(ex & 0x1FFFFF), of = ws.blockF[cb] + (int)((ex >> 21) & 0x1FFFFF);
+        int oa = a0 + (int)(ex >> 42);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int idx = code[k] & 255;
-            if (idx != 0 && idx != 255) {
-                const McFast fe = s_fast[idx];
-                const unsigned cnt = (code[k] >> 8) ? mc_counts(code[k]) : fe.cnt0;
-                cf[k] = cnt & 15;
-                cv[k] = __popc(fe.edgemask & owned_mask(ip.z, ip.y, ip.x0 + k)) + (cnt >> 4);
-                nv += cv[k]; nf += cf[k]; na += 1;
+            if (idx == 0 || idx == 255) continue;
+            const int x = ip.x0 + k;
+            const int cell = (int)(ip.row * W + x);
+            // the face kernel only needs the tiling: its position in the compact table goes into .w
+            const int key = idx * 64 + ((code[k] >> 8) & 63), tun = code[k] >> 14;
+            const int eid = tun ? n_base + d_mc_tun_index[key] + tun - 1 : ((code[k] >> 8) ? d_mc_entry_id[key] : s_fast[idx].eid0);
+            ws.active[oa] = make_int4(cell, ov, of, eid);
+            if (cv[k]) {   // vertex work list, in first-use order of the cell's tiling
+                const McEntry& en = s_tab[eid];
+                const unsigned own = s_fast[idx].edgemask & owned_mask(ip.z, ip.y, x);
+                int vid = ov;
+                for (int j = 0; j < en.nedge; ++j) {
+                    const int e = en.order[j];
+                    if (e < 12 && !((own >> e) & 1)) continue;
+                    float* __restrict__ row = verts + (vbase + vid) * 3;
+                    row[0] = __int_as_float(cell);
+                    row[1] = __int_as_float(e);
+                    ++vid;
+                }
             }
+            ++oa; ov += cv[k]; of += cf[k];
         }
-    }
-    __shared__ unsigned long long s_w[MC_WARPS];
-    const unsigned long long mine = pack3(nv, nf, na);
-    const unsigned long long incl = warp_incl_scan(mine, lane);
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    unsigned long long base = 0;
-#pragma unroll
-    for (int w = 0; w < MC_WARPS; ++w)
-        if (w < warp) base += s_w[w];
-    const unsigned long long ex = base + incl - mine;
-    int ov = ws.blockV[blockIdx.x] + (int)(ex & 0x1FFFFF), of = ws.blockF[blockIdx.x] + (int)((ex >> 21) & 0x1FFFFF);
-    int oa = a0 + (int)(ex >> 42);
-    const int64_t vbase = ws.rec->vbase;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int idx = code[k] & 255;
-        if (idx == 0 || idx == 255) continue;
-        const int x = ip.x0 + k;
-        const int cell = (int)(ip.row * W + x);
-        ws.active[oa] = make_int4(cell, ov, of, code[k]);
-        if (cv[k]) {   // vertex work list, in first-use order of the cell's tiling
-            const McEntry& en = mc_entry(code[k]);
-            const unsigned own = s_fast[idx].edgemask & owned_mask(ip.z, ip.y, x);
-            int vid = ov;
-            for (int j = 0; j < en.nedge; ++j) {
-                const int e = en.order[j];
-                if (e < 12 && !((own >> e) & 1)) continue;
-                float* __restrict__ row = verts + (vbase + vid) * 3;
-                row[0] = __int_as_float(cell);
-                row[1] = __int_as_float(e);
-                ++vid;
-            }
-        }
-        ++oa; ov += cv[k]; of += cf[k];
     }
 }
 
@@ -1075,37 +1134,48 @@ mc_vertices_kernel(const float* __restrict__ vols, int D, int H, int W, float le
 }
 
 // ---- kernel 5: faces -------------------------------------------------------------------------------------------
+// Persistent CTAs with the whole tiling table (~70 KB) in shared memory: the per-byte reads of a tiling's vertex order and
+// triangle list were what bound this kernel (L1 at 80 %, lg / mio throttle) when they went to global memory.
 __global__ void __launch_bounds__(MC_BLOCK)
-mc_faces_kernel(int D, int H, int W, int ascent, McBatch batch, int32_t* __restrict__ faces) {
-    const McWs ws = carve(batch, blockIdx.y);
-    const int64_t a = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
-    if (a >= ws.rec->A) return;
-    const int4 act = ws.active[a];
-    const int code = act.w;
-    const McEntry& en = mc_entry(code);
-    const int nf = en.ntri;
-    if (nf == 0) return;
-    const CellPos p = cell_pos(act.x, H, W);
-    const int64_t vol_n = batch.g.nvox;
-    int32_t vid[12 + MC_MAX_CEN];
-#pragma unroll
-    for (int e = 0; e < 12 + MC_MAX_CEN; ++e) vid[e] = -1;
-    for (int k = 0; k < en.nedge; ++k) {
-        const int e = en.order[k];
-        if (e >= 12) {
-            vid[e] = ws.edge_map[(int64_t)(3 + (e - 12)) * vol_n + act.x];
-        } else {
-            const int z0 = p.z + c_edge_dz[e], y0 = p.y + c_edge_dy[e], x0 = p.x + c_edge_dx[e];
-            vid[e] = ws.edge_map[(int64_t)c_edge_axis[e] * vol_n + ((int64_t)z0 * H + y0) * W + x0];
-        }
+mc_faces_kernel(int D, int H, int W, int ascent, McBatch batch, int n_entries, int32_t* __restrict__ faces) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    McEntry* s_tab = reinterpret_cast<McEntry*>(s_raw);
+    {
+        const int words = (n_entries * (int)sizeof(McEntry) + 3) / 4;
+        const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(d_mc_compact);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_raw);
+        for (int i = threadIdx.x; i < words; i += MC_BLOCK) dst[i] = src[i];
     }
-    int64_t f = ws.rec->fbase + act.z;
-    for (int t = 0; t < nf; ++t, ++f) {
-        const int a0 = vid[en.tri[t * 3]], b = vid[en.tri[t * 3 + 1]], cc = vid[en.tri[t * 3 + 2]];
-        // native winding: right-hand normal towards lower values ('descent'); 'ascent' reverses the columns
-        faces[f * 3 + 0] = ascent ? cc : a0;
-        faces[f * 3 + 1] = b;
-        faces[f * 3 + 2] = ascent ? a0 : cc;
+    __syncthreads();
+    const McWs ws = carve(batch, blockIdx.y);
+    const int64_t A = ws.rec->A, fbase = ws.rec->fbase;
+    const int64_t vol_n = batch.g.nvox;
+    for (int64_t a = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x; a < A; a += (int64_t)gridDim.x * MC_BLOCK) {
+        const int4 act = ws.active[a];
+        const McEntry& en = s_tab[act.w];
+        const int nf = en.ntri;
+        if (nf == 0) continue;
+        const CellPos p = cell_pos(act.x, H, W);
+        int32_t vid[12 + MC_MAX_CEN];
+#pragma unroll
+        for (int e = 0; e < 12 + MC_MAX_CEN; ++e) vid[e] = -1;
+        for (int k = 0; k < en.nedge; ++k) {
+            const int e = en.order[k];
+            if (e >= 12) {
+                vid[e] = ws.edge_map[(int64_t)(3 + (e - 12)) * vol_n + act.x];
+            } else {
+                const int z0 = p.z + c_edge_dz[e], y0 = p.y + c_edge_dy[e], x0 = p.x + c_edge_dx[e];
+                vid[e] = ws.edge_map[(int64_t)c_edge_axis[e] * vol_n + ((int64_t)z0 * H + y0) * W + x0];
+            }
+        }
+        int64_t f = fbase + act.z;
+        for (int t = 0; t < nf; ++t, ++f) {
+            const int a0 = vid[en.tri[t * 3]], b = vid[en.tri[t * 3 + 1]], cc = vid[en.tri[t * 3 + 2]];
+            // native winding: right-hand normal towards lower values ('descent'); 'ascent' reverses the columns
+            faces[f * 3 + 0] = ascent ? cc : a0;
+            faces[f * 3 + 1] = b;
+            faces[f * 3 + 2] = ascent ? a0 : cc;
+        }
     }
 }
 
@@ -1126,7 +1196,9 @@ static int32_t count_batch(const float* v, int N, int D, int H, int W, float lev
     mc_init_kernel<<<ceil_div(N, 128), 128, 0, st>>>(b, N);
     const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0) && ((reinterpret_cast<uintptr_t>(ws_) & 7) == 0) &&
                      (ws_stride % 8 == 0);
-    const dim3 grid((unsigned)b.g.nb, N);
+    // persistent CTAs: ~8 per SM over the whole batch, each striding over the count blocks of its volume
+    const int64_t per_vol = ceil_div<int64_t>((int64_t)sm_count() * 8, N);
+    const dim3 grid((unsigned)(b.g.nb < per_vol ? b.g.nb : per_vol), N);
     if (vec) mc_classify_kernel<true><<<grid, MC_BLOCK, 0, st>>>(v, D, H, W, level, b);
     else mc_classify_kernel<false><<<grid, MC_BLOCK, 0, st>>>(v, D, H, W, level, b);
     mc_scan_kernel<<<N, 1024, 0, st>>>(b);
@@ -1141,12 +1213,29 @@ static int32_t emit_batch(const float* v, int N, int D, int H, int W, float leve
     if (max_active <= 0 || max_verts <= 0) return GNB_OK;
     if (max_active > b.g.nvox) max_active = b.g.nvox;
     Spacing sp = {{spacing_host[0], spacing_host[1], spacing_host[2]}};
-    const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(ws_) & 7) == 0) && (ws_stride % 8 == 0);
-    if (vec) mc_compact_kernel<true><<<dim3((unsigned)b.g.nb, N), MC_BLOCK, 0, st>>>(D, H, W, b, verts);
-    else mc_compact_kernel<false><<<dim3((unsigned)b.g.nb, N), MC_BLOCK, 0, st>>>(D, H, W, b, verts);
+    if (ensure_tables() != 0) { set_error("gnb_mc_emit: table upload failed"); return GNB_ERR_CUDA; }
+    const int n_entries = g_mc_n_entries;
+    const int tab_smem = n_entries * (int)sizeof(McEntry) + 16;
+    const int64_t per_vol = ceil_div<int64_t>((int64_t)sm_count() * 3, N);   // ~3 CTAs (70 KB of shared memory each) per SM over the batch
+    {
+        const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(ws_) & 7) == 0) && (ws_stride % 8 == 0);
+        const dim3 grid((unsigned)(b.g.nb < per_vol ? b.g.nb : per_vol), N);
+        if (vec) {
+            GNB_CUDA(cudaFuncSetAttribute(mc_compact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_smem));
+            mc_compact_kernel<true><<<grid, MC_BLOCK, tab_smem, st>>>(D, H, W, b, n_entries, verts);
+        } else {
+            GNB_CUDA(cudaFuncSetAttribute(mc_compact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_smem));
+            mc_compact_kernel<false><<<grid, MC_BLOCK, tab_smem, st>>>(D, H, W, b, n_entries, verts);
+        }
+    }
     mc_vertices_kernel<<<dim3((unsigned)ceil_div<int64_t>(max_verts, MC_BLOCK), N), MC_BLOCK, 0, st>>>(
         v, D, H, W, level, sp, ggm, b, verts, normals, values, ggm_at);
-    mc_faces_kernel<<<dim3((unsigned)ceil_div<int64_t>(max_active, MC_BLOCK), N), MC_BLOCK, 0, st>>>(D, H, W, ascent, b, faces);
+    {
+        GNB_CUDA(cudaFuncSetAttribute(mc_faces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_smem));
+        int64_t gx = ceil_div<int64_t>(max_active, MC_BLOCK);
+        if (gx > per_vol) gx = per_vol;
+        mc_faces_kernel<<<dim3((unsigned)gx, N), MC_BLOCK, tab_smem, st>>>(D, H, W, ascent, b, n_entries, faces);
+    }
     return check_launch("gnb_mc_emit");
 }
 

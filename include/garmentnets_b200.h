@@ -260,6 +260,10 @@ int32_t gnb_decode_lattice(const float* U, int32_t B, int32_t G, int32_t Q, cons
                            int32_t w2f_scale_log2, const float* b2, const float* bn1_shift, const float* bn2_scale,
                            const float* bn2_shift, const float* W3, const float* b3, const float* bn3_scale,
                            const float* bn3_shift, int32_t Cout, float* scratch, float* out, void* stream);
+/* Kernel variant of gnb_decode_lattice: 1 (default) = clusters of two CTAs issuing tcgen05.mma.cta_group::2 (each SM keeps
+ * half of every W2 piece), 0 = one CTA per SM with cta_group::1.  Results are bit-identical; the switch exists for A/B
+ * measurements and tests. */
+int32_t gnb_decode_lattice_set_mode(int32_t cta_pair);
 /* Query mode of the same kernel (the surface / warp-field decoder, ref predict.py:184-187 and
  * networks/conv_implicit_wnf.py:263-269): H1 = BN1(ReLU(trilinear(U[b], q_r))) for explicit query points q f32[R,3] in
  * [0,1]^3 (coordinate 0 -> W axis: the reference does not flip xyz, :135-142).  Rows are ragged per sample: rows
@@ -358,6 +362,31 @@ int32_t gnb_mesh_cleanup_count(const int32_t* faces, const int64_t* fptr, const 
 int32_t gnb_mesh_cleanup_emit(const int32_t* faces, const int64_t* fptr, const int64_t* vptr, int32_t B, int64_t V,
                               int64_t F, void* workspace, const int64_t* rec, int64_t* keep, int32_t* out_faces,
                               void* stream);
+
+/* Largest connected component of the (cleaned) meshes, ref eval.py:538-546 (igl.adjacency_matrix +
+ * igl.connected_components + argmax of the component sizes).  Vertices are connected through faces; a component is
+ * named by its lowest vertex id (the order igl numbers components in), "largest" = most vertices, first on ties.
+ * Batched over packed meshes like the clean-up above.  parent_ws / size_ws: i32[V] scratch.  Outputs (each nullable):
+ * is_largest u8[V] membership mask (feed it to gnb_mesh_cleanup_*), labels i32[V] = LOCAL id of the lowest vertex of the
+ * vertex's component, summary i64[B,3] = {number of components, size of the largest, local id of its lowest vertex}. */
+int32_t gnb_mesh_components(const int32_t* faces, const int64_t* fptr, const int64_t* vptr, int32_t B, int64_t V, int64_t F,
+                            int32_t* parent_ws, int32_t* size_ws, uint8_t* is_largest, int32_t* labels, int64_t* summary,
+                            void* stream);
+
+/* Area-weighted surface sampling, ref common/geometry_util.py:184-223 (mesh_sample_barycentric) for ONE mesh: face m is
+ * drawn with probability area_m / sum(area) by inverse CDF (numpy RandomState.choice: cdf = cumsum(p) / cumsum(p)[-1],
+ * searchsorted(cdf, u, side='right')), u_face f64[M] and uv f64[M,2] being the uniform variates of the reference's own
+ * host generator (RandomState(seed).random_sample / .uniform); barycentric (a, b, 1-a-b) with (a, b) reflected into the
+ * triangle when a + b >= 1.  verts f32 or f64 [N,3] (verts_f64 selects), faces i32[F,3]; areas_in f64[F] optional
+ * (else twice the triangle areas are computed: igl.doublearea).  cdf_ws: f64[2F] scratch.  Outputs face_idx i64[M],
+ * bary f64[M,3]. */
+int32_t gnb_mesh_sample_barycentric(const void* verts, int32_t verts_f64, const int32_t* faces, int64_t F, const double* areas_in,
+                                    const double* u_face, const double* uv, int64_t M, double* cdf_ws, int64_t* face_idx,
+                                    double* bary, void* stream);
+/* ref common/geometry_util.py:160-181 (barycentric_interpolation): out[m,c] = sum_i bary[m,i] * field[faces[face_idx[m],i], c],
+ * accumulated in the field's dtype (f32 or f64, field_f64 selects) like the reference's in-place += on verts.dtype. */
+int32_t gnb_barycentric_interpolation(const double* bary, const int64_t* face_idx, const int32_t* faces, const void* field,
+                                      int32_t field_f64, int32_t C, int64_t M, void* out, void* stream);
 
 /* ---- next row: chamfer / hybrid chamfer nearest-neighbour core -----------
  * ref: eval.py:259-271 (get_chamfer in compute_chamfer) and :381-401 (get_chamfer in compute_hybrid_chamfer), which use

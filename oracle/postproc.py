@@ -149,3 +149,28 @@ def optimal_gradient_threshold(gt_mc_verts, gt_mc_is_on_surface, pred_mc_verts, 
     else:
         max_score_threshold = pred_mc_gm.min()
     return {"optimal_wnf_gradient_threshold": max_score_threshold}
+
+
+def connected_components(faces: np.ndarray, num_verts: int):
+    """ref eval.py:538-541 restated with scipy (igl is not installable offline): components of the vertex adjacency
+    graph of the faces, numbered in order of their lowest vertex like igl.connected_components; returns
+    (num_cc, cc_idxs, cc_sizes, is_cc_vert) where is_cc_vert marks the component with the most vertices (np.argmax:
+    first on ties)."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components as cc
+    f = np.asarray(faces, dtype=np.int64).reshape(-1, 3)
+    rows = np.concatenate([f[:, 0], f[:, 1], f[:, 2]])
+    cols = np.concatenate([f[:, 1], f[:, 2], f[:, 0]])
+    adj = sp.coo_matrix((np.ones(len(rows), np.int8), (rows, cols)), shape=(num_verts, num_verts))
+    num_cc, idx = cc(adj, directed=False)
+    # scipy labels components in order of first appearance along the vertex index = order of their lowest vertex
+    sizes = np.bincount(idx, minlength=num_cc)
+    return num_cc, idx, sizes, idx == int(np.argmax(sizes))
+
+
+def doublearea(verts: np.ndarray, faces: np.ndarray) -> np.ndarray:
+    """igl.doublearea restated: twice the triangle areas, float64."""
+    v = np.asarray(verts, dtype=np.float64)
+    r = v[faces[:, 1]] - v[faces[:, 0]]
+    s = v[faces[:, 2]] - v[faces[:, 0]]
+    return np.linalg.norm(np.cross(r, s), axis=1)

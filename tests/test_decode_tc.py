@@ -195,3 +195,25 @@ def test_two_streams_do_not_race_on_the_constant_operand_banks(dev):
         torch.cuda.synchronize()
         assert torch.equal(ya, ref_a) and torch.equal(yb, ref_b)
         assert torch.equal(la, lin_a) and torch.equal(lb, lin_b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("G,B,cout", [(32, 2, 1), (16, 1, 3), (7, 3, 2)])
+def test_cta_pair_lattice_kernel_is_bit_identical_to_single_cta(dev, G, B, cout):
+    """gnb_decode_lattice as clusters of two CTAs (tcgen05.mma.cta_group::2, each SM holds half of every W2 piece) against the
+    one-CTA-per-SM form: same products, same accumulation order -> identical bits."""
+    from garmentnets_b200 import _lib, ops
+    dec = _decoder(dev, cout, 40 + cout)
+    g = torch.Generator().manual_seed(G + B)
+    u = (torch.randn(B, G, G, G, 256, generator=g) * 0.9).to(dev)
+    try:
+        _lib.call("gnb_decode_lattice_set_mode", 0)
+        single = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
+        _lib.call("gnb_decode_lattice_set_mode", 1)
+        pair = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
+        again = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
+    finally:
+        _lib.call("gnb_decode_lattice_set_mode", 1)
+    torch.cuda.synchronize()
+    assert torch.equal(pair, single)
+    assert torch.equal(pair, again)

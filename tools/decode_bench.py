@@ -39,4 +39,10 @@ out1 = ops.decode_tc(*dec._tc_args(), U=u, Q=128, bn1=dec.mlp[0][2].folded_affin
 out2 = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
 print("max |pair - gen1| =", (out1 - out2).abs().max().item())
 timeit("decode_tc lattice (gen 1)", lambda: ops.decode_tc(*dec._tc_args(), U=u, Q=128, bn1=dec.mlp[0][2].folded_affine()))
-timeit("decode_lattice (pair tiles)", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128))
+from garmentnets_b200 import _lib
+_lib.call("gnb_decode_lattice_set_mode", 0)
+out3 = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
+print("max |cta pair - single cta| =", (out3 - out2).abs().max().item())
+timeit("decode_lattice (pair tiles, one CTA / SM)", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128))
+_lib.call("gnb_decode_lattice_set_mode", 1)
+timeit("decode_lattice (pair tiles, cta_group::2)", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128))
