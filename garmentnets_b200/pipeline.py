@@ -467,8 +467,15 @@ class ConvImplicitWNFPipeline(nn.Module):
         """Device version of the reference's per-sample loop predict.py:138-187, for a whole batch.
         Returns one dict per sample with the arrays predict.py writes under ``marching_cubes_mesh`` / ``point_cloud``."""
         marks = getattr(self, "stage_marks", None)  # optional [(name, cuda event)] sink used by bench.py
+        order = ("pointnet2", "aggregator", "unet3d", "dense_decode", "ggm", "marching_cubes", "surface_decode")
 
         def mark(name):
+            # closes the NVTX range of the stage that just ended and opens the next one (nsys / ncu --nvtx timelines)
+            if name != "start":
+                profiling.nvtx_pop()
+            nxt = order[order.index(name) + 1] if name in order[:-1] else (order[0] if name == "start" else None)
+            if nxt is not None:
+                profiling.nvtx_push("gnb." + nxt)
             if marks is not None:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()

@@ -52,3 +52,22 @@ class KernelTimer:
     def summary(self):
         torch.cuda.synchronize()
         return {t: (len(ev), sum(s.elapsed_time(e) for s, e in ev)) for t, ev in self.events.items()}
+
+
+# ---- NVTX stage ranges (profiling hooks) -----------------------------------------------------------
+try:
+    from torch.cuda import nvtx as _nvtx
+    _nvtx.range_push("gnb.probe")
+    _nvtx.range_pop()
+except Exception:  # no NVTX library in this build: ranges become no-ops
+    _nvtx = None
+
+
+def nvtx_push(name: str) -> None:
+    if _nvtx is not None:
+        _nvtx.range_push(name)
+
+
+def nvtx_pop() -> None:
+    if _nvtx is not None:
+        _nvtx.range_pop()
