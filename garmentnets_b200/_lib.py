@@ -13,7 +13,9 @@ from typing import Dict, List, Tuple
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
 HEADER_PATH = os.path.join(os.path.dirname(_ROOT), "include", "garmentnets_b200.h")
-LIB_PATH = os.path.join(_ROOT, "lib", "libgarmentnets_b200.so")
+# GNB_B200_LIBRARY (read once, at import): development override used by tools/ to load the profiling build
+# (`make PROFILE_KNOBS=1` -> lib/libgarmentnets_b200_prof.so); never a CPU fallback -- it must be another build of this library
+LIB_PATH = os.environ.get("GNB_B200_LIBRARY") or os.path.join(_ROOT, "lib", "libgarmentnets_b200.so")
 
 
 class GarmentNetsB200Error(RuntimeError):

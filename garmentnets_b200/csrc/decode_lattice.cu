@@ -55,6 +55,22 @@ static_assert(Smem::total + 1024 <= 227 * 1024, "shared memory budget");
 // Filled per launch by a stream-ordered device-to-device copy from the prep kernel's scratch (one stream at a time).
 __constant__ float c_epi[4 * 256];
 
+// Per-role wait-time attribution (profiling builds only, tools/decode_bench.py): cycles one thread of each role spends in
+// its barrier waits.  [cta][16]: 0 MMA a_full | 1 MMA W2 | 2 MMA d_empty | 3 MMA total | 4 producer a_empty | 5 producer total |
+// 6 producer row/store phase | 7 epilogue d_full | 8 epilogue total | 9 loader b_empty | 10 loader total
+#ifdef GNB_PROFILE_KNOBS
+__device__ unsigned long long g_prof[1024 * 16];
+#define DL2_PROF_DECL unsigned long long prof_acc[4] = {0, 0, 0, 0}; const long long prof_t0 = clock64()
+#define DL2_PROF(i, stmt) do { const long long t_ = clock64(); stmt; prof_acc[i] += (unsigned long long)(clock64() - t_); } while (0)
+#define DL2_PROF_STORE(i, slot) g_prof[blockIdx.x * 16 + (slot)] = prof_acc[i]
+#define DL2_PROF_TOTAL(slot) g_prof[blockIdx.x * 16 + (slot)] = (unsigned long long)(clock64() - prof_t0)
+#else
+#define DL2_PROF_DECL
+#define DL2_PROF(i, stmt) do { stmt; } while (0)
+#define DL2_PROF_STORE(i, slot)
+#define DL2_PROF_TOTAL(slot)
+#endif
+
 struct Params {
     const float* U;            // [B,G,G,G,256] hoisted grid (Linear1 applied on the feature grid), fp32 channels-last
     int B, G, Q;
@@ -277,6 +293,7 @@ decode_lattice_kernel(const Params p) {
         };
 
         float4 nxt[3][2][2];
+        DL2_PROF_DECL;
         uint32_t q = 0;  // running chunk counter (slot = q & 1)
         int64_t pair = blockIdx.x;
         if (pair < p.num_pairs && active && !(p.dbg & 1)) issue(item_of(pair), item_of(pair).j0, 0, nxt);
@@ -338,7 +355,10 @@ decode_lattice_kernel(const Params p) {
                         }
                     }
                     // 4. the slot must have been consumed by the tensor core (chunk q - 2)
-                    mbar_wait(a_empty(slot), ((q >> 1) & 1) ^ 1);
+                    DL2_PROF(0, mbar_wait(a_empty(slot), ((q >> 1) & 1) ^ 1));
+#ifdef GNB_PROFILE_KNOBS
+                    const long long t_rows = clock64();
+#endif
                     const uint32_t a_addr = sbase + Smem::a + slot * SLOT_BYTES + sub8;  // + part * PART_BYTES + row offset
 #pragma unroll
                     for (int cell = 0; cell < 2; ++cell) {
@@ -368,6 +388,9 @@ decode_lattice_kernel(const Params p) {
                         for (; k + 1 < k_end; k += 2) { row(k); row(k + 1); }   // two rows = eight independent chains in flight
                         if (k < k_end) row(k);
                     }
+#ifdef GNB_PROFILE_KNOBS
+                    prof_acc[1] += (unsigned long long)(clock64() - t_rows);
+#endif
                 } else {
                     // no D-cell (G < 32): still pace on the slot, or an early arrival for the NEXT use of this slot would be
                     // counted into the current phase of a_full
@@ -378,6 +401,7 @@ decode_lattice_kernel(const Params p) {
                 if (lane == 0) arrive_leader(a_full(slot));
             }
         }
+        if (threadIdx.x == 0) { DL2_PROF_STORE(0, 4); DL2_PROF_STORE(1, 6); DL2_PROF_TOTAL(5); }
     } else if (warp < 12) {
         // =========================== epilogue ===========================
         const int qd = warp & 3;  // TMEM lane quarter this warp may access (warp id mod 4)
@@ -386,12 +410,13 @@ decode_lattice_kernel(const Params p) {
 #pragma unroll
         for (int o = 0; o < COUT; ++o) { c_tail[o] = p.tail[o * 4]; bn3s[o] = p.tail[o * 4 + 1]; bn3h[o] = p.tail[o * 4 + 2]; }
         int it = 0;
+        DL2_PROF_DECL;
         for (int64_t pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x, ++it) {
             const int jp = (int)(pair % QH);
             const int64_t plane = pair / QH;  // b * Q + i
 #pragma unroll 1
             for (int t = 0; t < 2; ++t) {
-                mbar_wait_sleep(d_full(t), it & 1);
+                DL2_PROF(0, mbar_wait_sleep(d_full(t), it & 1));
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(t * N);
                 // software pipeline: the next 32 columns are in flight (tcgen05.ld) while the current 32 are folded.  The
@@ -444,11 +469,13 @@ decode_lattice_kernel(const Params p) {
                 }
             }
         }
+        if (threadIdx.x == 256) { DL2_PROF_STORE(0, 7); DL2_PROF_TOTAL(8); }
     } else if (warp == 12) {
         // =========================== MMA issuer (leader CTA) / W2 landing notifier (peer CTA) ===========================
         if (lane == 0 && rank == 0) {
             int it = 0;
             uint32_t piece = 0, q = 0;
+            DL2_PROF_DECL;
             auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
                 if (PAIR) umma_f16_pair(d, da, db, IDESC_PAIR, acc);
                 else umma_f16(d, da, db, IDESC, acc);
@@ -463,14 +490,13 @@ decode_lattice_kernel(const Params p) {
                 else mbar_wait(bar, parity);
             };
             auto wait_b = [&](uint32_t pc) {   // W2 piece pc (this CTA's part and, in a pair, the peer's)
-                mbar_wait(b_full(pc % BS), (pc / BS) & 1);
-                if (PAIR) mbar_wait_cluster(b_peer(pc % BS), (pc / BS) & 1);
+                DL2_PROF(1, mbar_wait(b_full(pc % BS), (pc / BS) & 1); if (PAIR) mbar_wait_cluster(b_peer(pc % BS), (pc / BS) & 1));
                 tc_fence_after();
             };
             for (int64_t pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x, ++it) {
                 for (int c = 0; c < NCHUNK; ++c, ++q) {
                     const int slot = q & 1;
-                    wait_x(a_full(slot), (q >> 1) & 1);
+                    DL2_PROF(0, wait_x(a_full(slot), (q >> 1) & 1));
                     const uint32_t a_slot = sbase + Smem::a + slot * SLOT_BYTES;
                     const int s_hi = piece % BS, s_lo = (piece + 1) % BS;
                     const uint32_t b_hi = sbase + Smem::b_ring + s_hi * BPB, b_lo = sbase + Smem::b_ring + s_lo * BPB;
@@ -496,12 +522,12 @@ decode_lattice_kernel(const Params p) {
                     if (c == 0 || c == NCHUNK - 1) {
                         // tile-major: accumulator 0 is released to / taken from the epilogue a whole tile (12 MMAs) before
                         // accumulator 1, so draining one tile overlaps the other tile's MMAs
-                        if (c == 0) { wait_x(d_empty(0), (it & 1) ^ 1); tc_fence_after(); }
+                        if (c == 0) { DL2_PROF(2, wait_x(d_empty(0), (it & 1) ^ 1)); tc_fence_after(); }
                         mma_hi(0);
                         wait_b(piece + 1);
                         mma_lo(0);
                         if (c == NCHUNK - 1) commit(d_full(0));
-                        if (c == 0) { wait_x(d_empty(1), (it & 1) ^ 1); tc_fence_after(); }
+                        if (c == 0) { DL2_PROF(2, wait_x(d_empty(1), (it & 1) ^ 1)); tc_fence_after(); }
                         mma_hi(1);
                         commit(b_empty(s_hi));
                         mma_lo(1);
@@ -521,6 +547,7 @@ decode_lattice_kernel(const Params p) {
                     piece += 2;
                 }
             }
+            DL2_PROF_STORE(0, 0); DL2_PROF_STORE(1, 1); DL2_PROF_STORE(2, 2); DL2_PROF_TOTAL(3);
         } else if (PAIR && lane == 0 && rank != 0) {
             // peer CTA: tell the leader when each of this CTA's W2 halves has landed (in order)
             uint32_t piece = 0;
@@ -534,10 +561,11 @@ decode_lattice_kernel(const Params p) {
         // =========================== B loader ===========================
         if (lane == 0) {
             uint32_t piece = 0;
+            DL2_PROF_DECL;
             for (int64_t pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x) {
                 for (int pc = 0; pc < 2 * NCHUNK; ++pc, ++piece) {
                     const int slot = piece % BS;
-                    mbar_wait(b_empty(slot), ((piece / BS) & 1) ^ 1);
+                    DL2_PROF(0, mbar_wait(b_empty(slot), ((piece / BS) & 1) ^ 1));
                     if (p.dbg & 2) { mbar_arrive(b_full(slot)); continue; }
                     mbar_expect_tx(b_full(slot), BPB);
                     // a CTA pair splits every piece by output column: rows [rank * 128, rank * 128 + 128) of the K-major image
@@ -545,6 +573,7 @@ decode_lattice_kernel(const Params p) {
                              b_full(slot));
                 }
             }
+            DL2_PROF_STORE(0, 9); DL2_PROF_TOTAL(10);
         }
     }
 
@@ -659,6 +688,13 @@ int32_t gnb_decode_lattice(const float* U, int32_t B, int32_t G, int32_t Q, cons
     if (Cout == 2) return dl2::launch<2>(p, st);
     return dl2::launch<3>(p, st);
 }
+
+#ifdef GNB_PROFILE_KNOBS
+// profiling builds only (not in the header): copy the per-CTA wait-time table of the last launch to the host
+__attribute__((visibility("default"))) int32_t gnb_prof_decode_lattice_read(unsigned long long* host_out, int32_t n) {
+    return cudaMemcpyFromSymbol(host_out, dl2::g_prof, sizeof(unsigned long long) * (size_t)n) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int32_t gnb_decode_lattice_set_mode(int32_t cta_pair) {
     dl2::g_force_single = cta_pair == 0;

@@ -117,8 +117,10 @@ face_doublearea_kernel(const T* __restrict__ verts, const int32_t* __restrict__ 
     const double ax = (double)verts[a * 3], ay = (double)verts[a * 3 + 1], az = (double)verts[a * 3 + 2];
     const double rx = (double)verts[b * 3] - ax, ry = (double)verts[b * 3 + 1] - ay, rz = (double)verts[b * 3 + 2] - az;
     const double sx = (double)verts[c * 3] - ax, sy = (double)verts[c * 3 + 1] - ay, sz = (double)verts[c * 3 + 2] - az;
-    const double cx = ry * sz - rz * sy, cy = rz * sx - rx * sz, cz = rx * sy - ry * sx;
-    area[f] = sqrt(cx * cx + cy * cy + cz * cz);   // |r x s| = twice the triangle area (igl.doublearea)
+    // every product and sum rounded on its own (numpy's cross / sum order; nvcc would contract these into FMAs)
+    const double cx = __dsub_rn(__dmul_rn(ry, sz), __dmul_rn(rz, sy)), cy = __dsub_rn(__dmul_rn(rz, sx), __dmul_rn(rx, sz)),
+                 cz = __dsub_rn(__dmul_rn(rx, sy), __dmul_rn(ry, sx));
+    area[f] = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(cx, cx), __dmul_rn(cy, cy)), __dmul_rn(cz, cz)));   // |r x s| = twice the triangle area (igl.doublearea)
 }
 // single-CTA inclusive scan in double (the mesh of one garment has a few 1e5 faces): cdf[i] = sum_{j<=i} a[j]; then
 // normalised by the total like numpy's RandomState.choice (p = a / sum(a); cdf = cumsum(p); cdf /= cdf[-1])
@@ -199,7 +201,8 @@ barycentric_interp_kernel(const double* __restrict__ bary, const int64_t* __rest
     const int64_t f = face_idx[m];
     T r = (T)0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) r = (T)((double)r + bary[m * 3 + k] * (double)field[(int64_t)faces[f * 3 + k] * C + c]);
+    for (int k = 0; k < 3; ++k)   // product and sum rounded separately like numpy (no FMA contraction)
+        r = (T)__dadd_rn((double)r, __dmul_rn(bary[m * 3 + k], (double)field[(int64_t)faces[f * 3 + k] * C + c]));
     out[i] = r;
 }
 
