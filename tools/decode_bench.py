@@ -46,3 +46,29 @@ print("max |cta pair - single cta| =", (out3 - out2).abs().max().item())
 timeit("decode_lattice (pair tiles, one CTA / SM)", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128))
 _lib.call("gnb_decode_lattice_set_mode", 1)
 timeit("decode_lattice (pair tiles, cta_group::2)", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128))
+
+# ---- profiling build only (GNB_B200_LIBRARY=garmentnets_b200/lib/libgarmentnets_b200_prof.so): knock-outs and per-role
+# wait-time attribution of both kernel forms
+lib = _lib.load()
+if hasattr(lib, "gnb_prof_decode_lattice_read"):
+    import ctypes
+    import numpy as np
+    names = ["mma:a_full", "mma:w2", "mma:d_empty", "mma:total", "prod:a_empty", "prod:total", "prod:rows", "epi:d_full",
+             "epi:total", "load:b_empty", "load:total"]
+
+    def prof(label):
+        buf = np.zeros(1024 * 16, np.uint64)
+        lib.gnb_prof_decode_lattice_read(ctypes.c_void_p(buf.ctypes.data), ctypes.c_int32(buf.size))
+        t = buf.reshape(1024, 16)[:148].astype(np.float64)
+        lead, peer = t[0::2], t[1::2]
+        fmt = lambda a: " ".join(f"{n}={a[:, i].mean() / 1e6:6.2f}" for i, n in enumerate(names))
+        print(f"   [{label}] Mcycles/CTA even: {fmt(lead)}")
+        print(f"   [{label}] Mcycles/CTA odd : {fmt(peer)}")
+
+    for mode, mname in ((0, "single"), (1, "cta_group::2")):
+        _lib.call("gnb_decode_lattice_set_mode", mode)
+        for dbg in (0, 1, 2, 4, 7):
+            os.environ["GNB_DL2_DBG"] = str(dbg)
+            timeit(f"{mname} dbg={dbg}", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128), n=3)
+            prof(f"{mname} dbg={dbg}")
+    os.environ["GNB_DL2_DBG"] = "0"
