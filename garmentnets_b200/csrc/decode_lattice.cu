@@ -43,10 +43,11 @@ struct Smem {
     static constexpr int bars = b_ring + B_SLOTS * B_PIECE_BYTES;
     static constexpr int n_bars = 8 + 3 * (2 * B_SLOTS);   // a_full/a_empty[2], b_full/b_empty/b_peer[<=6], d_full/d_empty[2]
     static constexpr int tmem_ptr = bars + n_bars * 8;
-    static constexpr int rowtab = tmem_ptr + 16;                  // [128] {float wz1, u32 byte offset of row k inside a swizzled tile}
+    static constexpr int rowtab = tmem_ptr + 16;                  // [128] {float w0, float w1}: axis_cell weights of every lattice index
     static constexpr int kstart = rowtab + M * 8;                 // [G+1]
     static constexpr int pairs = kstart + (MAX_G + 2) * 4;        // [Q/2][2] u8: the two lines of every pair
-    static constexpr int total = pairs + M;
+    static constexpr int axtab = pairs + M;                       // [128] u8: axis_cell lower cell index of every lattice index
+    static constexpr int total = axtab + M;
 };
 static_assert(Smem::total + 1024 <= 227 * 1024, "shared memory budget");
 
@@ -57,10 +58,11 @@ __constant__ float c_epi[4 * 256];
 
 // Per-role wait-time attribution (profiling builds only, tools/decode_bench.py): cycles one thread of each role spends in
 // its barrier waits.  [cta][16]: 0 MMA a_full | 1 MMA W2 | 2 MMA d_empty | 3 MMA total | 4 producer a_empty | 5 producer total |
-// 6 producer row/store phase | 7 epilogue d_full | 8 epilogue total | 9 loader b_empty | 10 loader total
+// 6 producer row/store phase | 7 epilogue d_full | 8 epilogue total | 9 loader b_empty | 10 loader total |
+// 11 producer x-blend (waits for the prefetched gathers) | 12 producer prefetch issue | 13 producer y-blend | 14 producer fence + arrive
 #ifdef GNB_PROFILE_KNOBS
 __device__ unsigned long long g_prof[1024 * 16];
-#define DL2_PROF_DECL unsigned long long prof_acc[4] = {0, 0, 0, 0}; const long long prof_t0 = clock64()
+#define DL2_PROF_DECL unsigned long long prof_acc[6] = {0, 0, 0, 0, 0, 0}; const long long prof_t0 = clock64()
 #define DL2_PROF(i, stmt) do { const long long t_ = clock64(); stmt; prof_acc[i] += (unsigned long long)(clock64() - t_); } while (0)
 #define DL2_PROF_STORE(i, slot) g_prof[blockIdx.x * 16 + (slot)] = prof_acc[i]
 #define DL2_PROF_TOTAL(slot) g_prof[blockIdx.x * 16 + (slot)] = (unsigned long long)(clock64() - prof_t0)
@@ -80,7 +82,7 @@ struct Params {
     const float* tail;         // [COUT][4] {c0, bn3_scale, bn3_shift, 0}
     float* out;                // [B, Q^3, COUT]
     int64_t num_pairs;         // B * Q * Q / 2
-    int dbg;                   // profiling aid (GNB_DL2_DBG): 1 producers idle, 2 no W2 copies, 4 epilogue math skipped
+    int dbg;                   // profiling aid (GNB_DL2_DBG): 1 producers idle, 2 no W2 copies, 4 epilogue math skipped, 8 no A stores, 16 no MMAs
 };
 
 // ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 issue two fp32 operations per instruction) ---------
@@ -127,13 +129,15 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem)
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
     return r;
 }
-// relu + fp16 hi/lo split of two fp32 values (ascending channel order inside the 32-bit words)
+// relu + fp16 hi/lo split of two fp32 values (ascending channel order inside the 32-bit words).  The ReLU rides on the
+// conversions: hi = relu(x) TRUNCATED to fp16 (cvt.rz.relu), so the remainder x - hi is >= 0 for x >= 0 and equals x < 0
+// otherwise, and lo = cvt.rn.relu(remainder) is the rounded remainder or 0 -- 5 instructions per channel pair instead of 7
+// (no FMNMX).  Truncating hi costs one bit: hi + lo carries 21 significant bits (2^-22 relative) instead of 22.
 __device__ __forceinline__ void relu_split2(float2 h, uint32_t& hi, uint32_t& lo) {
-    const float x0 = fmaxf(h.x, 0.f), x1 = fmaxf(h.y, 0.f);
-    hi = pack_f16x2_sat(x0, x1);
+    asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(h.y), "f"(h.x));
     const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-    const float2 r = sub2(make_float2(x0, x1), hf);
-    lo = pack_f16x2_sat(r.x, r.y);
+    const float2 r = sub2(h, hf);
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
 }
 
 // lattice index -> feature-grid cell and weights along one axis (same fp32 arithmetic as gnb_trilinear_sample_grid)
@@ -220,8 +224,8 @@ decode_lattice_kernel(const Params p) {
         int z0, z1;
         float w0, w1;
         axis_cell(k, sq, G, z0, z1, w0, w1);
-        reinterpret_cast<uint2*>(smem + Smem::rowtab)[k] =
-            make_uint2(__float_as_uint(w1), (uint32_t)((k >> 3) * 1024 + (k & 7) * 128));
+        reinterpret_cast<float2*>(smem + Smem::rowtab)[k] = make_float2(w0, w1);
+        (smem + Smem::axtab)[k] = (uint8_t)z0;
     }
     if (warp == 12) {
         if (PAIR) {
@@ -254,63 +258,91 @@ decode_lattice_kernel(const Params p) {
     if (warp < 8) {
         // =========================== A producers ===========================
         // A 16-lane group owns two adjacent D-cells (three slices) of both lines and 4 consecutive channels per lane.
+        // The producers are the critical path of the kernel (the MMA issuer waited on a_full for a third of the run), and each
+        // SM sub-partition runs only two of these warps, so the code is written for instruction-level parallelism: item
+        // decoding by shifts (Q = 128), per-axis cell / weight table in shared memory, corner pointers per pair, and two rows
+        // (eight independent blend -> ReLU -> split chains) computed before their eight stores.
         const int pw = warp;
         const int cp = pw * 2 + (lane >> 4);      // cell pair: cells 2cp, 2cp+1
         const int l16 = lane & 15;
         const bool active = 2 * cp < G;           // G < 32: the surplus groups only pace the barriers
         const int dA = 2 * cp < G ? 2 * cp : G - 1;
-        const int ds[3] = {dA, dA + 1 < G ? dA + 1 : G - 1, dA + 2 < G ? dA + 2 : G - 1};
-        const int* kst = reinterpret_cast<const int*>(smem + Smem::kstart);
-        const int64_t sd = (int64_t)G * G * K;
+        const uint32_t sd = (uint32_t)G * G * K;  // elements per D-slice (<= 2^18)
+        const uint32_t soff[3] = {(uint32_t)dA * sd, (uint32_t)(dA + 1 < G ? dA + 1 : G - 1) * sd, (uint32_t)(dA + 2 < G ? dA + 2 : G - 1) * sd};
         // byte offset of this lane's 8-byte store inside a 128-byte swizzled row: 16-byte unit (l16 >> 1) ^ (k & 7)
         const uint32_t unit = (uint32_t)(l16 >> 1), sub8 = (uint32_t)(l16 & 1) * 8u;
+        const uint32_t axtab = sbase + Smem::axtab, rowtab = sbase + Smem::rowtab, kstab = sbase + Smem::kstart;
+        // read-only tables: plain (non-volatile) shared loads, free to be hoisted and interleaved by the compiler
+        auto lds2 = [](uint32_t addr) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; };
+        auto lds1 = [](uint32_t addr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; };
+        auto ldsb = [](uint32_t addr) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; };
+        // axis_cell of lattice index idx from the tables: {w0, w1, c0, c1}
+        auto axis = [&](int idx) {
+            const uint2 w = lds2(rowtab + idx * 8);
+            const uint32_t c0 = ldsb(axtab + idx);
+            return make_uint4(w.x, w.y, c0, c0 + 1 < (uint32_t)G ? c0 + 1 : (uint32_t)G - 1);
+        };
+        const int k_lo[2] = {(int)lds1(kstab + 4 * (2 * cp < G ? 2 * cp : G)), (int)lds1(kstab + 4 * (2 * cp + 1 < G ? 2 * cp + 1 : G))};
+        const int k_hi[2] = {k_lo[1], (int)lds1(kstab + 4 * (2 * cp + 2 < G ? 2 * cp + 2 : G))};
 
         struct Item { int b, i, j0, j1; };
-        auto item_of = [&](int64_t pr) {
+        auto item_of = [&](uint32_t pr) {          // Q = 128: pr = (b * 128 + i) * 64 + jp
             Item it;
-            const int jp = (int)(pr % QH);
-            it.i = (int)((pr / QH) % Q);
-            it.b = (int)(pr / ((int64_t)QH * Q));
-            it.j0 = pairs[2 * jp];
-            it.j1 = pairs[2 * jp + 1];
+            const uint32_t jp = pr & (uint32_t)(M / 2 - 1);
+            it.i = (int)((pr >> 6) & (uint32_t)(M - 1));
+            it.b = (int)(pr >> 13);
+            const uint32_t pj = lds1(sbase + Smem::pairs + (jp >> 1) * 4);   // four u8 per word: pairs 2w, 2w+1
+            it.j0 = (int)((pj >> ((jp & 1) * 16)) & 0xffu);
+            it.j1 = (int)((pj >> ((jp & 1) * 16 + 8)) & 0xffu);
             return it;
         };
-        // gathers of line `j` for chunk c: [slice][y][x] 16-byte loads
-        auto issue = [&](const Item& it, int j, int c, float4 (&r)[3][2][2]) {
-            int x0, x1, y0, y1;
-            float t0, t1;
-            axis_cell(it.i, sq, G, x0, x1, t0, t1);
-            axis_cell(j, sq, G, y0, y1, t0, t1);
-            const float* ub = p.U + (int64_t)it.b * G * sd + c * KCHUNK + l16 * 4;
+        // the four (y, x) corner columns of lattice line (i, j) of sample b, at this lane's channels of chunk 0
+        auto corners = [&](int b, int i, int j, const float* (&cptr)[4]) {
+            const uint4 ax = axis(i), ay = axis(j);
+            const float* ub = p.U + (size_t)b * G * sd + l16 * 4;
+            cptr[0] = ub + (ay.z * (uint32_t)G + ax.z) * (uint32_t)K;
+            cptr[1] = ub + (ay.z * (uint32_t)G + ax.w) * (uint32_t)K;
+            cptr[2] = ub + (ay.w * (uint32_t)G + ax.z) * (uint32_t)K;
+            cptr[3] = ub + (ay.w * (uint32_t)G + ax.w) * (uint32_t)K;
+        };
+        // gathers of one line for chunk c: [slice][y][x] 16-byte loads
+        auto issue = [&](const float* const (&cptr)[4], int c, float4 (&r)[3][2][2]) {
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                const float* sp = ub + ds[s] * sd;
-                r[s][0][0] = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)y0 * G + x0) * K));
-                r[s][0][1] = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)y0 * G + x1) * K));
-                r[s][1][0] = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)y1 * G + x0) * K));
-                r[s][1][1] = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)y1 * G + x1) * K));
+                const uint32_t o = soff[s] + (uint32_t)c * KCHUNK;
+                r[s][0][0] = __ldg(reinterpret_cast<const float4*>(cptr[0] + o));
+                r[s][0][1] = __ldg(reinterpret_cast<const float4*>(cptr[1] + o));
+                r[s][1][0] = __ldg(reinterpret_cast<const float4*>(cptr[2] + o));
+                r[s][1][1] = __ldg(reinterpret_cast<const float4*>(cptr[3] + o));
             }
         };
 
         float4 nxt[3][2][2];
         DL2_PROF_DECL;
         uint32_t q = 0;  // running chunk counter (slot = q & 1)
-        int64_t pair = blockIdx.x;
-        if (pair < p.num_pairs && active && !(p.dbg & 1)) issue(item_of(pair), item_of(pair).j0, 0, nxt);
-        for (; pair < p.num_pairs; pair += gridDim.x) {
+        const uint32_t npairs = (uint32_t)p.num_pairs;
+        uint32_t pair = blockIdx.x;
+        const float* cA[4];   // corner pointers of line j0 of the current pair
+        if (pair < npairs) {
+            const Item it0 = item_of(pair);
+            corners(it0.b, it0.i, it0.j0, cA);
+            if (active && !(p.dbg & 1)) issue(cA, 0, nxt);
+        }
+        for (; pair < npairs; pair += gridDim.x) {
             const Item it = item_of(pair);
-            int x0, x1, ya0, ya1, yb0, yb1;
-            float wx0, wx1, wy0[2], wy1[2];
-            axis_cell(it.i, sq, G, x0, x1, wx0, wx1);
-            axis_cell(it.j0, sq, G, ya0, ya1, wy0[0], wy1[0]);
-            axis_cell(it.j1, sq, G, yb0, yb1, wy0[1], wy1[1]);
-            const bool same_y = ya0 == yb0;
-
+            const uint4 ax = axis(it.i), aya = axis(it.j0), ayb = axis(it.j1);
+            const float wx0 = __uint_as_float(ax.x), wx1 = __uint_as_float(ax.y);
+            const float wy0[2] = {__uint_as_float(aya.x), __uint_as_float(ayb.x)}, wy1[2] = {__uint_as_float(aya.y), __uint_as_float(ayb.y)};
+            const bool same_y = aya.z == ayb.z;
+            const bool has_next = pair + gridDim.x < npairs;
 
 #pragma unroll 1
             for (int c = 0; c < NCHUNK; ++c, ++q) {
                 const int slot = q & 1;
                 if (active && !(p.dbg & 1)) {
+#ifdef GNB_PROFILE_KNOBS
+                    const long long t_a = clock64();
+#endif
                     // 1. x-blend of the prefetched corners: X[s][y] (4 channels as two packed pairs)
                     float2 X[3][2][2];
                     const float2 vx0 = make_float2(wx0, wx0), vx1 = make_float2(wx1, wx1);
@@ -322,9 +354,23 @@ decode_lattice_kernel(const Params p) {
                             X[s][yy][0] = fma2(make_float2(bq.x, bq.y), vx1, mul2(make_float2(a.x, a.y), vx0));
                             X[s][yy][1] = fma2(make_float2(bq.z, bq.w), vx1, mul2(make_float2(a.z, a.w), vx0));
                         }
+#ifdef GNB_PROFILE_KNOBS
+                    // the clock read must follow the blend: make it depend on one blended value
+                    long long t_b;
+                    asm volatile("{ .reg .f32 t; mov.f32 t, %1; mov.u64 %0, %%clock64; }" : "=l"(t_b) : "f"(X[2][1][1].y) : "memory");
+                    prof_acc[2] += (unsigned long long)(t_b - t_a);
+#endif
                     // 2. prefetch the corners of the next chunk (or of the next pair's first chunk)
-                    if (c + 1 < NCHUNK) issue(it, it.j0, c + 1, nxt);
-                    else if (pair + gridDim.x < p.num_pairs) { const Item ni = item_of(pair + gridDim.x); issue(ni, ni.j0, 0, nxt); }
+                    if (c + 1 < NCHUNK) issue(cA, c + 1, nxt);
+                    else if (has_next) {   // cA is free from here on: it becomes the next pair's line j0
+                        const Item ni = item_of(pair + gridDim.x);
+                        corners(ni.b, ni.i, ni.j0, cA);
+                        issue(cA, 0, nxt);
+                    }
+#ifdef GNB_PROFILE_KNOBS
+                    const long long t_c = clock64();
+                    prof_acc[3] += (unsigned long long)(t_c - t_b);
+#endif
                     // 3. (x, y)-blended slices of both lines: P[l][s] (4 channels as two packed pairs)
                     float2 P[2][3][2];
 #pragma unroll
@@ -337,14 +383,15 @@ decode_lattice_kernel(const Params p) {
                                 for (int h2 = 0; h2 < 2; ++h2) P[l][s][h2] = fma2(X[s][1][h2], vy1, mul2(X[s][0][h2], vy0));
                         } else {
                             // line 1 lies in another y-cell (left-over lines, ~3 % of the pairs): its own gathers
-                            const float* ub = p.U + (int64_t)it.b * G * sd + c * KCHUNK + l16 * 4;
+                            const float* cB[4];
+                            corners(it.b, it.i, it.j1, cB);
 #pragma unroll
                             for (int s = 0; s < 3; ++s) {
-                                const float* sp = ub + ds[s] * sd;
-                                const float4 a00 = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)yb0 * G + x0) * K));
-                                const float4 a10 = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)yb0 * G + x1) * K));
-                                const float4 a01 = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)yb1 * G + x0) * K));
-                                const float4 a11 = __ldg(reinterpret_cast<const float4*>(sp + ((int64_t)yb1 * G + x1) * K));
+                                const uint32_t o = soff[s] + (uint32_t)c * KCHUNK;
+                                const float4 a00 = __ldg(reinterpret_cast<const float4*>(cB[0] + o));
+                                const float4 a10 = __ldg(reinterpret_cast<const float4*>(cB[1] + o));
+                                const float4 a01 = __ldg(reinterpret_cast<const float4*>(cB[2] + o));
+                                const float4 a11 = __ldg(reinterpret_cast<const float4*>(cB[3] + o));
                                 const float2 xa0 = fma2(make_float2(a10.x, a10.y), vx1, mul2(make_float2(a00.x, a00.y), vx0));
                                 const float2 xa1 = fma2(make_float2(a10.z, a10.w), vx1, mul2(make_float2(a00.z, a00.w), vx0));
                                 const float2 xb0 = fma2(make_float2(a11.x, a11.y), vx1, mul2(make_float2(a01.x, a01.y), vx0));
@@ -354,6 +401,11 @@ decode_lattice_kernel(const Params p) {
                             }
                         }
                     }
+#ifdef GNB_PROFILE_KNOBS
+                    long long t_d;
+                    asm volatile("{ .reg .f32 t; mov.f32 t, %1; mov.u64 %0, %%clock64; }" : "=l"(t_d) : "f"(P[1][2][1].y) : "memory");
+                    prof_acc[4] += (unsigned long long)(t_d - t_c);
+#endif
                     // 4. the slot must have been consumed by the tensor core (chunk q - 2)
                     DL2_PROF(0, mbar_wait(a_empty(slot), ((q >> 1) & 1) ^ 1));
 #ifdef GNB_PROFILE_KNOBS
@@ -362,31 +414,47 @@ decode_lattice_kernel(const Params p) {
                     const uint32_t a_addr = sbase + Smem::a + slot * SLOT_BYTES + sub8;  // + part * PART_BYTES + row offset
 #pragma unroll
                     for (int cell = 0; cell < 2; ++cell) {
-                        const int d = 2 * cp + cell;
-                        if (d >= G) break;
+                        if (2 * cp + cell >= G) break;
                         float2 sl[2][2];
 #pragma unroll
                         for (int l = 0; l < 2; ++l) { sl[l][0] = sub2(P[l][cell + 1][0], P[l][cell][0]); sl[l][1] = sub2(P[l][cell + 1][1], P[l][cell][1]); }
-                        const int k_end = kst[d + 1];
-                        auto row = [&](int k) {
-                            uint2 rt;
-                            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rt.x), "=r"(rt.y) : "r"(sbase + Smem::rowtab + k * 8));
-                            const float wz = __uint_as_float(rt.x);
+                        // one row: z-blend, ReLU, fp16 hi/lo split of this lane's 4 channels of both lines -> v[l] = {hi0, hi1, lo0, lo1}
+                        auto row_values = [&](const float wz, uint4 (&v)[2]) {
                             const float2 vz = make_float2(wz, wz);
-                            const uint32_t addr = a_addr + rt.y + ((unit << 4) ^ ((rt.y >> 3) & 0x70u));
 #pragma unroll
                             for (int l = 0; l < 2; ++l) {
-                                uint32_t hi0, lo0, hi1, lo1;
-                                relu_split2(fma2(sl[l][0], vz, P[l][cell][0]), hi0, lo0);
-                                relu_split2(fma2(sl[l][1], vz, P[l][cell][1]), hi1, lo1);
-                                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + (2 * l) * PART_BYTES), "r"(hi0), "r"(hi1) : "memory");
-                                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + (2 * l + 1) * PART_BYTES), "r"(lo0), "r"(lo1) : "memory");
+                                relu_split2(fma2(sl[l][0], vz, P[l][cell][0]), v[l].x, v[l].z);
+                                relu_split2(fma2(sl[l][1], vz, P[l][cell][1]), v[l].y, v[l].w);
                             }
                         };
-                        int k = kst[d];
+                        auto row_store = [&](const int k, const uint4 (&v)[2]) {   // row k: 8-row group k >> 3, 128-byte row k & 7, swizzled unit
+                            const uint32_t addr = a_addr + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u + ((unit ^ (uint32_t)(k & 7)) << 4);
+#ifdef GNB_PROFILE_KNOBS
+                            if (p.dbg & 8) return;   // knock-out: everything but the shared-memory stores
+#endif
+#pragma unroll
+                            for (int l = 0; l < 2; ++l) {
+                                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + (2 * l) * PART_BYTES), "r"(v[l].x), "r"(v[l].y) : "memory");
+                                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + (2 * l + 1) * PART_BYTES), "r"(v[l].z), "r"(v[l].w) : "memory");
+                            }
+                        };
+                        const int k_end = k_hi[cell];
+                        int k = k_lo[cell];
 #pragma unroll 1
-                        for (; k + 1 < k_end; k += 2) { row(k); row(k + 1); }   // two rows = eight independent chains in flight
-                        if (k < k_end) row(k);
+                        for (; k + 1 < k_end; k += 2) {
+                            const float wz0 = __uint_as_float(lds1(rowtab + k * 8 + 4)), wz1 = __uint_as_float(lds1(rowtab + k * 8 + 12));
+                            uint4 v0[2], v1[2];
+                            row_values(wz0, v0);
+                            row_values(wz1, v1);
+                            row_store(k, v0);
+                            row_store(k + 1, v1);
+                        }
+                        if (k < k_end) {
+                            const float wz0 = __uint_as_float(lds1(rowtab + k * 8 + 4));
+                            uint4 v0[2];
+                            row_values(wz0, v0);
+                            row_store(k, v0);
+                        }
                     }
 #ifdef GNB_PROFILE_KNOBS
                     prof_acc[1] += (unsigned long long)(clock64() - t_rows);
@@ -396,12 +464,21 @@ decode_lattice_kernel(const Params p) {
                     // counted into the current phase of a_full
                     mbar_wait(a_empty(slot), ((q >> 1) & 1) ^ 1);
                 }
+#ifdef GNB_PROFILE_KNOBS
+                const long long t_e = clock64();
+#endif
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) arrive_leader(a_full(slot));
+#ifdef GNB_PROFILE_KNOBS
+                prof_acc[5] += (unsigned long long)(clock64() - t_e);
+#endif
             }
         }
-        if (threadIdx.x == 0) { DL2_PROF_STORE(0, 4); DL2_PROF_STORE(1, 6); DL2_PROF_TOTAL(5); }
+        if (threadIdx.x == 0) {
+            DL2_PROF_STORE(0, 4); DL2_PROF_STORE(1, 6); DL2_PROF_TOTAL(5);
+            DL2_PROF_STORE(2, 11); DL2_PROF_STORE(3, 12); DL2_PROF_STORE(4, 13); DL2_PROF_STORE(5, 14);
+        }
     } else if (warp < 12) {
         // =========================== epilogue ===========================
         const int qd = warp & 3;  // TMEM lane quarter this warp may access (warp id mod 4)
@@ -477,6 +554,9 @@ decode_lattice_kernel(const Params p) {
             uint32_t piece = 0, q = 0;
             DL2_PROF_DECL;
             auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+#ifdef GNB_PROFILE_KNOBS
+                if (p.dbg & 16) return;      // knock-out: no MMAs (the commits arrive at once)
+#endif
                 if (PAIR) umma_f16_pair(d, da, db, IDESC_PAIR, acc);
                 else umma_f16(d, da, db, IDESC, acc);
             };
@@ -620,8 +700,11 @@ __global__ void lattice_prep_kernel(const float* __restrict__ W2, const float* _
 }
 
 // CTA pairs need an even grid and an even number of line pairs (both CTAs of a cluster run the same number of items)
-static bool g_use_pair = true;
-static bool g_force_single = false;   // gnb_decode_lattice_set_mode(0): the single-CTA kernel (A/B measurements, tests)
+// The CTA-pair form (tcgen05.mma.cta_group::2) is correct and tested but measured SLOWER than one CTA per SM on B200
+// (22.6 vs 19.8 ms at batch 32: the A producers are the critical path, and lock-stepping two CTAs per chunk adds their
+// variance), so the single-CTA kernel is the default; gnb_decode_lattice_set_mode(1) selects the pair form.
+static bool g_use_pair = false;
+static bool g_want_pair = false;
 
 template <int COUT>
 static int32_t launch(const Params& p, cudaStream_t st) {
@@ -683,7 +766,7 @@ int32_t gnb_decode_lattice(const float* U, int32_t B, int32_t G, int32_t Q, cons
     p.b2s = b2s; p.w3s = w3s; p.tail = tail; p.out = out;
     p.num_pairs = (int64_t)B * Q * (Q / 2);
     p.dbg = profile_knob("GNB_DL2_DBG");
-    dl2::g_use_pair = !(profile_knob("GNB_DL2_SINGLE") != 0 || dl2::g_force_single);
+    dl2::g_use_pair = dl2::g_want_pair;
     if (Cout == 1) return dl2::launch<1>(p, st);
     if (Cout == 2) return dl2::launch<2>(p, st);
     return dl2::launch<3>(p, st);
@@ -697,7 +780,7 @@ __attribute__((visibility("default"))) int32_t gnb_prof_decode_lattice_read(unsi
 #endif
 
 int32_t gnb_decode_lattice_set_mode(int32_t cta_pair) {
-    dl2::g_force_single = cta_pair == 0;
+    dl2::g_want_pair = cta_pair != 0;
     return GNB_OK;
 }
 

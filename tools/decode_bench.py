@@ -54,7 +54,7 @@ if hasattr(lib, "gnb_prof_decode_lattice_read"):
     import ctypes
     import numpy as np
     names = ["mma:a_full", "mma:w2", "mma:d_empty", "mma:total", "prod:a_empty", "prod:total", "prod:rows", "epi:d_full",
-             "epi:total", "load:b_empty", "load:total"]
+             "epi:total", "load:b_empty", "load:total", "prod:xblend", "prod:issue", "prod:yblend", "prod:fence"]
 
     def prof(label):
         buf = np.zeros(1024 * 16, np.uint64)
@@ -67,8 +67,9 @@ if hasattr(lib, "gnb_prof_decode_lattice_read"):
 
     for mode, mname in ((0, "single"), (1, "cta_group::2")):
         _lib.call("gnb_decode_lattice_set_mode", mode)
-        for dbg in (0, 1, 2, 4, 7):
+        for dbg in (0,):
             os.environ["GNB_DL2_DBG"] = str(dbg)
             timeit(f"{mname} dbg={dbg}", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128), n=3)
             prof(f"{mname} dbg={dbg}")
     os.environ["GNB_DL2_DBG"] = "0"
+_lib.call("gnb_decode_lattice_set_mode", 0)
