@@ -58,6 +58,11 @@ __device__ McFast d_mc_fast[256];
 // d_mc_n_base + d_mc_tun_index[key] + k
 constexpr int MC_MAX_ENTRIES = 700 + MC_MAX_TUN;
 __device__ McEntry d_mc_compact[MC_MAX_ENTRIES];
+// the same tilings packed for the emit kernels: 4-bit vertex ids (0..11 cube edges, 12+ centres), no per-byte loads.
+//   order: first-use vertex order, slot j in bits 4j..4j+3 (14 slots), nedge in bits 56..59, ntri in bits 60..63
+//   tri[w]: five triangles per word, triangle t in bits 12*(t%5) .. +11 of word t/5 (corner c in bits 4c..4c+3 of those)
+struct McPacked { unsigned long long order, tri[3]; };
+__device__ McPacked d_mc_packed[MC_MAX_ENTRIES];
 __device__ uint16_t d_mc_entry_id[256 * 64];
 __device__ int d_mc_n_base;
 __device__ uint16_t d_mc_edgemask[256];
@@ -542,6 +547,18 @@ static int ensure_tables() {
         if (n > MC_MAX_ENTRIES) return -1;
         g_mc_n_entries = n;
         if (cudaMemcpyToSymbol(d_mc_compact, compact, sizeof(McEntry) * n) != cudaSuccess) return -1;
+        static McPacked packed[MC_MAX_ENTRIES];
+        for (int i = 0; i < n; ++i) {
+            const McEntry& en = compact[i];
+            McPacked pk = {0ull, {0ull, 0ull, 0ull}};
+            for (int j = 0; j < en.nedge; ++j) pk.order |= (unsigned long long)(en.order[j] & 15) << (4 * j);
+            pk.order |= (unsigned long long)en.nedge << 56;
+            pk.order |= (unsigned long long)en.ntri << 60;
+            for (int t = 0; t < en.ntri; ++t)
+                for (int c = 0; c < 3; ++c) pk.tri[t / 5] |= (unsigned long long)(en.tri[t * 3 + c] & 15) << (12 * (t % 5) + 4 * c);
+            packed[i] = pk;
+        }
+        if (cudaMemcpyToSymbol(d_mc_packed, packed, sizeof(McPacked) * n) != cudaSuccess) return -1;
         if (cudaMemcpyToSymbol(d_mc_entry_id, eid, sizeof(eid)) != cudaSuccess) return -1;
         if (cudaMemcpyToSymbol(d_mc_n_base, &n_base, sizeof(int)) != cudaSuccess) return -1;
     }
@@ -557,7 +574,7 @@ static int ensure_tables() {
 // x = W-1, y = H-1 or z = D-1 do not exist and stay inactive), so rows of cells are rows of the volume.
 // Work is cut into ITEMS = (volume row, 128-value segment): one warp classifies one item with four 16-byte loads per
 // lane (the rows y, y+1 of the slices z, z+1) and gets the x+1 corners of its last cell from the next lane by shuffle.
-// A count block = MC_WARPS consecutive items = a contiguous range of padded cells.
+// Counts (vertices / faces / active cells) are kept per ITEM, so a warp never synchronises with the rest of its CTA.
 constexpr int MC_WARPS = 8, MC_BLOCK = MC_WARPS * 32, MC_SEG = 128;
 struct McRec {          // 512-byte record, read back by the host in ONE copy for the whole batch
     int64_t V, F, A;    // vertices, faces, active cells (cube index not 0 / 255)
@@ -569,7 +586,7 @@ struct McRec {          // 512-byte record, read back by the host in ONE copy fo
 static_assert(sizeof(McRec) == 512, "McRec layout");
 struct McWs {
     uint16_t* codes;    // [D*H*W] cube index | face bits << 8 | tunnel << 14 (0 for the padding cells)
-    int32_t* blockV;    // [nb] per-block counts -> exclusive offsets after the scan
+    int32_t* blockV;    // [nb = nitems] per-item counts -> exclusive offsets after the scan
     int32_t* blockF;    // [nb]
     int32_t* blockA;    // [nb]
     McRec* rec;
@@ -583,7 +600,7 @@ static McGeom geom(int D, int H, int W) {
     g.nvox = (int64_t)D * H * W;
     g.nseg = ceil_div<int64_t>(W, MC_SEG);
     g.nitems = (int64_t)D * H * g.nseg;
-    g.nb = ceil_div<int64_t>(g.nitems, MC_WARPS);
+    g.nb = g.nitems;
     size_t p = align256(sizeof(uint16_t) * g.nvox);
     g.o_blockV = p; p += align256(sizeof(int32_t) * g.nb);
     g.o_blockF = p; p += align256(sizeof(int32_t) * g.nb);
@@ -715,12 +732,13 @@ struct ItemPos { int z, y, x0; int64_t row; bool ok; };
 __device__ __forceinline__ ItemPos item_pos(int64_t item, int lane, int H, const McGeom& g) {
     ItemPos p;
     p.ok = item < g.nitems;
-    const int64_t it = p.ok ? item : 0;
-    p.row = it / g.nseg;
-    const int seg = (int)(it - p.row * g.nseg);
-    p.z = (int)(p.row / H);
-    p.y = (int)(p.row - (int64_t)p.z * H);
-    p.x0 = seg * MC_SEG + lane * 4;
+    // 32-bit divisions: a volume has fewer than 2^31 voxels (checked at the entry points), hence fewer items
+    const unsigned it = p.ok ? (unsigned)item : 0u, nseg = (unsigned)g.nseg;
+    const unsigned row = it / nseg, seg = it - row * nseg, z = row / (unsigned)H;
+    p.row = row;
+    p.z = (int)z;
+    p.y = (int)(row - z * (unsigned)H);
+    p.x0 = (int)seg * MC_SEG + lane * 4;
     return p;
 }
 
@@ -739,6 +757,8 @@ __device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long 
 }
 
 // ---- kernel 1: classify --------------------------------------------------------------------------------------
+// One warp per item, grid-striding over the items of its volume; no CTA-wide synchronisation inside the loop (the counts are
+// kept per item and reduced with shuffles, the data range is accumulated in registers and leaves the CTA once).
 // VEC: W % 4 == 0 and a 16-byte aligned volume -> float4 loads and 8-byte code stores
 template <bool VEC>
 __global__ void __launch_bounds__(MC_BLOCK, 4)
@@ -748,67 +768,68 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
     const float* __restrict__ v = vols + (int64_t)blockIdx.y * nvox;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // the per-index table of the cells without ambiguity (99 % of the active ones) lives in shared memory: a global
-    // table look-up per active cell made this kernel latency-bound (744 us for 32 x 128^3 against ~100 us of HBM time)
+    // table look-up per active cell made this kernel latency-bound
     __shared__ McFast s_fast[256];
-    __shared__ unsigned long long s_cnt[MC_WARPS];
     __shared__ float s_lo[MC_WARPS], s_hi[MC_WARPS];
     s_fast[threadIdx.x] = d_mc_fast[threadIdx.x];
     __syncthreads();
-    float vol_lo = INFINITY, vol_hi = -INFINITY;   // data range over every count block this CTA visits
-    // persistent over the count blocks of the volume: the table is staged once per CTA
-    for (int64_t cb = blockIdx.x; cb < batch.g.nb; cb += gridDim.x) {
-    const ItemPos ip = item_pos(cb * MC_WARPS + warp, lane, H, batch.g);
-    const bool row_ok = ip.ok && ip.z < D - 1 && ip.y < H - 1;
+    // data range: every voxel is row r = 0 of exactly one item (items exist for the last y-row / z-slice too)
     float lo = INFINITY, hi = -INFINITY;
-    int nv = 0, nf = 0, na = 0;
-    unsigned codes4[4] = {0u, 0u, 0u, 0u};
-    // a[r][k]: rows (z,y) (z,y+1) (z+1,y) (z+1,y+1), k = 0..3 own values, k = 4 the next lane's first value
-    float a[4][5];
-    if (row_ok) {
+    for (int64_t item = (int64_t)blockIdx.x * MC_WARPS + warp; item < batch.g.nitems; item += (int64_t)gridDim.x * MC_WARPS) {
+        const ItemPos ip = item_pos(item, lane, H, batch.g);
+        const bool row_ok = ip.z < D - 1 && ip.y < H - 1;
+        int nv = 0, nf = 0, na = 0;
+        unsigned codes4[4] = {0u, 0u, 0u, 0u};
+        // a[r][k]: rows (z,y) (z,y+1) (z+1,y) (z+1,y+1), k = 0..3 own values, k = 4 the next lane's first value
+        float a[4][5];
         const float* __restrict__ r0 = v + ip.row * W;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const float* __restrict__ p = r0 + (r & 1 ? W : 0) + (r & 2 ? (int64_t)H * W : 0);
-            if (VEC) {
-                if (ip.x0 + 3 < W) {
-                    const float4 q = *reinterpret_cast<const float4*>(p + ip.x0);
-                    a[r][0] = q.x; a[r][1] = q.y; a[r][2] = q.z; a[r][3] = q.w;
+            if (r == 0 || row_ok) {
+                const float* __restrict__ p = r0 + (r & 1 ? W : 0) + (r & 2 ? (int64_t)H * W : 0);
+                if (VEC) {
+                    if (ip.x0 + 3 < W) {
+                        const float4 q = *reinterpret_cast<const float4*>(p + ip.x0);
+                        a[r][0] = q.x; a[r][1] = q.y; a[r][2] = q.z; a[r][3] = q.w;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) a[r][k] = 0.f;
+                    }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) a[r][k] = 0.f;
+                    for (int k = 0; k < 4; ++k) a[r][k] = ip.x0 + k < W ? p[ip.x0 + k] : 0.f;
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) a[r][k] = ip.x0 + k < W ? p[ip.x0 + k] : 0.f;
+                for (int k = 0; k < 4; ++k) a[r][k] = 0.f;
             }
         }
-    } else {
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int k = 0; k < 4; ++k)
+            if (ip.x0 + k < W) { lo = fminf(lo, a[0][k]); hi = fmaxf(hi, a[0][k]); }
+        if (row_ok) {   // warp-uniform
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[r][k] = 0.f;
-    }
+            for (int r = 0; r < 4; ++r) a[r][4] = __shfl_down_sync(0xffffffffu, a[r][0], 1);
+            if (lane == 31 && ip.x0 + 4 < W) {   // a wider row continues in the next segment: fetch its first value
 #pragma unroll
-    for (int r = 0; r < 4; ++r) a[r][4] = __shfl_down_sync(0xffffffffu, a[r][0], 1);
-    if (row_ok) {
-        if (lane == 31 && ip.x0 + 4 < W) {   // a wider row continues in the next segment: fetch its first value
-            const float* __restrict__ r0 = v + ip.row * W;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) a[r][4] = r0[(r & 1 ? W : 0) + (r & 2 ? (int64_t)H * W : 0) + ip.x0 + 4];
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int x = ip.x0 + k;
-            if (x < W) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) { lo = fminf(lo, a[r][k]); hi = fmaxf(hi, a[r][k]); }
+                for (int r = 0; r < 4; ++r) a[r][4] = r0[(r & 1 ? W : 0) + (r & 2 ? (int64_t)H * W : 0) + ip.x0 + 4];
             }
-            if (x < W - 1) {
+            // above[r] bit k: a[r][k] > level.  (v > level) == ((double)v - (double)level > 0): both operands are exact in double
+            unsigned above[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                above[r] = 0u;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) above[r] |= (a[r][k] > level ? 1u : 0u) << k;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int x = ip.x0 + k;
+                if (x >= W - 1) continue;
                 // corner i at (dx,dy,dz): 0:000 1:100 2:110 3:010 4:001 5:101 6:111 7:011 ; rows: r = dy + 2 dz
-                // (v > level) == ((double)v - (double)level > 0): both operands are exact in double
-                const int idx = (a[0][k] > level ? 1 : 0) | (a[0][k + 1] > level ? 2 : 0) | (a[1][k + 1] > level ? 4 : 0) |
-                                (a[1][k] > level ? 8 : 0) | (a[2][k] > level ? 16 : 0) | (a[2][k + 1] > level ? 32 : 0) |
-                                (a[3][k + 1] > level ? 64 : 0) | (a[3][k] > level ? 128 : 0);
+                const unsigned b0 = above[0] >> k, b1 = above[1] >> k, b2 = above[2] >> k, b3 = above[3] >> k;
+                const int idx = (int)((b0 & 1u) | (b0 & 2u) | ((b1 & 2u) << 1) | ((b1 & 1u) << 3) | ((b2 & 1u) << 4) | ((b2 & 2u) << 4) |
+                                      ((b3 & 2u) << 5) | ((b3 & 1u) << 7));
                 if (idx != 0 && idx != 255) {
                     const McFast fe = s_fast[idx];
                     int code = idx;
@@ -825,43 +846,41 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
                 }
             }
         }
-    }
-    if (ip.ok) {   // code words of the lane's four cells (padding cells / rows: 0)
-        uint16_t* __restrict__ dst = ws.codes + ip.row * W + ip.x0;
-        if (VEC) {
-            if (ip.x0 + 3 < W)
-                *reinterpret_cast<uint2*>(dst) = make_uint2(codes4[0] | (codes4[1] << 16), codes4[2] | (codes4[3] << 16));
-        } else {
+        {   // code words of the lane's four cells (padding cells / rows: 0)
+            uint16_t* __restrict__ dst = ws.codes + ip.row * W + ip.x0;
+            if (VEC) {
+                if (ip.x0 + 3 < W)
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(codes4[0] | (codes4[1] << 16), codes4[2] | (codes4[3] << 16));
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (ip.x0 + k < W) dst[k] = (uint16_t)codes4[k];
+                for (int k = 0; k < 4; ++k)
+                    if (ip.x0 + k < W) dst[k] = (uint16_t)codes4[k];
+            }
+        }
+        // item totals
+        unsigned long long tot = pack3(nv, nf, na);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0) {
+            ws.blockV[item] = (int)(tot & 0x1FFFFF);
+            ws.blockF[item] = (int)((tot >> 21) & 0x1FFFFF);
+            ws.blockA[item] = (int)(tot >> 42);
         }
     }
-    // block totals + data range
-    unsigned long long tot = pack3(nv, nf, na);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        tot += __shfl_xor_sync(0xffffffffu, tot, o);
         lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
         hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if (lane == 0) { s_cnt[warp] = tot; s_lo[warp] = lo; s_hi[warp] = hi; }
+    if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned long long t = 0;
 #pragma unroll
-        for (int w = 0; w < MC_WARPS; ++w) { t += s_cnt[w]; lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
-        ws.blockV[cb] = (int)(t & 0x1FFFFF);
-        ws.blockF[cb] = (int)((t >> 21) & 0x1FFFFF);
-        ws.blockA[cb] = (int)(t >> 42);
-        vol_lo = fminf(vol_lo, lo);
-        vol_hi = fmaxf(vol_hi, hi);
-    }
-    __syncthreads();   // s_cnt / s_lo / s_hi are reused by the next count block
-    }
-    if (threadIdx.x == 0 && vol_lo <= vol_hi) {   // every voxel is a corner of some cell when D,H,W >= 2: one atomic pair per CTA
-        atomicMin(&ws.rec->min_enc, mc_enc(vol_lo));
-        atomicMax(&ws.rec->max_enc, mc_enc(vol_hi));
+        for (int w = 0; w < MC_WARPS; ++w) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
+        if (lo <= hi) {   // one atomic pair per CTA
+            atomicMin(&ws.rec->min_enc, mc_enc(lo));
+            atomicMax(&ws.rec->max_enc, mc_enc(hi));
+        }
     }
 }
 
@@ -924,39 +943,32 @@ __global__ void mc_bases_kernel(McBatch batch, int N) {
 }
 
 // ---- kernel 3: compaction of the active cells (order preserving) + the vertex work list ---------------------------
-// Same item mapping as the classifier.  Besides the active-cell records it leaves, in the (still unwritten) output row of
-// every vertex, the pair (cell, vertex slot) that the vertex kernel consumes: one thread per VERTEX there, no divergence
-// over cells that own 0..5 vertices.
+// Same item mapping as the classifier: one warp per item, no CTA-wide synchronisation in the loop.  Besides the active-cell
+// records it leaves, in the (still unwritten) output row of every vertex, the pair (cell, vertex slot) that the vertex
+// kernel consumes: one thread per VERTEX there, no divergence over cells that own 0..5 vertices.
 template <bool VEC>
-__global__ void __launch_bounds__(MC_BLOCK)
+__global__ void __launch_bounds__(MC_BLOCK, 4)
 mc_compact_kernel(int D, int H, int W, McBatch batch, int n_entries, float* __restrict__ verts) {
-    // persistent CTAs; the tiling table (vertex order of every tiling) and the per-index fast table live in shared memory
-    extern __shared__ __align__(16) uint8_t s_raw[];
-    McEntry* s_tab = reinterpret_cast<McEntry*>(s_raw);
+    // the first-use vertex order of every tiling (one 64-bit word each) and the per-index fast table live in shared memory
+    extern __shared__ __align__(16) unsigned long long s_order[];
     __shared__ McFast s_fast[256];
-    __shared__ unsigned long long s_w[MC_WARPS];
-    {
-        const int words = (n_entries * (int)sizeof(McEntry) + 3) / 4;
-        const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(d_mc_compact);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(s_raw);
-        for (int i = threadIdx.x; i < words; i += MC_BLOCK) dst[i] = src[i];
-        s_fast[threadIdx.x] = d_mc_fast[threadIdx.x];
-    }
+    for (int i = threadIdx.x; i < n_entries; i += MC_BLOCK) s_order[i] = d_mc_packed[i].order;
+    s_fast[threadIdx.x] = d_mc_fast[threadIdx.x];
     __syncthreads();
     const McWs ws = carve(batch, blockIdx.y);
-    const int64_t nb = batch.g.nb;
+    const int64_t nitems = batch.g.nitems;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_base = d_mc_n_base;
     const int64_t vbase = ws.rec->vbase;
     const int total_active = (int)ws.rec->A;
-    for (int64_t cb = blockIdx.x; cb < nb; cb += gridDim.x) {
-        const int a0 = ws.blockA[cb];
-        const int a1 = cb + 1 < nb ? ws.blockA[cb + 1] : total_active;
-        if (a1 == a0) continue;  // no active cell in this count block (uniform branch)
-        const ItemPos ip = item_pos(cb * MC_WARPS + warp, lane, H, batch.g);
+    for (int64_t item = (int64_t)blockIdx.x * MC_WARPS + warp; item < nitems; item += (int64_t)gridDim.x * MC_WARPS) {
+        const int a0 = ws.blockA[item];
+        const int a1 = item + 1 < nitems ? ws.blockA[item + 1] : total_active;
+        if (a1 == a0) continue;  // no active cell in this item (warp-uniform)
+        const ItemPos ip = item_pos(item, lane, H, batch.g);
         int code[4] = {0, 0, 0, 0}, cv[4] = {0, 0, 0, 0}, cf[4] = {0, 0, 0, 0};
         int nv = 0, nf = 0, na = 0;
-        if (ip.ok) {
+        {
             const uint16_t* __restrict__ src = ws.codes + ip.row * W + ip.x0;
             if (VEC) {
                 if (ip.x0 + 3 < W) {
@@ -981,16 +993,8 @@ mc_compact_kernel(int D, int H, int W, McBatch batch, int n_entries, float* __re
             }
         }
         const unsigned long long mine = pack3(nv, nf, na);
-        const unsigned long long incl = warp_incl_scan(mine, lane);
-        __syncthreads();   // s_w of the previous count block has been consumed
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        unsigned long long base = 0;
-#pragma unroll
-        for (int w = 0; w < MC_WARPS; ++w)
-            if (w < warp) base += s_w[w];
-        const unsigned long long ex = base + incl - mine;
-        int ov = ws.blockV[cb] + (int)(ex & 0x1FFFFF), of = ws.blockF[cb] + (int)((ex >> 21) & 0x1FFFFF);
+        const unsigned long long ex = warp_incl_scan(mine, lane) - mine;
+        int ov = ws.blockV[item] + (int)(ex & 0x1FFFFF), of = ws.blockF[item] + (int)((ex >> 21) & 0x1FFFFF);
         int oa = a0 + (int)(ex >> 42);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -998,17 +1002,18 @@ mc_compact_kernel(int D, int H, int W, McBatch batch, int n_entries, float* __re
             if (idx == 0 || idx == 255) continue;
             const int x = ip.x0 + k;
             const int cell = (int)(ip.row * W + x);
-            // the face kernel only needs the tiling: its position in the compact table goes into .w
+            // the face kernel only needs the tiling: its position in the packed table goes into .w
             const int key = idx * 64 + ((code[k] >> 8) & 63), tun = code[k] >> 14;
             const int eid = tun ? n_base + d_mc_tun_index[key] + tun - 1 : ((code[k] >> 8) ? d_mc_entry_id[key] : s_fast[idx].eid0);
             ws.active[oa] = make_int4(cell, ov, of, eid);
             if (cv[k]) {   // vertex work list, in first-use order of the cell's tiling
-                const McEntry& en = s_tab[eid];
-                const unsigned own = s_fast[idx].edgemask & owned_mask(ip.z, ip.y, x);
+                unsigned long long ow = s_order[eid];
+                const int nedge = (int)((ow >> 56) & 15);
+                const unsigned own = (s_fast[idx].edgemask & owned_mask(ip.z, ip.y, x)) | 0x3000u;   // centres (12, 13) are always this cell's
                 int vid = ov;
-                for (int j = 0; j < en.nedge; ++j) {
-                    const int e = en.order[j];
-                    if (e < 12 && !((own >> e) & 1)) continue;
+                for (int j = 0; j < nedge; ++j, ow >>= 4) {
+                    const int e = (int)(ow & 15);
+                    if (!((own >> e) & 1)) continue;
                     float* __restrict__ row = verts + (vbase + vid) * 3;
                     row[0] = __int_as_float(cell);
                     row[1] = __int_as_float(e);
@@ -1134,48 +1139,56 @@ mc_vertices_kernel(const float* __restrict__ vols, int D, int H, int W, float le
 }
 
 // ---- kernel 5: faces -------------------------------------------------------------------------------------------
-// Persistent CTAs with the whole tiling table (~70 KB) in shared memory: the per-byte reads of a tiling's vertex order and
-// triangle list were what bound this kernel (L1 at 80 %, lg / mio throttle) when they went to global memory.
+// One thread per active cell.  The tiling comes as four 64-bit words (McPacked: two 16-byte loads, L1-resident table), every
+// triangle corner is a 4-bit vertex id decoded with shifts and looked up in the edge map directly -- no per-byte table reads
+// and no locally indexed vertex array (both bound the previous form of this kernel: L1 at 80 %, lg / mio throttle).
+constexpr unsigned mc_bits12(const int8_t (&t)[12], int bit) {
+    unsigned m = 0;
+    for (int e = 0; e < 12; ++e) m |= (unsigned)((t[e] >> bit) & 1) << e;
+    return m;
+}
+constexpr int8_t k_edge_axis[12] = {0, 1, 0, 1, 0, 1, 0, 1, 2, 2, 2, 2};
+constexpr int8_t k_edge_dx[12] = {0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 0};
+constexpr int8_t k_edge_dy[12] = {0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 1};
+constexpr int8_t k_edge_dz[12] = {0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0};
+constexpr unsigned MC_AX0 = mc_bits12(k_edge_axis, 0), MC_AX1 = mc_bits12(k_edge_axis, 1), MC_DX = mc_bits12(k_edge_dx, 0),
+                   MC_DY = mc_bits12(k_edge_dy, 0), MC_DZ = mc_bits12(k_edge_dz, 0);
+
 __global__ void __launch_bounds__(MC_BLOCK)
-mc_faces_kernel(int D, int H, int W, int ascent, McBatch batch, int n_entries, int32_t* __restrict__ faces) {
-    extern __shared__ __align__(16) uint8_t s_raw[];
-    McEntry* s_tab = reinterpret_cast<McEntry*>(s_raw);
-    {
-        const int words = (n_entries * (int)sizeof(McEntry) + 3) / 4;
-        const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(d_mc_compact);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(s_raw);
-        for (int i = threadIdx.x; i < words; i += MC_BLOCK) dst[i] = src[i];
-    }
-    __syncthreads();
+mc_faces_kernel(int D, int H, int W, int ascent, McBatch batch, int32_t* __restrict__ faces) {
     const McWs ws = carve(batch, blockIdx.y);
-    const int64_t A = ws.rec->A, fbase = ws.rec->fbase;
+    const int64_t a = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
+    if (a >= ws.rec->A) return;
+    const int4 act = ws.active[a];
+    const uint4* __restrict__ pk = reinterpret_cast<const uint4*>(&d_mc_packed[act.w]);
+    const uint4 q0 = __ldg(pk), q1 = __ldg(pk + 1);
+    const unsigned long long tri[3] = {(unsigned long long)q0.z | ((unsigned long long)q0.w << 32),
+                                       (unsigned long long)q1.x | ((unsigned long long)q1.y << 32),
+                                       (unsigned long long)q1.z | ((unsigned long long)q1.w << 32)};
+    const int nf = (int)(q0.y >> 28);
+    if (nf == 0) return;
     const int64_t vol_n = batch.g.nvox;
-    for (int64_t a = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x; a < A; a += (int64_t)gridDim.x * MC_BLOCK) {
-        const int4 act = ws.active[a];
-        const McEntry& en = s_tab[act.w];
-        const int nf = en.ntri;
-        if (nf == 0) continue;
-        const CellPos p = cell_pos(act.x, H, W);
-        int32_t vid[12 + MC_MAX_CEN];
-#pragma unroll
-        for (int e = 0; e < 12 + MC_MAX_CEN; ++e) vid[e] = -1;
-        for (int k = 0; k < en.nedge; ++k) {
-            const int e = en.order[k];
-            if (e >= 12) {
-                vid[e] = ws.edge_map[(int64_t)(3 + (e - 12)) * vol_n + act.x];
-            } else {
-                const int z0 = p.z + c_edge_dz[e], y0 = p.y + c_edge_dy[e], x0 = p.x + c_edge_dx[e];
-                vid[e] = ws.edge_map[(int64_t)c_edge_axis[e] * vol_n + ((int64_t)z0 * H + y0) * W + x0];
-            }
-        }
-        int64_t f = fbase + act.z;
-        for (int t = 0; t < nf; ++t, ++f) {
-            const int a0 = vid[en.tri[t * 3]], b = vid[en.tri[t * 3 + 1]], cc = vid[en.tri[t * 3 + 2]];
-            // native winding: right-hand normal towards lower values ('descent'); 'ascent' reverses the columns
-            faces[f * 3 + 0] = ascent ? cc : a0;
-            faces[f * 3 + 1] = b;
-            faces[f * 3 + 2] = ascent ? a0 : cc;
-        }
+    const int HW = H * W;
+    const int32_t* __restrict__ em = ws.edge_map;
+    // vertex id of vertex e of this cell (cube edge: the edge map entry of its lower end point; centre: the cell's own plane)
+    auto vid_of = [&](unsigned e) {
+        if (e >= 12u) return em[(int64_t)(3 + (e - 12u)) * vol_n + act.x];
+        const unsigned ax = ((MC_AX0 >> e) & 1u) | (((MC_AX1 >> e) & 1u) << 1);
+        const int off = (int)((MC_DZ >> e) & 1u) * HW + (int)((MC_DY >> e) & 1u) * W + (int)((MC_DX >> e) & 1u);
+        return em[(int64_t)ax * vol_n + act.x + off];
+    };
+    int32_t* __restrict__ out = faces + (ws.rec->fbase + act.z) * 3;
+    unsigned long long w = tri[0];
+    for (int t = 0; t < nf; ++t) {
+        if (t == 5) w = tri[1];
+        if (t == 10) w = tri[2];
+        const unsigned c3 = (unsigned)w & 0xFFFu;
+        w >>= 12;
+        const int a0 = vid_of(c3 & 15u), b = vid_of((c3 >> 4) & 15u), cc = vid_of(c3 >> 8);
+        // native winding: right-hand normal towards lower values ('descent'); 'ascent' reverses the columns
+        out[t * 3 + 0] = ascent ? cc : a0;
+        out[t * 3 + 1] = b;
+        out[t * 3 + 2] = ascent ? a0 : cc;
     }
 }
 
@@ -1196,9 +1209,10 @@ static int32_t count_batch(const float* v, int N, int D, int H, int W, float lev
     mc_init_kernel<<<ceil_div(N, 128), 128, 0, st>>>(b, N);
     const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0) && ((reinterpret_cast<uintptr_t>(ws_) & 7) == 0) &&
                      (ws_stride % 8 == 0);
-    // persistent CTAs: ~8 per SM over the whole batch, each striding over the count blocks of its volume
-    const int64_t per_vol = ceil_div<int64_t>((int64_t)sm_count() * 8, N);
-    const dim3 grid((unsigned)(b.g.nb < per_vol ? b.g.nb : per_vol), N);
+    // persistent CTAs: 4 per SM over the whole batch, each warp striding over the items of its volume
+    const int64_t per_vol = ceil_div<int64_t>((int64_t)sm_count() * 4, N);
+    const int64_t item_ctas = ceil_div<int64_t>(b.g.nitems, MC_WARPS);
+    const dim3 grid((unsigned)(item_ctas < per_vol ? item_ctas : per_vol), N);
     if (vec) mc_classify_kernel<true><<<grid, MC_BLOCK, 0, st>>>(v, D, H, W, level, b);
     else mc_classify_kernel<false><<<grid, MC_BLOCK, 0, st>>>(v, D, H, W, level, b);
     mc_scan_kernel<<<N, 1024, 0, st>>>(b);
@@ -1215,27 +1229,18 @@ static int32_t emit_batch(const float* v, int N, int D, int H, int W, float leve
     Spacing sp = {{spacing_host[0], spacing_host[1], spacing_host[2]}};
     if (ensure_tables() != 0) { set_error("gnb_mc_emit: table upload failed"); return GNB_ERR_CUDA; }
     const int n_entries = g_mc_n_entries;
-    const int tab_smem = n_entries * (int)sizeof(McEntry) + 16;
-    const int64_t per_vol = ceil_div<int64_t>((int64_t)sm_count() * 3, N);   // ~3 CTAs (70 KB of shared memory each) per SM over the batch
+    const int tab_smem = n_entries * (int)sizeof(unsigned long long);
     {
+        const int64_t per_vol = ceil_div<int64_t>((int64_t)sm_count() * 4, N);
+        const int64_t item_ctas = ceil_div<int64_t>(b.g.nitems, MC_WARPS);
         const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(ws_) & 7) == 0) && (ws_stride % 8 == 0);
-        const dim3 grid((unsigned)(b.g.nb < per_vol ? b.g.nb : per_vol), N);
-        if (vec) {
-            GNB_CUDA(cudaFuncSetAttribute(mc_compact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_smem));
-            mc_compact_kernel<true><<<grid, MC_BLOCK, tab_smem, st>>>(D, H, W, b, n_entries, verts);
-        } else {
-            GNB_CUDA(cudaFuncSetAttribute(mc_compact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_smem));
-            mc_compact_kernel<false><<<grid, MC_BLOCK, tab_smem, st>>>(D, H, W, b, n_entries, verts);
-        }
+        const dim3 grid((unsigned)(item_ctas < per_vol ? item_ctas : per_vol), N);
+        if (vec) mc_compact_kernel<true><<<grid, MC_BLOCK, tab_smem, st>>>(D, H, W, b, n_entries, verts);
+        else mc_compact_kernel<false><<<grid, MC_BLOCK, tab_smem, st>>>(D, H, W, b, n_entries, verts);
     }
     mc_vertices_kernel<<<dim3((unsigned)ceil_div<int64_t>(max_verts, MC_BLOCK), N), MC_BLOCK, 0, st>>>(
         v, D, H, W, level, sp, ggm, b, verts, normals, values, ggm_at);
-    {
-        GNB_CUDA(cudaFuncSetAttribute(mc_faces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_smem));
-        int64_t gx = ceil_div<int64_t>(max_active, MC_BLOCK);
-        if (gx > per_vol) gx = per_vol;
-        mc_faces_kernel<<<dim3((unsigned)gx, N), MC_BLOCK, tab_smem, st>>>(D, H, W, ascent, b, n_entries, faces);
-    }
+    mc_faces_kernel<<<dim3((unsigned)ceil_div<int64_t>(max_active, MC_BLOCK), N), MC_BLOCK, 0, st>>>(D, H, W, ascent, b, faces);
     return check_launch("gnb_mc_emit");
 }
 
