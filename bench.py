@@ -504,7 +504,10 @@ def run_ours(args, rank, world):
             "config": _workload_config(B, world, V, F),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps,
+                    "outputs": "verts, faces, volume_gradient_magnitude, warp_field of every mesh + per-point NOCS / confidence; "
+                               "normals and volume_value are opt-in in HostPredictor (with_normals=True) and are neither "
+                               "computed nor copied in this leg -- the device-timed `value` computes them"},
             "gpu_launches": launches, "clocks": clocks, "wall_s": round(wall, 3), "stages_ms": stages_ms,
             "unet3d": _unet_report(stages_ms.get("unet3d"), B, peaks), "unet3d_g128": unet_g128,
             "per_category": per_category, "gather_meshes": gather}

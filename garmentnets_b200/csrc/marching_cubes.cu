@@ -742,24 +742,18 @@ __device__ __forceinline__ ItemPos item_pos(int64_t item, int lane, int H, const
     return p;
 }
 
-// warp-inclusive scan of three small counts packed into one 64-bit word (21 bits each: a block holds 1024 cells with at
-// most 14 + 2 vertices / 14 faces each)
-__device__ __forceinline__ unsigned long long pack3(int a, int b, int c) {
-    return (unsigned long long)a | ((unsigned long long)b << 21) | ((unsigned long long)c << 42);
-}
-__device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long v, int lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-    }
-    return v;
-}
-
 // ---- kernel 1: classify --------------------------------------------------------------------------------------
-// One warp per item, grid-striding over the items of its volume; no CTA-wide synchronisation inside the loop (the counts are
-// kept per item and reduced with shuffles, the data range is accumulated in registers and leaves the CTA once).
+// One warp walks a STRIP of MC_STRIP consecutive rows (same slab pair z, z+1, same 128-cell segment) with a two-row window:
+// every row is loaded once per slab pair instead of four times, and what is kept of it is one bit per value (v > level).  An
+// item whose 4 x 129 corner bits are all equal (three items out of four in a garment volume) is recognised with a handful of
+// bit operations and one ballot; the cube indices, table look-ups and counts are computed only for the items the surface
+// crosses.  No CTA-wide synchronisation inside the loop: counts are kept per item (one REDUX per item), the data range is
+// accumulated in registers and leaves the CTA once.
 // VEC: W % 4 == 0 and a 16-byte aligned volume -> float4 loads and 8-byte code stores
+constexpr int MC_STRIP = 16;
+// nv (<= 128 * 14), nf (<= 128 * 14), na (<= 128) of one item in one 32-bit word
+__device__ __forceinline__ unsigned pack3s(int nv, int nf, int na) { return (unsigned)nv | ((unsigned)nf << 11) | ((unsigned)na << 22); }
+
 template <bool VEC>
 __global__ void __launch_bounds__(MC_BLOCK, 4)
 mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float level, McBatch batch) {
@@ -773,98 +767,116 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
     __shared__ float s_lo[MC_WARPS], s_hi[MC_WARPS];
     s_fast[threadIdx.x] = d_mc_fast[threadIdx.x];
     __syncthreads();
-    // data range: every voxel is row r = 0 of exactly one item (items exist for the last y-row / z-slice too)
+    const unsigned nseg = (unsigned)batch.g.nseg, ygroups = (unsigned)ceil_div(H, MC_STRIP);
+    const int64_t nstrips = (int64_t)D * ygroups * nseg;
+    const int64_t HW = (int64_t)H * W;
+    // data range: every voxel is in row (z, y) of exactly one item
     float lo = INFINITY, hi = -INFINITY;
-    for (int64_t item = (int64_t)blockIdx.x * MC_WARPS + warp; item < batch.g.nitems; item += (int64_t)gridDim.x * MC_WARPS) {
-        const ItemPos ip = item_pos(item, lane, H, batch.g);
-        const bool row_ok = ip.z < D - 1 && ip.y < H - 1;
-        int nv = 0, nf = 0, na = 0;
-        unsigned codes4[4] = {0u, 0u, 0u, 0u};
-        // a[r][k]: rows (z,y) (z,y+1) (z+1,y) (z+1,y+1), k = 0..3 own values, k = 4 the next lane's first value
-        float a[4][5];
-        const float* __restrict__ r0 = v + ip.row * W;
+
+    // four values of row `p` at this lane's x0 (0 beyond the row)
+    auto load4 = [&](const float* __restrict__ p, int x0, float (&q)[4]) {
+        if (VEC) {
+            if (x0 + 3 < W) {
+                const float4 t = *reinterpret_cast<const float4*>(p + x0);
+                q[0] = t.x; q[1] = t.y; q[2] = t.z; q[3] = t.w;
+            } else {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            if (r == 0 || row_ok) {
-                const float* __restrict__ p = r0 + (r & 1 ? W : 0) + (r & 2 ? (int64_t)H * W : 0);
-                if (VEC) {
-                    if (ip.x0 + 3 < W) {
-                        const float4 q = *reinterpret_cast<const float4*>(p + ip.x0);
-                        a[r][0] = q.x; a[r][1] = q.y; a[r][2] = q.z; a[r][3] = q.w;
-                    } else {
+                for (int k = 0; k < 4; ++k) q[k] = 0.f;
+            }
+        } else {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) a[r][k] = 0.f;
+            for (int k = 0; k < 4; ++k) q[k] = x0 + k < W ? p[x0 + k] : 0.f;
+        }
+    };
+    // (v > level) == ((double)v - (double)level > 0): both operands are exact in double
+    auto bits4 = [&](const float (&q)[4]) {
+        return (q[0] > level ? 1u : 0u) | (q[1] > level ? 2u : 0u) | (q[2] > level ? 4u : 0u) | (q[3] > level ? 8u : 0u);
+    };
+    // 5-bit masks of the rows (z, y) and (z+1, y) at this lane (bit 4 = the next lane's first value), packed lo | hi << 8
+    auto row_masks = [&](const float* __restrict__ pz, const float* __restrict__ pz1, int x0, const float (&qa)[4], const float (&qb)[4]) {
+        const unsigned m4 = bits4(qa) | (bits4(qb) << 8);
+        unsigned nb = __shfl_down_sync(0xffffffffu, m4, 1);
+        if (lane == 31) nb = x0 + 4 < W ? ((pz[x0 + 4] > level ? 1u : 0u) | (pz1[x0 + 4] > level ? 0x100u : 0u)) : 0u;
+        return m4 | ((nb & 0x101u) << 4);
+    };
+
+    for (int64_t strip = (int64_t)blockIdx.x * MC_WARPS + warp; strip < nstrips; strip += (int64_t)gridDim.x * MC_WARPS) {
+        const unsigned su = (unsigned)strip, seg = su % nseg, t = su / nseg, yg = t % ygroups;
+        const int z = (int)(t / ygroups);
+        const int y0 = (int)yg * MC_STRIP, y1 = y0 + MC_STRIP < H ? y0 + MC_STRIP : H;
+        const int x0 = (int)seg * MC_SEG + lane * 4;
+        unsigned valid = 0u;   // cells (x, x+1) that exist along x
+#pragma unroll
+        for (int k = 0; k < 4; ++k) valid |= (x0 + k < W - 1 ? 1u : 0u) << k;
+        const float* __restrict__ rz = v + (int64_t)z * HW;   // slab z
+        const bool zin = z < D - 1;
+        float qa[4], qb[4];
+        load4(rz + (int64_t)y0 * W, x0, qa);
+        unsigned mprev = 0u;
+        if (zin) {
+            load4(rz + HW + (int64_t)y0 * W, x0, qb);
+            mprev = row_masks(rz + (int64_t)y0 * W, rz + HW + (int64_t)y0 * W, x0, qa, qb);
+        }
+        for (int y = y0; y < y1; ++y) {
+            const int64_t item = ((int64_t)z * H + y) * nseg + seg;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (x0 + k < W) { lo = fminf(lo, qa[k]); hi = fmaxf(hi, qa[k]); }
+            unsigned codes4[4] = {0u, 0u, 0u, 0u};
+            unsigned tot = 0u;
+            if (zin && y < H - 1) {   // warp-uniform
+                const float* __restrict__ pc = rz + (int64_t)(y + 1) * W;
+                load4(pc, x0, qa);
+                load4(pc + HW, x0, qb);
+                const unsigned mnext = row_masks(pc, pc + HW, x0, qa, qb);
+                // rows r = dy + 2 dz: r0 = (z,y) r1 = (z,y+1) r2 = (z+1,y) r3 = (z+1,y+1)
+                const unsigned m0 = mprev & 0x1Fu, m2 = mprev >> 8, m1 = mnext & 0x1Fu, m3 = mnext >> 8;
+                const unsigned any = m0 | m1 | m2 | m3, all = m0 & m1 & m2 & m3;
+                const unsigned act = (any | (any >> 1)) & ~(all & (all >> 1)) & valid;   // bit k: cell k is neither empty nor full
+                if (__ballot_sync(0xffffffffu, act != 0u) != 0u) {
+                    int nv = 0, nf = 0, na = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (!((act >> k) & 1u)) continue;
+                        // corner i at (dx,dy,dz): 0:000 1:100 2:110 3:010 4:001 5:101 6:111 7:011
+                        const unsigned b0 = m0 >> k, b1 = m1 >> k, b2 = m2 >> k, b3 = m3 >> k;
+                        const int idx = (int)((b0 & 3u) | ((b1 & 2u) << 1) | ((b1 & 1u) << 3) | ((b2 & 3u) << 4) | ((b3 & 2u) << 5) | ((b3 & 1u) << 7));
+                        const McFast fe = s_fast[idx];
+                        int code = idx;
+                        unsigned cnt = fe.cnt0;
+                        if (fe.resolve) {   // ambiguous faces / interior ambiguity: the rare slow path reads its eight values again
+                            const float* __restrict__ c0 = rz + (int64_t)y * W + x0 + k;
+                            const float val[8] = {c0[0], c0[1], c0[W + 1], c0[W], c0[HW], c0[HW + 1], c0[HW + W + 1], c0[HW + W]};
+                            code = mc_resolve(val, level, idx);
+                            cnt = mc_counts(code);
+                        }
+                        codes4[k] = (unsigned)code;
+                        na += 1;
+                        nf += cnt & 15;
+                        nv += __popc(fe.edgemask & owned_mask(z, y, x0 + k)) + (cnt >> 4);
                     }
+                    tot = __reduce_add_sync(0xffffffffu, pack3s(nv, nf, na));
+                }
+                mprev = mnext;
+            } else if (y + 1 < y1) {
+                load4(rz + (int64_t)(y + 1) * W, x0, qa);   // last slab: only the data range needs the rows
+            }
+            {   // code words of the lane's four cells (padding cells / rows: 0)
+                uint16_t* __restrict__ dst = ws.codes + ((int64_t)z * H + y) * W + x0;
+                if (VEC) {
+                    if (x0 + 3 < W)
+                        *reinterpret_cast<uint2*>(dst) = make_uint2(codes4[0] | (codes4[1] << 16), codes4[2] | (codes4[3] << 16));
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) a[r][k] = ip.x0 + k < W ? p[ip.x0 + k] : 0.f;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) a[r][k] = 0.f;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (ip.x0 + k < W) { lo = fminf(lo, a[0][k]); hi = fmaxf(hi, a[0][k]); }
-        if (row_ok) {   // warp-uniform
-#pragma unroll
-            for (int r = 0; r < 4; ++r) a[r][4] = __shfl_down_sync(0xffffffffu, a[r][0], 1);
-            if (lane == 31 && ip.x0 + 4 < W) {   // a wider row continues in the next segment: fetch its first value
-#pragma unroll
-                for (int r = 0; r < 4; ++r) a[r][4] = r0[(r & 1 ? W : 0) + (r & 2 ? (int64_t)H * W : 0) + ip.x0 + 4];
-            }
-            // above[r] bit k: a[r][k] > level.  (v > level) == ((double)v - (double)level > 0): both operands are exact in double
-            unsigned above[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                above[r] = 0u;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) above[r] |= (a[r][k] > level ? 1u : 0u) << k;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int x = ip.x0 + k;
-                if (x >= W - 1) continue;
-                // corner i at (dx,dy,dz): 0:000 1:100 2:110 3:010 4:001 5:101 6:111 7:011 ; rows: r = dy + 2 dz
-                const unsigned b0 = above[0] >> k, b1 = above[1] >> k, b2 = above[2] >> k, b3 = above[3] >> k;
-                const int idx = (int)((b0 & 1u) | (b0 & 2u) | ((b1 & 2u) << 1) | ((b1 & 1u) << 3) | ((b2 & 1u) << 4) | ((b2 & 2u) << 4) |
-                                      ((b3 & 2u) << 5) | ((b3 & 1u) << 7));
-                if (idx != 0 && idx != 255) {
-                    const McFast fe = s_fast[idx];
-                    int code = idx;
-                    unsigned cnt = fe.cnt0;
-                    if (fe.resolve) {   // ambiguous faces / interior ambiguity: the rare slow path
-                        const float val[8] = {a[0][k], a[0][k + 1], a[1][k + 1], a[1][k], a[2][k], a[2][k + 1], a[3][k + 1], a[3][k]};
-                        code = mc_resolve(val, level, idx);
-                        cnt = mc_counts(code);
-                    }
-                    codes4[k] = (unsigned)code;
-                    na += 1;
-                    nf += cnt & 15;
-                    nv += __popc(fe.edgemask & owned_mask(ip.z, ip.y, x)) + (cnt >> 4);
+                    for (int k = 0; k < 4; ++k)
+                        if (x0 + k < W) dst[k] = (uint16_t)codes4[k];
                 }
             }
-        }
-        {   // code words of the lane's four cells (padding cells / rows: 0)
-            uint16_t* __restrict__ dst = ws.codes + ip.row * W + ip.x0;
-            if (VEC) {
-                if (ip.x0 + 3 < W)
-                    *reinterpret_cast<uint2*>(dst) = make_uint2(codes4[0] | (codes4[1] << 16), codes4[2] | (codes4[3] << 16));
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (ip.x0 + k < W) dst[k] = (uint16_t)codes4[k];
+            if (lane == 0) {
+                ws.blockV[item] = (int)(tot & 0x7FFu);
+                ws.blockF[item] = (int)((tot >> 11) & 0x7FFu);
+                ws.blockA[item] = (int)(tot >> 22);
             }
-        }
-        // item totals
-        unsigned long long tot = pack3(nv, nf, na);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if (lane == 0) {
-            ws.blockV[item] = (int)(tot & 0x1FFFFF);
-            ws.blockF[item] = (int)((tot >> 21) & 0x1FFFFF);
-            ws.blockA[item] = (int)(tot >> 42);
         }
     }
 #pragma unroll
@@ -992,10 +1004,16 @@ mc_compact_kernel(int D, int H, int W, McBatch batch, int n_entries, float* __re
                 }
             }
         }
-        const unsigned long long mine = pack3(nv, nf, na);
-        const unsigned long long ex = warp_incl_scan(mine, lane) - mine;
-        int ov = ws.blockV[item] + (int)(ex & 0x1FFFFF), of = ws.blockF[item] + (int)((ex >> 21) & 0x1FFFFF);
-        int oa = a0 + (int)(ex >> 42);
+        const unsigned mine = pack3s(nv, nf, na);
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const unsigned ex = incl - mine;
+        int ov = ws.blockV[item] + (int)(ex & 0x7FFu), of = ws.blockF[item] + (int)((ex >> 11) & 0x7FFu);
+        int oa = a0 + (int)(ex >> 22);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int idx = code[k] & 255;
@@ -1066,13 +1084,15 @@ __device__ __forceinline__ void store_vertex(int64_t row, const float c[3], floa
         i2 = i2 < 0 ? 0 : (i2 > W - 1 ? W - 1 : i2);
         ggm_at[row] = ggm[(i0 * H + i1) * W + i2];
     }
-    const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(g[0], g[0]), __fmul_rn(g[1], g[1])), __fmul_rn(g[2], g[2]));
-    const float nrm = __fsqrt_rn(n2);
-    if (nrm > 0.f) { g[0] = __fdiv_rn(g[0], nrm); g[1] = __fdiv_rn(g[1], nrm); g[2] = __fdiv_rn(g[2], nrm); }
-    normals[row * 3 + 0] = g[0];
-    normals[row * 3 + 1] = g[1];
-    normals[row * 3 + 2] = g[2];
-    values[row] = val;
+    if (normals != nullptr) {
+        const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(g[0], g[0]), __fmul_rn(g[1], g[1])), __fmul_rn(g[2], g[2]));
+        const float nrm = __fsqrt_rn(n2);
+        if (nrm > 0.f) { g[0] = __fdiv_rn(g[0], nrm); g[1] = __fdiv_rn(g[1], nrm); g[2] = __fdiv_rn(g[2], nrm); }
+        normals[row * 3 + 0] = g[0];
+        normals[row * 3 + 1] = g[1];
+        normals[row * 3 + 2] = g[2];
+    }
+    if (values != nullptr) values[row] = val;
 }
 
 // one thread per VERTEX (work list left in the vertex rows by the compaction kernel)
@@ -1101,16 +1121,18 @@ mc_vertices_kernel(const float* __restrict__ vols, int D, int H, int W, float le
         }
         const float cc[3] = {(float)(acc[0] / (double)n), (float)(acc[1] / (double)n), (float)(acc[2] / (double)n)};
         float val[8], vmax = -INFINITY;
+        float g[3] = {0.f, 0.f, 0.f};
+        if (normals != nullptr || values != nullptr) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             val[i] = v[((int64_t)(p.z + c_corner_dz[i]) * H + (p.y + c_corner_dy[i])) * W + (p.x + c_corner_dx[i])];
             vmax = fmaxf(vmax, val[i]);
         }
         // cell-centre gradient: mean of the four parallel edge differences per axis
-        float g[3];
         g[0] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(val[4] - val[0], val[5] - val[1]), val[6] - val[2]), val[7] - val[3]), 0.25f);
         g[1] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(val[3] - val[0], val[2] - val[1]), val[7] - val[4]), val[6] - val[5]), 0.25f);
         g[2] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(val[1] - val[0], val[2] - val[3]), val[5] - val[4]), val[6] - val[7]), 0.25f);
+        }
         store_vertex(row, cc, g, vmax, sp, ggm, D, H, W, verts, normals, values, ggm_at);
         ws.edge_map[(int64_t)(3 + ci) * vol_n + cell] = (int)vid;
         return;
@@ -1120,13 +1142,15 @@ mc_vertices_kernel(const float* __restrict__ vols, int D, int H, int W, float le
     edge_vertex(v, H, W, level, p, e, cc, t, lo, hi);
     // values: max of the data over the cells that share the edge (local maximum near the vertex)
     float vmax = -INFINITY;
+    if (values != nullptr)
     for (int dz = (ax == 2 ? 0 : -1); dz <= 1; ++dz)
         for (int dy = (ax == 1 ? 0 : -1); dy <= 1; ++dy)
             for (int dx = (ax == 0 ? 0 : -1); dx <= 1; ++dx)
                 vmax = fmaxf(vmax, vol_at(v, D, H, W, lo[0] + dz, lo[1] + dy, lo[2] + dx));
     // normals: central-difference gradient at the two end points, blended with t, normalised
-    float g[3];
+    float g[3] = {0.f, 0.f, 0.f};
     const float tt = (float)t;
+    if (normals != nullptr)
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         const int dz = q == 0, dy = q == 1, dx = q == 2;
@@ -1209,10 +1233,10 @@ static int32_t count_batch(const float* v, int N, int D, int H, int W, float lev
     mc_init_kernel<<<ceil_div(N, 128), 128, 0, st>>>(b, N);
     const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0) && ((reinterpret_cast<uintptr_t>(ws_) & 7) == 0) &&
                      (ws_stride % 8 == 0);
-    // persistent CTAs: 4 per SM over the whole batch, each warp striding over the items of its volume
+    // persistent CTAs: 4 per SM over the whole batch, each warp striding over the strips of its volume
     const int64_t per_vol = ceil_div<int64_t>((int64_t)sm_count() * 4, N);
-    const int64_t item_ctas = ceil_div<int64_t>(b.g.nitems, MC_WARPS);
-    const dim3 grid((unsigned)(item_ctas < per_vol ? item_ctas : per_vol), N);
+    const int64_t strip_ctas = ceil_div<int64_t>((int64_t)D * ceil_div(H, MC_STRIP) * b.g.nseg, MC_WARPS);
+    const dim3 grid((unsigned)(strip_ctas < per_vol ? strip_ctas : per_vol), N);
     if (vec) mc_classify_kernel<true><<<grid, MC_BLOCK, 0, st>>>(v, D, H, W, level, b);
     else mc_classify_kernel<false><<<grid, MC_BLOCK, 0, st>>>(v, D, H, W, level, b);
     mc_scan_kernel<<<N, 1024, 0, st>>>(b);
@@ -1288,7 +1312,7 @@ int32_t gnb_mc_count(const float* v, int32_t D, int32_t H, int32_t W, float leve
 int32_t gnb_mc_emit(const float* v, int32_t D, int32_t H, int32_t W, float level, const double* spacing_host,
                     int32_t ascent, const float* ggm, void* ws_, int64_t n_active, int64_t n_verts, float* verts,
                     int32_t* faces, float* normals, float* values, float* ggm_at_verts, void* stream) {
-    GNB_REQUIRE(v && ws_ && verts && faces && normals && values && spacing_host, "gnb_mc_emit: null pointer");
+    GNB_REQUIRE(v && ws_ && verts && faces && spacing_host, "gnb_mc_emit: null pointer");
     GNB_REQUIRE(D >= 2 && H >= 2 && W >= 2, "gnb_mc_emit: volume must be at least 2x2x2");
     const McGeom g = geom(D, H, W);
     return emit_batch(v, 1, D, H, W, level, spacing_host, ascent, ggm, ws_, g.total, n_active, n_verts, verts, faces, normals,
@@ -1310,7 +1334,7 @@ int32_t gnb_mc_emit_batch(const float* v, int32_t N, int32_t D, int32_t H, int32
                           const double* spacing_host, int32_t ascent, const float* ggm, void* ws, int64_t ws_stride,
                           int64_t max_active, int64_t max_verts, float* verts, int32_t* faces, float* normals,
                           float* values, float* ggm_at_verts, void* stream) {
-    GNB_REQUIRE(v && ws && verts && faces && normals && values && spacing_host, "gnb_mc_emit_batch: null pointer");
+    GNB_REQUIRE(v && ws && verts && faces && spacing_host, "gnb_mc_emit_batch: null pointer");
     GNB_REQUIRE(N >= 1 && N <= 65535, "gnb_mc_emit_batch: 1 <= N <= 65535 volumes");
     GNB_REQUIRE(D >= 2 && H >= 2 && W >= 2, "gnb_mc_emit_batch: volumes must be at least 2x2x2");
     return emit_batch(v, N, D, H, W, level, spacing_host, ascent, ggm, ws, ws_stride, max_active, max_verts, verts, faces,

@@ -633,7 +633,7 @@ def gaussian_gradient_magnitude_batched(v: torch.Tensor, sigma: float) -> torch.
 
 
 def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0, 1.0), gradient_direction: str = "ascent",
-                         ggm: Optional[torch.Tensor] = None, return_packed: bool = False):
+                         ggm: Optional[torch.Tensor] = None, return_packed: bool = False, with_normals: bool = True):
     """Marching cubes of N volumes [N,D,H,W] in seven launches and ONE host synchronisation: classify / scan for the
     whole batch, the N 512-byte records come back in a single device->host copy, then compaction, one vertex launch (a
     thread per vertex) and one face launch (a thread per active cell) write every mesh into shared [sum V] / [sum F]
@@ -641,7 +641,10 @@ def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0,
     Returns a list of (verts, faces, normals, values, ggm_at) views or the exception skimage would raise for that volume
     (ValueError: level outside the data range, RuntimeError: no surface).  ``return_packed`` adds the shared buffers:
     ``{"verts": f32[sum V,3], "vptr": host i64[N+1] row offsets, "faces": i32[sum F,3], "fptr", "normals", "values",
-    "ggm_at"}`` (volumes without a mesh own zero rows)."""
+    "ggm_at"}`` (volumes without a mesh own zero rows).  ``with_normals=False`` skips the per-vertex normals and values
+    (``None`` in their place): the reference stores them (predict.py:193-200) but nothing downstream reads them.
+    The triangulation follows the MC33 structure but is NOT pinned to scikit-image's Lewiner tables: vertex / face order and
+    the tiling of ambiguous cells can differ from ``skimage.measure.marching_cubes``."""
     import ctypes
     import numpy as np
     volumes = _req(volumes, torch.float32, "volumes")
@@ -663,14 +666,14 @@ def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0,
     sumV, sumF = int(totals[:, 0].sum()), int(totals[:, 1].sum())
     verts = torch.empty((sumV, 3), dtype=torch.float32, device=dev)
     faces = torch.empty((sumF, 3), dtype=torch.int32, device=dev)
-    normals = torch.empty((sumV, 3), dtype=torch.float32, device=dev)
-    values = torch.empty((sumV,), dtype=torch.float32, device=dev)
+    normals = torch.empty((sumV, 3), dtype=torch.float32, device=dev) if with_normals else None
+    values = torch.empty((sumV,), dtype=torch.float32, device=dev) if with_normals else None
     ggm_at = torch.empty((sumV,), dtype=torch.float32, device=dev) if ggm is not None else None
     if sumV > 0:
         sp = (ctypes.c_double * 3)(*[float(x) for x in spacing])
         _lib.call("gnb_mc_emit_batch", volumes.data_ptr(), N, D, H, W, float(level), ctypes.cast(sp, ctypes.c_void_p).value,
                   1 if gradient_direction == "ascent" else 0, _ptr(ggm), ws.data_ptr(), ws_bytes, int(totals[:, 2].max()),
-                  int(totals[:, 0].max()), verts.data_ptr(), faces.data_ptr(), normals.data_ptr(), values.data_ptr(), _ptr(ggm_at), _stream())
+                  int(totals[:, 0].max()), verts.data_ptr(), faces.data_ptr(), _ptr(normals), _ptr(values), _ptr(ggm_at), _stream())
     out = []
     for i in range(N):
         V, Fc, _, vb, fb = (int(t) for t in totals[i])
@@ -679,8 +682,8 @@ def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0,
         elif V == 0:
             out.append(RuntimeError("No surface found at the given iso value."))
         else:
-            out.append((verts[vb:vb + V], faces[fb:fb + Fc], normals[vb:vb + V], values[vb:vb + V],
-                        ggm_at[vb:vb + V] if ggm_at is not None else None))
+            out.append((verts[vb:vb + V], faces[fb:fb + Fc], normals[vb:vb + V] if with_normals else None,
+                        values[vb:vb + V] if with_normals else None, ggm_at[vb:vb + V] if ggm_at is not None else None))
     if return_packed:
         vptr = np.zeros(N + 1, np.int64)
         np.cumsum(totals[:, 0], out=vptr[1:])

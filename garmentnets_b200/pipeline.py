@@ -463,9 +463,10 @@ class ConvImplicitWNFPipeline(nn.Module):
     @torch.no_grad()
     def predict(self, data, volume_size: int = 128, gradient_sigma: float = 0.5, iso_surface_level: float = 0.5,
                 gradient_direction: str = "ascent", index: Optional[CloudIndex] = None, fps_starts=None,
-                keep_volume: bool = False) -> List[Dict[str, torch.Tensor]]:
+                keep_volume: bool = False, with_normals: bool = True) -> List[Dict[str, torch.Tensor]]:
         """Device version of the reference's per-sample loop predict.py:138-187, for a whole batch.
-        Returns one dict per sample with the arrays predict.py writes under ``marching_cubes_mesh`` / ``point_cloud``."""
+        Returns one dict per sample with the arrays predict.py writes under ``marching_cubes_mesh`` / ``point_cloud``.
+        ``with_normals=False`` leaves out ``normals`` / ``volume_value`` (written by the reference, read by nothing)."""
         marks = getattr(self, "stage_marks", None)  # optional [(name, cuda event)] sink used by bench.py
         order = ("pointnet2", "aggregator", "unet3d", "dense_decode", "ggm", "marching_cubes", "surface_decode")
 
@@ -500,7 +501,7 @@ class ConvImplicitWNFPipeline(nn.Module):
         ggm = ops.gaussian_gradient_magnitude_batched(wnf, gradient_sigma)
         mark("ggm")
         mcs, packed = ops.marching_cubes_batch(wnf, iso_surface_level, (spacing,) * 3, gradient_direction, ggm,
-                                               return_packed=True)
+                                               return_packed=True, with_normals=with_normals)
         mark("marching_cubes")
         # warp field of every mesh vertex of the batch in one fused launch (gather + MLP on tcgen05)
         dec = self.surface_decoder
@@ -520,13 +521,16 @@ class ConvImplicitWNFPipeline(nn.Module):
                      "normals": torch.full((1, 3), nan, device=dev), "volume_value": torch.full((1,), nan, device=dev),
                      "volume_gradient_magnitude": torch.full((1,), nan, device=dev),
                      "warp_field": torch.full((1, 3), nan, device=dev)}
+                if not with_normals:
+                    del r["normals"], r["volume_value"]
             elif isinstance(mc, Exception):
                 raise mc  # skimage's RuntimeError ("No surface found") is not caught by the reference either
             else:
                 verts, faces, normals, values, ggm_at = mc
                 warp = warp_all[int(vptr[b]):int(vptr[b + 1])]
-                r = {"verts": verts, "faces": faces, "normals": normals, "volume_value": values,
-                     "volume_gradient_magnitude": ggm_at, "warp_field": warp}
+                r = {"verts": verts, "faces": faces, "volume_gradient_magnitude": ggm_at, "warp_field": warp}
+                if with_normals:
+                    r.update(normals=normals, volume_value=values)
             if keep_volume:
                 r["wnf_volume"] = wnf[b]
                 r["wnf_ggm"] = ggm[b]
@@ -547,15 +551,20 @@ class HostPredictor:
     prediction) are copied device -> host in SIX+2 bulk transfers into pinned staging buffers on a separate copy stream,
     so the transfers of batch i overlap the kernels of batch i+1.  ``result`` waits for the transfers of one ticket and
     returns per-sample dicts of numpy views into the staging buffers; a view stays valid until ``depth`` further batches
-    have been submitted."""
+    have been submitted.
+
+    ``with_normals`` (default False): the per-vertex ``normals`` / ``volume_value`` arrays the reference also stores
+    (predict.py:193-200) are opt-in here -- nothing downstream reads them (eval.py uses verts, faces, the gradient
+    magnitude and the warp field), and they are 36 % of the device -> host bytes of a batch."""
 
     MESH_KEYS = (("verts", "verts"), ("faces", "faces"), ("normals", "normals"), ("volume_value", "values"),
                  ("volume_gradient_magnitude", "ggm_at"), ("warp_field", "warp_field"))
 
-    def __init__(self, model: "ConvImplicitWNFPipeline", depth: int = 2, **predict_kwargs):
+    def __init__(self, model: "ConvImplicitWNFPipeline", depth: int = 2, with_normals: bool = False, **predict_kwargs):
         self.model = model
         self.depth = int(depth)
-        self.kw = predict_kwargs
+        self.kw = dict(predict_kwargs, with_normals=bool(with_normals))
+        self.with_normals = bool(with_normals)
         self.copy_stream = torch.cuda.Stream()
         self._staging = [dict() for _ in range(self.depth)]
         self._n = 0
@@ -618,6 +627,8 @@ class HostPredictor:
                 r = {"verts": np.full((1, 3), nan, np.float32), "faces": np.zeros((1, 3), np.int32),
                      "normals": np.full((1, 3), nan, np.float32), "volume_value": np.full((1,), nan, np.float32),
                      "volume_gradient_magnitude": np.full((1,), nan, np.float32), "warp_field": np.full((1, 3), nan, np.float32)}
+                if not self.with_normals:
+                    del r["normals"], r["volume_value"]
             elif err is not None:
                 raise err
             else:

@@ -305,12 +305,14 @@ int32_t gnb_gaussian_gradient_magnitude_batched(const float* v, int32_t nvol, in
  * ref: predict.py:172-181 `marching_cubes(wnf, level, spacing, gradient_direction, method='lewiner')`
  * + the ggm lookup at trunc(vert/spacing).
  * MC33 structure (face test, interior test, tunnel tilings; PARITY UNPINNED vs scikit-image's tables).
- * Two phases.  gnb_mc_count classifies the (D-1)(H-1)(W-1) cells (one warp per volume row: 16-byte loads, neighbour
- * corners by shuffle), scans the per-block counts and returns the vertex / face / active-cell totals in counts_host[3]
+ * Two phases.  gnb_mc_count classifies the (D-1)(H-1)(W-1) cells (one warp walks a strip of volume rows with a two-row
+ * window of "value > level" bits: 16-byte loads, neighbour bits by shuffle, one ballot skips the rows the surface does not
+ * cross), scans the per-row counts and returns the vertex / face / active-cell totals in counts_host[3]
  * (it synchronises `stream`).  gnb_mc_emit (n_active, n_verts = those totals) compacts the active cells, then writes
  *   verts f32[V,3] (axis0,axis1,axis2)*spacing, faces i32[F,3], normals f32[V,3], values f32[V],
  *   ggm_at_verts f32[V] (ggm may be NULL)
- * with one thread per vertex / per active cell.
+ * with one thread per vertex / per active cell.  normals and / or values may be NULL: they are then not computed (the
+ * reference stores them in prediction.zarr, predict.py:193-200, but nothing downstream reads them).
  * Vertex numbering = first-use order of a sequential axis0->axis1->axis2 cell scan; faces in cell order.
  * ws: workspace of gnb_mc_workspace_bytes(D,H,W) bytes, shared by both calls.  D*H*W < 2^31. */
 int64_t gnb_mc_workspace_bytes(int32_t D, int32_t H, int32_t W);

@@ -201,25 +201,29 @@ def test_folded_final_conv_equals_two_step(setup):
 
 
 @pytest.mark.gpu
-def test_host_predictor_matches_device_predict(setup):
+@pytest.mark.parametrize("with_normals", [True, False])
+def test_host_predictor_matches_device_predict(setup, with_normals):
     """The host-buffer API (pinned staging, copy stream, double buffering) returns exactly what predict() leaves on the
-    device, for every sample and for consecutive overlapping submissions."""
+    device, for every sample and for consecutive overlapping submissions.  normals / volume_value are opt-in
+    (``with_normals``): without them the other arrays are unchanged and the two are neither computed nor copied."""
     from garmentnets_b200.pipeline import HostPredictor
     model, d, index = setup["model"], setup["d"], setup["index"]
     ref = model.predict(setup["data"], volume_size=32, index=index)   # synthetic.build_pipeline fixes the FPS starts
     ref = [{k: v.cpu().numpy() for k, v in r.items()} for r in ref]
     nocs_ref = model._last_point_outputs["pred_nocs"].cpu().numpy()
-    hp = HostPredictor(model, depth=2, volume_size=32)
+    keys = ("verts", "faces", "volume_gradient_magnitude", "warp_field") + (("normals", "volume_value") if with_normals else ())
+    hp = HostPredictor(model, depth=2, volume_size=32, with_normals=with_normals)
     host = {k: torch.from_numpy(v).pin_memory() for k, v in d.items()}
     tickets = [hp.submit(host["x"], host["pos"], host["batch"], index=index) for _ in range(2)]
     for t in tickets:
         res = hp.result(t)
         assert len(res) == len(ref)
         for got, want in zip(res, ref):
-            for k in ("verts", "faces", "normals", "volume_value", "volume_gradient_magnitude", "warp_field"):
+            assert set(got) == set(keys)
+            for k in keys:
                 assert got[k].dtype == want[k].dtype and np.array_equal(got[k], want[k]), k
         assert np.array_equal(hp.point_outputs(t)["pred_nocs"], nocs_ref)
-        assert t["d2h_bytes"] == sum(v.nbytes for r in ref for v in r.values()) + 2 * nocs_ref.nbytes
+        assert t["d2h_bytes"] == sum(r[k].nbytes for r in ref for k in keys) + 2 * nocs_ref.nbytes
 
 
 @pytest.mark.gpu
