@@ -581,7 +581,8 @@ struct McRec {          // 512-byte record, read back by the host in ONE copy fo
     int64_t vbase, fbase;  // first row of this volume in the concatenated vertex / face outputs of the batch
     int64_t pad0[27];
     unsigned min_enc, max_enc;  // byte 256: order-preserving encodings of the data range
-    unsigned pad1[62];
+    int n_resolve;              // cells whose tiling needs the face / interior tests (listed in the `active` area during counting)
+    unsigned pad1[61];
 };
 static_assert(sizeof(McRec) == 512, "McRec layout");
 struct McWs {
@@ -822,7 +823,7 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (x0 + k < W) { lo = fminf(lo, qa[k]); hi = fmaxf(hi, qa[k]); }
-            unsigned codes4[4] = {0u, 0u, 0u, 0u};
+            unsigned long long codes = 0ull;   // the lane's four 16-bit code words
             unsigned tot = 0u;
             if (zin && y < H - 1) {   // warp-uniform
                 const float* __restrict__ pc = rz + (int64_t)(y + 1) * W;
@@ -832,30 +833,31 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
                 // rows r = dy + 2 dz: r0 = (z,y) r1 = (z,y+1) r2 = (z+1,y) r3 = (z+1,y+1)
                 const unsigned m0 = mprev & 0x1Fu, m2 = mprev >> 8, m1 = mnext & 0x1Fu, m3 = mnext >> 8;
                 const unsigned any = m0 | m1 | m2 | m3, all = m0 & m1 & m2 & m3;
-                const unsigned act = (any | (any >> 1)) & ~(all & (all >> 1)) & valid;   // bit k: cell k is neither empty nor full
+                unsigned act = (any | (any >> 1)) & ~(all & (all >> 1)) & valid;   // bit k: cell k is neither empty nor full
                 if (__ballot_sync(0xffffffffu, act != 0u) != 0u) {
-                    int nv = 0, nf = 0, na = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (!((act >> k) & 1u)) continue;
+                    unsigned cnt3 = 0u;
+                    // one copy of the per-cell code (a loop over the set bits, not four unrolled bodies): the classifier must
+                    // stay within 64 registers for 32 resident warps per SM
+#pragma unroll 1
+                    while (act) {
+                        const int k = __ffs(act) - 1;
+                        act &= act - 1u;
                         // corner i at (dx,dy,dz): 0:000 1:100 2:110 3:010 4:001 5:101 6:111 7:011
                         const unsigned b0 = m0 >> k, b1 = m1 >> k, b2 = m2 >> k, b3 = m3 >> k;
                         const int idx = (int)((b0 & 3u) | ((b1 & 2u) << 1) | ((b1 & 1u) << 3) | ((b2 & 3u) << 4) | ((b3 & 2u) << 5) | ((b3 & 1u) << 7));
                         const McFast fe = s_fast[idx];
-                        int code = idx;
-                        unsigned cnt = fe.cnt0;
-                        if (fe.resolve) {   // ambiguous faces / interior ambiguity: the rare slow path reads its eight values again
-                            const float* __restrict__ c0 = rz + (int64_t)y * W + x0 + k;
-                            const float val[8] = {c0[0], c0[1], c0[W + 1], c0[W], c0[HW], c0[HW + 1], c0[HW + W + 1], c0[HW + W]};
-                            code = mc_resolve(val, level, idx);
-                            cnt = mc_counts(code);
+                        const int code = idx;
+                        const unsigned cnt = fe.cnt0;
+                        if (fe.resolve) {
+                            // ambiguous faces / interior ambiguity (about 1 % of the active cells): the face and interior tests
+                            // run in mc_resolve_kernel, which patches the code word and the item's counts; here the cell is only
+                            // listed (the `active` area is free until the compaction) and counted with its fb = 0 tiling
+                            reinterpret_cast<int*>(ws.active)[atomicAdd(&ws.rec->n_resolve, 1)] = (int)(((int64_t)z * H + y) * W + x0 + k);
                         }
-                        codes4[k] = (unsigned)code;
-                        na += 1;
-                        nf += cnt & 15;
-                        nv += __popc(fe.edgemask & owned_mask(z, y, x0 + k)) + (cnt >> 4);
+                        codes |= (unsigned long long)(unsigned)code << (16 * k);
+                        cnt3 += pack3s(__popc(fe.edgemask & owned_mask(z, y, x0 + k)) + (int)(cnt >> 4), (int)(cnt & 15), 1);
                     }
-                    tot = __reduce_add_sync(0xffffffffu, pack3s(nv, nf, na));
+                    tot = __reduce_add_sync(0xffffffffu, cnt3);
                 }
                 mprev = mnext;
             } else if (y + 1 < y1) {
@@ -864,12 +866,11 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
             {   // code words of the lane's four cells (padding cells / rows: 0)
                 uint16_t* __restrict__ dst = ws.codes + ((int64_t)z * H + y) * W + x0;
                 if (VEC) {
-                    if (x0 + 3 < W)
-                        *reinterpret_cast<uint2*>(dst) = make_uint2(codes4[0] | (codes4[1] << 16), codes4[2] | (codes4[3] << 16));
+                    if (x0 + 3 < W) *reinterpret_cast<uint2*>(dst) = make_uint2((unsigned)codes, (unsigned)(codes >> 32));
                 } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (x0 + k < W) dst[k] = (uint16_t)codes4[k];
+                        if (x0 + k < W) dst[k] = (uint16_t)(codes >> (16 * k));
                 }
             }
             if (lane == 0) {
@@ -893,6 +894,33 @@ mc_classify_kernel(const float* __restrict__ vols, int D, int H, int W, float le
             atomicMin(&ws.rec->min_enc, mc_enc(lo));
             atomicMax(&ws.rec->max_enc, mc_enc(hi));
         }
+    }
+}
+
+// ---- kernel 1b: face / interior tests of the listed cells ----------------------------------------------------------
+// One thread per listed cell: the resolved code word replaces the provisional one (cube index only) and the differences of
+// its triangle / centre-vertex counts go to the item's counts with integer atomics (commutative: the result is deterministic).
+__global__ void __launch_bounds__(128)
+mc_resolve_kernel(const float* __restrict__ vols, int D, int H, int W, float level, McBatch batch) {
+    const McWs ws = carve(batch, blockIdx.y);
+    const float* __restrict__ v = vols + (int64_t)blockIdx.y * batch.g.nvox;
+    const int n = ws.rec->n_resolve;
+    const int* __restrict__ list = reinterpret_cast<const int*>(ws.active);
+    const int64_t HW = (int64_t)H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int cell = list[i];
+        const int idx = ws.codes[cell] & 255;
+        const float* __restrict__ c0 = v + cell;
+        const float val[8] = {c0[0], c0[1], c0[W + 1], c0[W], c0[HW], c0[HW + 1], c0[HW + W + 1], c0[HW + W]};
+        const int code = mc_resolve(val, level, idx);
+        if (code == idx) continue;
+        ws.codes[cell] = (uint16_t)code;
+        const unsigned c_new = mc_counts(code), c_old = d_mc_fast[idx].cnt0;
+        const CellPos p = cell_pos(cell, H, W);
+        const int64_t item = ((int64_t)p.z * H + p.y) * batch.g.nseg + p.x / MC_SEG;
+        const int dv = (int)(c_new >> 4) - (int)(c_old >> 4), df = (int)(c_new & 15) - (int)(c_old & 15);
+        if (dv) atomicAdd(&ws.blockV[item], dv);
+        if (df) atomicAdd(&ws.blockF[item], df);
     }
 }
 
@@ -964,6 +992,7 @@ mc_compact_kernel(int D, int H, int W, McBatch batch, int n_entries, float* __re
     // the first-use vertex order of every tiling (one 64-bit word each) and the per-index fast table live in shared memory
     extern __shared__ __align__(16) unsigned long long s_order[];
     __shared__ McFast s_fast[256];
+    __shared__ int4 s_cells[MC_WARPS][MC_SEG];   // per warp: the active cells of the item in flight
     for (int i = threadIdx.x; i < n_entries; i += MC_BLOCK) s_order[i] = d_mc_packed[i].order;
     s_fast[threadIdx.x] = d_mc_fast[threadIdx.x];
     __syncthreads();
@@ -974,12 +1003,13 @@ mc_compact_kernel(int D, int H, int W, McBatch batch, int n_entries, float* __re
     const int64_t vbase = ws.rec->vbase;
     const int total_active = (int)ws.rec->A;
     for (int64_t item = (int64_t)blockIdx.x * MC_WARPS + warp; item < nitems; item += (int64_t)gridDim.x * MC_WARPS) {
+        // every load of the item is issued before the first one is needed (the loop is bound by memory latency): the
+        // active-cell offsets that decide whether the item has work, its vertex / face bases and its code words
+        const ItemPos ip = item_pos(item, lane, H, batch.g);
         const int a0 = ws.blockA[item];
         const int a1 = item + 1 < nitems ? ws.blockA[item + 1] : total_active;
-        if (a1 == a0) continue;  // no active cell in this item (warp-uniform)
-        const ItemPos ip = item_pos(item, lane, H, batch.g);
+        const int bv = ws.blockV[item], bf = ws.blockF[item];
         int code[4] = {0, 0, 0, 0}, cv[4] = {0, 0, 0, 0}, cf[4] = {0, 0, 0, 0};
-        int nv = 0, nf = 0, na = 0;
         {
             const uint16_t* __restrict__ src = ws.codes + ip.row * W + ip.x0;
             if (VEC) {
@@ -992,16 +1022,20 @@ mc_compact_kernel(int D, int H, int W, McBatch batch, int n_entries, float* __re
                 for (int k = 0; k < 4; ++k)
                     if (ip.x0 + k < W - 1) code[k] = src[k];
             }
+        }
+        if (a1 == a0) continue;  // no active cell in this item (warp-uniform)
+        // owned-edge mask of the item's cells: the (z, y) part is the same for the whole row, x = 0 adds three edges
+        const unsigned own_row = owned_mask(ip.z, ip.y, 1), own_x0 = owned_mask(ip.z, ip.y, 0);
+        int nv = 0, nf = 0, na = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int idx = code[k] & 255;
-                if (idx != 0 && idx != 255) {
-                    const McFast fe = s_fast[idx];
-                    const unsigned cnt = (code[k] >> 8) ? mc_counts(code[k]) : fe.cnt0;
-                    cf[k] = cnt & 15;
-                    cv[k] = __popc(fe.edgemask & owned_mask(ip.z, ip.y, ip.x0 + k)) + (cnt >> 4);
-                    nv += cv[k]; nf += cf[k]; na += 1;
-                }
+        for (int k = 0; k < 4; ++k) {
+            const int idx = code[k] & 255;
+            if (idx != 0 && idx != 255) {
+                const McFast fe = s_fast[idx];
+                const unsigned cnt = (code[k] >> 8) ? mc_counts(code[k]) : fe.cnt0;
+                cf[k] = cnt & 15;
+                cv[k] = __popc(fe.edgemask & (ip.x0 + k == 0 ? own_x0 : own_row)) + (cnt >> 4);
+                nv += cv[k]; nf += cf[k]; na += 1;
             }
         }
         const unsigned mine = pack3s(nv, nf, na);
@@ -1012,34 +1046,42 @@ mc_compact_kernel(int D, int H, int W, McBatch batch, int n_entries, float* __re
             if (lane >= o) incl += t;
         }
         const unsigned ex = incl - mine;
-        int ov = ws.blockV[item] + (int)(ex & 0x7FFu), of = ws.blockF[item] + (int)((ex >> 11) & 0x7FFu);
-        int oa = a0 + (int)(ex >> 22);
+        // 1. the item's active cells, compacted into this warp's staging row: {cell, first vertex, first face, code}
+        {
+            int ov = bv + (int)(ex & 0x7FFu), of = bf + (int)((ex >> 11) & 0x7FFu), j = (int)(ex >> 22);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int idx = code[k] & 255;
-            if (idx == 0 || idx == 255) continue;
-            const int x = ip.x0 + k;
-            const int cell = (int)(ip.row * W + x);
-            // the face kernel only needs the tiling: its position in the packed table goes into .w
-            const int key = idx * 64 + ((code[k] >> 8) & 63), tun = code[k] >> 14;
-            const int eid = tun ? n_base + d_mc_tun_index[key] + tun - 1 : ((code[k] >> 8) ? d_mc_entry_id[key] : s_fast[idx].eid0);
-            ws.active[oa] = make_int4(cell, ov, of, eid);
-            if (cv[k]) {   // vertex work list, in first-use order of the cell's tiling
-                unsigned long long ow = s_order[eid];
-                const int nedge = (int)((ow >> 56) & 15);
-                const unsigned own = (s_fast[idx].edgemask & owned_mask(ip.z, ip.y, x)) | 0x3000u;   // centres (12, 13) are always this cell's
-                int vid = ov;
-                for (int j = 0; j < nedge; ++j, ow >>= 4) {
-                    const int e = (int)(ow & 15);
-                    if (!((own >> e) & 1)) continue;
-                    float* __restrict__ row = verts + (vbase + vid) * 3;
-                    row[0] = __int_as_float(cell);
-                    row[1] = __int_as_float(e);
-                    ++vid;
-                }
+            for (int k = 0; k < 4; ++k) {
+                const int idx = code[k] & 255;
+                if (idx == 0 || idx == 255) continue;
+                s_cells[warp][j++] = make_int4((int)(ip.row * W) + ip.x0 + k, ov, of, code[k]);
+                ov += cv[k]; of += cf[k];
             }
-            ++oa; ov += cv[k]; of += cf[k];
         }
+        __syncwarp();
+        // 2. one lane per active cell: the record of the face kernel (coalesced 16-byte stores) and the vertex work list
+        const int n_act = a1 - a0;
+        for (int j = lane; j < n_act; j += 32) {
+            const int4 c = s_cells[warp][j];
+            const int idx = c.w & 255;
+            // the face kernel only needs the tiling: its position in the packed table goes into .w
+            const int key = idx * 64 + ((c.w >> 8) & 63), tun = c.w >> 14;
+            const McFast fe = s_fast[idx];
+            const int eid = tun ? n_base + d_mc_tun_index[key] + tun - 1 : ((c.w >> 8) ? d_mc_entry_id[key] : fe.eid0);
+            ws.active[a0 + j] = make_int4(c.x, c.y, c.z, eid);
+            // vertices this cell creates, in first-use order of its tiling (centres 12, 13 are always the cell's own)
+            unsigned long long ow = s_order[eid];
+            const int nedge = (int)((ow >> 56) & 15);
+            const unsigned own = (fe.edgemask & (c.x == (int)(ip.row * W) ? own_x0 : own_row)) | 0x3000u;
+            float* __restrict__ row = verts + (vbase + c.y) * 3;
+            for (int q = 0; q < nedge; ++q, ow >>= 4) {
+                const unsigned e = (unsigned)ow & 15u;
+                if (!((own >> e) & 1u)) continue;
+                row[0] = __int_as_float(c.x);
+                row[1] = __int_as_float((int)e);
+                row += 3;
+            }
+        }
+        __syncwarp();   // the staging row is reused by the warp's next item
     }
 }
 
@@ -1222,6 +1264,7 @@ __global__ void mc_init_kernel(McBatch batch, int N) {
     if (i >= N) return;
     McRec* r = carve(batch, i).rec;
     r->V = r->F = r->A = r->vbase = r->fbase = 0;
+    r->n_resolve = 0;
     r->min_enc = 0xFFFFFFFFu;
     r->max_enc = 0u;
 }
@@ -1233,12 +1276,13 @@ static int32_t count_batch(const float* v, int N, int D, int H, int W, float lev
     mc_init_kernel<<<ceil_div(N, 128), 128, 0, st>>>(b, N);
     const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0) && ((reinterpret_cast<uintptr_t>(ws_) & 7) == 0) &&
                      (ws_stride % 8 == 0);
-    // persistent CTAs: 4 per SM over the whole batch, each warp striding over the strips of its volume
-    const int64_t per_vol = ceil_div<int64_t>((int64_t)sm_count() * 4, N);
+    // one strip per warp: strips differ a lot in cost (the surface crosses some rows and not others), so the grid is left
+    // to the block scheduler instead of a fixed striding (a persistent grid idled a quarter of the SMs in the tail)
     const int64_t strip_ctas = ceil_div<int64_t>((int64_t)D * ceil_div(H, MC_STRIP) * b.g.nseg, MC_WARPS);
-    const dim3 grid((unsigned)(strip_ctas < per_vol ? strip_ctas : per_vol), N);
+    const dim3 grid((unsigned)strip_ctas, N);
     if (vec) mc_classify_kernel<true><<<grid, MC_BLOCK, 0, st>>>(v, D, H, W, level, b);
     else mc_classify_kernel<false><<<grid, MC_BLOCK, 0, st>>>(v, D, H, W, level, b);
+    mc_resolve_kernel<<<dim3(16, N), 128, 0, st>>>(v, D, H, W, level, b);
     mc_scan_kernel<<<N, 1024, 0, st>>>(b);
     mc_bases_kernel<<<1, 32, 0, st>>>(b, N);
     return check_launch("gnb_mc_count");
@@ -1255,7 +1299,9 @@ static int32_t emit_batch(const float* v, int N, int D, int H, int W, float leve
     const int n_entries = g_mc_n_entries;
     const int tab_smem = n_entries * (int)sizeof(unsigned long long);
     {
-        const int64_t per_vol = ceil_div<int64_t>((int64_t)sm_count() * 4, N);
+        // ~16 CTAs per SM over the batch (four waves of the 4 resident ones): the tables are staged per CTA, so fewer CTAs
+        // than items, but enough of them that the block scheduler evens out the volumes
+        const int64_t per_vol = ceil_div<int64_t>((int64_t)sm_count() * 16, N);
         const int64_t item_ctas = ceil_div<int64_t>(b.g.nitems, MC_WARPS);
         const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(ws_) & 7) == 0) && (ws_stride % 8 == 0);
         const dim3 grid((unsigned)(item_ctas < per_vol ? item_ctas : per_vol), N);
