@@ -50,9 +50,63 @@ ConstBankGuard::~ConstBankGuard() {
     b.mu.unlock();
 }
 
+// ---- fp16 operand range flag ---------------------------------------------------------------------------------------------
+// The tensor-core paths split fp32 operands into fp16 hi + lo with SATURATING conversions: an activation beyond +-65504 would
+// silently become 65504.  One 32-bit flag per device records that this happened: set by the normalise-and-split pass of the
+// UNet and by gnb_f16_range_check (run by the pipeline on the grids the decoders read), fetched by gnb_f16_overflow_fetch.
+uint32_t* f16_flag_ptr() {
+    static uint32_t* flags[64] = {nullptr};
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (flags[dev] == nullptr) {
+        if (cudaMalloc(&flags[dev], sizeof(uint32_t)) != cudaSuccess) return nullptr;
+        cudaMemset(flags[dev], 0, sizeof(uint32_t));
+    }
+    return flags[dev];
+}
+
+__global__ void __launch_bounds__(256)
+f16_range_check_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool bad = false;   // !(|v| <= limit) is true for out-of-range values, infinities AND NaNs
+    const int64_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        bad |= !(fabsf(v.x) <= 65504.f) | !(fabsf(v.y) <= 65504.f) | !(fabsf(v.z) <= 65504.f) | !(fabsf(v.w) <= 65504.f);
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) bad |= !(fabsf(x[i]) <= 65504.f);
+    if (bad) *flag = 1u;
+}
+
 }  // namespace gnb
 
 extern "C" {
+
+int32_t gnb_f16_range_check(const float* x, int64_t n, void* stream) {
+    GNB_REQUIRE(x || n == 0, "gnb_f16_range_check: null pointer");
+    if (n <= 0) return GNB_OK;
+    uint32_t* flag = gnb::f16_flag_ptr();
+    GNB_REQUIRE(flag != nullptr, "gnb_f16_range_check: flag allocation failed");
+    int64_t blocks = (n / 4 + 255) / 256;
+    const int64_t cap = (int64_t)gnb::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    gnb::f16_range_check_kernel<<<(unsigned)blocks, 256, 0, gnb::as_stream(stream)>>>(x, n, flag);
+    return gnb::check_launch("gnb_f16_range_check");
+}
+
+int32_t gnb_f16_overflow_fetch(int32_t reset, void* stream) {
+    uint32_t* flag = gnb::f16_flag_ptr();
+    GNB_REQUIRE(flag != nullptr, "gnb_f16_overflow_fetch: flag allocation failed");
+    cudaStream_t st = gnb::as_stream(stream);
+    uint32_t h = 0;
+    GNB_CUDA(cudaMemcpyAsync(&h, flag, sizeof(h), cudaMemcpyDeviceToHost, st));
+    if (reset) GNB_CUDA(cudaMemsetAsync(flag, 0, sizeof(h), st));
+    GNB_CUDA(cudaStreamSynchronize(st));
+    return h ? 1 : 0;
+}
 
 int32_t gnb_version(void) { return 100; /* 0.1.0 */ }
 

@@ -43,6 +43,7 @@ template <typename T>
 __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
 int sm_count();  // cached SM count of the current device (148 on B200)
+uint32_t* f16_flag_ptr();  // per-device flag: an fp32 value outside the fp16 range reached a saturating operand split (capi.cu)
 
 // Serialises the users of one __constant__ operand bank.  Three launch families (lattice decode, query / row decode,
 // Linear blocks) refresh a per-device constant array with a stream-ordered copy in front of every launch; on ONE stream

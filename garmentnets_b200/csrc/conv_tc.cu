@@ -480,7 +480,7 @@ __device__ __forceinline__ uint32_t ct_cvt_f16x2_sat(float lo_elem, float hi_ele
 __global__ void __launch_bounds__(256)
 gn_apply_split_vec4_kernel(const float* __restrict__ x, int64_t rows, int64_t vox_per_sample, int C, int Cpad,
                            const float* __restrict__ scale, const float* __restrict__ shift, uint2* __restrict__ xh,
-                           uint2* __restrict__ xl) {
+                           uint2* __restrict__ xl, uint32_t* __restrict__ range_flag) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per channel quad
     const int quads = Cpad / 4;
     if (t >= rows * quads) return;
@@ -495,6 +495,8 @@ gn_apply_split_vec4_kernel(const float* __restrict__ x, int64_t rows, int64_t vo
             const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + (int64_t)b * C + c));
             v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
         }
+        // the clamp below would hide an activation outside the fp16 range (or a NaN): record it (gnb_f16_overflow_fetch)
+        if (!(fabsf(v.x) <= 65504.f) | !(fabsf(v.y) <= 65504.f) | !(fabsf(v.z) <= 65504.f) | !(fabsf(v.w) <= 65504.f)) *range_flag = 1u;
         v.x = fminf(fmaxf(v.x, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y, -65504.f), 65504.f);
         v.z = fminf(fmaxf(v.z, -65504.f), 65504.f); v.w = fminf(fmaxf(v.w, -65504.f), 65504.f);
     }
@@ -513,7 +515,7 @@ gn_apply_split_vec4_kernel(const float* __restrict__ x, int64_t rows, int64_t vo
 __global__ void __launch_bounds__(256)
 gn_apply_split_kernel(const float* __restrict__ x, int64_t rows, int64_t vox_per_sample, int C, int Cpad,
                       const float* __restrict__ scale, const float* __restrict__ shift, __half* __restrict__ xh,
-                      __half* __restrict__ xl) {
+                      __half* __restrict__ xl, uint32_t* __restrict__ range_flag) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per channel pair
     const int half_c = Cpad / 2;
     if (t >= rows * half_c) return;
@@ -529,6 +531,7 @@ gn_apply_split_kernel(const float* __restrict__ x, int64_t rows, int64_t vox_per
             const float2 sh = *reinterpret_cast<const float2*>(shift + (int64_t)b * C + c);
             v0 = fmaf(v0, sc.x, sh.x); v1 = fmaf(v1, sc.y, sh.y);
         }
+        if (!(fabsf(v0) <= 65504.f) | !(fabsf(v1) <= 65504.f)) *range_flag = 1u;
         v0 = fminf(fmaxf(v0, -65504.f), 65504.f);
         v1 = fminf(fmaxf(v1, -65504.f), 65504.f);
     }
@@ -601,15 +604,17 @@ int32_t gnb_gn_apply_split(const float* x, int32_t B, int64_t voxels, int32_t C,
     const int Cpad = ceil_div(C, CT_KC) * CT_KC;
     const int64_t rows = (int64_t)B * voxels;
     if (rows == 0) return GNB_OK;
+    uint32_t* flag = f16_flag_ptr();
+    GNB_REQUIRE(flag != nullptr, "gnb_gn_apply_split: range flag allocation failed");
     const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(xh) | reinterpret_cast<uintptr_t>(xl) |
                            reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0;
     if (C % 4 == 0 && aligned) {
         gn_apply_split_vec4_kernel<<<(unsigned)ceil_div<int64_t>(rows * (Cpad / 4), 256), 256, 0, as_stream(stream)>>>(
-            x, rows, voxels, C, Cpad, scale, shift, reinterpret_cast<uint2*>(xh), reinterpret_cast<uint2*>(xl));
+            x, rows, voxels, C, Cpad, scale, shift, reinterpret_cast<uint2*>(xh), reinterpret_cast<uint2*>(xl), flag);
         return check_launch("gnb_gn_apply_split");
     }
     gn_apply_split_kernel<<<(unsigned)ceil_div<int64_t>(rows * (Cpad / 2), 256), 256, 0, as_stream(stream)>>>(
-        x, rows, voxels, C, Cpad, scale, shift, reinterpret_cast<__half*>(xh), reinterpret_cast<__half*>(xl));
+        x, rows, voxels, C, Cpad, scale, shift, reinterpret_cast<__half*>(xh), reinterpret_cast<__half*>(xl), flag);
     return check_launch("gnb_gn_apply_split");
 }
 

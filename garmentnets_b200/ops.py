@@ -632,6 +632,19 @@ def gaussian_gradient_magnitude_batched(v: torch.Tensor, sigma: float) -> torch.
     return out
 
 
+def f16_range_check(t: torch.Tensor) -> None:
+    """Queue a check of ``t`` (fp32, any shape) against the fp16 range of the tensor-core operand split; the outcome is read
+    with :func:`f16_overflow` (one flag per device, see include/garmentnets_b200.h)."""
+    t = _req(t, torch.float32, "t")
+    _lib.call("gnb_f16_range_check", t.data_ptr(), t.numel(), _stream())
+
+
+def f16_overflow(reset: bool = True) -> bool:
+    """True if an fp32 value outside +-65504 (or a non-finite one) reached a saturating fp16 split since the last reset.
+    Synchronises the current stream."""
+    return _lib.call("gnb_f16_overflow_fetch", 1 if reset else 0, _stream()) == 1
+
+
 def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0, 1.0), gradient_direction: str = "ascent",
                          ggm: Optional[torch.Tensor] = None, return_packed: bool = False, with_normals: bool = True):
     """Marching cubes of N volumes [N,D,H,W] in seven launches and ONE host synchronisation: classify / scan for the

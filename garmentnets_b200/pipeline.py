@@ -28,6 +28,7 @@ import torch
 from torch import nn
 
 from . import ops, profiling
+from ._lib import GarmentNetsB200Error
 from .components.gridding import VirtualGrid
 from .components.mlp import MLP
 from .components.pointnet2 import CloudIndex, FPModule, GlobalSAModule, SAModule
@@ -390,6 +391,10 @@ class ConvImplicitWNFPipeline(nn.Module):
         if mc_surface_loss_weight > 0:
             self.mc_surface_decoder = ImplicitWNFDecoder(**mc_surface_decoder_params)
         self.volume_task_space = volume_task_space
+        if volume_task_space:
+            # ref conv_implicit_wnf.py:279-295,320-322 (apply_volume_task_space: the volume decoder is queried in task space
+            # through the predicted warp field).  Off in every shipped config; not built here, so refuse instead of ignoring it.
+            raise NotImplementedError("volume_task_space=True (conv_implicit_wnf.py:279-295) is not implemented in garmentnets_b200")
         self.batch_size = batch_size
         self.volume_decoder.profile_tag = "decode"
         self.surface_decoder.profile_tag = "surface"
@@ -463,10 +468,12 @@ class ConvImplicitWNFPipeline(nn.Module):
     @torch.no_grad()
     def predict(self, data, volume_size: int = 128, gradient_sigma: float = 0.5, iso_surface_level: float = 0.5,
                 gradient_direction: str = "ascent", index: Optional[CloudIndex] = None, fps_starts=None,
-                keep_volume: bool = False, with_normals: bool = True) -> List[Dict[str, torch.Tensor]]:
+                keep_volume: bool = False, with_normals: bool = True, check_range: bool = True) -> List[Dict[str, torch.Tensor]]:
         """Device version of the reference's per-sample loop predict.py:138-187, for a whole batch.
         Returns one dict per sample with the arrays predict.py writes under ``marching_cubes_mesh`` / ``point_cloud``.
-        ``with_normals=False`` leaves out ``normals`` / ``volume_value`` (written by the reference, read by nothing)."""
+        ``with_normals=False`` leaves out ``normals`` / ``volume_value`` (written by the reference, read by nothing).
+        ``check_range`` (default on, ~0.05 ms per batch): raise instead of returning clamped results when an activation
+        exceeds the fp16 range of the tensor-core operand split (UNet convolution operands and the decoder grids)."""
         marks = getattr(self, "stage_marks", None)  # optional [(name, cuda event)] sink used by bench.py
         order = ("pointnet2", "aggregator", "unet3d", "dense_decode", "ggm", "marching_cubes", "surface_decode")
 
@@ -491,7 +498,11 @@ class ConvImplicitWNFPipeline(nn.Module):
         unet = self.unet_3d.abstract_3d_unet
         x_last = unet.forward_ndhwc(ops.to_channels_last(vol_in), apply_final=False)
         mark("unet3d")
-        wnf = self.dense_decode(None, volume_size, hoisted=self.volume_decoder.hoisted_folded(x_last, unet.final_conv))
+        u_grid = self.volume_decoder.hoisted_folded(x_last, unet.final_conv)
+        if check_range:   # operands of the decoders' fp16 split: the grids they interpolate (a blend never exceeds its corners)
+            ops.f16_range_check(u_grid)
+            ops.f16_range_check(x_last)
+        wnf = self.dense_decode(None, volume_size, hoisted=u_grid)
         mark("dense_decode")
         B, Q = wnf.shape[0], wnf.shape[1]
         spacing = 1 / (Q - 1)
@@ -502,6 +513,9 @@ class ConvImplicitWNFPipeline(nn.Module):
         mark("ggm")
         mcs, packed = ops.marching_cubes_batch(wnf, iso_surface_level, (spacing,) * 3, gradient_direction, ggm,
                                                return_packed=True, with_normals=with_normals)
+        if check_range and ops.f16_overflow():   # the stream was just synchronised for the marching-cubes totals
+            raise GarmentNetsB200Error("an activation left the fp16 range of the tensor-core operand split (+-65504) or is not "
+                                       "finite: the 3D-UNet / decoder outputs of this batch are not trustworthy")
         mark("marching_cubes")
         # warp field of every mesh vertex of the batch in one fused launch (gather + MLP on tcgen05)
         dec = self.surface_decoder

@@ -402,6 +402,18 @@ int32_t gnb_nn1_distance(const float* q, const int64_t* ptr_q, const float* r, c
                          void* stream);
 
 #if defined(__GNUC__)
+/* ---- fp16 operand range flag --------------------------------------------------------------------------------------
+ * The tensor-core kernels split fp32 operands into fp16 hi + lo with saturating conversions (+-65504).  With trained
+ * checkpoints an activation outside that range would silently be clamped; one flag per device records it instead:
+ *   - gnb_gn_apply_split sets it for the operands of the 3D-UNet convolutions (no extra pass);
+ *   - gnb_f16_range_check(x, n) sets it when any of the n fp32 values is outside the range (or not finite): the pipeline
+ *     runs it on the grids the implicit decoders interpolate (a convex combination never exceeds its inputs);
+ *   - not covered: the inputs of the PointNet++ Linear blocks (gnb_linear_tc).
+ * gnb_f16_overflow_fetch synchronises `stream`, returns 1 if the flag is set (0 otherwise, < 0 on error) and clears it when
+ * reset != 0. */
+int32_t gnb_f16_range_check(const float* x, int64_t n, void* stream);
+int32_t gnb_f16_overflow_fetch(int32_t reset, void* stream);
+
 #pragma GCC visibility pop
 #endif
 

@@ -221,3 +221,29 @@ def test_upsample_concat_vectorised(dev, Cs, Cx, size, small):
     ref = torch.cat((skip, F.interpolate(low, size=size, mode="nearest")), 1).permute(0, 2, 3, 4, 1)
     got = ops.upsample_concat(ops.to_channels_last(skip.to(dev)), ops.to_channels_last(low.to(dev)))
     assert torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.gpu
+def test_f16_range_flag(dev):
+    """Hardening: values outside +-65504 (or NaN) reaching a saturating fp16 operand split raise the per-device flag --
+    through the explicit check the pipeline runs on the decoder grids and through the UNet's normalise-and-split pass."""
+    from garmentnets_b200 import ops
+    ops.f16_overflow(reset=True)
+    x = torch.randn(3, 1000, 7, device=dev) * 100
+    ops.f16_range_check(x)
+    assert not ops.f16_overflow()
+    x[1, 17, 3] = 7.0e4
+    ops.f16_range_check(x)
+    assert ops.f16_overflow(reset=False) and ops.f16_overflow()      # read without and with reset
+    assert not ops.f16_overflow()
+    x[1, 17, 3] = float("nan")
+    ops.f16_range_check(x.view(-1)[1:])                               # unaligned start: scalar path
+    assert ops.f16_overflow()
+    # the split pass of the UNet (GroupNorm scale / shift applied, then hi + lo)
+    v = torch.randn(2, 4, 4, 4, 32, device=dev)
+    sc, sh = torch.ones(2, 32, device=dev), torch.zeros(2, 32, device=dev)
+    ops.gn_apply_split(v, sc, sh)
+    assert not ops.f16_overflow()
+    sc[1, 5] = 1.0e6
+    ops.gn_apply_split(v, sc, sh)
+    assert ops.f16_overflow()
