@@ -1,0 +1,505 @@
+// Implicit decoder at explicit query points, both contractions on the tensor cores (ref networks/conv_implicit_wnf.py:128-149
+// called at predict.py:184-187 for the marching-cubes vertices: the surface / warp-field decoder).
+//
+// Per tile of 128 queries, one persistent warp-specialised CTA per SM computes
+//     x   = trilinear(X32)(q)                       32-channel feature grid (the UNet's last decoder level), fp32
+//     H1  = ReLU(x W1^T + b1)                       256 x 32 contraction  (final_conv and BatchNorm1 are folded into W1 / W2)
+//     H2  = ReLU(H1 W2^T + b2)                      256 x 256 contraction
+//     y   = BN3(ReLU(H2 W3'^T + c))                 Cout in {1,2,3}: per-row dot products in the epilogue registers
+// and writes only y.  The previous form of this path (decode_tc_kernel<COUT, 3>) applied Linear1 per query with packed FFMA2
+// in the producer warps: 1 M FMAs per tile on the CUDA cores took longer than the 3-pass 256 x 256 contraction on the tensor
+// cores (ncu: tensor pipe 23 % active, 30 k clk per tile against a 6 k clk MMA floor).  Here Linear1 is a second, small MMA
+// chain and the warps only move data:
+//
+//   warps 0-3   gather: 8 corner loads of 128 B per query (8 lanes x 16 B per row, four rows per warp-wide load), blend,
+//               fp16 hi/lo split -> A1 [128 rows][hi 32 | lo 32] in ONE 128-byte swizzled row per query (double buffered)
+//   warp 12     MMA issuer: per 64-channel chunk c of H1, six N = 64 MMAs  A1 x W1[64c..64c+63]  (hi*hi, lo*hi, hi*lo select
+//               the K-steps inside the 128-byte rows: A1 = [hi|lo], W1 rows = [hi|lo]) -> acc1[c & 1] (64 TMEM columns);
+//               then, once the mid-epilogue has turned that chunk into the A2 operand, the twelve N = 256 MMAs of Linear2
+//               against the streamed W2 pieces -> acc2 (256 columns).  A2 is read FROM TENSOR MEMORY (tcgen05.mma with a TMEM
+//               A operand): only W2 crosses the shared-memory port, which bounded the all-shared-memory form of this kernel
+//               (8 KB of operands per 64-clk N = 128 MMA = the whole 128 B/clk port)
+//   warps 4-7   mid-epilogue: acc1 chunk -> registers (tcgen05.ld), + b1, ReLU and fp16 hi/lo split riding on the conversions
+//               (cvt.rz.relu / cvt.rn.relu), tcgen05.st of the packed half pairs -> A2 slot in TMEM (the K-chunk of Linear2)
+//   warps 8-11  epilogue: acc2 -> bias / ReLU / BN2 folded with W3 / BN3, store
+//   warp 13     loader: W1 image once, W2 pieces (32 KB) through a five-slot ring with cp.async.bulk
+//
+// TMEM: acc2 columns 0..255, acc1 double buffer 256..383, A2 double buffer 384..511 (per slot: hi 32 | lo 32 columns, two fp16
+// per column).  Shared memory: A1 2 x 16 KB, W1 32 KB, W2 ring 5 x 32 KB.
+// Precision as in decode_tc.cu / decode_lattice.cu: fp16 hi + lo operands, hi*hi + lo*hi + hi*lo, fp32 accumulation.
+#include "tc_common.cuh"
+
+namespace gnb {
+namespace dq {
+
+constexpr int M = 128, N = 256, KC = 64, NCH = N / KC, C0 = 32;
+constexpr int A1_BYTES = M * 128;            // 16 KB
+constexpr int W1_BYTES = N * 128;            // 32 KB
+constexpr int B_PIECE = N * KC * 2;          // 32 KB: the 256 W2 rows, one K-chunk, one precision part
+constexpr int B_SLOTS = 5;
+constexpr int THREADS = 448;
+constexpr int MAX_B = 128;
+constexpr uint32_t IDESC_N64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+constexpr uint32_t IDESC_N256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+constexpr uint32_t ACC1_COL = 256;           // first TMEM column of the acc1 double buffer (2 x 64 columns)
+constexpr uint32_t A2_COL = 384;             // first TMEM column of the A2 double buffer (2 x {hi 32 | lo 32} columns)
+
+struct Smem {
+    static constexpr int a1 = 0;                              // [2][16 KB]
+    static constexpr int w1 = a1 + 2 * A1_BYTES;              // 32 KB
+    static constexpr int b_ring = w1 + W1_BYTES;              // [5][32 KB]
+    static constexpr int bars = b_ring + B_SLOTS * B_PIECE;
+    static constexpr int n_bars = 16 + 2 * B_SLOTS;
+    static constexpr int tmem_ptr = bars + n_bars * 8;
+    static constexpr int qptr = tmem_ptr + 16;                // [MAX_B + 1] i64 first row of every sample
+    static constexpr int total = qptr + (MAX_B + 1) * 8;
+};
+static_assert(Smem::total + 1024 <= 227 * 1024, "shared memory budget");
+
+// b1[256] | b2[256] | w3s[COUT][256]: immediate constant-bank operands of the two epilogues (one stream at a time, ConstBankGuard)
+__constant__ float c_epi[5 * 256];
+
+// per-role wait-time attribution (profiling builds only, tools/surface_bench.py): cycles one thread of each role spends in its
+// barrier waits.  [cta][16]: 0 mma:a1_full 1 mma:acc1_empty 2 mma:d_empty 3 mma:a2_full 4 mma:b_full 5 mma:total |
+// 6 gather:a1_empty 7 gather:total | 8 mid:acc1_full 9 mid:a2_empty 10 mid:total | 11 epi:d_full 12 epi:total | 13 load:b_empty
+#ifdef GNB_PROFILE_KNOBS
+__device__ unsigned long long g_prof[1024 * 16];
+#define DQ_PROF_DECL unsigned long long prof_acc[5] = {0, 0, 0, 0, 0}; const long long prof_t0 = clock64()
+#define DQ_PROF(i, stmt) do { const long long t_ = clock64(); stmt; prof_acc[i] += (unsigned long long)(clock64() - t_); } while (0)
+#define DQ_PROF_STORE(i, slot) g_prof[blockIdx.x * 16 + (slot)] = prof_acc[i]
+#define DQ_PROF_TOTAL(slot) g_prof[blockIdx.x * 16 + (slot)] = (unsigned long long)(clock64() - prof_t0)
+#else
+#define DQ_PROF_DECL
+#define DQ_PROF(i, stmt) do { stmt; } while (0)
+#define DQ_PROF_STORE(i, slot)
+#define DQ_PROF_TOTAL(slot)
+#endif
+
+struct Params {
+    const float* X;            // [B,G,G,G,32] fp32 channels-last
+    int B, G;
+    const float* q;            // [R,3] query points in [0,1]^3 (coordinate 0 -> W axis)
+    const int64_t* qptr;       // [B+1] first row of every sample
+    int64_t R, num_tiles;
+    const uint8_t* w1_image;   // 32 KB: W1 * 2^s1 as [256 rows][hi 32 | lo 32] fp16, K-major SWIZZLE_128B
+    const float* inv_s1;       // device scalar 2^-s1
+    const uint8_t* w2_packed;  // gnb_pack_f16_split layout: [4 chunks][hi, lo][256 rows x 128 B]
+    float acc_scale;           // 2^-s2
+    const float* tail;         // [COUT][4] = {c0, bn3_scale, bn3_shift, 0}
+    float* out;                // [R, COUT]
+};
+
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+// ReLU + fp16 hi/lo split of two fp32 values, the ReLU riding on the conversions (see decode_lattice.cu)
+__device__ __forceinline__ void relu_split2(float2 h, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(h.y), "f"(h.x));
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    const float2 r = sub2(h, hf);
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
+}
+// signed fp16 hi/lo split of two fp32 values
+__device__ __forceinline__ void split2(float2 h, uint32_t& hi, uint32_t& lo) {
+    hi = cvt_f16x2_sat(h.x, h.y);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    const float2 r = sub2(h, hf);
+    lo = cvt_f16x2_sat(r.x, r.y);
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(THREADS, 1)
+decode_query_kernel(const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const uint32_t bar0 = sbase + Smem::bars;
+    auto a1_full = [&](int s) { return bar0 + 8 * s; };
+    auto a1_empty = [&](int s) { return bar0 + 8 * (2 + s); };
+    auto acc1_full = [&](int s) { return bar0 + 8 * (4 + s); };
+    auto acc1_empty = [&](int s) { return bar0 + 8 * (6 + s); };
+    auto a2_full = [&](int s) { return bar0 + 8 * (8 + s); };
+    auto a2_empty = [&](int s) { return bar0 + 8 * (10 + s); };
+    const uint32_t d_full = bar0 + 8 * 12, w1_full = bar0 + 8 * 13;
+    auto d_empty = [&](int h) { return bar0 + 8 * (14 + h); };   // acc2 drained (slot 1 unused)
+    auto b_full = [&](int s) { return bar0 + 8 * (16 + s); };
+    auto b_empty = [&](int s) { return bar0 + 8 * (16 + B_SLOTS + s); };
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(a1_full(s), 4); mbar_init(a1_empty(s), 1);
+            mbar_init(acc1_full(s), 1); mbar_init(acc1_empty(s), 4);
+            mbar_init(a2_full(s), 4); mbar_init(a2_empty(s), 1);
+        }
+        mbar_init(d_full, 1); mbar_init(d_empty(0), 4); mbar_init(d_empty(1), 4); mbar_init(w1_full, 1);
+        for (int s = 0; s < B_SLOTS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        int64_t* qp = reinterpret_cast<int64_t*>(smem + Smem::qptr);
+        for (int i = threadIdx.x; i <= p.B; i += THREADS) qp[i] = p.qptr[i];
+    }
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Smem::tmem_ptr), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp < 4) {
+        // =========================== gather: A1 = split(trilinear(X32)(q)) ===========================
+        // Lane l sets up row 32*warp + l (corner offsets and weights); the gather then runs with 8 lanes per row (one float4 =
+        // 4 channels each): a warp-wide LDG.128 fetches one corner of FOUR rows (4 x 128 contiguous bytes).
+        const int G = p.G;
+        const int64_t* qp = reinterpret_cast<const int64_t*>(smem + Smem::qptr);
+        float qn[3] = {0.f, 0.f, 0.f};   // query point of this lane's row of the NEXT tile (loaded one tile ahead)
+        {
+            const int64_t r = (int64_t)blockIdx.x * M + warp * 32 + lane;
+            if (r < p.R) { qn[0] = __ldg(p.q + r * 3); qn[1] = __ldg(p.q + r * 3 + 1); qn[2] = __ldg(p.q + r * 3 + 2); }
+        }
+        const float* xbase = p.X + 4 * (lane & 7);
+        const uint32_t unit = (uint32_t)((lane & 7) >> 1), sub8 = (uint32_t)(lane & 1) * 8u;
+        int it = 0;
+        DQ_PROF_DECL;
+        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            int off[8];
+            float wgt[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { off[k] = 0; wgt[k] = 0.f; }
+            {
+                const int64_t r = tile * M + warp * 32 + lane;
+                if (r < p.R) {
+                    int lo_b = 0, hi_b = p.B;  // largest b with qptr[b] <= r
+                    while (hi_b - lo_b > 1) { const int mid = (lo_b + hi_b) >> 1; if (qp[mid] <= r) lo_b = mid; else hi_b = mid; }
+                    const float g0 = __fsub_rn(__fmul_rn(2.0f, qn[0]), 1.0f);
+                    const float g1 = __fsub_rn(__fmul_rn(2.0f, qn[1]), 1.0f);
+                    const float g2 = __fsub_rn(__fmul_rn(2.0f, qn[2]), 1.0f);
+                    TriW t;
+                    trilinear_setup(g0, g1, g2, G, G, G, C0, t);
+                    const int sb = lo_b * G * G * G * C0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { off[k] = sb + (int)t.off[k]; wgt[k] = t.w[k]; }
+                }
+                // the next tile's query point: its HBM latency hides behind this tile's gather
+                const int64_t rn = (tile + gridDim.x) * M + warp * 32 + lane;
+                if (rn < p.R) { qn[0] = __ldg(p.q + rn * 3); qn[1] = __ldg(p.q + rn * 3 + 1); qn[2] = __ldg(p.q + rn * 3 + 2); }
+            }
+            DQ_PROF(0, mbar_wait(a1_empty(buf), ((it >> 1) & 1) ^ 1));
+            const uint32_t a1 = sbase + Smem::a1 + buf * A1_BYTES + sub8;
+#pragma unroll 2
+            for (int grp = 0; grp < 8; ++grp) {
+                const int src = grp * 4 + (lane >> 3);      // row (within the warp's 32) this lane gathers for
+                float4 v[8];
+                float w[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int o = __shfl_sync(0xffffffffu, off[k], src);
+                    w[k] = __shfl_sync(0xffffffffu, wgt[k], src);
+                    v[k] = __ldg(reinterpret_cast<const float4*>(xbase + o));
+                }
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    a.x = fmaf(v[k].x, w[k], a.x); a.y = fmaf(v[k].y, w[k], a.y);
+                    a.z = fmaf(v[k].z, w[k], a.z); a.w = fmaf(v[k].w, w[k], a.w);
+                }
+                uint32_t h0, l0, h1, l1;
+                split2(make_float2(a.x, a.y), h0, l0);
+                split2(make_float2(a.z, a.w), h1, l1);
+                // row r: [hi 32 ch | lo 32 ch] = 16-byte units 0..3 | 4..7, unit u stored at u ^ (r & 7)
+                const int r = warp * 32 + src;
+                const uint32_t rowaddr = a1 + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(rowaddr + ((unit ^ (uint32_t)(r & 7)) << 4)), "r"(h0), "r"(h1) : "memory");
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(rowaddr + (((unit + 4u) ^ (uint32_t)(r & 7)) << 4)), "r"(l0), "r"(l1) : "memory");
+            }
+            fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a1_full(buf));
+        }
+        if (threadIdx.x == 0) { DQ_PROF_STORE(0, 6); DQ_PROF_TOTAL(7); }
+    } else if (warp < 8) {
+        // =========================== mid-epilogue: acc1 chunk -> A2 slot ===========================
+        const int qd = warp & 3;          // TMEM lane quarter this warp may access (warp id mod 4)
+        const float inv1 = __ldg(p.inv_s1);
+        uint32_t q1 = 0;
+        DQ_PROF_DECL;
+        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c, ++q1) {
+                const uint32_t s = q1 & 1u;
+                DQ_PROF(0, mbar_wait(acc1_full(s), (q1 >> 1) & 1u));
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + ACC1_COL + s * 64u;
+                uint32_t r0[32], r1[32];
+                tmem_ld32(taddr, r0);
+                tmem_ld32(taddr + 32, r1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc1_empty(s));   // the tensor core may overwrite this acc1 buffer (chunk c + 2)
+                DQ_PROF(1, mbar_wait(a2_empty(s), ((q1 >> 1) & 1u) ^ 1u));   // A2 slots and acc1 buffers advance together (slot = q1 & 1)
+                // this row's 64 channels as 32 + 32 packed half pairs: exactly the A-operand columns of the tensor memory
+                const uint32_t a2addr = tmem_base + ((uint32_t)(qd * 32) << 16) + A2_COL + s * 64u;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {   // 32 accumulator columns -> 16 + 16 packed words
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t x0 = half ? r1[2 * j] : r0[2 * j], x1 = half ? r1[2 * j + 1] : r0[2 * j + 1];
+                        const int col = half * 32 + 2 * j;
+                        const float2 h = make_float2(fmaf(__uint_as_float(x0), inv1, c_epi[c * KC + col]),
+                                                     fmaf(__uint_as_float(x1), inv1, c_epi[c * KC + col + 1]));
+                        // rounded (not truncated) hi part: this warp group has issue slots to spare, and the 22nd bit of H1 is
+                        // visible in the float64-yardstick test of the warp field (tests/test_pipeline.py)
+                        relu_split_f16x2(h.x, h.y, hi[j], lo[j]);
+                    }
+                    tmem_st16(a2addr + half * 16, hi);
+                    tmem_st16(a2addr + 32 + half * 16, lo);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a2_full(s));
+            }
+        }
+        if (threadIdx.x == 128) { DQ_PROF_STORE(0, 8); DQ_PROF_STORE(1, 9); DQ_PROF_TOTAL(10); }
+    } else if (warp < 12) {
+        // =========================== epilogue: acc2 -> y ===========================
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        float c_tail[COUT], bn3s[COUT], bn3h[COUT];
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) { c_tail[o] = p.tail[o * 4]; bn3s[o] = p.tail[o * 4 + 1]; bn3h[o] = p.tail[o * 4 + 2]; }
+        const float as = p.acc_scale;
+        int it = 0;
+        DQ_PROF_DECL;
+        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            DQ_PROF(0, mbar_wait_sleep(d_full, it & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
+            // software pipeline: the next 32 columns are in flight (tcgen05.ld) while the current 32 are folded; the column
+            // loop is fully unrolled so that every b2 / w3s value is an immediate constant-bank operand
+            uint32_t r0[32], r1[32];
+            float dsum[COUT][4];
+#pragma unroll
+            for (int o = 0; o < COUT; ++o)
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) dsum[o][q4] = 0.f;
+            tmem_ld32(taddr, r0);
+#pragma unroll
+            for (int n0 = 0; n0 < N; n0 += 64) {
+                tmem_ld_wait();
+                tmem_ld32(taddr + n0 + 32, r1);
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    const float v = fmaxf(fmaf(__uint_as_float(r0[u]), as, c_epi[256 + n0 + u]), 0.f);
+#pragma unroll
+                    for (int o = 0; o < COUT; ++o) dsum[o][u & 3] = fmaf(v, c_epi[(2 + o) * 256 + n0 + u], dsum[o][u & 3]);
+                }
+                tmem_ld_wait();
+                if (n0 + 64 < N) {
+                    tmem_ld32(taddr + n0 + 64, r0);
+                } else {
+                    // every TMEM read of acc2 has completed: the next tile's Linear2 may overwrite it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(d_empty(0));
+                }
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    const float v = fmaxf(fmaf(__uint_as_float(r1[u]), as, c_epi[256 + n0 + 32 + u]), 0.f);
+#pragma unroll
+                    for (int o = 0; o < COUT; ++o) dsum[o][u & 3] = fmaf(v, c_epi[(2 + o) * 256 + n0 + 32 + u], dsum[o][u & 3]);
+                }
+            }
+            const int64_t grow = tile * M + row;
+            if (grow < p.R) {
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) {
+                    const float dot = (dsum[o][0] + dsum[o][1]) + (dsum[o][2] + dsum[o][3]);
+                    p.out[grow * COUT + o] = fmaxf(dot + c_tail[o], 0.f) * bn3s[o] + bn3h[o];
+                }
+            }
+        }
+        if (threadIdx.x == 256) { DQ_PROF_STORE(0, 11); DQ_PROF_TOTAL(12); }
+    } else if (warp == 12) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            mbar_wait(w1_full, 0);
+            tc_fence_after();
+            uint32_t q1 = 0, q2 = 0, piece = 0;
+            const uint32_t w1 = sbase + Smem::w1;
+            int it = 0;
+            DQ_PROF_DECL;
+            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                DQ_PROF(0, mbar_wait_sleep(a1_full(buf), (it >> 1) & 1));
+                tc_fence_after();
+                const uint32_t a1 = sbase + Smem::a1 + buf * A1_BYTES;
+                // Linear1, chunk c: acc1[q1 & 1] = A1 x W1[64c .. 64c+63]^T.  Rows of both operands are [hi | lo] (K-steps 0,1 |
+                // 2,3 of the 128-byte row): hi*hi, lo*hi and hi*lo are picked by the K-step offsets of the two descriptors.
+                auto mma1 = [&](int c) {
+                    const uint32_t s = q1 & 1u;
+                    DQ_PROF(1, mbar_wait_sleep(acc1_empty(s), ((q1 >> 1) & 1u) ^ 1u));
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + ACC1_COL + s * 64u;
+                    const uint32_t w = w1 + (uint32_t)c * (64u * 128u);
+                    umma_f16(d, umma_desc(a1), umma_desc(w), IDESC_N64, 0);
+                    umma_f16(d, umma_desc(a1 + 32), umma_desc(w + 32), IDESC_N64, 1);
+                    umma_f16(d, umma_desc(a1 + 64), umma_desc(w), IDESC_N64, 1);
+                    umma_f16(d, umma_desc(a1 + 96), umma_desc(w + 32), IDESC_N64, 1);
+                    umma_f16(d, umma_desc(a1), umma_desc(w + 64), IDESC_N64, 1);
+                    umma_f16(d, umma_desc(a1 + 32), umma_desc(w + 96), IDESC_N64, 1);
+                    umma_commit(acc1_full(s));
+                    ++q1;
+                };
+                mma1(0);
+                mma1(1);
+                for (int c = 0; c < NCH; ++c, ++q2) {
+                    const uint32_t s = q2 & 1u;
+                    DQ_PROF(3, mbar_wait_sleep(a2_full(s), (q2 >> 1) & 1u));
+                    tc_fence_after();
+                    const uint32_t ahi = tmem_base + A2_COL + s * 64u, alo = ahi + 32u;   // TMEM columns: 8 per K-step of 16
+                    // piece 0: W2_hi chunk c -> A_hi*B_hi and A_lo*B_hi ; piece 1: W2_lo chunk c -> A_hi*B_lo.  N = 256 MMAs: measured
+                    // faster than N = 128 halves with an early hand-over of the lower accumulator half (2.47 vs 2.70 ms)
+                    if (c == 0) { DQ_PROF(2, mbar_wait_sleep(d_empty(0), (it & 1) ^ 1)); tc_fence_after(); }   // acc2 drained by the previous tile's epilogue
+                    const uint32_t acc2 = tmem_base;
+                    {
+                        const int slot = piece % B_SLOTS;
+                        DQ_PROF(4, mbar_wait_sleep(b_full(slot), (piece / B_SLOTS) & 1));
+                        tc_fence_after();
+                        const uint32_t bs = sbase + Smem::b_ring + slot * B_PIECE;
+#pragma unroll
+                        for (int kk = 0; kk < KC / 16; ++kk) umma_f16_ta(acc2, ahi + kk * 8, umma_desc(bs + kk * 32), IDESC_N256, (c | kk) != 0);
+#pragma unroll
+                        for (int kk = 0; kk < KC / 16; ++kk) umma_f16_ta(acc2, alo + kk * 8, umma_desc(bs + kk * 32), IDESC_N256, 1);
+                        umma_commit(b_empty(slot));
+                        ++piece;
+                    }
+                    {
+                        const int slot = piece % B_SLOTS;
+                        DQ_PROF(4, mbar_wait_sleep(b_full(slot), (piece / B_SLOTS) & 1));
+                        tc_fence_after();
+                        const uint32_t bs = sbase + Smem::b_ring + slot * B_PIECE;
+#pragma unroll
+                        for (int kk = 0; kk < KC / 16; ++kk) umma_f16_ta(acc2, ahi + kk * 8, umma_desc(bs + kk * 32), IDESC_N256, 1);
+                        umma_commit(b_empty(slot));
+                        ++piece;
+                    }
+                    umma_commit(a2_empty(s));
+                    if (c + 2 < NCH) mma1(c + 2);
+                    if (c == 1) umma_commit(a1_empty(buf));   // the last Linear1 MMAs of this tile have been issued
+                }
+                umma_commit(d_full);
+            }
+            DQ_PROF_STORE(0, 0); DQ_PROF_STORE(1, 1); DQ_PROF_STORE(2, 2); DQ_PROF_STORE(3, 3); DQ_PROF_STORE(4, 4); DQ_PROF_TOTAL(5);
+        }
+    } else {
+        // =========================== loader ===========================
+        if (lane == 0) {
+            mbar_expect_tx(w1_full, W1_BYTES);
+            bulk_g2s(sbase + Smem::w1, p.w1_image, W1_BYTES, w1_full);
+            uint32_t piece = 0;
+            DQ_PROF_DECL;
+            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                for (int pc = 0; pc < 2 * NCH; ++pc, ++piece) {
+                    const int slot = piece % B_SLOTS;
+                    DQ_PROF(0, mbar_wait_sleep(b_empty(slot), ((piece / B_SLOTS) & 1) ^ 1));
+                    mbar_expect_tx(b_full(slot), B_PIECE);
+                    bulk_g2s(sbase + Smem::b_ring + slot * B_PIECE, p.w2_packed + (size_t)pc * B_PIECE, B_PIECE, b_full(slot));
+                }
+            }
+            DQ_PROF_STORE(0, 13);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// W1 fp32 [256][32] -> 32 KB image [256 rows][hi 32 | lo 32] fp16 (K-major, SWIZZLE_128B) of W1 * 2^s1 with s1 chosen so that
+// max|W1| * 2^s1 lies in [2^12, 2^13) (keeps the lo parts out of the fp16 subnormals); inv[0] = 2^-s1.  One CTA of 256 threads.
+__global__ void __launch_bounds__(256)
+prep_w1_kernel(const float* __restrict__ W1, uint8_t* __restrict__ image, float* __restrict__ inv) {
+    __shared__ float red[256];
+    const int n = threadIdx.x;
+    float m = 0.f;
+    for (int k = 0; k < C0; ++k) m = fmaxf(m, fabsf(W1[n * C0 + k]));
+    red[n] = m;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (n < s) red[n] = fmaxf(red[n], red[n + s]);
+        __syncthreads();
+    }
+    const float mx = red[0];
+    const int s1 = (mx > 0.f && mx < INFINITY) ? 12 - ilogbf(mx) : 0;
+    const float sc = ldexpf(1.0f, s1);
+    if (n == 0) inv[0] = ldexpf(1.0f, -s1);
+    for (int k = 0; k < C0; ++k) {
+        const float w = fminf(fmaxf(W1[n * C0 + k] * sc, -65504.f), 65504.f);
+        const __half h = __float2half_rn(w);
+        const __half l = __float2half_rn(w - __half2float(h));
+        *reinterpret_cast<__half*>(image + sw128_offset(n, k)) = h;
+        *reinterpret_cast<__half*>(image + sw128_offset(n, C0 + k)) = l;
+    }
+}
+
+template <int COUT>
+static int32_t launch(const Params& p, cudaStream_t st) {
+    const int smem = Smem::total + 1024;
+    GNB_CUDA(cudaFuncSetAttribute(decode_query_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int grid = sm_count();
+    if ((int64_t)grid > p.num_tiles) grid = (int)p.num_tiles;
+    decode_query_kernel<COUT><<<grid, THREADS, smem, st>>>(p);
+    return check_launch("gnb_decode_tc_query_fused");
+}
+
+}  // namespace dq
+
+#ifdef GNB_PROFILE_KNOBS
+extern "C" __attribute__((visibility("default"))) int32_t gnb_prof_decode_query_read(unsigned long long* host_out, int32_t n) {
+    return cudaMemcpyFromSymbol(host_out, dq::g_prof, sizeof(unsigned long long) * (size_t)n) == cudaSuccess ? 0 : -1;
+}
+#endif
+
+// Called by gnb_decode_tc_query_fused (decode_tc.cu) when BatchNorm1 is folded into W2.  scratch: 16384 floats =
+// [w3s 768 | tail 12 ... | @1024: inv_s1 | @2048: W1 image (32 KB)].
+int32_t launch_decode_query(const float* X, int B, int G, const float* W1, const float* b1, const float* q, const int64_t* qptr,
+                            int64_t R, const void* w2_packed, int w2_scale_log2, const float* b2, const float* w3s,
+                            const float* tail, int Cout, float* scratch, float* out, cudaStream_t st) {
+    float* inv = scratch + 1024;
+    uint8_t* image = reinterpret_cast<uint8_t*>(scratch + 2048);
+    dq::prep_w1_kernel<<<1, 256, 0, st>>>(W1, image, inv);
+    ConstBankGuard guard(BANK_DECODE_QUERY, st);
+    GNB_CUDA(cudaMemcpyToSymbolAsync(dq::c_epi, b1, sizeof(float) * 256, 0, cudaMemcpyDeviceToDevice, st));
+    GNB_CUDA(cudaMemcpyToSymbolAsync(dq::c_epi, b2, sizeof(float) * 256, sizeof(float) * 256, cudaMemcpyDeviceToDevice, st));
+    GNB_CUDA(cudaMemcpyToSymbolAsync(dq::c_epi, w3s, sizeof(float) * 256 * Cout, sizeof(float) * 512, cudaMemcpyDeviceToDevice, st));
+    dq::Params p;
+    p.X = X; p.B = B; p.G = G; p.q = q; p.qptr = qptr; p.R = R;
+    p.num_tiles = ceil_div<int64_t>(R, dq::M);
+    p.w1_image = image; p.inv_s1 = inv;
+    p.w2_packed = reinterpret_cast<const uint8_t*>(w2_packed);
+    p.acc_scale = ldexpf(1.0f, -w2_scale_log2);
+    p.tail = tail; p.out = out;
+    if (Cout == 1) return dq::launch<1>(p, st);
+    if (Cout == 2) return dq::launch<2>(p, st);
+    return dq::launch<3>(p, st);
+}
+
+}  // namespace gnb

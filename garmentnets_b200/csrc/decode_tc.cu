@@ -756,6 +756,13 @@ int32_t gnb_decode_tc_query(const float* U, int32_t B, int32_t G, const float* q
     return launch_decode_tc<3, 2>(p, st);
 }
 
+// tests / A-B measurements: 1 selects the first-generation kernel (Linear1 with FFMA2 in the producers) for every call
+static bool g_force_ffma_linear1 = false;
+int32_t gnb_decode_query_set_mode(int32_t ffma_linear1) {
+    g_force_ffma_linear1 = ffma_linear1 != 0;
+    return GNB_OK;
+}
+
 int32_t gnb_decode_tc_query_fused(const float* X, int32_t B, int32_t G, int32_t C0, const float* W1, const float* b1,
                                   const float* q, const int64_t* qptr, int64_t R, const float* bn1_scale,
                                   const float* bn1_shift, const void* w2_packed, int32_t w2_scale_log2, const float* b2,
@@ -774,6 +781,10 @@ int32_t gnb_decode_tc_query_fused(const float* X, int32_t B, int32_t G, int32_t 
     float* w3s = scratch;
     float* tail = scratch + 3 * TC_N;
     fold_tail_kernel<<<Cout, TC_N, 0, st>>>(W3, b3, bn2_scale, bn2_shift, bn3_scale, bn3_shift, Cout, w3s, tail);
+    // BatchNorm1 folded into W2 (the shipped configuration): Linear1 runs on the tensor cores too (decode_query.cu); the
+    // kernel below (Linear1 per query with FFMA2 in the producer warps) remains for an un-folded BatchNorm1
+    if (bn1_scale == nullptr && !g_force_ffma_linear1)
+        return launch_decode_query(X, B, G, W1, b1, q, qptr, R, w2_packed, w2_scale_log2, b2, w3s, tail, Cout, scratch, out, st);
     ConstBankGuard guard(BANK_DECODE_TC, st);
     { const int32_t rc = upload_epilogue_constants(b2, w3s, Cout, st); if (rc != GNB_OK) return rc; }
     TcParams p;

@@ -282,13 +282,19 @@ int32_t gnb_decode_tc_query(const float* U, int32_t B, int32_t G, const float* q
  * final_conv is folded into W1), W1 f32[256,32], b1 f32[256].  The gather shrinks from 8 x 1 KB to 8 x 128 B per
  * query; everything else as gnb_decode_tc_query.  bn1_scale / bn1_shift may be NULL when the caller has folded
  * BatchNorm1 (it follows the ReLU, so it is linear in front of Linear2) into w2_packed / b2: W2' = W2 diag(scale),
- * b2' = b2 + W2 shift -- the fast path. */
+ * b2' = b2 + W2 shift -- the fast path: BOTH contractions then run on tcgen05 (decode_query.cu: Linear1 as six N = 64 MMAs per
+ * 64-channel chunk into a TMEM double buffer, a mid-epilogue warp group turns each chunk into the fp16 hi/lo operand of
+ * Linear2 in shared memory).  With BatchNorm1 given, Linear1 is applied per query with FFMA2 in the producer warps.
+ * scratch: f32[16384] (tail constants, the power-of-two scale of W1 and its 32 KB fp16 shared-memory image). */
 int32_t gnb_decode_tc_query_fused(const float* X, int32_t B, int32_t G, int32_t C0, const float* W1, const float* b1,
                                   const float* q, const int64_t* qptr, int64_t R, const float* bn1_scale,
                                   const float* bn1_shift, const void* w2_packed, int32_t w2_scale_log2,
                                   const float* b2, const float* bn2_scale, const float* bn2_shift,
                                   const float* W3, const float* b3, const float* bn3_scale,
                                   const float* bn3_shift, int32_t Cout, float* scratch, float* out, void* stream);
+/* Tests / A-B measurements: 1 forces the FFMA2-Linear1 kernel for every gnb_decode_tc_query_fused call, 0 (default) picks by
+ * bn1_scale as described above. */
+int32_t gnb_decode_query_set_mode(int32_t ffma_linear1);
 
 /* ---- N13: gaussian gradient magnitude ------------------------------------------------------
  * ref: predict.py:162-163 `ni.gaussian_gradient_magnitude(wnf, sigma, mode="nearest")` (scipy 1.7).

@@ -151,6 +151,32 @@ def test_fused_query_mode_matches_oracle(dev, counts, cout, G):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("counts,cout", [([4000, 1, 0, 2500], 3), ([777], 1)])
+def test_tensor_core_linear1_equals_ffma_linear1(dev, counts, cout):
+    """gnb_decode_tc_query_fused with Linear1 on tcgen05 (decode_query.cu, the default when BatchNorm1 is folded) against the
+    first-generation kernel that applies Linear1 per query with FFMA2: same math, fp16 hi/lo split products vs fp32 FMAs."""
+    from garmentnets_b200 import _lib
+    dec = _decoder(dev, cout, 50 + cout)
+    B, G = len(counts), 16
+    g = torch.Generator().manual_seed(11 + cout)
+    x32 = (torch.randn(B, G, G, G, 32, generator=g) * 0.8).to(dev)
+    final_conv = torch.nn.Conv3d(32, 128, 1).to(dev).requires_grad_(False)
+    q_all = torch.rand(sum(counts), 3, generator=g).to(dev)
+    qptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    try:
+        _lib.call("gnb_decode_query_set_mode", 1)
+        ffma = dec.forward_fused_ragged(x32, final_conv, q_all, qptr)
+        _lib.call("gnb_decode_query_set_mode", 0)
+        tc = dec.forward_fused_ragged(x32, final_conv, q_all, qptr)
+        again = dec.forward_fused_ragged(x32, final_conv, q_all, qptr)
+    finally:
+        _lib.call("gnb_decode_query_set_mode", 0)
+    torch.cuda.synchronize()
+    assert torch.equal(tc, again)
+    assert (tc - ffma).abs().max().item() < 2e-5
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("G,B", [(32, 3), (8, 1), (16, 2), (5, 2), (31, 1)])
 def test_pair_lattice_equals_first_generation(dev, G, B):
     """Pair-tile lattice kernel vs decode_tc lattice mode on other grid sizes (G < 32: idle producer groups; G > 32:

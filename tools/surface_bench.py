@@ -43,6 +43,22 @@ def timeit(name, fn, n=5):
     return best
 
 
-timeit("fused query mode (32-ch gather + Linear1 in kernel)", lambda: dec.forward_fused_ragged(x32, final_conv, q_all, qptr))
+from garmentnets_b200 import _lib
+timeit("query decoder, Linear1 + Linear2 on tcgen05 (default)", lambda: dec.forward_fused_ragged(x32, final_conv, q_all, qptr))
+_lib.call("gnb_decode_query_set_mode", 1)
+timeit("query decoder, Linear1 with FFMA2 in the producers", lambda: dec.forward_fused_ragged(x32, final_conv, q_all, qptr))
+_lib.call("gnb_decode_query_set_mode", 0)
 u = dec.hoisted_folded(x32, final_conv)
 timeit("hoisted query mode (256-ch gather)", lambda: dec.forward_hoisted_ragged(u, q_all, qptr))
+
+# profiling build only (GNB_B200_LIBRARY=.../libgarmentnets_b200_prof.so): per-role wait-time attribution of the query decoder
+lib = _lib.load()
+if hasattr(lib, "gnb_prof_decode_query_read"):
+    import ctypes
+    names = ["mma:a1_full", "mma:acc1_empty", "mma:d_empty", "mma:a2_full", "mma:b_full", "mma:total", "gather:a1_empty", "gather:total",
+             "mid:acc1_full", "mid:a2_empty", "mid:total", "epi:d_full", "epi:total", "load:b_empty"]
+    timeit("query decoder (profiling build)", lambda: dec.forward_fused_ragged(x32, final_conv, q_all, qptr), n=2)
+    buf = np.zeros(1024 * 16, np.uint64)
+    lib.gnb_prof_decode_query_read(ctypes.c_void_p(buf.ctypes.data), ctypes.c_int32(buf.size))
+    t = buf.reshape(1024, 16)[:148].astype(np.float64)
+    print("   Mcycles/CTA: " + " ".join(f"{n}={t[:, i].mean() / 1e6:6.2f}" for i, n in enumerate(names)))
