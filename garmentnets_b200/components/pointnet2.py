@@ -115,6 +115,10 @@ def knn_interpolate(x, pos_x, pos_y, batch_x=None, batch_y=None, k=3, num_worker
     return out
 
 
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
 class PointConv(nn.Module):
     """torch_geometric.nn.PointConv (1.7.2) restricted to what the reference uses: ``local_nn``, max aggregation,
     ``add_self_loops=True``, no ``global_nn``."""
@@ -134,6 +138,10 @@ class PointConv(nn.Module):
         M, K = nbr.shape
         eoffs = ops.pointconv_edges(nbr, cnt)
         cin = 0 if x is None else x.shape[1]
+        fused = self._fused_layers(cin)
+        if fused is not None and x is not None and x.dtype == torch.float32 and x.stride(1) == 1:
+            # one kernel: gather + the three Linear -> ReLU -> BatchNorm blocks + max aggregation, activations stay on chip
+            return ops.pointconv_mlp_max(x, _f32c(pos_x), _f32c(pos_y), nbr, cnt, eoffs, ops.pointconv_mlp_pack(self, fused))
         rows = M * (K + 1)  # worst case; kernels stop at the device-side edge total eoffs[M]
         edge = torch.empty((rows, cin + 3), dtype=torch.float32, device=pos_x.device)
         ops.pointconv_gather(x, pos_x, pos_y, nbr, cnt, eoffs, edge)
@@ -151,6 +159,18 @@ class PointConv(nn.Module):
         lin = last[0]
         w = ops.packed_linear_for(last, "block", lin.weight, lin.bias, last[2] if len(last) > 2 else None)
         return ops.linear_tc_segmax(h, w, ops.segment_ids(eoffs, rows), M, relu=True, rows_dev=total)
+
+    def _fused_layers(self, cin: int):
+        """(weight, bias, bn_scale, bn_shift) of the three blocks when gnb_pointconv_mlp_max can run this MLP, else None."""
+        if not (ops.USE_SA_MLP and self.add_self_loops) or _Block.calibrating:
+            return None
+        blocks = list(self.local_nn) if self.local_nn is not None else []
+        if len(blocks) != 3 or not all(isinstance(b, _Block) and len(b) > 2 and not b.training for b in blocks):
+            return None
+        ch = [blocks[0][0].in_features] + [b[0].out_features for b in blocks]
+        if ch[0] != cin + 3 or not ops.pointconv_mlp_supported(cin, ch[1], ch[2], ch[3]):
+            return None
+        return [(b[0].weight, b[0].bias, *b[2].folded_affine()) for b in blocks]
 
     # Off by default: measured on B200 (batch 32) the fused epilogue -- column-wise run maxima out of a shared-memory box --
     # costs more than it saves (SA1 last layer 1140 us fused vs 525 + 217 us for gnb_linear_tc + gnb_segment_max, both of

@@ -51,7 +51,7 @@ uint32_t* f16_flag_ptr();  // per-device flag: an fp32 value outside the fp16 ra
 // would overwrite the bank under a running kernel, so the guard (a) holds a host mutex from the copy to the launch and
 // (b) makes the new stream wait, on the device, for the event the previous user recorded after its kernel.  Same-stream
 // sequences pay one cudaEventRecord per launch; nothing is serialised on the host.
-enum ConstBank { BANK_LATTICE = 0, BANK_DECODE_TC = 1, BANK_LINEAR_TC = 2, BANK_DECODE_QUERY = 3, BANK_COUNT = 4 };
+enum ConstBank { BANK_LATTICE = 0, BANK_DECODE_TC = 1, BANK_LINEAR_TC = 2, BANK_DECODE_QUERY = 3, BANK_SA_MLP = 4, BANK_COUNT = 5 };
 class ConstBankGuard {
 public:
     ConstBankGuard(ConstBank bank, cudaStream_t st);

@@ -632,6 +632,51 @@ def gaussian_gradient_magnitude_batched(v: torch.Tensor, sigma: float) -> torch.
     return out
 
 
+USE_SA_MLP = True          # False: PointConv runs as gather + three Linear blocks + segment max (the unfused chain)
+
+
+def pointconv_mlp_supported(cin: int, c1: int, c2: int, c3: int) -> bool:
+    return bool(_lib.call("gnb_pointconv_mlp_supported", int(cin), int(c1), int(c2), int(c3)))
+
+
+def pointconv_mlp_pack(owner, layers):
+    """``layers`` = three (weight, bias, bn_scale, bn_shift) tuples of a PointConv message MLP -> cached (packed images,
+    scales, constants) for :func:`pointconv_mlp_max`.  BatchNorm1 / 2 (they follow a ReLU) are folded into the next layer."""
+    key = _version_key(*[t for layer in layers for t in layer])
+    cached = getattr(owner, "_gnb_sa_mlp", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    (w1, b1, s1, t1), (w2, b2, s2, t2), (w3, b3, s3, t3) = layers
+    with torch.no_grad():
+        w2f = (w2 * s1[None, :]).contiguous()
+        b2f = b2 + w2 @ t1
+        w3f = (w3 * s2[None, :]).contiguous()
+        b3f = b3 + w3 @ t2
+        c1, cin = w1.shape[0], w1.shape[1] - 3
+        c2, c3 = w2.shape[0], w3.shape[0]
+        small = w1[:, cin:] if cin >= 16 else w1                       # layer-1 weights applied in fp32: [C1, KIN]
+        consts = torch.cat([b1, small.t().contiguous().view(-1), b2f, b3f, s3, t3]).contiguous().float()
+        scales = (_pow2_scale(w1[:, :cin]) if cin >= 16 else 0, _pow2_scale(w2f), _pow2_scale(w3f))
+        packed = torch.empty(int(_lib.load().gnb_pointconv_mlp_packed_bytes(cin, c1, c2, c3)), dtype=torch.uint8, device=w1.device)
+        _lib.call("gnb_pointconv_mlp_pack", w1.contiguous().data_ptr(), w2f.data_ptr(), w3f.data_ptr(), cin, c1, c2, c3, *scales,
+                  packed.data_ptr(), _stream())
+    val = (packed, scales, consts, (cin, c1, c2, c3))
+    owner._gnb_sa_mlp = (key, val)
+    return val
+
+
+def pointconv_mlp_max(x, pos_x, pos_y, nbr, cnt, eoffs, pack) -> torch.Tensor:
+    """Fused PointConv (``gnb_pointconv_mlp_max``): message MLP over the grouped edges + max aggregation -> [M, C3]."""
+    packed, scales, consts, (cin, c1, c2, c3) = pack
+    M, K = nbr.shape
+    out = torch.empty((M, c3), dtype=torch.float32, device=pos_x.device)
+    ws = torch.empty(2 * M * (K + 1), dtype=torch.int32, device=pos_x.device)
+    _lib.call("gnb_pointconv_mlp_max", _ptr(x), x.stride(0) if x is not None else 0, cin, pos_x.data_ptr(), pos_y.data_ptr(),
+              nbr.data_ptr(), cnt.data_ptr(), eoffs.data_ptr(), M, K, packed.data_ptr(), c1, c2, c3, *scales, consts.data_ptr(),
+              ws.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
 def f16_range_check(t: torch.Tensor) -> None:
     """Queue a check of ``t`` (fp32, any shape) against the fp16 range of the tensor-core operand split; the outcome is read
     with :func:`f16_overflow` (one flag per device, see include/garmentnets_b200.h)."""

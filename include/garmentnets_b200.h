@@ -408,6 +408,26 @@ int32_t gnb_nn1_distance(const float* q, const int64_t* ptr_q, const float* r, c
                          void* stream);
 
 #if defined(__GNUC__)
+/* ---- PointConv message MLP + max aggregation in one kernel (ref components/pointnet2.py:30-31 with
+ * local_nn = MLP([Cin+3, C1, C2, C3]), components/mlp.py:9-20; aggr = 'max') -----------------------------------------
+ * Replaces gnb_pointconv_gather + 3 x gnb_linear_tc + gnb_segment_max for the two local set-abstraction levels: the [E, C]
+ * activations of the edge MLP never reach HBM (11 GB per step at batch 32).  Supported widths (gnb_pointconv_mlp_supported):
+ * 3+3 -> 64 -> 64 -> 128 (SA1) and 128+3 -> 128 -> 128 -> 256 (SA2).
+ *   gnb_pointconv_mlp_pack: W1 [C1, Cin+3], W2' [C2, C1], W3' [C3, C2] fp32 (BatchNorm1 / 2 folded into W2' / W3' by the caller:
+ *     they follow a ReLU) -> fp16 hi/lo shared-memory images, scaled by 2^s1 / 2^s2 / 2^s3; packed: gnb_pointconv_mlp_packed_bytes.
+ *   gnb_pointconv_mlp_max: edges = gnb_ball_query output (nbr i64[sumM,K], cnt) with PointConv's self loops, offsets eoffs
+ *     i64[sumM+1] from gnb_pointconv_edge_count + scan (as for gnb_pointconv_gather); consts f32 = [b1 C1 | w1 KIN x C1 | b2' C2 |
+ *     b3' C3 | bn3_scale C3 | bn3_shift C3] where w1 holds, input-major, the layer-1 weights applied in fp32 (SA1: all 6 inputs,
+ *     SA2: the 3 relative-position inputs, KIN = 3); edge_ws i32[2 * sumM * (K+1)] scratch; out f32[sumM, C3]. */
+int32_t gnb_pointconv_mlp_supported(int32_t Cin, int32_t C1, int32_t C2, int32_t C3);
+int64_t gnb_pointconv_mlp_packed_bytes(int32_t Cin, int32_t C1, int32_t C2, int32_t C3);
+int32_t gnb_pointconv_mlp_pack(const float* W1, const float* W2, const float* W3, int32_t Cin, int32_t C1, int32_t C2,
+                               int32_t C3, int32_t s1, int32_t s2, int32_t s3, void* packed, void* stream);
+int32_t gnb_pointconv_mlp_max(const float* x, int64_t ldx, int32_t Cin, const float* pos_x, const float* pos_y,
+                              const int64_t* nbr, const int32_t* cnt, const int64_t* eoffs, int64_t sumM, int32_t K,
+                              const void* packed, int32_t C1, int32_t C2, int32_t C3, int32_t s1, int32_t s2, int32_t s3,
+                              const float* consts, int32_t* edge_ws, float* out, void* stream);
+
 /* ---- fp16 operand range flag --------------------------------------------------------------------------------------
  * The tensor-core kernels split fp32 operands into fp16 hi + lo with saturating conversions (+-65504).  With trained
  * checkpoints an activation outside that range would silently be clamped; one flag per device records it instead:

@@ -184,3 +184,42 @@ def test_segment_max_shapes(dev, nseg, C, maxlen):
         if lens[i]:
             ref[i] = rows[offs[i]:offs[i + 1]].max(0)
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,channels,r,sizes", [(3, [6, 64, 64, 128], 0.08, [1500, 900]), (128, [131, 128, 128, 256], 0.15, [700, 1100, 300]),
+                                                  (3, [6, 64, 64, 128], 0.6, [400])])
+def test_fused_pointconv_matches_unfused_chain(dev, cin, channels, r, sizes):
+    """gnb_pointconv_mlp_max (gather + three Linear->ReLU->BN blocks on tcgen05 + max aggregation in one kernel, activations in
+    tensor memory) against the unfused chain gather / gnb_linear_tc x 3 / gnb_segment_max, which the oracle tests pin
+    (ref components/pointnet2.py:30-31).  The third case saturates the 64-neighbour limit (65 edges per centre with the self loop)."""
+    from garmentnets_b200 import ops, synthetic
+    from garmentnets_b200.components.mlp import MLP
+    from garmentnets_b200.components.pointnet2 import CloudIndex, PointConv, fps
+    torch.manual_seed(cin)
+    conv = PointConv(synthetic.randomize_(MLP(channels), 3)).eval().requires_grad_(False).to(dev)
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    index = CloudIndex(torch.from_numpy(ptr).to(dev), ptr)
+    g = torch.Generator().manual_seed(sum(sizes))
+    pos = torch.rand(int(ptr[-1]), 3, generator=g).to(dev)
+    x = (torch.randn(int(ptr[-1]), cin, generator=g) * (1.0 if cin == 3 else 0.7)).to(dev)
+    sub = index.subsample(0.5)
+    idx = fps(pos, None, 0.5, False, index=index)
+    pos_y = pos[idx]
+    nbr, cnt = ops.ball_query(pos, pos_y, index.ptr, sub.ptr, r, 64)
+    if r > 0.5:
+        assert int(cnt.max()) == 64
+    assert conv._fused_layers(cin) is not None
+    try:
+        ops.USE_SA_MLP = False
+        ref = conv.forward_grouped(x, pos, pos_y, nbr, cnt)
+        ops.USE_SA_MLP = True
+        got = conv.forward_grouped(x, pos, pos_y, nbr, cnt)
+        again = conv.forward_grouped(x, pos, pos_y, nbr, cnt)
+    finally:
+        ops.USE_SA_MLP = True
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape == (pos_y.shape[0], channels[-1])
+    assert torch.equal(got, again)                       # integer atomics: deterministic
+    tol = 3e-5 * max(1.0, float(ref.abs().max()))
+    assert float((got - ref).abs().max()) < tol, (float((got - ref).abs().max()), tol)
