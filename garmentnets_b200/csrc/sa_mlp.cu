@@ -115,20 +115,30 @@ struct Cfg {
 constexpr uint32_t idesc_n(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 
 // MMAs of one layer: acc[128 x N] = A[128 x K] (TMEM: hi columns a_col.., lo columns a_col + K/2..) x W^T (image of K/64 x {hi, lo}
-// pieces of N rows x 128 B)
+// pieces of N rows x 128 B).  The tensor core truncates its fp32 accumulator on every instruction (~0.5 ulp of the ACCUMULATOR,
+// whatever the size of the addend); the small cross terms lo*hi and hi*lo therefore go FIRST, while the accumulator is still
+// 2^-11 of its final size and its ulp negligible, and only the K/16 hi*hi instructions truncate at full scale -- the effect of
+// gnb_linear_tc's separate cross-term accumulator without its TMEM columns (sharing one accumulator in the order hi*hi, lo*hi,
+// hi*lo per K-step doubled the end-to-end error of the PointNet++ chain).
 template <int K, int N>
 __device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t a_col, uint32_t acc_col, uint32_t w_smem) {
     constexpr uint32_t PIECE = (uint32_t)N * 128u;
+    const uint32_t acc = tmem_base + acc_col, ahi = tmem_base + a_col, alo = ahi + (uint32_t)(K / 2);
 #pragma unroll
     for (int kc = 0; kc < K / 64; ++kc) {
         const uint32_t whi = w_smem + (uint32_t)(2 * kc) * PIECE, wlo = whi + PIECE;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const uint32_t ks = (uint32_t)(kc * 4 + kk);
-            umma_f16_ta(tmem_base + acc_col, tmem_base + a_col + ks * 8u, umma_desc(whi + kk * 32), idesc_n(N), ks != 0);
-            umma_f16_ta(tmem_base + acc_col, tmem_base + a_col + (uint32_t)(K / 2) + ks * 8u, umma_desc(whi + kk * 32), idesc_n(N), 1);
-            umma_f16_ta(tmem_base + acc_col, tmem_base + a_col + ks * 8u, umma_desc(wlo + kk * 32), idesc_n(N), 1);
+            umma_f16_ta(acc, alo + ks * 8u, umma_desc(whi + kk * 32), idesc_n(N), ks != 0);
+            umma_f16_ta(acc, ahi + ks * 8u, umma_desc(wlo + kk * 32), idesc_n(N), 1);
         }
+    }
+#pragma unroll
+    for (int kc = 0; kc < K / 64; ++kc) {
+        const uint32_t whi = w_smem + (uint32_t)(2 * kc) * PIECE;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_f16_ta(acc, ahi + (uint32_t)(kc * 4 + kk) * 8u, umma_desc(whi + kk * 32), idesc_n(N), 1);
     }
 }
 

@@ -200,12 +200,14 @@ def test_reference_own_sa_fp_modules_on_our_pyg_stand_ins(setup):
     x1, pos1, b1 = sa1_ref(data.x, data.pos, data.batch)
     mx1, mpos1, mb1 = net.sa1_module(data.x, data.pos, data.batch)
     assert torch.equal(pos1, mpos1) and torch.equal(b1, mb1)
-    assert torch.equal(x1, mx1)
-    assert close(x1.cpu().numpy(), s["s1"]["sa1"][0])
+    # the reference module reaches PointConv.forward(x, pos, edge_index) (gather / three Linear blocks / segment max); our
+    # SAModule runs the fused gnb_pointconv_mlp_max: same edges and weights, fp16 hi/lo tensor-core products both ways
+    assert close(x1.cpu().numpy(), mx1.cpu().numpy())
+    assert close(x1.cpu().numpy(), s["s1"]["sa1"][0]) and close(mx1.cpu().numpy(), s["s1"]["sa1"][0])
     sa2_ref = rp.SAModule(net.sa2_module.ratio, net.sa2_module.r, net.sa2_module.conv.local_nn).to(s["dev"]).eval()
     x2, pos2, b2 = sa2_ref(x1, pos1, b1)
     mx2, mpos2, mb2 = net.sa2_module(mx1, mpos1, mb1)
-    assert torch.equal(pos2, mpos2) and torch.equal(x2, mx2)
+    assert torch.equal(pos2, mpos2) and close(x2.cpu().numpy(), mx2.cpu().numpy())
     assert close(x2.cpu().numpy(), s["s1"]["sa2"][0])
     sa3_ref = rp.GlobalSAModule(net.sa3_module.nn)
     x3, pos3, b3 = sa3_ref(x2, pos2, b2)
