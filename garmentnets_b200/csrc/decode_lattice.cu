@@ -162,9 +162,15 @@ __device__ __forceinline__ void axis_cell(int idx, float sq, int G, int& c0, int
 // producers' stores compete for.  Cross-CTA hand-shakes: the peer's producers / epilogue arrive remotely on the leader's
 // a_full / d_empty barriers, the leader's commits are multicast to both CTAs' a_empty / b_empty / d_full barriers, and the
 // peer reports the landing of its W2 halves on the leader's b_peer barriers.
-template <int COUT, bool PAIR>
-__global__ void __launch_bounds__(THREADS, 1)
+// NPW: A-producer warps.  8 = 16 lanes x 4 channels per cell pair (one warp covers a 64-channel chunk of two cell pairs);
+// 16 = the same cell pairs with 2 channels per lane, warps 8-15 taking the upper 32 channels of the chunk (80 registers per
+// thread).  Measured: no gain from the extra warps, see g_producer_warps.
+template <int COUT, bool PAIR, int NPW>
+__global__ void __launch_bounds__(NPW == 16 ? 768 : THREADS, 1)
 decode_lattice_kernel(const Params p) {
+    constexpr int CPL = NPW == 16 ? 2 : 4;        // channels per producer lane
+    constexpr int NH = CPL / 2;                   // packed channel pairs per lane
+    constexpr int W_MMA = NPW + 4, W_LOAD = NPW + 5;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
@@ -191,12 +197,12 @@ decode_lattice_kernel(const Params p) {
     const float sq = __fdiv_rn(1.0f, (float)(Q - 1));
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < A_SLOTS; ++s) { mbar_init(a_full(s), PAIR ? 16 : 8); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < A_SLOTS; ++s) { mbar_init(a_full(s), PAIR ? 2 * NPW : NPW); mbar_init(a_empty(s), 1); }
         for (int s = 0; s < BS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); mbar_init(b_peer(s), 1); }
         for (int t = 0; t < 2; ++t) { mbar_init(d_full(t), 1); mbar_init(d_empty(t), PAIR ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x == 416) {
+    if (warp == W_LOAD && lane == 0) {
         // pairing of the Q lattice lines of one i-plane: two lines of the same y-cell share their corner columns, so
         // pairs are formed inside the runs of equal y-cell; the few left-over lines are paired with each other
         uint8_t* pt = smem + Smem::pairs;
@@ -227,7 +233,7 @@ decode_lattice_kernel(const Params p) {
         reinterpret_cast<float2*>(smem + Smem::rowtab)[k] = make_float2(w0, w1);
         (smem + Smem::axtab)[k] = (uint8_t)z0;
     }
-    if (warp == 12) {
+    if (warp == W_MMA) {
         if (PAIR) {
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Smem::tmem_ptr), "r"(512));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
@@ -255,22 +261,23 @@ decode_lattice_kernel(const Params p) {
     __syncthreads();
     const uint8_t* pairs = smem + Smem::pairs;
 
-    if (warp < 8) {
+    if (warp < NPW) {
         // =========================== A producers ===========================
         // A 16-lane group owns two adjacent D-cells (three slices) of both lines and 4 consecutive channels per lane.
         // The producers are the critical path of the kernel (the MMA issuer waited on a_full for a third of the run), and each
         // SM sub-partition runs only two of these warps, so the code is written for instruction-level parallelism: item
         // decoding by shifts (Q = 128), per-axis cell / weight table in shared memory, corner pointers per pair, and two rows
         // (eight independent blend -> ReLU -> split chains) computed before their eight stores.
-        const int pw = warp;
+        const int pw = warp & 7;
         const int cp = pw * 2 + (lane >> 4);      // cell pair: cells 2cp, 2cp+1
         const int l16 = lane & 15;
+        const int cho = (warp >> 3) * 32 + l16 * CPL;   // first channel of this lane inside a 64-channel chunk
         const bool active = 2 * cp < G;           // G < 32: the surplus groups only pace the barriers
         const int dA = 2 * cp < G ? 2 * cp : G - 1;
         const uint32_t sd = (uint32_t)G * G * K;  // elements per D-slice (<= 2^18)
         const uint32_t soff[3] = {(uint32_t)dA * sd, (uint32_t)(dA + 1 < G ? dA + 1 : G - 1) * sd, (uint32_t)(dA + 2 < G ? dA + 2 : G - 1) * sd};
         // byte offset of this lane's 8-byte store inside a 128-byte swizzled row: 16-byte unit (l16 >> 1) ^ (k & 7)
-        const uint32_t unit = (uint32_t)(l16 >> 1), sub8 = (uint32_t)(l16 & 1) * 8u;
+        const uint32_t unit = (uint32_t)(cho >> 3), sub8 = (uint32_t)(cho & 7) * 2u;
         const uint32_t axtab = sbase + Smem::axtab, rowtab = sbase + Smem::rowtab, kstab = sbase + Smem::kstart;
         // read-only tables: plain (non-volatile) shared loads, free to be hoisted and interleaved by the compiler
         auto lds2 = [](uint32_t addr) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; };
@@ -299,25 +306,35 @@ decode_lattice_kernel(const Params p) {
         // the four (y, x) corner columns of lattice line (i, j) of sample b, at this lane's channels of chunk 0
         auto corners = [&](int b, int i, int j, const float* (&cptr)[4]) {
             const uint4 ax = axis(i), ay = axis(j);
-            const float* ub = p.U + (size_t)b * G * sd + l16 * 4;
+            const float* ub = p.U + (size_t)b * G * sd + cho;
             cptr[0] = ub + (ay.z * (uint32_t)G + ax.z) * (uint32_t)K;
             cptr[1] = ub + (ay.z * (uint32_t)G + ax.w) * (uint32_t)K;
             cptr[2] = ub + (ay.w * (uint32_t)G + ax.z) * (uint32_t)K;
             cptr[3] = ub + (ay.w * (uint32_t)G + ax.w) * (uint32_t)K;
         };
         // gathers of one line for chunk c: [slice][y][x] 16-byte loads
-        auto issue = [&](const float* const (&cptr)[4], int c, float4 (&r)[3][2][2]) {
+        // this lane's CPL channels at p as NH packed pairs
+        auto ldv = [](const float* ptr, float2 (&v)[NH]) {
+            if (CPL == 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(ptr));
+                v[0] = make_float2(t.x, t.y);
+                v[NH - 1] = make_float2(t.z, t.w);
+            } else {
+                v[0] = __ldg(reinterpret_cast<const float2*>(ptr));
+            }
+        };
+        auto issue = [&](const float* const (&cptr)[4], int c, float2 (&r)[3][2][2][NH]) {
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
                 const uint32_t o = soff[s] + (uint32_t)c * KCHUNK;
-                r[s][0][0] = __ldg(reinterpret_cast<const float4*>(cptr[0] + o));
-                r[s][0][1] = __ldg(reinterpret_cast<const float4*>(cptr[1] + o));
-                r[s][1][0] = __ldg(reinterpret_cast<const float4*>(cptr[2] + o));
-                r[s][1][1] = __ldg(reinterpret_cast<const float4*>(cptr[3] + o));
+                ldv(cptr[0] + o, r[s][0][0]);
+                ldv(cptr[1] + o, r[s][0][1]);
+                ldv(cptr[2] + o, r[s][1][0]);
+                ldv(cptr[3] + o, r[s][1][1]);
             }
         };
 
-        float4 nxt[3][2][2];
+        float2 nxt[3][2][2][NH];
         DL2_PROF_DECL;
         uint32_t q = 0;  // running chunk counter (slot = q & 1)
         const uint32_t npairs = (uint32_t)p.num_pairs;
@@ -344,20 +361,18 @@ decode_lattice_kernel(const Params p) {
                     const long long t_a = clock64();
 #endif
                     // 1. x-blend of the prefetched corners: X[s][y] (4 channels as two packed pairs)
-                    float2 X[3][2][2];
+                    float2 X[3][2][NH];
                     const float2 vx0 = make_float2(wx0, wx0), vx1 = make_float2(wx1, wx1);
 #pragma unroll
                     for (int s = 0; s < 3; ++s)
 #pragma unroll
-                        for (int yy = 0; yy < 2; ++yy) {
-                            const float4 a = nxt[s][yy][0], bq = nxt[s][yy][1];
-                            X[s][yy][0] = fma2(make_float2(bq.x, bq.y), vx1, mul2(make_float2(a.x, a.y), vx0));
-                            X[s][yy][1] = fma2(make_float2(bq.z, bq.w), vx1, mul2(make_float2(a.z, a.w), vx0));
-                        }
+                        for (int yy = 0; yy < 2; ++yy)
+#pragma unroll
+                            for (int h2 = 0; h2 < NH; ++h2) X[s][yy][h2] = fma2(nxt[s][yy][1][h2], vx1, mul2(nxt[s][yy][0][h2], vx0));
 #ifdef GNB_PROFILE_KNOBS
                     // the clock read must follow the blend: make it depend on one blended value
                     long long t_b;
-                    asm volatile("{ .reg .f32 t; mov.f32 t, %1; mov.u64 %0, %%clock64; }" : "=l"(t_b) : "f"(X[2][1][1].y) : "memory");
+                    asm volatile("{ .reg .f32 t; mov.f32 t, %1; mov.u64 %0, %%clock64; }" : "=l"(t_b) : "f"(X[2][1][NH - 1].y) : "memory");
                     prof_acc[2] += (unsigned long long)(t_b - t_a);
 #endif
                     // 2. prefetch the corners of the next chunk (or of the next pair's first chunk)
@@ -372,7 +387,7 @@ decode_lattice_kernel(const Params p) {
                     prof_acc[3] += (unsigned long long)(t_c - t_b);
 #endif
                     // 3. (x, y)-blended slices of both lines: P[l][s] (4 channels as two packed pairs)
-                    float2 P[2][3][2];
+                    float2 P[2][3][NH];
 #pragma unroll
                     for (int l = 0; l < 2; ++l) {
                         const float2 vy0 = make_float2(wy0[l], wy0[l]), vy1 = make_float2(wy1[l], wy1[l]);
@@ -380,7 +395,7 @@ decode_lattice_kernel(const Params p) {
 #pragma unroll
                             for (int s = 0; s < 3; ++s)
 #pragma unroll
-                                for (int h2 = 0; h2 < 2; ++h2) P[l][s][h2] = fma2(X[s][1][h2], vy1, mul2(X[s][0][h2], vy0));
+                                for (int h2 = 0; h2 < NH; ++h2) P[l][s][h2] = fma2(X[s][1][h2], vy1, mul2(X[s][0][h2], vy0));
                         } else {
                             // line 1 lies in another y-cell (left-over lines, ~3 % of the pairs): its own gathers
                             const float* cB[4];
@@ -388,22 +403,19 @@ decode_lattice_kernel(const Params p) {
 #pragma unroll
                             for (int s = 0; s < 3; ++s) {
                                 const uint32_t o = soff[s] + (uint32_t)c * KCHUNK;
-                                const float4 a00 = __ldg(reinterpret_cast<const float4*>(cB[0] + o));
-                                const float4 a10 = __ldg(reinterpret_cast<const float4*>(cB[1] + o));
-                                const float4 a01 = __ldg(reinterpret_cast<const float4*>(cB[2] + o));
-                                const float4 a11 = __ldg(reinterpret_cast<const float4*>(cB[3] + o));
-                                const float2 xa0 = fma2(make_float2(a10.x, a10.y), vx1, mul2(make_float2(a00.x, a00.y), vx0));
-                                const float2 xa1 = fma2(make_float2(a10.z, a10.w), vx1, mul2(make_float2(a00.z, a00.w), vx0));
-                                const float2 xb0 = fma2(make_float2(a11.x, a11.y), vx1, mul2(make_float2(a01.x, a01.y), vx0));
-                                const float2 xb1 = fma2(make_float2(a11.z, a11.w), vx1, mul2(make_float2(a01.z, a01.w), vx0));
-                                P[l][s][0] = fma2(xb0, vy1, mul2(xa0, vy0));
-                                P[l][s][1] = fma2(xb1, vy1, mul2(xa1, vy0));
+                                float2 a00[NH], a10[NH], a01[NH], a11[NH];
+                                ldv(cB[0] + o, a00); ldv(cB[1] + o, a10); ldv(cB[2] + o, a01); ldv(cB[3] + o, a11);
+#pragma unroll
+                                for (int h2 = 0; h2 < NH; ++h2) {
+                                    const float2 xa = fma2(a10[h2], vx1, mul2(a00[h2], vx0)), xb = fma2(a11[h2], vx1, mul2(a01[h2], vx0));
+                                    P[l][s][h2] = fma2(xb, vy1, mul2(xa, vy0));
+                                }
                             }
                         }
                     }
 #ifdef GNB_PROFILE_KNOBS
                     long long t_d;
-                    asm volatile("{ .reg .f32 t; mov.f32 t, %1; mov.u64 %0, %%clock64; }" : "=l"(t_d) : "f"(P[1][2][1].y) : "memory");
+                    asm volatile("{ .reg .f32 t; mov.f32 t, %1; mov.u64 %0, %%clock64; }" : "=l"(t_d) : "f"(P[1][2][NH - 1].y) : "memory");
                     prof_acc[4] += (unsigned long long)(t_d - t_c);
 #endif
                     // 4. the slot must have been consumed by the tensor core (chunk q - 2)
@@ -415,16 +427,18 @@ decode_lattice_kernel(const Params p) {
 #pragma unroll
                     for (int cell = 0; cell < 2; ++cell) {
                         if (2 * cp + cell >= G) break;
-                        float2 sl[2][2];
+                        float2 sl[2][NH];
 #pragma unroll
-                        for (int l = 0; l < 2; ++l) { sl[l][0] = sub2(P[l][cell + 1][0], P[l][cell][0]); sl[l][1] = sub2(P[l][cell + 1][1], P[l][cell][1]); }
+                        for (int l = 0; l < 2; ++l)
+#pragma unroll
+                            for (int h2 = 0; h2 < NH; ++h2) sl[l][h2] = sub2(P[l][cell + 1][h2], P[l][cell][h2]);
                         // one row: z-blend, ReLU, fp16 hi/lo split of this lane's 4 channels of both lines -> v[l] = {hi0, hi1, lo0, lo1}
                         auto row_values = [&](const float wz, uint4 (&v)[2]) {
                             const float2 vz = make_float2(wz, wz);
 #pragma unroll
                             for (int l = 0; l < 2; ++l) {
                                 relu_split2(fma2(sl[l][0], vz, P[l][cell][0]), v[l].x, v[l].z);
-                                relu_split2(fma2(sl[l][1], vz, P[l][cell][1]), v[l].y, v[l].w);
+                                if (NH == 2) relu_split2(fma2(sl[l][NH - 1], vz, P[l][cell][NH - 1]), v[l].y, v[l].w);
                             }
                         };
                         auto row_store = [&](const int k, const uint4 (&v)[2]) {   // row k: 8-row group k >> 3, 128-byte row k & 7, swizzled unit
@@ -434,8 +448,13 @@ decode_lattice_kernel(const Params p) {
 #endif
 #pragma unroll
                             for (int l = 0; l < 2; ++l) {
-                                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + (2 * l) * PART_BYTES), "r"(v[l].x), "r"(v[l].y) : "memory");
-                                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + (2 * l + 1) * PART_BYTES), "r"(v[l].z), "r"(v[l].w) : "memory");
+                                if (NH == 2) {
+                                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + (2 * l) * PART_BYTES), "r"(v[l].x), "r"(v[l].y) : "memory");
+                                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + (2 * l + 1) * PART_BYTES), "r"(v[l].z), "r"(v[l].w) : "memory");
+                                } else {
+                                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + (2 * l) * PART_BYTES), "r"(v[l].x) : "memory");
+                                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + (2 * l + 1) * PART_BYTES), "r"(v[l].z) : "memory");
+                                }
                             }
                         };
                         const int k_end = k_hi[cell];
@@ -479,7 +498,7 @@ decode_lattice_kernel(const Params p) {
             DL2_PROF_STORE(0, 4); DL2_PROF_STORE(1, 6); DL2_PROF_TOTAL(5);
             DL2_PROF_STORE(2, 11); DL2_PROF_STORE(3, 12); DL2_PROF_STORE(4, 13); DL2_PROF_STORE(5, 14);
         }
-    } else if (warp < 12) {
+    } else if (warp < NPW + 4) {
         // =========================== epilogue ===========================
         const int qd = warp & 3;  // TMEM lane quarter this warp may access (warp id mod 4)
         const int row = qd * 32 + lane;
@@ -496,29 +515,30 @@ decode_lattice_kernel(const Params p) {
                 DL2_PROF(0, mbar_wait_sleep(d_full(t), it & 1));
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(t * N);
-                // software pipeline: the next 32 columns are in flight (tcgen05.ld) while the current 32 are folded.  The
+                // software pipeline: the next EC columns are in flight (tcgen05.ld) while the current EC are folded.  The
                 // column loop is fully unrolled so that every b2s / w3s value is an immediate constant-bank operand.
-                uint32_t r0[32], r1[32];
+                constexpr int EC = NPW == 16 ? 16 : 32;   // 16 producer warps leave 80 registers per thread
+                uint32_t r0[EC], r1[EC];
                 float dsum[COUT][4];
 #pragma unroll
                 for (int o = 0; o < COUT; ++o)
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) dsum[o][q4] = 0.f;
-                tmem_ld32(taddr, r0);
+                tmem_ldn(taddr, r0);
 #pragma unroll
-                for (int n0 = 0; n0 < N; n0 += 64) {
+                for (int n0 = 0; n0 < N; n0 += 2 * EC) {
                     if ((p.dbg & 4) && n0 >= 64) break;
                     tmem_ld_wait();
-                    tmem_ld32(taddr + n0 + 32, r1);
+                    tmem_ldn(taddr + n0 + EC, r1);
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) {
+                    for (int u = 0; u < EC; ++u) {
                         const float v = fmaxf(__uint_as_float(r0[u]) + c_epi[n0 + u], 0.f);
 #pragma unroll
                         for (int o = 0; o < COUT; ++o) dsum[o][u & 3] = fmaf(v, c_epi[(1 + o) * N + n0 + u], dsum[o][u & 3]);
                     }
                     tmem_ld_wait();
-                    if (n0 + 64 < N && !((p.dbg & 4) && n0 + 64 >= 64)) {
-                        tmem_ld32(taddr + n0 + 64, r0);
+                    if (n0 + 2 * EC < N && !((p.dbg & 4) && n0 + 2 * EC >= 64)) {
+                        tmem_ldn(taddr + n0 + 2 * EC, r0);
                     } else {
                         // every TMEM read of accumulator t has completed: the next pair's MMAs may overwrite it
                         tc_fence_before();
@@ -526,10 +546,10 @@ decode_lattice_kernel(const Params p) {
                         if (lane == 0) arrive_leader(d_empty(t));
                     }
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) {
-                        const float v = fmaxf(__uint_as_float(r1[u]) + c_epi[n0 + 32 + u], 0.f);
+                    for (int u = 0; u < EC; ++u) {
+                        const float v = fmaxf(__uint_as_float(r1[u]) + c_epi[n0 + EC + u], 0.f);
 #pragma unroll
-                        for (int o = 0; o < COUT; ++o) dsum[o][u & 3] = fmaf(v, c_epi[(1 + o) * N + n0 + 32 + u], dsum[o][u & 3]);
+                        for (int o = 0; o < COUT; ++o) dsum[o][u & 3] = fmaf(v, c_epi[(1 + o) * N + n0 + EC + u], dsum[o][u & 3]);
                     }
                 }
                 float2 dot[COUT][2];
@@ -546,8 +566,8 @@ decode_lattice_kernel(const Params p) {
                 }
             }
         }
-        if (threadIdx.x == 256) { DL2_PROF_STORE(0, 7); DL2_PROF_TOTAL(8); }
-    } else if (warp == 12) {
+        if (warp == NPW && lane == 0) { DL2_PROF_STORE(0, 7); DL2_PROF_TOTAL(8); }
+    } else if (warp == W_MMA) {
         // =========================== MMA issuer (leader CTA) / W2 landing notifier (peer CTA) ===========================
         if (lane == 0 && rank == 0) {
             int it = 0;
@@ -660,7 +680,7 @@ decode_lattice_kernel(const Params p) {
     tc_fence_before();
     __syncthreads();
     if (PAIR) cluster_sync_all();   // both CTAs have drained their accumulators before the pair's TMEM is released
-    if (warp == 12) {
+    if (warp == W_MMA) {
         tc_fence_after();
         if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -705,6 +725,10 @@ __global__ void lattice_prep_kernel(const float* __restrict__ W2, const float* _
 // variance), so the single-CTA kernel is the default; gnb_decode_lattice_set_mode(1) selects the pair form.
 static bool g_use_pair = false;
 static bool g_want_pair = false;
+// 16 producer warps (2 channels per lane) are bit-identical and were measured SLOWER than 8 (17.7 vs 17.1 ms): the row phase of
+// the producers did not shrink with twice the warps -- it is bound by the shared-memory store path it shares with the MMA
+// operand reads, not by per-warp latency.  gnb_decode_lattice_set_mode(2) selects the 16-warp form.
+static int g_producer_warps = 8;
 
 template <int COUT>
 static int32_t launch(const Params& p, cudaStream_t st) {
@@ -713,7 +737,7 @@ static int32_t launch(const Params& p, cudaStream_t st) {
     if ((int64_t)grid > p.num_pairs) grid = (int)p.num_pairs;
     if (g_use_pair && grid >= 2 && (p.num_pairs % 2) == 0) {
         grid &= ~1;
-        GNB_CUDA(cudaFuncSetAttribute(decode_lattice_kernel<COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GNB_CUDA(cudaFuncSetAttribute(decode_lattice_kernel<COUT, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(THREADS);
@@ -726,11 +750,16 @@ static int32_t launch(const Params& p, cudaStream_t st) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        GNB_CUDA(cudaLaunchKernelEx(&cfg, decode_lattice_kernel<COUT, true>, p));
+        GNB_CUDA(cudaLaunchKernelEx(&cfg, decode_lattice_kernel<COUT, true, 8>, p));
         return check_launch("gnb_decode_lattice");
     }
-    GNB_CUDA(cudaFuncSetAttribute(decode_lattice_kernel<COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    decode_lattice_kernel<COUT, false><<<grid, THREADS, smem, st>>>(p);
+    if (g_producer_warps == 16) {
+        GNB_CUDA(cudaFuncSetAttribute(decode_lattice_kernel<COUT, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        decode_lattice_kernel<COUT, false, 16><<<grid, (16 + 6) * 32, smem, st>>>(p);
+        return check_launch("gnb_decode_lattice");
+    }
+    GNB_CUDA(cudaFuncSetAttribute(decode_lattice_kernel<COUT, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    decode_lattice_kernel<COUT, false, 8><<<grid, THREADS, smem, st>>>(p);
     return check_launch("gnb_decode_lattice");
 }
 
@@ -780,7 +809,8 @@ __attribute__((visibility("default"))) int32_t gnb_prof_decode_lattice_read(unsi
 #endif
 
 int32_t gnb_decode_lattice_set_mode(int32_t cta_pair) {
-    dl2::g_want_pair = cta_pair != 0;
+    dl2::g_want_pair = cta_pair == 1;
+    dl2::g_producer_warps = cta_pair == 2 ? 16 : 8;
     return GNB_OK;
 }
 

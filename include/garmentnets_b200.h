@@ -260,9 +260,10 @@ int32_t gnb_decode_lattice(const float* U, int32_t B, int32_t G, int32_t Q, cons
                            int32_t w2f_scale_log2, const float* b2, const float* bn1_shift, const float* bn2_scale,
                            const float* bn2_shift, const float* W3, const float* b3, const float* bn3_scale,
                            const float* bn3_shift, int32_t Cout, float* scratch, float* out, void* stream);
-/* Kernel variant of gnb_decode_lattice: 0 (default) = one CTA per SM with cta_group::1, 1 = clusters of two CTAs issuing
- * tcgen05.mma.cta_group::2 (each SM keeps half of every W2 piece; measured slower on B200, kept for A/B measurements and
- * tests).  Results are bit-identical. */
+/* Kernel variant of gnb_decode_lattice: 0 (default) = one CTA per SM, cta_group::1, 8 A-producer warps (4 channels per lane);
+ * 2 = the same with 16 producer warps (2 channels per lane); 1 = clusters of two CTAs issuing tcgen05.mma.cta_group::2 (each SM
+ * keeps half of every W2 piece).  Both alternatives were measured slower on B200 (17.7 / 18.7 vs 17.1 ms at batch 32) and are
+ * kept for A/B measurements and tests; results are bit-identical across the three. */
 int32_t gnb_decode_lattice_set_mode(int32_t cta_pair);
 /* Query mode of the same kernel (the surface / warp-field decoder, ref predict.py:184-187 and
  * networks/conv_implicit_wnf.py:263-269): H1 = BN1(ReLU(trilinear(U[b], q_r))) for explicit query points q f32[R,3] in

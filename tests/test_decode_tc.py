@@ -235,11 +235,13 @@ def test_cta_pair_lattice_kernel_is_bit_identical_to_single_cta(dev, G, B, cout)
     try:
         _lib.call("gnb_decode_lattice_set_mode", 0)
         single = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
+        _lib.call("gnb_decode_lattice_set_mode", 2)      # 16 producer warps x 2 channels per lane
+        eight = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
         _lib.call("gnb_decode_lattice_set_mode", 1)
         pair = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
         again = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
     finally:
         _lib.call("gnb_decode_lattice_set_mode", 0)   # back to the default (one CTA per SM)
     torch.cuda.synchronize()
-    assert torch.equal(pair, single)
+    assert torch.equal(pair, single) and torch.equal(eight, single)
     assert torch.equal(pair, again)

@@ -40,12 +40,14 @@ out2 = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
 print("max |pair - gen1| =", (out1 - out2).abs().max().item())
 timeit("decode_tc lattice (gen 1)", lambda: ops.decode_tc(*dec._tc_args(), U=u, Q=128, bn1=dec.mlp[0][2].folded_affine()))
 from garmentnets_b200 import _lib
-_lib.call("gnb_decode_lattice_set_mode", 0)
+_lib.call("gnb_decode_lattice_set_mode", 2)
 out3 = ops.decode_lattice(*dec._lattice_args(), U=u, Q=128)
-print("max |cta pair - single cta| =", (out3 - out2).abs().max().item())
-timeit("decode_lattice (pair tiles, one CTA / SM)", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128))
+print("max |8 producer warps - 16 producer warps| =", (out3 - out2).abs().max().item())
+timeit("decode_lattice (one CTA / SM, 16 producer warps)", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128))
 _lib.call("gnb_decode_lattice_set_mode", 1)
-timeit("decode_lattice (pair tiles, cta_group::2)", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128))
+timeit("decode_lattice (cta_group::2 pairs)", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128))
+_lib.call("gnb_decode_lattice_set_mode", 0)
+timeit("decode_lattice (one CTA / SM, 8 producer warps, default)", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128))
 
 # ---- profiling build only (GNB_B200_LIBRARY=garmentnets_b200/lib/libgarmentnets_b200_prof.so): knock-outs and per-role
 # wait-time attribution of both kernel forms
@@ -65,7 +67,7 @@ if hasattr(lib, "gnb_prof_decode_lattice_read"):
         print(f"   [{label}] Mcycles/CTA even: {fmt(lead)}")
         print(f"   [{label}] Mcycles/CTA odd : {fmt(peer)}")
 
-    for mode, mname in ((0, "single"), (1, "cta_group::2")):
+    for mode, mname in ((0, "8 warps"), (2, "16 warps")):
         _lib.call("gnb_decode_lattice_set_mode", mode)
         for dbg in (0,):
             os.environ["GNB_DL2_DBG"] = str(dbg)
