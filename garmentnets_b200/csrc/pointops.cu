@@ -128,59 +128,34 @@ __device__ __forceinline__ int find_segment(const int64_t* __restrict__ ptr, int
     return lo;
 }
 
-// QPW queries per warp: the 32 candidate positions of a round are loaded once and tested against all of them (the loop is
-// bound by its instruction count, a third of which were the three strided position loads).
-constexpr int BQ_QPW = 4;
+// (Four queries per warp sharing the candidate loads were measured slower, 490 vs 455 us for SA1: the loop is bound by
+// the distance / ballot / rank arithmetic per query, not by the position loads.)
 __global__ void __launch_bounds__(256)
 ball_query_kernel(const float* __restrict__ x, const float* __restrict__ y, const int64_t* __restrict__ ptr_x,
                   const int64_t* __restrict__ ptr_y, int B, int64_t sumM, float r2, int K,
                   int64_t* __restrict__ nbr, int32_t* __restrict__ cnt) {
     const int lane = threadIdx.x & 31;
-    const int64_t q0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * BQ_QPW;
-    if (q0 >= sumM) return;
-    const int nq = sumM - q0 < BQ_QPW ? (int)(sumM - q0) : BQ_QPW;
-    float qx[BQ_QPW], qy[BQ_QPW], qz[BQ_QPW];
-    int64_t qs[BQ_QPW], qe[BQ_QPW];
-    int count[BQ_QPW];
-    int64_t lo = INT64_MAX, hi = 0;
-#pragma unroll
-    for (int u = 0; u < BQ_QPW; ++u) {
-        const int64_t q = q0 + (u < nq ? u : 0);
-        const int b = find_segment(ptr_y, B, q);
-        qx[u] = y[q * 3]; qy[u] = y[q * 3 + 1]; qz[u] = y[q * 3 + 2];
-        qs[u] = ptr_x[b]; qe[u] = u < nq ? ptr_x[b + 1] : ptr_x[b];   // padding queries scan nothing
-        count[u] = 0;
-        lo = qs[u] < lo ? qs[u] : lo;
-        hi = qe[u] > hi ? qe[u] : hi;
-    }
-    // the queries of a warp normally share one cloud ([lo, hi) is that cloud); a warp that straddles two clouds scans both
-    // and every query keeps to its own range -- candidates are visited in index order either way
-    for (int64_t base = lo; base < hi; base += 32) {
-        bool live = false;
-#pragma unroll
-        for (int u = 0; u < BQ_QPW; ++u) live |= count[u] < K && base < qe[u];
-        if (!live) break;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= sumM) return;
+    const int b = find_segment(ptr_y, B, q);
+    const float qx = y[q * 3], qy = y[q * 3 + 1], qz = y[q * 3 + 2];
+    const int64_t s = ptr_x[b], e = ptr_x[b + 1];
+    int count = 0;
+    for (int64_t base = s; base < e && count < K; base += 32) {
         const int64_t j = base + lane;
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (j < hi) { px = x[j * 3]; py = x[j * 3 + 1]; pz = x[j * 3 + 2]; }
-#pragma unroll
-        for (int u = 0; u < BQ_QPW; ++u) {
-            const bool hit = j >= qs[u] && j < qe[u] && sqdist_nofma(px, py, pz, qx[u], qy[u], qz[u]) < r2;
-            const unsigned mask = __ballot_sync(0xffffffffu, hit);
-            if (count[u] < K) {
-                const int rank = __popc(mask & ((1u << lane) - 1u));
-                if (hit && count[u] + rank < K) nbr[(q0 + u) * K + count[u] + rank] = j;
-                count[u] += __popc(mask);
-            }
+        bool hit = false;
+        if (j < e) {
+            float d = sqdist_nofma(x[j * 3], x[j * 3 + 1], x[j * 3 + 2], qx, qy, qz);
+            hit = d < r2;
         }
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        const int rank = __popc(mask & ((1u << lane) - 1u));
+        if (hit && count + rank < K) nbr[q * K + count + rank] = j;
+        count += __popc(mask);
     }
-#pragma unroll
-    for (int u = 0; u < BQ_QPW; ++u) {
-        if (u >= nq) break;
-        const int c = count[u] < K ? count[u] : K;
-        for (int t = c + lane; t < K; t += 32) nbr[(q0 + u) * K + t] = -1;
-        if (lane == 0) cnt[q0 + u] = c;
-    }
+    count = count < K ? count : K;
+    for (int t = count + lane; t < K; t += 32) nbr[q * K + t] = -1;
+    if (lane == 0) cnt[q] = count;
 }
 
 __global__ void radius_pairs_kernel(const int64_t* __restrict__ nbr, const int32_t* __restrict__ cnt,
@@ -458,7 +433,7 @@ int32_t gnb_ball_query(const float* x, const float* y, const int64_t* ptr_x, con
     if (sumM == 0) return GNB_OK;
     const float r2 = (float)(r * r);  // torch_cluster passes r*r (double) into a float kernel argument
     const int wpb = 8;
-    ball_query_kernel<<<(unsigned)ceil_div<int64_t>(sumM, (int64_t)wpb * BQ_QPW), wpb * 32, 0, as_stream(stream)>>>(
+    ball_query_kernel<<<(unsigned)ceil_div<int64_t>(sumM, wpb), wpb * 32, 0, as_stream(stream)>>>(
         x, y, ptr_x, ptr_y, B, sumM, r2, K, nbr, cnt);
     return check_launch("gnb_ball_query");
 }
