@@ -462,15 +462,17 @@ def run_ours(args, rank, world):
     # one event pair per gnb_decode_tc call (it brackets fold_tail, ~2 us, and the decode kernel)
     queries_per_launch = (B * args.steps * pr["volume_size"] ** 3) / max(n_k, 1)
     achieved = DECODE_FLOP_PER_QUERY * queries_per_launch / (ms_k / max(n_k, 1) * 1e-3) / 1e12 if n_k else None
-    # DRAM traffic of one launch of that kernel, from the committed `ncu --set full` capture (profiles/ncu_traffic_r01.json,
+    # DRAM traffic of one launch of that kernel, from the committed `ncu --set full` capture (profiles/ncu_traffic_r02.json,
     # written by tools/ncu_traffic.py from the .ncu-rep); null when the capture does not match this batch size
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath)).get("decode_lattice_kernel")
         if tj and tj.get("batch") == B:
             traffic = tj["dram_bytes_per_launch"]
-    roofline = {"kernel": "dl2::decode_lattice_kernel<1> (fused lattice decode: trilinear gather + ReLU + Linear2 (BN1 folded) on "
+    roofline = {"kernel": "dl2::decode_lattice_kernel<1, false, 8> (fused lattice decode: trilinear gather + ReLU + Linear2 (BN1 folded) on "
                           "tcgen05 + BN2 + Linear3 + BN3 for B x 128^3 queries in one launch, pair tiles)",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": (achieved / peaks["bf16_tflops_sustained"]) if achieved else None, "traffic": traffic,

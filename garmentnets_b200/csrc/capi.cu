@@ -108,6 +108,16 @@ int32_t gnb_f16_overflow_fetch(int32_t reset, void* stream) {
     return h ? 1 : 0;
 }
 
+int32_t gnb_f16_overflow_fetch_async(uint32_t* pinned_host_out, int32_t reset, void* stream) {
+    GNB_REQUIRE(pinned_host_out != nullptr, "gnb_f16_overflow_fetch_async: null pointer");
+    uint32_t* flag = gnb::f16_flag_ptr();
+    GNB_REQUIRE(flag != nullptr, "gnb_f16_overflow_fetch_async: flag allocation failed");
+    cudaStream_t st = gnb::as_stream(stream);
+    GNB_CUDA(cudaMemcpyAsync(pinned_host_out, flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (reset) GNB_CUDA(cudaMemsetAsync(flag, 0, sizeof(uint32_t), st));
+    return GNB_OK;
+}
+
 int32_t gnb_version(void) { return 100; /* 0.1.0 */ }
 
 const char* gnb_last_error(void) { return gnb::g_err; }

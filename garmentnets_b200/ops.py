@@ -690,8 +690,16 @@ def f16_overflow(reset: bool = True) -> bool:
     return _lib.call("gnb_f16_overflow_fetch", 1 if reset else 0, _stream()) == 1
 
 
+def f16_overflow_async(pinned: torch.Tensor, reset: bool = True) -> None:
+    """Stream-ordered copy of the flag into ``pinned`` (int32[1], pinned host memory): valid after the next synchronisation of
+    the current stream."""
+    assert pinned.is_pinned() and pinned.dtype == torch.int32 and pinned.numel() >= 1
+    _lib.call("gnb_f16_overflow_fetch_async", pinned.data_ptr(), 1 if reset else 0, _stream())
+
+
 def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0, 1.0), gradient_direction: str = "ascent",
-                         ggm: Optional[torch.Tensor] = None, return_packed: bool = False, with_normals: bool = True):
+                         ggm: Optional[torch.Tensor] = None, return_packed: bool = False, with_normals: bool = True,
+                         lazy_views: bool = False):
     """Marching cubes of N volumes [N,D,H,W] in seven launches and ONE host synchronisation: classify / scan for the
     whole batch, the N 512-byte records come back in a single device->host copy, then compaction, one vertex launch (a
     thread per vertex) and one face launch (a thread per active cell) write every mesh into shared [sum V] / [sum F]
@@ -701,6 +709,8 @@ def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0,
     ``{"verts": f32[sum V,3], "vptr": host i64[N+1] row offsets, "faces": i32[sum F,3], "fptr", "normals", "values",
     "ggm_at"}`` (volumes without a mesh own zero rows).  ``with_normals=False`` skips the per-vertex normals and values
     (``None`` in their place): the reference stores them (predict.py:193-200) but nothing downstream reads them.
+    ``lazy_views`` (with ``return_packed``) leaves ``None`` instead of the per-volume views: 5 x N tensor slices cost ~1 ms of
+    host time for a batch of 32, which the caller should spend AFTER queueing the kernels that consume the packed buffers.
     The triangulation follows the MC33 structure but is NOT pinned to scikit-image's Lewiner tables: vertex / face order and
     the tiling of ambiguous cells can differ from ``skimage.measure.marching_cubes``."""
     import ctypes
@@ -739,6 +749,8 @@ def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0,
             out.append(ValueError("Surface level must be within volume data range."))
         elif V == 0:
             out.append(RuntimeError("No surface found at the given iso value."))
+        elif lazy_views:
+            out.append(None)     # the caller slices the packed buffers itself (after it has queued its next kernels)
         else:
             out.append((verts[vb:vb + V], faces[fb:fb + Fc], normals[vb:vb + V] if with_normals else None,
                         values[vb:vb + V] if with_normals else None, ggm_at[vb:vb + V] if ggm_at is not None else None))

@@ -511,9 +511,14 @@ class ConvImplicitWNFPipeline(nn.Module):
         # Linear1 of the surface decoder hoisted onto the feature grids once
         ggm = ops.gaussian_gradient_magnitude_batched(wnf, gradient_sigma)
         mark("ggm")
+        if check_range:   # the flag rides to the host in front of the marching-cubes totals: no synchronisation of its own
+            flag_host = getattr(self, "_gnb_flag_host", None)
+            if flag_host is None:
+                flag_host = self._gnb_flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            ops.f16_overflow_async(flag_host)
         mcs, packed = ops.marching_cubes_batch(wnf, iso_surface_level, (spacing,) * 3, gradient_direction, ggm,
-                                               return_packed=True, with_normals=with_normals)
-        if check_range and ops.f16_overflow():   # the stream was just synchronised for the marching-cubes totals
+                                               return_packed=True, with_normals=with_normals, lazy_views=True)
+        if check_range and int(flag_host[0]) != 0:   # marching_cubes_batch synchronised the stream for its totals
             raise GarmentNetsB200Error("an activation left the fp16 range of the tensor-core operand split (+-65504) or is not "
                                        "finite: the 3D-UNet / decoder outputs of this batch are not trustworthy")
         mark("marching_cubes")
@@ -540,7 +545,11 @@ class ConvImplicitWNFPipeline(nn.Module):
             elif isinstance(mc, Exception):
                 raise mc  # skimage's RuntimeError ("No surface found") is not caught by the reference either
             else:
-                verts, faces, normals, values, ggm_at = mc
+                # per-sample views of the packed buffers, built only now: the surface decoder is already queued
+                v0, v1, f0, f1 = int(vptr[b]), int(vptr[b + 1]), int(packed["fptr"][b]), int(packed["fptr"][b + 1])
+                verts, faces, ggm_at = packed["verts"][v0:v1], packed["faces"][f0:f1], packed["ggm_at"][v0:v1]
+                normals = packed["normals"][v0:v1] if with_normals else None
+                values = packed["values"][v0:v1] if with_normals else None
                 warp = warp_all[int(vptr[b]):int(vptr[b + 1])]
                 r = {"verts": verts, "faces": faces, "volume_gradient_magnitude": ggm_at, "warp_field": warp}
                 if with_normals:

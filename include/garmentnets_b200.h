@@ -440,6 +440,9 @@ int32_t gnb_pointconv_mlp_max(const float* x, int64_t ldx, int32_t Cin, const fl
  * reset != 0. */
 int32_t gnb_f16_range_check(const float* x, int64_t n, void* stream);
 int32_t gnb_f16_overflow_fetch(int32_t reset, void* stream);
+/* Stream-ordered form: copies the flag into pinned host memory (valid once `stream` has reached this point, e.g. after the
+ * caller's next synchronisation) and clears it when reset != 0; no synchronisation of its own. */
+int32_t gnb_f16_overflow_fetch_async(uint32_t* pinned_host_out, int32_t reset, void* stream);
 
 #pragma GCC visibility pop
 #endif

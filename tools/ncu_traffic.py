@@ -1,4 +1,4 @@
-"""Extract per-launch DRAM traffic of a kernel from an `ncu --set full` report into profiles/ncu_traffic_r01.json (read by
+"""Extract per-launch DRAM traffic of a kernel from an `ncu --set full` report into profiles/ncu_traffic_r02.json (read by
 bench.py for `roofline.traffic`).   python tools/ncu_traffic.py <report.ncu-rep> <key> <batch>"""
 import csv
 import io
@@ -22,7 +22,7 @@ def metric(name):
 
 rd, wr = metric("dram__bytes_read.sum"), metric("dram__bytes_write.sum")
 dur_i = hdr.index("gpu__time_duration.sum")
-out_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic_r01.json")
+out_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic_r02.json")
 data = json.load(open(out_path)) if os.path.exists(out_path) else {}
 data[key] = {"kernel": vals[hdr.index("Kernel Name")], "batch": batch, "dram_bytes_read": rd, "dram_bytes_write": wr,
              "dram_bytes_per_launch": rd + wr, "duration": f"{vals[dur_i]} {units[dur_i]} (under ncu, cold caches)",
