@@ -665,8 +665,8 @@ decode_lattice_kernel(const Params p) {
             for (int64_t pair = blockIdx.x; pair < p.num_pairs; pair += gridDim.x) {
                 for (int pc = 0; pc < 2 * NCHUNK; ++pc, ++piece) {
                     const int slot = piece % BS;
-                    // (spinning on purpose: with the suspend-hint form of try_wait the W2 pieces arrive late, 18.9 vs 17.1 ms, although
-                    // the polling of this thread and of the MMA issuer costs ~10 % of the shared-memory pipe)
+                    // (spinning: neither the suspend-hint form of try_wait nor a 64 ns back-off between probes changed the kernel time
+                    // beyond run-to-run noise in same-run A/B measurements, although polling shows up as ~6 % of the shared-memory pipe)
                     DL2_PROF(0, mbar_wait(b_empty(slot), ((piece / BS) & 1) ^ 1));
                     if (p.dbg & 2) { mbar_arrive(b_full(slot)); continue; }
                     mbar_expect_tx(b_full(slot), BPB);
