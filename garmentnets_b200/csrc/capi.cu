@@ -34,19 +34,31 @@ struct BankState {
 BankState g_banks[BANK_COUNT];
 }  // namespace
 
+// A stream that is being captured into a CUDA graph (pipeline.py captures the static front part of predict()) must not wait on
+// or record the guard's events: inside one captured stream the launches are ordered anyway, and a replayed graph is ordered
+// against other work by the stream it is launched on.  The guard then only serialises the host side.
+static bool stream_is_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &status) != cudaSuccess) { cudaGetLastError(); return false; }
+    return status != cudaStreamCaptureStatusNone;
+}
+
 ConstBankGuard::ConstBankGuard(ConstBank bank, cudaStream_t st) : bank_(bank), dev_(0), st_(st) {
     BankState& b = g_banks[bank_];
     b.mu.lock();
     if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= 64) dev_ = 0;
+    if (stream_is_capturing(st_)) return;
     if (b.done[dev_] == nullptr) cudaEventCreateWithFlags(&b.done[dev_], cudaEventDisableTiming);
     if (b.used[dev_] && b.last[dev_] != st_) cudaStreamWaitEvent(st_, b.done[dev_], 0);
 }
 
 ConstBankGuard::~ConstBankGuard() {
     BankState& b = g_banks[bank_];
-    if (b.done[dev_] != nullptr) cudaEventRecord(b.done[dev_], st_);
-    b.last[dev_] = st_;
-    b.used[dev_] = true;
+    if (!stream_is_capturing(st_)) {
+        if (b.done[dev_] != nullptr) cudaEventRecord(b.done[dev_], st_);
+        b.last[dev_] = st_;
+        b.used[dev_] = true;
+    }
     b.mu.unlock();
 }
 

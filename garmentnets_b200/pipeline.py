@@ -27,7 +27,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import ops, profiling
+from . import _lib, ops, profiling
 from ._lib import GarmentNetsB200Error
 from .components.gridding import VirtualGrid
 from .components.mlp import MLP
@@ -465,15 +465,73 @@ class ConvImplicitWNFPipeline(nn.Module):
                 self.volume_decoder.forward_lattice(u, b, Q, m0, M, out=out[b, m0:m0 + M].view(M, -1))
         return out.view(B, Q, Q, Q)
 
+    def _front(self, data, index, fps_starts, volume_size, gradient_sigma, check_range, mark=lambda name: None):
+        """PointNet++ -> aggregator -> UNet (up to the last decoder) -> dense decode -> ggm: no host synchronisation."""
+        p = self.pointnet2_forward(data, index=index, fps_starts=fps_starts)
+        mark("pointnet2")
+        vol_in = self.volume_agg(p["nocs_data"])
+        mark("aggregator")
+        # UNet up to the last decoder; final_conv (1x1x1, affine) is folded into each implicit decoder's first Linear
+        unet = self.unet_3d.abstract_3d_unet
+        x_last = unet.forward_ndhwc(ops.to_channels_last(vol_in), apply_final=False)
+        mark("unet3d")
+        u_grid = self.volume_decoder.hoisted_folded(x_last, unet.final_conv)
+        if check_range:   # operands of the decoders' fp16 split: the grids they interpolate (a blend never exceeds its corners)
+            ops.f16_range_check(u_grid)
+            ops.f16_range_check(x_last)
+        wnf = self.dense_decode(None, volume_size, hoisted=u_grid)
+        mark("dense_decode")
+        # tail for the whole batch: one set of ggm launches, one host synchronisation for all marching-cubes counts
+        ggm = ops.gaussian_gradient_magnitude_batched(wnf, gradient_sigma)
+        return p, x_last, wnf, ggm
+
+    def _front_graph(self, data, index, volume_size, gradient_sigma, check_range):
+        """``_front`` replayed from a CUDA graph: inputs are copied into the graph's static buffers; the outputs are the
+        graph's static tensors, except the per-point outputs, which are cloned (HostPredictor ships them to the host while the
+        next batch is already being computed)."""
+        key = (tuple(data.x.shape), tuple(data.pos.shape), index.ptr_host.tobytes(), int(volume_size), float(gradient_sigma),
+               bool(check_range), data.x.device.index)
+        cache = self.__dict__.setdefault("_gnb_graphs", {})
+        entry = cache.get(key)
+        if entry is None:
+            static = Batch(x=data.x.clone(), pos=data.pos.clone(), batch=data.batch.clone())
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):       # warm-up on a side stream: caches, lazily packed weights, allocator pools
+                for _ in range(2):
+                    self._front(static, index, None, volume_size, gradient_sigma, check_range)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count
+            with torch.cuda.graph(graph):
+                outs = self._front(static, index, None, volume_size, gradient_sigma, check_range)
+            entry = cache[key] = (graph, static, outs, _lib.launch_count - n0)   # kernels per replay (for the launch counter)
+            if len(cache) > 4:                  # a handful of input shapes at most: drop the oldest graph (and its memory pool)
+                cache.pop(next(iter(cache)))
+        graph, static, (p, x_last, wnf, ggm), n_kernels = entry
+        static.x.copy_(data.x)
+        static.pos.copy_(data.pos)
+        static.batch.copy_(data.batch)
+        graph.replay()
+        _lib.launch_count += n_kernels
+        nd = p["nocs_data"]
+        nocs_data = Batch(x=nd.x, pos=nd.pos.clone(), batch=nd.batch, sim_points=nd.sim_points, pred_confidence=nd.pred_confidence.clone())
+        nocs_data.num_graphs = index.num_graphs
+        return dict(p, nocs_data=nocs_data), x_last, wnf, ggm
+
     @torch.no_grad()
     def predict(self, data, volume_size: int = 128, gradient_sigma: float = 0.5, iso_surface_level: float = 0.5,
                 gradient_direction: str = "ascent", index: Optional[CloudIndex] = None, fps_starts=None,
-                keep_volume: bool = False, with_normals: bool = True, check_range: bool = True) -> List[Dict[str, torch.Tensor]]:
+                keep_volume: bool = False, with_normals: bool = True, check_range: bool = True,
+                cuda_graph: bool = False) -> List[Dict[str, torch.Tensor]]:
         """Device version of the reference's per-sample loop predict.py:138-187, for a whole batch.
         Returns one dict per sample with the arrays predict.py writes under ``marching_cubes_mesh`` / ``point_cloud``.
         ``with_normals=False`` leaves out ``normals`` / ``volume_value`` (written by the reference, read by nothing).
         ``check_range`` (default on, ~0.05 ms per batch): raise instead of returning clamped results when an activation
-        exceeds the fp16 range of the tensor-core operand split (UNet convolution operands and the decoder grids)."""
+        exceeds the fp16 range of the tensor-core operand split (UNet convolution operands and the decoder grids).
+        ``cuda_graph``: capture the static-shape front part (PointNet++ -> gridding -> UNet -> dense decode -> ggm) once per input
+        shape and replay it (needs ``index``, a deterministic FPS start and no ``fps_starts``); the tail after the
+        marching-cubes host synchronisation has data-dependent sizes and stays eager."""
         marks = getattr(self, "stage_marks", None)  # optional [(name, cuda event)] sink used by bench.py
         order = ("pointnet2", "aggregator", "unet3d", "dense_decode", "ggm", "marching_cubes", "surface_decode")
 
@@ -490,26 +548,19 @@ class ConvImplicitWNFPipeline(nn.Module):
                 marks.append((name, ev))
 
         mark("start")
-        p = self.pointnet2_forward(data, index=index, fps_starts=fps_starts)
-        mark("pointnet2")
-        vol_in = self.volume_agg(p["nocs_data"])
-        mark("aggregator")
-        # UNet up to the last decoder; final_conv (1x1x1, affine) is folded into each implicit decoder's first Linear
+        graph_ok = (cuda_graph and marks is None and index is not None and fps_starts is None
+                    and not getattr(self.pointnet2_nocs.sa1_module, "random_start", True))
+        if graph_ok:
+            # static-shape front part (PointNet++ .. ggm, ~95 launches, no host synchronisation) replayed from a CUDA graph
+            p, x_last, wnf, ggm = self._front_graph(data, index, volume_size, gradient_sigma, check_range)
+            if keep_volume:   # the graph's static tensors are overwritten by the next replay
+                wnf, ggm = wnf.clone(), ggm.clone()
+        else:
+            p, x_last, wnf, ggm = self._front(data, index, fps_starts, volume_size, gradient_sigma, check_range, mark)
         unet = self.unet_3d.abstract_3d_unet
-        x_last = unet.forward_ndhwc(ops.to_channels_last(vol_in), apply_final=False)
-        mark("unet3d")
-        u_grid = self.volume_decoder.hoisted_folded(x_last, unet.final_conv)
-        if check_range:   # operands of the decoders' fp16 split: the grids they interpolate (a blend never exceeds its corners)
-            ops.f16_range_check(u_grid)
-            ops.f16_range_check(x_last)
-        wnf = self.dense_decode(None, volume_size, hoisted=u_grid)
-        mark("dense_decode")
         B, Q = wnf.shape[0], wnf.shape[1]
         spacing = 1 / (Q - 1)
         nocs_data = p["nocs_data"]
-        # tail for the whole batch: one set of ggm launches, one host synchronisation for all marching-cubes counts,
-        # Linear1 of the surface decoder hoisted onto the feature grids once
-        ggm = ops.gaussian_gradient_magnitude_batched(wnf, gradient_sigma)
         mark("ggm")
         if check_range:   # the flag rides to the host in front of the marching-cubes totals: no synchronisation of its own
             flag_host = getattr(self, "_gnb_flag_host", None)

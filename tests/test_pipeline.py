@@ -201,6 +201,33 @@ def test_folded_final_conv_equals_two_step(setup):
 
 
 @pytest.mark.gpu
+def test_cuda_graph_front_part_is_bit_identical(setup):
+    """predict(cuda_graph=True) captures PointNet++ .. ggm once and replays it: same kernels, same inputs -> the same bits as
+    the eager path, on the capturing call, on replays, and after the inputs changed."""
+    model, index = setup["model"], setup["index"]
+    data = setup["data"]
+    ref = model.predict(data, volume_size=32, index=index)
+    ref = [{k: v.clone() for k, v in r.items()} for r in ref]
+    for _ in range(3):
+        got = model.predict(data, volume_size=32, index=index, cuda_graph=True)
+        assert len(got) == len(ref)
+        for g, r in zip(got, ref):
+            for k in r:
+                assert torch.equal(g[k], r[k]), k
+    assert len(model.__dict__["_gnb_graphs"]) == 1
+    # different values, same shapes: the replay must see the new inputs
+    from garmentnets_b200.pipeline import Batch
+    moved = Batch(x=data.x.flip(0).contiguous(), pos=data.pos.flip(0).contiguous(), batch=data.batch)
+    eager = model.predict(moved, volume_size=32, index=index)
+    eager = [{k: v.clone() for k, v in r.items()} for r in eager]
+    graph = model.predict(moved, volume_size=32, index=index, cuda_graph=True)
+    for g, r in zip(graph, eager):
+        for k in r:
+            assert torch.equal(g[k], r[k]), k
+    assert torch.equal(model._last_point_outputs["pred_nocs"], model.pointnet2_forward(moved, index=index)["nocs_data"].pos)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("with_normals", [True, False])
 def test_host_predictor_matches_device_predict(setup, with_normals):
     """The host-buffer API (pinned staging, copy stream, double buffering) returns exactly what predict() leaves on the
