@@ -24,6 +24,7 @@ from .. import ops
 
 # tensor-core (TMA + tcgen05) convolutions; False selects the fp32 FFMA kernel everywhere (used by the parity tests)
 USE_TENSOR_CORES = True
+FUSE_UPSAMPLE_CONCAT = True   # decoders: GroupNorm passes read (skip, low-res) directly instead of a materialised upsample + concat
 USE_STACKED_DX = True    # Cout in {32, 64} layers: stacked-kw tensor-core kernel (gnb_conv3d_tc_dx)
 
 
@@ -105,7 +106,41 @@ class SingleConv(nn.Sequential):
                 # narrow layer: the three kw taps share one activation box (shift applied to the output)
                 return ops.conv3d_tc_dx(xh, xl, Cin, self.packed_weight_tc(dx=True), Cout, relu='r' in self.order)
             return ops.conv3d_tc(xh, xl, Cin, self.packed_weight_tc(), Cout, relu='r' in self.order)
+        if USE_TENSOR_CORES and Cout % 128 == 0 and Cout > 128 and ops.conv3d_tc_supported(B, D, H, W, Cin, 128):
+            # wide layer (the 4^3 level's 128 -> 256): Cout / 128 launches of the 128-column tensor-core kernel on slices of the
+            # weight (the fp32 SIMT fallback took 0.31 ms for 5 GFLOP); the slices are concatenated along the channel axis
+            xh, xl = ops.gn_apply_split(x, scale, shift)
+            parts = [ops.conv3d_tc(xh, xl, Cin, w, 128, relu='r' in self.order) for w in self.packed_weight_tc_slices(128)]
+            return torch.cat(parts, dim=-1)
         return ops.conv3d_k3(x, self.packed_weight(), scale, shift, relu='r' in self.order)
+
+    def packed_weight_tc_slices(self, width: int):
+        w = self.conv.weight
+        key = (w._version, w.data_ptr(), width)
+        cached = getattr(self, '_gnb_wt_tc_slices', None)
+        if cached is None or cached[0] != key:
+            cached = (key, [ops.conv3d_tc_pack_weights(w[o:o + width].contiguous()) for o in range(0, w.shape[0], width)])
+            self._gnb_wt_tc_slices = cached
+        return cached[1]
+
+    def forward_ndhwc_cat(self, skip: torch.Tensor, x_low: torch.Tensor) -> torch.Tensor:
+        """``forward_ndhwc(cat((skip, nearest_upsample_2x(x_low)), channel))`` -- the decoder's joining (ref
+        components/unet3d.py:291,325-330) -- without writing the concatenated tensor: the GroupNorm statistics and the
+        normalise-and-split pass read the two sources directly."""
+        B, D, H, W, Cs = skip.shape
+        Cx = x_low.shape[-1]
+        Cin, Cout = Cs + Cx, self.conv.out_channels
+        gn = self.groupnorm
+        ok = (self._fusable and self.conv.bias is None and USE_TENSOR_CORES and FUSE_UPSAMPLE_CONCAT and Cs % 4 == 0 and Cx % 4 == 0
+              and (Cin // gn.num_groups) % 4 == 0 and tuple(x_low.shape[1:4]) == (D // 2, H // 2, W // 2) and D % 2 == 0 and H % 2 == 0
+              and W % 2 == 0 and skip.is_contiguous() and x_low.is_contiguous() and ops.conv3d_tc_supported(B, D, H, W, Cin, Cout))
+        if not ok:
+            return self.forward_ndhwc(ops.upsample_concat(skip, x_low))
+        scale, shift = ops.groupnorm_stats_cat(skip, x_low, gn.num_groups, gn.eps, gn.weight, gn.bias)
+        xh, xl = ops.gn_apply_split_cat(skip, x_low, scale, shift)
+        if USE_STACKED_DX and ops.conv3d_tc_dx_supported(B, D, H, W, Cin, Cout):
+            return ops.conv3d_tc_dx(xh, xl, Cin, self.packed_weight_tc(dx=True), Cout, relu='r' in self.order)
+        return ops.conv3d_tc(xh, xl, Cin, self.packed_weight_tc(), Cout, relu='r' in self.order)
 
     def packed_weight_tc(self, dx: bool = False) -> torch.Tensor:
         w = self.conv.weight
@@ -226,8 +261,12 @@ class Decoder(nn.Module):
     def forward_ndhwc(self, encoder_features, x):
         if not self._concat or self.upsampling.mode != 'nearest':
             _unsupported("Decoder with transposed-conv / summation joining")
-        # nearest upsample to the skip's size + cat((encoder_features, x), channel) in one kernel
-        return self.basic_module.forward_ndhwc(ops.upsample_concat(encoder_features, x))
+        # nearest upsample to the skip's size + cat((encoder_features, x), channel): read in place by the first SingleConv's
+        # GroupNorm passes (forward_ndhwc_cat); one materialising kernel (gnb_upsample_concat) otherwise
+        bm = self.basic_module
+        if isinstance(bm, DoubleConv):
+            return bm.SingleConv2.forward_ndhwc(bm.SingleConv1.forward_ndhwc_cat(encoder_features, x))
+        return bm.forward_ndhwc(ops.upsample_concat(encoder_features, x))
 
     def forward(self, encoder_features, x):
         y = self.forward_ndhwc(ops.to_channels_last(encoder_features), ops.to_channels_last(x))

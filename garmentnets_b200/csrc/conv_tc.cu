@@ -511,6 +511,50 @@ gn_apply_split_vec4_kernel(const float* __restrict__ x, int64_t rows, int64_t vo
     xl[t] = l;
 }
 
+// The same pass on the VIRTUAL tensor cat(skip, nearest_upsample_2x(x_low)) (ref components/unet3d.py:291,325-330: the decoder's
+// joining): channel quads below Cs come from skip [B,D,H,W,Cs], the others from x_low [B,D/2,H/2,W/2,Cx] at the parent voxel.
+// The concatenated fp32 tensor is never written.
+__global__ void __launch_bounds__(256)
+gn_apply_split_cat_kernel(const float* __restrict__ skip, int Cs, const float* __restrict__ xlow, int Cx, int64_t rows, int D, int H,
+                          int W, int Cpad, const float* __restrict__ scale, const float* __restrict__ shift, uint2* __restrict__ xh,
+                          uint2* __restrict__ xl, uint32_t* __restrict__ range_flag) {
+    // 32-bit index arithmetic (the entry point checks rows * quads < 2^32): the 64-bit divisions of the first version cost
+    // more than the memory traffic
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per channel quad
+    const unsigned quads = (unsigned)Cpad / 4u;
+    const int C = Cs + Cx;
+    if ((int64_t)t >= rows * quads) return;
+    const unsigned r = t / quads;
+    const int c = (int)(t - r * quads) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+        const unsigned vox = (unsigned)D * H * W;
+        const unsigned b = r / vox;
+        if (c < Cs) {
+            v = __ldg(reinterpret_cast<const float4*>(skip + (int64_t)r * Cs + c));
+        } else {
+            const unsigned rv = r - b * vox, row = rv / (unsigned)W, x = rv - row * (unsigned)W, z = row / (unsigned)H, y = row - z * (unsigned)H;
+            const unsigned rl = ((b * (unsigned)(D / 2) + (z >> 1)) * (unsigned)(H / 2) + (y >> 1)) * (unsigned)(W / 2) + (x >> 1);
+            v = __ldg(reinterpret_cast<const float4*>(xlow + (int64_t)rl * Cx + (c - Cs)));
+        }
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + (int64_t)b * C + c));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + (int64_t)b * C + c));
+        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        if (!(fabsf(v.x) <= 65504.f) | !(fabsf(v.y) <= 65504.f) | !(fabsf(v.z) <= 65504.f) | !(fabsf(v.w) <= 65504.f)) *range_flag = 1u;
+        v.x = fminf(fmaxf(v.x, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y, -65504.f), 65504.f);
+        v.z = fminf(fmaxf(v.z, -65504.f), 65504.f); v.w = fminf(fmaxf(v.w, -65504.f), 65504.f);
+    }
+    uint2 h, l;
+    h.x = ct_cvt_f16x2_sat(v.x, v.y);
+    h.y = ct_cvt_f16x2_sat(v.z, v.w);
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+    l.x = ct_cvt_f16x2_sat(v.x - f0.x, v.y - f0.y);
+    l.y = ct_cvt_f16x2_sat(v.z - f1.x, v.w - f1.y);
+    xh[t] = h;
+    xl[t] = l;
+}
+
 // generic path (C % 4 != 0 or unaligned pointers): one thread per channel pair
 __global__ void __launch_bounds__(256)
 gn_apply_split_kernel(const float* __restrict__ x, int64_t rows, int64_t vox_per_sample, int C, int Cpad,
@@ -616,6 +660,24 @@ int32_t gnb_gn_apply_split(const float* x, int32_t B, int64_t voxels, int32_t C,
     gn_apply_split_kernel<<<(unsigned)ceil_div<int64_t>(rows * (Cpad / 2), 256), 256, 0, as_stream(stream)>>>(
         x, rows, voxels, C, Cpad, scale, shift, reinterpret_cast<__half*>(xh), reinterpret_cast<__half*>(xl), flag);
     return check_launch("gnb_gn_apply_split");
+}
+
+int32_t gnb_gn_apply_split_cat(const float* skip, int32_t Cs, const float* x_low, int32_t Cx, int32_t B, int32_t D, int32_t H,
+                               int32_t W, const float* scale, const float* shift, void* xh, void* xl, void* stream) {
+    GNB_REQUIRE(skip && x_low && scale && shift && xh && xl, "gnb_gn_apply_split_cat: null pointer");
+    GNB_REQUIRE(Cs % 4 == 0 && Cx % 4 == 0 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "gnb_gn_apply_split_cat: bad shape");
+    GNB_REQUIRE((int64_t)B * D * H * W * (ceil_div(Cs + Cx, CT_KC) * CT_KC / 4) < (1ll << 32), "gnb_gn_apply_split_cat: more than 2^32 channel quads");
+    GNB_REQUIRE(((reinterpret_cast<uintptr_t>(skip) | reinterpret_cast<uintptr_t>(x_low) | reinterpret_cast<uintptr_t>(xh) |
+                  reinterpret_cast<uintptr_t>(xl) | reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0,
+                "gnb_gn_apply_split_cat: pointers must be 16-byte aligned");
+    const int C = Cs + Cx, Cpad = ceil_div(C, CT_KC) * CT_KC;
+    const int64_t rows = (int64_t)B * D * H * W;
+    if (rows == 0) return GNB_OK;
+    uint32_t* flag = f16_flag_ptr();
+    GNB_REQUIRE(flag != nullptr, "gnb_gn_apply_split_cat: range flag allocation failed");
+    gn_apply_split_cat_kernel<<<(unsigned)ceil_div<int64_t>(rows * (Cpad / 4), 256), 256, 0, as_stream(stream)>>>(
+        skip, Cs, x_low, Cx, rows, D, H, W, Cpad, scale, shift, reinterpret_cast<uint2*>(xh), reinterpret_cast<uint2*>(xl), flag);
+    return check_launch("gnb_gn_apply_split_cat");
 }
 
 int32_t gnb_conv3d_tc_supported(int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout) {

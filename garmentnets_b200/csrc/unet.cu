@@ -47,7 +47,11 @@ gn_partial_kernel(const float* __restrict__ x, int64_t voxels, int C, int groups
 // float4 channel quad -- always inside one group -- and strides over the voxels of its CTA's slab with 16-byte
 // coalesced loads; double accumulators; one shared + one global double atomic per thread / per CTA and group.
 __global__ void __launch_bounds__(256)
-gn_partial_vec4_kernel(const float* __restrict__ x, int64_t voxels, int C, int groups, double* __restrict__ ws) {
+gn_partial_vec4_kernel(const float* __restrict__ x, int64_t voxels, int C, int groups, double* __restrict__ ws,
+                       int c_off = 0, int c_total = 0, double mult = 1.0) {
+    // c_off / c_total / mult: x is a channel slice [c_off, c_off + C) of a virtual tensor with c_total channels whose statistics
+    // are accumulated in ws (gnb_groupnorm_stats_cat); mult = 8 for a nearest-upsampled source (every value appears 8 times)
+    if (c_total == 0) c_total = C;
     extern __shared__ double sh[];  // [2*groups]
     const int b = blockIdx.y;
     const int quads = C >> 2;
@@ -79,9 +83,9 @@ gn_partial_vec4_kernel(const float* __restrict__ x, int64_t voxels, int C, int g
             s += (e0 + e1) + (e2 + e3);
             ss += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
         }
-        const int g = (q << 2) / (C / groups);
-        atomicAdd(&sh[2 * g], s);
-        atomicAdd(&sh[2 * g + 1], ss);
+        const int g = (c_off + (q << 2)) / (c_total / groups);
+        atomicAdd(&sh[2 * g], s * mult);
+        atomicAdd(&sh[2 * g + 1], ss * mult);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&ws[(int64_t)b * groups * 2 + i], sh[i]);
@@ -336,6 +340,29 @@ int32_t gnb_groupnorm_stats(const float* x, int32_t B, int64_t voxels, int32_t C
     else gn_partial_kernel<<<dim3(chunks, B), 256, 2 * groups * sizeof(double), st>>>(x, voxels, C, groups, ws);
     gn_finalize_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(ws, B, voxels, C, groups, eps, gamma, beta, scale, shift);
     return check_launch("gnb_groupnorm_stats");
+}
+
+int32_t gnb_groupnorm_stats_cat(const float* skip, int32_t Cs, const float* x_low, int32_t Cx, int32_t B, int64_t voxels,
+                                int32_t groups, float eps, const float* gamma, const float* beta, float* scale, float* shift,
+                                double* ws, void* stream) {
+    GNB_REQUIRE(skip && x_low && scale && shift && ws, "gnb_groupnorm_stats_cat: null pointer");
+    const int C = Cs + Cx;
+    GNB_REQUIRE(B > 0 && voxels > 0 && voxels % 8 == 0 && groups > 0 && C % groups == 0, "gnb_groupnorm_stats_cat: bad shape");
+    GNB_REQUIRE(Cs % 4 == 0 && Cx % 4 == 0 && (C / groups) % 4 == 0 && Cs / 4 <= 256 && Cx / 4 <= 256 &&
+                ((reinterpret_cast<uintptr_t>(skip) | reinterpret_cast<uintptr_t>(x_low)) & 15) == 0,
+                "gnb_groupnorm_stats_cat: channel counts must be multiples of 4 (groups of whole quads), 16-byte aligned sources");
+    cudaStream_t st = as_stream(stream);
+    GNB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)B * groups * 2, st));
+    const int target = ceil_div(8 * sm_count(), B);
+    auto chunks_for = [&](int64_t vox, int c) {
+        int ch = (int)ceil_div<int64_t>(vox * c, 256 * 64);
+        return ch < 1 ? 1 : (ch > target ? target : ch);
+    };
+    // the statistics of cat(skip, upsample(x_low)) are the sums over skip plus 8 x the sums over x_low
+    gn_partial_vec4_kernel<<<dim3(chunks_for(voxels, Cs), B), 256, 2 * groups * sizeof(double), st>>>(skip, voxels, Cs, groups, ws, 0, C, 1.0);
+    gn_partial_vec4_kernel<<<dim3(chunks_for(voxels / 8, Cx), B), 256, 2 * groups * sizeof(double), st>>>(x_low, voxels / 8, Cx, groups, ws, Cs, C, 8.0);
+    gn_finalize_kernel<<<ceil_div(B * C, 256), 256, 0, st>>>(ws, B, voxels, C, groups, eps, gamma, beta, scale, shift);
+    return check_launch("gnb_groupnorm_stats_cat");
 }
 
 int32_t gnb_conv3d_k3(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin, const float* scale,

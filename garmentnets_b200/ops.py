@@ -326,6 +326,31 @@ def groupnorm_stats(x: torch.Tensor, groups: int, eps: float, gamma, beta):
     return scale, shift
 
 
+def groupnorm_stats_cat(skip: torch.Tensor, x_low: torch.Tensor, groups: int, eps: float, gamma, beta):
+    """GroupNorm scale / shift of the virtual tensor cat((skip, nearest_upsample_2x(x_low)), channel) without materialising it."""
+    B, D, H, W, Cs = skip.shape
+    Cx = x_low.shape[-1]
+    C = Cs + Cx
+    scale = torch.empty((B, C), dtype=torch.float32, device=skip.device)
+    shift = torch.empty((B, C), dtype=torch.float32, device=skip.device)
+    ws = torch.empty((B * groups * 2,), dtype=torch.float64, device=skip.device)
+    _lib.call("gnb_groupnorm_stats_cat", skip.data_ptr(), Cs, x_low.data_ptr(), Cx, B, D * H * W, int(groups), float(eps),
+              _ptr(gamma), _ptr(beta), scale.data_ptr(), shift.data_ptr(), ws.data_ptr(), _stream())
+    return scale, shift
+
+
+def gn_apply_split_cat(skip: torch.Tensor, x_low: torch.Tensor, scale, shift):
+    """cat((skip, upsample(x_low))) * scale + shift as fp16 hi + lo [B,D,H,W,Cpad] (see gn_apply_split)."""
+    B, D, H, W, Cs = skip.shape
+    Cx = x_low.shape[-1]
+    cpad = (Cs + Cx + 63) // 64 * 64
+    xh = torch.empty((B, D, H, W, cpad), dtype=torch.float16, device=skip.device)
+    xl = torch.empty((B, D, H, W, cpad), dtype=torch.float16, device=skip.device)
+    _lib.call("gnb_gn_apply_split_cat", skip.data_ptr(), Cs, x_low.data_ptr(), Cx, B, D, H, W, scale.data_ptr(), shift.data_ptr(),
+              xh.data_ptr(), xl.data_ptr(), _stream())
+    return xh, xl
+
+
 def conv3d_k3(x: torch.Tensor, wt: torch.Tensor, scale=None, shift=None, relu: bool = True) -> torch.Tensor:
     """x [B,D,H,W,Cin] contiguous, wt [27,Cin,Cout] -> [B,D,H,W,Cout]."""
     B, D, H, W, Cin = x.shape

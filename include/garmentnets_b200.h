@@ -192,6 +192,15 @@ int32_t gnb_conv3d_tc_pack_weights(const float* W, int32_t Cout, int32_t Cin, in
                                    void* stream);
 int32_t gnb_gn_apply_split(const float* x, int32_t B, int64_t voxels, int32_t C, const float* scale, const float* shift,
                            void* xh, void* xl, void* stream);
+/* The two passes above on the VIRTUAL tensor cat((skip, nearest_upsample_2x(x_low)), channel) -- the decoder's joining
+ * (ref components/unet3d.py:291,325-330) -- without materialising it: skip f32[B,D,H,W,Cs], x_low f32[B,D/2,H/2,W/2,Cx];
+ * voxels = D*H*W; scale / shift f32[B, Cs+Cx]; Cs, Cx and the group width multiples of 4. */
+int32_t gnb_groupnorm_stats_cat(const float* skip, int32_t Cs, const float* x_low, int32_t Cx, int32_t B, int64_t voxels,
+                                int32_t groups, float eps, const float* gamma, const float* beta, float* scale,
+                                float* shift, double* ws, void* stream);
+int32_t gnb_gn_apply_split_cat(const float* skip, int32_t Cs, const float* x_low, int32_t Cx, int32_t B, int32_t D,
+                               int32_t H, int32_t W, const float* scale, const float* shift, void* xh, void* xl,
+                               void* stream);
 int32_t gnb_conv3d_tc(const void* xh, const void* xl, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin,
                       const void* w_packed, int32_t scale_log2, int32_t Cout, int32_t relu, float* y, void* stream);
 
