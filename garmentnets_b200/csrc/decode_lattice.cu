@@ -587,7 +587,7 @@ decode_lattice_kernel(const Params p) {
             // barriers the peer CTA arrives on need a cluster-scope acquire
             auto wait_x = [&](uint32_t bar, uint32_t parity) {
                 if (PAIR) mbar_wait_cluster(bar, parity);
-                else mbar_wait(bar, parity);   // latency-critical: the suspend-hint form was measured slower here (18.9 vs 17.1 ms)
+                else mbar_wait(bar, parity);   // latency-critical: plain polling (the suspend-hint form brought nothing measurable)
             };
             auto wait_b = [&](uint32_t pc) {   // W2 piece pc (this CTA's part and, in a pair, the peer's)
                 DL2_PROF(1, mbar_wait(b_full(pc % BS), (pc / BS) & 1); if (PAIR) mbar_wait_cluster(b_peer(pc % BS), (pc / BS) & 1));
