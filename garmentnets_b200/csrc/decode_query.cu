@@ -28,6 +28,7 @@
 // per column).  Shared memory: A1 2 x 16 KB, W1 32 KB, W2 ring 5 x 32 KB.
 // Precision as in decode_tc.cu / decode_lattice.cu: fp16 hi + lo operands, hi*hi + lo*hi + hi*lo, fp32 accumulation.
 #include "tc_common.cuh"
+#include <type_traits>
 
 namespace gnb {
 namespace dq {
@@ -37,7 +38,8 @@ constexpr int A1_BYTES = M * 128;            // 16 KB
 constexpr int W1_BYTES = N * 128;            // 32 KB
 constexpr int B_PIECE = N * KC * 2;          // 32 KB: the 256 W2 rows, one K-chunk, one precision part
 constexpr int B_SLOTS = 5;
-constexpr int THREADS = 448;
+constexpr int THREADS = 576;                 // 4 gather + 4 mid-epilogue + 8 epilogue warps + MMA issuer + loader
+constexpr int W_MMA = 16, W_LOAD = 17;
 constexpr int MAX_B = 128;
 constexpr uint32_t IDESC_N64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 constexpr uint32_t IDESC_N256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -87,6 +89,7 @@ struct Params {
     float acc_scale;           // 2^-s2
     const float* tail;         // [COUT][4] = {c0, bn3_scale, bn3_shift, 0}
     float* out;                // [R, COUT]
+    float* epi_scratch;        // [grid][128][4] partial dot products handed between the two epilogue warps of a lane quarter
 };
 
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
@@ -114,7 +117,7 @@ __device__ __forceinline__ void split2(float2 h, uint32_t& hi, uint32_t& lo) {
 }
 
 template <int COUT>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(640, 1)   // 18 warps: 5 on two of the four sub-partitions -> 96 registers per thread
 decode_query_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -140,7 +143,7 @@ decode_query_kernel(const Params p) {
             mbar_init(acc1_full(s), 1); mbar_init(acc1_empty(s), 4);
             mbar_init(a2_full(s), 4); mbar_init(a2_empty(s), 1);
         }
-        mbar_init(d_full, 1); mbar_init(d_empty(0), 4); mbar_init(d_empty(1), 4); mbar_init(w1_full, 1);
+        mbar_init(d_full, 1); mbar_init(d_empty(0), 8); mbar_init(d_empty(1), 8); mbar_init(w1_full, 1);
         for (int s = 0; s < B_SLOTS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -148,7 +151,7 @@ decode_query_kernel(const Params p) {
         int64_t* qp = reinterpret_cast<int64_t*>(smem + Smem::qptr);
         for (int i = threadIdx.x; i <= p.B; i += THREADS) qp[i] = p.qptr[i];
     }
-    if (warp == 12) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Smem::tmem_ptr), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -242,25 +245,26 @@ decode_query_kernel(const Params p) {
                 DQ_PROF(0, mbar_wait(acc1_full(s), (q1 >> 1) & 1u));
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + ACC1_COL + s * 64u;
-                uint32_t r0[32], r1[32];
-                tmem_ld32(taddr, r0);
-                tmem_ld32(taddr + 32, r1);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc1_empty(s));   // the tensor core may overwrite this acc1 buffer (chunk c + 2)
                 DQ_PROF(1, mbar_wait(a2_empty(s), ((q1 >> 1) & 1u) ^ 1u));   // A2 slots and acc1 buffers advance together (slot = q1 & 1)
-                // this row's 64 channels as 32 + 32 packed half pairs: exactly the A-operand columns of the tensor memory
+                // this row's 64 channels as 32 + 32 packed half pairs: exactly the A-operand columns of the tensor memory;
+                // 32 accumulator columns at a time (96 registers per thread)
                 const uint32_t a2addr = tmem_base + ((uint32_t)(qd * 32) << 16) + A2_COL + s * 64u;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {   // 32 accumulator columns -> 16 + 16 packed words
+                    uint32_t r[32];
+                    tmem_ld32(taddr + half * 32, r);
+                    tmem_ld_wait();
+                    if (half == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc1_empty(s));   // the tensor core may overwrite this acc1 buffer (chunk c + 2)
+                    }
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const uint32_t x0 = half ? r1[2 * j] : r0[2 * j], x1 = half ? r1[2 * j + 1] : r0[2 * j + 1];
                         const int col = half * 32 + 2 * j;
-                        const float2 h = make_float2(fmaf(__uint_as_float(x0), inv1, c_epi[c * KC + col]),
-                                                     fmaf(__uint_as_float(x1), inv1, c_epi[c * KC + col + 1]));
+                        const float2 h = make_float2(fmaf(__uint_as_float(r[2 * j]), inv1, c_epi[c * KC + col]),
+                                                     fmaf(__uint_as_float(r[2 * j + 1]), inv1, c_epi[c * KC + col + 1]));
                         // rounded (not truncated) hi part: this warp group has issue slots to spare, and the 22nd bit of H1 is
                         // visible in the float64-yardstick test of the warp field (tests/test_pipeline.py)
                         relu_split_f16x2(h.x, h.y, hi[j], lo[j]);
@@ -275,10 +279,13 @@ decode_query_kernel(const Params p) {
             }
         }
         if (threadIdx.x == 128) { DQ_PROF_STORE(0, 8); DQ_PROF_STORE(1, 9); DQ_PROF_TOTAL(10); }
-    } else if (warp < 12) {
+    } else if (warp < 16) {
         // =========================== epilogue: acc2 -> y ===========================
-        const int qd = warp & 3;
+        // two warps per TMEM lane quarter: eh = 0 folds accumulator columns [0, 128) and finishes the row, eh = 1 folds [128, 256)
+        // and hands its partial dot products over through a per-CTA scratch row in global memory (L2) and a named barrier
+        const int qd = warp & 3, eh = (warp - 8) >> 2;
         const int row = qd * 32 + lane;
+        float* part = p.epi_scratch + ((size_t)blockIdx.x * M + row) * 4;
         float c_tail[COUT], bn3s[COUT], bn3h[COUT];
 #pragma unroll
         for (int o = 0; o < COUT; ++o) { c_tail[o] = p.tail[o * 4]; bn3s[o] = p.tail[o * 4 + 1]; bn3h[o] = p.tail[o * 4 + 2]; }
@@ -297,44 +304,62 @@ decode_query_kernel(const Params p) {
             for (int o = 0; o < COUT; ++o)
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) dsum[o][q4] = 0.f;
-            tmem_ld32(taddr, r0);
+            // (the two column halves are written out: the constant-bank operands need compile-time offsets)
+            auto fold = [&](auto EH) {
+                constexpr int C0 = decltype(EH)::value * 128;
+                tmem_ld32(taddr + C0, r0);
 #pragma unroll
-            for (int n0 = 0; n0 < N; n0 += 64) {
-                tmem_ld_wait();
-                tmem_ld32(taddr + n0 + 32, r1);
+                for (int n0 = C0; n0 < C0 + 128; n0 += 64) {
+                    tmem_ld_wait();
+                    tmem_ld32(taddr + n0 + 32, r1);
 #pragma unroll
-                for (int u = 0; u < 32; ++u) {
-                    const float v = fmaxf(fmaf(__uint_as_float(r0[u]), as, c_epi[256 + n0 + u]), 0.f);
+                    for (int u = 0; u < 32; ++u) {
+                        const float v = fmaxf(fmaf(__uint_as_float(r0[u]), as, c_epi[256 + n0 + u]), 0.f);
 #pragma unroll
-                    for (int o = 0; o < COUT; ++o) dsum[o][u & 3] = fmaf(v, c_epi[(2 + o) * 256 + n0 + u], dsum[o][u & 3]);
+                        for (int o = 0; o < COUT; ++o) dsum[o][u & 3] = fmaf(v, c_epi[(2 + o) * 256 + n0 + u], dsum[o][u & 3]);
+                    }
+                    tmem_ld_wait();
+                    if (n0 + 64 < C0 + 128) {
+                        tmem_ld32(taddr + n0 + 64, r0);
+                    } else {
+                        // every TMEM read of this warp's part of acc2 has completed (the next tile's Linear2 may overwrite acc2
+                        // once all eight epilogue warps have said so)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(d_empty(0));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) {
+                        const float v = fmaxf(fmaf(__uint_as_float(r1[u]), as, c_epi[256 + n0 + 32 + u]), 0.f);
+#pragma unroll
+                        for (int o = 0; o < COUT; ++o) dsum[o][u & 3] = fmaf(v, c_epi[(2 + o) * 256 + n0 + 32 + u], dsum[o][u & 3]);
+                    }
                 }
-                tmem_ld_wait();
-                if (n0 + 64 < N) {
-                    tmem_ld32(taddr + n0 + 64, r0);
-                } else {
-                    // every TMEM read of acc2 has completed: the next tile's Linear2 may overwrite it
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(d_empty(0));
-                }
+            };
+            if (eh == 0) fold(std::integral_constant<int, 0>{}); else fold(std::integral_constant<int, 1>{});
+            float dot[COUT];
 #pragma unroll
-                for (int u = 0; u < 32; ++u) {
-                    const float v = fmaxf(fmaf(__uint_as_float(r1[u]), as, c_epi[256 + n0 + 32 + u]), 0.f);
+            for (int o = 0; o < COUT; ++o) dot[o] = (dsum[o][0] + dsum[o][1]) + (dsum[o][2] + dsum[o][3]);
+            if (eh == 1) {
 #pragma unroll
-                    for (int o = 0; o < COUT; ++o) dsum[o][u & 3] = fmaf(v, c_epi[(2 + o) * 256 + n0 + 32 + u], dsum[o][u & 3]);
+                for (int o = 0; o < COUT; ++o) part[o] = dot[o];
+                __threadfence_block();
+            }
+            // the two warps of this lane quarter meet: partials written above are visible to the partner afterwards
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+            if (eh == 0) {
+                const int64_t grow = tile * M + row;
+                if (grow < p.R) {
+#pragma unroll
+                    for (int o = 0; o < COUT; ++o)
+                        p.out[grow * COUT + o] = fmaxf((dot[o] + __ldcg(part + o)) + c_tail[o], 0.f) * bn3s[o] + bn3h[o];
                 }
             }
-            const int64_t grow = tile * M + row;
-            if (grow < p.R) {
-#pragma unroll
-                for (int o = 0; o < COUT; ++o) {
-                    const float dot = (dsum[o][0] + dsum[o][1]) + (dsum[o][2] + dsum[o][3]);
-                    p.out[grow * COUT + o] = fmaxf(dot + c_tail[o], 0.f) * bn3s[o] + bn3h[o];
-                }
-            }
+            // second meeting: the partner has read this tile's partials before the next tile's are written
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
         }
         if (threadIdx.x == 256) { DQ_PROF_STORE(0, 11); DQ_PROF_TOTAL(12); }
-    } else if (warp == 12) {
+    } else if (warp == W_MMA) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             mbar_wait(w1_full, 0);
@@ -427,7 +452,7 @@ decode_query_kernel(const Params p) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) {
+    if (warp == W_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
@@ -497,6 +522,7 @@ int32_t launch_decode_query(const float* X, int B, int G, const float* W1, const
     p.w2_packed = reinterpret_cast<const uint8_t*>(w2_packed);
     p.acc_scale = ldexpf(1.0f, -w2_scale_log2);
     p.tail = tail; p.out = out;
+    p.epi_scratch = scratch + 16384;   // 148 x 128 x 4 floats
     if (Cout == 1) return dq::launch<1>(p, st);
     if (Cout == 2) return dq::launch<2>(p, st);
     return dq::launch<3>(p, st);

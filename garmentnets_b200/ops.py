@@ -576,7 +576,7 @@ def decode_tc_query_fused(W1, b1, w2_packed, b2, bn2, W3, b3, bn3, *, X, q, qptr
         out = torch.empty((R, Cout), dtype=torch.float32, device=dev)
     s2, h2 = bn2 if bn2 is not None else (None, None)
     s3, h3 = bn3 if bn3 is not None else (None, None)
-    scratch = torch.empty(16384, dtype=torch.float32, device=dev)
+    scratch = torch.empty(16384 + 256 * 512, dtype=torch.float32, device=dev)
     s1, h1 = bn1 if bn1 is not None else (None, None)   # None: BatchNorm1 already folded into w2_packed / b2
     _lib.call("gnb_decode_tc_query_fused", X.data_ptr(), B, G, C0, W1.data_ptr(), b1.data_ptr(), q.data_ptr(), qptr.data_ptr(),
               R, _ptr(s1), _ptr(h1), w2_packed.data_ptr(), w2_s, b2.data_ptr(), _ptr(s2), _ptr(h2),

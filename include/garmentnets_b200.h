@@ -295,7 +295,8 @@ int32_t gnb_decode_tc_query(const float* U, int32_t B, int32_t G, const float* q
  * b2' = b2 + W2 shift -- the fast path: BOTH contractions then run on tcgen05 (decode_query.cu: Linear1 as six N = 64 MMAs per
  * 64-channel chunk into a TMEM double buffer, a mid-epilogue warp group turns each chunk into the fp16 hi/lo operand of
  * Linear2 in shared memory).  With BatchNorm1 given, Linear1 is applied per query with FFMA2 in the producer warps.
- * scratch: f32[16384] (tail constants, the power-of-two scale of W1 and its 32 KB fp16 shared-memory image). */
+ * scratch: f32[16384 + 512 * SMs] (tail constants, the power-of-two scale of W1 and its 32 KB fp16 shared-memory image, one
+ * 128 x 4 row of partial dot products per CTA); 16384 + 131072 floats cover up to 256 SMs. */
 int32_t gnb_decode_tc_query_fused(const float* X, int32_t B, int32_t G, int32_t C0, const float* W1, const float* b1,
                                   const float* q, const int64_t* qptr, int64_t R, const float* bn1_scale,
                                   const float* bn1_shift, const void* w2_packed, int32_t w2_scale_log2,
