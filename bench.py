@@ -355,6 +355,9 @@ def run_ours(args, rank, world):
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU: keep this rank's threads and its pinned staging buffers on the GPU's NUMA node
+    from garmentnets_b200 import dist as gnb_dist
+    numa_node = gnb_dist.bind_to_gpu_numa_node(local_rank)
     _lib.load()
     B = args.batch
     hp = synthetic.HPARAMS
@@ -510,7 +513,8 @@ def run_ours(args, rank, world):
             "config": dict(_workload_config(B, world, V, F),
                            launch=("eager launches" if not args.cuda_graph else
                                    "static front part (PointNet++ .. ggm) replayed from a CUDA graph, tail after the "
-                                   "marching-cubes host synchronisation launched eagerly")),
+                                   "marching-cubes host synchronisation launched eagerly"),
+                           numa_node=numa_node),   # rank 0's binding (None: platform does not report one)
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps,

@@ -56,11 +56,16 @@ static_assert(Smem::total + 1024 <= 227 * 1024, "shared memory budget");
 // Filled per launch by a stream-ordered device-to-device copy from the prep kernel's scratch (one stream at a time).
 __constant__ float c_epi[4 * 256];
 
+// (make PROFILE_KNOBS=1 PROFILE_NO_CLOCKS=1 keeps the knock-out switches but leaves the clock reads out: they slow the producers
+// down by ~60 %, which makes every knock-out look producer-bound)
+#if defined(GNB_PROFILE_KNOBS) && !defined(GNB_PROFILE_NO_CLOCKS)
+#define GNB_PROFILE_CLOCKS
+#endif
 // Per-role wait-time attribution (profiling builds only, tools/decode_bench.py): cycles one thread of each role spends in
 // its barrier waits.  [cta][16]: 0 MMA a_full | 1 MMA W2 | 2 MMA d_empty | 3 MMA total | 4 producer a_empty | 5 producer total |
 // 6 producer row/store phase | 7 epilogue d_full | 8 epilogue total | 9 loader b_empty | 10 loader total |
 // 11 producer x-blend (waits for the prefetched gathers) | 12 producer prefetch issue | 13 producer y-blend | 14 producer fence + arrive
-#ifdef GNB_PROFILE_KNOBS
+#ifdef GNB_PROFILE_CLOCKS
 __device__ unsigned long long g_prof[1024 * 16];
 #define DL2_PROF_DECL unsigned long long prof_acc[6] = {0, 0, 0, 0, 0, 0}; const long long prof_t0 = clock64()
 #define DL2_PROF(i, stmt) do { const long long t_ = clock64(); stmt; prof_acc[i] += (unsigned long long)(clock64() - t_); } while (0)
@@ -357,7 +362,7 @@ decode_lattice_kernel(const Params p) {
             for (int c = 0; c < NCHUNK; ++c, ++q) {
                 const int slot = q & 1;
                 if (active && !(p.dbg & 1)) {
-#ifdef GNB_PROFILE_KNOBS
+#ifdef GNB_PROFILE_CLOCKS
                     const long long t_a = clock64();
 #endif
                     // 1. x-blend of the prefetched corners: X[s][y] (4 channels as two packed pairs)
@@ -369,7 +374,7 @@ decode_lattice_kernel(const Params p) {
                         for (int yy = 0; yy < 2; ++yy)
 #pragma unroll
                             for (int h2 = 0; h2 < NH; ++h2) X[s][yy][h2] = fma2(nxt[s][yy][1][h2], vx1, mul2(nxt[s][yy][0][h2], vx0));
-#ifdef GNB_PROFILE_KNOBS
+#ifdef GNB_PROFILE_CLOCKS
                     // the clock read must follow the blend: make it depend on one blended value
                     long long t_b;
                     asm volatile("{ .reg .f32 t; mov.f32 t, %1; mov.u64 %0, %%clock64; }" : "=l"(t_b) : "f"(X[2][1][NH - 1].y) : "memory");
@@ -382,7 +387,7 @@ decode_lattice_kernel(const Params p) {
                         corners(ni.b, ni.i, ni.j0, cA);
                         issue(cA, 0, nxt);
                     }
-#ifdef GNB_PROFILE_KNOBS
+#ifdef GNB_PROFILE_CLOCKS
                     const long long t_c = clock64();
                     prof_acc[3] += (unsigned long long)(t_c - t_b);
 #endif
@@ -413,14 +418,14 @@ decode_lattice_kernel(const Params p) {
                             }
                         }
                     }
-#ifdef GNB_PROFILE_KNOBS
+#ifdef GNB_PROFILE_CLOCKS
                     long long t_d;
                     asm volatile("{ .reg .f32 t; mov.f32 t, %1; mov.u64 %0, %%clock64; }" : "=l"(t_d) : "f"(P[1][2][NH - 1].y) : "memory");
                     prof_acc[4] += (unsigned long long)(t_d - t_c);
 #endif
                     // 4. the slot must have been consumed by the tensor core (chunk q - 2)
                     DL2_PROF(0, mbar_wait(a_empty(slot), ((q >> 1) & 1) ^ 1));
-#ifdef GNB_PROFILE_KNOBS
+#ifdef GNB_PROFILE_CLOCKS
                     const long long t_rows = clock64();
 #endif
                     const uint32_t a_addr = sbase + Smem::a + slot * SLOT_BYTES + sub8;  // + part * PART_BYTES + row offset
@@ -475,7 +480,7 @@ decode_lattice_kernel(const Params p) {
                             row_store(k, v0);
                         }
                     }
-#ifdef GNB_PROFILE_KNOBS
+#ifdef GNB_PROFILE_CLOCKS
                     prof_acc[1] += (unsigned long long)(clock64() - t_rows);
 #endif
                 } else {
@@ -483,13 +488,13 @@ decode_lattice_kernel(const Params p) {
                     // counted into the current phase of a_full
                     mbar_wait(a_empty(slot), ((q >> 1) & 1) ^ 1);
                 }
-#ifdef GNB_PROFILE_KNOBS
+#ifdef GNB_PROFILE_CLOCKS
                 const long long t_e = clock64();
 #endif
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) arrive_leader(a_full(slot));
-#ifdef GNB_PROFILE_KNOBS
+#ifdef GNB_PROFILE_CLOCKS
                 prof_acc[5] += (unsigned long long)(clock64() - t_e);
 #endif
             }
@@ -803,7 +808,7 @@ int32_t gnb_decode_lattice(const float* U, int32_t B, int32_t G, int32_t Q, cons
     return dl2::launch<3>(p, st);
 }
 
-#ifdef GNB_PROFILE_KNOBS
+#ifdef GNB_PROFILE_CLOCKS
 // profiling builds only (not in the header): copy the per-CTA wait-time table of the last launch to the host
 __attribute__((visibility("default"))) int32_t gnb_prof_decode_lattice_read(unsigned long long* host_out, int32_t n) {
     return cudaMemcpyFromSymbol(host_out, dl2::g_prof, sizeof(unsigned long long) * (size_t)n) == cudaSuccess ? 0 : -1;

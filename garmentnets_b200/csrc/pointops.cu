@@ -37,12 +37,27 @@ __device__ __forceinline__ unsigned long long warp_argmax_key(unsigned long long
     return ((unsigned long long)mhi << 32) | mlo;
 }
 
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
+}
+__device__ __forceinline__ unsigned long long sub_f32x2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 template <int T, int PPT>
 __global__ void __launch_bounds__(T, 1)
 fps_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, const int64_t* __restrict__ start,
            const int64_t* __restrict__ out_ptr, int64_t* __restrict__ out, int stride) {
     extern __shared__ float sm[];
     __shared__ unsigned long long wbest[2][32];
+    constexpr int NW = T / 32;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t p0 = ptr[b];
     const int n = (int)(ptr[b + 1] - p0);
@@ -79,22 +94,46 @@ fps_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, const
             pd[j] = ok ? CUDART_INF_F : -1.f;  // -1 never wins (real distances are >= 0)
         }
     }
-    constexpr int NW = T / 32;
+    // the thread's points as register PAIRS for the packed fp32x2 arithmetic of the loop below
+    constexpr int H = PPT > 0 ? (PPT + 1) / 2 : 1;
+    unsigned long long qx[H], qy[H], qz[H];
+    if (PPT > 0) {
+#pragma unroll
+        for (int j = 0; j + 1 < PPT; j += 2) {
+            qx[j >> 1] = pack_f32x2(px[j], px[j + 1]);
+            qy[j >> 1] = pack_f32x2(py[j], py[j + 1]);
+            qz[j >> 1] = pack_f32x2(pz[j], pz[j + 1]);
+        }
+    }
     for (int s = 1; s < m; ++s) {
         const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
         unsigned long long best = 0ull;
         if (PPT > 0) {
+            // the running (distance, slot) pair stays in two 32-bit registers; the 64-bit key is built once per iteration.
+            // Strict > with ascending j keeps the smallest index among equal distances, as the key order does.
+            float bd = -1.f;   // -1 never wins (real distances are >= 0; padding slots hold -1)
+            int bj = 0;
+            // two points per packed fp32x2 instruction (sub / mul / add, each individually rounded: the same bits as
+            // sqdist_nofma); the loop is bound by instruction issue on the one SM a cloud occupies
+            const unsigned long long c2x = pack_f32x2(cx, cx), c2y = pack_f32x2(cy, cy), c2z = pack_f32x2(cz, cz);
 #pragma unroll
-            for (int j = 0; j < PPT; ++j) {
-                float d = sqdist_nofma(px[j], py[j], pz[j], cx, cy, cz);
-                float dm = fminf(pd[j], d);
-                pd[j] = dm;
-                if (dm >= 0.f) {
-                    unsigned long long key = ((unsigned long long)__float_as_uint(dm) << 32) |
-                                             (unsigned long long)(0xFFFFFFFFu - (unsigned)(tid + j * T));
-                    best = key > best ? key : best;
-                }
+            for (int j = 0; j < PPT; j += 2) {
+                const unsigned long long dx = sub_f32x2(qx[j >> 1], c2x), dy = sub_f32x2(qy[j >> 1], c2y), dz = sub_f32x2(qz[j >> 1], c2z);
+                // the sums stay scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (CUDA 12.9, also with
+                // -fmad=false), which would round differently from the oracle
+                const unsigned long long xx = mul_f32x2(dx, dx), yy = mul_f32x2(dy, dy), zz = mul_f32x2(dz, dz);
+                const float d0 = __fadd_rn(__fadd_rn(__uint_as_float((unsigned)xx), __uint_as_float((unsigned)yy)), __uint_as_float((unsigned)zz));
+                const float d1 = __fadd_rn(__fadd_rn(__uint_as_float((unsigned)(xx >> 32)), __uint_as_float((unsigned)(yy >> 32))),
+                                           __uint_as_float((unsigned)(zz >> 32)));
+                const float dm0 = fminf(pd[j], d0);
+                const float dm1 = fminf(pd[j + 1], d1);
+                pd[j] = dm0;
+                pd[j + 1] = dm1;
+                if (dm0 > bd) { bd = dm0; bj = j; }
+                if (dm1 > bd) { bd = dm1; bj = j + 1; }
             }
+            if (bd >= 0.f)
+                best = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(tid + bj * T));
         } else {
             for (int i = tid; i < n; i += T) {
                 float d = sqdist_nofma(sx[i], sy[i], sz[i], cx, cy, cz);
@@ -106,6 +145,8 @@ fps_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, const
             }
         }
         best = warp_argmax_key(best);
+        // (measured alternatives for this second level, profiles/fps_variants_r02.txt: one shared 64-bit atomicMax per warp --
+        // a CAS loop in SASS -- 1144 us, every thread folding the per-warp keys itself 1344 us, against 854 us for this)
         if (lane == 0) wbest[s & 1][warp] = best;
         __syncthreads();
         unsigned long long k2 = lane < NW ? wbest[s & 1][lane] : 0ull;
@@ -406,10 +447,17 @@ int32_t gnb_fps(const float* pos, const int64_t* ptr, int32_t B, const int64_t* 
     if (B == 0 || max_n_host == 0) return GNB_OK;
     cudaStream_t st = as_stream(stream);
     const int stride = (max_n_host + 31) & ~31;
-    if (max_n_host <= 512 * 8) {
+    // threads x points-per-thread: the loop is a latency chain (centre load -> distances -> two-level reduction -> barrier) with a
+    // fixed part of ~200 ns per selected point, so few warps with many register-resident points each win: measured for 32
+    // clouds 4096 -> 2048: 512x8 854 us, 256x16 797 us, 128x32 785 us; 2048 -> 512: 512x8 (half padding) 226 us, 256x8 / 128x16 151 us
+    if (max_n_host <= 256 * 8) {
         const size_t smem = (size_t)3 * stride * sizeof(float);
-        GNB_CUDA(cudaFuncSetAttribute(fps_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fps_kernel<512, 8><<<B, 512, smem, st>>>(pos, ptr, start, out_ptr, out, stride);
+        GNB_CUDA(cudaFuncSetAttribute(fps_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fps_kernel<256, 8><<<B, 256, smem, st>>>(pos, ptr, start, out_ptr, out, stride);
+    } else if (max_n_host <= 128 * 32) {
+        const size_t smem = (size_t)3 * stride * sizeof(float);
+        GNB_CUDA(cudaFuncSetAttribute(fps_kernel<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fps_kernel<128, 32><<<B, 128, smem, st>>>(pos, ptr, start, out_ptr, out, stride);
     } else if (max_n_host <= 1024 * 8) {
         const size_t smem = (size_t)3 * stride * sizeof(float);
         GNB_CUDA(cudaFuncSetAttribute(fps_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

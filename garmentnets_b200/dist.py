@@ -6,7 +6,8 @@ all-gather of the variable-length meshes.  Works with NCCL (GPU tensors) and glo
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence, Tuple
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -19,6 +20,50 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     base, rem = divmod(int(total), int(world))
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _parse_cpulist(text: str) -> List[int]:
+    """'0-3,8,10-11' -> [0, 1, 2, 3, 8, 10, 11] (the format of /sys/devices/system/node/nodeN/cpulist)."""
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int, sysfs: str = "/sys") -> Optional[int]:
+    """Restrict this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned staging buffer is
+    allocated (first touch then places the pinned pages on that node, so the device -> host mesh transfers of a rank
+    do not cross the socket interconnect).  One process per GPU: with eight ranks on a two-socket host an unbound rank
+    has an even chance of staging through the far socket.  Returns the node, or None when the platform does not say
+    (no sysfs entry, node -1, an affinity mask that excludes the node): the process is then left as it is."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = props.pci_bus_id
+        if not isinstance(bus, str):   # torch reports domain / bus / device as integers
+            bus = f"{int(props.pci_domain_id):04x}:{int(bus):02x}:{int(props.pci_device_id):02x}.0"
+    except Exception:
+        return None
+    return _bind_to_numa_node_of(bus.lower(), sysfs)
+
+
+def _bind_to_numa_node_of(pci_bus_id: str, sysfs: str = "/sys") -> Optional[int]:
+    try:
+        with open(os.path.join(sysfs, "bus/pci/devices", pci_bus_id, "numa_node")) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(os.path.join(sysfs, "devices/system/node", f"node{node}", "cpulist")) as f:
+            cpus = set(_parse_cpulist(f.read()))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
 
 
 def _device():

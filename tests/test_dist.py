@@ -80,3 +80,29 @@ def test_gloo_world2_gather():
     assert abs(s0["volumes_per_s"] - 7 / 0.02) < 1e-9  # units of all ranks / max time over ranks
     assert ok0 and ok1 and sh0 == sh1
     assert sh0 == [[(5, 3, 4, 3), (6, 3, 6, 3)], [(8, 3, 5, 3), (9, 3, 7, 3)]]
+
+
+def test_numa_binding_reads_sysfs(tmp_path):
+    """bind_to_gpu_numa_node's sysfs walk on a fake tree: the process ends up on the node's CPUs that it was allowed to use;
+    a node of -1 (single-socket hosts, VMs) or a missing entry leaves the affinity alone."""
+    import os
+    from garmentnets_b200 import dist as gd
+
+    assert gd._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    before = os.sched_getaffinity(0)
+    some = sorted(before)[: max(1, len(before) // 2)]
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    (node / "cpulist").write_text(",".join(str(c) for c in some) + "\n")
+    try:
+        assert gd._bind_to_numa_node_of("0000:1b:00.0", str(tmp_path)) == 1
+        assert os.sched_getaffinity(0) == set(some)
+    finally:
+        os.sched_setaffinity(0, before)
+    (dev / "numa_node").write_text("-1\n")
+    assert gd._bind_to_numa_node_of("0000:1b:00.0", str(tmp_path)) is None
+    assert gd._bind_to_numa_node_of("0000:ff:00.0", str(tmp_path)) is None
+    assert os.sched_getaffinity(0) == before

@@ -52,13 +52,16 @@ timeit("decode_lattice (one CTA / SM, 8 producer warps, default)", lambda: ops.d
 # ---- profiling build only (GNB_B200_LIBRARY=garmentnets_b200/lib/libgarmentnets_b200_prof.so): knock-outs and per-role
 # wait-time attribution of both kernel forms
 lib = _lib.load()
-if hasattr(lib, "gnb_prof_decode_lattice_read"):
+has_clocks = hasattr(lib, "gnb_prof_decode_lattice_read")   # absent in PROFILE_NO_CLOCKS=1 builds (knock-outs only)
+if os.environ.get("GNB_B200_LIBRARY"):
     import ctypes
     import numpy as np
     names = ["mma:a_full", "mma:w2", "mma:d_empty", "mma:total", "prod:a_empty", "prod:total", "prod:rows", "epi:d_full",
              "epi:total", "load:b_empty", "load:total", "prod:xblend", "prod:issue", "prod:yblend", "prod:fence"]
 
     def prof(label):
+        if not has_clocks:
+            return
         buf = np.zeros(1024 * 16, np.uint64)
         lib.gnb_prof_decode_lattice_read(ctypes.c_void_p(buf.ctypes.data), ctypes.c_int32(buf.size))
         t = buf.reshape(1024, 16)[:148].astype(np.float64)
@@ -67,9 +70,9 @@ if hasattr(lib, "gnb_prof_decode_lattice_read"):
         print(f"   [{label}] Mcycles/CTA even: {fmt(lead)}")
         print(f"   [{label}] Mcycles/CTA odd : {fmt(peer)}")
 
-    for mode, mname in ((0, "8 warps"), (2, "16 warps")):
+    for mode, mname in ((0, "8 warps"),):
         _lib.call("gnb_decode_lattice_set_mode", mode)
-        for dbg in (0,):
+        for dbg in (0, 4, 8, 16, 24, 28):
             os.environ["GNB_DL2_DBG"] = str(dbg)
             timeit(f"{mname} dbg={dbg}", lambda: ops.decode_lattice(*dec._lattice_args(), U=u, Q=128), n=3)
             prof(f"{mname} dbg={dbg}")
