@@ -92,9 +92,51 @@ f16_range_check_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restr
     if (bad) *flag = 1u;
 }
 
+// ---- small device -> host transfers without the copy engine ----------------------------------------------------------------
+// A few hundred bytes the host is WAITING for (marching-cubes totals, the range flag) must not queue behind the bulk
+// device -> host transfers of the previous batch on the copy engine (HostPredictor: 316 MB per batch; with eight ranks sharing
+// one host those transfers occupy the engine for most of a step, and a cudaMemcpy of 2 KB waited milliseconds behind them).
+// Pinned host memory is device-addressable under unified addressing: a kernel stores the words straight into it.
+__global__ void __launch_bounds__(256)
+copy_words_to_host_kernel(const uint32_t* __restrict__ src, int64_t src_pitch_words, uint32_t* __restrict__ host_dst,
+                          int64_t dst_pitch_words, int width_words, int64_t rows) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * width_words) return;
+    const int64_t r = t / width_words;
+    const int c = (int)(t - r * width_words);
+    host_dst[r * dst_pitch_words + c] = src[r * src_pitch_words + c];
+    __threadfence_system();
+}
+
+__global__ void f16_flag_to_host_kernel(uint32_t* __restrict__ flag, uint32_t* __restrict__ host_dst, int reset) {
+    *host_dst = *flag;
+    if (reset) *flag = 0u;
+    __threadfence_system();
+}
+
 }  // namespace gnb
 
 extern "C" {
+
+int32_t gnb_copy_to_pinned_host(const void* src, int64_t src_pitch, void* pinned_host_dst, int64_t dst_pitch,
+                                int64_t width_bytes, int64_t rows, void* stream) {
+    GNB_REQUIRE(src && pinned_host_dst, "gnb_copy_to_pinned_host: null pointer");
+    GNB_REQUIRE(width_bytes >= 0 && rows >= 0 && width_bytes <= (1 << 20) && width_bytes * rows <= (1ll << 24),
+                "gnb_copy_to_pinned_host: meant for small records (<= 16 MiB)");
+    GNB_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(pinned_host_dst) | (uintptr_t)src_pitch |
+                  (uintptr_t)dst_pitch | (uintptr_t)width_bytes) & 3) == 0,
+                "gnb_copy_to_pinned_host: pointers, pitches and width must be multiples of 4 bytes");
+    if (width_bytes == 0 || rows == 0) return GNB_OK;
+    cudaPointerAttributes attr;
+    GNB_CUDA(cudaPointerGetAttributes(&attr, pinned_host_dst));
+    GNB_REQUIRE(attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr,
+                "gnb_copy_to_pinned_host: destination is not pinned (device-addressable) host memory");
+    const int64_t words = width_bytes / 4 * rows;
+    gnb::copy_words_to_host_kernel<<<(unsigned)((words + 255) / 256), 256, 0, gnb::as_stream(stream)>>>(
+        static_cast<const uint32_t*>(src), src_pitch / 4, static_cast<uint32_t*>(attr.devicePointer), dst_pitch / 4,
+        (int)(width_bytes / 4), rows);
+    return gnb::check_launch("gnb_copy_to_pinned_host");
+}
 
 int32_t gnb_f16_range_check(const float* x, int64_t n, void* stream) {
     GNB_REQUIRE(x || n == 0, "gnb_f16_range_check: null pointer");
@@ -124,10 +166,13 @@ int32_t gnb_f16_overflow_fetch_async(uint32_t* pinned_host_out, int32_t reset, v
     GNB_REQUIRE(pinned_host_out != nullptr, "gnb_f16_overflow_fetch_async: null pointer");
     uint32_t* flag = gnb::f16_flag_ptr();
     GNB_REQUIRE(flag != nullptr, "gnb_f16_overflow_fetch_async: flag allocation failed");
-    cudaStream_t st = gnb::as_stream(stream);
-    GNB_CUDA(cudaMemcpyAsync(pinned_host_out, flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    if (reset) GNB_CUDA(cudaMemsetAsync(flag, 0, sizeof(uint32_t), st));
-    return GNB_OK;
+    // a kernel store into the (device-addressable) pinned word, not a cudaMemcpyAsync: see copy_words_to_host_kernel
+    cudaPointerAttributes attr;
+    GNB_CUDA(cudaPointerGetAttributes(&attr, pinned_host_out));
+    GNB_REQUIRE(attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr,
+                "gnb_f16_overflow_fetch_async: destination is not pinned (device-addressable) host memory");
+    gnb::f16_flag_to_host_kernel<<<1, 1, 0, gnb::as_stream(stream)>>>(flag, static_cast<uint32_t*>(attr.devicePointer), reset);
+    return gnb::check_launch("gnb_f16_overflow_fetch_async");
 }
 
 int32_t gnb_version(void) { return 100; /* 0.1.0 */ }

@@ -39,7 +39,7 @@ constexpr int W1_BYTES = N * 128;            // 32 KB
 constexpr int B_PIECE = N * KC * 2;          // 32 KB: the 256 W2 rows, one K-chunk, one precision part
 constexpr int B_SLOTS = 5;
 constexpr int THREADS = 576;                 // 4 gather + 4 mid-epilogue + 8 epilogue warps + MMA issuer + loader
-constexpr int W_MMA = 16, W_LOAD = 17;
+constexpr int W_MMA = 16;                      // warp 17 = loader
 constexpr int MAX_B = 128;
 constexpr uint32_t IDESC_N64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 constexpr uint32_t IDESC_N256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -6,7 +6,8 @@ PyTorch is plumbing here: it owns device memory and the current stream; every co
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
+import threading
+from typing import Dict, Optional, Tuple
 
 import torch
 
@@ -722,6 +723,19 @@ def f16_overflow_async(pinned: torch.Tensor, reset: bool = True) -> None:
     _lib.call("gnb_f16_overflow_fetch_async", pinned.data_ptr(), 1 if reset else 0, _stream())
 
 
+_MC_RECORDS: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _mc_record_buffer(dev: torch.device, n: int) -> torch.Tensor:
+    """Pinned [>= n, 512] byte buffer for the per-volume marching-cubes records (one per device and host thread, grown on
+    demand; the caller consumes it before it returns)."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), threading.get_ident())
+    buf = _MC_RECORDS.get(key)
+    if buf is None or buf.shape[0] < n:
+        buf = _MC_RECORDS[key] = torch.zeros((max(n, 64), 512), dtype=torch.uint8).pin_memory()
+    return buf
+
+
 def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0, 1.0), gradient_direction: str = "ascent",
                          ggm: Optional[torch.Tensor] = None, return_packed: bool = False, with_normals: bool = True,
                          lazy_views: bool = False):
@@ -752,7 +766,14 @@ def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0,
     off = int(lib.gnb_mc_totals_offset(D, H, W))
     ws = torch.empty((N, ws_bytes), dtype=torch.uint8, device=dev)
     _lib.call("gnb_mc_count_batch", volumes.data_ptr(), N, D, H, W, float(level), ws.data_ptr(), ws_bytes, _stream())
-    rec = ws[:, off:off + 512].cpu().numpy()  # the one synchronisation
+    # the one synchronisation: the N records are stored into pinned host memory by a kernel (not a cudaMemcpy, which would queue
+    # behind the previous batch's bulk result transfers on the copy engine) and the host waits on an event behind it
+    rec_host = _mc_record_buffer(dev, N)
+    _lib.call("gnb_copy_to_pinned_host", ws.data_ptr() + off, ws_bytes, rec_host.data_ptr(), 512, 512, N, _stream())
+    done = torch.cuda.Event()
+    done.record()
+    done.synchronize()
+    rec = rec_host[:N].numpy()
     totals = rec[:, :40].copy().view(np.int64)  # V, F, A, vbase, fbase
     enc = rec[:, 256:264].copy().view(np.uint32)
     dec = np.where(enc & 0x80000000, enc & 0x7FFFFFFF, ~enc).astype(np.uint32).view(np.float32)

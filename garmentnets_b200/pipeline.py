@@ -572,6 +572,8 @@ class ConvImplicitWNFPipeline(nn.Module):
         if check_range and int(flag_host[0]) != 0:   # marching_cubes_batch synchronised the stream for its totals
             raise GarmentNetsB200Error("an activation left the fp16 range of the tensor-core operand split (+-65504) or is not "
                                        "finite: the 3D-UNet / decoder outputs of this batch are not trustworthy")
+        mesh_ready = torch.cuda.Event()   # verts / faces / normals / values / ggm_at are final here: HostPredictor starts their
+        mesh_ready.record()               # device -> host transfers while the surface decoder is still running
         mark("marching_cubes")
         # warp field of every mesh vertex of the batch in one fused launch (gather + MLP on tcgen05)
         dec = self.surface_decoder
@@ -611,7 +613,8 @@ class ConvImplicitWNFPipeline(nn.Module):
             results.append(r)
         mark("surface_decode")
         self._last_point_outputs = {"pred_nocs": nocs_data.pos, "pred_confidence": nocs_data.pred_confidence}
-        self._last_packed = dict(packed, warp_field=warp_all, errors=[mc if isinstance(mc, Exception) else None for mc in mcs])
+        self._last_packed = dict(packed, warp_field=warp_all, errors=[mc if isinstance(mc, Exception) else None for mc in mcs],
+                                 mesh_ready=mesh_ready)
         return results
 
 
@@ -665,11 +668,14 @@ class HostPredictor:
         ready.record()
         host, keep, nbytes = {}, [], 0
         with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(ready)
+            # the marching-cubes outputs (76 % of the bytes) leave as soon as they are final, under the surface decoder
+            self.copy_stream.wait_event(packed.get("mesh_ready", ready))
             for out_key, pk in self.MESH_KEYS:
                 t = packed[pk]
                 if t is None:
                     continue
+                if pk == "warp_field":
+                    self.copy_stream.wait_event(ready)
                 h = self._stage(slot, out_key, t)
                 h.copy_(t, non_blocking=True)
                 t.record_stream(self.copy_stream)

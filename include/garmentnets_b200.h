@@ -450,9 +450,18 @@ int32_t gnb_pointconv_mlp_max(const float* x, int64_t ldx, int32_t Cin, const fl
  * reset != 0. */
 int32_t gnb_f16_range_check(const float* x, int64_t n, void* stream);
 int32_t gnb_f16_overflow_fetch(int32_t reset, void* stream);
-/* Stream-ordered form: copies the flag into pinned host memory (valid once `stream` has reached this point, e.g. after the
+/* Stream-ordered form: stores the flag into pinned host memory from a one-thread kernel (valid once `stream` has reached this point, e.g. after the
  * caller's next synchronisation) and clears it when reset != 0; no synchronisation of its own. */
 int32_t gnb_f16_overflow_fetch_async(uint32_t* pinned_host_out, int32_t reset, void* stream);
+
+/* Small stream-ordered device -> host transfer WITHOUT the copy engine: a kernel stores `rows` records of `width_bytes`
+ * (pitches in bytes; everything a multiple of 4) straight into pinned, device-addressable host memory.  For the few hundred
+ * bytes the host is waiting for in the middle of a batch (the marching-cubes totals, predict.py:172-177 hands the same
+ * numbers back through skimage's return values): a cudaMemcpy of that size queues behind the bulk result transfers of the
+ * previous batch on the copy engine -- milliseconds when eight ranks share one host.  Valid on the host once `stream` has
+ * reached this point.  GNB_ERR_INVALID for pageable destinations and for transfers above 16 MiB. */
+int32_t gnb_copy_to_pinned_host(const void* src, int64_t src_pitch, void* pinned_host_dst, int64_t dst_pitch,
+                                int64_t width_bytes, int64_t rows, void* stream);
 
 #pragma GCC visibility pop
 #endif
