@@ -247,3 +247,41 @@ def test_f16_range_flag(dev):
     sc[1, 5] = 1.0e6
     ops.gn_apply_split(v, sc, sh)
     assert ops.f16_overflow()
+
+
+@pytest.mark.gpu
+def test_copy_to_pinned_host_and_async_flag(dev):
+    """The small device -> host path that bypasses the copy engine (marching-cubes totals, range flag): a strided 2-D record copy
+    stored by a kernel into pinned memory equals the source after a stream synchronisation; pageable destinations, odd sizes
+    and bulk sizes are refused; the asynchronous flag fetch lands in pinned memory and resets the device flag."""
+    from garmentnets_b200 import _lib, ops
+    from garmentnets_b200._lib import GarmentNetsB200Error
+    src = torch.arange(7 * 64, dtype=torch.int32, device=dev).view(7, 64)
+    dst = torch.full((7, 16), -1, dtype=torch.int32).pin_memory()
+    st = torch.cuda.current_stream().cuda_stream
+    # columns 8..19 of every row -> columns 2..13 of the pinned rows
+    _lib.call("gnb_copy_to_pinned_host", src.data_ptr() + 8 * 4, 64 * 4, dst.data_ptr() + 2 * 4, 16 * 4, 12 * 4, 7, st)
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:, 2:14], src[:, 8:20].cpu())
+    assert (dst[:, :2] == -1).all() and (dst[:, 14:] == -1).all()
+    _lib.call("gnb_copy_to_pinned_host", src.data_ptr(), 256, dst.data_ptr(), 64, 0, 7, st)   # empty: no-op
+    pageable = torch.zeros((7, 16), dtype=torch.int32)
+    with pytest.raises(GarmentNetsB200Error):
+        _lib.call("gnb_copy_to_pinned_host", src.data_ptr(), 256, pageable.data_ptr(), 64, 48, 7, st)
+    with pytest.raises(GarmentNetsB200Error):
+        _lib.call("gnb_copy_to_pinned_host", src.data_ptr(), 256, dst.data_ptr(), 64, 46, 7, st)        # width not a multiple of 4
+    with pytest.raises(GarmentNetsB200Error):
+        _lib.call("gnb_copy_to_pinned_host", src.data_ptr(), 256, dst.data_ptr(), 64, 2 << 20, 7, st)   # not a small record
+    # the flag, stream-ordered
+    ops.f16_overflow(reset=True)
+    flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+    x = torch.full((64,), 1.0e5, device=dev)
+    ops.f16_range_check(x)
+    ops.f16_overflow_async(flag)
+    torch.cuda.synchronize()
+    assert int(flag[0]) == 1 and not ops.f16_overflow()    # fetched and reset
+    ops.f16_overflow_async(flag)
+    torch.cuda.synchronize()
+    assert int(flag[0]) == 0
+    with pytest.raises(GarmentNetsB200Error):
+        _lib.call("gnb_f16_overflow_fetch_async", torch.zeros(1, dtype=torch.int32).data_ptr(), 1, st)   # pageable
