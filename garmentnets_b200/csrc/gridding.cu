@@ -109,7 +109,7 @@ struct Corners { float lc[3], uc[3]; };
 __global__ void __launch_bounds__(256)
 aggregator_features_kernel(const float* __restrict__ feat, int64_t ldf, int Cf, const float* __restrict__ nocs,
                            const float* __restrict__ sim, const float* __restrict__ conf,
-                           const int64_t* __restrict__ batch, int64_t N, int G, Corners cr,
+                           const int64_t* __restrict__ batch, int64_t N, int G, Corners cr, int with_point, int with_conf,
                            int64_t* __restrict__ flat_idx, float* __restrict__ out, int64_t ldo) {
     const int lane = threadIdx.x & 31;
     const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -124,11 +124,15 @@ aggregator_features_kernel(const float* __restrict__ feat, int64_t ldf, int Cf, 
         const float f = __fmul_rn(__fadd_rn(p, -cr.lc[lane]), __fdiv_rn(gm1, ext));
         long long i = (long long)f;  // trunc toward zero, like Tensor.to(int64)
         i = i < 0 ? 0 : (i > G - 1 ? G - 1 : i);
-        // components/gridding.py:249-255: idx * ((uc-lc)/(shape-1)) + lc
-        const float origin = __fadd_rn(__fmul_rn((float)i, __fdiv_rn(ext, gm1)), cr.lc[lane]);
-        dst[Cf + lane] = __fsub_rn(p, origin);
-        dst[Cf + 3 + lane] = sim[n * 3 + lane];
-        dst[Cf + 6 + lane] = conf[n * 3 + lane];
+        int col = Cf;
+        if (with_point) {   // include_point_feature: offset inside the voxel + the simulation points
+            // components/gridding.py:249-255: idx * ((uc-lc)/(shape-1)) + lc
+            const float origin = __fadd_rn(__fmul_rn((float)i, __fdiv_rn(ext, gm1)), cr.lc[lane]);
+            dst[col + lane] = __fsub_rn(p, origin);
+            dst[col + 3 + lane] = sim[n * 3 + lane];
+            col += 6;
+        }
+        if (with_conf) dst[col + lane] = conf[n * 3 + lane];   // include_confidence_feature
         const long long i0 = __shfl_sync(0x7u, i, 0), i1 = __shfl_sync(0x7u, i, 1), i2 = __shfl_sync(0x7u, i, 2);
         if (lane == 0) flat_idx[n] = ((batch[n] * G + i0) * G + i1) * G + i2;
     }
@@ -253,13 +257,24 @@ int32_t gnb_scatter_reduce(const float* src, int64_t src_sc, int64_t src_sn, con
 
 int32_t gnb_aggregator_features(const float* feat, int64_t ldf, int32_t Cf, const float* nocs,
                                 const float* sim_points, const float* conf, const int64_t* batch, int64_t N,
-                                int32_t G, int64_t* flat_idx, float* out, int64_t ldo, void* stream) {
-    GNB_REQUIRE(feat && nocs && sim_points && conf && batch && flat_idx && out, "gnb_aggregator_features: null pointer");
-    GNB_REQUIRE(G >= 2 && ldo >= Cf + 9, "gnb_aggregator_features: bad G/ldo");
+                                int32_t G, const float* lower_corner, const float* upper_corner,
+                                int32_t include_point_feature, int32_t include_confidence_feature,
+                                int64_t* flat_idx, float* out, int64_t ldo, void* stream) {
+    GNB_REQUIRE(feat && nocs && batch && flat_idx && out, "gnb_aggregator_features: null pointer");
+    GNB_REQUIRE(!include_point_feature || sim_points, "gnb_aggregator_features: include_point_feature needs sim_points");
+    GNB_REQUIRE(!include_confidence_feature || conf, "gnb_aggregator_features: include_confidence_feature needs conf");
+    const int cols = Cf + (include_point_feature ? 6 : 0) + (include_confidence_feature ? 3 : 0);
+    GNB_REQUIRE(G >= 2 && ldo >= cols, "gnb_aggregator_features: bad G/ldo");
     if (N == 0) return GNB_OK;
     Corners cr = {{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
+    for (int a = 0; a < 3; ++a) {
+        if (lower_corner) cr.lc[a] = lower_corner[a];
+        if (upper_corner) cr.uc[a] = upper_corner[a];
+        GNB_REQUIRE(cr.uc[a] > cr.lc[a], "gnb_aggregator_features: upper corner must lie above the lower corner");
+    }
     aggregator_features_kernel<<<(unsigned)ceil_div<int64_t>(N, 8), 256, 0, as_stream(stream)>>>(
-        feat, ldf, Cf, nocs, sim_points, conf, batch, N, G, cr, flat_idx, out, ldo);
+        feat, ldf, Cf, nocs, sim_points, conf, batch, N, G, cr, include_point_feature ? 1 : 0,
+        include_confidence_feature ? 1 : 0, flat_idx, out, ldo);
     return check_launch("gnb_aggregator_features");
 }
 

@@ -300,17 +300,27 @@ def scatter_reduce(src: torch.Tensor, index: torch.Tensor, dim_size: int, reduce
     return phys.t() if channels_last else phys
 
 
-def aggregator_features(feat, nocs, sim_points, conf, batch, G: int):
+def aggregator_features(feat, nocs, sim_points, conf, batch, G: int, lower_corner=(0.0, 0.0, 0.0),
+                        upper_corner=(1.0, 1.0, 1.0), include_point_feature: bool = True,
+                        include_confidence_feature: bool = True):
+    """Per-point aggregator rows [feat | offset in voxel, sim_points | confidence] and flat voxel indices
+    (ref networks/conv_implicit_wnf.py:62-85); the optional blocks follow the reference's two flags."""
+    import ctypes
     feat, ldf = _rows(feat, "feat")
     nocs = _req(nocs, torch.float32, "nocs")
-    sim_points = _req(sim_points, torch.float32, "sim_points")
-    conf = _req(conf, torch.float32, "conf")
+    sim_points = _req(sim_points, torch.float32, "sim_points") if include_point_feature else None
+    conf = _req(conf, torch.float32, "conf") if include_confidence_feature else None
     batch = _req(batch, torch.int64, "batch")
     N, Cf = feat.shape
-    out = torch.empty((N, Cf + 9), dtype=torch.float32, device=feat.device)
+    cols = Cf + (6 if include_point_feature else 0) + (3 if include_confidence_feature else 0)
+    out = torch.empty((N, cols), dtype=torch.float32, device=feat.device)
     flat = torch.empty((N,), dtype=torch.int64, device=feat.device)
-    _lib.call("gnb_aggregator_features", feat.data_ptr(), ldf, Cf, nocs.data_ptr(), sim_points.data_ptr(),
-              conf.data_ptr(), batch.data_ptr(), N, int(G), flat.data_ptr(), out.data_ptr(), out.stride(0), _stream())
+    lc = (ctypes.c_float * 3)(*[float(v) for v in lower_corner])
+    uc = (ctypes.c_float * 3)(*[float(v) for v in upper_corner])
+    _lib.call("gnb_aggregator_features", feat.data_ptr(), ldf, Cf, nocs.data_ptr(), _ptr(sim_points), _ptr(conf),
+              batch.data_ptr(), N, int(G), ctypes.cast(lc, ctypes.c_void_p).value, ctypes.cast(uc, ctypes.c_void_p).value,
+              1 if include_point_feature else 0, 1 if include_confidence_feature else 0, flat.data_ptr(), out.data_ptr(),
+              out.stride(0), _stream())
     return out, flat
 
 

@@ -148,14 +148,15 @@ class VolumeFeatureAggregator(nn.Module):
         """Per-point features [nocs features | offset inside the voxel | sim points | confidence] -> MLP ->
         scatter-reduce into the voxel grid.  Returns logical [B,C,G,G,G] stored channels-last."""
         G = self.grid_shape[0]
-        unit_cube = self.lower_corner == (0, 0, 0) and self.upper_corner == (1, 1, 1)
-        if not (unit_cube and len(set(self.grid_shape)) == 1 and self.include_point_feature
-                and self.include_confidence_feature):
-            raise NotImplementedError("VolumeFeatureAggregator: only the shipped configuration (unit cube, cubic grid, "
-                                      "point + confidence features) has a fused kernel")
+        if len(set(self.grid_shape)) != 1:
+            raise NotImplementedError("VolumeFeatureAggregator: only cubic grids (every shipped config; the 3D-UNet and the "
+                                      "decoders of this package assume one)")
         B = int(nocs_data.num_graphs)
         feats, flat = ops.aggregator_features(nocs_data.x, nocs_data.pos, nocs_data.sim_points,
-                                              nocs_data.pred_confidence, nocs_data.batch, G)
+                                              nocs_data.pred_confidence, nocs_data.batch, G,
+                                              lower_corner=self.lower_corner, upper_corner=self.upper_corner,
+                                              include_point_feature=self.include_point_feature,
+                                              include_confidence_feature=self.include_confidence_feature)
         h = self.local_nn(feats)
         vol = ops.scatter_reduce(h.t(), flat, B * G ** 3, self.reduce_method, channels_last=True)  # [C, B*G^3] view
         C = h.shape[1]

@@ -159,11 +159,15 @@ int32_t gnb_scatter_reduce(const float* src, int64_t src_sc, int64_t src_sn, con
 /* Aggregator glue, ref networks/conv_implicit_wnf.py:62-85 + components/gridding.py:161-206,230-256:
  * voxel index of each point from its NOCS position (trunc((p-lc)*((G-1)/(uc-lc))), clamped), flat index
  * b*G^3 + i0*G^2 + i1*G + i2, and the per-point feature row
- * [feat(Cf) | p - voxel_origin (3) | sim_points (3) | confidence (3)] written with row stride ldo.
- * (lower corner 0, upper corner 1 as shipped: config/train_pipeline_default.yaml:43-44.) */
+ * [feat(Cf) | p - voxel_origin (3), sim_points (3) if include_point_feature | confidence (3) if
+ * include_confidence_feature] written with row stride ldo (conv_implicit_wnf.py:76-85).
+ * lower_corner / upper_corner: HOST float[3], NULL = (0,0,0) / (1,1,1) as shipped
+ * (config/train_pipeline_default.yaml:43-44).  sim_points / conf may be NULL when their flag is 0. */
 int32_t gnb_aggregator_features(const float* feat, int64_t ldf, int32_t Cf, const float* nocs,
-                                const float* sim_points, const float* conf, const int64_t* batch,
-                                int64_t N, int32_t G, int64_t* flat_idx, float* out, int64_t ldo, void* stream);
+                                const float* sim_points, const float* conf, const int64_t* batch, int64_t N,
+                                int32_t G, const float* lower_corner, const float* upper_corner,
+                                int32_t include_point_feature, int32_t include_confidence_feature,
+                                int64_t* flat_idx, float* out, int64_t ldo, void* stream);
 
 /* ---- N6-N8: 3D-UNet layers on channels-last (NDHWC) activations ---------------------------
  * ref: components/unet3d.py:43-72 ('gcr' SingleConv = GroupNorm -> Conv3d(3x3x3, pad 1, no bias) -> ReLU),

@@ -127,25 +127,38 @@ def nocs_head(logits: np.ndarray, bins: int):
     return b.numpy(), conf.numpy(), nocs.numpy()
 
 
-def points_grid_idxs(points: np.ndarray, G: int) -> np.ndarray:
-    """components/gridding.py:161-186 with lower corner 0 / upper corner 1."""
+def points_grid_idxs(points: np.ndarray, G: int, lower=(0.0, 0.0, 0.0), upper=(1.0, 1.0, 1.0)) -> np.ndarray:
+    """components/gridding.py:161-186 (lower corner 0 / upper corner 1 unless given)."""
     p = _t(points)
-    scales = (torch.tensor([G] * 3, dtype=torch.float32) - 1) / (torch.ones(3) - torch.zeros(3))
-    f = (p + (-torch.zeros(3))) * scales
+    lc, uc = torch.tensor(lower, dtype=torch.float32), torch.tensor(upper, dtype=torch.float32)
+    scales = (torch.tensor([G] * 3, dtype=torch.float32) - 1) / (uc - lc)
+    f = (p + (-lc)) * scales
     return torch.clamp(f.to(torch.int64), 0, G - 1).numpy()
 
 
-def volume_feature_aggregator(sd: SD, prefix: str, feat, nocs, sim_points, conf, batch, B: int, G: int):
-    """networks/conv_implicit_wnf.py:43-100 with include_point_feature / include_confidence_feature, reduce max.
-    Returns (volume [B,C,G,G,G], flat_idx, pre-MLP features)."""
-    idx3 = points_grid_idxs(nocs, G)
+def aggregator_rows(feat, nocs, sim_points, conf, batch, G: int, lower=(0.0, 0.0, 0.0), upper=(1.0, 1.0, 1.0),
+                    include_point_feature: bool = True, include_confidence_feature: bool = True):
+    """networks/conv_implicit_wnf.py:62-85: flat voxel index and the concatenated per-point feature rows."""
+    idx3 = points_grid_idxs(nocs, G, lower, upper)
     flat = (_t(batch).to(torch.int64) * G ** 3 + _t(idx3[:, 0]) * G ** 2 + _t(idx3[:, 1]) * G + _t(idx3[:, 2])).numpy()
-    scales = (torch.ones(3) - torch.zeros(3)) / (torch.tensor([G] * 3, dtype=torch.float32) - 1)
-    origin = _t(idx3) * scales + torch.zeros(3)
-    local_offset = _t(nocs) - origin
-    feats = torch.cat([_t(feat), local_offset, _t(sim_points), _t(conf)], dim=-1)
+    parts = [_t(feat)]
+    if include_point_feature:
+        lc, uc = torch.tensor(lower, dtype=torch.float32), torch.tensor(upper, dtype=torch.float32)
+        scales = (uc - lc) / (torch.tensor([G] * 3, dtype=torch.float32) - 1)   # components/gridding.py:249-255
+        origin = _t(idx3) * scales + lc
+        parts += [_t(nocs) - origin, _t(sim_points)]
+    if include_confidence_feature:
+        parts.append(_t(conf))
+    return flat, torch.cat(parts, dim=-1)
+
+
+def volume_feature_aggregator(sd: SD, prefix: str, feat, nocs, sim_points, conf, batch, B: int, G: int, reduce: str = "max",
+                              **flags):
+    """networks/conv_implicit_wnf.py:43-100 (shipped: include_point_feature / include_confidence_feature, reduce max).
+    Returns (volume [B,C,G,G,G], flat_idx, pre-MLP features)."""
+    flat, feats = aggregator_rows(feat, nocs, sim_points, conf, batch, G, **flags)
     h = mlp(sd, prefix + "local_nn.", feats)
-    vol_flat = P.scatter(h.numpy().T, flat, B * G ** 3, "max")
+    vol_flat = P.scatter(h.numpy().T, flat, B * G ** 3, reduce)
     C = h.shape[1]
     vol = vol_flat.reshape(C, B, G, G, G).transpose(1, 0, 2, 3, 4)
     return np.ascontiguousarray(vol), flat, feats.numpy(), h.numpy()

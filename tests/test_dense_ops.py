@@ -116,6 +116,15 @@ def test_nocs_head_and_aggregator_features(dev):
     local = torch.from_numpy(nocs_ref) - torch.from_numpy(idx3) * scales
     ref = np.concatenate([feat, local.numpy(), sim, conf.cpu().numpy()], 1)
     assert np.array_equal(out.cpu().numpy(), ref)
+    # the reference's other configurations (conv_implicit_wnf.py:27-32,76-85): flags off, a box that is not the unit cube
+    pts = (rng.random((N, 3)).astype(np.float32) * 2.4 - 1.2)   # some points outside the box: clamped indices
+    for lower, upper, ip, ic in (((0, 0, 0), (1, 1, 1), False, False), ((0, 0, 0), (1, 1, 1), True, False),
+                                 ((0, 0, 0), (1, 1, 1), False, True), ((-1.0, -0.5, -1.0), (1.0, 1.5, 0.25), True, True)):
+        flat_ref, rows_ref = ON.aggregator_rows(feat, pts, sim, conf.cpu().numpy(), batch, G, lower, upper, ip, ic)
+        out, flat = ops.aggregator_features(_t(feat, dev), _t(pts, dev), _t(sim, dev), conf, _t(batch, dev), G, lower_corner=lower,
+                                            upper_corner=upper, include_point_feature=ip, include_confidence_feature=ic)
+        assert out.shape[1] == 128 + 6 * ip + 3 * ic
+        assert np.array_equal(flat.cpu().numpy(), flat_ref) and np.array_equal(out.cpu().numpy(), rows_ref.numpy())
 
 
 @pytest.mark.gpu
