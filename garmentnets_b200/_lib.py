@@ -83,7 +83,7 @@ KERNELS_PER_CALL = {"gnb_scatter_reduce": 2, "gnb_gaussian_gradient_magnitude": 
                     "gnb_gaussian_gradient_magnitude_batched": 1, "gnb_conv3d_tc_supported": 0, "gnb_conv3d_tc_dx_supported": 0, "gnb_mc_totals_offset": 0, "gnb_decode_lattice_set_mode": 0, "gnb_decode_query_set_mode": 0, "gnb_mc_cell_tiling_host": 0,
                     "gnb_mc_count": 5, "gnb_mc_emit": 3, "gnb_mc_count_batch": 5, "gnb_mc_emit_batch": 3,
                     "gnb_groupnorm_stats": 2, "gnb_groupnorm_stats_cat": 3, "gnb_decode_tc": 2, "gnb_decode_tc_query": 2, "gnb_decode_tc_query_fused": 3, "gnb_decode_lattice": 2, "gnb_version": 0, "gnb_last_error": 0, "gnb_device_sm_count": 0,
-                    "gnb_mc_workspace_bytes": 0, "gnb_f16_overflow_fetch": 0, "gnb_f16_overflow_fetch_async": 1, "gnb_copy_to_pinned_host": 1, "gnb_pointconv_mlp_supported": 0, "gnb_pointconv_mlp_packed_bytes": 0, "gnb_pointconv_mlp_pack": 3, "gnb_pointconv_mlp_max": 3, "gnb_linear_tc_packed_bytes": 0,
+                    "gnb_mc_workspace_bytes": 0, "gnb_f16_overflow_fetch": 0, "gnb_f16_overflow_fetch_async": 1, "gnb_copy_to_pinned_host": 1, "gnb_conv_tc_set_cross_precision": 0, "gnb_conv_tc_cross_precision": 0, "gnb_pointconv_mlp_supported": 0, "gnb_pointconv_mlp_packed_bytes": 0, "gnb_pointconv_mlp_pack": 3, "gnb_pointconv_mlp_max": 3, "gnb_linear_tc_packed_bytes": 0,
                     "gnb_linear_tc_padded_cols": 0, "gnb_mesh_cleanup_workspace_bytes": 0, "gnb_mesh_cleanup_count": 8,
                     "gnb_mesh_cleanup_emit": 2, "gnb_linear_tc_segmax": 1, "gnb_mesh_components": 4,
                     "gnb_mesh_sample_barycentric": 5}

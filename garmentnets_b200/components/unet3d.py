@@ -116,7 +116,7 @@ class SingleConv(nn.Sequential):
 
     def packed_weight_tc_slices(self, width: int):
         w = self.conv.weight
-        key = (w._version, w.data_ptr(), width)
+        key = (w._version, w.data_ptr(), width, ops.conv_tc_cross_precision())
         cached = getattr(self, '_gnb_wt_tc_slices', None)
         if cached is None or cached[0] != key:
             cached = (key, [ops.conv3d_tc_pack_weights(w[o:o + width].contiguous()) for o in range(0, w.shape[0], width)])
@@ -144,7 +144,7 @@ class SingleConv(nn.Sequential):
 
     def packed_weight_tc(self, dx: bool = False) -> torch.Tensor:
         w = self.conv.weight
-        key = (w._version, w.data_ptr())
+        key = (w._version, w.data_ptr(), ops.conv_tc_cross_precision())   # the packed image depends on the cross-term format
         attr = '_gnb_wt_tc_dx' if dx else '_gnb_wt_tc'
         cached = getattr(self, attr, None)
         if cached is None or cached[0] != key:

@@ -75,6 +75,17 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// e4m3 x e4m3 -> fp32: K = 32 elements (32 bytes) per instruction, twice the MACs of kind::f16 at the same operand bytes.
+// The instruction descriptor is the f16 one (format code 0 = F16 there, = E4M3 here; fp32 accumulator).
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -94,7 +105,23 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __host__ __device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 3) ^ (r & 7)) & 7) << 4) + (c & 7) * 2);
 }
+// byte j (0..127) of row r of a K-major SWIZZLE_128B tile (8-bit operands)
+__host__ __device__ __forceinline__ uint32_t sw128_byte_offset(int r, int j) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((j >> 4) ^ (r & 7)) & 7) << 4) + (j & 15));
+}
 }  // namespace ctc
+
+// ---- cross-term precision ----------------------------------------------------------------------------------------------
+// Mode 0 (default): a*w = hi*hi + lo*hi + hi*lo, three kind::f16 MMAs per K-step.
+// Mode 1: the two cross terms as ONE kind::f8f6f4 MMA per K-step.  The "lo" activation tensor then holds, per channel pair
+// (c, c+1), the four e4m3 bytes [lo(c)*2^12, lo(c+1)*2^12, a(c), a(c+1)] and the "lo" weight image the matching
+// [w(c)*2^(s-12), w(c+1)*2^(s-12), w_lo(c)*2^s, w_lo(c+1)*2^s]: 64 channels = 128 one-byte K elements = the same 128-byte
+// rows, the same TMA boxes and shared-memory descriptors, and  sum_K' a8*w8 = 2^s (lo*w + a*w_lo).  Two tensor
+// pass-equivalents instead of three.  e4m3 keeps 4 significant bits of each cross term (relative error 2^-5 of something that is
+// 2^-11 of the product): ~2e-5 relative per layer instead of ~1e-7 (tools/fp8_cross_term_sim.py); saturation (|a| > 448, or a
+// remainder above 448 * 2^-12) degrades towards one-pass accuracy for that element instead of failing.
+constexpr float CT_LO8_SCALE = 4096.f;   // 2^12
+static int g_cross_fp8 = 0;
 
 constexpr int CT_M = 128, CT_KC = 64, CT_THREADS = 192, CT_MAX_STAGES = 4;
 constexpr int CT_NACC = 4;  // 3 rotating hi*hi accumulators + 1 for the cross terms
@@ -109,6 +136,7 @@ struct ConvTcParams {
     int nbuf;                  // 2: accumulator sets double-buffered in TMEM (4*acc_stride*2 <= 512 columns), else 1
     int acc_stride;            // TMEM columns between accumulators: Cout rounded up to a power of two (32/64/128)
     float out_scale;           // 2^-s: undoes the power-of-two scaling applied to the packed weights
+    int cross_fp8;             // cross terms as one e4m3 MMA per K-step (see g_cross_fp8)
     const uint8_t* w_packed;   // [27][nchunk][hi,lo][Cout*128 B]
     float* y;                  // [B,D,H,W,Cout] fp32
     int64_t num_tiles;
@@ -194,12 +222,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 #pragma unroll
                     for (int kk = 0; kk < CT_KC / 16; ++kk)
                         umma_f16(d_main, umma_desc(ahi + kk * 32), umma_desc(bhi + kk * 32), idesc, (ks >= 3) || kk != 0);
+                    if (p.cross_fp8) {
 #pragma unroll
-                    for (int kk = 0; kk < CT_KC / 16; ++kk)
-                        umma_f16(d_cross, umma_desc(alo + kk * 32), umma_desc(bhi + kk * 32), idesc, (ks | kk) != 0);
+                        for (int kk = 0; kk < CT_KC / 16; ++kk)   // 32 one-byte K elements per instruction: the same 32-byte steps
+                            umma_f8(d_cross, umma_desc(alo + kk * 32), umma_desc(blo + kk * 32), idesc, (ks | kk) != 0);
+                    } else {
 #pragma unroll
-                    for (int kk = 0; kk < CT_KC / 16; ++kk)
-                        umma_f16(d_cross, umma_desc(ahi + kk * 32), umma_desc(blo + kk * 32), idesc, 1);
+                        for (int kk = 0; kk < CT_KC / 16; ++kk)
+                            umma_f16(d_cross, umma_desc(alo + kk * 32), umma_desc(bhi + kk * 32), idesc, (ks | kk) != 0);
+#pragma unroll
+                        for (int kk = 0; kk < CT_KC / 16; ++kk)
+                            umma_f16(d_cross, umma_desc(ahi + kk * 32), umma_desc(blo + kk * 32), idesc, 1);
+                    }
                     umma_commit(empty(slot));
                 }
                 umma_commit(d_full(db));
@@ -281,6 +315,7 @@ struct ConvDxParams {
     int nchunk, nstages, stage_bytes, b_bytes;   // b_bytes = 2 * 3 * Cout * 128 (hi rows then lo rows of one (kd,kh,chunk) piece)
     int relu;
     float out_scale;
+    int cross_fp8;
     const uint8_t* w_packed;   // [9][nchunk][hi: 3*Cout rows, lo: 3*Cout rows][128 B]
     float* y;
     int64_t num_tiles;
@@ -361,7 +396,14 @@ conv_tc_dx_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                     tc_fence_after();
                     const uint32_t ahi = sbase + slot * p.stage_bytes, alo = ahi + CT_A_BYTES;
                     const uint32_t bw_ = ahi + 2 * CT_A_BYTES;   // rows 0..NJ-1 = hi, NJ..2NJ-1 = lo
-                    if (wide) {
+                    if (p.cross_fp8) {
+                        const uint32_t b8 = bw_ + (uint32_t)NJ * 128;   // the e4m3 image [w | w_lo] takes the place of the lo rows
+#pragma unroll
+                        for (int kk = 0; kk < CT_KC / 16; ++kk) {
+                            umma_f16(d_set, umma_desc(ahi + kk * 32), umma_desc(bw_ + kk * 32), idesc_half, (ks | kk) != 0);
+                            umma_f8(d_set + (uint32_t)NJ, umma_desc(alo + kk * 32), umma_desc(b8 + kk * 32), idesc_half, (ks | kk) != 0);
+                        }
+                    } else if (wide) {
 #pragma unroll
                         for (int kk = 0; kk < CT_KC / 16; ++kk) {
                             umma_f16(d_set, umma_desc(ahi + kk * 32), umma_desc(bw_ + kk * 32), idesc_wide, (ks | kk) != 0);
@@ -446,8 +488,22 @@ conv_tc_dx_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     }
 }
 
+// two floats -> two e4m3 bytes (first argument in the LOW byte), round to nearest, saturating at +-448
+__device__ __forceinline__ uint32_t ct_cvt_e4m3x2(float lo_elem, float hi_elem) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi_elem), "f"(lo_elem));
+    return (uint32_t)r;
+}
+// weight element of channel kc (0..63 inside its chunk) of row r in the e4m3 image: [w(c), w(c+1), w_lo(c), w_lo(c+1)] per pair
+__device__ __forceinline__ void store_weight_e4m3(uint8_t* tile, int r, int kc, float w_scaled, float w_lo) {
+    const uint32_t b = ct_cvt_e4m3x2(w_scaled * (1.0f / CT_LO8_SCALE), w_lo);   // low byte: w * 2^(s-12), high byte: w_lo * 2^s
+    const int j = (kc >> 1) * 4 + (kc & 1);
+    tile[ctc::sw128_byte_offset(r, j)] = (uint8_t)(b & 0xffu);
+    tile[ctc::sw128_byte_offset(r, j + 2)] = (uint8_t)(b >> 8);
+}
+
 // W fp32 [Cout, Cin, 3,3,3] -> [9 (kd,kh)][Cpad/64][hi rows j*Cout+n (j = kw), then lo rows][64 K] fp16 SWIZZLE_128B images
-__global__ void pack_conv_weights_dx_kernel(const float* __restrict__ W, int Cout, int Cin, int Cpad, float wscale,
+__global__ void pack_conv_weights_dx_kernel(const float* __restrict__ W, int Cout, int Cin, int Cpad, float wscale, int cross_fp8,
                                             uint8_t* __restrict__ out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)27 * Cpad * Cout;
@@ -466,7 +522,8 @@ __global__ void pack_conv_weights_dx_kernel(const float* __restrict__ W, int Cou
     const int NJ = 3 * Cout;
     uint8_t* piece = out + ((size_t)pair * nchunk + cc) * (size_t)(2 * NJ * 128);
     *reinterpret_cast<__half*>(piece + ctc::sw128_offset(j * Cout + n, kc)) = h;
-    *reinterpret_cast<__half*>(piece + ctc::sw128_offset(NJ + j * Cout + n, kc)) = l;
+    if (cross_fp8) store_weight_e4m3(piece + (size_t)NJ * 128, j * Cout + n, kc, w, w - __half2float(h));
+    else *reinterpret_cast<__half*>(piece + ctc::sw128_offset(NJ + j * Cout + n, kc)) = l;
 }
 
 // x fp32 [rows, C] (rows = B*voxels), scale/shift [B, C] -> xh, xl fp16 [rows, Cpad] (zero padded channels)
@@ -480,7 +537,7 @@ __device__ __forceinline__ uint32_t ct_cvt_f16x2_sat(float lo_elem, float hi_ele
 __global__ void __launch_bounds__(256)
 gn_apply_split_vec4_kernel(const float* __restrict__ x, int64_t rows, int64_t vox_per_sample, int C, int Cpad,
                            const float* __restrict__ scale, const float* __restrict__ shift, uint2* __restrict__ xh,
-                           uint2* __restrict__ xl, uint32_t* __restrict__ range_flag) {
+                           uint2* __restrict__ xl, uint32_t* __restrict__ range_flag, int cross_fp8) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per channel quad
     const int quads = Cpad / 4;
     if (t >= rows * quads) return;
@@ -505,8 +562,13 @@ gn_apply_split_vec4_kernel(const float* __restrict__ x, int64_t rows, int64_t vo
     h.y = ct_cvt_f16x2_sat(v.z, v.w);
     const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
     const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
-    l.x = ct_cvt_f16x2_sat(v.x - f0.x, v.y - f0.y);
-    l.y = ct_cvt_f16x2_sat(v.z - f1.x, v.w - f1.y);
+    if (cross_fp8) {   // per channel pair: [lo * 2^12, lo * 2^12, a, a] as e4m3 (see g_cross_fp8)
+        l.x = ct_cvt_e4m3x2((v.x - f0.x) * CT_LO8_SCALE, (v.y - f0.y) * CT_LO8_SCALE) | (ct_cvt_e4m3x2(v.x, v.y) << 16);
+        l.y = ct_cvt_e4m3x2((v.z - f1.x) * CT_LO8_SCALE, (v.w - f1.y) * CT_LO8_SCALE) | (ct_cvt_e4m3x2(v.z, v.w) << 16);
+    } else {
+        l.x = ct_cvt_f16x2_sat(v.x - f0.x, v.y - f0.y);
+        l.y = ct_cvt_f16x2_sat(v.z - f1.x, v.w - f1.y);
+    }
     xh[t] = h;
     xl[t] = l;
 }
@@ -517,7 +579,7 @@ gn_apply_split_vec4_kernel(const float* __restrict__ x, int64_t rows, int64_t vo
 __global__ void __launch_bounds__(256)
 gn_apply_split_cat_kernel(const float* __restrict__ skip, int Cs, const float* __restrict__ xlow, int Cx, int64_t rows, int D, int H,
                           int W, int Cpad, const float* __restrict__ scale, const float* __restrict__ shift, uint2* __restrict__ xh,
-                          uint2* __restrict__ xl, uint32_t* __restrict__ range_flag) {
+                          uint2* __restrict__ xl, uint32_t* __restrict__ range_flag, int cross_fp8) {
     // 32-bit index arithmetic (the entry point checks rows * quads < 2^32): the 64-bit divisions of the first version cost
     // more than the memory traffic
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per channel quad
@@ -549,8 +611,13 @@ gn_apply_split_cat_kernel(const float* __restrict__ skip, int Cs, const float* _
     h.y = ct_cvt_f16x2_sat(v.z, v.w);
     const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
     const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
-    l.x = ct_cvt_f16x2_sat(v.x - f0.x, v.y - f0.y);
-    l.y = ct_cvt_f16x2_sat(v.z - f1.x, v.w - f1.y);
+    if (cross_fp8) {   // per channel pair: [lo * 2^12, lo * 2^12, a, a] as e4m3 (see g_cross_fp8)
+        l.x = ct_cvt_e4m3x2((v.x - f0.x) * CT_LO8_SCALE, (v.y - f0.y) * CT_LO8_SCALE) | (ct_cvt_e4m3x2(v.x, v.y) << 16);
+        l.y = ct_cvt_e4m3x2((v.z - f1.x) * CT_LO8_SCALE, (v.w - f1.y) * CT_LO8_SCALE) | (ct_cvt_e4m3x2(v.z, v.w) << 16);
+    } else {
+        l.x = ct_cvt_f16x2_sat(v.x - f0.x, v.y - f0.y);
+        l.y = ct_cvt_f16x2_sat(v.z - f1.x, v.w - f1.y);
+    }
     xh[t] = h;
     xl[t] = l;
 }
@@ -559,7 +626,7 @@ gn_apply_split_cat_kernel(const float* __restrict__ skip, int Cs, const float* _
 __global__ void __launch_bounds__(256)
 gn_apply_split_kernel(const float* __restrict__ x, int64_t rows, int64_t vox_per_sample, int C, int Cpad,
                       const float* __restrict__ scale, const float* __restrict__ shift, __half* __restrict__ xh,
-                      __half* __restrict__ xl, uint32_t* __restrict__ range_flag) {
+                      __half* __restrict__ xl, uint32_t* __restrict__ range_flag, int cross_fp8) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per channel pair
     const int half_c = Cpad / 2;
     if (t >= rows * half_c) return;
@@ -581,13 +648,17 @@ gn_apply_split_kernel(const float* __restrict__ x, int64_t rows, int64_t vox_per
     }
     const __half2 h = __floats2half2_rn(v0, v1);
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
     *reinterpret_cast<__half2*>(xh + r * Cpad + c) = h;
-    *reinterpret_cast<__half2*>(xl + r * Cpad + c) = l;
+    if (cross_fp8) {
+        *reinterpret_cast<uint32_t*>(xl + r * Cpad + c) =
+            ct_cvt_e4m3x2((v0 - hf.x) * CT_LO8_SCALE, (v1 - hf.y) * CT_LO8_SCALE) | (ct_cvt_e4m3x2(v0, v1) << 16);
+    } else {
+        *reinterpret_cast<__half2*>(xl + r * Cpad + c) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    }
 }
 
 // W fp32 [Cout, Cin, 3,3,3] -> [27][Cpad/64][hi,lo][Cout rows x 64 K] fp16 K-major SWIZZLE_128B images
-__global__ void pack_conv_weights_kernel(const float* __restrict__ W, int Cout, int Cin, int Cpad, float wscale,
+__global__ void pack_conv_weights_kernel(const float* __restrict__ W, int Cout, int Cin, int Cpad, float wscale, int cross_fp8,
                                          uint8_t* __restrict__ out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)27 * Cpad * Cout;
@@ -606,7 +677,8 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ W, int Cout, 
     uint8_t* piece = out + ((size_t)tap * nchunk + cc) * 2 * b_bytes;
     const uint32_t off = ctc::sw128_offset(n, kc);
     *reinterpret_cast<__half*>(piece + off) = h;
-    *reinterpret_cast<__half*>(piece + b_bytes + off) = l;
+    if (cross_fp8) store_weight_e4m3(piece + b_bytes, n, kc, w, w - __half2float(h));
+    else *reinterpret_cast<__half*>(piece + b_bytes + off) = l;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -630,6 +702,14 @@ using namespace gnb;
 
 extern "C" {
 
+int32_t gnb_conv_tc_set_cross_precision(int32_t mode) {
+    GNB_REQUIRE(mode == 0 || mode == 1, "gnb_conv_tc_set_cross_precision: mode must be 0 (fp16 cross terms) or 1 (e4m3 cross terms)");
+    g_cross_fp8 = mode;
+    return GNB_OK;
+}
+
+int32_t gnb_conv_tc_cross_precision(void) { return g_cross_fp8; }
+
 int32_t gnb_conv3d_tc_pack_weights(const float* W, int32_t Cout, int32_t Cin, int32_t scale_log2, void* packed,
                                    void* stream) {
     GNB_REQUIRE(W && packed, "gnb_conv3d_tc_pack_weights: null pointer");
@@ -637,7 +717,7 @@ int32_t gnb_conv3d_tc_pack_weights(const float* W, int32_t Cout, int32_t Cin, in
     const int Cpad = ceil_div(Cin, CT_KC) * CT_KC;
     const int64_t total = (int64_t)27 * Cpad * Cout;
     pack_conv_weights_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, as_stream(stream)>>>(
-        W, Cout, Cin, Cpad, ldexpf(1.0f, scale_log2), reinterpret_cast<uint8_t*>(packed));
+        W, Cout, Cin, Cpad, ldexpf(1.0f, scale_log2), g_cross_fp8, reinterpret_cast<uint8_t*>(packed));
     return check_launch("gnb_conv3d_tc_pack_weights");
 }
 
@@ -654,11 +734,11 @@ int32_t gnb_gn_apply_split(const float* x, int32_t B, int64_t voxels, int32_t C,
                            reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0;
     if (C % 4 == 0 && aligned) {
         gn_apply_split_vec4_kernel<<<(unsigned)ceil_div<int64_t>(rows * (Cpad / 4), 256), 256, 0, as_stream(stream)>>>(
-            x, rows, voxels, C, Cpad, scale, shift, reinterpret_cast<uint2*>(xh), reinterpret_cast<uint2*>(xl), flag);
+            x, rows, voxels, C, Cpad, scale, shift, reinterpret_cast<uint2*>(xh), reinterpret_cast<uint2*>(xl), flag, g_cross_fp8);
         return check_launch("gnb_gn_apply_split");
     }
     gn_apply_split_kernel<<<(unsigned)ceil_div<int64_t>(rows * (Cpad / 2), 256), 256, 0, as_stream(stream)>>>(
-        x, rows, voxels, C, Cpad, scale, shift, reinterpret_cast<__half*>(xh), reinterpret_cast<__half*>(xl), flag);
+        x, rows, voxels, C, Cpad, scale, shift, reinterpret_cast<__half*>(xh), reinterpret_cast<__half*>(xl), flag, g_cross_fp8);
     return check_launch("gnb_gn_apply_split");
 }
 
@@ -676,7 +756,7 @@ int32_t gnb_gn_apply_split_cat(const float* skip, int32_t Cs, const float* x_low
     uint32_t* flag = f16_flag_ptr();
     GNB_REQUIRE(flag != nullptr, "gnb_gn_apply_split_cat: range flag allocation failed");
     gn_apply_split_cat_kernel<<<(unsigned)ceil_div<int64_t>(rows * (Cpad / 4), 256), 256, 0, as_stream(stream)>>>(
-        skip, Cs, x_low, Cx, rows, D, H, W, Cpad, scale, shift, reinterpret_cast<uint2*>(xh), reinterpret_cast<uint2*>(xl), flag);
+        skip, Cs, x_low, Cx, rows, D, H, W, Cpad, scale, shift, reinterpret_cast<uint2*>(xh), reinterpret_cast<uint2*>(xl), flag, g_cross_fp8);
     return check_launch("gnb_gn_apply_split_cat");
 }
 
@@ -702,6 +782,7 @@ int32_t gnb_conv3d_tc(const void* xh, const void* xl, int32_t B, int32_t D, int3
     ConvTcParams p;
     p.B = B; p.D = D; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu;
     p.out_scale = ldexpf(1.0f, -scale_log2);
+    p.cross_fp8 = g_cross_fp8;
     p.acc_stride = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
     p.nbuf = (CT_NACC * p.acc_stride * 2 <= 512) ? 2 : 1;
     p.Cpad = ceil_div(Cin, CT_KC) * CT_KC;
@@ -754,7 +835,7 @@ int32_t gnb_conv3d_tc_dx_pack_weights(const float* W, int32_t Cout, int32_t Cin,
     const int Cpad = ceil_div(Cin, CT_KC) * CT_KC;
     const int64_t total = (int64_t)27 * Cpad * Cout;
     pack_conv_weights_dx_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, as_stream(stream)>>>(
-        W, Cout, Cin, Cpad, ldexpf(1.0f, scale_log2), reinterpret_cast<uint8_t*>(packed));
+        W, Cout, Cin, Cpad, ldexpf(1.0f, scale_log2), g_cross_fp8, reinterpret_cast<uint8_t*>(packed));
     return check_launch("gnb_conv3d_tc_dx_pack_weights");
 }
 
@@ -767,6 +848,7 @@ int32_t gnb_conv3d_tc_dx(const void* xh, const void* xl, int32_t B, int32_t D, i
     ConvDxParams p;
     p.B = B; p.D = D; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu;
     p.out_scale = ldexpf(1.0f, -scale_log2);
+    p.cross_fp8 = g_cross_fp8;
     p.Cpad = ceil_div(Cin, CT_KC) * CT_KC;
     p.nchunk = p.Cpad / CT_KC;
     int rem = CT_M;

@@ -596,6 +596,23 @@ def decode_tc_query_fused(W1, b1, w2_packed, b2, bn2, W3, b3, bn3, *, X, q, qptr
 
 
 # ---------------------------------------------------------------------------------------------- tensor-core 3x3x3 conv
+_CROSS_PRECISION = [None]   # mirror of the library's process-wide mode (avoids a ctypes call per layer)
+
+
+def conv_tc_cross_precision() -> int:
+    """0: fp16 cross terms (three tensor passes), 1: e4m3 cross terms (two pass-equivalents); see
+    ``gnb_conv_tc_set_cross_precision`` in the header."""
+    if _CROSS_PRECISION[0] is None:
+        _CROSS_PRECISION[0] = int(_lib.load().gnb_conv_tc_cross_precision())
+    return _CROSS_PRECISION[0]
+
+
+def conv_tc_set_cross_precision(mode: int) -> None:
+    """Process-wide; packed weights are re-packed on their next use (the module caches are keyed on the mode)."""
+    _lib.call("gnb_conv_tc_set_cross_precision", int(mode))
+    _CROSS_PRECISION[0] = int(mode)
+
+
 def conv3d_tc_supported(B, D, H, W, Cin, Cout) -> bool:
     return bool(_lib.call("gnb_conv3d_tc_supported", int(B), int(D), int(H), int(W), int(Cin), int(Cout)))
 

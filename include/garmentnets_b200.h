@@ -183,6 +183,15 @@ int32_t gnb_groupnorm_stats(const float* x, int32_t B, int64_t voxels, int32_t C
 int32_t gnb_conv3d_k3(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cin,
                       const float* scale, const float* shift, const float* Wt, int32_t Cout,
                       int32_t relu, float* y, void* stream);
+/* Precision of the two cross terms (lo*hi + hi*lo) of the tensor-core 3x3x3 convolutions, process-wide:
+ *   0 (default)  two fp16 MMAs per K-step (three tensor passes in total, ~1e-7 relative per layer);
+ *   1            ONE e4m3 MMA per K-step over [lo*2^12 | a] x [w*2^(s-12) | w_lo*2^s] (two pass-equivalents, ~2e-5 relative
+ *                per layer).
+ * The mode is read by gnb_conv3d_tc*_pack_weights, gnb_gn_apply_split* (they emit the operands in the mode's format) and
+ * gnb_conv3d_tc / gnb_conv3d_tc_dx: set it BEFORE packing weights and do not change it between a split and its convolution. */
+int32_t gnb_conv_tc_set_cross_precision(int32_t mode);
+int32_t gnb_conv_tc_cross_precision(void);
+
 /* Tensor-core (TMA + tcgen05) version of gnb_conv3d_k3 for power-of-two grids with at least 128 voxels in the batch and
  * Cout in {32,64,96,128} (gnb_conv3d_tc_supported).  Three launches per 'gcr' SingleConv:
  *   gnb_groupnorm_stats -> gnb_gn_apply_split (x*scale+shift written once as fp16 hi + lo, channels zero-padded to a

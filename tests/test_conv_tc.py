@@ -82,3 +82,40 @@ def test_unet_tc_equals_fp32_path(dev):
     print(f"UNet max-abs error vs float64: tensor-core {err_tc:.2e}, fp32 FFMA {err_32:.2e}, torch CPU fp32 {err_cpu:.2e}")
     assert err_tc < TOL * scale and err_32 < TOL * scale
     assert np.abs(y_tc.cpu().numpy() - ref).max() < TOL * scale  # and against the fp32 oracle itself
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,G,Cin,Cout,dx", [(1, 8, 64, 64, False), (2, 4, 128, 128, False), (1, 16, 96, 32, True), (2, 16, 192, 64, True)])
+def test_conv_tc_e4m3_cross_terms(dev, B, G, Cin, Cout, dx):
+    """Opt-in mode 1 of gnb_conv_tc_set_cross_precision: hi*hi in fp16 plus ONE e4m3 MMA per K-step for lo*w + a*w_lo.
+    Two tensor pass-equivalents instead of three; the cross terms keep 4 significant bits, so a layer is good to ~1e-5
+    relative rms (1e-4 max) instead of ~1e-6 -- measured 4.4e-4 over the 14 layers of the UNet, which is why the default stays
+    mode 0.  The mode must not leak: mode 0 results are bit-identical before and after."""
+    from garmentnets_b200 import ops
+    g = torch.Generator().manual_seed(Cin * 7 + Cout)
+    x = torch.randn(B, Cin, G, G, G, generator=g) * 1.5 + 0.3
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5
+    ref = F.relu(F.conv3d(x.double(), w.double(), None, padding=1)).permute(0, 2, 3, 4, 1)
+
+    def run():
+        xh, xl = ops.gn_apply_split(ops.to_channels_last(x.to(dev)), None, None)
+        if dx:
+            return ops.conv3d_tc_dx(xh, xl, Cin, ops.conv3d_tc_dx_pack_weights(w.to(dev)), Cout, relu=True)
+        return ops.conv3d_tc(xh, xl, Cin, ops.conv3d_tc_pack_weights(w.to(dev)), Cout, relu=True)
+
+    assert ops.conv_tc_cross_precision() == 0
+    y0 = run()
+    try:
+        ops.conv_tc_set_cross_precision(1)
+        assert ops.conv_tc_cross_precision() == 1
+        y1 = run()
+    finally:
+        ops.conv_tc_set_cross_precision(0)
+    e0 = (y0.cpu().double() - ref).abs()
+    e1 = (y1.cpu().double() - ref).abs()
+    assert e0.max().item() < 2e-5
+    assert e1.max().item() < 2e-4 and e1.pow(2).mean().sqrt().item() < 3e-5, (e1.max().item(), e1.pow(2).mean().sqrt().item())
+    assert not torch.equal(y0, y1)          # the mode really changed the arithmetic
+    assert torch.equal(run(), y0)           # and mode 0 is back, bit for bit
+    with pytest.raises(Exception):
+        ops.conv_tc_set_cross_precision(2)
