@@ -113,7 +113,7 @@ def test_conv_tc_e4m3_cross_terms(dev, B, G, Cin, Cout, dx):
         ops.conv_tc_set_cross_precision(0)
     e0 = (y0.cpu().double() - ref).abs()
     e1 = (y1.cpu().double() - ref).abs()
-    assert e0.max().item() < 2e-5
+    assert e0.max().item() < 3e-5
     assert e1.max().item() < 2e-4 and e1.pow(2).mean().sqrt().item() < 3e-5, (e1.max().item(), e1.pow(2).mean().sqrt().item())
     assert not torch.equal(y0, y1)          # the mode really changed the arithmetic
     assert torch.equal(run(), y0)           # and mode 0 is back, bit for bit
