@@ -58,6 +58,7 @@ struct LtParams {
     int64_t ldo;
     int use_const;             // cparams fit in c_lt (n_blocks * Npad <= LT_MAX_COLS)
     int split;                 // Npad <= 128: the lo*hi + hi*lo cross terms accumulate in their own TMEM columns (+Npad)
+    uint32_t* range_flag;      // nullable: raised when an OUTPUT value is outside +-65504 or not finite (gnb_linear_tc_flagged)
 };
 
 __global__ void __launch_bounds__(LT_THREADS, 1)
@@ -160,6 +161,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
         const uint32_t stage = b_ring + p.nb * p.piece_bytes + (uint32_t)(warp - 8) * LT_STAGE_BYTES;
         const uint32_t sdst = stage + (uint32_t)lane * 128;
         int it = 0;
+        bool bad = false;   // an output outside the fp16 range of the consumer's operand split (or NaN), see range_flag
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int db = it & 1;
             const int nb = (int)(tile % p.n_blocks);
@@ -226,6 +228,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
                         if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                         o.x = fmaf(o.x, sc.x, sh.x); o.y = fmaf(o.y, sc.y, sh.y);
                         o.z = fmaf(o.z, sc.z, sh.z); o.w = fmaf(o.w, sc.w, sh.w);
+                        bad |= !(fabsf(o.x) <= 65504.f) | !(fabsf(o.y) <= 65504.f) | !(fabsf(o.z) <= 65504.f) | !(fabsf(o.w) <= 65504.f);
                         const int n = n0 + t;
                         if (tma_tile || seg_mode) {
                             // SWIZZLE_128B box: 16-byte chunk j of row r lives at chunk j ^ (r & 7) (bank-conflict free)
@@ -279,6 +282,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap y_map, const LtParams p) {
             mbar_arrive(d_empty(db));  // accumulator buffer drained: the MMAs of tile it+2 may overwrite it
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (bad && p.range_flag != nullptr) *p.range_flag = 1u;
     } else if (warp == 16) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
@@ -460,7 +464,7 @@ int32_t gnb_linear_tc_pack(const float* W, int32_t N, int32_t K, const float* bi
 
 static int32_t linear_tc_launch(const float* X, int64_t R, int32_t K, int64_t ldx, const void* packed, const float* cparams,
                                 int32_t scale_log2, int32_t N, int32_t relu, float* Y, int64_t ldy, const int64_t* rows_dev,
-                                const int32_t* seg, uint32_t* seg_out, int64_t ldo, void* stream) {
+                                const int32_t* seg, uint32_t* seg_out, int64_t ldo, void* stream, uint32_t* range_flag = nullptr) {
     GNB_REQUIRE(X && packed && cparams && (Y || seg), "gnb_linear_tc: null pointer");
     GNB_REQUIRE(R >= 0 && K >= 1 && N >= 1 && ldx >= K && (seg || ldy >= N), "gnb_linear_tc: bad shape R=%lld K=%d N=%d ldx=%lld ldy=%lld",
                 (long long)R, K, N, (long long)ldx, (long long)ldy);
@@ -472,6 +476,7 @@ static int32_t linear_tc_launch(const float* X, int64_t R, int32_t K, int64_t ld
     p.acc_scale = ldexpf(1.0f, -scale_log2);
     p.Y = Y; p.ldy = ldy; p.rows_dev = rows_dev;
     p.seg = seg; p.seg_out = seg_out; p.ldo = ldo;
+    p.range_flag = range_flag;
     p.piece_bytes = l.piece_bytes;
     p.m_tiles = ceil_div<int64_t>(R, LT_M);
     // separate cross-term accumulator whenever TMEM has room -- also for short contractions: measured on the PointNet++
@@ -527,6 +532,15 @@ int32_t gnb_linear_tc(const float* X, int64_t R, int32_t K, int64_t ldx, const v
                       void* stream) {
     GNB_REQUIRE(Y, "gnb_linear_tc: null pointer");
     return linear_tc_launch(X, R, K, ldx, packed, cparams, scale_log2, N, relu, Y, ldy, rows_dev, nullptr, nullptr, 0, stream);
+}
+
+int32_t gnb_linear_tc_flagged(const float* X, int64_t R, int32_t K, int64_t ldx, const void* packed, const float* cparams,
+                              int32_t scale_log2, int32_t N, int32_t relu, float* Y, int64_t ldy, const int64_t* rows_dev,
+                              void* stream) {
+    GNB_REQUIRE(Y, "gnb_linear_tc_flagged: null pointer");
+    uint32_t* flag = f16_flag_ptr();
+    GNB_REQUIRE(flag != nullptr, "gnb_linear_tc_flagged: range flag allocation failed");
+    return linear_tc_launch(X, R, K, ldx, packed, cparams, scale_log2, N, relu, Y, ldy, rows_dev, nullptr, nullptr, 0, stream, flag);
 }
 
 int32_t gnb_linear_tc_segmax(const float* X, int64_t R, int32_t K, int64_t ldx, const void* packed, const float* cparams,

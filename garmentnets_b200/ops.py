@@ -223,16 +223,17 @@ def padded_rows(R: int, N: int, device) -> torch.Tensor:
 
 
 def linear_tc(x: torch.Tensor, w: PackedLinear, relu: bool = False, out: Optional[torch.Tensor] = None,
-              rows_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Tensor-core Linear block (``gnb_linear_tc``): x [R,K] (any row stride) -> [R,N]."""
+              rows_dev: Optional[torch.Tensor] = None, flag_range: bool = False) -> torch.Tensor:
+    """Tensor-core Linear block (``gnb_linear_tc``): x [R,K] (any row stride) -> [R,N].  ``flag_range``: the epilogue also
+    raises the fp16 range flag for outputs outside +-65504 (``gnb_linear_tc_flagged``)."""
     x, ldx = _rows(x, "x")
     R, K = x.shape
     assert K == w.K, f"packed weight K={w.K} vs input K={K}"
     if out is None:
         out = padded_rows(R, w.N, x.device)
     assert out.stride(1) == 1 or w.N == 1
-    _lib.call("gnb_linear_tc", x.data_ptr(), R, K, ldx, w.packed.data_ptr(), w.cparams.data_ptr(), w.scale_log2, w.N,
-              int(relu), out.data_ptr(), out.stride(0), _ptr(rows_dev), _stream())
+    _lib.call("gnb_linear_tc_flagged" if flag_range else "gnb_linear_tc", x.data_ptr(), R, K, ldx, w.packed.data_ptr(),
+              w.cparams.data_ptr(), w.scale_log2, w.N, int(relu), out.data_ptr(), out.stride(0), _ptr(rows_dev), _stream())
     return out
 
 
@@ -259,11 +260,17 @@ def linear_tc_segmax(x: torch.Tensor, w: PackedLinear, seg: torch.Tensor, nseg: 
     return out.view(torch.float32)
 
 
-def linear_module(owner, slot: str, x: torch.Tensor, weight, bias=None, relu: bool = False) -> torch.Tensor:
-    """A plain ``nn.Linear`` (optionally + ReLU) applied to rows: tensor cores for large row counts, fp32 kernel below."""
+def linear_module(owner, slot: str, x: torch.Tensor, weight, bias=None, relu: bool = False,
+                  flag_range: bool = False) -> torch.Tensor:
+    """A plain ``nn.Linear`` (optionally + ReLU) applied to rows: tensor cores for large row counts, fp32 kernel below.
+    ``flag_range``: outputs outside the fp16 range raise the range flag (in the epilogue on the tensor-core path, with a
+    separate pass over the result otherwise)."""
     if USE_LINEAR_TC and x.shape[0] >= LINEAR_TC_MIN_ROWS:
-        return linear_tc(x, packed_linear_for(owner, slot, weight, bias), relu)
-    return linear(x, weight, bias, relu)
+        return linear_tc(x, packed_linear_for(owner, slot, weight, bias), relu, flag_range=flag_range)
+    y = linear(x, weight, bias, relu)
+    if flag_range:
+        f16_range_check(y)
+    return y
 
 
 def nocs_head(logits: torch.Tensor, bins: int):

@@ -203,14 +203,14 @@ class ImplicitWNFDecoder(nn.Module):
             self._gnb_folded = cached
         return cached[1], cached[2]
 
-    def hoisted_folded(self, x_ndhwc: torch.Tensor, final_conv: nn.Conv3d) -> torch.Tensor:
+    def hoisted_folded(self, x_ndhwc: torch.Tensor, final_conv: nn.Conv3d, flag_range: bool = False) -> torch.Tensor:
         """``hoisted(final_conv(x))`` as ONE affine map: grid @ (W1 Wf)^T + (W1 bf + b1).  ``x`` is the last UNet
         decoder's output [B,D,H,W,Cf] (Cf = 32): the 128-channel feature volume is never materialised and the
         per-voxel contraction runs over 32 instead of 128 channels (ref components/unet3d.py:467 followed by
         networks/conv_implicit_wnf.py:148, first Linear of the MLP)."""
         w, b = self.folded_first_linear(final_conv)
         B, D, H, W, C = x_ndhwc.shape
-        u = ops.linear_module(self, "hoisted_folded", x_ndhwc.reshape(-1, C), w, b)
+        u = ops.linear_module(self, "hoisted_folded", x_ndhwc.reshape(-1, C), w, b, flag_range=flag_range)
         return u.view(B, D, H, W, -1)
 
     def forward_fused_ragged(self, x_ndhwc: torch.Tensor, final_conv: nn.Conv3d, q_all: torch.Tensor, qptr_host):
@@ -476,9 +476,10 @@ class ConvImplicitWNFPipeline(nn.Module):
         unet = self.unet_3d.abstract_3d_unet
         x_last = unet.forward_ndhwc(ops.to_channels_last(vol_in), apply_final=False)
         mark("unet3d")
-        u_grid = self.volume_decoder.hoisted_folded(x_last, unet.final_conv)
-        if check_range:   # operands of the decoders' fp16 split: the grids they interpolate (a blend never exceeds its corners)
-            ops.f16_range_check(u_grid)
+        # operands of the decoders' fp16 split are the grids they interpolate (a blend never exceeds its corners): the 1 GB hoisted
+        # grid is checked by the epilogue of the kernel that writes it, the 134 MB UNet output by a pass of its own
+        u_grid = self.volume_decoder.hoisted_folded(x_last, unet.final_conv, flag_range=check_range)
+        if check_range:
             ops.f16_range_check(x_last)
         wnf = self.dense_decode(None, volume_size, hoisted=u_grid)
         mark("dense_decode")

@@ -126,6 +126,13 @@ int32_t gnb_linear_tc(const float* X, int64_t R, int32_t K, int64_t ldx, const v
                       const float* cparams, int32_t scale_log2, int32_t N, int32_t relu,
                       float* Y, int64_t ldy, const int64_t* rows_dev, void* stream);
 
+/* gnb_linear_tc that also raises the per-device fp16 range flag (gnb_f16_overflow_fetch) when an OUTPUT value lies outside
+ * +-65504 or is not finite: for outputs that feed a saturating fp16 operand split (the hoisted first decoder layer, whose
+ * 1 GB result the pipeline would otherwise have to read once more with gnb_f16_range_check). */
+int32_t gnb_linear_tc_flagged(const float* X, int64_t R, int32_t K, int64_t ldx, const void* packed,
+                      const float* cparams, int32_t scale_log2, int32_t N, int32_t relu,
+                      float* Y, int64_t ldy, const int64_t* rows_dev, void* stream);
+
 /* PointConv aggregation fused into the last edge-MLP layer (ref components/pointnet2.py:31, PyG PointConv aggr='max'):
  * the rows of one segment (centroid) are contiguous; seg i32[R] holds the segment id of every row
  * (gnb_segment_ids fills it from the CSR offsets).  Instead of writing Y, every 128-row tile is reduced on chip and

@@ -256,6 +256,19 @@ def test_f16_range_flag(dev):
     sc[1, 5] = 1.0e6
     ops.gn_apply_split(v, sc, sh)
     assert ops.f16_overflow()
+    # a Linear whose OUTPUT feeds a split (the hoisted first decoder layer): checked by the epilogue that writes it, on the
+    # tensor-core path (full TMA tiles and the ragged last tile) and on the fp32 path
+    g = torch.Generator().manual_seed(0)
+    w, b = (torch.randn(256, 32, generator=g) * 0.2).to(dev), torch.randn(256, generator=g).to(dev)
+    for rows in (5000, 300):
+        x = torch.randn(rows, 32, generator=g).to(dev)
+        y = ops.linear_module(torch.nn.Module(), "t", x, w, b, flag_range=True)
+        assert not ops.f16_overflow() and torch.allclose(y, x @ w.t() + b, atol=1e-4)
+        x[rows - 3, 7] = 3.0e6        # one output row far outside the fp16 range (last, partial tile)
+        ops.linear_module(torch.nn.Module(), "t", x, w, b, flag_range=True)
+        assert ops.f16_overflow()
+        ops.linear_module(torch.nn.Module(), "t", x, w, b)     # unflagged entry point: no check
+        assert not ops.f16_overflow()
 
 
 @pytest.mark.gpu
