@@ -244,8 +244,22 @@ class GlobalSAModule(nn.Module):
 
     def forward(self, x, pos, batch, *, index: Optional[CloudIndex] = None):
         index = index or CloudIndex.from_batch(batch)
-        h = self.nn(torch.cat([x, pos], dim=1))
-        out = ops.segment_max(h, index.ptr)
+        h = torch.cat([x, pos], dim=1)
+        blocks = list(self.nn) if isinstance(self.nn, nn.Sequential) else None
+        last = blocks[-1] if blocks else None
+        rows = h.shape[0]
+        fuse = (blocks is not None and ops.USE_LINEAR_TC and rows >= ops.LINEAR_TC_MIN_ROWS and not _Block.calibrating
+                and isinstance(last, _Block) and not last.training)
+        if fuse:
+            # global max pooling fused into the last layer's epilogue (as in PointConv): its [rows, C] output never reaches HBM
+            # and the pooling does not run as 32 CTAs of its own
+            for block in blocks[:-1]:
+                h = block(h)
+            lin = last[0]
+            w = ops.packed_linear_for(last, "block", lin.weight, lin.bias, last[2] if len(last) > 2 else None)
+            out = ops.linear_tc_segmax(h, w, ops.segment_ids(index.ptr, rows), index.num_graphs, relu=True)
+        else:
+            out = ops.segment_max(self.nn(h), index.ptr)
         B = out.shape[0]
         return out, pos.new_zeros((B, 3)), torch.arange(B, device=pos.device)
 

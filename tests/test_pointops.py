@@ -158,13 +158,20 @@ def test_knn_fewer_points_than_k(dev):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [0, 1, 1000, 1024, 70000])
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 1000, 1024, 16384, 16385, 65536, 70000])
 def test_exclusive_scan(dev, n):
+    """Pass boundaries of the 16-elements-per-thread scan (16384 per pass), ragged tails, an input that does not start on a
+    16-byte boundary (scalar loads), and sums beyond 32 bits."""
     from garmentnets_b200 import ops
     v = torch.randint(0, 66, (n,), dtype=torch.int32, device=dev)
     out = ops.exclusive_scan(v).cpu().numpy()
     ref = np.concatenate([[0], np.cumsum(v.cpu().numpy().astype(np.int64))])
     assert np.array_equal(out, ref)
+    if n > 1:
+        w = torch.randint(0, 66, (n + 1,), dtype=torch.int32, device=dev)[1:]      # 4-byte aligned view
+        assert np.array_equal(ops.exclusive_scan(w).cpu().numpy(), np.concatenate([[0], np.cumsum(w.cpu().numpy().astype(np.int64))]))
+        big = torch.full((n,), 2 ** 31 - 1, dtype=torch.int32, device=dev)
+        assert int(ops.exclusive_scan(big)[-1]) == n * (2 ** 31 - 1)
 
 
 @pytest.mark.gpu
