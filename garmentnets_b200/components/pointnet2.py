@@ -289,7 +289,9 @@ class FPModule(nn.Module):
         index_skip = index_skip or CloudIndex.from_batch(batch_skip)
         c = x.shape[1]
         cs = 0 if x_skip is None else x_skip.shape[1]
-        buf = torch.empty((pos_skip.shape[0], c + cs), dtype=torch.float32, device=x.device)
+        # row stride padded to a multiple of 4 floats: the interpolation kernel then takes its 16-byte path (FP1 concatenates
+        # 128 + 3 channels) and the Linear block reads rows at any stride
+        buf = ops.padded_rows(pos_skip.shape[0], c + cs, x.device)
         knn_interpolate(x, pos, pos_skip, k=self.k, index_x=index, index_y=index_skip, out=buf)
         if x_skip is not None:
             buf[:, c:] = x_skip

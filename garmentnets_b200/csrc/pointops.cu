@@ -335,25 +335,62 @@ knn_kernel(const float* __restrict__ x, const float* __restrict__ y, const int64
     }
 }
 
-// inverse-distance interpolation, one warp per output row, channels across lanes.
+// inverse-distance interpolation, one warp per output row, channels across lanes.  The k neighbour indices and weights are
+// computed once per row (not once per 32 channels: the division dominated the first version); VEC: four channels per lane
+// with 16-byte loads and stores.  Same operation order per channel as the oracle: sum_p(f_p * w_p) / sum_p(w_p), p ascending.
+template <int KT, bool VEC>
 __global__ void __launch_bounds__(256)
 knn_interp_kernel(const float* __restrict__ feat, int64_t ldf, const int64_t* __restrict__ idx,
                   const float* __restrict__ d2, int64_t Ny, int k, int C, float* __restrict__ out, int64_t ldo) {
     const int lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= Ny) return;
-    for (int c = lane; c < C; c += 32) {
-        float num = 0.f, den = 0.f;
-        bool first = true;
-        for (int p = 0; p < k; ++p) {
-            const int64_t j = idx[q * k + p];
-            if (j < 0) continue;
-            const float w = __fdiv_rn(1.0f, fmaxf(d2[q * k + p], 1e-16f));
-            const float t = __fmul_rn(feat[j * ldf + c], w);
-            if (first) { num = t; den = w; first = false; }
-            else { num = __fadd_rn(num, t); den = __fadd_rn(den, w); }
+    int64_t jj[KT];
+    float ww[KT];
+    float den = 0.f;
+    bool first = true;
+#pragma unroll
+    for (int p = 0; p < KT; ++p) {
+        jj[p] = -1;
+        ww[p] = 0.f;
+        if (p < k) {
+            jj[p] = idx[q * k + p];
+            if (jj[p] >= 0) {
+                ww[p] = __fdiv_rn(1.0f, fmaxf(d2[q * k + p], 1e-16f));
+                den = first ? ww[p] : __fadd_rn(den, ww[p]);
+                first = false;
+            }
         }
-        out[q * ldo + c] = first ? 0.f : __fdiv_rn(num, den);
+    }
+    if (VEC) {
+        for (int c = lane * 4; c < C; c += 128) {
+            float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool f0 = true;
+#pragma unroll
+            for (int p = 0; p < KT; ++p) {
+                if (jj[p] < 0) continue;
+                const float4 f = __ldg(reinterpret_cast<const float4*>(feat + jj[p] * ldf + c));
+                const float4 t = make_float4(__fmul_rn(f.x, ww[p]), __fmul_rn(f.y, ww[p]), __fmul_rn(f.z, ww[p]), __fmul_rn(f.w, ww[p]));
+                if (f0) { num = t; f0 = false; }
+                else { num.x = __fadd_rn(num.x, t.x); num.y = __fadd_rn(num.y, t.y); num.z = __fadd_rn(num.z, t.z); num.w = __fadd_rn(num.w, t.w); }
+            }
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!first) o = make_float4(__fdiv_rn(num.x, den), __fdiv_rn(num.y, den), __fdiv_rn(num.z, den), __fdiv_rn(num.w, den));
+            *reinterpret_cast<float4*>(out + q * ldo + c) = o;
+        }
+    } else {
+        for (int c = lane; c < C; c += 32) {
+            float num = 0.f;
+            bool f0 = true;
+#pragma unroll
+            for (int p = 0; p < KT; ++p) {
+                if (jj[p] < 0) continue;
+                const float t = __fmul_rn(feat[jj[p] * ldf + c], ww[p]);
+                num = f0 ? t : __fadd_rn(num, t);
+                f0 = false;
+            }
+            out[q * ldo + c] = first ? 0.f : __fdiv_rn(num, den);
+        }
     }
 }
 
@@ -560,8 +597,21 @@ int32_t gnb_knn_interpolate(const float* feat, int64_t ldf, const int64_t* idx, 
                             int32_t k, int32_t C, float* out, int64_t ldo, void* stream) {
     GNB_REQUIRE(feat && idx && d2 && out, "gnb_knn_interpolate: null pointer");
     if (Ny == 0 || C == 0) return GNB_OK;
-    knn_interp_kernel<<<(unsigned)ceil_div<int64_t>(Ny, 8), 256, 0, as_stream(stream)>>>(feat, ldf, idx, d2, Ny, k, C,
-                                                                                      out, ldo);
+    GNB_REQUIRE(k >= 1 && k <= 16, "gnb_knn_interpolate: k=%d outside [1,16]", k);
+    const unsigned grid = (unsigned)ceil_div<int64_t>(Ny, 8);
+    cudaStream_t st = as_stream(stream);
+    const bool vec = C % 4 == 0 && ldf % 4 == 0 && ldo % 4 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+#define GNB_INTERP(KT_)                                                                                                  \
+    do {                                                                                                                 \
+        if (vec) knn_interp_kernel<KT_, true><<<grid, 256, 0, st>>>(feat, ldf, idx, d2, Ny, k, C, out, ldo);              \
+        else knn_interp_kernel<KT_, false><<<grid, 256, 0, st>>>(feat, ldf, idx, d2, Ny, k, C, out, ldo);                 \
+    } while (0)
+    if (k == 1) GNB_INTERP(1);
+    else if (k <= 3) GNB_INTERP(3);
+    else if (k <= 8) GNB_INTERP(8);
+    else GNB_INTERP(16);
+#undef GNB_INTERP
     return check_launch("gnb_knn_interpolate");
 }
 

@@ -121,7 +121,7 @@ def test_ball_query_bit_exact(dev, B, n, r, ragged):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k", [1, 3, 5])
+@pytest.mark.parametrize("k", [1, 3, 5, 12])
 def test_knn_interpolate(dev, k):
     from garmentnets_b200 import ops
     d = _cloud_batch(2, 1024, seed=3)
@@ -140,6 +140,14 @@ def test_knn_interpolate(dev, k):
     ref = P.knn_interpolate(feat, idx_ref, d2_ref)
     assert np.array_equal(out[:, :37].cpu().numpy(), ref)  # same op order, no FMA -> bit-exact
     assert torch.all(out[:, 37:] == 0)
+    # 16-byte channel path (C, both row strides multiples of 4): 256 channels written into a wider concat buffer, and 130
+    # channels (two passes of 128 per warp, the second one partial)
+    for C in (256, 132):
+        featv = np.random.default_rng(2).normal(size=(len(src), C)).astype(np.float32)
+        outv = torch.full((len(d["pos"]), C + 8), -7.0, device=dev)
+        ops.knn_interpolate_into(t(featv), idx, d2, outv)
+        assert np.array_equal(outv[:, :C].cpu().numpy(), P.knn_interpolate(featv, idx_ref, d2_ref))
+        assert torch.all(outv[:, C:] == -7.0)
 
 
 @pytest.mark.gpu
