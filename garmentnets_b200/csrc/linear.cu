@@ -151,6 +151,42 @@ linear_smalln_kernel(const float* __restrict__ X, int64_t R, int K, int64_t ldx,
     }
 }
 
+// A handful of rows (the global head of PointNet++: 32 rows x K = 1024): the tiled kernel above would run as N/64 CTAs that
+// each walk K sequentially (65 us for 2 MB of weights).  One CTA per output column instead: every warp takes rows
+// warp, warp + 8, ... and reduces its 32 partial dot products with shuffles (weights of the column stay in L1).
+__global__ void __launch_bounds__(256)
+linear_smallr_kernel(const float* __restrict__ X, int64_t R, int K, int64_t ldx, const float* __restrict__ Wt,
+                     const float* __restrict__ bias, int N, int relu, const float* __restrict__ bn_scale,
+                     const float* __restrict__ bn_shift, float* __restrict__ Y, int64_t ldy,
+                     const int64_t* __restrict__ rows_dev) {
+    int64_t rows = R;
+    if (rows_dev != nullptr) { const int64_t rd = *rows_dev; rows = rd < rows ? rd : rows; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.x;
+    const float* __restrict__ w = Wt + (int64_t)n * K;
+    for (int64_t r = warp; r < rows; r += 8) {
+        const float* __restrict__ x = X + r * ldx;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int k = lane;
+        for (; k + 96 < K; k += 128) {
+            a0 = fmaf(x[k], __ldg(w + k), a0);
+            a1 = fmaf(x[k + 32], __ldg(w + k + 32), a1);
+            a2 = fmaf(x[k + 64], __ldg(w + k + 64), a2);
+            a3 = fmaf(x[k + 96], __ldg(w + k + 96), a3);
+        }
+        for (; k < K; k += 32) a0 = fmaf(x[k], __ldg(w + k), a0);
+        float v = (a0 + a1) + (a2 + a3);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+            v += bias ? bias[n] : 0.f;
+            if (relu) v = fmaxf(v, 0.f);
+            if (bn_scale) v = fmaf(v, bn_scale[n], bn_shift[n]);
+            Y[r * ldy + n] = v;
+        }
+    }
+}
+
 }  // namespace gnb
 
 using namespace gnb;
@@ -168,6 +204,10 @@ extern "C" int32_t gnb_linear(const float* X, int64_t R, int32_t K, int64_t ldx,
         linear_smalln_kernel<<<(unsigned)ceil_div<int64_t>(R, 8), 256, 0, st>>>(X, R, K, ldx, W, bias, N, relu, bn_scale,
                                                                              bn_shift, Y, ldy, rows_dev);
         return check_launch("gnb_linear(small N)");
+    }
+    if (R <= 64) {
+        linear_smallr_kernel<<<(unsigned)N, 256, 0, st>>>(X, R, K, ldx, W, bias, N, relu, bn_scale, bn_shift, Y, ldy, rows_dev);
+        return check_launch("gnb_linear(few rows)");
     }
     const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
     const unsigned gx = (unsigned)ceil_div<int64_t>(R, LBM);
