@@ -147,29 +147,42 @@ nocs_head_kernel(const float* __restrict__ logits, int64_t R, int bins, int64_t*
     if (r >= R) return;
     const float* row = logits + r * (int64_t)bins * 3;
     const float inv = __fdiv_rn(1.0f, (float)(bins - 1));
+    // the three axes run side by side (three independent load / arg-max / exp-sum chains per lane instead of three serial
+    // passes over the row); per axis the operation order is unchanged
+    float best[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int bi[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+    for (int k = lane; k < bins; k += 32) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        float best = -INFINITY;
-        int bi = 0x7fffffff;
-        for (int k = lane; k < bins; k += 32) {
+        for (int a = 0; a < 3; ++a) {
             const float v = row[k * 3 + a];
-            if (v > best) { best = v; bi = k; }
+            if (v > best[a]) { best[a] = v; bi[a] = k; }
         }
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        float s = 0.f;
-        for (int k = lane; k < bins; k += 32) s += expf(row[k * 3 + a] - best);
+    for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) {
-            bin[r * 3 + a] = bi;
-            conf[r * 3 + a] = __fdiv_rn(1.0f, s);
-            nocs[r * 3 + a] = __fmul_rn((float)bi, inv);
+        for (int a = 0; a < 3; ++a) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best[a], o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi[a], o);
+            if (ov > best[a] || (ov == best[a] && oi < bi[a])) { best[a] = ov; bi[a] = oi; }
         }
+    }
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int k = lane; k < bins; k += 32) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) s[a] += expf(row[k * 3 + a] - best[a]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) s[a] += __shfl_xor_sync(0xffffffffu, s[a], o);
+    }
+    if (lane < 3) {   // every lane holds all three results: lane a writes axis a
+        const int b_ = lane == 0 ? bi[0] : (lane == 1 ? bi[1] : bi[2]);
+        const float s_ = lane == 0 ? s[0] : (lane == 1 ? s[1] : s[2]);
+        bin[r * 3 + lane] = b_;
+        conf[r * 3 + lane] = __fdiv_rn(1.0f, s_);
+        nocs[r * 3 + lane] = __fmul_rn((float)b_, inv);
     }
 }
 
