@@ -490,6 +490,7 @@ static int32_t launch(const Params& p, cudaStream_t st) {
     const int smem = Smem::total + 1024;
     GNB_CUDA(cudaFuncSetAttribute(decode_query_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = sm_count();
+    if (grid > 256) grid = 256;   // the caller's scratch holds 256 per-CTA rows of partial dot products (epi_scratch)
     if ((int64_t)grid > p.num_tiles) grid = (int)p.num_tiles;
     decode_query_kernel<COUT><<<grid, THREADS, smem, st>>>(p);
     return check_launch("gnb_decode_tc_query_fused");
@@ -503,8 +504,8 @@ extern "C" __attribute__((visibility("default"))) int32_t gnb_prof_decode_query_
 }
 #endif
 
-// Called by gnb_decode_tc_query_fused (decode_tc.cu) when BatchNorm1 is folded into W2.  scratch: 16384 floats =
-// [w3s 768 | tail 12 ... | @1024: inv_s1 | @2048: W1 image (32 KB)].
+// Called by gnb_decode_tc_query_fused (decode_tc.cu) when BatchNorm1 is folded into W2.  scratch: 16384 + 256 * 512 floats =
+// [w3s 768 | tail 12 ... | @1024: inv_s1 | @2048: W1 image (32 KB) | @16384: 256 x (128 rows x 4) partial dot products].
 int32_t launch_decode_query(const float* X, int B, int G, const float* W1, const float* b1, const float* q, const int64_t* qptr,
                             int64_t R, const void* w2_packed, int w2_scale_log2, const float* b2, const float* w3s,
                             const float* tail, int Cout, float* scratch, float* out, cudaStream_t st) {
