@@ -14,6 +14,6 @@ echo "racecheck exit $?" >> $OUT/racecheck.log
 tail -8 $OUT/racecheck.log
 # the tensor-core kernels (tcgen05 / TMA / mbarrier pipelines): memcheck only, smallest decoder + linear tests
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 \
-    python -m pytest tests/test_linear_tc.py tests/test_conv_tc.py -m gpu -x -q > $OUT/memcheck_tc.log 2>&1
+    python -m pytest tests/test_linear_tc.py tests/test_conv_tc.py tests/test_decode_tc.py -m gpu -x -q -k "not 128 and not lattice" > $OUT/memcheck_tc.log 2>&1
 echo "memcheck_tc exit $?" >> $OUT/memcheck_tc.log
 tail -8 $OUT/memcheck_tc.log
