@@ -391,11 +391,10 @@ class ConvImplicitWNFPipeline(nn.Module):
         self.mc_surface_decoder = None
         if mc_surface_loss_weight > 0:
             self.mc_surface_decoder = ImplicitWNFDecoder(**mc_surface_decoder_params)
-        self.volume_task_space = volume_task_space
-        if volume_task_space:
-            # ref conv_implicit_wnf.py:279-295,320-322 (apply_volume_task_space: the volume decoder is queried in task space
-            # through the predicted warp field).  Off in every shipped config; not built here, so refuse instead of ignoring it.
-            raise NotImplementedError("volume_task_space=True (conv_implicit_wnf.py:279-295) is not implemented in garmentnets_b200")
+        # ref conv_implicit_wnf.py:204,315-322: ``forward`` grids the per-point features at the normalised SIMULATION coordinates
+        # instead of the predicted NOCS coordinates (apply_volume_task_space below).  ``predict`` follows predict.py:141-142,
+        # which calls the stage forwards directly and never applies it.
+        self.volume_task_space = bool(volume_task_space)
         self.batch_size = batch_size
         self.volume_decoder.profile_tag = "decode"
         self.surface_decoder.profile_tag = "surface"
@@ -428,8 +427,34 @@ class ConvImplicitWNFPipeline(nn.Module):
     def surface_decoder_forward(self, unet3d_result, query_points):
         return {"out_features": self.surface_decoder(unet3d_result["out_feature_volume"], query_points)}
 
+    @staticmethod
+    def get_aabb_scale_offset(aabb: torch.Tensor, padding: float = 0.05):
+        """ref conv_implicit_wnf.py:297-310.  aabb [B,2,3] (lower / upper corner of the cloth in simulation space, gripper at the
+        x-y origin) -> the isotropic scale that fits |x|, |y| into a NOCS radius of 0.5 - padding and the height into
+        2 * (0.5 - padding), and the offset that centres x / y at 0.5 and puts the top of the box at 1 - padding."""
+        nocs_radius = 0.5 - padding
+        radius = aabb.abs().max(dim=1)[0][:, :2]
+        radius_scale = (nocs_radius / radius).min(dim=1)[0]
+        z_scale = (nocs_radius * 2) / (aabb[:, 1, 2] - aabb[:, 0, 2])
+        scale = torch.minimum(radius_scale, z_scale)
+        offset = torch.full((aabb.shape[0], 3), 0.5, dtype=aabb.dtype, device=aabb.device)
+        offset[:, 2] = 1 - padding - aabb[:, 1, 2] * scale
+        return scale, offset
+
+    def apply_volume_task_space(self, data, pointnet2_result):
+        """ref conv_implicit_wnf.py:279-295: a copy of the stage-1 result whose ``nocs_data.pos`` is the input cloud mapped into
+        the unit cube by the first sample's box (the reference: "assume the same scaling for now")."""
+        scale, offset = self.get_aabb_scale_offset(data.cloth_sim_aabb)
+        nd = pointnet2_result["nocs_data"]
+        new_nd = Batch(x=nd.x, pos=data.pos * scale[0] + offset[0], batch=nd.batch, sim_points=nd.sim_points,
+                       pred_confidence=nd.pred_confidence)
+        new_nd.num_graphs = nd.num_graphs
+        return dict(pointnet2_result, nocs_data=new_nd)
+
     def forward(self, data):
         p = self.pointnet2_forward(data)
+        if self.volume_task_space:
+            p = self.apply_volume_task_space(data, p)
         u = self.unet3d_forward(p)
         return {"pointnet2_result": p, "unet3d_result": u,
                 "volume_decoder_result": self.volume_decoder_forward(u, data.volume_query_points),

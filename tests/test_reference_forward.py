@@ -173,6 +173,39 @@ def test_reference_full_forward_on_gpu(setup):
     assert dv < TOL * max(1.0, ref_v.abs().max().item()) and ds < TOL * max(1.0, ref_s.abs().max().item()), (dv, ds)
 
 
+def test_reference_forward_volume_task_space(setup, ref_networks):
+    """ref networks/conv_implicit_wnf.py:279-310,320-322: with ``volume_task_space`` the aggregator grids the per-point features at
+    the AABB-normalised simulation coordinates.  Our ``get_aabb_scale_offset`` / ``apply_volume_task_space`` against the
+    reference's own methods (bit-equal: a handful of elementwise operations) and the two full forwards against each other."""
+    from garmentnets_b200.pipeline import Batch
+    s = setup
+    dev = s["dev"]
+    g = torch.Generator().manual_seed(9)
+    lo = -(torch.rand(s["B"], 3, generator=g) * 0.6 + 0.2)
+    hi = torch.rand(s["B"], 3, generator=g) * 0.6 + 0.2
+    aabb = torch.stack([lo, hi], dim=1).to(dev)                      # [B, 2, 3]
+    sc_r, of_r = ref_networks.ConvImplicitWNFPipeline.get_aabb_scale_offset(aabb)
+    sc_o, of_o = s["model"].get_aabb_scale_offset(aabb)
+    assert torch.equal(sc_r, sc_o) and torch.equal(of_r, of_o)
+    data = Batch(x=s["data"].x, pos=s["data"].pos, batch=s["data"].batch, volume_query_points=s["vq"].to(dev),
+                 surf_query_points=s["sq"].to(dev), cloth_sim_aabb=aabb)
+    plain = s["model"].forward(data)
+    try:
+        s["ref"].volume_task_space = True
+        s["model"].volume_task_space = True
+        res = s["ref"](data)
+        ours = s["model"].forward(data)
+    finally:
+        s["ref"].volume_task_space = False
+        s["model"].volume_task_space = False
+    assert torch.equal(res["pointnet2_result"]["nocs_data"].pos, ours["pointnet2_result"]["nocs_data"].pos)
+    assert close(ours["unet3d_result"]["out_feature_volume"].cpu().numpy(), res["unet3d_result"]["out_feature_volume"].cpu().numpy())
+    for k in ("volume_decoder_result", "surface_decoder_result"):
+        assert (res[k]["out_features"] - ours[k]["out_features"]).abs().max().item() < TOL, k
+    # and the flag really changes the volume
+    assert (plain["unet3d_result"]["out_feature_volume"] - ours["unet3d_result"]["out_feature_volume"]).abs().max().item() > 1e-3
+
+
 def _load_ref_pointnet2():
     from garmentnets_b200 import shims
     shims.install()
