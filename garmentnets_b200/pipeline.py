@@ -427,6 +427,10 @@ class ConvImplicitWNFPipeline(nn.Module):
     def surface_decoder_forward(self, unet3d_result, query_points):
         return {"out_features": self.surface_decoder(unet3d_result["out_feature_volume"], query_points)}
 
+    def mc_surface_decoder_forward(self, unet3d_result, query_points):
+        """ref conv_implicit_wnf.py:270-276 (the optional third decoder, present when ``mc_surface_loss_weight > 0``)."""
+        return {"out_features": self.mc_surface_decoder(unet3d_result["out_feature_volume"], query_points)}
+
     @staticmethod
     def get_aabb_scale_offset(aabb: torch.Tensor, padding: float = 0.05):
         """ref conv_implicit_wnf.py:297-310.  aabb [B,2,3] (lower / upper corner of the cloth in simulation space, gripper at the
@@ -456,9 +460,12 @@ class ConvImplicitWNFPipeline(nn.Module):
         if self.volume_task_space:
             p = self.apply_volume_task_space(data, p)
         u = self.unet3d_forward(p)
-        return {"pointnet2_result": p, "unet3d_result": u,
-                "volume_decoder_result": self.volume_decoder_forward(u, data.volume_query_points),
-                "surface_decoder_result": self.surface_decoder_forward(u, data.surf_query_points)}
+        result = {"pointnet2_result": p, "unet3d_result": u,
+                  "volume_decoder_result": self.volume_decoder_forward(u, data.volume_query_points),
+                  "surface_decoder_result": self.surface_decoder_forward(u, data.surf_query_points)}
+        if self.mc_surface_decoder is not None:   # ref conv_implicit_wnf.py:334-337
+            result["mc_surface_decoder_result"] = self.mc_surface_decoder_forward(u, data.mc_surf_query_points)
+        return result
 
     # ---- fast tier: the whole predict loop on the device ------------------------------------------------------
     @torch.no_grad()

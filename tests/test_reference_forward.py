@@ -206,6 +206,39 @@ def test_reference_forward_volume_task_space(setup, ref_networks):
     assert (plain["unet3d_result"]["out_feature_volume"] - ours["unet3d_result"]["out_feature_volume"]).abs().max().item() > 1e-3
 
 
+def test_reference_forward_mc_surface_decoder(setup, ref_networks):
+    """ref networks/conv_implicit_wnf.py:195-199,270-276,334-337: with ``mc_surface_loss_weight > 0`` the class owns a third implicit
+    decoder and ``forward`` returns ``mc_surface_decoder_result``.  Same constructor call for the reference class and ours, strict
+    ``state_dict`` load, outputs of the extra decoder against each other."""
+    from garmentnets_b200.pipeline import Batch, ConvImplicitWNFPipeline
+    s = setup
+    dev, hp = s["dev"], s["hp"]
+    kw = dict(pointnet2_params=hp["pointnet2"], volume_agg_params=hp["volume_agg"], unet3d_params=hp["unet3d"],
+              volume_decoder_params=hp["volume_decoder"], surface_decoder_params=hp["surface_decoder"],
+              mc_surface_decoder_params=hp["surface_decoder"], mc_surface_loss_weight=1.0)
+    ours = ConvImplicitWNFPipeline(**kw)
+    sd = dict(s["model"].state_dict())
+    for k, v in list(sd.items()):                                   # the third decoder: a perturbed copy of the surface decoder
+        if k.startswith("surface_decoder."):
+            sd["mc_" + k] = v.clone() * 1.03 if v.dtype.is_floating_point else v.clone()
+    ours.load_state_dict(sd, strict=True)
+    ours = ours.to(dev).eval().requires_grad_(False)
+    ours.pointnet2_nocs.set_random_start(False)
+    ref = ref_networks.ConvImplicitWNFPipeline(**kw)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    ref = ref.to(dev).eval().requires_grad_(False)
+    for m in (ref.pointnet2_nocs.sa1_module, ref.pointnet2_nocs.sa2_module):
+        m.random_start = False
+    data = Batch(x=s["data"].x, pos=s["data"].pos, batch=s["data"].batch, volume_query_points=s["vq"].to(dev),
+                 surf_query_points=s["sq"].to(dev), mc_surf_query_points=s["sq"].to(dev).flip(1))
+    a, b = ref(data), ours.forward(data)
+    assert set(a.keys()) == set(b.keys()) and "mc_surface_decoder_result" in b
+    for k in ("volume_decoder_result", "surface_decoder_result", "mc_surface_decoder_result"):
+        ra, rb = a[k]["out_features"], b[k]["out_features"]
+        assert (ra - rb).abs().max().item() < TOL * max(1.0, ra.abs().max().item()), k
+    assert (b["mc_surface_decoder_result"]["out_features"] - b["surface_decoder_result"]["out_features"].flip(1)).abs().max().item() > 1e-3
+
+
 def _load_ref_pointnet2():
     from garmentnets_b200 import shims
     shims.install()
