@@ -806,11 +806,14 @@ def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0,
     _lib.call("gnb_copy_to_pinned_host", ws.data_ptr() + off, ws_bytes, rec_host.data_ptr(), 512, 512, N, _stream())
     done = torch.cuda.Event()
     done.record()
-    done.synchronize()
+    # everything that does not need the totals happens before the wait: the device is idle from here until the emission launch
+    sp = (ctypes.c_double * 3)(*[float(x) for x in spacing])
+    sp_ptr = ctypes.cast(sp, ctypes.c_void_p).value
+    ascent = 1 if gradient_direction == "ascent" else 0
+    stream = _stream()
     rec = rec_host[:N].numpy()
+    done.synchronize()
     totals = rec[:, :40].copy().view(np.int64)  # V, F, A, vbase, fbase
-    enc = rec[:, 256:264].copy().view(np.uint32)
-    dec = np.where(enc & 0x80000000, enc & 0x7FFFFFFF, ~enc).astype(np.uint32).view(np.float32)
     sumV, sumF = int(totals[:, 0].sum()), int(totals[:, 1].sum())
     verts = torch.empty((sumV, 3), dtype=torch.float32, device=dev)
     faces = torch.empty((sumF, 3), dtype=torch.int32, device=dev)
@@ -818,10 +821,12 @@ def marching_cubes_batch(volumes: torch.Tensor, level: float, spacing=(1.0, 1.0,
     values = torch.empty((sumV,), dtype=torch.float32, device=dev) if with_normals else None
     ggm_at = torch.empty((sumV,), dtype=torch.float32, device=dev) if ggm is not None else None
     if sumV > 0:
-        sp = (ctypes.c_double * 3)(*[float(x) for x in spacing])
-        _lib.call("gnb_mc_emit_batch", volumes.data_ptr(), N, D, H, W, float(level), ctypes.cast(sp, ctypes.c_void_p).value,
-                  1 if gradient_direction == "ascent" else 0, _ptr(ggm), ws.data_ptr(), ws_bytes, int(totals[:, 2].max()),
-                  int(totals[:, 0].max()), verts.data_ptr(), faces.data_ptr(), _ptr(normals), _ptr(values), _ptr(ggm_at), _stream())
+        _lib.call("gnb_mc_emit_batch", volumes.data_ptr(), N, D, H, W, float(level), sp_ptr, ascent, _ptr(ggm), ws.data_ptr(),
+                  ws_bytes, int(totals[:, 2].max()), int(totals[:, 0].max()), verts.data_ptr(), faces.data_ptr(), _ptr(normals),
+                  _ptr(values), _ptr(ggm_at), stream)
+    # (the value range of every volume, for skimage's ValueError: decoded while the emission kernels run)
+    enc = rec[:, 256:264].copy().view(np.uint32)
+    dec = np.where(enc & 0x80000000, enc & 0x7FFFFFFF, ~enc).astype(np.uint32).view(np.float32)
     out = []
     for i in range(N):
         V, Fc, _, vb, fb = (int(t) for t in totals[i])
